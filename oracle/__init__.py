@@ -1,0 +1,366 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` legs may import
+this package.  The product package ``noether_b200`` never does.  See ``oracle/oracle.h`` for what each entry point
+restates (reference file:line).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+MOMENTS_F32_SEQUENTIAL = 0
+MOMENTS_F64 = 1
+SLICE_FAITHFUL = 0
+SLICE_INTENT = 1
+SCAN_ALL_CELLS = 0
+SCAN_BINNED = 1
+
+OK = 0
+ERR_INVALID = 1
+ERR_TOO_MANY_CONNECTING = 2
+ERR_NOT_A_DAG = 3
+ERR_TOPO_SORT = 4
+ERR_JOIN = 5
+ERR_NON_MANIFOLD = 6
+ERR_CLOSED_LOOP = 7
+ERR_TOO_FEW_POINTS = 8
+ERR_SEGMENT_TOO_SHORT = 9
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"oracle error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so with the committed Makefile (gcc only, no reference sources involved)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h")) or f == "Makefile"]
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class PcaResult(C.Structure):
+    _fields_ = [("mean", C.c_float * 3), ("evecs", C.c_float * 9), ("evals", C.c_float * 3),
+                ("scales", C.c_float * 3), ("cov", C.c_float * 9)]
+
+
+class Lattice(C.Structure):
+    _fields_ = [("cut_direction", C.c_double * 3), ("cut_normal", C.c_double * 3), ("cut_origin", C.c_double * 3),
+                ("start_loc", C.c_double * 3), ("line_spacing", C.c_double), ("d_min", C.c_double),
+                ("d_max", C.c_double), ("num_planes", C.c_uint64), ("no_cuts", C.c_int32), ("pad_", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(_LIB_PATH)
+    f32p = C.POINTER(C.c_float)
+    f64p = C.POINTER(C.c_double)
+    u32p = C.POINTER(C.c_uint32)
+    u64p = C.POINTER(C.c_uint64)
+    i64p = C.POINTER(C.c_int64)
+    L.orc_last_error.restype = C.c_char_p
+    L.orc_pca.argtypes = [f32p, C.c_uint64, C.c_int, C.POINTER(PcaResult)]
+    L.orc_centroid.argtypes = [f32p, C.c_uint64, C.c_int, f64p]
+    L.orc_principal_axis_direction.argtypes = [C.POINTER(PcaResult), C.c_double, f64p]
+    L.orc_eigen_solver_3f.argtypes = [f32p, f32p, f32p]
+    L.orc_make_lattice.argtypes = [C.POINTER(PcaResult), f64p, f64p, C.c_double, C.c_int, C.POINTER(Lattice)]
+    L.orc_normals_from_mesh_faces.argtypes = [f32p, C.c_uint64, u32p, C.c_uint64, f32p]
+    L.orc_slice.argtypes = [f32p, f32p, C.c_uint64, u32p, C.c_uint64, C.POINTER(Lattice), C.c_int, C.c_int,
+                            C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.orc_paths_create.restype = C.c_void_p
+    L.orc_paths_free.argtypes = [C.c_void_p]
+    L.orc_paths_clone.argtypes = [C.c_void_p]
+    L.orc_paths_clone.restype = C.c_void_p
+    L.orc_paths_add_path.argtypes = [C.c_void_p]
+    L.orc_paths_add_segment.argtypes = [C.c_void_p]
+    L.orc_paths_add_waypoint.argtypes = [C.c_void_p, f64p]
+    for n in ("orc_paths_num_paths", "orc_paths_num_segments", "orc_paths_num_waypoints"):
+        getattr(L, n).argtypes = [C.c_void_p]
+        getattr(L, n).restype = C.c_uint64
+    L.orc_paths_export.argtypes = [C.c_void_p, u64p, u64p, i64p, f32p, f32p, u32p, u32p, f64p]
+    L.orc_paths_export.restype = None
+    for n in ("orc_raster_organization", "orc_direction_of_travel"):
+        getattr(L, n).argtypes = [C.c_void_p]
+    for n in ("orc_join_close_segments", "orc_minimum_segment_length", "orc_uniform_spacing"):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_double]
+    L.orc_fixture_random_transform.argtypes = [C.c_double, C.c_double, f64p]
+    L.orc_fixture_random_transform.restype = None
+    L.orc_fixture_plane_mesh.argtypes = [C.c_float, C.c_float, f64p, f32p, f32p, u32p]
+    L.orc_fixture_plane_mesh.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise OracleError(rc, lib().orc_last_error().decode())
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _u32(a):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+@dataclass
+class Pca:
+    mean: np.ndarray      # (3,) float32
+    evecs: np.ndarray     # (3,3) float32, evecs[:, i] = i-th axis (descending eigenvalue)
+    evals: np.ndarray     # (3,) float32 descending
+    scales: np.ndarray    # (3,) float32
+    cov: np.ndarray       # (3,3) float32
+    raw: PcaResult
+
+
+def pca(xyz, mode=MOMENTS_F32_SEQUENTIAL) -> Pca:
+    a, p = _f32(xyz)
+    r = PcaResult()
+    _check(lib().orc_pca(p, a.shape[0], mode, C.byref(r)))
+    return Pca(mean=np.array(r.mean, dtype=np.float32),
+               evecs=np.array(r.evecs, dtype=np.float32).reshape(3, 3).T.copy(),
+               evals=np.array(r.evals, dtype=np.float32), scales=np.array(r.scales, dtype=np.float32),
+               cov=np.array(r.cov, dtype=np.float32).reshape(3, 3).T.copy(), raw=r)
+
+
+def pca_from_parts(mean, evecs, scales) -> Pca:
+    """Build a Pca from externally computed mean / eigenvectors (columns) / scales (e.g. the GPU's)."""
+    r = PcaResult()
+    ev = np.asarray(evecs, dtype=np.float32)
+    for i in range(3):
+        r.mean[i] = float(mean[i])
+        r.scales[i] = float(scales[i])
+        for row in range(3):
+            r.evecs[i * 3 + row] = float(ev[row, i])
+    return Pca(mean=np.asarray(mean, np.float32), evecs=ev, evals=np.zeros(3, np.float32),
+               scales=np.asarray(scales, np.float32), cov=np.zeros((3, 3), np.float32), raw=r)
+
+
+def centroid(xyz, mode=MOMENTS_F32_SEQUENTIAL) -> np.ndarray:
+    a, p = _f32(xyz)
+    out = np.zeros(3)
+    _check(lib().orc_centroid(p, a.shape[0], mode, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def principal_axis_direction(p: Pca, rotation_offset: float = 0.0) -> np.ndarray:
+    out = np.zeros(3)
+    _check(lib().orc_principal_axis_direction(C.byref(p.raw), rotation_offset,
+                                              out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def eigen_solver_3f(cov) -> tuple[np.ndarray, np.ndarray]:
+    c = np.ascontiguousarray(np.asarray(cov, dtype=np.float32).T)  # column-major
+    evals = np.zeros(3, np.float32)
+    evecs = np.zeros(9, np.float32)
+    fp = C.POINTER(C.c_float)
+    lib().orc_eigen_solver_3f(c.ctypes.data_as(fp), evals.ctypes.data_as(fp), evecs.ctypes.data_as(fp))
+    return evals, evecs.reshape(3, 3).T.copy()
+
+
+def make_lattice(p: Pca, cut_direction, cut_origin, line_spacing: float, bidirectional: bool = True) -> Lattice:
+    _, d = _f64(cut_direction)
+    _, o = _f64(cut_origin)
+    L = Lattice()
+    _check(lib().orc_make_lattice(C.byref(p.raw), d, o, line_spacing, int(bidirectional), C.byref(L)))
+    return L
+
+
+def normals_from_mesh_faces(xyz, tri) -> np.ndarray:
+    a, ap = _f32(xyz)
+    t, tp = _u32(tri)
+    out = np.zeros((a.shape[0], 3), np.float32)
+    _check(lib().orc_normals_from_mesh_faces(ap, a.shape[0], tp, t.shape[0], out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
+@dataclass
+class FlatPaths:
+    """noether::ToolPaths flattened: paths -> segments -> waypoints."""
+    path_off: np.ndarray   # (P+1,) uint64 into segments
+    seg_off: np.ndarray    # (S+1,) uint64 into waypoints
+    path_plane: np.ndarray  # (P,) int64 lattice index
+    pos: np.ndarray        # (W,3) float32
+    nrm: np.ndarray        # (W,3) float32 (interpolated, not normalised)
+    edge_lo: np.ndarray    # (W,) uint32
+    edge_hi: np.ndarray    # (W,) uint32
+    pose: np.ndarray       # (W,4,4) float64 (row, col)
+
+    @property
+    def num_paths(self):
+        return len(self.path_off) - 1
+
+    def segments_per_path(self):
+        return np.diff(self.path_off).astype(np.int64)
+
+
+class Paths:
+    """Owning handle on an orc_paths (noether::ToolPaths + provenance)."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().orc_paths_free(self._h)
+        except Exception:
+            pass
+
+    @classmethod
+    def from_nested(cls, nested):
+        """nested: list of paths, each a list of segments, each an array (n,4,4) of poses."""
+        L = lib()
+        h = cls(L.orc_paths_create())
+        for path in nested:
+            L.orc_paths_add_path(h._h)
+            for seg in path:
+                L.orc_paths_add_segment(h._h)
+                for T in seg:
+                    m = np.ascontiguousarray(np.asarray(T, dtype=np.float64).T)  # column-major
+                    L.orc_paths_add_waypoint(h._h, m.ctypes.data_as(C.POINTER(C.c_double)))
+        return h
+
+    def clone(self):
+        return Paths(lib().orc_paths_clone(self._h))
+
+    def flat(self) -> FlatPaths:
+        L = lib()
+        P = L.orc_paths_num_paths(self._h)
+        S = L.orc_paths_num_segments(self._h)
+        W = L.orc_paths_num_waypoints(self._h)
+        path_off = np.zeros(P + 1, np.uint64)
+        seg_off = np.zeros(S + 1, np.uint64)
+        plane = np.zeros(P, np.int64)
+        pos = np.zeros((W, 3), np.float32)
+        nrm = np.zeros((W, 3), np.float32)
+        lo = np.zeros(W, np.uint32)
+        hi = np.zeros(W, np.uint32)
+        pose = np.zeros((W, 16), np.float64)
+        L.orc_paths_export(self._h, path_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                           seg_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                           plane.ctypes.data_as(C.POINTER(C.c_int64)),
+                           pos.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
+                           lo.ctypes.data_as(C.POINTER(C.c_uint32)), hi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                           pose.ctypes.data_as(C.POINTER(C.c_double)))
+        pose = pose.reshape(W, 4, 4).transpose(0, 2, 1).copy()
+        return FlatPaths(path_off, seg_off, plane, pos, nrm, lo, hi, pose)
+
+    def nested_poses(self):
+        f = self.flat()
+        out = []
+        for p in range(f.num_paths):
+            path = []
+            for s in range(int(f.path_off[p]), int(f.path_off[p + 1])):
+                path.append(f.pose[int(f.seg_off[s]):int(f.seg_off[s + 1])])
+            out.append(path)
+        return out
+
+    # RasterPlanner::plan post-ops and the legacy modifiers, in place
+    def raster_organization(self):
+        _check(lib().orc_raster_organization(self._h))
+        return self
+
+    def direction_of_travel(self):
+        _check(lib().orc_direction_of_travel(self._h))
+        return self
+
+    def join_close_segments(self, distance):
+        _check(lib().orc_join_close_segments(self._h, distance))
+        return self
+
+    def minimum_segment_length(self, min_length):
+        _check(lib().orc_minimum_segment_length(self._h, min_length))
+        return self
+
+    def uniform_spacing(self, point_spacing):
+        _check(lib().orc_uniform_spacing(self._h, point_spacing))
+        return self
+
+
+def slice_mesh(xyz, normals, tri, lattice: Lattice, slice_mode=SLICE_FAITHFUL, scan_mode=SCAN_ALL_CELLS,
+               plane_begin=0, plane_end=None) -> Paths:
+    """PlaneSlicerRasterPlanner::planImpl's plane loop (plane_slicer_raster_planner.cpp:596-628)."""
+    a, ap = _f32(xyz)
+    n, npn = _f32(normals)
+    t, tp = _u32(tri)
+    if plane_end is None:
+        plane_end = lattice.num_planes
+    out = C.c_void_p()
+    _check(lib().orc_slice(ap, npn, a.shape[0], tp, t.shape[0], C.byref(lattice), slice_mode, scan_mode,
+                           plane_begin, plane_end, C.byref(out)))
+    return Paths(out.value)
+
+
+def plan_plane_slicer(xyz, normals, tri, line_spacing, bidirectional=True, direction=None, origin=None,
+                      rotation_offset=0.0, moments_mode=MOMENTS_F32_SEQUENTIAL, slice_mode=SLICE_FAITHFUL,
+                      scan_mode=SCAN_ALL_CELLS, post_ops=True):
+    """RasterPlanner::plan for PlaneSlicerRasterPlanner (raster_planner.cpp:16-35).
+
+    direction=None -> PrincipalAxisDirectionGenerator(rotation_offset); origin=None -> CentroidOriginGenerator.
+    Returns (Paths, Lattice, Pca).
+    """
+    p = pca(xyz, moments_mode)
+    d = principal_axis_direction(p, rotation_offset) if direction is None else np.asarray(direction, np.float64)
+    o = centroid(xyz, moments_mode) if origin is None else np.asarray(origin, np.float64)
+    lat = make_lattice(p, d, o, line_spacing, bidirectional)
+    paths = slice_mesh(xyz, normals, tri, lat, slice_mode, scan_mode)
+    if post_ops and paths.flat().num_paths > 0:
+        paths.raster_organization().direction_of_travel()
+    return paths, lat, p
+
+
+def plan_plane_slicer_legacy(xyz, normals, tri, line_spacing, point_spacing, min_segment_size, min_hole_size,
+                             bidirectional=True, direction=None, origin=None, **kw):
+    """PlaneSlicerLegacyRasterPlanner (plane_slicer_legacy_raster_planner.cpp:22-33) through RasterPlanner::plan."""
+    paths, lat, p = plan_plane_slicer(xyz, normals, tri, line_spacing, bidirectional, direction, origin,
+                                      post_ops=False, **kw)
+    paths.join_close_segments(min_hole_size).minimum_segment_length(min_segment_size).uniform_spacing(point_spacing)
+    if paths.flat().num_paths > 0:
+        paths.raster_organization().direction_of_travel()
+    return paths, lat, p
+
+
+def fixture_random_transform(translation_limit, rotation_limit) -> np.ndarray:
+    out = np.zeros(16)
+    lib().orc_fixture_random_transform(translation_limit, rotation_limit, out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out.reshape(4, 4).T.copy()
+
+
+def fixture_plane_mesh(lx, ly, T=None):
+    T = np.eye(4) if T is None else np.asarray(T, np.float64)
+    m = np.ascontiguousarray(T.T)
+    xyz = np.zeros((4, 3), np.float32)
+    nrm = np.zeros((4, 3), np.float32)
+    tri = np.zeros((2, 3), np.uint32)
+    lib().orc_fixture_plane_mesh(lx, ly, m.ctypes.data_as(C.POINTER(C.c_double)),
+                                 xyz.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
+                                 tri.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return xyz, nrm, tri

@@ -1,0 +1,151 @@
+/* TEST INFRASTRUCTURE ONLY.
+ *
+ * C API of the CPU oracle: a restatement of the raster-slicing hot path of ros-industrial/noether (noether_tpp 0.16.0)
+ * and of the third-party calls it makes (VTK 9.1 vtkCutter/vtkTriangle::Contour/vtkMergePoints/vtkStripper,
+ * PCL pcl::PCA/computeCentroid/getMinMax3D, Eigen 3.4 fixed-size kernels, Boost.Graph topological_sort).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * The product (libnoether_b200.so) never links or calls it.
+ *
+ * PARITY STATUS: the reference cannot be compiled in this image (VTK, PCL, Eigen, Boost, yaml-cpp and
+ * boost_plugin_loader are absent, no network), so this oracle is pinned against the reference's own test expectations
+ * (tool_path_planner_utest.cpp:104-119,151-176; tool_path_modifier_utest.cpp:361-399) — which pin counts and topology
+ * only.  Coordinates, normals, PCA axes and centroid are "parity unpinned" at the third-party boundary.
+ */
+#ifndef NOETHER_ORACLE_H
+#define NOETHER_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* moment accumulation mode */
+#define ORC_MOMENTS_F32_SEQUENTIAL 0 /* what PCL does: float accumulators, vertex order */
+#define ORC_MOMENTS_F64 1            /* double accumulators, result cast to float (GPU-comparable) */
+
+/* slicing mode */
+#define ORC_SLICE_FAITHFUL 0 /* vtkStripper + unify/topological sort/stack join, as the reference */
+#define ORC_SLICE_INTENT 1   /* one segment per maximal open chain (reference's documented contract) */
+
+/* which cells each plane visits */
+#define ORC_SCAN_ALL_CELLS 0 /* every vertex + every cell per plane, like vtkCutter (Theta(P(V+F))) */
+#define ORC_SCAN_BINNED 1    /* only cells whose conservative plane interval contains the plane; same results */
+
+/* status codes */
+#define ORC_OK 0
+#define ORC_ERR_INVALID 1
+#define ORC_ERR_TOO_MANY_CONNECTING 2 /* plane_slicer_raster_planner.cpp:37-38 */
+#define ORC_ERR_NOT_A_DAG 3           /* boost::not_a_dag out of topological_sort (:148) */
+#define ORC_ERR_TOPO_SORT 4           /* :158-159 */
+#define ORC_ERR_JOIN 5                /* :264,282,287 */
+#define ORC_ERR_NON_MANIFOLD 6        /* intent mode: cut point with more than two incident lines */
+#define ORC_ERR_CLOSED_LOOP 7         /* intent mode: cut lines forming a cycle */
+#define ORC_ERR_TOO_FEW_POINTS 8
+#define ORC_ERR_SEGMENT_TOO_SHORT 9 /* uniform_spacing_modifier.cpp:20-21 */
+
+const char* orc_last_error(void);
+
+/* ---- PCA / generators (plane_slicer_raster_planner.cpp:534-553, principal_axis_direction_generator.cpp:14-26,
+ *      centroid_origin_generator.cpp:8-17) ---- */
+typedef struct orc_pca_result
+{
+  float mean[3];
+  float evecs[9]; /* column-major 3x3; column 0 = largest eigenvalue, column 2 = smallest (pcl::PCA order) */
+  float evals[3]; /* descending */
+  float scales[3]; /* max - min of the cloud projected on evecs (pcl::PCA::project + getMinMax3D) */
+  float cov[9];   /* column-major covariance handed to the eigen solver */
+} orc_pca_result;
+
+int orc_pca(const float* xyz, uint64_t n_vertices, int moments_mode, orc_pca_result* out);
+int orc_centroid(const float* xyz, uint64_t n_vertices, int moments_mode, double out[3]);
+int orc_principal_axis_direction(const orc_pca_result* pca, double rotation_offset, double out[3]);
+/* Eigen 3.4 SelfAdjointEigenSolver<Matrix3f>::compute restated; cov column-major, evecs column-major ascending */
+int orc_eigen_solver_3f(const float cov[9], float evals_ascending[3], float evecs_ascending[9]);
+
+/* ---- plane lattice (plane_slicer_raster_planner.cpp:550-586, 460-501) ---- */
+typedef struct orc_lattice
+{
+  double cut_direction[3];
+  double cut_normal[3];
+  double cut_origin[3];
+  double start_loc[3];
+  double line_spacing;
+  double d_min, d_max;
+  uint64_t num_planes;
+  int32_t no_cuts; /* set when !bidirectional && d_max < 0 (:569-570) */
+  int32_t pad_;
+} orc_lattice;
+
+int orc_make_lattice(const orc_pca_result* pca,
+                     const double cut_direction[3],
+                     const double cut_origin[3],
+                     double line_spacing,
+                     int bidirectional,
+                     orc_lattice* out);
+
+/* ---- vertex normals (normals_from_mesh_faces_modifier.cpp:15-46, utils.cpp:135-162) ---- */
+int orc_normals_from_mesh_faces(const float* xyz,
+                                uint64_t n_vertices,
+                                const uint32_t* tri,
+                                uint64_t n_tri,
+                                float* normals_out /* 3 per vertex */);
+
+/* ---- tool paths ---- */
+typedef struct orc_paths orc_paths; /* opaque: noether::ToolPaths + per-waypoint provenance */
+
+/* planImpl's plane loop (:596-628) on planes [plane_begin, plane_end) of the lattice */
+int orc_slice(const float* xyz,
+              const float* normals,
+              uint64_t n_vertices,
+              const uint32_t* tri,
+              uint64_t n_tri,
+              const orc_lattice* lattice,
+              int slice_mode,
+              int scan_mode,
+              uint64_t plane_begin,
+              uint64_t plane_end,
+              orc_paths** out);
+
+orc_paths* orc_paths_create(void);
+void orc_paths_free(orc_paths* p);
+orc_paths* orc_paths_clone(const orc_paths* p);
+/* append a tool path / a segment to the last tool path / a waypoint (4x4 column-major) to the last segment */
+void orc_paths_add_path(orc_paths* p);
+void orc_paths_add_segment(orc_paths* p);
+void orc_paths_add_waypoint(orc_paths* p, const double pose16[16]);
+
+uint64_t orc_paths_num_paths(const orc_paths* p);
+uint64_t orc_paths_num_segments(const orc_paths* p);
+uint64_t orc_paths_num_waypoints(const orc_paths* p);
+/* flatten: any pointer may be NULL.  path_off has num_paths+1 entries indexing segments, seg_off has num_segments+1
+ * entries indexing waypoints.  edge_lo/edge_hi = mesh edge that generated the cut point (lower-scalar vertex first),
+ * plane = lattice index of the tool path. */
+void orc_paths_export(const orc_paths* p,
+                      uint64_t* path_off,
+                      uint64_t* seg_off,
+                      int64_t* path_plane,
+                      float* pos,
+                      float* nrm,
+                      uint32_t* edge_lo,
+                      uint32_t* edge_hi,
+                      double* pose16);
+
+/* RasterPlanner::plan post-ops (raster_planner.cpp:16-35) */
+int orc_raster_organization(orc_paths* p);        /* raster_organization_modifier.cpp:7-46 */
+int orc_direction_of_travel(orc_paths* p);        /* direction_of_travel_orientation_modifier.cpp:6-48 */
+/* legacy post-ops (plane_slicer_legacy_raster_planner.cpp:22-33) */
+int orc_join_close_segments(orc_paths* p, double distance);     /* join_close_segments_modifier.cpp:11-39 */
+int orc_minimum_segment_length(orc_paths* p, double min_length); /* minimum_segment_length_modifier.cpp:12-37 */
+int orc_uniform_spacing(orc_paths* p, double point_spacing);     /* uniform_spacing_modifier.cpp:18-70, degree 1 */
+
+/* ---- restated test fixtures ---- */
+/* createRandomTransform(translation_limit, rotation_limit): tool_path_planner_utest.cpp:32-46 (std::mt19937(0)) */
+void orc_fixture_random_transform(double translation_limit, double rotation_limit, double out16[16]);
+/* createPlaneMesh(lx, ly, origin): utils.cpp:249-291 -> 4 vertices (xyz + normal), 2 triangles */
+void orc_fixture_plane_mesh(float lx, float ly, const double origin16[16], float xyz[12], float nrm[12], uint32_t tri[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
