@@ -1,0 +1,232 @@
+/*
+ * noether_b200 — C ABI of the B200-native raster-slicing path.
+ *
+ * This is the drop-in boundary: a plain C interface (pointers + sizes, no C++/PCL/Eigen/torch types) that the
+ * boost_plugin_loader plugin shim (plugin/b200_plugins.cpp) binds so that it can export the reference's aliases
+ * `PlaneSlicer`, `PlaneSlicerLegacy`, `PrincipalAxis`, `Centroid` and `NormalsFromMeshFaces`
+ * (reference: noether_tpp/src/plugins.cpp:62,89,111,151-179,252-278).  Each entry point names the reference code it
+ * replaces (paths relative to the reference checkout, noether_tpp 0.16.0).
+ *
+ * All computation runs in hand-written sm_100a CUDA kernels inside libnoether_b200.so.  There is no CPU fallback: a
+ * missing / failing device makes every entry point return NB2_ERR_CUDA.
+ *
+ * Threading: a context serialises its own calls internally (mutex); distinct contexts are independent.
+ * Errors: every function returns an nb2_status; nb2_last_error() gives the message the shim re-throws as
+ * std::runtime_error (reference error behaviour: noether_tpp/src/core/tool_path_planner_pipeline.cpp:64-101).
+ */
+#ifndef NOETHER_B200_H
+#define NOETHER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB2_ABI_VERSION 1
+
+typedef enum nb2_status
+{
+  NB2_OK = 0,
+  NB2_ERR_INVALID_ARGUMENT = 1,
+  NB2_ERR_CUDA = 2,            /* no usable device, launch or memory failure */
+  NB2_ERR_NO_NORMALS = 3,      /* plane_slicer_raster_planner.cpp:520-528 */
+  NB2_ERR_NON_MANIFOLD = 4,    /* a cut point with more than two incident cut lines */
+  NB2_ERR_CLOSED_LOOP = 5,     /* cut lines forming a cycle (the reference throws "Topological sort failed"/not_a_dag) */
+  NB2_ERR_TOO_FEW_POINTS = 6,  /* pcl::PCA needs >= 3 points; centroid needs >= 1 (centroid_origin_generator.cpp:13) */
+  NB2_ERR_NOT_TRIANGLES = 7,
+  NB2_ERR_NON_FINITE = 8,      /* non-finite vertex coordinate */
+  NB2_ERR_SEGMENT_TOO_SHORT = 9, /* uniform_spacing_modifier.cpp:20-21 */
+  NB2_ERR_NCCL = 10,
+  NB2_ERR_NO_MESH = 11,
+  NB2_ERR_INTERNAL = 12
+} nb2_status;
+
+typedef struct nb2_context nb2_context; /* one per GPU: stream, workspace arenas, the resident mesh */
+typedef struct nb2_result nb2_result;   /* one planned set of tool paths (host SoA + device copies) */
+
+int nb2_abi_version(void);
+/* Message of the last failing call on this thread (never NULL). */
+const char* nb2_last_error(void);
+
+/* Create / destroy the per-GPU context (device = CUDA ordinal). */
+int nb2_context_create(int device, nb2_context** out);
+void nb2_context_destroy(nb2_context* ctx);
+int nb2_context_device(const nb2_context* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Mesh ingest.  Replaces pcl::fromPCLPointCloud2 + pcl::io::mesh2vtk and the by-name field accessors
+ * (plane_slicer_raster_planner.cpp:536-537,589-590; utils.cpp:65-117).  The shim resolves field names to byte
+ * offsets; `cloud_data` is pcl::PCLPointCloud2::data, `triangles` is mesh.polygons flattened to uint32[3 * n].
+ * Host pointers may be pageable or pinned.  The mesh stays resident in HBM (SoA float4 positions / normals,
+ * uint32 x 3 faces) until the next upload.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nb2_mesh_view
+{
+  const void* cloud_data;   /* n_points * point_step bytes */
+  uint64_t n_points;        /* cloud.width * cloud.height */
+  uint32_t point_step;
+  uint32_t offset_xyz;      /* offset of field "x"; "y","z" must follow contiguously (utils.cpp:82-83) */
+  int32_t offset_normal;    /* offset of "normal_x" (normal_y, normal_z contiguous, utils.cpp:104-105); -1 = none */
+  uint32_t reserved_;
+  const uint32_t* triangles; /* 3 * n_triangles vertex indices */
+  uint64_t n_triangles;
+} nb2_mesh_view;
+
+int nb2_mesh_upload(nb2_context* ctx, const nb2_mesh_view* mesh);
+/* Replace the resident normals with packed float[3 * n_points] from the host (e.g. another modifier's output). */
+int nb2_mesh_set_normals(nb2_context* ctx, const float* normals);
+/* Copy the resident SoA back (packed float[3 * n]); either pointer may be NULL.  Test / debugging aid. */
+int nb2_mesh_download(nb2_context* ctx, float* xyz, float* normals);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * PCA frame.  Replaces the pcl::PCA block of planImpl (plane_slicer_raster_planner.cpp:534-553), and feeds
+ * PrincipalAxisDirectionGenerator::generate (principal_axis_direction_generator.cpp:14-26) and
+ * CentroidOriginGenerator::generate (centroid_origin_generator.cpp:8-17).  One fused pass accumulates centroid,
+ * covariance and AABB in fp64 (warp-shuffle + block reduction, fixed order => run-to-run deterministic); the
+ * symmetric 3x3 eigen-solve restates Eigen 3.4's SelfAdjointEigenSolver<Matrix3f>; a second pass takes the float
+ * extents of the cloud in the PCA frame (pcl::PCA::project + getMinMax3D).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nb2_pca
+{
+  float mean[3];   /* pca.getMean() */
+  float evecs[9];  /* pca.getEigenVectors(), column-major, column 0 = largest eigenvalue */
+  float evals[3];  /* descending */
+  float scales[3]; /* max - min of the projected cloud */
+  float cov[9];    /* covariance handed to the eigen solver, column-major */
+  float aabb_min[3];
+  float aabb_max[3];
+  float pad_;
+  double mean64[3]; /* fp64 moments before the float cast */
+  double cov64[9];
+} nb2_pca;
+
+int nb2_mesh_pca(nb2_context* ctx, nb2_pca* out);
+int nb2_principal_axis_direction(nb2_context* ctx, double rotation_offset, double out_direction[3]);
+int nb2_centroid_origin(nb2_context* ctx, double out_origin[3]);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * NormalsFromMeshFacesMeshModifier::modify (normals_from_mesh_faces_modifier.cpp:15-46; getFaceNormal
+ * utils.cpp:135-162).  Unit face normals, accumulated per vertex through a CSR vertex->face list in ascending face
+ * order (no float atomics; bit-identical to the reference's sequential float sums), normalised.  The result
+ * replaces the resident normals and, when `normals_out` is not NULL, is copied to the host as packed float[3 * n].
+ * The shim builds the concatenated output cloud (pcl::concatenateFields) from it.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int nb2_normals_from_mesh_faces(nb2_context* ctx, float* normals_out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Plane lattice (plane_slicer_raster_planner.cpp:556-586 and getDistancesToMinMaxCuts :460-501).  Pure host
+ * arithmetic in double, restated with the reference's quirks (OBB centred on the mean, `else if` min/max update,
+ * floored start offset, ceil'ed plane count).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nb2_lattice
+{
+  double cut_direction[3];
+  double cut_normal[3];
+  double cut_origin[3];
+  double start_loc[3];
+  double line_spacing;
+  double d_min, d_max;
+  uint64_t num_planes;
+  int32_t no_cuts; /* !bidirectional && d_max < 0 -> planImpl returns {} (:569-570) */
+  int32_t pad_;
+} nb2_lattice;
+
+int nb2_make_lattice(const nb2_pca* pca,
+                     const double cut_direction[3],
+                     const double cut_origin[3],
+                     double line_spacing,
+                     int bidirectional,
+                     nb2_lattice* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Planning.
+ * nb2_slice  = the plane loop of PlaneSlicerRasterPlanner::planImpl (:596-628: vtkCutter + vtkStripper +
+ *              processPolyLines + convertToPoses) for planes [plane_begin, plane_end) of a given lattice.
+ * nb2_plan   = RasterPlanner::plan (raster_planner.cpp:16-35) for PlaneSlicerRasterPlanner /
+ *              PlaneSlicerLegacyRasterPlanner: PCA, generators, lattice, slice, optional legacy modifiers, then
+ *              RasterOrganizationModifier + DirectionOfTravelOrientationModifier.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define NB2_DIRECTION_EXPLICIT 0       /* value produced by any noether::DirectionGenerator */
+#define NB2_DIRECTION_PRINCIPAL_AXIS 1 /* PrincipalAxisDirectionGenerator(rotation_offset), computed here */
+#define NB2_ORIGIN_EXPLICIT 0          /* value produced by any noether::OriginGenerator */
+#define NB2_ORIGIN_CENTROID 1          /* CentroidOriginGenerator, computed here */
+#define NB2_ALL_PLANES UINT64_MAX
+
+typedef struct nb2_plan_params
+{
+  double line_spacing;    /* RasterPlanner::setLineSpacing */
+  int32_t bidirectional;  /* PlaneSlicerRasterPlanner::generateRastersBidirectionally */
+  int32_t direction_mode;
+  double direction[3];
+  double rotation_offset;
+  int32_t origin_mode;
+  int32_t raster_post_ops; /* 1 = apply RasterOrganization + DirectionOfTravel (what RasterPlanner::plan returns) */
+  double origin[3];
+  /* PlaneSlicerLegacyRasterPlanner (plane_slicer_legacy_raster_planner.cpp:22-33); legacy = 0 ignores the rest */
+  int32_t legacy;
+  int32_t emit_edges;      /* 1 = also return the generating mesh edge of every waypoint (connectivity provenance) */
+  double point_spacing;
+  double min_segment_size;
+  double min_hole_size;
+  /* plane-slab sharding: this context plans lattice planes [shard_rank * P / shard_count, (shard_rank+1) * P / shard_count) */
+  int32_t shard_rank;
+  int32_t shard_count; /* 0 or 1 = unsharded */
+} nb2_plan_params;
+
+void nb2_plan_params_default(nb2_plan_params* p);
+
+int nb2_slice(nb2_context* ctx, const nb2_lattice* lattice, uint64_t plane_begin, uint64_t plane_end, nb2_result** out);
+int nb2_plan(nb2_context* ctx, const nb2_plan_params* params, nb2_result** out);
+/* Lattice used by the last nb2_plan on this context. */
+int nb2_last_lattice(const nb2_context* ctx, nb2_lattice* out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Results.  noether::ToolPaths (core/types.h:31-50) as SoA on the host: tool paths -> segments -> waypoints.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nb2_result_view
+{
+  uint64_t n_paths;
+  uint64_t n_segments;
+  uint64_t n_waypoints;
+  const uint32_t* path_offsets;    /* n_paths + 1, indexes segments */
+  const uint32_t* segment_offsets; /* n_segments + 1, indexes waypoints */
+  const int64_t* path_plane;       /* n_paths, lattice index of each tool path */
+  const float* positions;          /* 3 * n_waypoints, float32 cut points (what vtkCutter stores) */
+  const float* normals;            /* 3 * n_waypoints, float32 interpolated vertex normals (not normalised) */
+  const uint32_t* edge_lo;         /* n_waypoints: generating mesh edge, lower-scalar vertex */
+  const uint32_t* edge_hi;         /* n_waypoints: generating mesh edge, higher-scalar vertex */
+  const double* poses;             /* NULL unless the result carries explicit poses (legacy resampling): 16 * n */
+  int32_t raster_post_ops_applied;
+  int32_t legacy;
+} nb2_result_view;
+
+int nb2_result_get(const nb2_result* r, nb2_result_view* out);
+/* Expand to Eigen::Isometry3d storage: 16 doubles per waypoint, column-major, last row 0 0 0 1
+ * (createTransform :380-394, then DirectionOfTravelOrientationModifier when post-ops were applied). */
+int nb2_result_poses(const nb2_result* r, double* out16);
+void nb2_result_free(nb2_result* r);
+
+/* Device timings of the last nb2_plan / nb2_slice / nb2_normals_from_mesh_faces / nb2_mesh_upload on the context
+ * (CUDA events on the context's stream), in milliseconds; `names` points at static strings.  Returns the number of
+ * stages written (<= capacity). */
+int nb2_last_timings(const nb2_context* ctx, const char** names, float* ms, int capacity);
+/* Number of kernel launches issued by this context since creation. */
+uint64_t nb2_kernel_launches(const nb2_context* ctx);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  Plane slabs are independent (the reference's loop :596-628 carries no state), so
+ * the only exchange is the gather of per-slab polylines to rank 0, over NCCL (NVLink 5 / NVSwitch).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define NB2_UNIQUE_ID_BYTES 128
+int nb2_comm_unique_id(uint8_t out[NB2_UNIQUE_ID_BYTES]);
+int nb2_comm_init(nb2_context* ctx, const uint8_t unique_id[NB2_UNIQUE_ID_BYTES], int rank, int world_size);
+/* Collective: every rank passes its slab result; on `root` *gathered receives the concatenation in rank (= plane)
+ * order, on other ranks NULL.  Post-ops, when requested in the original params, are applied to the gathered result. */
+int nb2_result_gather(nb2_context* ctx, const nb2_result* local, int root, nb2_result** gathered);
+int nb2_comm_destroy(nb2_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOETHER_B200_H */

@@ -1,0 +1,812 @@
+// C ABI of libnoether_b200.so (include/noether_b200.h): context, mesh ingest, PCA frame, planning, results.
+#include "host_math.h"
+#include "nb2_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <exception>
+#include <memory>
+
+namespace nb2
+{
+namespace
+{
+thread_local std::string t_last_error;
+}
+void setLastError(const std::string& msg) { t_last_error = msg; }
+void fail(int status, const std::string& msg) { throw Error{ status, msg }; }
+
+void DevBuf::ensure(size_t bytes)
+{
+  if (bytes <= cap)
+    return;
+  if (ptr)
+    NB2_CUDA(cudaFree(ptr));
+  ptr = nullptr;
+  cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  NB2_CUDA(cudaMalloc(&ptr, want));
+  cap = want;
+}
+void DevBuf::release()
+{
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+void PinnedBuf::ensure(size_t bytes)
+{
+  if (bytes <= cap)
+    return;
+  if (ptr)
+    NB2_CUDA(cudaFreeHost(ptr));
+  ptr = nullptr;
+  cap = 0;
+  NB2_CUDA(cudaMallocHost(&ptr, bytes));
+  cap = bytes;
+}
+void PinnedBuf::release()
+{
+  if (ptr)
+    cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+void StageTimer::begin(cudaStream_t s)
+{
+  used = 0;
+  names.clear();
+  if (events.empty())
+  {
+    events.resize(24);
+    for (auto& e : events)
+      NB2_CUDA(cudaEventCreate(&e));
+  }
+  NB2_CUDA(cudaEventRecord(events[0], s));
+}
+void StageTimer::mark(const char* name, cudaStream_t s)
+{
+  if (used + 2 > events.size())
+    return;
+  ++used;
+  names.push_back(name);
+  NB2_CUDA(cudaEventRecord(events[used], s));
+}
+int StageTimer::collect(const char** out_names, float* ms, int capacity) const
+{
+  int n = 0;
+  for (size_t i = 0; i < used && n < capacity; ++i, ++n)
+  {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, events[i], events[i + 1]) != cudaSuccess)
+      t = -1.f;
+    out_names[n] = names[i];
+    ms[n] = t;
+  }
+  return n;
+}
+void StageTimer::destroy()
+{
+  for (auto& e : events)
+    cudaEventDestroy(e);
+  events.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// result storage
+// ---------------------------------------------------------------------------------------------------------------
+static size_t align64(size_t x) { return (x + 63) & ~size_t(63); }
+
+nb2_result* allocResult(nb2_context* c, uint64_t P, uint64_t S, uint64_t W, bool edges, bool poses)
+{
+  size_t off = 0;
+  const size_t o_path = off;
+  off = align64(off + 4 * (P + 1));
+  const size_t o_seg = off;
+  off = align64(off + 4 * (S + 1));
+  const size_t o_plane = off;
+  off = align64(off + 8 * (P + 1));
+  const size_t o_pos = off;
+  off = align64(off + 12 * (W + 1));
+  const size_t o_nrm = off;
+  off = align64(off + 12 * (W + 1));
+  size_t o_lo = 0, o_hi = 0, o_pose = 0;
+  if (edges)
+  {
+    o_lo = off;
+    off = align64(off + 4 * (W + 1));
+    o_hi = off;
+    off = align64(off + 4 * (W + 1));
+  }
+  if (poses)
+  {
+    o_pose = off;
+    off = align64(off + 128 * (W + 1));
+  }
+  const size_t need = off;
+
+  auto* r = new nb2_result();
+  r->owner = c;
+  {
+    // recycle the smallest pooled pinned block that fits
+    int best = -1;
+    for (size_t i = 0; i < c->hostPool.size(); ++i)
+      if (c->hostPool[i].cap >= need && (best < 0 || c->hostPool[i].cap < c->hostPool[best].cap))
+        best = static_cast<int>(i);
+    if (best >= 0)
+    {
+      r->block = c->hostPool[best].ptr;
+      r->block_cap = c->hostPool[best].cap;
+      c->hostPool.erase(c->hostPool.begin() + best);
+    }
+    else
+    {
+      const size_t cap = need + need / 8 + 4096;
+      cudaError_t err = cudaMallocHost(&r->block, cap);
+      if (err != cudaSuccess)
+      {
+        delete r;
+        fail(NB2_ERR_CUDA, std::string("cudaMallocHost failed: ") + cudaGetErrorString(err));
+      }
+      r->block_cap = cap;
+    }
+  }
+  auto* base = static_cast<uint8_t*>(r->block);
+  r->n_paths = P;
+  r->n_segments = S;
+  r->n_waypoints = W;
+  r->path_offsets = reinterpret_cast<uint32_t*>(base + o_path);
+  r->segment_offsets = reinterpret_cast<uint32_t*>(base + o_seg);
+  r->path_plane = reinterpret_cast<int64_t*>(base + o_plane);
+  r->positions = reinterpret_cast<float*>(base + o_pos);
+  r->normals = reinterpret_cast<float*>(base + o_nrm);
+  r->edge_lo = edges ? reinterpret_cast<uint32_t*>(base + o_lo) : nullptr;
+  r->edge_hi = edges ? reinterpret_cast<uint32_t*>(base + o_hi) : nullptr;
+  r->poses = poses ? reinterpret_cast<double*>(base + o_pose) : nullptr;
+  r->path_offsets[0] = 0;
+  r->segment_offsets[0] = 0;
+  return r;
+}
+
+void freeResult(nb2_result* r)
+{
+  if (!r)
+    return;
+  if (r->block && r->owner)
+  {
+    auto& pool = r->owner->hostPool;
+    if (pool.size() < 8)
+      pool.push_back({ r->block, r->block_cap });
+    else
+      cudaFreeHost(r->block);
+  }
+  delete r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct DeviceGuard
+{
+  int prev = -1;
+  explicit DeviceGuard(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev)
+      NB2_CUDA(cudaSetDevice(dev));
+    else
+      prev = -1;
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0)
+      cudaSetDevice(prev);
+  }
+};
+
+void requireMesh(const nb2_context* c)
+{
+  if (c->V == 0)
+    fail(NB2_ERR_NO_MESH, "no mesh has been uploaded to this context");
+}
+
+void ensurePca(nb2_context* c)
+{
+  requireMesh(c);
+  if (c->V < 3)
+    fail(NB2_ERR_TOO_FEW_POINTS, "[pcl::PCA::initCompute] number of points < 3");
+  if (c->pca_valid)
+    return;
+  // extents of the cloud in the PCA frame (second, smaller pass)
+  launchExtents(c, c->pca.mean, c->pca.evecs);
+  c->hostSmall.ensure(4096);
+  float* h = c->hostSmall.as<float>();
+  NB2_CUDA(cudaMemcpyAsync(h, c->extents.ptr, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; ++i)
+    c->pca.scales[i] = h[3 + i] - h[i];
+  c->pca_valid = true;
+}
+
+nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
+{
+  nb2_result* r = allocResult(c, 0, 0, 0, true, false);
+  r->lattice = L;
+  return r;
+}
+
+/** planImpl's plane loop on the device */
+nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, bool emit_edges)
+{
+  requireMesh(c);
+  if (!c->has_normals)
+    fail(NB2_ERR_NO_NORMALS, "The input mesh does not have vertex normals, which are required for the plane slice raster "
+                             "tool path planner. Use a MeshModifier to generate vertex normals for the mesh, or provide a "
+                             "different mesh with vertex normals.");
+  plane_end = std::min<uint64_t>(plane_end, lat.num_planes);
+  if (plane_begin >= plane_end || c->F == 0)
+    return emptyResult(c, lat);
+  const uint64_t nP = plane_end - plane_begin;
+
+  LatticeDev L{};
+  for (int i = 0; i < 3; ++i)
+  {
+    L.n[i] = lat.cut_normal[i];
+    L.start[i] = lat.start_loc[i];
+    L.dir[i] = lat.cut_direction[i];
+  }
+  L.spacing = lat.line_spacing;
+  L.num_planes = static_cast<long long>(lat.num_planes);
+  L.plane_begin = static_cast<long long>(plane_begin);
+  L.plane_end = static_cast<long long>(plane_end);
+
+  // counters: [0] moments ticket, [1] extents ticket, [4] H, [5] n_max, [8] link ticket, [10] status, [11] failing plane
+  unsigned init[16] = { 0 };
+  init[11] = 0xffffffffu;
+  NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + 4, init + 4, 12 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+
+  c->timer.begin(c->stream);
+  launchClassify(c, L);
+  c->timer.mark("classify", c->stream);
+  launchCountHits(c, L);
+  c->timer.mark("count", c->stream);
+  launchScanPlanes(c, L);
+  c->timer.mark("scan", c->stream);
+
+  c->hostSmall.ensure(4096);
+  unsigned* h = c->hostSmall.as<unsigned>();
+  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  const uint64_t H = h[0];
+  const uint32_t n_max = h[1];
+  if (H == 0)
+    return emptyResult(c, lat);
+  if (H >= (1ull << 30))
+    fail(NB2_ERR_INVALID_ARGUMENT, "more than 2^30 triangle/plane intersections in one slab; shard the plan");
+
+  c->bucket.ensure(sizeof(uint32_t) * H);
+  launchFillBuckets(c, L);
+  c->timer.mark("fill", c->stream);
+
+  const uint64_t w_cap = 2 * H, s_cap = H;
+  c->outPos.ensure(sizeof(float) * 3 * w_cap);
+  c->outNrm.ensure(sizeof(float) * 3 * w_cap);
+  if (emit_edges)
+    c->outEdge.ensure(sizeof(uint32_t) * 2 * w_cap);
+  c->outSegLen.ensure(sizeof(unsigned) * s_cap);
+  launchLinkPlanes(c, L, n_max, w_cap, s_cap, emit_edges ? 1 : 0);
+  c->timer.mark("link", c->stream);
+
+  // totals, per-plane meta and status
+  c->hostSmall.ensure(64 + sizeof(unsigned) * 2 * nP);
+  h = c->hostSmall.as<unsigned>();
+  auto* h64 = reinterpret_cast<unsigned long long*>(h);
+  unsigned* hstat = h + 2;
+  unsigned* hmeta = h + 16;
+  NB2_CUDA(cudaMemcpyAsync(h64, c->lookback.as<unsigned long long>() + (nP - 1), sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(hstat, c->counters.as<unsigned>() + 10, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  if (hstat[0])
+  {
+    const std::string where = " (lattice plane " + std::to_string(plane_begin + hstat[1]) + ")";
+    if (hstat[0] & 1u)
+      fail(NB2_ERR_NON_MANIFOLD, "cut point with more than two incident cut lines: the mesh is not a manifold surface there" + where);
+    if (hstat[0] & 2u)
+      fail(NB2_ERR_CLOSED_LOOP, "cut lines form a closed loop; the reference aborts such plans (Topological sort failed / "
+                                "not a DAG)" + where);
+    fail(NB2_ERR_INTERNAL, "output capacity exceeded while linking" + where);
+  }
+  const uint64_t Wt = (h64[0] >> 31) & 0x7fffffffull;
+  const uint64_t St = h64[0] & 0x7fffffffull;
+  uint64_t Pn = 0;
+  for (uint64_t k = 0; k < nP; ++k)
+    Pn += hmeta[2 * k + 1] > 0;
+
+  nb2_result* r = allocResult(c, Pn, St, Wt, emit_edges, false);
+  r->lattice = lat;
+  try
+  {
+    if (Wt)
+    {
+      NB2_CUDA(cudaMemcpyAsync(r->positions, c->outPos.ptr, sizeof(float) * 3 * Wt, cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaMemcpyAsync(r->normals, c->outNrm.ptr, sizeof(float) * 3 * Wt, cudaMemcpyDeviceToHost, c->stream));
+      if (emit_edges)
+      {
+        NB2_CUDA(cudaMemcpyAsync(r->edge_lo, c->outEdge.ptr, sizeof(uint32_t) * Wt, cudaMemcpyDeviceToHost, c->stream));
+        NB2_CUDA(cudaMemcpyAsync(r->edge_hi, c->outEdge.as<uint32_t>() + w_cap, sizeof(uint32_t) * Wt,
+                                 cudaMemcpyDeviceToHost, c->stream));
+      }
+      NB2_CUDA(cudaMemcpyAsync(r->segment_offsets + 1, c->outSegLen.ptr, sizeof(unsigned) * St, cudaMemcpyDeviceToHost,
+                               c->stream));
+    }
+    c->timer.mark("d2h", c->stream);
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  catch (...)
+  {
+    freeResult(r);
+    throw;
+  }
+  // segment lengths -> offsets; planes with segments -> tool paths
+  for (uint64_t s = 0; s < St; ++s)
+    r->segment_offsets[s + 1] += r->segment_offsets[s];
+  uint64_t p = 0, s_acc = 0;
+  for (uint64_t k = 0; k < nP; ++k)
+  {
+    const unsigned sk = hmeta[2 * k + 1];
+    if (!sk)
+      continue;
+    r->path_offsets[p] = static_cast<uint32_t>(s_acc);
+    r->path_plane[p] = static_cast<int64_t>(plane_begin + k);
+    s_acc += sk;
+    ++p;
+  }
+  r->path_offsets[p] = static_cast<uint32_t>(s_acc);
+  return r;
+}
+
+}  // namespace
+
+void directionOfTravelInPlace(nb2_result& r);
+
+}  // namespace nb2
+
+using namespace nb2;
+
+#define NB2_API_BEGIN                                                                                                  \
+  try                                                                                                                  \
+  {
+#define NB2_API_END                                                                                                    \
+  }                                                                                                                    \
+  catch (const nb2::Error& e)                                                                                          \
+  {                                                                                                                    \
+    nb2::setLastError(e.msg);                                                                                          \
+    return e.status;                                                                                                   \
+  }                                                                                                                    \
+  catch (const std::exception& e)                                                                                      \
+  {                                                                                                                    \
+    nb2::setLastError(std::string("internal error: ") + e.what());                                                     \
+    return NB2_ERR_INTERNAL;                                                                                           \
+  }                                                                                                                    \
+  return NB2_OK;
+
+extern "C" {
+
+int nb2_abi_version(void) { return NB2_ABI_VERSION; }
+const char* nb2_last_error(void) { return t_last_error.c_str(); }
+
+int nb2_context_create(int device, nb2_context** out)
+{
+  NB2_API_BEGIN
+  if (!out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0)
+    fail(NB2_ERR_CUDA, std::string("no CUDA device available (this library has no CPU fallback): ") +
+                           (err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0"));
+  if (device < 0 || device >= count)
+    fail(NB2_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  DeviceGuard g(device);
+  cudaDeviceProp prop{};
+  NB2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    fail(NB2_ERR_CUDA, std::string("device '") + prop.name + "' is not a Blackwell (sm_100a) GPU; this library ships sm_100a code only");
+  auto c = std::make_unique<nb2_context>();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  NB2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->counters.ensure(64 * sizeof(unsigned));
+  NB2_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64 * sizeof(unsigned), c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c.release();
+  NB2_API_END
+}
+
+void nb2_context_destroy(nb2_context* c)
+{
+  if (!c)
+    return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  if (c->stream)
+    cudaStreamSynchronize(c->stream);
+  nb2_comm_destroy(c);
+  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->counters, &c->vertK, &c->planeCnt,
+                     &c->planeOff, &c->planeCursor, &c->bucket, &c->lookback, &c->planeMeta, &c->outPos, &c->outNrm,
+                     &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
+                     &c->csrAdj, &c->scanState })
+    b->release();
+  c->hostSmall.release();
+  for (auto& hb : c->hostPool)
+    cudaFreeHost(hb.ptr);
+  c->timer.destroy();
+  if (c->stream)
+    cudaStreamDestroy(c->stream);
+  if (prev >= 0)
+    cudaSetDevice(prev);
+  delete c;
+}
+
+int nb2_context_device(const nb2_context* c) { return c ? c->device : -1; }
+
+int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
+{
+  NB2_API_BEGIN
+  if (!c || !m)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or mesh is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  if (m->n_points == 0)
+    fail(NB2_ERR_TOO_FEW_POINTS, "mesh has no vertices");
+  if (!m->cloud_data || (m->n_triangles && !m->triangles))
+    fail(NB2_ERR_INVALID_ARGUMENT, "mesh data pointer is NULL");
+  if (m->point_step % 4 || m->offset_xyz % 4 || m->offset_xyz + 12 > m->point_step)
+    fail(NB2_ERR_INVALID_ARGUMENT, "XYZ fields are not contiguous floats");  // utils.cpp:82-83
+  if (m->offset_normal >= 0 && (m->offset_normal % 4 || static_cast<uint32_t>(m->offset_normal) + 12 > m->point_step))
+    fail(NB2_ERR_INVALID_ARGUMENT, "Normal fields are not contiguous floats");  // utils.cpp:104-105
+  if (m->n_points >= (1ull << 31) || m->n_triangles >= (1ull << 31))
+    fail(NB2_ERR_INVALID_ARGUMENT, "meshes with 2^31 or more vertices / triangles are not supported");
+
+  c->V = 0;
+  c->pca_valid = false;
+  const uint64_t V = m->n_points, F = m->n_triangles;
+  c->timer.begin(c->stream);
+  c->blob.ensure(V * m->point_step);
+  c->pos.ensure(sizeof(float4) * V);
+  c->nrm.ensure(sizeof(float4) * V);
+  c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+  NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, V * m->point_step, cudaMemcpyHostToDevice, c->stream));
+  if (F)
+    NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, sizeof(uint32_t) * 3 * F, cudaMemcpyHostToDevice, c->stream));
+  c->timer.mark("h2d", c->stream);
+  c->V = V;
+  c->F = F;
+  c->has_normals = m->offset_normal >= 0;
+  if (!c->has_normals)
+    NB2_CUDA(cudaMemsetAsync(c->nrm.ptr, 0, sizeof(float4) * V, c->stream));
+  launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
+  c->timer.mark("ingest+moments", c->stream);
+  launchValidateTriangles(c);
+  c->timer.mark("validate", c->stream);
+
+  c->hostSmall.ensure(4096);
+  auto* h = c->hostSmall.as<uint8_t>();
+  const int grid = static_cast<int>(std::min<uint64_t>((V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  // pivot = first vertex
+  float pivot[3];
+  std::memcpy(pivot, static_cast<const uint8_t*>(m->cloud_data) + m->offset_xyz, 12);
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  MomentPartial total;
+  std::memcpy(&total, h, sizeof(total));
+  unsigned max_index;
+  std::memcpy(&max_index, h + 512, 4);
+  if (total.non_finite)
+  {
+    c->V = 0;
+    fail(NB2_ERR_NON_FINITE, std::to_string(total.non_finite) + " vertices have non-finite coordinates");
+  }
+  if (F && max_index >= V)
+  {
+    c->V = 0;
+    fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(max_index) + " but the cloud has " +
+                                       std::to_string(V) + " points");
+  }
+  std::memset(&c->pca, 0, sizeof(c->pca));
+  if (V >= 3)
+    finalizeMoments(total, V, pivot, c->pca);
+  else
+  {
+    const double n = static_cast<double>(V);
+    for (int i = 0; i < 3; ++i)
+    {
+      c->pca.mean64[i] = pivot[i] + total.s[i] / n;
+      c->pca.mean[i] = static_cast<float>(c->pca.mean64[i]);
+    }
+  }
+  NB2_API_END
+}
+
+int nb2_mesh_set_normals(nb2_context* c, const float* normals)
+{
+  NB2_API_BEGIN
+  if (!c || !normals)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or normals is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  c->faceNrm.ensure(sizeof(float) * 3 * c->V);  // staging
+  NB2_CUDA(cudaMemcpyAsync(c->faceNrm.ptr, normals, sizeof(float) * 3 * c->V, cudaMemcpyHostToDevice, c->stream));
+  launchSetNormals(c, c->faceNrm.as<float>());
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  c->has_normals = true;
+  NB2_API_END
+}
+
+int nb2_mesh_download(nb2_context* c, float* xyz, float* normals)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  c->outPos.ensure(sizeof(float) * 3 * c->V);
+  c->outNrm.ensure(sizeof(float) * 3 * c->V);
+  launchPackOut(c, xyz ? c->outPos.as<float>() : nullptr, normals ? c->outNrm.as<float>() : nullptr);
+  if (xyz)
+    NB2_CUDA(cudaMemcpyAsync(xyz, c->outPos.ptr, sizeof(float) * 3 * c->V, cudaMemcpyDeviceToHost, c->stream));
+  if (normals)
+    NB2_CUDA(cudaMemcpyAsync(normals, c->outNrm.ptr, sizeof(float) * 3 * c->V, cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  NB2_API_END
+}
+
+int nb2_mesh_pca(nb2_context* c, nb2_pca* out)
+{
+  NB2_API_BEGIN
+  if (!c || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  ensurePca(c);
+  *out = c->pca;
+  NB2_API_END
+}
+
+int nb2_principal_axis_direction(nb2_context* c, double rotation_offset, double out[3])
+{
+  NB2_API_BEGIN
+  if (!c || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  if (c->V < 3)
+    fail(NB2_ERR_TOO_FEW_POINTS, "[pcl::PCA::initCompute] number of points < 3");
+  principalAxisDirection(c->pca, rotation_offset, out);
+  NB2_API_END
+}
+
+int nb2_centroid_origin(nb2_context* c, double out[3])
+{
+  NB2_API_BEGIN
+  if (!c || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  requireMesh(c);
+  for (int i = 0; i < 3; ++i)
+    out[i] = static_cast<double>(c->pca.mean[i]);
+  NB2_API_END
+}
+
+int nb2_normals_from_mesh_faces(nb2_context* c, float* normals_out)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  c->timer.begin(c->stream);
+  launchVertexNormals(c);
+  c->has_normals = true;
+  if (normals_out)
+  {
+    c->outPos.ensure(sizeof(float) * 3 * c->V);
+    launchPackOut(c, nullptr, c->outPos.as<float>());
+    c->timer.mark("pack", c->stream);
+    NB2_CUDA(cudaMemcpyAsync(normals_out, c->outPos.ptr, sizeof(float) * 3 * c->V, cudaMemcpyDeviceToHost, c->stream));
+    c->timer.mark("d2h", c->stream);
+  }
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  NB2_API_END
+}
+
+int nb2_make_lattice(const nb2_pca* pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
+                     nb2_lattice* out)
+{
+  NB2_API_BEGIN
+  if (!pca || !dir || !origin || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  const int rc = makeLattice(*pca, dir, origin, spacing, bidirectional, *out);
+  if (rc != NB2_OK)
+    return rc;
+  NB2_API_END
+}
+
+void nb2_plan_params_default(nb2_plan_params* p)
+{
+  if (!p)
+    return;
+  std::memset(p, 0, sizeof(*p));
+  p->line_spacing = 0.1;  // GUI default (raster_planner_widget.ui:89-100)
+  p->bidirectional = 1;
+  p->direction_mode = NB2_DIRECTION_PRINCIPAL_AXIS;
+  p->origin_mode = NB2_ORIGIN_CENTROID;
+  p->raster_post_ops = 1;
+  p->emit_edges = 1;
+  p->point_spacing = 0.025;
+  p->min_segment_size = 0.1;
+  p->min_hole_size = 0.1;
+  p->shard_rank = 0;
+  p->shard_count = 1;
+}
+
+int nb2_slice(nb2_context* c, const nb2_lattice* lat, uint64_t plane_begin, uint64_t plane_end, nb2_result** out)
+{
+  NB2_API_BEGIN
+  if (!c || !lat || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  if (!(lat->line_spacing > 0.0))
+    fail(NB2_ERR_INVALID_ARGUMENT, "line_spacing must be a positive finite number");
+  *out = sliceImpl(c, *lat, plane_begin, plane_end, true);
+  NB2_API_END
+}
+
+int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
+{
+  NB2_API_BEGIN
+  if (!c || !prm || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  if (!c->has_normals)
+    fail(NB2_ERR_NO_NORMALS, "The input mesh does not have vertex normals, which are required for the plane slice raster "
+                             "tool path planner. Use a MeshModifier to generate vertex normals for the mesh, or provide a "
+                             "different mesh with vertex normals.");
+  ensurePca(c);
+  double dir[3], origin[3];
+  if (prm->direction_mode == NB2_DIRECTION_PRINCIPAL_AXIS)
+    principalAxisDirection(c->pca, prm->rotation_offset, dir);
+  else
+    std::copy(prm->direction, prm->direction + 3, dir);
+  if (prm->origin_mode == NB2_ORIGIN_CENTROID)
+    for (int i = 0; i < 3; ++i)
+      origin[i] = static_cast<double>(c->pca.mean[i]);
+  else
+    std::copy(prm->origin, prm->origin + 3, origin);
+
+  nb2_lattice lat{};
+  const int rc = makeLattice(c->pca, dir, origin, prm->line_spacing, prm->bidirectional, lat);
+  if (rc != NB2_OK)
+    return rc;
+  c->last_lattice = lat;
+  c->have_lattice = true;
+
+  uint64_t kb = 0, ke = lat.num_planes;
+  if (prm->shard_count > 1)
+  {
+    if (prm->shard_rank < 0 || prm->shard_rank >= prm->shard_count)
+      fail(NB2_ERR_INVALID_ARGUMENT, "shard_rank out of range");
+    kb = lat.num_planes * static_cast<uint64_t>(prm->shard_rank) / prm->shard_count;
+    ke = lat.num_planes * (static_cast<uint64_t>(prm->shard_rank) + 1) / prm->shard_count;
+  }
+  nb2_result* r = sliceImpl(c, lat, kb, ke, prm->emit_edges != 0 || prm->legacy != 0);
+  r->params = *prm;
+  try
+  {
+    const bool sharded = prm->shard_count > 1;
+    // sharded plans defer the modifiers to nb2_result_gather: they need the whole set of tool paths
+    if (!sharded)
+    {
+      if (prm->legacy && r->n_paths)
+        legacyModifiers(r, prm->point_spacing, prm->min_segment_size, prm->min_hole_size);
+      if (prm->raster_post_ops && r->n_paths)
+      {
+        rasterOrganization(r);
+        r->post_ops_applied = true;
+        directionOfTravelInPlace(*r);
+      }
+    }
+  }
+  catch (...)
+  {
+    freeResult(r);
+    throw;
+  }
+  *out = r;
+  NB2_API_END
+}
+
+int nb2_last_lattice(const nb2_context* c, nb2_lattice* out)
+{
+  NB2_API_BEGIN
+  if (!c || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!c->have_lattice)
+    fail(NB2_ERR_INVALID_ARGUMENT, "no plan has run on this context");
+  *out = c->last_lattice;
+  NB2_API_END
+}
+
+int nb2_result_get(const nb2_result* r, nb2_result_view* out)
+{
+  NB2_API_BEGIN
+  if (!r || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  out->n_paths = r->n_paths;
+  out->n_segments = r->n_segments;
+  out->n_waypoints = r->n_waypoints;
+  out->path_offsets = r->path_offsets;
+  out->segment_offsets = r->segment_offsets;
+  out->path_plane = r->path_plane;
+  out->positions = r->positions;
+  out->normals = r->normals;
+  out->edge_lo = r->edge_lo;
+  out->edge_hi = r->edge_hi;
+  out->poses = r->poses;
+  out->raster_post_ops_applied = r->post_ops_applied ? 1 : 0;
+  out->legacy = r->legacy ? 1 : 0;
+  NB2_API_END
+}
+
+int nb2_result_poses(const nb2_result* r, double* out16)
+{
+  NB2_API_BEGIN
+  if (!r || (!out16 && r->n_waypoints))
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  expandPoses(*r, out16);
+  NB2_API_END
+}
+
+void nb2_result_free(nb2_result* r)
+{
+  if (!r)
+    return;
+  if (r->owner)
+  {
+    std::lock_guard<std::mutex> lock(r->owner->mu);
+    freeResult(r);
+  }
+  else
+    freeResult(r);
+}
+
+int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int capacity)
+{
+  if (!c || !names || !ms)
+    return 0;
+  return c->timer.collect(names, ms, capacity);
+}
+
+uint64_t nb2_kernel_launches(const nb2_context* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

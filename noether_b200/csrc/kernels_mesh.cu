@@ -1,0 +1,391 @@
+// Mesh ingest, moments, PCA-frame extents and per-vertex lattice classification (sm_100a).
+//
+//   K0+K1a  k_ingest_moments : interleaved PCLPointCloud2 blob -> SoA float4 positions / normals, fused with the
+//                              single-pass fp64 reduction of sum(x), sum(x x^T) and the AABB
+//                              (replaces pcl::fromPCLPointCloud2 x3, pcl::io::mesh2vtk, pcl::PCA's mean/covariance
+//                              passes, pcl::computeCentroid: plane_slicer_raster_planner.cpp:536-541,589-590,
+//                              principal_axis_direction_generator.cpp:16-19, centroid_origin_generator.cpp:10-13)
+//   K1c     k_extents        : float extents of the cloud in the PCA frame (pcl::PCA::project + getMinMax3D,
+//                              plane_slicer_raster_planner.cpp:544-548)
+//   S1      k_classify       : per vertex, the last lattice plane the vertex is "inside" of (scalar >= 0); replaces
+//                              the per-plane vtkPlane::EvaluateFunction sweep over all vertices (:600-608)
+#include "device_math.cuh"
+#include "nb2_internal.h"
+
+#include <cfloat>
+
+namespace nb2
+{
+namespace
+{
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ double warpSum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warpMin(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fminf(v, __shfl_down_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ float warpMax(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_down_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned long long warpSumU(unsigned long long v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_down_sync(kFull, v, o);
+  return v;
+}
+
+/** Thread-level partial -> block partial (fixed shuffle tree, then warps summed in index order by thread 0). */
+__device__ void blockReducePartial(MomentPartial& p, MomentPartial* smem /*[warps]*/)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    p.s[i] = warpSum(p.s[i]);
+    p.mn[i] = warpMin(p.mn[i]);
+    p.mx[i] = warpMax(p.mx[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    p.q[i] = warpSum(p.q[i]);
+  p.non_finite = warpSumU(p.non_finite);
+  if (lane == 0)
+    smem[warp] = p;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    MomentPartial t = smem[0];
+    for (int w = 1; w < nwarps; ++w)
+    {
+      for (int i = 0; i < 3; ++i)
+      {
+        t.s[i] += smem[w].s[i];
+        t.mn[i] = fminf(t.mn[i], smem[w].mn[i]);
+        t.mx[i] = fmaxf(t.mx[i], smem[w].mx[i]);
+      }
+      for (int i = 0; i < 6; ++i)
+        t.q[i] += smem[w].q[i];
+      t.non_finite += smem[w].non_finite;
+    }
+    p = t;
+  }
+}
+
+/**
+ * One pass over the interleaved cloud.  Thread i handles vertices i, i + stride, ... (fixed grid => fixed summation
+ * order => bit-reproducible moments).  Moments are taken about the first vertex (pivot) to avoid cancellation for
+ * meshes far from the origin.  The last block to finish folds the block partials in index order.
+ */
+__global__ void __launch_bounds__(kMomentThreads)
+    k_ingest_moments(const uint8_t* __restrict__ blob, unsigned long long V, unsigned point_step, unsigned off_xyz,
+                     int off_nrm, float4* __restrict__ pos, float4* __restrict__ nrm, MomentPartial* partials,
+                     unsigned* done_counter)
+{
+  __shared__ MomentPartial s_part[kMomentThreads / 32];
+  __shared__ bool s_last;
+
+  const float* piv = reinterpret_cast<const float*>(blob + off_xyz);
+  const double px = piv[0], py = piv[1], pz = piv[2];
+
+  MomentPartial p;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    p.s[i] = 0.0;
+    p.mn[i] = FLT_MAX;
+    p.mx[i] = -FLT_MAX;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    p.q[i] = 0.0;
+  p.non_finite = 0;
+
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
+  {
+    const uint8_t* rec = blob + v * point_step;
+    const float* f = reinterpret_cast<const float*>(rec + off_xyz);
+    const float x = __ldg(f), y = __ldg(f + 1), z = __ldg(f + 2);
+    pos[v] = make_float4(x, y, z, 0.f);
+    if (off_nrm >= 0)
+    {
+      const float* g = reinterpret_cast<const float*>(rec + off_nrm);
+      nrm[v] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), 0.f);
+    }
+    if (!(isfinite(x) && isfinite(y) && isfinite(z)))
+    {
+      ++p.non_finite;
+      continue;
+    }
+    const double dx = static_cast<double>(x) - px, dy = static_cast<double>(y) - py, dz = static_cast<double>(z) - pz;
+    p.s[0] += dx;
+    p.s[1] += dy;
+    p.s[2] += dz;
+    p.q[0] += dx * dx;
+    p.q[1] += dx * dy;
+    p.q[2] += dx * dz;
+    p.q[3] += dy * dy;
+    p.q[4] += dy * dz;
+    p.q[5] += dz * dz;
+    p.mn[0] = fminf(p.mn[0], x);
+    p.mn[1] = fminf(p.mn[1], y);
+    p.mn[2] = fminf(p.mn[2], z);
+    p.mx[0] = fmaxf(p.mx[0], x);
+    p.mx[1] = fmaxf(p.mx[1], y);
+    p.mx[2] = fmaxf(p.mx[2], z);
+  }
+
+  blockReducePartial(p, s_part);
+  if (threadIdx.x == 0)
+  {
+    partials[blockIdx.x] = p;
+    __threadfence();
+    const unsigned ticket = atomicAdd(done_counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+
+  // final fold by the last block: thread t sums partials t, t + blockDim, ... then the same fixed tree
+  MomentPartial t;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    t.s[i] = 0.0;
+    t.mn[i] = FLT_MAX;
+    t.mx[i] = -FLT_MAX;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    t.q[i] = 0.0;
+  t.non_finite = 0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+  {
+    const MomentPartial o = partials[b];
+    for (int i = 0; i < 3; ++i)
+    {
+      t.s[i] += o.s[i];
+      t.mn[i] = fminf(t.mn[i], o.mn[i]);
+      t.mx[i] = fmaxf(t.mx[i], o.mx[i]);
+    }
+    for (int i = 0; i < 6; ++i)
+      t.q[i] += o.q[i];
+    t.non_finite += o.non_finite;
+  }
+  __syncthreads();
+  blockReducePartial(t, s_part);
+  if (threadIdx.x == 0)
+  {
+    partials[gridDim.x] = t;  // slot after the block partials holds the total
+    *done_counter = 0;
+  }
+}
+
+/** Float extents in the PCA frame: proj_c = e_c . (x - mean) with Eigen's 3-term order a0 + (a1 + a2); min/max are
+ *  order independent so any reduction tree reproduces pcl::getMinMax3D exactly. */
+__global__ void __launch_bounds__(256)
+    k_extents(const float4* __restrict__ pos, unsigned long long V, float mx_, float my_, float mz_, float e00, float e01,
+              float e02, float e10, float e11, float e12, float e20, float e21, float e22, float* partial /*[grid][6]*/,
+              unsigned* done_counter, float* out6)
+{
+  __shared__ float s_mn[3][8], s_mx[3][8];
+  __shared__ bool s_last;
+  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
+  {
+    const float4 p = __ldg(pos + v);
+    const float dx = __fsub_rn(p.x, mx_), dy = __fsub_rn(p.y, my_), dz = __fsub_rn(p.z, mz_);
+    const float p0 = __fadd_rn(__fmul_rn(e00, dx), __fadd_rn(__fmul_rn(e01, dy), __fmul_rn(e02, dz)));
+    const float p1 = __fadd_rn(__fmul_rn(e10, dx), __fadd_rn(__fmul_rn(e11, dy), __fmul_rn(e12, dz)));
+    const float p2 = __fadd_rn(__fmul_rn(e20, dx), __fadd_rn(__fmul_rn(e21, dy), __fmul_rn(e22, dz)));
+    mn[0] = fminf(mn[0], p0);
+    mx[0] = fmaxf(mx[0], p0);
+    mn[1] = fminf(mn[1], p1);
+    mx[1] = fmaxf(mx[1], p1);
+    mn[2] = fminf(mn[2], p2);
+    mx[2] = fmaxf(mx[2], p2);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+  {
+    mn[c] = warpMin(mn[c]);
+    mx[c] = warpMax(mx[c]);
+    if (lane == 0)
+    {
+      s_mn[c][warp] = mn[c];
+      s_mx[c][warp] = mx[c];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    for (int c = 0; c < 3; ++c)
+    {
+      float a = s_mn[c][0], b = s_mx[c][0];
+      for (int w = 1; w < (blockDim.x >> 5); ++w)
+      {
+        a = fminf(a, s_mn[c][w]);
+        b = fmaxf(b, s_mx[c][w]);
+      }
+      partial[blockIdx.x * 6 + c] = a;
+      partial[blockIdx.x * 6 + 3 + c] = b;
+    }
+    __threadfence();
+    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+  if (threadIdx.x < 6)
+  {
+    const bool is_max = threadIdx.x >= 3;
+    float a = is_max ? -FLT_MAX : FLT_MAX;
+    for (unsigned b = 0; b < gridDim.x; ++b)
+    {
+      const float v = partial[b * 6 + threadIdx.x];
+      a = is_max ? fmaxf(a, v) : fminf(a, v);
+    }
+    out6[threadIdx.x] = a;
+  }
+  if (threadIdx.x == 0)
+    *done_counter = 0;
+}
+
+/**
+ * K_v = the largest lattice index k in [0, P) whose plane scalar at vertex v is >= 0, or -1.  The scalar
+ * n . (x - (start + (k s) n)) evaluated with the reference's operation order is non-increasing in k (each rounding is
+ * monotone), so "inside" is a prefix of the planes and one integer per vertex encodes the whole per-plane sweep of
+ * vtkCutter.  A triangle is cut by plane k  <=>  min K < k <= max K over its vertices, with case bit i = (k <= K_i).
+ */
+__global__ void __launch_bounds__(256) k_classify(const float4* __restrict__ pos, unsigned long long V, LatticeDev L,
+                                                  int* __restrict__ vertK)
+{
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  const long long P = L.num_planes;
+  for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
+  {
+    const float4 p = __ldg(pos + v);
+    // estimate
+    const double d = L.n[0] * (static_cast<double>(p.x) - L.start[0]) + L.n[1] * (static_cast<double>(p.y) - L.start[1]) +
+                     L.n[2] * (static_cast<double>(p.z) - L.start[2]);
+    double q = floor(d / L.spacing);
+    q = fmin(fmax(q, -1.0), static_cast<double>(P - 1));
+    long long k = static_cast<long long>(q);
+    // exact fix-up against the reference's own expression
+    while (k + 1 < P && planeScalar(L, planeOrigin(L, k + 1), p.x, p.y, p.z) >= 0.0)
+      ++k;
+    while (k >= 0 && !(planeScalar(L, planeOrigin(L, k), p.x, p.y, p.z) >= 0.0))
+      --k;
+    vertK[v] = static_cast<int>(k);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_set_normals(const float* __restrict__ packed, unsigned long long V, float4* __restrict__ nrm)
+{
+  const unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v < V)
+    nrm[v] = make_float4(packed[3 * v], packed[3 * v + 1], packed[3 * v + 2], 0.f);
+}
+
+__global__ void __launch_bounds__(256) k_pack_out(const float4* __restrict__ src, unsigned long long V, float* __restrict__ dst)
+{
+  const unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v < V)
+  {
+    const float4 a = src[v];
+    dst[3 * v] = a.x;
+    dst[3 * v + 1] = a.y;
+    dst[3 * v + 2] = a.z;
+  }
+}
+
+inline int gridFor(unsigned long long n, int threads, int cap)
+{
+  unsigned long long b = (n + threads - 1) / threads;
+  if (b < 1)
+    b = 1;
+  if (b > static_cast<unsigned long long>(cap))
+    b = cap;
+  return static_cast<int>(b);
+}
+}  // namespace
+
+void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, int32_t off_nrm)
+{
+  const int grid = gridFor(c->V, kMomentThreads, kMomentBlocks);
+  c->partials.ensure(sizeof(MomentPartial) * (kMomentBlocks + 1));
+  k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz, off_nrm,
+                                                           c->pos.as<float4>(), c->nrm.as<float4>(),
+                                                           c->partials.as<MomentPartial>(), c->counters.as<unsigned>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
+void launchExtents(nb2_context* c, const float mean[3], const float E[9])
+{
+  const int grid = gridFor(c->V, 256, c->sm_count * 8);
+  c->extents.ensure(sizeof(float) * (6 * static_cast<size_t>(grid) + 8));
+  float* partial = c->extents.as<float>() + 8;
+  // E is column-major: axis c = (E[3c], E[3c+1], E[3c+2])
+  k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, mean[0], mean[1], mean[2], E[0], E[1], E[2], E[3],
+                                         E[4], E[5], E[6], E[7], E[8], partial, c->counters.as<unsigned>() + 1,
+                                         c->extents.as<float>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
+void launchClassify(nb2_context* c, const LatticeDev& L)
+{
+  c->vertK.ensure(sizeof(int) * c->V);
+  const int grid = gridFor(c->V, 256, c->sm_count * 16);
+  k_classify<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, L, c->vertK.as<int>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
+void launchSetNormals(nb2_context* c, const float* dev_packed)
+{
+  const int grid = static_cast<int>((c->V + 255) / 256);
+  k_set_normals<<<grid, 256, 0, c->stream>>>(dev_packed, c->V, c->nrm.as<float4>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
+void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed)
+{
+  const int grid = static_cast<int>((c->V + 255) / 256);
+  if (xyz_packed)
+  {
+    k_pack_out<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, xyz_packed);
+    ++c->launches;
+  }
+  if (nrm_packed)
+  {
+    k_pack_out<<<grid, 256, 0, c->stream>>>(c->nrm.as<float4>(), c->V, nrm_packed);
+    ++c->launches;
+  }
+  NB2_CUDA(cudaGetLastError());
+}
+
+}  // namespace nb2

@@ -1,0 +1,224 @@
+// Internal declarations shared by the host side and the CUDA kernels of libnoether_b200.so.
+#pragma once
+#include "../../include/noether_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace nb2
+{
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+struct Error
+{
+  int status;
+  std::string msg;
+};
+void setLastError(const std::string& msg);
+[[noreturn]] void fail(int status, const std::string& msg);
+
+#define NB2_CUDA(expr)                                                                                                 \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t err__ = (expr);                                                                                        \
+    if (err__ != cudaSuccess)                                                                                          \
+      ::nb2::fail(NB2_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " + __FILE__ + ":" +    \
+                                    std::to_string(__LINE__) + " (" #expr ")");                                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// growable device buffer (arena slot).  Capacity only grows; contents are not preserved across growth.
+// ---------------------------------------------------------------------------------------------------------------
+struct DevBuf
+{
+  void* ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const
+  {
+    return static_cast<T*>(ptr);
+  }
+};
+
+struct PinnedBuf
+{
+  void* ptr = nullptr;
+  size_t cap = 0;
+  void ensure(size_t bytes);
+  void release();
+  template <typename T>
+  T* as() const
+  {
+    return static_cast<T*>(ptr);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// device-side PODs
+// ---------------------------------------------------------------------------------------------------------------
+/** fp64 partial moments of one thread block: sums of (x - pivot), of its outer product, and float AABB */
+struct MomentPartial
+{
+  double s[3];
+  double q[6];  // xx xy xz yy yz zz
+  float mn[3];
+  float mx[3];
+  unsigned long long non_finite;
+};
+
+/** Lattice constants handed to kernels by value (plane_slicer_raster_planner.cpp:584-602) */
+struct LatticeDev
+{
+  double n[3];      // cut_normal
+  double start[3];  // start_loc
+  double spacing;   // line_spacing_
+  double dir[3];    // cut_direction (orientation / ordering of chains)
+  long long num_planes;
+  long long plane_begin;  // slab handled by this launch
+  long long plane_end;
+};
+
+constexpr int kMomentBlocks = 1184;  // fixed (not SM-count derived) so that sums are identical on any device
+constexpr int kMomentThreads = 256;
+
+/** Per-stage CUDA-event timing */
+struct StageTimer
+{
+  std::vector<const char*> names;
+  std::vector<cudaEvent_t> events;  // events[i] .. events[i+1] brackets stage i
+  size_t used = 0;
+  void begin(cudaStream_t s);
+  void mark(const char* name, cudaStream_t s);
+  int collect(const char** out_names, float* ms, int capacity) const;
+  void destroy();
+};
+
+}  // namespace nb2
+
+// ---------------------------------------------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------------------------------------------
+struct nb2_context
+{
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  mutable std::mutex mu;
+  uint64_t launches = 0;
+
+  // resident mesh (SoA)
+  uint64_t V = 0, F = 0;
+  bool has_normals = false;
+  nb2::DevBuf blob;      // staging copy of the interleaved cloud
+  nb2::DevBuf pos;       // float4[V]  (x, y, z, unused)
+  nb2::DevBuf nrm;       // float4[V]
+  nb2::DevBuf tri;       // uint32[3F]
+  // moments / frame
+  nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
+  nb2::DevBuf extents;   // float[6] min/max in PCA frame (+ block partials)
+  nb2::DevBuf counters;  // misc device counters (zeroed per plan)
+  bool pca_valid = false;
+  nb2_pca pca{};
+  // slicing workspace
+  nb2::DevBuf vertK;       // int32[V]
+  nb2::DevBuf planeCnt;    // uint32[P + 1]
+  nb2::DevBuf planeOff;    // uint32[P + 1]
+  nb2::DevBuf planeCursor; // uint32[P]
+  nb2::DevBuf bucket;      // uint32[H] triangle ids grouped by plane
+  nb2::DevBuf lookback;    // uint64[P] decoupled look-back status
+  nb2::DevBuf planeMeta;   // uint32[2 * P]: waypoints, segments of each plane
+  nb2::DevBuf outPos;      // float[3 * Wcap]
+  nb2::DevBuf outNrm;      // float[3 * Wcap]
+  nb2::DevBuf outEdge;     // uint32[2 * Wcap]
+  nb2::DevBuf outSegLen;   // uint32[Scap]
+  nb2::DevBuf linkScratch; // global scratch for planes too large for shared memory
+  // normals workspace
+  nb2::DevBuf faceNrm;   // float4[F]
+  nb2::DevBuf valence;   // uint32[V + 1]
+  nb2::DevBuf csrOff;    // uint32[V + 1]
+  nb2::DevBuf csrCursor; // uint32[V]
+  nb2::DevBuf csrAdj;    // uint32[3F]
+  nb2::DevBuf scanState; // uint64[num tiles] look-back status for the generic scan
+  // host staging
+  nb2::PinnedBuf hostSmall;  // small read-backs
+  struct HostBlock
+  {
+    void* ptr;
+    size_t cap;
+  };
+  std::vector<HostBlock> hostPool;  // pinned blocks recycled between results
+
+  nb2_lattice last_lattice{};
+  bool have_lattice = false;
+  nb2::StageTimer timer;
+
+  // NCCL (dlopen'ed lazily)
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// the result: one pinned host block carved into the SoA arrays (device -> host copies land in their final place)
+// ---------------------------------------------------------------------------------------------------------------
+struct nb2_result
+{
+  nb2_context* owner = nullptr;  // the block returns to the owner's pool on nb2_result_free
+  void* block = nullptr;
+  size_t block_cap = 0;
+  uint64_t n_paths = 0, n_segments = 0, n_waypoints = 0;
+  uint32_t* path_offsets = nullptr;     // n_paths + 1
+  uint32_t* segment_offsets = nullptr;  // n_segments + 1
+  int64_t* path_plane = nullptr;        // n_paths
+  float* positions = nullptr;           // 3 W
+  float* normals = nullptr;             // 3 W
+  uint32_t* edge_lo = nullptr;          // W (or null)
+  uint32_t* edge_hi = nullptr;
+  double* poses = nullptr;              // 16 W, only for legacy (resampled) results
+  bool post_ops_applied = false;
+  bool legacy = false;
+  nb2_plan_params params{};
+  nb2_lattice lattice{};
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel launchers (implemented in the .cu files)
+// ---------------------------------------------------------------------------------------------------------------
+namespace nb2
+{
+void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, int32_t off_nrm);
+void launchExtents(nb2_context* c, const float mean[3], const float evecs[9]);
+void launchClassify(nb2_context* c, const LatticeDev& L);
+void launchCountHits(nb2_context* c, const LatticeDev& L);
+void launchScanPlanes(nb2_context* c, const LatticeDev& L);  // writes {H, n_max} to counters[0..1]
+void launchFillBuckets(nb2_context* c, const LatticeDev& L);
+void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t w_cap, uint64_t s_cap, int emit_edges);
+void launchSetNormals(nb2_context* c, const float* dev_packed);
+void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);
+void launchVertexNormals(nb2_context* c);
+void launchValidateTriangles(nb2_context* c);
+
+// host-side frame arithmetic (frame.cpp)
+void finalizeMoments(const MomentPartial& total, uint64_t V, const float pivot[3], nb2_pca& out);
+void eigenSolver3f(const float A[9], float evals[3], float evecs[9]);
+void principalAxisDirection(const nb2_pca& pca, double rotation_offset, double out[3]);
+int makeLattice(const nb2_pca& pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
+                nb2_lattice& L);
+
+// result storage (api.cu)
+nb2_result* allocResult(nb2_context* c, uint64_t n_paths, uint64_t n_segments, uint64_t n_waypoints, bool edges, bool poses);
+void freeResult(nb2_result* r);
+
+// host-side tool path post-ops (toolpath.cpp)
+void rasterOrganization(nb2_result*& r);
+void expandPoses(const nb2_result& r, double* out16);
+void legacyModifiers(nb2_result*& r, double point_spacing, double min_segment_size, double min_hole_size);
+}  // namespace nb2

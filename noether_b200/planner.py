@@ -1,0 +1,427 @@
+"""Host-side mirror of the reference's component interface for the raster-slicing path, over the C ABI.
+
+Same names, argument meaning and error behaviour as noether_tpp 0.16.0:
+
+  PlaneSlicerRasterPlanner / PlaneSlicerLegacyRasterPlanner   tool_path_planners/raster/plane_slicer_raster_planner.h,
+                                                             plane_slicer_legacy_raster_planner.h; RasterPlanner::plan
+  PrincipalAxisDirectionGenerator, FixedDirectionGenerator    raster/direction_generators/*.h (DirectionGenerator::generate)
+  CentroidOriginGenerator, FixedOriginGenerator               raster/origin_generators/*.h (OriginGenerator::generate)
+  NormalsFromMeshFacesMeshModifier                            mesh_modifiers/normals_from_mesh_faces_modifier.h
+  Factory.create_*(config)                                    plugin_interface.h:106-129, plugins.cpp (aliases + YAML keys)
+
+The production drop-in is the C++ boost_plugin_loader shim in plugin/b200_plugins.cpp; this module is the same thing
+for Python callers, tests and the benchmark.  Everything computes on the GPU through libnoether_b200.so; nothing here
+falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _capi
+from .meshes import MeshBlob
+
+
+class Context:
+    """One nb2_context (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.load()
+        h = C.c_void_p()
+        _capi.check(self._lib.nb2_context_create(device, C.byref(h)))
+        self._h = h
+        self._mesh_key = None
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.nb2_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mesh -------------------------------------------------------------------------------------------------
+    def upload(self, mesh: MeshBlob, force: bool = False):
+        key = (id(mesh.data), id(mesh.tri), mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal)
+        if not force and key == self._mesh_key:
+            return
+        self._mesh_key = None
+        data = np.ascontiguousarray(mesh.data)
+        tri = np.ascontiguousarray(mesh.tri, dtype=np.uint32)
+        mv = _capi.MeshView(data.ctypes.data, mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal, 0,
+                            tri.ctypes.data if tri.size else None, tri.shape[0])
+        _capi.check(self._lib.nb2_mesh_upload(self._h, C.byref(mv)))
+        self._mesh_key = key
+        self._keep = (data, tri)
+
+    def upload_raw(self, data_ptr: int, n_vertices: int, point_step: int, off_xyz: int, off_normal: int,
+                   tri_ptr: int, n_triangles: int):
+        """Upload from raw host pointers (e.g. pinned buffers owned by the caller)."""
+        self._mesh_key = None
+        mv = _capi.MeshView(data_ptr, n_vertices, point_step, off_xyz, off_normal, 0, tri_ptr, n_triangles)
+        _capi.check(self._lib.nb2_mesh_upload(self._h, C.byref(mv)))
+
+    def set_normals(self, normals: np.ndarray):
+        n = np.ascontiguousarray(normals, dtype=np.float32)
+        _capi.check(self._lib.nb2_mesh_set_normals(self._h, n.ctypes.data))
+
+    def download(self, n_vertices: int):
+        xyz = np.zeros((n_vertices, 3), np.float32)
+        nrm = np.zeros((n_vertices, 3), np.float32)
+        _capi.check(self._lib.nb2_mesh_download(self._h, xyz.ctypes.data, nrm.ctypes.data))
+        return xyz, nrm
+
+    # -- frame ------------------------------------------------------------------------------------------------
+    def pca(self) -> _capi.Pca:
+        out = _capi.Pca()
+        _capi.check(self._lib.nb2_mesh_pca(self._h, C.byref(out)))
+        return out
+
+    def principal_axis_direction(self, rotation_offset: float) -> np.ndarray:
+        out = (C.c_double * 3)()
+        _capi.check(self._lib.nb2_principal_axis_direction(self._h, rotation_offset, out))
+        return np.array(out)
+
+    def centroid_origin(self) -> np.ndarray:
+        out = (C.c_double * 3)()
+        _capi.check(self._lib.nb2_centroid_origin(self._h, out))
+        return np.array(out)
+
+    def normals_from_mesh_faces(self, n_vertices: int, download: bool = True):
+        out = np.zeros((n_vertices, 3), np.float32) if download else None
+        _capi.check(self._lib.nb2_normals_from_mesh_faces(self._h, out.ctypes.data if download else None))
+        return out
+
+    # -- planning ---------------------------------------------------------------------------------------------
+    def plan(self, params: _capi.PlanParams) -> "ToolPaths":
+        r = C.c_void_p()
+        _capi.check(self._lib.nb2_plan(self._h, C.byref(params), C.byref(r)))
+        return ToolPaths(self, r)
+
+    def slice(self, lattice: _capi.Lattice, plane_begin: int = 0, plane_end: int | None = None) -> "ToolPaths":
+        r = C.c_void_p()
+        pe = _capi.NB2_ALL_PLANES if plane_end is None else plane_end
+        _capi.check(self._lib.nb2_slice(self._h, C.byref(lattice), plane_begin, pe, C.byref(r)))
+        return ToolPaths(self, r)
+
+    def last_lattice(self) -> _capi.Lattice:
+        out = _capi.Lattice()
+        _capi.check(self._lib.nb2_last_lattice(self._h, C.byref(out)))
+        return out
+
+    def timings(self) -> dict:
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = self._lib.nb2_last_timings(self._h, names, ms, 32)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.nb2_kernel_launches(self._h))
+
+    # -- multi-GPU --------------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * _capi.NB2_UNIQUE_ID_BYTES)()
+        _capi.check(_capi.load().nb2_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world_size: int):
+        buf = (C.c_uint8 * _capi.NB2_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _capi.check(self._lib.nb2_comm_init(self._h, buf, rank, world_size))
+
+    def gather(self, local: "ToolPaths", root: int = 0) -> "ToolPaths | None":
+        out = C.c_void_p()
+        _capi.check(self._lib.nb2_result_gather(self._h, local._r, root, C.byref(out)))
+        return ToolPaths(self, out) if out.value else None
+
+
+def make_lattice(pca: _capi.Pca, direction, origin, line_spacing: float, bidirectional: bool = True) -> _capi.Lattice:
+    d = (C.c_double * 3)(*[float(v) for v in direction])
+    o = (C.c_double * 3)(*[float(v) for v in origin])
+    out = _capi.Lattice()
+    _capi.check(_capi.load().nb2_make_lattice(C.byref(pca), d, o, line_spacing, int(bidirectional), C.byref(out)))
+    return out
+
+
+class ToolPaths:
+    """noether::ToolPaths as returned by the C ABI: SoA arrays (views into the result's pinned block)."""
+
+    def __init__(self, ctx: Context, handle):
+        self._ctx = ctx
+        self._lib = ctx._lib
+        self._r = handle
+        v = _capi.ResultView()
+        _capi.check(self._lib.nb2_result_get(self._r, C.byref(v)))
+        self.n_paths, self.n_segments, self.n_waypoints = int(v.n_paths), int(v.n_segments), int(v.n_waypoints)
+        P, S, W = self.n_paths, self.n_segments, self.n_waypoints
+
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).view(dt)
+
+        self.path_offsets = arr(v.path_offsets, P + 1, np.uint32)
+        self.segment_offsets = arr(v.segment_offsets, S + 1, np.uint32)
+        self.path_plane = arr(v.path_plane, P, np.int64)
+        self.positions = arr(v.positions, 3 * W, np.float32).reshape(-1, 3)
+        self.normals = arr(v.normals, 3 * W, np.float32).reshape(-1, 3)
+        self.edge_lo = arr(v.edge_lo, W, np.uint32) if v.edge_lo else None
+        self.edge_hi = arr(v.edge_hi, W, np.uint32) if v.edge_hi else None
+        self.post_ops_applied = bool(v.raster_post_ops_applied)
+        self.legacy = bool(v.legacy)
+
+    def free(self):
+        if self._r:
+            self._lib.nb2_result_free(self._r)
+            self._r = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self.n_paths
+
+    def segments_per_path(self) -> np.ndarray:
+        return np.diff(self.path_offsets.astype(np.int64))
+
+    def poses(self) -> np.ndarray:
+        """(W, 4, 4) float64, [row, col] — Eigen::Isometry3d matrices"""
+        out = np.zeros((self.n_waypoints, 16), np.float64)
+        _capi.check(self._lib.nb2_result_poses(self._r, out.ctypes.data))
+        return out.reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+    def nested(self):
+        """list[tool path] of list[segment] of (n, 4, 4) pose arrays — the shape of noether::ToolPaths"""
+        poses = self.poses()
+        out = []
+        for p in range(self.n_paths):
+            path = []
+            for s in range(int(self.path_offsets[p]), int(self.path_offsets[p + 1])):
+                path.append(poses[int(self.segment_offsets[s]):int(self.segment_offsets[s + 1])])
+            out.append(path)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# components (reference interface)
+# ---------------------------------------------------------------------------------------------------------------------
+_default_contexts: dict[int, Context] = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_contexts:
+        _default_contexts[device] = Context(device)
+    return _default_contexts[device]
+
+
+class DirectionGenerator:
+    def generate(self, mesh: MeshBlob) -> np.ndarray:  # noqa: D401
+        raise NotImplementedError
+
+
+class OriginGenerator:
+    def generate(self, mesh: MeshBlob) -> np.ndarray:
+        raise NotImplementedError
+
+
+class FixedDirectionGenerator(DirectionGenerator):
+    """direction_generators/fixed_direction_generator.cpp: returns the configured direction (host only)"""
+
+    def __init__(self, direction):
+        self.direction = np.asarray(direction, np.float64)
+
+    def generate(self, mesh):
+        return self.direction
+
+
+class FixedOriginGenerator(OriginGenerator):
+    def __init__(self, origin=(0.0, 0.0, 0.0)):
+        self.origin = np.asarray(origin, np.float64)
+
+    def generate(self, mesh):
+        return self.origin
+
+
+class PrincipalAxisDirectionGenerator(DirectionGenerator):
+    """principal_axis_direction_generator.cpp:14-26 — AngleAxis(rotation_offset, e2) * e1 from the device PCA"""
+
+    def __init__(self, rotation_offset: float = 0.0, context: Context | None = None):
+        self.rotation_offset = float(rotation_offset)
+        self._ctx = context
+
+    def generate(self, mesh):
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        return ctx.principal_axis_direction(self.rotation_offset)
+
+
+class CentroidOriginGenerator(OriginGenerator):
+    """centroid_origin_generator.cpp:8-17 — mean of the vertices from the device moment reduction"""
+
+    def __init__(self, context: Context | None = None):
+        self._ctx = context
+
+    def generate(self, mesh):
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        return ctx.centroid_origin()
+
+
+class PlaneSlicerRasterPlanner:
+    """RasterPlanner::plan for the plane slicer (raster_planner.cpp:16-35, plane_slicer_raster_planner.cpp:518-631)"""
+
+    def __init__(self, dir_gen: DirectionGenerator, origin_gen: OriginGenerator, context: Context | None = None):
+        self.dir_gen = dir_gen
+        self.origin_gen = origin_gen
+        self.line_spacing = None  # the reference leaves it unset until setLineSpacing (raster_planner.h:85)
+        self.bidirectional = True
+        self._ctx = context
+        self.emit_edges = True
+        self.raster_post_ops = True
+
+    def set_line_spacing(self, line_spacing: float):
+        self.line_spacing = float(line_spacing)
+
+    def generate_rasters_bidirectionally(self, bidirectional: bool):
+        self.bidirectional = bool(bidirectional)
+
+    def _params(self, mesh) -> _capi.PlanParams:
+        if self.line_spacing is None:
+            raise ValueError("line_spacing has not been set (RasterPlanner::setLineSpacing)")
+        p = _capi.PlanParams()
+        _capi.load().nb2_plan_params_default(C.byref(p))
+        p.line_spacing = self.line_spacing
+        p.bidirectional = int(self.bidirectional)
+        p.emit_edges = int(self.emit_edges)
+        p.raster_post_ops = int(self.raster_post_ops)
+        if isinstance(self.dir_gen, PrincipalAxisDirectionGenerator):
+            p.direction_mode = _capi.NB2_DIRECTION_PRINCIPAL_AXIS
+            p.rotation_offset = self.dir_gen.rotation_offset
+        else:
+            p.direction_mode = _capi.NB2_DIRECTION_EXPLICIT
+            d = self.dir_gen.generate(mesh)
+            p.direction[:] = [float(v) for v in d]
+        if isinstance(self.origin_gen, CentroidOriginGenerator):
+            p.origin_mode = _capi.NB2_ORIGIN_CENTROID
+        else:
+            p.origin_mode = _capi.NB2_ORIGIN_EXPLICIT
+            o = self.origin_gen.generate(mesh)
+            p.origin[:] = [float(v) for v in o]
+        return p
+
+    def plan(self, mesh: MeshBlob, shard_rank: int = 0, shard_count: int = 1) -> ToolPaths:
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        p = self._params(mesh)
+        p.shard_rank, p.shard_count = shard_rank, shard_count
+        return ctx.plan(p)
+
+
+class PlaneSlicerLegacyRasterPlanner(PlaneSlicerRasterPlanner):
+    """plane_slicer_legacy_raster_planner.cpp:10-33"""
+
+    def __init__(self, dir_gen, origin_gen, point_spacing: float, min_segment_size: float, min_hole_size: float,
+                 context: Context | None = None):
+        super().__init__(dir_gen, origin_gen, context)
+        self.point_spacing = float(point_spacing)
+        self.min_segment_size = float(min_segment_size)
+        self.min_hole_size = float(min_hole_size)
+
+    def _params(self, mesh):
+        p = super()._params(mesh)
+        p.legacy = 1
+        p.point_spacing = self.point_spacing
+        p.min_segment_size = self.min_segment_size
+        p.min_hole_size = self.min_hole_size
+        return p
+
+
+class NormalsFromMeshFacesMeshModifier:
+    """normals_from_mesh_faces_modifier.cpp:15-46.  Returns [mesh] whose cloud is concatenateFields(mesh.cloud,
+    normals): a 32-byte pcl::Normal record (normal_x0 normal_y4 normal_z8 curvature16) followed by the input's
+    fields (the input's own normal fields, if any, are overridden by name)."""
+
+    def __init__(self, context: Context | None = None):
+        self._ctx = context
+
+    def modify(self, mesh: MeshBlob) -> list[MeshBlob]:
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        normals = ctx.normals_from_mesh_faces(mesh.n_vertices)
+        n = mesh.n_vertices
+        step = 32 + mesh.point_step
+        data = np.zeros(n * step, np.uint8)
+        rec = data.reshape(n, step)
+        rec[:, 0:12] = normals.view(np.uint8).reshape(n, 12)
+        rec[:, 32:] = np.asarray(mesh.data).reshape(n, mesh.point_step)
+        out = MeshBlob(data, n, step, 32 + mesh.off_xyz, 0, mesh.tri)
+        return [out]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Factory (aliases + YAML keys of plugins.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _member(config: dict, key: str):
+    if key not in config:
+        # serialization.h:10-16
+        raise RuntimeError(f"Required member '{key}' not found in YAML node")
+    return config[key]
+
+
+def _vec3(node) -> np.ndarray:
+    if isinstance(node, dict):
+        return np.array([_member(node, "x"), _member(node, "y"), _member(node, "z")], np.float64)
+    return np.asarray(node, np.float64)
+
+
+class Factory:
+    """noether::Factory for the aliases on this path (plugin_interface.h:106-129)."""
+
+    def __init__(self, context: Context | None = None):
+        self._ctx = context
+
+    def create_direction_generator(self, config: dict) -> DirectionGenerator:
+        name = _member(config, "name")
+        if name == "PrincipalAxis":
+            return PrincipalAxisDirectionGenerator(_member(config, "rotation_offset"), self._ctx)
+        if name == "FixedDirection":
+            return FixedDirectionGenerator(_vec3(_member(config, "direction")))
+        raise RuntimeError(f"Failed to find plugin '{name}' in section 'dg'")
+
+    def create_origin_generator(self, config: dict) -> OriginGenerator:
+        name = _member(config, "name")
+        if name == "Centroid":
+            return CentroidOriginGenerator(self._ctx)
+        if name == "FixedOrigin":
+            return FixedOriginGenerator(_vec3(_member(config, "origin")))
+        raise RuntimeError(f"Failed to find plugin '{name}' in section 'og'")
+
+    def create_tool_path_planner(self, config: dict) -> PlaneSlicerRasterPlanner:
+        name = _member(config, "name")
+        if name not in ("PlaneSlicer", "PlaneSlicerLegacy"):
+            raise RuntimeError(f"Failed to find plugin '{name}' in section 'tpp'")
+        dir_gen = self.create_direction_generator(_member(config, "direction_generator"))
+        origin_gen = self.create_origin_generator(_member(config, "origin_generator"))
+        if name == "PlaneSlicer":
+            tpp = PlaneSlicerRasterPlanner(dir_gen, origin_gen, self._ctx)
+        else:
+            tpp = PlaneSlicerLegacyRasterPlanner(dir_gen, origin_gen, float(_member(config, "point_spacing")),
+                                                 float(_member(config, "min_segment_size")),
+                                                 float(_member(config, "min_hole_size")), self._ctx)
+        tpp.set_line_spacing(float(_member(config, "line_spacing")))
+        tpp.generate_rasters_bidirectionally(bool(_member(config, "bidirectional")))
+        return tpp
+
+    def create_mesh_modifier(self, config: dict) -> NormalsFromMeshFacesMeshModifier:
+        name = _member(config, "name")
+        if name == "NormalsFromMeshFaces":
+            return NormalsFromMeshFacesMeshModifier(self._ctx)
+        raise RuntimeError(f"Failed to find plugin '{name}' in section 'mesh'")
+

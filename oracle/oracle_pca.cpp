@@ -70,7 +70,11 @@ static void tridiagonalQrStep(float* diag, float* subdiag, int start, int end, f
   else if (e != 0.f)
   {
     const float e2 = e * e;
-    const float h = ::hypotf(td, e);
+    // numext::hypot -> internal::positive_real_hypot(|x|, |y|) = p * sqrt(1 + (q/p)^2) (Eigen/src/Core/MathFunctionsImpl.h)
+    const float ax = std::abs(td), ay = std::abs(e);
+    const float pmax = std::max(ax, ay);
+    const float qp = pmax == 0.f ? 0.f : std::min(ay, ax) / pmax;
+    const float h = pmax == 0.f ? 0.f : pmax * std::sqrt(1.f + qp * qp);
     if (e2 == 0.f)
       mu -= e / ((td + (td > 0.f ? h : -h)) / e);
     else

@@ -1,0 +1,419 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Every test needs a B200: -m gpu."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import assert_same_paths, bits, capi_lattice_from_oracle, oracle_pca_from_capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _wavy_mesh(nx, ny, layout="PointNormal", hole=False, **kw):
+    import oracle
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(nx, ny, **kw)
+    if hole:
+        xyz, tri = meshes.cut_hole(xyz, tri)
+    nrm = oracle.normals_from_mesh_faces(xyz, tri)
+    return meshes.pack_blob(xyz, nrm, tri, layout), xyz, nrm, tri
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K0: ingest
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["PointNormal", "NormalsFirst", "Packed24"])
+def test_ingest_roundtrip(ctx, orc, layout):
+    blob, xyz, nrm, tri = _wavy_mesh(37, 23, layout)
+    ctx.upload(blob, force=True)
+    gx, gn = ctx.download(blob.n_vertices)
+    np.testing.assert_array_equal(bits(gx), bits(xyz))
+    np.testing.assert_array_equal(bits(gn), bits(nrm))
+
+
+def test_ingest_rejects_bad_input(ctx):
+    from noether_b200 import _capi, meshes
+    xyz, tri = meshes.wavy(4, 4)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (xyz.shape[0], 1))
+    bad = xyz.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(_capi.Nb2Error) as e:
+        ctx.upload(meshes.pack_blob(bad, nrm, tri), force=True)
+    assert e.value.status == _capi.NB2_ERR_NON_FINITE
+    t2 = tri.copy()
+    t2[5, 2] = xyz.shape[0] + 7
+    with pytest.raises(_capi.Nb2Error) as e:
+        ctx.upload(meshes.pack_blob(xyz, nrm, t2), force=True)
+    assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K1: PCA frame, generators
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(40, 25), (200, 160), (313, 97)])
+def test_pca_matches_fp64_oracle(ctx, orc, shape):
+    blob, xyz, nrm, tri = _wavy_mesh(*shape)
+    # move it away from the origin and rotate so no axis is special
+    T = orc.fixture_random_transform(3.0, np.pi)
+    from noether_b200 import meshes
+    xyz = meshes.rigid_transform(xyz, T)
+    blob = meshes.pack_blob(xyz, nrm, tri)
+    ctx.upload(blob, force=True)
+    g = ctx.pca()
+    o = orc.pca(xyz, orc.MOMENTS_F64)
+    # fp64 tree sums differ from the oracle's sequential long-double sums by ~1e-16 relative: after the float cast the
+    # frame is identical
+    np.testing.assert_array_equal(bits(np.array(g.mean)), bits(o.mean))
+    np.testing.assert_array_equal(bits(np.array(g.cov)), bits(o.cov.T.ravel()))
+    np.testing.assert_array_equal(bits(np.array(g.evecs)), bits(o.evecs.T.ravel()))
+    np.testing.assert_array_equal(bits(np.array(g.scales)), bits(o.scales))
+    # and it agrees with the reference-faithful float32 sequential accumulation within float noise
+    f = orc.pca(xyz, orc.MOMENTS_F32_SEQUENTIAL)
+    diag = np.linalg.norm(xyz.max(0) - xyz.min(0))
+    assert np.abs(np.array(g.mean) - f.mean).max() < 1e-5 * diag
+    for i in range(3):
+        c = abs(float(np.dot(np.array(g.evecs).reshape(3, 3)[i], f.evecs[:, i])))
+        assert c > 1 - 1e-6
+    # generators
+    np.testing.assert_array_equal(ctx.centroid_origin(), orc.centroid(xyz, orc.MOMENTS_F64))
+    for rot in (0.0, 0.3, -1.2):
+        np.testing.assert_array_equal(ctx.principal_axis_direction(rot), orc.principal_axis_direction(o, rot))
+
+
+def test_lattice_matches_oracle(ctx, orc, ply_mesh):
+    from noether_b200 import make_lattice
+    ctx.upload(ply_mesh, force=True)
+    g = ctx.pca()
+    o = oracle_pca_from_capi(orc, g)
+    for spacing, bidir, d, org in [(0.1, True, [1, 0, 0], [0, 0, 0]), (1.05, True, [1, 0, 0], [0, 0, 0]),
+                                   (0.37, False, [0.3, 1, 0.1], [5, 5, 0]), (0.05, False, [1, 0, 0], [0, 20, 0])]:
+        a = make_lattice(g, d, org, spacing, bidir)
+        b = orc.make_lattice(o, d, org, spacing, bidir)
+        assert bytes(a) == bytes(b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2: vertex normals
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("permuted", [False, True])
+def test_normals_bit_exact(ctx, orc, permuted):
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(120, 90)
+    if permuted:
+        xyz, tri = meshes.permute(xyz, tri, seed=7)
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob, force=True)
+    g = ctx.normals_from_mesh_faces(blob.n_vertices)
+    o = orc.normals_from_mesh_faces(xyz, tri)
+    np.testing.assert_array_equal(bits(g), bits(o))
+
+
+def test_normals_degenerate_and_isolated(ctx, orc):
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(6, 5)
+    xyz = np.concatenate([xyz, [[9, 9, 9]]]).astype(np.float32)       # isolated vertex -> zero normal
+    tri = np.concatenate([tri, [[0, 0, 1]], [[2, 3, 3]]]).astype(np.uint32)  # degenerate faces add zero
+    # a high-valence fan (> 16 faces at vertex 0)
+    fan = np.array([[0, 8 + i, 9 + i] for i in range(20)], np.uint32)
+    tri = np.concatenate([tri, fan]).astype(np.uint32)
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob, force=True)
+    g = ctx.normals_from_mesh_faces(blob.n_vertices)
+    o = orc.normals_from_mesh_faces(xyz, tri)
+    np.testing.assert_array_equal(bits(g), bits(o))
+    assert np.all(g[-1] == 0)
+
+
+def test_normals_modifier_field_contract(ctx, ply_mesh):
+    # mesh_modifier_utest.cpp:154-183: every input field is still present; normals come first (concatenateFields)
+    import noether_b200 as nb
+    out = nb.NormalsFromMeshFacesMeshModifier(ctx).modify(ply_mesh)
+    assert len(out) == 1
+    m = out[0]
+    assert m.point_step == 32 + ply_mesh.point_step and m.off_normal == 0 and m.off_xyz == 32 + ply_mesh.off_xyz
+    np.testing.assert_array_equal(m.xyz(), ply_mesh.xyz())
+    assert np.allclose(np.linalg.norm(m.normals(), axis=1), 1.0, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3-K6: slicing with an injected lattice -> bit-exact against the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+def _slice_both(ctx, orc, blob, xyz, nrm, tri, spacing, direction, origin, bidirectional=True, mode=None):
+    ctx.upload(blob, force=True)
+    p = orc.pca(xyz, orc.MOMENTS_F64)
+    lat = orc.make_lattice(p, direction, origin, spacing, bidirectional)
+    ref = orc.slice_mesh(xyz, nrm, tri, lat, orc.SLICE_INTENT if mode is None else mode, orc.SCAN_BINNED).flat()
+    gpu = ctx.slice(capi_lattice_from_oracle(lat))
+    return gpu, ref, lat
+
+
+def test_slice_reference_fixture(ctx, orc, ply_mesh):
+    xyz, nrm, tri = ply_mesh.xyz(), ply_mesh.normals(), ply_mesh.tri
+    for spacing in (1.05, 0.1, 0.05):
+        gpu, ref, _ = _slice_both(ctx, orc, ply_mesh, xyz, nrm, tri, spacing, [1, 0, 0], [0, 0, 0])
+        assert_same_paths(gpu, ref, f"ply spacing {spacing}")
+    # the reference's own expectation (tool_path_planner_utest.cpp:151-167)
+    gpu, ref, _ = _slice_both(ctx, orc, ply_mesh, xyz, nrm, tri, 1.05, [1, 0, 0], [0, 0, 0])
+    assert gpu.n_paths == 10
+    assert list(gpu.segments_per_path()[4:7]) == [2, 2, 2]
+
+
+@pytest.mark.parametrize("nx,ny,spacing,hole", [(40, 32, 0.02, False), (64, 50, 0.013, True), (200, 160, 0.005, True),
+                                                (96, 77, 0.0371, False)])
+def test_slice_wavy(ctx, orc, nx, ny, spacing, hole):
+    blob, xyz, nrm, tri = _wavy_mesh(nx, ny, hole=hole)
+    p = orc.pca(xyz, orc.MOMENTS_F64)
+    d = orc.principal_axis_direction(p, 0.0)
+    o = orc.centroid(xyz, orc.MOMENTS_F64)
+    gpu, ref, _ = _slice_both(ctx, orc, blob, xyz, nrm, tri, spacing, d, o)
+    assert ref.num_paths > 5
+    assert_same_paths(gpu, ref, "wavy")
+
+
+def test_slice_vertex_hits_and_in_plane_edges(ctx, orc):
+    # flat grid, planes exactly through vertex rows (snap-to-vertex merges, zero-length lines, in-plane edges)
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(16, 16, lx=1.0, ly=1.0, amp=0.0)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (xyz.shape[0], 1))
+    blob = meshes.pack_blob(xyz, nrm, tri)
+    for spacing in (0.0625, 0.125, 0.03125):  # multiples / fractions of the 1/16 cell
+        gpu, ref, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, spacing, [1, 0, 0], [0, 0.5, 0])
+        assert ref.num_paths > 3
+        assert_same_paths(gpu, ref, f"grid-aligned spacing {spacing}")
+    # diagonal direction: planes through the diagonal vertices of every cell
+    gpu, ref, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, 0.0625 / np.sqrt(2), [1, 1, 0], [0.5, 0.5, 0])
+    assert_same_paths(gpu, ref, "diagonal")
+
+
+def test_slice_permutation_invariance(ctx, orc):
+    # shuffled vertex / face order: same polylines after mapping vertex ids back
+    from noether_b200 import meshes
+    from util import canonical_segments
+    blob, xyz, nrm, tri = _wavy_mesh(48, 40, hole=True)
+    gpu0, ref0, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, 0.021, [0.1, 1, 0], [0.5, 0.4, 0])
+    xyz2, tri2, nrm2 = meshes.permute(xyz, tri, seed=3, normals=nrm)
+    blob2 = meshes.pack_blob(xyz2, nrm2, tri2)
+    ctx.upload(blob2, force=True)
+    gpu1 = ctx.slice(capi_lattice_from_oracle(lat))
+    ref1 = orc.slice_mesh(xyz2, nrm2, tri2, lat, orc.SLICE_INTENT, orc.SCAN_BINNED).flat()
+    assert_same_paths(gpu1, ref1, "permuted")
+    # positions are the same set per segment regardless of the permutation
+    assert gpu1.n_waypoints == gpu0.n_waypoints and gpu1.n_segments == gpu0.n_segments
+    np.testing.assert_array_equal(np.sort(bits(gpu1.positions).view(np.uint32).ravel()),
+                                  np.sort(bits(gpu0.positions).ravel()))
+
+
+def test_slice_plane_slabs_concatenate(ctx, orc):
+    blob, xyz, nrm, tri = _wavy_mesh(80, 64, hole=True)
+    gpu, ref, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, 0.011, [0, 1, 0], [0.5, 0.4, 0])
+    P = int(lat.num_planes)
+    cl = capi_lattice_from_oracle(lat)
+    pos, lo, planes = [], [], []
+    for r in range(3):
+        part = ctx.slice(cl, P * r // 3, P * (r + 1) // 3)
+        pos.append(part.positions.copy())
+        lo.append(part.edge_lo.copy())
+        planes.append(part.path_plane.copy())
+    np.testing.assert_array_equal(np.concatenate(pos), gpu.positions)
+    np.testing.assert_array_equal(np.concatenate(lo), gpu.edge_lo)
+    np.testing.assert_array_equal(np.concatenate(planes), gpu.path_plane)
+
+
+def test_large_plane_uses_global_scratch(ctx, orc):
+    # one plane with more hits than fit the shared-memory work area (> 4096): the global-memory fallback
+    blob, xyz, nrm, tri = _wavy_mesh(8, 2600, lx=0.05, ly=2.0)
+    gpu, ref, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, 0.0125, [0, 1, 0], [0.0281, 1.0, 0])
+    assert np.diff(ref.seg_off.astype(np.int64)).max() > 4200
+    assert_same_paths(gpu, ref, "large plane")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole plan: RasterPlanner::plan
+# ---------------------------------------------------------------------------------------------------------------------
+def test_plan_end_to_end_matches_oracle(ctx, orc):
+    import noether_b200 as nb
+    blob, xyz, nrm, tri = _wavy_mesh(100, 80, hole=True)
+    planner = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx), nb.CentroidOriginGenerator(ctx), ctx)
+    planner.set_line_spacing(0.0123)
+    planner.generate_rasters_bidirectionally(True)
+    gpu = planner.plan(blob)
+    paths, lat, p = orc.plan_plane_slicer(xyz, nrm, tri, 0.0123, True, moments_mode=orc.MOMENTS_F64,
+                                          slice_mode=orc.SLICE_INTENT, scan_mode=orc.SCAN_BINNED)
+    assert bytes(ctx.last_lattice()) == bytes(lat)
+    assert gpu.post_ops_applied
+    assert_same_paths(gpu, paths.flat(), "plan")
+
+
+def test_plan_reference_tests_through_factory(ctx, orc, ply_mesh):
+    """The reference's two planner tests, written the way tool_path_planner_utest.cpp:74-177 writes them."""
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    factory = nb.Factory(ctx)
+    base = {"name": "PlaneSlicer", "direction_generator": {"name": "FixedDirection", "direction": {"x": 1.0, "y": 0.0, "z": 0.0}},
+            "origin_generator": {"name": "Centroid"}, "line_spacing": 0.1, "point_spacing": 0.05, "min_segment_size": 0.01,
+            "min_hole_size": 0.05, "bidirectional": True, "search_radius": 0.01}
+    n_lines = 10
+
+    # FlatSquareMesh
+    dim = 1.0
+    T = orc.fixture_random_transform(dim * 5.0, np.pi)
+    direction = T[:3, :3] @ np.array([1.0, 0, 0])
+    xyz, nrm, tri = orc.fixture_plane_mesh(dim, dim, T)
+    mesh = meshes.pack_blob(xyz, nrm, tri)
+    cfg = dict(base, line_spacing=0.95 * dim / n_lines)
+    cfg["direction_generator"] = {"name": "FixedDirection", "direction": list(direction)}
+    cfg["origin_generator"] = {"name": "FixedOrigin", "origin": list(T[:3, 3])}
+    tool_paths = factory.create_tool_path_planner(cfg).plan(mesh).nested()
+    assert len(tool_paths) == n_lines + 1
+    for path in tool_paths:
+        assert len(path) == 1
+        d = path[-1][-1][:3, 3] - path[0][0][:3, 3]
+        d /= np.linalg.norm(d)
+        assert abs(d @ direction) > np.cos(np.radians(1.0))
+
+    # SemiPlanarMeshFile
+    dim = 10.5
+    cfg = dict(base, line_spacing=dim / n_lines)
+    cfg["origin_generator"] = {"name": "FixedOrigin", "origin": [0.0, 0.0, 0.0]}
+    tool_paths = factory.create_tool_path_planner(cfg).plan(ply_mesh).nested()
+    assert len(tool_paths) == n_lines
+    for i, path in enumerate(tool_paths):
+        assert len(path) >= 1 and len(path[0]) >= 2
+        if 3 < i < 7:
+            assert len(path) == 2 and len(path[-1]) >= 2
+        d = path[-1][-1][:3, 3] - path[0][0][:3, 3]
+        d /= np.linalg.norm(d)
+        assert abs(d @ np.array([1.0, 0, 0])) > np.cos(np.radians(10.0))
+
+
+def test_plan_default_yaml_on_reference_mesh(ctx, orc, ply_mesh):
+    # cfg1: the reference's default YAML (line_spacing 0.1, FixedDirection x, Centroid, bidirectional)
+    import noether_b200 as nb
+    cfg = {"name": "PlaneSlicer", "direction_generator": {"name": "FixedDirection", "direction": [1.0, 0.0, 0.0]},
+           "origin_generator": {"name": "Centroid"}, "line_spacing": 0.1, "bidirectional": True}
+    gpu = nb.Factory(ctx).create_tool_path_planner(cfg).plan(ply_mesh)
+    xyz, nrm, tri = ply_mesh.xyz(), ply_mesh.normals(), ply_mesh.tri
+    paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.1, True, direction=[1, 0, 0], moments_mode=orc.MOMENTS_F64,
+                                          slice_mode=orc.SLICE_INTENT)
+    assert_same_paths(gpu, paths.flat(), "cfg1")
+    assert gpu.n_paths > 100
+
+
+def test_plan_unidirectional_and_empty(ctx, orc):
+    import noether_b200 as nb
+    blob, xyz, nrm, tri = _wavy_mesh(30, 24)
+    # origin beyond the mesh along the cut normal: unidirectional plans nothing (:569-570)
+    for origin, expect_empty in (([5.0, 0.4, 0], None), ([-5.0, 0.4, 0], None)):
+        pl = nb.PlaneSlicerRasterPlanner(nb.FixedDirectionGenerator([0, 1, 0]), nb.FixedOriginGenerator(origin), ctx)
+        pl.set_line_spacing(0.05)
+        pl.generate_rasters_bidirectionally(False)
+        gpu = pl.plan(blob)
+        paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.05, False, direction=[0, 1, 0], origin=origin,
+                                              moments_mode=orc.MOMENTS_F64, slice_mode=orc.SLICE_INTENT)
+        assert_same_paths(gpu, paths.flat(), f"unidirectional {origin}")
+    # exactly one of the two origins yields no cuts at all
+    # (which one depends on the sign of the PCA normal, which the oracle shares)
+
+
+def test_plan_errors(ctx, orc):
+    import noether_b200 as nb
+    from noether_b200 import _capi, meshes
+    xyz, tri = meshes.wavy(10, 8)
+    no_normals = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    pl = nb.PlaneSlicerRasterPlanner(nb.FixedDirectionGenerator([1, 0, 0]), nb.FixedOriginGenerator(), ctx)
+    pl.set_line_spacing(0.05)
+    with pytest.raises(_capi.Nb2Error) as e:
+        pl.plan(no_normals)
+    assert e.value.status == _capi.NB2_ERR_NO_NORMALS and "does not have vertex normals" in str(e.value)
+    # closed loops: a closed tube sliced across its axis
+    n, m = 24, 40
+    th = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    zs = np.linspace(0, 10, m)
+    v = np.array([[np.cos(t), np.sin(t) * 0.5, z] for z in zs for t in th], np.float32)
+    f = []
+    for j in range(m - 1):
+        for i in range(n):
+            a, b = j * n + i, j * n + (i + 1) % n
+            f += [[a, b, a + n], [b, b + n, a + n]]
+    f = np.array(f, np.uint32)
+    nr = orc.normals_from_mesh_faces(v, f)
+    tube = meshes.pack_blob(v, nr, f)
+    pl = nb.PlaneSlicerRasterPlanner(nb.FixedDirectionGenerator([1, 0, 0]), nb.FixedOriginGenerator([0, 0, 5.0]), ctx)
+    pl.set_line_spacing(0.7)
+    ctx.upload(tube, force=True)
+    p = orc.pca(v, orc.MOMENTS_F64)
+    lat = orc.make_lattice(p, [1, 0, 0], [0, 0, 5.0], 0.7, True)
+    with pytest.raises(orc.OracleError) as oe:
+        orc.slice_mesh(v, nr, f, lat, orc.SLICE_INTENT)
+    assert oe.value.code == orc.ERR_CLOSED_LOOP
+    with pytest.raises(_capi.Nb2Error) as e:
+        ctx.slice(capi_lattice_from_oracle(lat))
+    assert e.value.status == _capi.NB2_ERR_CLOSED_LOOP
+    with pytest.raises(_capi.Nb2Error):
+        pl.set_line_spacing(0.0)
+        pl.plan(tube)
+
+
+def test_legacy_planner(ctx, orc, ply_mesh):
+    import noether_b200 as nb
+    xyz, nrm, tri = ply_mesh.xyz(), ply_mesh.normals(), ply_mesh.tri
+    cfg = {"name": "PlaneSlicerLegacy", "direction_generator": {"name": "FixedDirection", "direction": [1.0, 0.0, 0.0]},
+           "origin_generator": {"name": "FixedOrigin", "origin": [0.0, 0.0, 0.0]}, "line_spacing": 1.05,
+           "point_spacing": 0.25, "min_segment_size": 0.5, "min_hole_size": 0.0, "bidirectional": True}
+    gpu = nb.Factory(ctx).create_tool_path_planner(cfg).plan(ply_mesh)
+    paths, _, _ = orc.plan_plane_slicer_legacy(xyz, nrm, tri, 1.05, 0.25, 0.5, 0.0, True, [1, 0, 0], [0, 0, 0],
+                                               moments_mode=orc.MOMENTS_F64, slice_mode=orc.SLICE_INTENT)
+    ref = paths.flat()
+    assert gpu.legacy and gpu.n_paths == ref.num_paths
+    np.testing.assert_array_equal(gpu.segment_offsets.astype(np.uint64), ref.seg_off)
+    gp = gpu.poses()
+    diag = np.linalg.norm(xyz.max(0) - xyz.min(0))
+    assert np.abs(gp[:, :3, 3] - ref.pose[:, :3, 3]).max() <= 1e-6 * diag
+    assert np.abs(gp[:, :3, :3] - ref.pose[:, :3, :3]).max() <= 1e-5
+    # uniform spacing inside every segment
+    for s in range(gpu.n_segments):
+        b, e = int(gpu.segment_offsets[s]), int(gpu.segment_offsets[s + 1])
+        step = np.linalg.norm(np.diff(gp[b:e, :3, 3], axis=0), axis=1)
+        assert np.allclose(step[1:-1], 0.25, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# benchmark-sized properties (1 M triangles) — structure checks that do not need the oracle's full run
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg2_properties(ctx, orc):
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(800, 625)
+    blob0 = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob0, force=True)
+    nrm = ctx.normals_from_mesh_faces(blob0.n_vertices)
+    blob = meshes.pack_blob(xyz, nrm, tri)
+    pl = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx), nb.CentroidOriginGenerator(ctx), ctx)
+    pl.set_line_spacing(0.005)
+    gpu = pl.plan(blob)
+    lat = ctx.last_lattice()
+    n = np.array(lat.cut_normal)
+    assert 190 <= gpu.n_paths <= 210
+    assert np.all(gpu.segments_per_path() == 1)           # no holes: one chain per plane
+    assert np.all(np.diff(gpu.path_plane) == 1)           # consecutive lattice planes
+    # every waypoint lies on its plane (float32 storage error only) and on its generating mesh edge
+    seg_of_wp = np.repeat(np.arange(gpu.n_segments), np.diff(gpu.segment_offsets.astype(np.int64)))
+    path_of_seg = np.repeat(np.arange(gpu.n_paths), gpu.segments_per_path())
+    plane = gpu.path_plane[path_of_seg[seg_of_wp]]
+    o = np.array(lat.start_loc)[None, :] + (plane[:, None] * lat.line_spacing) * n[None, :]
+    dist = ((gpu.positions.astype(np.float64) - o) * n[None, :]).sum(1)
+    assert np.abs(dist).max() < 2e-7
+    a, b = xyz[gpu.edge_lo].astype(np.float64), xyz[gpu.edge_hi].astype(np.float64)
+    ab = b - a
+    t = ((gpu.positions - a) * ab).sum(1) / np.maximum((ab * ab).sum(1), 1e-30)
+    assert t.min() > -1e-6 and t.max() < 1 + 1e-6
+    assert np.abs(a + t[:, None] * ab - gpu.positions).max() < 2e-7
+    # consecutive waypoints of a segment share a triangle: their generating edges share a vertex
+    e0 = np.stack([gpu.edge_lo, gpu.edge_hi], 1)
+    same_seg = seg_of_wp[1:] == seg_of_wp[:-1]
+    share = (e0[1:, :, None] == e0[:-1, None, :]).any(axis=(1, 2))
+    assert np.all(share[same_seg])
+    # and the binned oracle agrees bit for bit on the whole 1 M-triangle plan
+    paths, lat_o, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.005, True, moments_mode=orc.MOMENTS_F64,
+                                            slice_mode=orc.SLICE_INTENT, scan_mode=orc.SCAN_BINNED)
+    assert_same_paths(gpu, paths.flat(), "cfg2", poses=False)
