@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the raster-slicing hot path (BASELINE.json metric: triangles sliced / s and ms per plan).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1      # the reference's CPU algorithm on the host cores
+
+A step = one plan of the workload mesh: PlaneSlicerRasterPlanner(PrincipalAxis(0), Centroid) at the workload's line
+spacing.  Workload `cfg3` (default) is SURVEY.md §8(d) cfg3: wavy(2500, 2000) = 10,000,000 triangles / 5,004,501
+vertices, 1 mm spacing (BASELINE.json configs[2], the mesh the metric is quoted on; it fits one GPU).
+
+  value  device throughput: the interleaved cloud + triangle list are resident in HBM when the timed region starts; each
+         step runs ingest + moments + extents + lattice classification + hit count / scan / bucket fill + per-plane
+         linking, tool paths left in HBM.  Timed with CUDA events on the library's stream; max over ranks.
+  e2e    the same plan through the reference-facing planner call (noether_b200.PlaneSlicerRasterPlanner.plan) from
+         pinned HOST buffers: H2D of the mesh, the plan, D2H of the tool paths, raster post-ops (and, for N > 1, the
+         NCCL gather of the slabs to rank 0) inside the timed region.  Wall clock around synchronous calls.
+
+For N > 1 the lattice planes are split into N contiguous slabs (one rank = one GPU = one slab); total work is fixed, so
+scaling is "strong".  torch is plumbing only (pinned/device buffers, rendezvous, barriers).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, line_spacing, description)
+    "cfg3": (2500, 2000, 0.001, "wavy(2500,2000) 10M tris / 5.0M verts, 1 mm spacing, PrincipalAxis(0)+Centroid, bidirectional"),
+    "cfg2": (800, 625, 0.005, "wavy(800,625) 1M tris / 0.5M verts, 5 mm spacing, PrincipalAxis(0)+Centroid, bidirectional"),
+    "tiny": (80, 64, 0.02, "wavy(80,64) smoke-sized mesh"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        self.file.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.file.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.file.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(name: str):
+    from noether_b200 import meshes
+    nx, ny, spacing, desc = WORKLOADS[name]
+    xyz, tri = meshes.wavy(nx, ny)
+    return xyz, tri, spacing, desc
+
+
+def cpu_reference_sample(xyz, nrm, tri, spacing, n_planes: int):
+    """The reference's algorithm (oracle, faithful mode, every vertex + every cell per plane, one thread) on a bounded
+    sample: the plane-independent prologue plus `n_planes` evenly spaced lattice planes, extrapolated linearly in the
+    plane count (iterations of the reference's loop are independent).  Returns a dict."""
+    import oracle as orc
+    t0 = time.perf_counter()
+    p = orc.pca(xyz, orc.MOMENTS_F32_SEQUENTIAL)
+    d = orc.principal_axis_direction(p, 0.0)
+    o = orc.centroid(xyz, orc.MOMENTS_F32_SEQUENTIAL)
+    lat = orc.make_lattice(p, d, o, spacing, True)
+    t_pro = time.perf_counter() - t0
+    P = int(lat.num_planes)
+    ks = np.unique(np.linspace(0, P - 1, min(n_planes, P)).round().astype(int))
+    t_planes = []
+    for k in ks:
+        t1 = time.perf_counter()
+        orc.slice_mesh(xyz, nrm, tri, lat, orc.SLICE_FAITHFUL, orc.SCAN_ALL_CELLS, int(k), int(k) + 1)
+        t_planes.append(time.perf_counter() - t1)
+    per_plane = float(np.mean(t_planes))
+    t_full = t_pro + per_plane * P
+    return {"t_prologue_s": t_pro, "t_per_plane_s": per_plane, "planes_sampled": int(len(ks)), "planes": P,
+            "t_plan_extrapolated_s": t_full, "t_measured_s": t_pro + float(np.sum(t_planes)),
+            "tri_per_s": tri.shape[0] / t_full}
+
+
+def algorithmic_bytes(stage: str, V: int, F: int, H: int, W: int, S: int, P: int, point_step: int) -> float | None:
+    """Compulsory bytes of each kernel: what it must read and write once."""
+    table = {
+        "ingest+moments": 24 * V + 24 * V,       # xyz + normal in, xyz + normal out (the blob's other fields are not needed)
+        "validate": 12 * F,
+        "extents": 12 * V,
+        "classify": 12 * V + 4 * V,
+        "count": 12 * F + 4 * V,
+        "fill": 12 * F + 4 * V + 4 * H,
+        "link": 4 * H + 12 * H + 24 * W + 24 * W + 4 * S,  # bucket, triangles of hits, vertex data of cut edges, waypoints out
+        "scan": 8 * P,
+    }
+    return table.get(stage)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-planes", type=int, default=24, help="lattice planes sampled by the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from noether_b200.dist import RankInfo
+    info = RankInfo.from_env()
+    if info.world != args.gpus and info.world > 1:
+        print(f"warning: WORLD_SIZE={info.world} but --gpus {args.gpus}", file=sys.stderr)
+
+    xyz, tri, spacing, desc = build_workload(args.workload)
+    V, F = xyz.shape[0], tri.shape[0]
+
+    # -----------------------------------------------------------------------------------------------------------------
+    # reference arm: the reference's own CPU algorithm on the host cores (rank 0 only)
+    # -----------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if info.rank != 0:
+            return
+        import oracle as orc
+        orc.build()
+        nrm = orc.normals_from_mesh_faces(xyz, tri)
+        per_step = max(2, args.cpu_planes // 3)
+        for _ in range(args.warmup):
+            cpu_reference_sample(xyz, nrm, tri, spacing, 2)
+        t0 = time.perf_counter()
+        runs = [cpu_reference_sample(xyz, nrm, tri, spacing, per_step) for _ in range(args.steps)]
+        wall = time.perf_counter() - t0
+        t_plan = float(np.mean([r["t_plan_extrapolated_s"] for r in runs]))
+        value = F / t_plan
+        line = {
+            "impl": "reference", "metric": "triangles sliced/sec", "value": value, "unit": "triangles/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_plan,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "timing": "wall clock; extrapolated to the full lattice"},
+            "cpu_baseline": {"value": value, "unit": "triangles/s", "cores": 1, "kind": "port",
+                             "sample": (f"plane-independent prologue + {runs[0]['planes_sampled']} of {runs[0]['planes']} "
+                                        "lattice planes per step (every vertex and every cell visited per plane, as "
+                                        "vtkCutter does), extrapolated linearly in the plane count; the reference is "
+                                        "single-threaded so 1 core is all it can use; wall time of the sampled work "
+                                        f"{wall:.1f} s")},
+            "e2e": {"value": value, "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # -----------------------------------------------------------------------------------------------------------------
+    # our arm
+    # -----------------------------------------------------------------------------------------------------------------
+    import torch
+
+    import noether_b200 as nb
+    from noether_b200 import _capi, meshes
+    from noether_b200.dist import broadcast_bytes, init_process_group, max_over_ranks
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: noether_b200 has no CPU fallback")
+    torch.cuda.set_device(info.local_rank)
+    dev = torch.device("cuda", info.local_rank)
+    init_process_group(info, "nccl")
+    ctx = nb.Context(info.local_rank)
+    if info.world > 1:
+        uid = broadcast_bytes(ctx.comm_unique_id() if info.rank == 0 else None, 0, info.world)
+        ctx.comm_init(uid, info.rank, info.world)
+
+    def barrier():
+        if info.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # vertex normals from our own NormalsFromMeshFaces (timed separately; not part of the plan)
+    blob0 = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob0, force=True)
+    nrm = ctx.normals_from_mesh_faces(V)
+    ctx.normals_from_mesh_faces(V, download=False)
+    normals_ms = {k: v for k, v in ctx.timings().items()}
+    blob = meshes.pack_blob(xyz, nrm, tri, "PointNormal")
+
+    # pinned host copies (e2e input) and device-resident copies (value input); torch only allocates the memory
+    h_cloud = torch.empty(blob.data.size, dtype=torch.uint8, pin_memory=True)
+    h_cloud.numpy()[:] = blob.data
+    h_tri = torch.empty(tri.size, dtype=torch.int32, pin_memory=True)
+    h_tri.numpy()[:] = tri.reshape(-1).view(np.int32)
+    d_cloud = h_cloud.to(dev)
+    d_tri = h_tri.to(dev)
+    torch.cuda.synchronize()
+    pinned_mesh = meshes.MeshBlob(h_cloud.numpy(), V, blob.point_step, blob.off_xyz, blob.off_normal,
+                                  h_tri.numpy().view(np.uint32).reshape(-1, 3))
+
+    prm = _capi.PlanParams()
+    _capi.load().nb2_plan_params_default(prm)
+    prm.line_spacing = spacing
+    prm.bidirectional = 1
+    prm.direction_mode = _capi.NB2_DIRECTION_PRINCIPAL_AXIS
+    prm.origin_mode = _capi.NB2_ORIGIN_CENTROID
+    prm.emit_edges = 0
+    prm.shard_rank, prm.shard_count = info.rank, info.world
+    prm.download = 0
+
+    def device_step():
+        ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
+        up = ctx.timings()
+        r = ctx.plan(prm)
+        pl = ctx.timings()
+        counts = (r.n_paths, r.n_segments, r.n_waypoints)
+        r.free()
+        return up, pl, counts
+
+    planner = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx), nb.CentroidOriginGenerator(ctx), ctx)
+    planner.set_line_spacing(spacing)
+    planner.generate_rasters_bidirectionally(True)
+    planner.emit_edges = False
+
+    def e2e_step():
+        ctx._mesh_key = None  # every step uploads the mesh again from the pinned host buffers
+        local = planner.plan(pinned_mesh, info.rank, info.world)
+        if info.world > 1:
+            out = ctx.gather(local, 0)
+            n = (out.n_paths, out.n_segments, out.n_waypoints) if out is not None else (0, 0, 0)
+            d2h = local.n_waypoints * 24 + local.n_segments * 4
+            local.free()
+            if out is not None:
+                out.free()
+            return n, d2h
+        n = (local.n_paths, local.n_segments, local.n_waypoints)
+        d2h = local.n_waypoints * 24 + local.n_segments * 4
+        local.free()
+        return n, d2h
+
+    # ---- value: device-resident ------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sampler = ClockSampler(info.local_rank)
+    stage_acc: dict[str, list[float]] = {}
+    launches0 = ctx.kernel_launches()
+    barrier()
+    sampler.start()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    counts = None
+    for _ in range(args.steps):
+        up, pl, counts = device_step()
+        for k, v in list(up.items()) + list(pl.items()):
+            stage_acc.setdefault(k, []).append(v)
+    dev_ms = ctx.timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches() - launches0
+    dev_ms = max_over_ranks(dev_ms, info.world, dev)
+    wall_ms = max_over_ranks(wall_ms, info.world, dev)
+    ms_per_step = dev_ms / args.steps
+
+    # ---- e2e ---------------------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    totals, d2h_bytes = None, 0
+    for _ in range(args.steps):
+        totals, d2h_bytes = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0), info.world, dev) / args.steps
+    h2d_bytes = int(blob.data.size + tri.size * 4)
+
+    if info.rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event stage times averaged over the timed steps) -------------
+    peak, peak_src = measured_peaks()
+    lat = ctx.last_lattice()
+    P_planes = int(lat.num_planes)
+    n_paths, n_segments, n_waypoints = totals if info.world == 1 else totals
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h", "setup")}
+    dominant = max(kernel_stages, key=kernel_stages.get)
+    # per-rank quantities for the dominant kernel's launch on this rank
+    W_rank, S_rank = counts[2], counts[1]
+    H_rank = max(W_rank - S_rank, 0)
+    B = algorithmic_bytes(dominant, V, F, H_rank, W_rank, S_rank, P_planes, blob.point_step)
+    achieved = (B / 1e9) / (kernel_stages[dominant] / 1e3) if B else None
+    B_plan = 12 * F + 24 * V + 24 * n_waypoints + 4 * (n_segments + 1) + 4 * (n_paths + 1)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "algorithmic_bytes_per_launch": B, "launch_ms": kernel_stages[dominant], "peak_source": peak_src,
+                "stage_ms": stage_ms,
+                "plan": {"algorithmic_bytes": B_plan, "achieved": (B_plan / 1e9) / (ms_per_step / 1e3),
+                         "frac": (B_plan / 1e9) / (ms_per_step / 1e3) / peak,
+                         "note": "B_plan = 12F + 24V + 24W + 4(S+1) + 4(P+1) over the whole device step"}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle as orc
+        orc.build()
+        s = cpu_reference_sample(xyz, nrm, tri, spacing, args.cpu_planes)
+        cpu = {"value": s["tri_per_s"], "unit": "triangles/s", "cores": 1, "kind": "port",
+               "host_cores_available": os.cpu_count(),
+               "sample": (f"prologue + {s['planes_sampled']} of {s['planes']} lattice planes "
+                          f"({s['t_measured_s']:.1f} s measured), extrapolated linearly to the full lattice "
+                          f"({s['t_plan_extrapolated_s']:.1f} s per plan); reference-structured single-thread oracle")}
+
+    line = {
+        "metric": "triangles sliced/sec", "value": F / (ms_per_step / 1e3), "unit": "triangles/s",
+        "n_gpus": info.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "planes": P_planes, "tool_paths": int(n_paths),
+                   "segments": int(n_segments), "waypoints": int(n_waypoints),
+                   "parallelism": f"plane slabs x{info.world}" if info.world > 1 else "single GPU",
+                   "l2": "inputs (cloud + triangles = %d MB) are larger than the 126 MB L2" % (h2d_bytes // 2**20),
+                   "timing": "CUDA events on the library stream, max over ranks; wall clock %.3f ms/step" % (wall_ms / args.steps)},
+        "clocks": clocks,
+        "e2e": {"value": F / (e2e_ms / 1e3), "unit": "triangles/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "normals_from_mesh_faces_ms": normals_ms,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -172,6 +172,10 @@ typedef struct nb2_plan_params
   /* plane-slab sharding: this context plans lattice planes [shard_rank * P / shard_count, (shard_rank+1) * P / shard_count) */
   int32_t shard_rank;
   int32_t shard_count; /* 0 or 1 = unsharded */
+  /* 1 (default) = copy the tool paths to the host.  0 = leave them in HBM: the result carries the counts only and the
+   * host-side modifiers (legacy, raster post-ops) are skipped — used to time the device path on resident data. */
+  int32_t download;
+  int32_t reserved_;
 } nb2_plan_params;
 
 void nb2_plan_params_default(nb2_plan_params* p);
@@ -213,6 +217,10 @@ void nb2_result_free(nb2_result* r);
 int nb2_last_timings(const nb2_context* ctx, const char** names, float* ms, int capacity);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t nb2_kernel_launches(const nb2_context* ctx);
+/* Bracket any sequence of calls on this context with CUDA events on the context's stream.  nb2_timer_stop waits for the
+ * stop event and returns the elapsed device time in milliseconds. */
+int nb2_timer_start(nb2_context* ctx);
+int nb2_timer_stop(nb2_context* ctx, float* ms);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  Plane slabs are independent (the reference's loop :596-628 carries no state), so

@@ -37,7 +37,8 @@ DECLARED_SYMBOLS = [
     "nb2_mesh_upload", "nb2_mesh_set_normals", "nb2_mesh_download", "nb2_mesh_pca", "nb2_principal_axis_direction",
     "nb2_centroid_origin", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_plan_params_default", "nb2_slice",
     "nb2_plan", "nb2_last_lattice", "nb2_result_get", "nb2_result_poses", "nb2_result_free", "nb2_last_timings",
-    "nb2_kernel_launches", "nb2_comm_unique_id", "nb2_comm_init", "nb2_result_gather", "nb2_comm_destroy",
+    "nb2_kernel_launches", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
+    "nb2_result_gather", "nb2_comm_destroy",
 ]
 
 
@@ -65,7 +66,8 @@ class PlanParams(C.Structure):
                 ("direction", C.c_double * 3), ("rotation_offset", C.c_double), ("origin_mode", C.c_int32),
                 ("raster_post_ops", C.c_int32), ("origin", C.c_double * 3), ("legacy", C.c_int32),
                 ("emit_edges", C.c_int32), ("point_spacing", C.c_double), ("min_segment_size", C.c_double),
-                ("min_hole_size", C.c_double), ("shard_rank", C.c_int32), ("shard_count", C.c_int32)]
+                ("min_hole_size", C.c_double), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
+                ("download", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class ResultView(C.Structure):
@@ -123,6 +125,8 @@ def load():
     L.nb2_last_timings.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.nb2_kernel_launches.argtypes = [vp]
     L.nb2_kernel_launches.restype = C.c_uint64
+    L.nb2_timer_start.argtypes = [vp]
+    L.nb2_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.nb2_comm_unique_id.argtypes = [C.c_void_p]
     L.nb2_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     L.nb2_result_gather.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]

@@ -17,8 +17,25 @@ thread_local std::string t_last_error;
 void setLastError(const std::string& msg) { t_last_error = msg; }
 void fail(int status, const std::string& msg) { throw Error{ status, msg }; }
 
+void DevBuf::adopt(void* device_ptr)
+{
+  if (!borrowed)
+  {
+    own_ptr = ptr;
+    own_cap = cap;
+  }
+  ptr = device_ptr;
+  cap = 0;
+  borrowed = true;
+}
 void DevBuf::ensure(size_t bytes)
 {
+  if (borrowed)
+  {
+    ptr = own_ptr;
+    cap = own_cap;
+    borrowed = false;
+  }
   if (bytes <= cap)
     return;
   if (ptr)
@@ -31,6 +48,12 @@ void DevBuf::ensure(size_t bytes)
 }
 void DevBuf::release()
 {
+  if (borrowed)
+  {
+    ptr = own_ptr;
+    cap = own_cap;
+    borrowed = false;
+  }
   if (ptr)
     cudaFree(ptr);
   ptr = nullptr;
@@ -171,10 +194,32 @@ nb2_result* allocResult(nb2_context* c, uint64_t P, uint64_t S, uint64_t W, bool
   return r;
 }
 
+// contexts that are still alive: a result may outlive its context (garbage-collected bindings), in which case its
+// pinned block is released directly instead of going back to the context's pool
+std::mutex g_live_mu;
+std::vector<nb2_context*> g_live;
+void registerContext(nb2_context* c)
+{
+  std::lock_guard<std::mutex> l(g_live_mu);
+  g_live.push_back(c);
+}
+void unregisterContext(nb2_context* c)
+{
+  std::lock_guard<std::mutex> l(g_live_mu);
+  g_live.erase(std::remove(g_live.begin(), g_live.end(), c), g_live.end());
+}
+bool contextAlive(nb2_context* c)
+{
+  std::lock_guard<std::mutex> l(g_live_mu);
+  return std::find(g_live.begin(), g_live.end(), c) != g_live.end();
+}
+
 void freeResult(nb2_result* r)
 {
   if (!r)
     return;
+  if (r->block && !r->owner)
+    cudaFreeHost(r->block);
   if (r->block && r->owner)
   {
     auto& pool = r->owner->hostPool;
@@ -224,6 +269,7 @@ void ensurePca(nb2_context* c)
     return;
   // extents of the cloud in the PCA frame (second, smaller pass)
   launchExtents(c, c->pca.mean, c->pca.evecs);
+  c->timer.mark("extents", c->stream);
   c->hostSmall.ensure(4096);
   float* h = c->hostSmall.as<float>();
   NB2_CUDA(cudaMemcpyAsync(h, c->extents.ptr, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -241,7 +287,8 @@ nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
 }
 
 /** planImpl's plane loop on the device */
-nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, bool emit_edges)
+nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, bool emit_edges,
+                      bool download = true)
 {
   requireMesh(c);
   if (!c->has_normals)
@@ -270,7 +317,7 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   init[11] = 0xffffffffu;
   NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + 4, init + 4, 12 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
 
-  c->timer.begin(c->stream);
+  c->timer.mark("setup", c->stream);
   launchClassify(c, L);
   c->timer.mark("classify", c->stream);
   launchCountHits(c, L);
@@ -288,6 +335,8 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
     return emptyResult(c, lat);
   if (H >= (1ull << 30))
     fail(NB2_ERR_INVALID_ARGUMENT, "more than 2^30 triangle/plane intersections in one slab; shard the plan");
+  if (n_max >= (1u << 19))
+    fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects 2^19 or more triangles; not supported");
 
   c->bucket.ensure(sizeof(uint32_t) * H);
   launchFillBuckets(c, L);
@@ -329,6 +378,19 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   for (uint64_t k = 0; k < nP; ++k)
     Pn += hmeta[2 * k + 1] > 0;
 
+  if (!download)
+  {
+    // tool paths stay in HBM: report the counts only
+    nb2_result* r = allocResult(c, 0, 0, 0, false, false);
+    r->lattice = lat;
+    r->n_paths = Pn;
+    r->n_segments = St;
+    r->n_waypoints = Wt;
+    r->path_offsets = r->segment_offsets = nullptr;
+    r->path_plane = nullptr;
+    r->positions = r->normals = nullptr;
+    return r;
+  }
   nb2_result* r = allocResult(c, Pn, St, Wt, emit_edges, false);
   r->lattice = lat;
   try
@@ -428,6 +490,7 @@ int nb2_context_create(int device, nb2_context** out)
   c->counters.ensure(64 * sizeof(unsigned));
   NB2_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64 * sizeof(unsigned), c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  registerContext(c.get());
   *out = c.release();
   NB2_API_END
 }
@@ -436,6 +499,7 @@ void nb2_context_destroy(nb2_context* c)
 {
   if (!c)
     return;
+  unregisterContext(c);
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
@@ -482,13 +546,34 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   c->pca_valid = false;
   const uint64_t V = m->n_points, F = m->n_triangles;
   c->timer.begin(c->stream);
-  c->blob.ensure(V * m->point_step);
+  // Inputs that already live in this GPU's memory are used in place (no copy; the caller keeps them alive until the
+  // next upload).  Anything else is copied host -> device.
+  auto onThisDevice = [&](const void* p) {
+    cudaPointerAttributes a{};
+    if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeDevice && a.device == c->device;
+  };
   c->pos.ensure(sizeof(float4) * V);
   c->nrm.ensure(sizeof(float4) * V);
-  c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
-  NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, V * m->point_step, cudaMemcpyHostToDevice, c->stream));
-  if (F)
-    NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, sizeof(uint32_t) * 3 * F, cudaMemcpyHostToDevice, c->stream));
+  if (onThisDevice(m->cloud_data))
+    c->blob.adopt(const_cast<void*>(m->cloud_data));
+  else
+  {
+    c->blob.ensure(V * m->point_step);
+    NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, V * m->point_step, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (F && onThisDevice(m->triangles))
+    c->tri.adopt(const_cast<uint32_t*>(m->triangles));
+  else
+  {
+    c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+    if (F)
+      NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, sizeof(uint32_t) * 3 * F, cudaMemcpyHostToDevice, c->stream));
+  }
   c->timer.mark("h2d", c->stream);
   c->V = V;
   c->F = F;
@@ -506,9 +591,10 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   // pivot = first vertex
-  float pivot[3];
-  std::memcpy(pivot, static_cast<const uint8_t*>(m->cloud_data) + m->offset_xyz, 12);
+  NB2_CUDA(cudaMemcpyAsync(h + 1024, c->blob.as<uint8_t>() + m->offset_xyz, 12, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  float pivot[3];
+  std::memcpy(pivot, h + 1024, 12);
   MomentPartial total;
   std::memcpy(&total, h, sizeof(total));
   unsigned max_index;
@@ -663,6 +749,7 @@ void nb2_plan_params_default(nb2_plan_params* p)
   p->min_hole_size = 0.1;
   p->shard_rank = 0;
   p->shard_count = 1;
+  p->download = 1;
 }
 
 int nb2_slice(nb2_context* c, const nb2_lattice* lat, uint64_t plane_begin, uint64_t plane_end, nb2_result** out)
@@ -675,6 +762,7 @@ int nb2_slice(nb2_context* c, const nb2_lattice* lat, uint64_t plane_begin, uint
   DeviceGuard g(c->device);
   if (!(lat->line_spacing > 0.0))
     fail(NB2_ERR_INVALID_ARGUMENT, "line_spacing must be a positive finite number");
+  c->timer.begin(c->stream);
   *out = sliceImpl(c, *lat, plane_begin, plane_end, true);
   NB2_API_END
 }
@@ -692,6 +780,7 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
     fail(NB2_ERR_NO_NORMALS, "The input mesh does not have vertex normals, which are required for the plane slice raster "
                              "tool path planner. Use a MeshModifier to generate vertex normals for the mesh, or provide a "
                              "different mesh with vertex normals.");
+  c->timer.begin(c->stream);
   ensurePca(c);
   double dir[3], origin[3];
   if (prm->direction_mode == NB2_DIRECTION_PRINCIPAL_AXIS)
@@ -719,13 +808,14 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
     kb = lat.num_planes * static_cast<uint64_t>(prm->shard_rank) / prm->shard_count;
     ke = lat.num_planes * (static_cast<uint64_t>(prm->shard_rank) + 1) / prm->shard_count;
   }
-  nb2_result* r = sliceImpl(c, lat, kb, ke, prm->emit_edges != 0 || prm->legacy != 0);
+  const bool download = prm->download != 0;
+  nb2_result* r = sliceImpl(c, lat, kb, ke, prm->emit_edges != 0 || prm->legacy != 0, download);
   r->params = *prm;
   try
   {
     const bool sharded = prm->shard_count > 1;
     // sharded plans defer the modifiers to nb2_result_gather: they need the whole set of tool paths
-    if (!sharded)
+    if (!sharded && download)
     {
       if (prm->legacy && r->n_paths)
         legacyModifiers(r, prm->point_spacing, prm->min_segment_size, prm->min_hole_size);
@@ -791,13 +881,16 @@ void nb2_result_free(nb2_result* r)
 {
   if (!r)
     return;
-  if (r->owner)
+  if (r->owner && contextAlive(r->owner))
   {
     std::lock_guard<std::mutex> lock(r->owner->mu);
     freeResult(r);
   }
   else
+  {
+    r->owner = nullptr;  // context already destroyed: release the pinned block directly
     freeResult(r);
+  }
 }
 
 int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int capacity)
@@ -808,5 +901,34 @@ int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int ca
 }
 
 uint64_t nb2_kernel_launches(const nb2_context* c) { return c ? c->launches : 0; }
+
+int nb2_timer_start(nb2_context* c)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  if (!c->ev_start)
+  {
+    NB2_CUDA(cudaEventCreate(&c->ev_start));
+    NB2_CUDA(cudaEventCreate(&c->ev_stop));
+  }
+  NB2_CUDA(cudaEventRecord(c->ev_start, c->stream));
+  NB2_API_END
+}
+
+int nb2_timer_stop(nb2_context* c, float* ms)
+{
+  NB2_API_BEGIN
+  if (!c || !ms || !c->ev_start)
+    fail(NB2_ERR_INVALID_ARGUMENT, "timer not started");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  NB2_CUDA(cudaEventRecord(c->ev_stop, c->stream));
+  NB2_CUDA(cudaEventSynchronize(c->ev_stop));
+  NB2_CUDA(cudaEventElapsedTime(ms, c->ev_start, c->ev_stop));
+  NB2_API_END
+}
 
 }  // extern "C"

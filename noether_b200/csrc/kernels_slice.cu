@@ -200,6 +200,13 @@ struct LinkParams
 };
 
 constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u, kErrOverflow = 4u;
+// pairing cell of a hash slot: [31:20] number of line ends at the point, [19:0] last line end that arrived
+constexpr unsigned kCellShift = 20u, kCellMask = (1u << kCellShift) - 1u;
+constexpr unsigned kMaxCrowded = 16u;      // points with more than two incident lines handled per plane
+constexpr unsigned kMaxCrowdedEnds = 32u;  // line ends at one such point
+// s_misc: [0] chains, [1] error bits, [2] baseW, [3] baseS, [4] plane waypoints, [5] ranking flag, [6] crowded points,
+//         [7] closed loops present, [8..] crowded slot ids
+constexpr int kMiscWords = 8 + kMaxCrowded;
 
 // look-back status word: [63:62] flag, [61:31] waypoints, [30:0] segments
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62;
@@ -270,7 +277,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   const unsigned mask = W.cap - 1;
 
   // s_misc: [0] nHeads, [1] local error bits, [2] baseW, [3] baseS, [4] totalW, [5] any-unfinished flag
-  if (tid < 8)
+  if (tid < kMiscWords)
     s_misc[tid] = 0;
 
   // ---- A: contour every hit (vtkTriangle::Contour) ----------------------------------------------------------------
@@ -326,8 +333,11 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   __syncthreads();
 
   // ---- H2: pair the two line ends meeting at each point -------------------------------------------------------------
+  // The pairing cell of a slot packs {number of line ends that arrived, last arrival}: the second arrival pairs with
+  // the first.  Points with more than two incident lines (a plane through a saddle-like vertex, or a doubled line
+  // where the plane grazes a mesh edge) are re-paired below in tag order so the result does not depend on arrival order.
   for (unsigned s = tid; s < W.cap; s += nth)
-    W.slots[s].first = kEmpty;
+    W.slots[s].first = 0u;
   for (unsigned e = tid; e < E; e += nth)
     W.twin[e] = kNone;
   __syncthreads();
@@ -336,20 +346,83 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
     // a line whose two ends merged into one point is dropped (vtkTriangle::Contour: pts[0] != pts[1])
     if (W.etag[e] == W.etag[e ^ 1u])
       continue;
-    const unsigned prev = atomicExch(&W.slots[W.etag[e]].first, e);
-    if (prev != kEmpty)
+    unsigned* cell = &W.slots[W.etag[e]].first;
+    unsigned old = *reinterpret_cast<volatile unsigned*>(cell);
+    while (true)
     {
+      const unsigned seen = atomicCAS(cell, old, (((old >> kCellShift) + 1u) << kCellShift) | e);
+      if (seen == old)
+        break;
+      old = seen;
+    }
+    if ((old >> kCellShift) == 1u)
+    {
+      const unsigned prev = old & kCellMask;
       W.twin[e] = static_cast<Idx>(prev);
       W.twin[prev] = static_cast<Idx>(e);
     }
   }
   __syncthreads();
-  // symmetry check (a third line at a point breaks it) and slot index -> first-inserter rank
   for (unsigned e = tid; e < E; e += nth)
   {
-    const Idx tw = W.twin[e];
-    if (tw != kNone && W.twin[tw] != static_cast<Idx>(e))
-      atomicOr(&s_misc[1], kErrNonManifold);
+    if (W.etag[e] == W.etag[e ^ 1u])
+      continue;
+    const unsigned cellv = W.slots[W.etag[e]].first;
+    if ((cellv >> kCellShift) > 2u)
+    {
+      W.twin[e] = kNone;
+      if ((cellv & kCellMask) == e)  // one registration per crowded point
+      {
+        const unsigned i = atomicAdd(&s_misc[6], 1u);
+        if (i < kMaxCrowded)
+          s_misc[8 + i] = W.etag[e];
+        else
+          atomicOr(&s_misc[1], kErrNonManifold);
+      }
+    }
+  }
+  __syncthreads();
+  if (s_misc[6] > 0 && !(s_misc[1] & kErrNonManifold))
+  {
+    // rare: one thread per crowded point gathers its line ends, sorts them by tag and pairs them consecutively
+    if (tid < s_misc[6])
+    {
+      const unsigned slot = s_misc[8 + tid];
+      unsigned mem[kMaxCrowdedEnds];
+      unsigned cnt = 0;
+      bool overflow = false;
+      for (unsigned e = 0; e < E; ++e)
+      {
+        if (W.etag[e] != slot || W.etag[e ^ 1u] == slot)
+          continue;
+        if (cnt == kMaxCrowdedEnds)
+        {
+          overflow = true;
+          break;
+        }
+        // insertion sort by line-end tag
+        const unsigned tg = 2u * __ldg(P.bucket + off + (e >> 1)) + (e & 1u);
+        unsigned j = cnt++;
+        while (j > 0)
+        {
+          const unsigned o = mem[j - 1];
+          const unsigned to = 2u * __ldg(P.bucket + off + (o >> 1)) + (o & 1u);
+          if (to < tg)
+            break;
+          mem[j] = o;
+          --j;
+        }
+        mem[j] = e;
+      }
+      if (overflow)
+        atomicOr(&s_misc[1], kErrNonManifold);
+      else
+        for (unsigned i = 0; i + 1 < cnt; i += 2)
+        {
+          W.twin[mem[i]] = static_cast<Idx>(mem[i + 1]);
+          W.twin[mem[i + 1]] = static_cast<Idx>(mem[i]);
+        }
+    }
   }
   __syncthreads();
   // slot index -> first-inserter rank of the merged point.  Each thread owns the pair (2j, 2j+1), so reading both slots
@@ -439,21 +512,96 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
       chainEnd[e] = kNone;
     }
     if (bad)
-      atomicOr(&s_misc[1], kErrClosedLoop);
+      s_misc[7] = 1u;  // some darts never reached an end: closed loops
   }
   __syncthreads();
-  if (s_misc[1] & kErrClosedLoop)
-    return;
 
   // ---- C: chain heads, orientation, order ---------------------------------------------------------------------------
   struct Head
   {
     double key;    // first point . cut_direction
     unsigned e;    // head dart
-    unsigned tag;  // first point's first-inserter rank
+    unsigned tag;  // tag (2 * triangle + line end) of the chain's first line end: tie-break of the order
   };
   Head* heads = reinterpret_cast<Head*>(W.slots);  // slots are dead; 16 B per head, cap >= E >= 2 * heads
   unsigned* lenSorted = reinterpret_cast<unsigned*>(W.twin);
+  auto endTag = [&](unsigned e) { return 2u * __ldg(P.bucket + off + (e >> 1)) + (e & 1u); };
+
+  if (s_misc[7])
+  {
+    // Closed loops are rare (the reference targets open, roughly planar surfaces): one thread walks them.  A loop
+    // starts at end 0 of its lowest-tag line and first walks that line, as vtkStripper does from its seed; it is
+    // reversed, keeping the start point, when that first step points against the cut direction.
+    if (tid == 0)
+    {
+      for (unsigned e0 = 0; e0 < E; ++e0)
+      {
+        if (nxt[e0] == kNone)
+          continue;
+        unsigned c = e0, best = endTag(e0), len = 0;
+        for (unsigned d = e0;;)
+        {
+          const unsigned t = endTag(d);
+          if (t < best)
+          {
+            best = t;
+            c = d;
+          }
+          ++len;
+          d = W.twin[d ^ 1u];
+          if (d == e0)
+            break;
+        }
+        bool forward = false;
+        CutPoint a{};
+        if ((best & 1u) == 0u)
+        {
+          a = cutPointOfTag(P, org, W.etag[c], false);
+          const CutPoint b = cutPointOfTag(P, org, W.etag[c ^ 1u], false);
+          const double dd = dotLR(dsub(static_cast<double>(b.x), static_cast<double>(a.x)),
+                                  dsub(static_cast<double>(b.y), static_cast<double>(a.y)),
+                                  dsub(static_cast<double>(b.z), static_cast<double>(a.z)), P.L.dir);
+          forward = !(dd < 0.0);
+          // walk c = d_0 .. d_{len-1}; selected darts get list ranks, the others become inert singletons
+          unsigned d = c;
+          const unsigned tailF = [&] {
+            unsigned q = c;
+            for (unsigned i = 0; i + 1 < len; ++i)
+              q = W.twin[q ^ 1u];
+            return q;
+          }();
+          for (unsigned i = 0; i < len; ++i)
+          {
+            const unsigned nd = W.twin[d ^ 1u];
+            const unsigned m = d ^ 1u;  // reverse dart d'_{len-1-i}
+            if (forward)
+            {
+              nxt[d] = kNone, rnk[d] = static_cast<Idx>(len - 1 - i), lst[d] = static_cast<Idx>(tailF);
+              nxt[m] = kNone, rnk[m] = 0, lst[m] = static_cast<Idx>(m);
+            }
+            else
+            {
+              nxt[d] = kNone, rnk[d] = 0, lst[d] = static_cast<Idx>(d);
+              nxt[m] = kNone, rnk[m] = static_cast<Idx>(i), lst[m] = static_cast<Idx>(c ^ 1u);
+            }
+            d = nd;
+          }
+          const unsigned h = atomicAdd(&s_misc[0], 1u);
+          heads[h].key = dotLR(static_cast<double>(a.x), static_cast<double>(a.y), static_cast<double>(a.z), P.L.dir);
+          heads[h].e = forward ? c : (tailF ^ 1u);
+          heads[h].tag = best;
+        }
+        // a loop whose lowest tag is odd is the mirror image of a loop handled (or to be handled) above; the walk of
+        // its canonical twin rewrites these darts, so nothing to do here
+      }
+      // whatever is still marked as cyclic now belongs to mirror loops whose canonical twin was visited later
+      for (unsigned e0 = 0; e0 < E; ++e0)
+        if (nxt[e0] != kNone)
+          nxt[e0] = kNone, rnk[e0] = 0, lst[e0] = static_cast<Idx>(e0);
+    }
+    __syncthreads();
+  }
+
   // twin[] is still needed to find heads: collect first, then reuse
   for (unsigned e = tid; e < E; e += nth)
   {
@@ -462,9 +610,9 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
       continue;  // interior end, or dead line (twin == self)
     // open end: head of the dart list that starts here
     const unsigned tail = lst[e];
-    const unsigned tagFirst = W.etag[e], tagLast = W.etag[tail ^ 1u];
-    const CutPoint a = cutPointOfTag(P, org, tagFirst, false);
-    const CutPoint b = cutPointOfTag(P, org, tagLast, false);
+    const unsigned tagFirst = endTag(e), tagLast = endTag(tail ^ 1u);
+    const CutPoint a = cutPointOfTag(P, org, W.etag[e], false);
+    const CutPoint b = cutPointOfTag(P, org, W.etag[tail ^ 1u], false);
     const double d = dotLR(dsub(static_cast<double>(b.x), static_cast<double>(a.x)),
                            dsub(static_cast<double>(b.y), static_cast<double>(a.y)),
                            dsub(static_cast<double>(b.z), static_cast<double>(a.z)), P.L.dir);
@@ -598,7 +746,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
 __global__ void __launch_bounds__(512, 1) k_link_planes(LinkParams P)
 {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ unsigned s_misc[8];
+  __shared__ unsigned s_misc[kMiscWords];
   __shared__ unsigned s_ticket;
   const long long nP = P.L.plane_end - P.L.plane_begin;
 

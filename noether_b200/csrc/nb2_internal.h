@@ -39,7 +39,12 @@ struct DevBuf
 {
   void* ptr = nullptr;
   size_t cap = 0;
+  // a caller-owned device pointer may temporarily stand in for the owned allocation (zero-copy ingest)
+  void* own_ptr = nullptr;
+  size_t own_cap = 0;
+  bool borrowed = false;
   void ensure(size_t bytes);
+  void adopt(void* device_ptr);
   void release();
   template <typename T>
   T* as() const
@@ -160,6 +165,7 @@ struct nb2_context
   nb2_lattice last_lattice{};
   bool have_lattice = false;
   nb2::StageTimer timer;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // nb2_timer_start / nb2_timer_stop
 
   // NCCL (dlopen'ed lazily)
   void* nccl_comm = nullptr;

@@ -122,6 +122,15 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.nb2_kernel_launches(self._h))
 
+    def timer_start(self):
+        _capi.check(self._lib.nb2_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Elapsed device time (ms) since timer_start, from CUDA events on the context's stream."""
+        ms = C.c_float()
+        _capi.check(self._lib.nb2_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
     # -- multi-GPU --------------------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -38,6 +38,7 @@ struct CutOutput
   std::vector<V3f> nrms;
   std::vector<uint32_t> lo, hi;
   std::vector<std::array<int64_t, 2>> lines;
+  std::vector<uint64_t> line_cell;  // input cell that produced each line
 };
 
 struct FloatKey
@@ -174,7 +175,10 @@ void cutPlane(const Mesh& m,
       }
     }
     if (pts[0] != pts[1])
+    {
       out.lines.push_back({ pts[0], pts[1] });
+      out.line_cell.push_back(cell);
+    }
   }
 }
 
@@ -471,80 +475,100 @@ int joinContiguousSegments(std::vector<IdList>& segs)
   return ORC_OK;
 }
 
-/** Maximal open chains of the cut graph in a canonical orientation and order (the reference's documented contract,
- *  plane_slicer_raster_planner.cpp:290-301; see DESIGN.md "intent mode"):
- *   - orientation: (p_last - p_first) . cut_direction >= 0 (double, left-to-right sum); a zero dot keeps the end with
- *     the lower first-inserter rank (= lower vtk point id) first;
- *   - order within the plane: ascending p_first . cut_direction, ties by first-inserter rank. */
+/** Chains of the cut graph in a canonical orientation and order — the reference's documented contract ("joins
+ *  contiguous line segments", plane_slicer_raster_planner.cpp:290-301) made independent of traversal order; see
+ *  DESIGN.md "intent mode".
+ *
+ *  Every 2-point line has two ends; end tag = 2 * cell id + end index (the order in which vtkCutter produced them).
+ *   - pairing: at each merged cut point the incident line ends are sorted by tag and paired consecutively
+ *     (1st with 2nd, 3rd with 4th, ...); an unpaired end is an open end.  At an ordinary point (two incident lines)
+ *     this is simply "the two lines continue into each other".
+ *   - open chain: walk from an open end to the other open end.  Orientation: (p_last - p_first) . cut_direction > 0
+ *     (double, left-to-right sum); on a zero dot the open end with the lower tag comes first.
+ *   - closed loop (no open end): starts at end 0 of its lowest-tag line and first walks that line (what vtkStripper
+ *     does from its seed); reversed, keeping the start point, when that first step . cut_direction < 0.  The start
+ *     point is repeated at the end, as vtkStripper emits a closed polyline.
+ *   - order within the plane: ascending p_first . cut_direction, ties by the tag of the chain's first line end. */
 int maximalChains(const CutOutput& cut, const V3d& ref, std::vector<IdList>& segs)
 {
   const size_t np = cut.pts.size();
-  std::vector<std::array<int64_t, 2>> nb(np, { -1, -1 });
-  std::vector<int> deg(np, 0);
-  for (const auto& l : cut.lines)
-  {
-    for (int e = 0; e < 2; ++e)
+  const size_t nl = cut.lines.size();
+  const size_t ne = 2 * nl;
+  auto tagOf = [&](size_t e) { return 2 * cut.line_cell[e >> 1] + (e & 1); };
+  auto pointOf = [&](size_t e) { return cut.lines[e >> 1][e & 1]; };
+  // incident ends per point, ascending tag (lines are stored in cell order, so ascending end index)
+  std::vector<std::vector<size_t>> ends(np);
+  for (size_t e = 0; e < ne; ++e)
+    ends[pointOf(e)].push_back(e);
+  const size_t kNone = static_cast<size_t>(-1);
+  std::vector<size_t> twin(ne, kNone);
+  for (const auto& v : ends)
+    for (size_t i = 0; i + 1 < v.size(); i += 2)
     {
-      const int64_t a = l[e], b = l[1 - e];
-      if (deg[a] >= 2)
-      {
-        setError("cut point with more than two incident lines (non-manifold cut)");
-        return ORC_ERR_NON_MANIFOLD;
-      }
-      nb[a][deg[a]++] = b;
+      twin[v[i]] = v[i + 1];
+      twin[v[i + 1]] = v[i];
     }
-  }
-  std::vector<char> used(np, 0);
-  size_t lines_used = 0;
+
   struct Keyed
   {
     double key;
-    int64_t rank;
+    uint64_t tag;
     IdList ids;
   };
   std::vector<Keyed> chains;
+  std::vector<char> used(nl, 0);
   auto dotLR = [&](const V3d& a) { return (a.x * ref.x + a.y * ref.y) + a.z * ref.z; };
-  for (size_t p = 0; p < np; ++p)
+
+  // open chains
+  for (size_t e0 = 0; e0 < ne; ++e0)
   {
-    if (deg[p] != 1 || used[p])
+    if (twin[e0] != kNone || used[e0 >> 1])
       continue;
     IdList ids;
-    int64_t prev = -1, cur = static_cast<int64_t>(p);
+    size_t e = e0, last_end = e0;
     while (true)
     {
-      ids.push_back(cur);
-      used[cur] = 1;
-      int64_t next = -1;
-      for (int k = 0; k < deg[cur]; ++k)
-        if (nb[cur][k] != prev)
-          next = nb[cur][k];
-      // a 2-cycle (two lines between the same pair of points) would make nb[cur] = {prev, prev}
-      if (deg[cur] == 2 && nb[cur][0] == nb[cur][1])
-      {
-        setError("duplicate cut line between the same pair of points (non-manifold cut)");
-        return ORC_ERR_NON_MANIFOLD;
-      }
-      if (next < 0)
+      used[e >> 1] = 1;
+      ids.push_back(pointOf(e));
+      last_end = e ^ 1;
+      const size_t nx = twin[e ^ 1];
+      if (nx == kNone)
         break;
-      ++lines_used;
-      prev = cur;
-      cur = next;
+      e = nx;
     }
-    const V3d d = pointD(cut, ids.back()) - pointD(cut, ids.front());
-    const double dd = dotLR(d);
-    if (dd < 0.0 || (dd == 0.0 && ids.back() < ids.front()))
+    ids.push_back(pointOf(last_end));
+    const double dd = dotLR(pointD(cut, ids.back()) - pointD(cut, ids.front()));
+    uint64_t first_tag = tagOf(e0);
+    if (dd < 0.0 || (dd == 0.0 && tagOf(last_end) < tagOf(e0)))
+    {
       std::reverse(ids.begin(), ids.end());
-    chains.push_back({ dotLR(pointD(cut, ids.front())), ids.front(), std::move(ids) });
+      first_tag = tagOf(last_end);
+    }
+    chains.push_back({ dotLR(pointD(cut, ids.front())), first_tag, std::move(ids) });
   }
-  if (lines_used != cut.lines.size())
+  // closed loops
+  for (size_t l = 0; l < nl; ++l)
   {
-    setError("cut lines form a closed loop");
-    return ORC_ERR_CLOSED_LOOP;
+    if (used[l])
+      continue;
+    IdList ids;
+    size_t e = 2 * l;
+    while (!used[e >> 1])
+    {
+      used[e >> 1] = 1;
+      ids.push_back(pointOf(e));
+      e = twin[e ^ 1];
+    }
+    ids.push_back(ids.front());
+    const double dd = dotLR(pointD(cut, ids[1]) - pointD(cut, ids[0]));
+    if (dd < 0.0)
+      std::reverse(ids.begin(), ids.end());
+    chains.push_back({ dotLR(pointD(cut, ids.front())), tagOf(2 * l), std::move(ids) });
   }
   std::sort(chains.begin(), chains.end(), [](const Keyed& a, const Keyed& b) {
     if (a.key != b.key)
       return a.key < b.key;
-    return a.rank < b.rank;
+    return a.tag < b.tag;
   });
   segs.clear();
   for (auto& c : chains)

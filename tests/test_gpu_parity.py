@@ -343,12 +343,16 @@ def test_plan_errors(ctx, orc):
     ctx.upload(tube, force=True)
     p = orc.pca(v, orc.MOMENTS_F64)
     lat = orc.make_lattice(p, [1, 0, 0], [0, 0, 5.0], 0.7, True)
-    with pytest.raises(orc.OracleError) as oe:
-        orc.slice_mesh(v, nr, f, lat, orc.SLICE_INTENT)
-    assert oe.value.code == orc.ERR_CLOSED_LOOP
-    with pytest.raises(_capi.Nb2Error) as e:
-        ctx.slice(capi_lattice_from_oracle(lat))
-    assert e.value.status == _capi.NB2_ERR_CLOSED_LOOP
+    # closed contours come out as closed segments (first point repeated), exactly as the reference's vtkStripper
+    # emits a loop it can walk in one piece: intent and faithful modes agree, and so does the GPU
+    ref = orc.slice_mesh(v, nr, f, lat, orc.SLICE_INTENT).flat()
+    faithful = orc.slice_mesh(v, nr, f, lat, orc.SLICE_FAITHFUL).flat()
+    np.testing.assert_array_equal(ref.pose, faithful.pose)
+    gpu = ctx.slice(capi_lattice_from_oracle(lat))
+    assert_same_paths(gpu, ref, "closed loops")
+    b, e = int(gpu.segment_offsets[0]), int(gpu.segment_offsets[1])
+    assert e - b == n * 2 + 1 or e - b > n
+    np.testing.assert_array_equal(gpu.positions[b], gpu.positions[e - 1])
     with pytest.raises(_capi.Nb2Error):
         pl.set_line_spacing(0.0)
         pl.plan(tube)
@@ -412,7 +416,10 @@ def test_cfg2_properties(ctx, orc):
     e0 = np.stack([gpu.edge_lo, gpu.edge_hi], 1)
     same_seg = seg_of_wp[1:] == seg_of_wp[:-1]
     share = (e0[1:, :, None] == e0[:-1, None, :]).any(axis=(1, 2))
-    assert np.all(share[same_seg])
+    # (a waypoint that landed exactly on a mesh vertex reports the edge of its first inserter, which may belong to a
+    # neighbouring triangle of the fan)
+    on_vertex = (gpu.positions == xyz[gpu.edge_hi]).all(1) | (gpu.positions == xyz[gpu.edge_lo]).all(1)
+    assert np.all((share | on_vertex[1:] | on_vertex[:-1])[same_seg])
     # and the binned oracle agrees bit for bit on the whole 1 M-triangle plan
     paths, lat_o, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.005, True, moments_mode=orc.MOMENTS_F64,
                                             slice_mode=orc.SLICE_INTENT, scan_mode=orc.SCAN_BINNED)
