@@ -294,18 +294,28 @@ def main():
     sampler = ClockSampler(info.local_rank)
     stage_acc: dict[str, list[float]] = {}
     launches0 = ctx.kernel_launches()
+    # L2 is flushed between timed iterations (a 256 MB write, outside the timed intervals): exactly K steps are timed,
+    # each bracketed by CUDA events on the library's stream; the K intervals are summed.
+    flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
+
+    def l2_flush():
+        flush.zero_()
+        torch.cuda.synchronize()
+
     barrier()
     sampler.start()
-    ctx.timer_start()
-    t0 = time.perf_counter()
     counts = None
+    dev_ms = wall_ms = 0.0
     for _ in range(args.steps):
+        l2_flush()
+        t0 = time.perf_counter()
+        ctx.timer_start()
         up, pl, counts = device_step()
+        dev_ms += ctx.timer_stop()
+        wall_ms += 1e3 * (time.perf_counter() - t0)
         for k, v in list(up.items()) + list(pl.items()):
             stage_acc.setdefault(k, []).append(v)
-    dev_ms = ctx.timer_stop()
     barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
     clocks = sampler.stop()
     launches = ctx.kernel_launches() - launches0
     dev_ms = max_over_ranks(dev_ms, info.world, dev)
@@ -316,12 +326,17 @@ def main():
     for _ in range(max(args.warmup, 3)):
         e2e_step()
     barrier()
-    t0 = time.perf_counter()
     totals, d2h_bytes = None, 0
+    e2e_total = 0.0
     for _ in range(args.steps):
+        l2_flush()
+        barrier()
+        t0 = time.perf_counter()
         totals, d2h_bytes = e2e_step()
+        torch.cuda.synchronize()
+        e2e_total += 1e3 * (time.perf_counter() - t0)
     barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0), info.world, dev) / args.steps
+    e2e_ms = max_over_ranks(e2e_total, info.world, dev) / args.steps
     h2d_bytes = int(blob.data.size + tri.size * 4)
 
     if info.rank != 0:
@@ -367,7 +382,7 @@ def main():
         "config": {"workload": f"{args.workload}: {desc}", "planes": P_planes, "tool_paths": int(n_paths),
                    "segments": int(n_segments), "waypoints": int(n_waypoints),
                    "parallelism": f"plane slabs x{info.world}" if info.world > 1 else "single GPU",
-                   "l2": "inputs (cloud + triangles = %d MB) are larger than the 126 MB L2" % (h2d_bytes // 2**20),
+                   "l2": "flushed between timed iterations (256 MB write outside the timed intervals); inputs are %d MB" % (h2d_bytes // 2**20),
                    "timing": "CUDA events on the library stream, max over ranks; wall clock %.3f ms/step" % (wall_ms / args.steps)},
         "clocks": clocks,
         "e2e": {"value": F / (e2e_ms / 1e3), "unit": "triangles/s", "ms_per_step": e2e_ms,

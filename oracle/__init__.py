@@ -321,15 +321,23 @@ def slice_mesh(xyz, normals, tri, lattice: Lattice, slice_mode=SLICE_FAITHFUL, s
 
 def plan_plane_slicer(xyz, normals, tri, line_spacing, bidirectional=True, direction=None, origin=None,
                       rotation_offset=0.0, moments_mode=MOMENTS_F32_SEQUENTIAL, slice_mode=SLICE_FAITHFUL,
-                      scan_mode=SCAN_ALL_CELLS, post_ops=True):
+                      scan_mode=SCAN_ALL_CELLS, post_ops=True, frame: Pca | None = None):
     """RasterPlanner::plan for PlaneSlicerRasterPlanner (raster_planner.cpp:16-35).
 
     direction=None -> PrincipalAxisDirectionGenerator(rotation_offset); origin=None -> CentroidOriginGenerator.
+    frame: use this PCA frame (mean, axes, scales — 15 floats) instead of accumulating moments here; the centroid
+    generator then returns the frame's mean.  Lets a test hand the oracle exactly the frame another implementation
+    computed, so that everything downstream of those 15 scalars can be compared bit for bit.
     Returns (Paths, Lattice, Pca).
     """
-    p = pca(xyz, moments_mode)
+    p = pca(xyz, moments_mode) if frame is None else frame
     d = principal_axis_direction(p, rotation_offset) if direction is None else np.asarray(direction, np.float64)
-    o = centroid(xyz, moments_mode) if origin is None else np.asarray(origin, np.float64)
+    if origin is not None:
+        o = np.asarray(origin, np.float64)
+    elif frame is not None:
+        o = np.asarray(frame.mean, np.float32).astype(np.float64)
+    else:
+        o = centroid(xyz, moments_mode)
     lat = make_lattice(p, d, o, line_spacing, bidirectional)
     paths = slice_mesh(xyz, normals, tri, lat, slice_mode, scan_mode)
     if post_ops and paths.flat().num_paths > 0:
