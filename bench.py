@@ -145,8 +145,9 @@ def algorithmic_bytes(stage: str, V: int, F: int, H: int, W: int, S: int, P: int
         "extents": 12 * V,
         "classify": 12 * V + 4 * V,
         "count": 12 * F + 4 * V,
-        "fill": 12 * F + 4 * V + 4 * H,
-        "link": 4 * H + 12 * H + 24 * W + 24 * W + 4 * S,  # bucket, triangles of hits, vertex data of cut edges, waypoints out
+        "emit": 12 * F + 4 * V + 32 * H,          # triangles, vertex classes, two 16-byte endpoint records per hit
+        "link": 32 * H + 8 * W + 4 * S,            # endpoint records in, one {rank, plane} word pair per waypoint out
+        "waypoints": 8 * W + 12 * W + 24 * W + 24 * W,  # tags, first-inserter triangles, cut-edge vertex data, waypoints out
         "scan": 8 * P,
     }
     return table.get(stage)

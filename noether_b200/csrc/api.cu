@@ -327,10 +327,14 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
 
   c->hostSmall.ensure(4096);
   unsigned* h = c->hostSmall.as<unsigned>();
-  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 9 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
   const uint64_t H = h[0];
   const uint32_t n_max = h[1];
+  if (h[8] >= c->V)  // counters[12]: largest out-of-range vertex index met by k_count_hits
+    fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[8]) + " but the cloud has " +
+                                       std::to_string(c->V) + " points");
+  c->tri_checked = true;
   if (H == 0)
     return emptyResult(c, lat);
   if (H >= (1ull << 30))
@@ -338,9 +342,9 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   if (n_max >= (1u << 19))
     fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects 2^19 or more triangles; not supported");
 
-  c->bucket.ensure(sizeof(uint32_t) * H);
-  launchFillBuckets(c, L);
-  c->timer.mark("fill", c->stream);
+  c->hitRec.ensure(sizeof(float4) * 2 * H);
+  launchEmitHits(c, L);
+  c->timer.mark("emit", c->stream);
 
   const uint64_t w_cap = 2 * H, s_cap = H;
   c->outPos.ensure(sizeof(float) * 3 * w_cap);
@@ -348,8 +352,10 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   if (emit_edges)
     c->outEdge.ensure(sizeof(uint32_t) * 2 * w_cap);
   c->outSegLen.ensure(sizeof(unsigned) * s_cap);
-  launchLinkPlanes(c, L, n_max, w_cap, s_cap, emit_edges ? 1 : 0);
+  launchLinkPlanes(c, L, n_max, H);
   c->timer.mark("link", c->stream);
+  launchWaypoints(c, L, w_cap, H + nP, emit_edges ? 1 : 0);
+  c->timer.mark("waypoints", c->stream);
 
   // totals, per-plane meta and status
   c->hostSmall.ensure(64 + sizeof(unsigned) * 2 * nP);
@@ -357,8 +363,8 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   auto* h64 = reinterpret_cast<unsigned long long*>(h);
   unsigned* hstat = h + 2;
   unsigned* hmeta = h + 16;
-  NB2_CUDA(cudaMemcpyAsync(h64, c->lookback.as<unsigned long long>() + (nP - 1), sizeof(unsigned long long),
-                           cudaMemcpyDeviceToHost, c->stream));
+  // counters[6..7] = waypoint / segment totals (k_scan_meta), counters[10..11] = link status
+  NB2_CUDA(cudaMemcpyAsync(h64, c->counters.as<unsigned>() + 6, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(hstat, c->counters.as<unsigned>() + 10, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
@@ -370,10 +376,10 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
     if (hstat[0] & 2u)
       fail(NB2_ERR_CLOSED_LOOP, "cut lines form a closed loop; the reference aborts such plans (Topological sort failed / "
                                 "not a DAG)" + where);
-    fail(NB2_ERR_INTERNAL, "output capacity exceeded while linking" + where);
+    fail(NB2_ERR_INTERNAL, "linking failed" + where);
   }
-  const uint64_t Wt = (h64[0] >> 31) & 0x7fffffffull;
-  const uint64_t St = h64[0] & 0x7fffffffull;
+  const uint64_t Wt = h[0];
+  const uint64_t St = h[1];
   uint64_t Pn = 0;
   for (uint64_t k = 0; k < nP; ++k)
     Pn += hmeta[2 * k + 1] > 0;
@@ -507,7 +513,7 @@ void nb2_context_destroy(nb2_context* c)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
   for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->counters, &c->vertK, &c->planeCnt,
-                     &c->planeOff, &c->planeCursor, &c->bucket, &c->lookback, &c->planeMeta, &c->outPos, &c->outNrm,
+                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->scanState })
     b->release();
@@ -566,8 +572,12 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     c->blob.ensure(V * m->point_step);
     NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, V * m->point_step, cudaMemcpyHostToDevice, c->stream));
   }
+  bool tri_adopted = false;
   if (F && onThisDevice(m->triangles))
+  {
     c->tri.adopt(const_cast<uint32_t*>(m->triangles));
+    tri_adopted = true;
+  }
   else
   {
     c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
@@ -582,8 +592,15 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     NB2_CUDA(cudaMemsetAsync(c->nrm.ptr, 0, sizeof(float4) * V, c->stream));
   launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
   c->timer.mark("ingest+moments", c->stream);
-  launchValidateTriangles(c);
-  c->timer.mark("validate", c->stream);
+  // Triangles copied from the host are range-checked now (noise next to the PCIe copy).  Triangles adopted in place
+  // from device memory are checked by the first kernel that streams them anyway (k_count_hits / the normals pass).
+  c->tri_checked = false;
+  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, sizeof(unsigned), c->stream));
+  if (!tri_adopted)
+  {
+    launchValidateTriangles(c);
+    c->timer.mark("validate", c->stream);
+  }
 
   c->hostSmall.ensure(4096);
   auto* h = c->hostSmall.as<uint8_t>();
@@ -610,6 +627,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(max_index) + " but the cloud has " +
                                        std::to_string(V) + " points");
   }
+  c->tri_checked = !tri_adopted;
   std::memset(&c->pca, 0, sizeof(c->pca));
   if (V >= 3)
     finalizeMoments(total, V, pivot, c->pca);
@@ -707,6 +725,19 @@ int nb2_normals_from_mesh_faces(nb2_context* c, float* normals_out)
   DeviceGuard g(c->device);
   requireMesh(c);
   c->timer.begin(c->stream);
+  if (!c->tri_checked && c->F)
+  {
+    launchValidateTriangles(c);
+    c->hostSmall.ensure(4096);
+    unsigned* h = c->hostSmall.as<unsigned>();
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+    if (h[0] >= c->V)
+      fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[0]) + " but the cloud has " +
+                                         std::to_string(c->V) + " points");
+    c->tri_checked = true;
+    c->timer.mark("validate", c->stream);
+  }
   launchVertexNormals(c);
   c->has_normals = true;
   if (normals_out)

@@ -74,11 +74,12 @@ __device__ __forceinline__ int contourCase(const double s[3])
   return (s[0] >= 0.0 ? 1 : 0) | (s[1] >= 0.0 ? 2 : 0) | (s[2] >= 0.0 ? 4 : 0);
 }
 
-/** Interpolate endpoint `which` (0/1) of the line of case `index`; normals only when nrm != nullptr.
+/** Interpolate endpoint `which` (0/1) of the line of case `index`; normals only when nv != nullptr (nv = the vertex
+ *  normals of the triangle's three vertices, already in registers).
  *  Restates vtkTriangle::Contour: interpolate from the lower- to the higher-scalar end, t = (0 - s_lo) / (s_hi - s_lo),
  *  x = x_lo + t (x_hi - x_lo) in double, stored as float; attributes a_lo (1 - t) + a_hi t in double, stored as float. */
 __device__ __forceinline__ CutPoint interpolateCut(int index, int which, const uint32_t ids[3], const float4 p[3],
-                                                   const double s[3], const float4* __restrict__ nrm)
+                                                   const double s[3], const float4* nv)
 {
   const int edge = lineCaseEdge(index, which);
   const int v0 = edge, v1 = edge == 2 ? 0 : edge + 1;
@@ -103,9 +104,9 @@ __device__ __forceinline__ CutPoint interpolateCut(int index, int which, const u
   c.z = __double2float_rn(dadd(static_cast<double>(a.z), dmul(t, dsub(static_cast<double>(b.z), static_cast<double>(a.z)))));
   c.lo = pick3(ids, e1);
   c.hi = pick3(ids, e2);
-  if (nrm != nullptr)
+  if (nv != nullptr)
   {
-    const float4 n1 = nrm[c.lo], n2 = nrm[c.hi];
+    const float4 n1 = pick3(nv, e1), n2 = pick3(nv, e2);
     const double omt = dsub(1.0, t);
     c.nx = __double2float_rn(dadd(dmul(static_cast<double>(n1.x), omt), dmul(static_cast<double>(n2.x), t)));
     c.ny = __double2float_rn(dadd(dmul(static_cast<double>(n1.y), omt), dmul(static_cast<double>(n2.y), t)));

@@ -4,16 +4,20 @@
 // (plane_slicer_raster_planner.cpp:596-628).  Here the loop is inverted:
 //
 //   S2  k_count_hits   : each triangle projects onto the plane lattice through the per-vertex indices K_v
-//                        (k_classify) and bumps a per-plane hit counter
+//                        (k_classify) and bumps a per-plane hit counter; vertex indices are range-checked on the way
 //   S3  k_scan_planes  : exclusive scan of the per-plane counters -> bucket offsets (+ total hits, largest plane)
-//   S4  k_fill_buckets : each (triangle, plane) hit drops its triangle id into the plane's bucket
-//   S5  k_link_planes  : one persistent CTA per plane: contour every hit exactly as vtkTriangle::Contour does,
-//                        merge cut points exactly as vtkMergePoints does (float-coordinate equality, staged in a
-//                        shared-memory hash), pair the lines at shared points, rank the chains by pointer jumping,
-//                        orient and order them, size the output through a decoupled look-back across planes, and
-//                        write ordered waypoints (position, interpolated normal, generating mesh edge)
+//   S4  k_emit_hits    : the triangles are streamed a second time; every (triangle, plane) hit is contoured exactly as
+//                        vtkTriangle::Contour does, where the triangle's vertices are hot in cache, and its two cut
+//                        points (float32 position + first-inserter rank) are appended to the plane's bucket
+//   S5  k_link_planes  : one persistent CTA per plane, shared memory only: merge cut points exactly as vtkMergePoints
+//                        does (float-coordinate equality, shared-memory hash), pair the lines at shared points, rank
+//                        the chains by pointer jumping, orient and order them, size the output through a decoupled
+//                        look-back across planes, and write, per output waypoint, the rank (triangle, line end) of the
+//                        cut point that inserted it first
+//   S6  k_waypoints    : one thread per output waypoint: re-contour the first inserter, interpolate the vertex normals
+//                        along the cut edge, write position / normal / generating mesh edge
 //
-// Output of S5 is the reference's planImpl result before convertToPoses expands it to 4x4 matrices.
+// Output of S6 is the reference's planImpl result before convertToPoses expands it to 4x4 matrices.
 #include "device_math.cuh"
 #include "nb2_internal.h"
 
@@ -27,19 +31,39 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCountThreads = 256;
 constexpr int kSmemBins = 8192;  // per-block privatised plane histogram (32 KB)
 
-__device__ __forceinline__ void triangleSpan(const uint32_t* __restrict__ tri, const int* __restrict__ vertK,
-                                             unsigned long long t, const LatticeDev& L, long long& k0, long long& k1)
+/** Four consecutive triangles per thread: three 16-byte loads when the index array is 16-byte aligned. */
+__device__ __forceinline__ int loadQuad(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long q,
+                                        bool aligned, uint32_t id[12])
 {
-  const uint32_t a = __ldg(tri + 3 * t), b = __ldg(tri + 3 * t + 1), c = __ldg(tri + 3 * t + 2);
-  const int ka = __ldg(vertK + a), kb = __ldg(vertK + b), kc = __ldg(vertK + c);
+  const unsigned long long t0 = 4ull * q;
+  if (aligned && t0 + 4 <= F)
+  {
+    const uint4* p = reinterpret_cast<const uint4*>(tri) + 3ull * q;
+    const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    id[0] = a.x, id[1] = a.y, id[2] = a.z, id[3] = a.w;
+    id[4] = b.x, id[5] = b.y, id[6] = b.z, id[7] = b.w;
+    id[8] = c.x, id[9] = c.y, id[10] = c.z, id[11] = c.w;
+    return 4;
+  }
+  const int n = static_cast<int>(F - t0 < 4ull ? F - t0 : 4ull);
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+    id[i] = (i < 3 * n) ? __ldg(tri + 3ull * t0 + i) : 0u;
+  return n;
+}
+
+/** Lattice planes [k0, k1] (clamped to the slab) that cut a triangle whose vertices classify as ka, kb, kc */
+__device__ __forceinline__ void planeSpan(int ka, int kb, int kc, const LatticeDev& L, long long& k0, long long& k1)
+{
   const int lo = min(ka, min(kb, kc)), hi = max(ka, max(kb, kc));
   k0 = max(static_cast<long long>(lo) + 1, L.plane_begin);
   k1 = min(static_cast<long long>(hi), L.plane_end - 1);
 }
 
 __global__ void __launch_bounds__(kCountThreads)
-    k_count_hits(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK, LatticeDev L,
-                 unsigned* __restrict__ planeCnt, int use_smem)
+    k_count_hits(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
+                 const int* __restrict__ vertK, LatticeDev L, unsigned* __restrict__ planeCnt, int use_smem, int aligned,
+                 unsigned* __restrict__ maxIndex)
 {
   __shared__ unsigned s_bins[kSmemBins];
   const long long nP = L.plane_end - L.plane_begin;
@@ -49,17 +73,40 @@ __global__ void __launch_bounds__(kCountThreads)
       s_bins[i] = 0;
     __syncthreads();
   }
+  const unsigned long long Q = (F + 3) / 4;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  for (unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < F; t += stride)
+  for (unsigned long long q = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < Q; q += stride)
   {
-    long long k0, k1;
-    triangleSpan(tri, vertK, t, L, k0, k1);
-    for (long long k = k0; k <= k1; ++k)
+    uint32_t id[12];
+    const int n = loadQuad(tri, F, q, aligned != 0, id);
+    // range check of the vertex indices (the reference would read out of bounds; here the plan fails instead)
+    uint32_t m = id[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i)
+      m = max(m, id[i]);
+    if (m >= V)
     {
-      if (use_smem)
-        atomicAdd(&s_bins[k - L.plane_begin], 1u);
-      else
-        atomicAdd(&planeCnt[k - L.plane_begin], 1u);
+      atomicMax(maxIndex, m);
+      continue;
+    }
+    int K[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+      K[i] = __ldg(vertK + id[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      if (i >= n)
+        break;
+      long long k0, k1;
+      planeSpan(K[3 * i], K[3 * i + 1], K[3 * i + 2], L, k0, k1);
+      for (long long k = k0; k <= k1; ++k)
+      {
+        if (use_smem)
+          atomicAdd(&s_bins[k - L.plane_begin], 1u);
+        else
+          atomicAdd(&planeCnt[k - L.plane_begin], 1u);
+      }
     }
   }
   if (use_smem)
@@ -77,7 +124,7 @@ __global__ void __launch_bounds__(kCountThreads)
 /** Single-block exclusive scan of the per-plane counters.  out[0] = total hits, out[1] = largest plane. */
 __global__ void __launch_bounds__(1024)
     k_scan_planes(const unsigned* __restrict__ cnt, long long nP, unsigned* __restrict__ off, unsigned* __restrict__ cursor,
-                  unsigned long long* __restrict__ lookback, unsigned* __restrict__ out2)
+                  unsigned* __restrict__ out2)
 {
   __shared__ unsigned s_warp[32];
   __shared__ unsigned s_carry;
@@ -122,7 +169,6 @@ __global__ void __launch_bounds__(1024)
     {
       off[i] = incl - v;
       cursor[i] = 0;
-      lookback[i] = 0ull;
     }
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1)
@@ -146,20 +192,116 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
-__global__ void __launch_bounds__(kCountThreads)
-    k_fill_buckets(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK, LatticeDev L,
-                   const unsigned* __restrict__ planeOff, unsigned* __restrict__ cursor, uint32_t* __restrict__ bucket)
+/**
+ * S4.  Contour every (triangle, plane) hit where the triangles are streamed: the three vertices of a triangle are
+ * shared with its neighbours in the stream, so the position gathers hit L1/L2.  A hit appends two endpoint records
+ * {x, y, z, rank} to its plane's bucket; rank = 2 * triangle + line end is the order in which vtkCutter (cells in id
+ * order, vtkTriangle::Contour inserting pts[0] then pts[1]) would have inserted the point.  The order of the hits
+ * inside a bucket is arbitrary (integer atomics on the cursors); every later decision is made on ranks, never on bucket
+ * positions, so the result does not depend on it.
+ *
+ * Only a fraction of the triangles is cut by any plane, and contouring is ~200 fp64 instructions, so the block first
+ * lists the hits of a tile of triangles in shared memory (block scan of the per-thread hit counts) and then contours
+ * them with all lanes busy.
+ */
+constexpr int kEmitThreads = 256;
+constexpr int kEmitList = 2048;  // hits contoured per round of a tile
+
+__global__ void __launch_bounds__(kEmitThreads)
+    k_emit_hits(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK,
+                const float4* __restrict__ pos, LatticeDev L, const unsigned* __restrict__ planeOff,
+                unsigned* __restrict__ cursor, float4* __restrict__ rec, int aligned)
 {
-  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  for (unsigned long long t = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < F; t += stride)
+  __shared__ uint2 s_list[kEmitList];  // {triangle, slab-local plane}
+  __shared__ unsigned s_warp[kEmitThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long Q = (F + 3) / 4;
+  const unsigned long long tiles = (Q + kEmitThreads - 1) / kEmitThreads;
+  for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
   {
-    long long k0, k1;
-    triangleSpan(tri, vertK, t, L, k0, k1);
-    for (long long k = k0; k <= k1; ++k)
+    const unsigned long long q = tile * kEmitThreads + threadIdx.x;
+    int k0[4];
+    unsigned cnt[4] = { 0u, 0u, 0u, 0u };
+    if (q < Q)
     {
-      const long long b = k - L.plane_begin;
-      const unsigned slot = __ldg(planeOff + b) + atomicAdd(&cursor[b], 1u);
-      bucket[slot] = static_cast<uint32_t>(t);
+      uint32_t id[12];
+      const int n = loadQuad(tri, F, q, aligned != 0, id);
+      int K[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        K[i] = __ldg(vertK + id[i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        long long a, b;
+        planeSpan(K[3 * i], K[3 * i + 1], K[3 * i + 2], L, a, b);
+        k0[i] = static_cast<int>(a - L.plane_begin);
+        cnt[i] = (i < n && b >= a) ? static_cast<unsigned>(b - a + 1) : 0u;
+      }
+    }
+    // block-wide exclusive scan of the per-thread hit counts
+    const unsigned mine = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    unsigned x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o)
+        x += y;
+    }
+    __syncthreads();  // the previous tile's readers of s_warp / s_list are done
+    if (lane == 31)
+      s_warp[warp] = x;
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEmitThreads / 32; ++w)
+    {
+      const unsigned t = s_warp[w];
+      before += (w < warp) ? t : 0u;
+      total += t;
+    }
+    const unsigned first = before + x - mine;  // tile-local index of this thread's first hit
+
+    for (unsigned w0 = 0; w0 < total; w0 += kEmitList)
+    {
+      if (w0)
+        __syncthreads();
+      // scatter this thread's hits that fall into the window [w0, w0 + kEmitList)
+      unsigned at = first;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        if (cnt[i] && at + cnt[i] > w0 && at < w0 + kEmitList)
+        {
+          const unsigned jb = at < w0 ? w0 - at : 0u;
+          const unsigned je = min(cnt[i], w0 + kEmitList - at);
+          const unsigned t = static_cast<unsigned>(4ull * q + i);
+          for (unsigned j = jb; j < je; ++j)
+            s_list[at + j - w0] = make_uint2(t, static_cast<unsigned>(k0[i]) + j);
+        }
+        at += cnt[i];
+      }
+      __syncthreads();
+      const unsigned m = min(total - w0, static_cast<unsigned>(kEmitList));
+      for (unsigned h = threadIdx.x; h < m; h += kEmitThreads)
+      {
+        const uint2 hit = s_list[h];
+        const unsigned t = hit.x;
+        const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
+        const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
+        const unsigned slot = __ldg(planeOff + hit.y) + atomicAdd(&cursor[hit.y], 1u);
+        const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(hit.y));
+        double s[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+        const int index = contourCase(s);
+        const CutPoint c0 = interpolateCut(index, 0, ids, p, s, nullptr);
+        const CutPoint c1 = interpolateCut(index, 1, ids, p, s, nullptr);
+        rec[2ull * slot] = make_float4(c0.x, c0.y, c0.z, __uint_as_float(2u * t));
+        rec[2ull * slot + 1] = make_float4(c1.x, c1.y, c1.z, __uint_as_float(2u * t + 1u));
+      }
     }
   }
 }
@@ -177,43 +319,33 @@ struct Slot
 
 struct LinkParams
 {
-  const uint32_t* tri;
-  const float4* pos;
-  const float4* nrm;
+  const float4* rec;  // [2 * H] endpoint records {x, y, z, rank bits}, grouped by plane (k_emit_hits)
   const unsigned* planeOff;
-  const uint32_t* bucket;
   LatticeDev L;
-  unsigned long long* lookback;
   unsigned* ticket;
-  unsigned* planeMeta;  // [2 * nP] waypoints, segments
-  float* outPos;
-  float* outNrm;
-  uint32_t* outEdgeLo;
-  uint32_t* outEdgeHi;
-  unsigned* outSegLen;
+  unsigned* planeMeta;  // [2 * nP] waypoints, segments of each plane
+  // A plane with n hits yields at most 2 n waypoints and n segments, so plane k writes its waypoint ranks at
+  // wpTag[2 * planeOff[k] ...] and its segment lengths at segLen[planeOff[k] ...]: no plane waits for another one.
+  // k_scan_meta + k_waypoints close the gaps.
+  unsigned* wpTag;   // [2 * H] rank (2 * triangle + line end) of the first inserter of each waypoint
+  unsigned* segLen;  // [H]
   unsigned* status;  // [0] error bits, [1] first failing plane
   uint8_t* scratch;  // global work areas for planes that do not fit shared memory
   unsigned long long scratchStride;
   unsigned smemHitCap;  // largest plane (in hits) that fits the shared-memory work area
-  unsigned long long wCap, sCap;
-  int emitEdges;
 };
 
-constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u, kErrOverflow = 4u;
+constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u;
 // pairing cell of a hash slot: [31:20] number of line ends at the point, [19:0] last line end that arrived
 constexpr unsigned kCellShift = 20u, kCellMask = (1u << kCellShift) - 1u;
 constexpr unsigned kMaxCrowded = 16u;      // points with more than two incident lines handled per plane
 constexpr unsigned kMaxCrowdedEnds = 32u;  // line ends at one such point
-// s_misc: [0] chains, [1] error bits, [2] baseW, [3] baseS, [4] plane waypoints, [5] ranking flag, [6] crowded points,
+// s_misc: [0] chains, [1] error bits, [2] splitters, [4] plane waypoints, [5] ranking flag, [6] crowded points,
 //         [7] closed loops present, [8..] crowded slot ids
 constexpr int kMiscWords = 8 + kMaxCrowded;
-
-// look-back status word: [63:62] flag, [61:31] waypoints, [30:0] segments
-constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62;
-__device__ __forceinline__ unsigned long long packStatus(unsigned long long flag, unsigned long long w, unsigned long long s)
-{
-  return flag | (w << 31) | s;
-}
+constexpr int kLinkThreads = 1024;
+// list ranking: both darts of every (1 << kSplitShift)-th line of the bucket are splitters (Helman & JaJa)
+constexpr unsigned kSplitShift = 4u, kSplitMask = (1u << kSplitShift) - 1u;
 
 __device__ __forceinline__ unsigned hashPoint(float x, float y, float z)
 {
@@ -233,37 +365,13 @@ __device__ __forceinline__ unsigned hashPoint(float x, float y, float z)
 template <typename Idx>
 struct PlaneWork
 {
-  float* epos;     // [3 * E]   endpoint positions (phase A/H); later ping-pong ranking buffers
-  unsigned* etag;  // [E]       slot index, later the merged point's first-inserter rank
-  Idx* twin;       // [E]       endpoint sharing the same cut point in another line
-  Slot* slots;     // [cap]     hash of cut points; later chain heads
-  unsigned cap;    // power of two >= E
+  float* epos;      // [3 * E]   endpoint positions (phase A/H); later the list-ranking arrays
+  size_t eposBytes; //           size of that region: 12 E with 16-bit indices, 32 E with 32-bit indices
+  unsigned* etag;   // [E]       slot index, later the merged point's first-inserter rank
+  Idx* twin;        // [E]       endpoint sharing the same cut point in another line
+  Slot* slots;      // [cap]     hash of cut points; later list-ranking arrays, then chain heads
+  unsigned cap;     // power of two >= E
 };
-
-template <typename Idx>
-__host__ __device__ inline size_t planeWorkBytes(unsigned hits)
-{
-  const size_t E = 2 * static_cast<size_t>(hits);
-  size_t cap = 16;
-  while (cap < E)
-    cap <<= 1;
-  const size_t a = 12 * E;  // epos; ranking needs 2 buffers x 3 arrays x sizeof(Idx) x E <= 12 E for Idx <= 2 bytes
-  const size_t rank = 6 * sizeof(Idx) * E;
-  return (a > rank ? a : rank) + 4 * E + sizeof(Idx) * E + 8 * cap + 64;
-}
-
-/** The triangle of first-inserter rank `tag` contoured against plane k: endpoint tag & 1 */
-__device__ __forceinline__ CutPoint cutPointOfTag(const LinkParams& P, const PlaneOrigin& o, unsigned tag, bool with_normal)
-{
-  const unsigned t = tag >> 1;
-  uint32_t ids[3] = { __ldg(P.tri + 3ull * t), __ldg(P.tri + 3ull * t + 1), __ldg(P.tri + 3ull * t + 2) };
-  float4 p[3] = { __ldg(P.pos + ids[0]), __ldg(P.pos + ids[1]), __ldg(P.pos + ids[2]) };
-  double s[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    s[i] = planeScalar(P.L, o, p[i].x, p[i].y, p[i].z);
-  return interpolateCut(contourCase(s), tag & 1, ids, p, s, with_normal ? P.nrm : nullptr);
-}
 
 template <typename Idx>
 __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long long kLocal, unsigned n, unsigned* s_misc)
@@ -271,35 +379,25 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   constexpr Idx kNone = static_cast<Idx>(~static_cast<Idx>(0));
   const unsigned E = 2 * n;
   const unsigned tid = threadIdx.x, nth = blockDim.x;
-  const long long k = P.L.plane_begin + kLocal;
-  const PlaneOrigin org = planeOrigin(P.L, k);
   const unsigned off = P.planeOff[kLocal];
   const unsigned mask = W.cap - 1;
+  const float4* __restrict__ rec = P.rec + 2ull * off;  // this plane's endpoint records
+  // rank (2 * triangle + line end) and float32 position of endpoint e, straight from the records (L2 resident)
+  auto endTag = [&](unsigned e) { return __float_as_uint(__ldg(reinterpret_cast<const float*>(rec + e) + 3)); };
+  auto endPos = [&](unsigned e) { return __ldg(rec + e); };
 
   // s_misc: [0] nHeads, [1] local error bits, [2] baseW, [3] baseS, [4] totalW, [5] any-unfinished flag
   if (tid < kMiscWords)
     s_misc[tid] = 0;
 
-  // ---- A: contour every hit (vtkTriangle::Contour) ----------------------------------------------------------------
-  for (unsigned j = tid; j < n; j += nth)
+  // ---- A: stage the plane's endpoint records (coalesced 16-byte loads) ---------------------------------------------
+  for (unsigned e = tid; e < E; e += nth)
   {
-    const unsigned t = __ldg(P.bucket + off + j);
-    uint32_t ids[3] = { __ldg(P.tri + 3ull * t), __ldg(P.tri + 3ull * t + 1), __ldg(P.tri + 3ull * t + 2) };
-    float4 p[3] = { __ldg(P.pos + ids[0]), __ldg(P.pos + ids[1]), __ldg(P.pos + ids[2]) };
-    double s[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      s[i] = planeScalar(P.L, org, p[i].x, p[i].y, p[i].z);
-    const int index = contourCase(s);
-#pragma unroll
-    for (int w = 0; w < 2; ++w)
-    {
-      const CutPoint c = interpolateCut(index, w, ids, p, s, nullptr);
-      float* e = W.epos + 3 * (2 * j + w);
-      e[0] = c.x;
-      e[1] = c.y;
-      e[2] = c.z;
-    }
+    const float4 r = __ldg(rec + e);
+    W.epos[3 * e] = r.x;
+    W.epos[3 * e + 1] = r.y;
+    W.epos[3 * e + 2] = r.z;
+    W.etag[e] = __float_as_uint(r.w);
   }
   for (unsigned s = tid; s < W.cap; s += nth)
   {
@@ -312,7 +410,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   for (unsigned e = tid; e < E; e += nth)
   {
     const float x = W.epos[3 * e], y = W.epos[3 * e + 1], z = W.epos[3 * e + 2];
-    const unsigned tag = 2u * __ldg(P.bucket + off + (e >> 1)) + (e & 1u);
+    const unsigned tag = W.etag[e];
     unsigned s = hashPoint(x, y, z) & mask;
     while (true)
     {
@@ -401,12 +499,12 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
           break;
         }
         // insertion sort by line-end tag
-        const unsigned tg = 2u * __ldg(P.bucket + off + (e >> 1)) + (e & 1u);
+        const unsigned tg = endTag(e);
         unsigned j = cnt++;
         while (j > 0)
         {
           const unsigned o = mem[j - 1];
-          const unsigned to = 2u * __ldg(P.bucket + off + (o >> 1)) + (o & 1u);
+          const unsigned to = endTag(o);
           if (to < tg)
             break;
           mem[j] = o;
@@ -445,74 +543,150 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   if (s_misc[1] & kErrNonManifold)
     return;
 
-  // ---- R: rank the darts of every chain by pointer jumping (Wyllie), both directions ---------------------------------
-  // dart e = "traverse line e>>1 starting at end e"; next(e) = twin(e ^ 1)
-  Idx* buf[2][3];
+  // ---- R: list ranking of the darts (Helman & JaJa: splitters, sequential sublist walks, pointer jumping on the
+  //         splitters only) ----------------------------------------------------------------------------------------
+  // dart e = "traverse line e >> 1 starting at its end e"; next(e) = twin(e ^ 1).  Wanted per dart: rnk = number of
+  // hops to the last dart of its list, lst = that last dart.  Every open chain gives two lists (one per direction).
+  // Splitters are the list heads (darts starting at an open end) plus both darts of every 16th line of the bucket; each
+  // splitter walks its sublist (about 16 hops) up to the next splitter, then only the ~E/16 splitters are ranked by
+  // pointer jumping: O(E) work instead of Wyllie's O(E log E).
+  Idx* const r1 = reinterpret_cast<Idx*>(W.epos);
+  Idx* const lst = r1;                 // during the walk: owner = compact index of the splitter whose sublist holds e
+  Idx* const rnk = r1 + E;             // during the walk: hops from that splitter
+  Idx* const chainEnd = r1 + 2ull * E;
+  Idx* cArr[7];                        // compact splitter arrays: dart, next[2], dist[2], last[2]
   {
-    Idx* base = reinterpret_cast<Idx*>(W.epos);
-    for (int b = 0; b < 2; ++b)
-      for (int a = 0; a < 3; ++a)
-        buf[b][a] = base + (static_cast<size_t>(b) * 3 + a) * E;
+    const unsigned inR1 = static_cast<unsigned>(W.eposBytes / (sizeof(Idx) * static_cast<size_t>(E > 0 ? E : 1)));
+    Idx* const r2 = reinterpret_cast<Idx*>(W.slots);
+    unsigned a1 = 3, a2 = 0;
+    for (int i = 0; i < 7; ++i)
+      cArr[i] = (a1 < inR1) ? r1 + static_cast<size_t>(a1++) * E : r2 + static_cast<size_t>(a2++) * E;
   }
+  Idx* const cDart = cArr[0];
+  Idx* cNext[2] = { cArr[1], cArr[2] };
+  Idx* cDist[2] = { cArr[3], cArr[4] };
+  Idx* cLast[2] = { cArr[5], cArr[6] };
   for (unsigned e = tid; e < E; e += nth)
   {
-    const bool dead = (W.twin[e] == static_cast<Idx>(e));
-    Idx nx = kNone;
-    if (!dead)
-      nx = W.twin[e ^ 1u];
-    buf[0][0][e] = nx;
-    buf[0][1][e] = static_cast<Idx>(nx != kNone ? 1 : 0);
-    buf[0][2][e] = static_cast<Idx>(e);
+    lst[e] = kNone;
+    chainEnd[e] = kNone;
+  }
+  __syncthreads();
+  for (unsigned e0 = 0; e0 < E; e0 += nth)
+  {
+    const unsigned e = e0 + tid;
+    bool sel = false;
+    if (e < E)
+    {
+      const Idx tw = W.twin[e];
+      sel = tw != static_cast<Idx>(e) && (tw == kNone || ((e >> 1) & kSplitMask) == 0u);
+    }
+    const unsigned m = __ballot_sync(kFull, sel);
+    unsigned base = 0;
+    if ((tid & 31u) == 0u && m)
+      base = atomicAdd(&s_misc[2], __popc(m));
+    base = __shfl_sync(kFull, base, 0);
+    if (sel)
+    {
+      const unsigned c = base + __popc(m & ((1u << (tid & 31u)) - 1u));
+      cDart[c] = static_cast<Idx>(e);
+      lst[e] = static_cast<Idx>(c);
+    }
+  }
+  __syncthreads();
+  const unsigned Ns = s_misc[2];
+  for (unsigned c = tid; c < Ns; c += nth)
+  {
+    unsigned d = cDart[c], j = 0;
+    while (true)
+    {
+      if (j)
+        lst[d] = static_cast<Idx>(c);
+      rnk[d] = static_cast<Idx>(j);
+      const Idx nd = W.twin[d ^ 1u];
+      if (nd == kNone)  // d ends at an open end: last dart of the list
+      {
+        cNext[0][c] = kNone;
+        cDist[0][c] = static_cast<Idx>(j);
+        cLast[0][c] = static_cast<Idx>(d);
+        break;
+      }
+      if (((nd >> 1) & kSplitMask) == 0u)  // the next dart is a splitter (a list head never has a predecessor)
+      {
+        cNext[0][c] = lst[nd];
+        cDist[0][c] = static_cast<Idx>(j + 1u);
+        cLast[0][c] = kNone;
+        break;
+      }
+      d = nd;
+      ++j;
+    }
   }
   __syncthreads();
   int cur = 0;
-  unsigned rounds = 1;
-  while ((1u << rounds) < n + 1)
-    ++rounds;
-  ++rounds;
-  for (unsigned r = 0; r < rounds; ++r)
   {
-    Idx *nxt = buf[cur][0], *rnk = buf[cur][1], *lst = buf[cur][2];
-    Idx *nxt2 = buf[cur ^ 1][0], *rnk2 = buf[cur ^ 1][1], *lst2 = buf[cur ^ 1][2];
-    unsigned pending = 0;
+    unsigned rounds = 1;
+    while ((1u << rounds) < Ns + 1u)
+      ++rounds;
+    ++rounds;
+    for (unsigned r = 0; r < rounds; ++r)
+    {
+      unsigned pending = 0;
+      for (unsigned c = tid; c < Ns; c += nth)
+      {
+        const Idx nx = cNext[cur][c];
+        if (nx != kNone)
+        {
+          const Idx nn = cNext[cur][nx];
+          cNext[cur ^ 1][c] = nn;
+          cDist[cur ^ 1][c] = static_cast<Idx>(cDist[cur][c] + cDist[cur][nx]);
+          cLast[cur ^ 1][c] = cLast[cur][nx];
+          pending |= (nn != kNone);
+        }
+        else
+        {
+          cNext[cur ^ 1][c] = kNone;
+          cDist[cur ^ 1][c] = cDist[cur][c];
+          cLast[cur ^ 1][c] = cLast[cur][c];
+        }
+      }
+      if (pending)
+        s_misc[5] = r + 1;
+      __syncthreads();
+      cur ^= 1;
+      const unsigned more = s_misc[5];
+      __syncthreads();  // everyone has read the flag before the next round may overwrite it
+      if (more != r + 1)
+        break;
+    }
+  }
+  {
+    // owner / hops -> lst / rnk, in place.  Darts no splitter reached, and darts whose splitters never reached an end,
+    // lie on closed loops: lst = kNone marks them for the loop walker below.
+    unsigned cyclic = 0;
     for (unsigned e = tid; e < E; e += nth)
     {
-      const Idx nx = nxt[e];
-      if (nx != kNone)
+      if (W.twin[e] == static_cast<Idx>(e))  // dropped line
       {
-        const Idx nn = nxt[nx];
-        nxt2[e] = nn;
-        rnk2[e] = static_cast<Idx>(rnk[e] + rnk[nx]);
-        lst2[e] = lst[nx];
-        pending |= (nn != kNone);
+        lst[e] = static_cast<Idx>(e);
+        rnk[e] = 0;
+        continue;
+      }
+      const Idx c = lst[e];
+      if (c == kNone || cNext[cur][c] != kNone)
+      {
+        lst[e] = kNone;
+        rnk[e] = 0;
+        cyclic = 1;
       }
       else
       {
-        nxt2[e] = kNone;
-        rnk2[e] = rnk[e];
-        lst2[e] = lst[e];
+        rnk[e] = static_cast<Idx>(cDist[cur][c] - rnk[e]);
+        lst[e] = cLast[cur][c];
       }
     }
-    if (pending)
-      s_misc[5] = r + 1;
-    __syncthreads();
-    cur ^= 1;
-    const unsigned more = s_misc[5];
-    __syncthreads();  // everyone has read the flag before the next round may overwrite it
-    if (more != r + 1)
-      break;
-  }
-  Idx *nxt = buf[cur][0], *rnk = buf[cur][1], *lst = buf[cur][2];
-  Idx* chainEnd = buf[cur ^ 1][0];  // dead buffer, reused
-  {
-    unsigned bad = 0;
-    for (unsigned e = tid; e < E; e += nth)
-    {
-      bad |= (nxt[e] != kNone);
-      chainEnd[e] = kNone;
-    }
-    if (bad)
-      s_misc[7] = 1u;  // some darts never reached an end: closed loops
+    if (cyclic)
+      s_misc[7] = 1u;
   }
   __syncthreads();
 
@@ -525,7 +699,6 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   };
   Head* heads = reinterpret_cast<Head*>(W.slots);  // slots are dead; 16 B per head, cap >= E >= 2 * heads
   unsigned* lenSorted = reinterpret_cast<unsigned*>(W.twin);
-  auto endTag = [&](unsigned e) { return 2u * __ldg(P.bucket + off + (e >> 1)) + (e & 1u); };
 
   if (s_misc[7])
   {
@@ -536,7 +709,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
     {
       for (unsigned e0 = 0; e0 < E; ++e0)
       {
-        if (nxt[e0] == kNone)
+        if (lst[e0] != kNone)
           continue;
         unsigned c = e0, best = endTag(e0), len = 0;
         for (unsigned d = e0;;)
@@ -553,11 +726,9 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
             break;
         }
         bool forward = false;
-        CutPoint a{};
         if ((best & 1u) == 0u)
         {
-          a = cutPointOfTag(P, org, W.etag[c], false);
-          const CutPoint b = cutPointOfTag(P, org, W.etag[c ^ 1u], false);
+          const float4 a = endPos(c), b = endPos(c ^ 1u);
           const double dd = dotLR(dsub(static_cast<double>(b.x), static_cast<double>(a.x)),
                                   dsub(static_cast<double>(b.y), static_cast<double>(a.y)),
                                   dsub(static_cast<double>(b.z), static_cast<double>(a.z)), P.L.dir);
@@ -576,13 +747,13 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
             const unsigned m = d ^ 1u;  // reverse dart d'_{len-1-i}
             if (forward)
             {
-              nxt[d] = kNone, rnk[d] = static_cast<Idx>(len - 1 - i), lst[d] = static_cast<Idx>(tailF);
-              nxt[m] = kNone, rnk[m] = 0, lst[m] = static_cast<Idx>(m);
+              rnk[d] = static_cast<Idx>(len - 1 - i), lst[d] = static_cast<Idx>(tailF);
+              rnk[m] = 0, lst[m] = static_cast<Idx>(m);
             }
             else
             {
-              nxt[d] = kNone, rnk[d] = 0, lst[d] = static_cast<Idx>(d);
-              nxt[m] = kNone, rnk[m] = static_cast<Idx>(i), lst[m] = static_cast<Idx>(c ^ 1u);
+              rnk[d] = 0, lst[d] = static_cast<Idx>(d);
+              rnk[m] = static_cast<Idx>(i), lst[m] = static_cast<Idx>(c ^ 1u);
             }
             d = nd;
           }
@@ -596,8 +767,8 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
       }
       // whatever is still marked as cyclic now belongs to mirror loops whose canonical twin was visited later
       for (unsigned e0 = 0; e0 < E; ++e0)
-        if (nxt[e0] != kNone)
-          nxt[e0] = kNone, rnk[e0] = 0, lst[e0] = static_cast<Idx>(e0);
+        if (lst[e0] == kNone)
+          rnk[e0] = 0, lst[e0] = static_cast<Idx>(e0);
     }
     __syncthreads();
   }
@@ -611,8 +782,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
     // open end: head of the dart list that starts here
     const unsigned tail = lst[e];
     const unsigned tagFirst = endTag(e), tagLast = endTag(tail ^ 1u);
-    const CutPoint a = cutPointOfTag(P, org, W.etag[e], false);
-    const CutPoint b = cutPointOfTag(P, org, W.etag[tail ^ 1u], false);
+    const float4 a = endPos(e), b = endPos(tail ^ 1u);
     const double d = dotLR(dsub(static_cast<double>(b.x), static_cast<double>(a.x)),
                            dsub(static_cast<double>(b.y), static_cast<double>(a.y)),
                            dsub(static_cast<double>(b.z), static_cast<double>(a.z)), P.L.dir);
@@ -627,7 +797,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   __syncthreads();
   const unsigned S = s_misc[0];
   // order of each head = number of heads that sort before it (key, then first-inserter rank)
-  unsigned* headOrder = reinterpret_cast<unsigned*>(buf[cur ^ 1][1]);  // dead ranking buffer: room for n entries
+  unsigned* headOrder = reinterpret_cast<unsigned*>(r1 + 3ull * E);  // dead splitter array: room for n entries
   for (unsigned h = tid; h < S; h += nth)
   {
     unsigned ord = 0;
@@ -668,40 +838,12 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   __syncthreads();
   const unsigned Wk = s_misc[4];
 
-  // ---- L: decoupled look-back over planes: where do this plane's waypoints / segments start? -----------------------
   if (tid == 0)
   {
-    unsigned long long exclW = 0, exclS = 0;
-    if (kLocal > 0)
-    {
-      *reinterpret_cast<volatile unsigned long long*>(&P.lookback[kLocal]) = packStatus(kFlagAggregate, Wk, S);
-      long long j = kLocal - 1;
-      while (true)
-      {
-        unsigned long long st;
-        do
-        {
-          st = *reinterpret_cast<volatile unsigned long long*>(&P.lookback[j]);
-        } while ((st >> 62) == 0ull);
-        exclW += (st >> 31) & 0x7fffffffull;
-        exclS += st & 0x7fffffffull;
-        if ((st >> 62) == 2ull)
-          break;
-        --j;
-      }
-    }
-    *reinterpret_cast<volatile unsigned long long*>(&P.lookback[kLocal]) = packStatus(kFlagPrefix, exclW + Wk, exclS + S);
-    s_misc[2] = static_cast<unsigned>(exclW);
-    s_misc[3] = static_cast<unsigned>(exclS);
     P.planeMeta[2 * kLocal] = Wk;
     P.planeMeta[2 * kLocal + 1] = S;
-    if (exclW + Wk > P.wCap || exclS + S > P.sCap)
-      atomicOr(&s_misc[1], kErrOverflow);
   }
-  __syncthreads();
-  if (s_misc[1] & kErrOverflow)
-    return;
-  const unsigned long long baseW = s_misc[2], baseS = s_misc[3];
+  const unsigned long long baseW = 2ull * off, baseS = off;  // the plane's own output windows (see LinkParams)
 
   // ---- O: output ----------------------------------------------------------------------------------------------------
   for (unsigned h = tid; h < S; h += nth)
@@ -710,7 +852,7 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
     const unsigned e = heads[h].e;
     const unsigned lines = static_cast<unsigned>(rnk[e]) + 1u;
     chainEnd[lst[e]] = static_cast<Idx>(lenSorted[ord] + lines);  // plane-local index of the chain's last point
-    P.outSegLen[baseS + ord] = lines + 1u;
+    P.segLen[baseS + ord] = lines + 1u;
   }
   __syncthreads();
   for (unsigned e = tid; e < E; e += nth)
@@ -721,29 +863,14 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
     if (ce == kNone)
       continue;  // dart of the non-selected direction
     const unsigned r = rnk[e];
-    for (int last = 0; last < 2; ++last)
-    {
-      if (last && r != 0)
-        break;
-      const unsigned tag = last ? W.etag[e ^ 1u] : W.etag[e];
-      const unsigned long long idx = baseW + (last ? static_cast<unsigned>(ce) : static_cast<unsigned>(ce) - 1u - r);
-      const CutPoint c = cutPointOfTag(P, org, tag, true);
-      P.outPos[3 * idx] = c.x;
-      P.outPos[3 * idx + 1] = c.y;
-      P.outPos[3 * idx + 2] = c.z;
-      P.outNrm[3 * idx] = c.nx;
-      P.outNrm[3 * idx + 1] = c.ny;
-      P.outNrm[3 * idx + 2] = c.nz;
-      if (P.emitEdges)
-      {
-        P.outEdgeLo[idx] = c.lo;
-        P.outEdgeHi[idx] = c.hi;
-      }
-    }
+    const unsigned last = static_cast<unsigned>(ce);
+    P.wpTag[baseW + last - 1u - r] = W.etag[e];
+    if (r == 0)
+      P.wpTag[baseW + last] = W.etag[e ^ 1u];
   }
 }
 
-__global__ void __launch_bounds__(512, 1) k_link_planes(LinkParams P)
+__global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ unsigned s_misc[kMiscWords];
@@ -760,17 +887,22 @@ __global__ void __launch_bounds__(512, 1) k_link_planes(LinkParams P)
     if (kLocal >= nP)
       break;
     const unsigned n = P.planeOff[kLocal + 1] - P.planeOff[kLocal];
-
+    if (n == 0)
+    {
+      if (threadIdx.x == 0)
+        P.planeMeta[2 * kLocal] = P.planeMeta[2 * kLocal + 1] = 0u;
+      continue;
+    }
+    const unsigned E = 2 * n;
+    unsigned cap = 16;
+    while (cap < E)
+      cap <<= 1;
     if (n <= P.smemHitCap)
     {
-      const unsigned E = 2 * n;
-      unsigned cap = 16;
-      while (cap < E)
-        cap <<= 1;
       PlaneWork<uint16_t> W;
-      const size_t a = 12ull * E;
+      W.eposBytes = 12ull * E;
       W.epos = reinterpret_cast<float*>(smem);
-      W.etag = reinterpret_cast<unsigned*>(smem + ((a + 15) & ~size_t(15)));
+      W.etag = reinterpret_cast<unsigned*>(smem + ((W.eposBytes + 15) & ~size_t(15)));
       W.slots = reinterpret_cast<Slot*>(reinterpret_cast<uint8_t*>(W.etag) + 4ull * E);
       W.twin = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(W.slots) + 8ull * cap);
       W.cap = cap;
@@ -778,15 +910,11 @@ __global__ void __launch_bounds__(512, 1) k_link_planes(LinkParams P)
     }
     else
     {
-      const unsigned E = 2 * n;
-      unsigned cap = 16;
-      while (cap < E)
-        cap <<= 1;
       uint8_t* g = P.scratch + P.scratchStride * blockIdx.x;
       PlaneWork<uint32_t> W;
-      const size_t a = 24ull * E;  // 2 buffers x 3 arrays x 4 B
+      W.eposBytes = 32ull * E;  // 8 index arrays of 4 E bytes
       W.epos = reinterpret_cast<float*>(g);
-      W.etag = reinterpret_cast<unsigned*>(g + ((a + 15) & ~size_t(15)));
+      W.etag = reinterpret_cast<unsigned*>(g + ((W.eposBytes + 15) & ~size_t(15)));
       W.slots = reinterpret_cast<Slot*>(reinterpret_cast<uint8_t*>(W.etag) + 4ull * E);
       W.twin = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(W.slots) + 8ull * cap);
       W.cap = cap;
@@ -797,29 +925,137 @@ __global__ void __launch_bounds__(512, 1) k_link_planes(LinkParams P)
     {
       atomicOr(&P.status[0], s_misc[1]);
       atomicMin(&P.status[1], static_cast<unsigned>(kLocal));
-      // a failed plane must still publish a prefix, or later planes would spin forever
-      unsigned long long exclW = 0, exclS = 0;
-      const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&P.lookback[kLocal]);
-      if ((cur >> 62) != 2ull)
+      P.planeMeta[2 * kLocal] = P.planeMeta[2 * kLocal + 1] = 0u;
+    }
+  }
+}
+
+/** Exclusive prefix of the per-plane waypoint and segment counts (one block; nP is at most a few thousand).
+ *  prefix[k] = {waypoints, segments} before plane k; prefix[nP] = totals, also written to totals[0..1]. */
+__global__ void __launch_bounds__(1024)
+    k_scan_meta(const unsigned* __restrict__ planeMeta, long long nP, uint2* __restrict__ prefix, unsigned* __restrict__ totals)
+{
+  __shared__ uint2 s_warp[32];
+  __shared__ uint2 s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_carry = make_uint2(0u, 0u);
+  __syncthreads();
+  for (long long base = 0; base < nP; base += blockDim.x)
+  {
+    const long long i = base + threadIdx.x;
+    const uint2 v = (i < nP) ? make_uint2(planeMeta[2 * i], planeMeta[2 * i + 1]) : make_uint2(0u, 0u);
+    uint2 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned yx = __shfl_up_sync(kFull, x.x, o), yy = __shfl_up_sync(kFull, x.y, o);
+      if (lane >= o)
+        x.x += yx, x.y += yy;
+    }
+    if (lane == 31)
+      s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+      uint2 w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
       {
-        long long j = kLocal - 1;
-        while (j >= 0)
-        {
-          unsigned long long st;
-          do
-          {
-            st = *reinterpret_cast<volatile unsigned long long*>(&P.lookback[j]);
-          } while ((st >> 62) == 0ull);
-          exclW += (st >> 31) & 0x7fffffffull;
-          exclS += st & 0x7fffffffull;
-          if ((st >> 62) == 2ull)
-            break;
-          --j;
-        }
-        *reinterpret_cast<volatile unsigned long long*>(&P.lookback[kLocal]) = packStatus(kFlagPrefix, exclW, exclS);
-        P.planeMeta[2 * kLocal] = 0;
-        P.planeMeta[2 * kLocal + 1] = 0;
+        const unsigned yx = __shfl_up_sync(kFull, w.x, o), yy = __shfl_up_sync(kFull, w.y, o);
+        if (lane >= o)
+          w.x += yx, w.y += yy;
       }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint2 carry = s_carry;
+    const uint2 wprev = warp ? s_warp[warp - 1] : make_uint2(0u, 0u);
+    const uint2 incl = make_uint2(x.x + wprev.x + carry.x, x.y + wprev.y + carry.y);
+    if (i < nP)
+      prefix[i] = make_uint2(incl.x - v.x, incl.y - v.y);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1)
+      s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    prefix[nP] = s_carry;
+    totals[0] = s_carry.x;
+    totals[1] = s_carry.y;
+  }
+}
+
+// =================================================================================================================
+// S6: waypoints
+// =================================================================================================================
+/** Largest k in [0, nP) with prefix[k].{x|y} <= i (prefix is non-decreasing; empty planes repeat a value). */
+template <bool kSegments>
+__device__ __forceinline__ unsigned planeOfIndex(const uint2* __restrict__ prefix, unsigned nP, unsigned i)
+{
+  unsigned lo = 0, hi = nP;  // invariant: prefix[lo] <= i < prefix[hi]
+  while (hi - lo > 1)
+  {
+    const unsigned mid = (lo + hi) >> 1;
+    const uint2 v = __ldg(prefix + mid);
+    if ((kSegments ? v.y : v.x) <= i)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+/**
+ * One thread per output waypoint.  The waypoint is the cut point its first inserter (triangle rank >> 1, line end
+ * rank & 1) produced: contour that triangle against the waypoint's plane again — same operands, same operation order,
+ * hence the same float32 position the linker merged on — and interpolate the vertex normals along the cut edge
+ * (vtkDataSetAttributes::InterpolateEdge; only the first inserter's attributes are kept by vtkCutter).  The same
+ * kernel packs the per-plane segment lengths.
+ */
+__global__ void __launch_bounds__(256)
+    k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const float4* __restrict__ nrm,
+                LatticeDev L, const unsigned* __restrict__ planeOff, const uint2* __restrict__ prefix,
+                const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen, float* __restrict__ outPos,
+                float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo, uint32_t* __restrict__ outEdgeHi,
+                unsigned* __restrict__ outSegLen, int emitEdges)
+{
+  const unsigned nP = static_cast<unsigned>(L.plane_end - L.plane_begin);
+  const uint2 total = __ldg(prefix + nP);
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+  const unsigned long long gid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (unsigned long long i = gid; i < total.y; i += stride)
+  {
+    const unsigned k = planeOfIndex<true>(prefix, nP, static_cast<unsigned>(i));
+    outSegLen[i] = __ldg(segLen + __ldg(planeOff + k) + (static_cast<unsigned>(i) - __ldg(prefix + k).y));
+  }
+  for (unsigned long long i = gid; i < total.x; i += stride)
+  {
+    const unsigned k = planeOfIndex<false>(prefix, nP, static_cast<unsigned>(i));
+    const unsigned tg = __ldg(wpTag + 2ull * __ldg(planeOff + k) + (static_cast<unsigned>(i) - __ldg(prefix + k).x));
+    const unsigned t = tg >> 1;
+    const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
+    // positions and normals of all three vertices are requested together: the two the cut edge needs are only known
+    // after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
+    const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
+    const float4 nv[3] = { __ldg(nrm + ids[0]), __ldg(nrm + ids[1]), __ldg(nrm + ids[2]) };
+    const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
+    double s[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+    const CutPoint c = interpolateCut(contourCase(s), tg & 1u, ids, p, s, nv);
+    outPos[3 * i] = c.x;
+    outPos[3 * i + 1] = c.y;
+    outPos[3 * i + 2] = c.z;
+    outNrm[3 * i] = c.nx;
+    outNrm[3 * i + 1] = c.ny;
+    outNrm[3 * i + 2] = c.nz;
+    if (emitEdges)
+    {
+      outEdgeLo[i] = c.lo;
+      outEdgeHi[i] = c.hi;
     }
   }
 }
@@ -848,7 +1084,7 @@ size_t globalWorkBytes(unsigned hits)
   size_t cap = 16;
   while (cap < E)
     cap <<= 1;
-  return ((24 * E + 15) & ~size_t(15)) + 4 * E + 8 * cap + 4 * E + 256;
+  return ((32 * E + 15) & ~size_t(15)) + 4 * E + 8 * cap + 4 * E + 256;
 }
 }  // namespace
 
@@ -857,9 +1093,11 @@ void launchCountHits(nb2_context* c, const LatticeDev& L)
   const long long nP = L.plane_end - L.plane_begin;
   c->planeCnt.ensure(sizeof(unsigned) * (nP + 1));
   NB2_CUDA(cudaMemsetAsync(c->planeCnt.ptr, 0, sizeof(unsigned) * (nP + 1), c->stream));
-  const int grid = gridFor(c->F, kCountThreads, c->sm_count * 8);
-  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->vertK.as<int>(), L,
-                                                      c->planeCnt.as<unsigned>(), nP <= kSmemBins ? 1 : 0);
+  const int grid = gridFor((c->F + 3) / 4, kCountThreads, c->sm_count * 8);
+  const int aligned = (reinterpret_cast<uintptr_t>(c->tri.ptr) & 15u) == 0 ? 1 : 0;
+  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(), L,
+                                                      c->planeCnt.as<unsigned>(), nP <= kSmemBins ? 1 : 0, aligned,
+                                                      c->counters.as<unsigned>() + 12);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
@@ -869,25 +1107,24 @@ void launchScanPlanes(nb2_context* c, const LatticeDev& L)
   const long long nP = L.plane_end - L.plane_begin;
   c->planeOff.ensure(sizeof(unsigned) * (nP + 1));
   c->planeCursor.ensure(sizeof(unsigned) * (nP + 1));
-  c->lookback.ensure(sizeof(unsigned long long) * (nP + 1));
   k_scan_planes<<<1, 1024, 0, c->stream>>>(c->planeCnt.as<unsigned>(), nP, c->planeOff.as<unsigned>(),
-                                           c->planeCursor.as<unsigned>(), c->lookback.as<unsigned long long>(),
-                                           c->counters.as<unsigned>() + 4);
+                                           c->planeCursor.as<unsigned>(), c->counters.as<unsigned>() + 4);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchFillBuckets(nb2_context* c, const LatticeDev& L)
+void launchEmitHits(nb2_context* c, const LatticeDev& L)
 {
-  const int grid = gridFor(c->F, kCountThreads, c->sm_count * 8);
-  k_fill_buckets<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->vertK.as<int>(), L,
-                                                        c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
-                                                        c->bucket.as<uint32_t>());
+  const int grid = gridFor((c->F + 3) / 4, kEmitThreads, c->sm_count * 8);
+  const int aligned = (reinterpret_cast<uintptr_t>(c->tri.ptr) & 15u) == 0 ? 1 : 0;
+  k_emit_hits<<<grid, kEmitThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->vertK.as<int>(), c->pos.as<float4>(), L,
+                                                     c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
+                                                     c->hitRec.as<float4>(), aligned);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t w_cap, uint64_t s_cap, int emit_edges)
+void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H)
 {
   const long long nP = L.plane_end - L.plane_begin;
   // largest plane that fits the opt-in shared memory (uint16 indices additionally need 2 n < 65535)
@@ -918,32 +1155,44 @@ void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint6
     c->linkScratch.ensure(stride * grid);
   }
   c->planeMeta.ensure(sizeof(unsigned) * 2 * (nP + 1));
+  c->planePrefix.ensure(sizeof(uint2) * (nP + 1));
+  c->wpTag.ensure(sizeof(unsigned) * 2 * H);
+  c->segLen.ensure(sizeof(unsigned) * H);
 
   LinkParams P{};
-  P.tri = c->tri.as<uint32_t>();
-  P.pos = c->pos.as<float4>();
-  P.nrm = c->nrm.as<float4>();
+  P.rec = c->hitRec.as<float4>();
   P.planeOff = c->planeOff.as<unsigned>();
-  P.bucket = c->bucket.as<uint32_t>();
   P.L = L;
-  P.lookback = c->lookback.as<unsigned long long>();
   P.ticket = c->counters.as<unsigned>() + 8;
   P.planeMeta = c->planeMeta.as<unsigned>();
-  P.outPos = c->outPos.as<float>();
-  P.outNrm = c->outNrm.as<float>();
-  P.outEdgeLo = c->outEdge.as<uint32_t>();
-  P.outEdgeHi = c->outEdge.as<uint32_t>() + w_cap;
-  P.outSegLen = c->outSegLen.as<unsigned>();
+  P.wpTag = c->wpTag.as<unsigned>();
+  P.segLen = c->segLen.as<unsigned>();
   P.status = c->counters.as<unsigned>() + 10;
   P.scratch = c->linkScratch.as<uint8_t>();
   P.scratchStride = stride;
   P.smemHitCap = hit_cap;
-  P.wCap = w_cap;
-  P.sCap = s_cap;
-  P.emitEdges = emit_edges;
 
   NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  k_link_planes<<<grid, 512, smem_bytes, c->stream>>>(P);
+  k_link_planes<<<grid, kLinkThreads, smem_bytes, c->stream>>>(P);
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  // totals land in counters[6..7]
+  k_scan_meta<<<1, 1024, 0, c->stream>>>(c->planeMeta.as<unsigned>(), nP, c->planePrefix.as<uint2>(),
+                                         c->counters.as<unsigned>() + 6);
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
+void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint64_t w_expected, int emit_edges)
+{
+  // the waypoint total is only known on the device (k_scan_meta): a grid-stride launch sized for the expected count
+  // (one waypoint per hit plus one per chain) covers whatever it turns out to be
+  const int grid = gridFor(w_expected, 256, c->sm_count * 32);
+  k_waypoints<<<grid, 256, 0, c->stream>>>(c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm.as<float4>(), L,
+                                           c->planeOff.as<unsigned>(), c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(),
+                                           c->segLen.as<unsigned>(), c->outPos.as<float>(), c->outNrm.as<float>(),
+                                           c->outEdge.as<uint32_t>(), c->outEdge.as<uint32_t>() + w_cap,
+                                           c->outSegLen.as<unsigned>(), emit_edges);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -123,6 +123,7 @@ struct nb2_context
   // resident mesh (SoA)
   uint64_t V = 0, F = 0;
   bool has_normals = false;
+  bool tri_checked = false;  // vertex indices of the resident triangles are known to be < V
   nb2::DevBuf blob;      // staging copy of the interleaved cloud
   nb2::DevBuf pos;       // float4[V]  (x, y, z, unused)
   nb2::DevBuf nrm;       // float4[V]
@@ -138,8 +139,10 @@ struct nb2_context
   nb2::DevBuf planeCnt;    // uint32[P + 1]
   nb2::DevBuf planeOff;    // uint32[P + 1]
   nb2::DevBuf planeCursor; // uint32[P]
-  nb2::DevBuf bucket;      // uint32[H] triangle ids grouped by plane
-  nb2::DevBuf lookback;    // uint64[P] decoupled look-back status
+  nb2::DevBuf hitRec;      // float4[2 H] endpoint records {x, y, z, rank} of every (triangle, plane) hit, grouped by plane
+  nb2::DevBuf wpTag;       // uint32[2 H] first-inserter rank of every waypoint, in per-plane windows
+  nb2::DevBuf segLen;      // uint32[H] segment lengths, in per-plane windows
+  nb2::DevBuf planePrefix; // uint2[P + 1] waypoints / segments before each plane
   nb2::DevBuf planeMeta;   // uint32[2 * P]: waypoints, segments of each plane
   nb2::DevBuf outPos;      // float[3 * Wcap]
   nb2::DevBuf outNrm;      // float[3 * Wcap]
@@ -205,8 +208,9 @@ void launchExtents(nb2_context* c, const float mean[3], const float evecs[9]);
 void launchClassify(nb2_context* c, const LatticeDev& L);
 void launchCountHits(nb2_context* c, const LatticeDev& L);
 void launchScanPlanes(nb2_context* c, const LatticeDev& L);  // writes {H, n_max} to counters[0..1]
-void launchFillBuckets(nb2_context* c, const LatticeDev& L);
-void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t w_cap, uint64_t s_cap, int emit_edges);
+void launchEmitHits(nb2_context* c, const LatticeDev& L);
+void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H);
+void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint64_t w_expected, int emit_edges);
 void launchSetNormals(nb2_context* c, const float* dev_packed);
 void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);
 void launchVertexNormals(nb2_context* c);
