@@ -211,9 +211,9 @@ int nb2_result_get(const nb2_result* r, nb2_result_view* out);
 int nb2_result_poses(const nb2_result* r, double* out16);
 void nb2_result_free(nb2_result* r);
 
-/* Device timings of the last nb2_plan / nb2_slice / nb2_normals_from_mesh_faces / nb2_mesh_upload on the context
- * (CUDA events on the context's stream), in milliseconds; `names` points at static strings.  Returns the number of
- * stages written (<= capacity). */
+/* Device timings (CUDA events on the context's stream, milliseconds) of the last nb2_mesh_upload followed by those of
+ * the last nb2_plan / nb2_slice / nb2_normals_from_mesh_faces on the context; `names` points at static strings.
+ * Returns the number of stages written (<= capacity). */
 int nb2_last_timings(const nb2_context* ctx, const char** names, float* ms, int capacity);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t nb2_kernel_launches(const nb2_context* ctx);

@@ -271,9 +271,16 @@ void ensurePca(nb2_context* c)
   launchExtents(c, c->pca.mean, c->pca.evecs);
   c->timer.mark("extents", c->stream);
   c->hostSmall.ensure(4096);
-  float* h = c->hostSmall.as<float>();
-  NB2_CUDA(cudaMemcpyAsync(h, c->extents.ptr, 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  unsigned* hb = c->hostSmall.as<unsigned>();
+  NB2_CUDA(cudaMemcpyAsync(hb, c->extents.ptr, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  float h[6];
+  for (int i = 0; i < 6; ++i)
+  {
+    // inverse of the kernel's order-preserving float -> unsigned map
+    const unsigned u = (hb[i] & 0x80000000u) ? (hb[i] & 0x7fffffffu) : ~hb[i];
+    std::memcpy(&h[i], &u, 4);
+  }
   for (int i = 0; i < 3; ++i)
     c->pca.scales[i] = h[3 + i] - h[i];
   c->pca_valid = true;
@@ -354,7 +361,7 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   c->outSegLen.ensure(sizeof(unsigned) * s_cap);
   launchLinkPlanes(c, L, n_max, H);
   c->timer.mark("link", c->stream);
-  launchWaypoints(c, L, w_cap, H + nP, emit_edges ? 1 : 0);
+  launchWaypoints(c, L, w_cap, n_max, emit_edges ? 1 : 0);
   c->timer.mark("waypoints", c->stream);
 
   // totals, per-plane meta and status
@@ -521,6 +528,7 @@ void nb2_context_destroy(nb2_context* c)
   for (auto& hb : c->hostPool)
     cudaFreeHost(hb.ptr);
   c->timer.destroy();
+  c->timer_upload.destroy();
   if (c->stream)
     cudaStreamDestroy(c->stream);
   if (prev >= 0)
@@ -551,7 +559,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   c->V = 0;
   c->pca_valid = false;
   const uint64_t V = m->n_points, F = m->n_triangles;
-  c->timer.begin(c->stream);
+  c->timer_upload.begin(c->stream);
   // Inputs that already live in this GPU's memory are used in place (no copy; the caller keeps them alive until the
   // next upload).  Anything else is copied host -> device.
   auto onThisDevice = [&](const void* p) {
@@ -584,14 +592,14 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     if (F)
       NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, sizeof(uint32_t) * 3 * F, cudaMemcpyHostToDevice, c->stream));
   }
-  c->timer.mark("h2d", c->stream);
+  c->timer_upload.mark("h2d", c->stream);
   c->V = V;
   c->F = F;
   c->has_normals = m->offset_normal >= 0;
   if (!c->has_normals)
     NB2_CUDA(cudaMemsetAsync(c->nrm.ptr, 0, sizeof(float4) * V, c->stream));
   launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
-  c->timer.mark("ingest+moments", c->stream);
+  c->timer_upload.mark("ingest+moments", c->stream);
   // Triangles copied from the host are range-checked now (noise next to the PCIe copy).  Triangles adopted in place
   // from device memory are checked by the first kernel that streams them anyway (k_count_hits / the normals pass).
   c->tri_checked = false;
@@ -599,7 +607,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   if (!tri_adopted)
   {
     launchValidateTriangles(c);
-    c->timer.mark("validate", c->stream);
+    c->timer_upload.mark("validate", c->stream);
   }
 
   c->hostSmall.ensure(4096);
@@ -928,7 +936,9 @@ int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int ca
 {
   if (!c || !names || !ms)
     return 0;
-  return c->timer.collect(names, ms, capacity);
+  // stages of the last upload, then the stages of the last plan / slice / normals call
+  const int n = c->timer_upload.collect(names, ms, capacity);
+  return n + c->timer.collect(names + n, ms + n, capacity - n);
 }
 
 uint64_t nb2_kernel_launches(const nb2_context* c) { return c ? c->launches : 0; }

@@ -198,20 +198,23 @@ __global__ void __launch_bounds__(kMomentThreads)
   }
 }
 
+/** Monotone map float -> unsigned (a < b  <=>  orderedBits(a) < orderedBits(b)), and back */
+__device__ __forceinline__ unsigned orderedBits(float f)
+{
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 /** Float extents in the PCA frame: proj_c = e_c . (x - mean) with Eigen's 3-term order a0 + (a1 + a2); min/max are
  *  order independent so any reduction tree reproduces pcl::getMinMax3D exactly. */
 __global__ void __launch_bounds__(256)
     k_extents(const float4* __restrict__ pos, unsigned long long V, float mx_, float my_, float mz_, float e00, float e01,
-              float e02, float e10, float e11, float e12, float e20, float e21, float e22, float* partial /*[grid][6]*/,
-              unsigned* done_counter, float* out6)
+              float e02, float e10, float e11, float e12, float e20, float e21, float e22, unsigned* __restrict__ out6)
 {
   __shared__ float s_mn[3][8], s_mx[3][8];
-  __shared__ bool s_last;
   float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
-  {
-    const float4 p = __ldg(pos + v);
+  auto project = [&](const float4 p) {
     const float dx = __fsub_rn(p.x, mx_), dy = __fsub_rn(p.y, my_), dz = __fsub_rn(p.z, mz_);
     const float p0 = __fadd_rn(__fmul_rn(e00, dx), __fadd_rn(__fmul_rn(e01, dy), __fmul_rn(e02, dz)));
     const float p1 = __fadd_rn(__fmul_rn(e10, dx), __fadd_rn(__fmul_rn(e11, dy), __fmul_rn(e12, dz)));
@@ -222,7 +225,20 @@ __global__ void __launch_bounds__(256)
     mx[1] = fmaxf(mx[1], p1);
     mn[2] = fminf(mn[2], p2);
     mx[2] = fmaxf(mx[2], p2);
+  };
+  unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // four independent 16-byte loads in flight per thread
+  for (; v + 3 * stride < V; v += 4 * stride)
+  {
+    const float4 a = __ldg(pos + v), b = __ldg(pos + v + stride), c = __ldg(pos + v + 2 * stride),
+                 d = __ldg(pos + v + 3 * stride);
+    project(a);
+    project(b);
+    project(c);
+    project(d);
   }
+  for (; v < V; v += stride)
+    project(__ldg(pos + v));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
@@ -236,39 +252,20 @@ __global__ void __launch_bounds__(256)
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    for (int c = 0; c < 3; ++c)
-    {
-      float a = s_mn[c][0], b = s_mx[c][0];
-      for (int w = 1; w < (blockDim.x >> 5); ++w)
-      {
-        a = fminf(a, s_mn[c][w]);
-        b = fmaxf(b, s_mx[c][w]);
-      }
-      partial[blockIdx.x * 6 + c] = a;
-      partial[blockIdx.x * 6 + 3 + c] = b;
-    }
-    __threadfence();
-    s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last)
-    return;
-  __threadfence();
+  // min / max are order independent: fold the block result into the six global slots with integer atomics on the
+  // order-preserving bit pattern of the floats
   if (threadIdx.x < 6)
   {
+    const int c = threadIdx.x % 3;
     const bool is_max = threadIdx.x >= 3;
-    float a = is_max ? -FLT_MAX : FLT_MAX;
-    for (unsigned b = 0; b < gridDim.x; ++b)
-    {
-      const float v = partial[b * 6 + threadIdx.x];
-      a = is_max ? fmaxf(a, v) : fminf(a, v);
-    }
-    out6[threadIdx.x] = a;
+    float a = is_max ? s_mx[c][0] : s_mn[c][0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w)
+      a = is_max ? fmaxf(a, s_mx[c][w]) : fminf(a, s_mn[c][w]);
+    if (is_max)
+      atomicMax(out6 + threadIdx.x, orderedBits(a));
+    else
+      atomicMin(out6 + threadIdx.x, orderedBits(a));
   }
-  if (threadIdx.x == 0)
-    *done_counter = 0;
 }
 
 /**
@@ -282,13 +279,14 @@ __global__ void __launch_bounds__(256) k_classify(const float4* __restrict__ pos
 {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   const long long P = L.num_planes;
+  const double inv_spacing = 1.0 / L.spacing;
   for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
   {
     const float4 p = __ldg(pos + v);
     // estimate
     const double d = L.n[0] * (static_cast<double>(p.x) - L.start[0]) + L.n[1] * (static_cast<double>(p.y) - L.start[1]) +
                      L.n[2] * (static_cast<double>(p.z) - L.start[2]);
-    double q = floor(d / L.spacing);
+    double q = floor(d * inv_spacing);  // an estimate only: the loops below settle the exact index
     q = fmin(fmax(q, -1.0), static_cast<double>(P - 1));
     long long k = static_cast<long long>(q);
     // exact fix-up against the reference's own expression
@@ -345,12 +343,13 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
 void launchExtents(nb2_context* c, const float mean[3], const float E[9])
 {
   const int grid = gridFor(c->V, 256, c->sm_count * 8);
-  c->extents.ensure(sizeof(float) * (6 * static_cast<size_t>(grid) + 8));
-  float* partial = c->extents.as<float>() + 8;
+  c->extents.ensure(sizeof(unsigned) * 8);
+  // slots 0..2 = ordered bits of the minima (start at the largest pattern), 3..5 = of the maxima (start at 0)
+  NB2_CUDA(cudaMemsetAsync(c->extents.ptr, 0xff, 3 * sizeof(unsigned), c->stream));
+  NB2_CUDA(cudaMemsetAsync(c->extents.as<unsigned>() + 3, 0, 3 * sizeof(unsigned), c->stream));
   // E is column-major: axis c = (E[3c], E[3c+1], E[3c+2])
   k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, mean[0], mean[1], mean[2], E[0], E[1], E[2], E[3],
-                                         E[4], E[5], E[6], E[7], E[8], partial, c->counters.as<unsigned>() + 1,
-                                         c->extents.as<float>());
+                                         E[4], E[5], E[6], E[7], E[8], c->extents.as<unsigned>());
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

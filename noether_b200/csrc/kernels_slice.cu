@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(1024)
 constexpr int kEmitThreads = 256;
 constexpr int kEmitList = 2048;  // hits contoured per round of a tile
 
-__global__ void __launch_bounds__(kEmitThreads)
+__global__ void __launch_bounds__(kEmitThreads, 4)
     k_emit_hits(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK,
                 const float4* __restrict__ pos, LatticeDev L, const unsigned* __restrict__ planeOff,
                 unsigned* __restrict__ cursor, float4* __restrict__ rec, int aligned)
@@ -990,73 +990,59 @@ __global__ void __launch_bounds__(1024)
 // =================================================================================================================
 // S6: waypoints
 // =================================================================================================================
-/** Largest k in [0, nP) with prefix[k].{x|y} <= i (prefix is non-decreasing; empty planes repeat a value). */
-template <bool kSegments>
-__device__ __forceinline__ unsigned planeOfIndex(const uint2* __restrict__ prefix, unsigned nP, unsigned i)
-{
-  unsigned lo = 0, hi = nP;  // invariant: prefix[lo] <= i < prefix[hi]
-  while (hi - lo > 1)
-  {
-    const unsigned mid = (lo + hi) >> 1;
-    const uint2 v = __ldg(prefix + mid);
-    if ((kSegments ? v.y : v.x) <= i)
-      lo = mid;
-    else
-      hi = mid;
-  }
-  return lo;
-}
-
 /**
- * One thread per output waypoint.  The waypoint is the cut point its first inserter (triangle rank >> 1, line end
- * rank & 1) produced: contour that triangle against the waypoint's plane again — same operands, same operation order,
- * hence the same float32 position the linker merged on — and interpolate the vertex normals along the cut edge
- * (vtkDataSetAttributes::InterpolateEdge; only the first inserter's attributes are kept by vtkCutter).  The same
- * kernel packs the per-plane segment lengths.
+ * One thread per output waypoint; blockIdx.x = slab-local plane, blockIdx.y = 256-waypoint chunk of that plane (the
+ * grid covers the 2 n_max waypoints the largest plane could have; chunks past a plane's count exit at once).
+ * The waypoint is the cut point its first inserter (triangle rank >> 1, line end rank & 1) produced: contour that
+ * triangle against the plane again — same operands, same operation order, hence the same float32 position the linker
+ * merged on — and interpolate the vertex normals along the cut edge (vtkDataSetAttributes::InterpolateEdge; only the
+ * first inserter's attributes are kept by vtkCutter).  The same kernel packs the per-plane segment lengths.
  */
 __global__ void __launch_bounds__(256)
     k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const float4* __restrict__ nrm,
-                LatticeDev L, const unsigned* __restrict__ planeOff, const uint2* __restrict__ prefix,
-                const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen, float* __restrict__ outPos,
-                float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo, uint32_t* __restrict__ outEdgeHi,
-                unsigned* __restrict__ outSegLen, int emitEdges)
+                LatticeDev L, const unsigned* __restrict__ planeOff, const unsigned* __restrict__ planeMeta,
+                const uint2* __restrict__ prefix, const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen,
+                float* __restrict__ outPos, float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo,
+                uint32_t* __restrict__ outEdgeHi, unsigned* __restrict__ outSegLen, int emitEdges)
 {
-  const unsigned nP = static_cast<unsigned>(L.plane_end - L.plane_begin);
-  const uint2 total = __ldg(prefix + nP);
-  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  const unsigned long long gid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (unsigned long long i = gid; i < total.y; i += stride)
+  const unsigned k = blockIdx.x;
+  const unsigned Wk = __ldg(planeMeta + 2 * k);
+  const unsigned local = blockIdx.y * blockDim.x + threadIdx.x;
+  if (blockIdx.y * blockDim.x >= Wk)
+    return;
+  const unsigned off = __ldg(planeOff + k);
+  const uint2 before = __ldg(prefix + k);
   {
-    const unsigned k = planeOfIndex<true>(prefix, nP, static_cast<unsigned>(i));
-    outSegLen[i] = __ldg(segLen + __ldg(planeOff + k) + (static_cast<unsigned>(i) - __ldg(prefix + k).y));
+    const unsigned Sk = __ldg(planeMeta + 2 * k + 1);
+    if (local < Sk)
+      outSegLen[before.y + local] = __ldg(segLen + off + local);
   }
-  for (unsigned long long i = gid; i < total.x; i += stride)
-  {
-    const unsigned k = planeOfIndex<false>(prefix, nP, static_cast<unsigned>(i));
-    const unsigned tg = __ldg(wpTag + 2ull * __ldg(planeOff + k) + (static_cast<unsigned>(i) - __ldg(prefix + k).x));
-    const unsigned t = tg >> 1;
-    const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
-    // positions and normals of all three vertices are requested together: the two the cut edge needs are only known
-    // after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
-    const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
-    const float4 nv[3] = { __ldg(nrm + ids[0]), __ldg(nrm + ids[1]), __ldg(nrm + ids[2]) };
-    const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
-    double s[3];
+  if (local >= Wk)
+    return;
+  const unsigned long long i = static_cast<unsigned long long>(before.x) + local;
+  const unsigned tg = __ldg(wpTag + 2ull * off + local);
+  const unsigned t = tg >> 1;
+  const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
+  // positions and normals of all three vertices are requested together: the two the cut edge needs are only known
+  // after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
+  const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
+  const float4 nv[3] = { __ldg(nrm + ids[0]), __ldg(nrm + ids[1]), __ldg(nrm + ids[2]) };
+  const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
+  double s[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
-    const CutPoint c = interpolateCut(contourCase(s), tg & 1u, ids, p, s, nv);
-    outPos[3 * i] = c.x;
-    outPos[3 * i + 1] = c.y;
-    outPos[3 * i + 2] = c.z;
-    outNrm[3 * i] = c.nx;
-    outNrm[3 * i + 1] = c.ny;
-    outNrm[3 * i + 2] = c.nz;
-    if (emitEdges)
-    {
-      outEdgeLo[i] = c.lo;
-      outEdgeHi[i] = c.hi;
-    }
+  for (int j = 0; j < 3; ++j)
+    s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+  const CutPoint c = interpolateCut(contourCase(s), tg & 1u, ids, p, s, nv);
+  outPos[3 * i] = c.x;
+  outPos[3 * i + 1] = c.y;
+  outPos[3 * i + 2] = c.z;
+  outNrm[3 * i] = c.nx;
+  outNrm[3 * i + 1] = c.ny;
+  outNrm[3 * i + 2] = c.nz;
+  if (emitEdges)
+  {
+    outEdgeLo[i] = c.lo;
+    outEdgeHi[i] = c.hi;
   }
 }
 
@@ -1183,16 +1169,19 @@ void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint6
   ++c->launches;
 }
 
-void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint64_t w_expected, int emit_edges)
+void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges)
 {
-  // the waypoint total is only known on the device (k_scan_meta): a grid-stride launch sized for the expected count
-  // (one waypoint per hit plus one per chain) covers whatever it turns out to be
-  const int grid = gridFor(w_expected, 256, c->sm_count * 32);
+  // per-plane counts are only known on the device: cover the 2 n_max waypoints the largest plane could have
+  const long long nP = L.plane_end - L.plane_begin;
+  const unsigned chunks = (2u * n_max + 255u) / 256u;
+  if (chunks > 65535u)
+    fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects too many triangles");
+  const dim3 grid(static_cast<unsigned>(nP), chunks > 0 ? chunks : 1u);
   k_waypoints<<<grid, 256, 0, c->stream>>>(c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm.as<float4>(), L,
-                                           c->planeOff.as<unsigned>(), c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(),
-                                           c->segLen.as<unsigned>(), c->outPos.as<float>(), c->outNrm.as<float>(),
-                                           c->outEdge.as<uint32_t>(), c->outEdge.as<uint32_t>() + w_cap,
-                                           c->outSegLen.as<unsigned>(), emit_edges);
+                                           c->planeOff.as<unsigned>(), c->planeMeta.as<unsigned>(),
+                                           c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
+                                           c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(),
+                                           c->outEdge.as<uint32_t>() + w_cap, c->outSegLen.as<unsigned>(), emit_edges);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -167,7 +167,8 @@ struct nb2_context
 
   nb2_lattice last_lattice{};
   bool have_lattice = false;
-  nb2::StageTimer timer;
+  nb2::StageTimer timer;         // last plan / slice / normals call
+  nb2::StageTimer timer_upload;  // last mesh upload
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // nb2_timer_start / nb2_timer_stop
 
   // NCCL (dlopen'ed lazily)
@@ -210,7 +211,7 @@ void launchCountHits(nb2_context* c, const LatticeDev& L);
 void launchScanPlanes(nb2_context* c, const LatticeDev& L);  // writes {H, n_max} to counters[0..1]
 void launchEmitHits(nb2_context* c, const LatticeDev& L);
 void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H);
-void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint64_t w_expected, int emit_edges);
+void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges);
 void launchSetNormals(nb2_context* c, const float* dev_packed);
 void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);
 void launchVertexNormals(nb2_context* c);

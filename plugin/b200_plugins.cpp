@@ -1,0 +1,453 @@
+// noether_b200 plugin library: the B200-native raster-slicing path exported through the reference's own
+// boost_plugin_loader factories, sections and YAML keys.
+//
+// This is the only translation unit of the product that sees noether / PCL / Eigen / yaml-cpp / boost_plugin_loader
+// types.  Everything below the C ABI (include/noether_b200.h) is hand-written sm_100a CUDA in libnoether_b200.so.
+//
+//   alias                 section  replaces (reference, noether_tpp)
+//   PlaneSlicer           tpp      Plugin_PlaneSlicerRasterPlanner        src/plugins.cpp:252-278
+//   PlaneSlicerLegacy     tpp      Plugin_PlaneSlicerLegacyRasterPlanner  src/plugins.cpp:151-179
+//   PrincipalAxis         dg       PrincipalAxisDirectionGenerator        src/plugins.cpp:89
+//   Centroid              og       CentroidOriginGenerator                src/plugins.cpp:111
+//   NormalsFromMeshFaces  mesh     NormalsFromMeshFacesMeshModifier       src/plugins.cpp:62
+//
+// Built against the real headers inside a noether workspace (plugin/CMakeLists.txt).  In the development image those
+// packages do not exist; there the file is compiled against plugin/compat/ (minimal stand-ins declaring the same
+// interfaces) so that the shim and the C ABI are exercised by tests/cpp/plugin_shim_test.cpp.
+#include <noether_b200.h>
+
+#include <noether_tpp/core/mesh_modifier.h>
+#include <noether_tpp/core/tool_path_planner.h>
+#include <noether_tpp/core/types.h>
+#include <noether_tpp/plugin_interface.h>
+#include <noether_tpp/serialization.h>
+#include <noether_tpp/tool_path_planners/raster/raster_planner.h>
+
+#include <pcl/PCLPointCloud2.h>
+#include <pcl/PCLPointField.h>
+#include <pcl/PolygonMesh.h>
+#include <pcl/common/io.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace noether_b200
+{
+// ---------------------------------------------------------------------------------------------------------------------
+// device context shared by the components of this library
+// ---------------------------------------------------------------------------------------------------------------------
+/** One nb2_context per process and device.  The reference's component methods are all `const` and may be called from
+ *  any thread (plugin_interface.h:39-40, tool_path_planner.h:37): calls are serialised here so that "upload, then
+ *  compute on the resident mesh" stays atomic per call. */
+class Device
+{
+public:
+  static Device& instance()
+  {
+    static Device dev;
+    return dev;
+  }
+  std::mutex& mutex() { return mutex_; }
+  nb2_context* ctx()
+  {
+    if (!ctx_)
+    {
+      int ordinal = 0;
+      if (const char* env = std::getenv("NOETHER_B200_DEVICE"))
+        ordinal = std::atoi(env);
+      check(nb2_context_create(ordinal, &ctx_));
+    }
+    return ctx_;
+  }
+  /** status -> exception, the way the reference reports failures (std::runtime_error, caught and re-thrown nested by
+   *  ToolPathPlannerPipeline::plan, tool_path_planner_pipeline.cpp:64-101) */
+  static void check(int status)
+  {
+    if (status != NB2_OK)
+      throw std::runtime_error(nb2_last_error());
+  }
+
+private:
+  Device() = default;
+  ~Device()
+  {
+    if (ctx_)
+      nb2_context_destroy(ctx_);
+  }
+  std::mutex mutex_;
+  nb2_context* ctx_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pcl::PolygonMesh -> nb2_mesh_view (replaces the by-name accessors of utils.cpp:49-117 and the per-plan copies of
+// plane_slicer_raster_planner.cpp:536-537,589-590)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace
+{
+const pcl::PCLPointField* findField(const pcl::PCLPointCloud2& cloud, const char* name)
+{
+  for (const auto& f : cloud.fields)
+    if (f.name == name)
+      return &f;
+  return nullptr;
+}
+
+const pcl::PCLPointField& findFieldOrThrow(const pcl::PCLPointCloud2& cloud, const char* name)
+{
+  const pcl::PCLPointField* f = findField(cloud, name);
+  if (!f)
+    throw std::runtime_error(std::string("Failed to find field '") + name + "'");  // utils.cpp:59-60
+  return *f;
+}
+
+bool hasNormals(const pcl::PCLPointCloud2& cloud)  // utils.cpp:65-72
+{
+  return findField(cloud, "normal_x") && findField(cloud, "normal_y") && findField(cloud, "normal_z");
+}
+
+/** The mesh as the C ABI wants it; owns the flattened triangle list (pcl::Vertices is one heap block per face). */
+struct MeshView
+{
+  nb2_mesh_view view{};
+  std::vector<std::uint32_t> triangles;
+};
+
+MeshView makeView(const pcl::PolygonMesh& mesh, bool want_normals)
+{
+  MeshView m;
+  const pcl::PCLPointCloud2& cloud = mesh.cloud;
+  const auto& x = findFieldOrThrow(cloud, "x");
+  const auto& y = findFieldOrThrow(cloud, "y");
+  const auto& z = findFieldOrThrow(cloud, "z");
+  if ((y.offset - x.offset != 4) || (z.offset - y.offset != 4) || x.datatype != pcl::PCLPointField::FLOAT32)
+    throw std::runtime_error("XYZ fields are not contiguous floats");  // utils.cpp:82-83
+  m.view.cloud_data = cloud.data.data();
+  m.view.n_points = static_cast<std::uint64_t>(cloud.width) * cloud.height;  // utils.cpp:169
+  m.view.point_step = cloud.point_step;
+  m.view.offset_xyz = x.offset;
+  m.view.offset_normal = -1;
+  if (want_normals && hasNormals(cloud))
+  {
+    const auto& nx = findFieldOrThrow(cloud, "normal_x");
+    const auto& ny = findFieldOrThrow(cloud, "normal_y");
+    const auto& nz = findFieldOrThrow(cloud, "normal_z");
+    if ((ny.offset - nx.offset != 4) || (nz.offset - ny.offset != 4) || nx.datatype != pcl::PCLPointField::FLOAT32)
+      throw std::runtime_error("Normal fields are not contiguous floats");  // utils.cpp:104-105
+    m.view.offset_normal = static_cast<std::int32_t>(nx.offset);
+  }
+  m.triangles.reserve(3 * mesh.polygons.size());
+  for (const auto& p : mesh.polygons)
+  {
+    if (p.vertices.size() < 3)
+      throw std::runtime_error("Polygon has fewer than 3 vertices");  // getFaceNormal, utils.cpp:137-142
+    if (p.vertices.size() != 3)
+      throw std::runtime_error("noether_b200 slices triangle meshes only; triangulate the mesh first");
+    for (const auto v : p.vertices)
+      m.triangles.push_back(static_cast<std::uint32_t>(v));
+  }
+  m.view.triangles = m.triangles.data();
+  m.view.n_triangles = mesh.polygons.size();
+  return m;
+}
+
+void upload(nb2_context* ctx, const pcl::PolygonMesh& mesh, bool want_normals)
+{
+  const MeshView m = makeView(mesh, want_normals);
+  Device::check(nb2_mesh_upload(ctx, &m.view));
+}
+
+/** SoA result -> noether::ToolPaths (core/types.h:31-50): nested vectors of Eigen::Isometry3d */
+noether::ToolPaths toToolPaths(const nb2_result* r)
+{
+  nb2_result_view v{};
+  Device::check(nb2_result_get(r, &v));
+  std::vector<double> poses(16 * v.n_waypoints);
+  Device::check(nb2_result_poses(r, poses.data()));
+  noether::ToolPaths out;
+  out.reserve(v.n_paths);
+  for (std::uint64_t p = 0; p < v.n_paths; ++p)
+  {
+    noether::ToolPath path;
+    path.reserve(v.path_offsets[p + 1] - v.path_offsets[p]);
+    for (std::uint32_t s = v.path_offsets[p]; s < v.path_offsets[p + 1]; ++s)
+    {
+      noether::ToolPathSegment seg;
+      seg.reserve(v.segment_offsets[s + 1] - v.segment_offsets[s]);
+      for (std::uint32_t w = v.segment_offsets[s]; w < v.segment_offsets[s + 1]; ++w)
+      {
+        Eigen::Isometry3d pose;  // 4x4 double, column-major, last row 0 0 0 1 — the layout nb2_result_poses writes
+        std::memcpy(pose.matrix().data(), poses.data() + 16 * static_cast<std::size_t>(w), 16 * sizeof(double));
+        seg.push_back(pose);
+      }
+      path.push_back(std::move(seg));
+    }
+    out.push_back(std::move(path));
+  }
+  return out;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// generators
+// ---------------------------------------------------------------------------------------------------------------------
+/** PrincipalAxisDirectionGenerator (principal_axis_direction_generator.cpp:14-26): the PCA runs on the GPU as part of
+ *  the ingest pass. */
+class PrincipalAxisDirectionGenerator : public noether::DirectionGenerator
+{
+public:
+  explicit PrincipalAxisDirectionGenerator(double rotation_offset = 0.0) : rotation_offset_(rotation_offset) {}
+  double rotationOffset() const { return rotation_offset_; }
+
+  Eigen::Vector3d generate(const pcl::PolygonMesh& mesh) const override final
+  {
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    upload(dev.ctx(), mesh, false);
+    double d[3];
+    Device::check(nb2_principal_axis_direction(dev.ctx(), rotation_offset_, d));
+    return Eigen::Vector3d(d[0], d[1], d[2]);
+  }
+
+private:
+  double rotation_offset_;
+};
+
+/** CentroidOriginGenerator (centroid_origin_generator.cpp:8-17) */
+class CentroidOriginGenerator : public noether::OriginGenerator
+{
+public:
+  Eigen::Vector3d generate(const pcl::PolygonMesh& mesh) const override final
+  {
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    upload(dev.ctx(), mesh, false);
+    double o[3];
+    Device::check(nb2_centroid_origin(dev.ctx(), o));
+    return Eigen::Vector3d(o[0], o[1], o[2]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// planners
+// ---------------------------------------------------------------------------------------------------------------------
+/**
+ * PlaneSlicerRasterPlanner (plane_slicer_raster_planner.cpp:518-631).  Deriving from noether::RasterPlanner keeps the
+ * reference's own `plan` (raster_planner.cpp:16-35, final): it calls this planImpl and then applies the reference's
+ * RasterOrganizationModifier and DirectionOfTravelOrientationModifier, so post-processing is the reference's code.
+ *
+ * When the configured generators are this library's PrincipalAxis / Centroid, their values come out of the same mesh
+ * upload as the plan (one H2D copy, one PCA); any other generator (FixedDirection, PCARotated, Offset, ... from the
+ * reference's plugin library) is evaluated through its own `generate` and passed as an explicit vector.
+ */
+class PlaneSlicerRasterPlanner : public noether::RasterPlanner
+{
+public:
+  PlaneSlicerRasterPlanner(noether::DirectionGenerator::ConstPtr dir_gen, noether::OriginGenerator::ConstPtr origin_gen)
+    : noether::RasterPlanner(std::move(dir_gen), std::move(origin_gen))
+  {
+  }
+  void generateRastersBidirectionally(const bool bidirectional) { bidirectional_ = bidirectional; }
+
+protected:
+  virtual void fillLegacy(nb2_plan_params&) const {}
+
+  noether::ToolPaths planImpl(const pcl::PolygonMesh& mesh) const override
+  {
+    if (!hasNormals(mesh.cloud))  // same message as plane_slicer_raster_planner.cpp:520-528
+      throw std::runtime_error("The input mesh does not have vertex normals, which are required for the plane slice "
+                               "raster tool path planner. Use a MeshModifier to generate vertex normals for the mesh, "
+                               "or provide a different mesh with vertex normals.");
+    nb2_plan_params prm;
+    nb2_plan_params_default(&prm);
+    prm.line_spacing = line_spacing_;
+    prm.bidirectional = bidirectional_ ? 1 : 0;
+    prm.raster_post_ops = 0;  // RasterPlanner::plan applies the reference's own modifiers after planImpl
+    prm.emit_edges = 0;
+    fillLegacy(prm);
+
+    // foreign generators run first: they may use the device themselves (through this library or not)
+    if (const auto* pa = dynamic_cast<const PrincipalAxisDirectionGenerator*>(dir_gen_.get()))
+    {
+      prm.direction_mode = NB2_DIRECTION_PRINCIPAL_AXIS;
+      prm.rotation_offset = pa->rotationOffset();
+    }
+    else
+    {
+      const Eigen::Vector3d d = dir_gen_->generate(mesh);
+      prm.direction_mode = NB2_DIRECTION_EXPLICIT;
+      prm.direction[0] = d.x(), prm.direction[1] = d.y(), prm.direction[2] = d.z();
+    }
+    if (dynamic_cast<const CentroidOriginGenerator*>(origin_gen_.get()))
+      prm.origin_mode = NB2_ORIGIN_CENTROID;
+    else
+    {
+      const Eigen::Vector3d o = origin_gen_->generate(mesh);
+      prm.origin_mode = NB2_ORIGIN_EXPLICIT;
+      prm.origin[0] = o.x(), prm.origin[1] = o.y(), prm.origin[2] = o.z();
+    }
+
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    upload(dev.ctx(), mesh, true);
+    nb2_result* r = nullptr;
+    Device::check(nb2_plan(dev.ctx(), &prm, &r));
+    std::unique_ptr<nb2_result, void (*)(nb2_result*)> guard(r, nb2_result_free);
+    return toToolPaths(r);
+  }
+
+  bool bidirectional_ = true;
+};
+
+/** PlaneSlicerLegacyRasterPlanner (plane_slicer_legacy_raster_planner.cpp:22-33): the plane slicer followed by
+ *  JoinCloseSegments, MinimumSegmentLength and UniformSpacing(degree 1). */
+class PlaneSlicerLegacyRasterPlanner : public PlaneSlicerRasterPlanner
+{
+public:
+  PlaneSlicerLegacyRasterPlanner(noether::DirectionGenerator::ConstPtr dir_gen, noether::OriginGenerator::ConstPtr origin_gen,
+                                 const double point_spacing, const double min_segment_size, const double min_hole_size)
+    : PlaneSlicerRasterPlanner(std::move(dir_gen), std::move(origin_gen))
+    , point_spacing_(point_spacing)
+    , min_segment_size_(min_segment_size)
+    , min_hole_size_(min_hole_size)
+  {
+  }
+
+protected:
+  void fillLegacy(nb2_plan_params& prm) const override
+  {
+    prm.legacy = 1;
+    prm.point_spacing = point_spacing_;
+    prm.min_segment_size = min_segment_size_;
+    prm.min_hole_size = min_hole_size_;
+  }
+
+  double point_spacing_, min_segment_size_, min_hole_size_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mesh modifier
+// ---------------------------------------------------------------------------------------------------------------------
+/** NormalsFromMeshFacesMeshModifier (normals_from_mesh_faces_modifier.cpp:15-46): vertex normals on the GPU, then the
+ *  reference's own field concatenation (pcl::concatenateFields) so the output cloud has the layout the reference
+ *  produces: a 32-byte pcl::Normal record (normal_x, normal_y, normal_z, curvature) followed by the input's fields. */
+class NormalsFromMeshFacesMeshModifier : public noether::MeshModifier
+{
+public:
+  std::vector<pcl::PolygonMesh> modify(const pcl::PolygonMesh& mesh) const override final
+  {
+    const std::size_t n = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+    std::vector<float> normals(3 * n);
+    {
+      Device& dev = Device::instance();
+      std::lock_guard<std::mutex> lock(dev.mutex());
+      upload(dev.ctx(), mesh, false);
+      Device::check(nb2_normals_from_mesh_faces(dev.ctx(), normals.data()));
+    }
+    // what pcl::toPCLPointCloud2(pcl::PointCloud<pcl::Normal>) yields: 32-byte points, zero curvature / padding
+    pcl::PCLPointCloud2 normals_pc2;
+    normals_pc2.header = mesh.cloud.header;
+    normals_pc2.width = mesh.cloud.width;
+    normals_pc2.height = mesh.cloud.height;
+    normals_pc2.is_bigendian = false;
+    normals_pc2.is_dense = true;
+    normals_pc2.point_step = 32;
+    normals_pc2.row_step = 32 * mesh.cloud.width;
+    const char* names[4] = { "normal_x", "normal_y", "normal_z", "curvature" };
+    const std::uint32_t offsets[4] = { 0, 4, 8, 16 };
+    for (int i = 0; i < 4; ++i)
+    {
+      pcl::PCLPointField f;
+      f.name = names[i];
+      f.offset = offsets[i];
+      f.datatype = pcl::PCLPointField::FLOAT32;
+      f.count = 1;
+      normals_pc2.fields.push_back(f);
+    }
+    normals_pc2.data.assign(32 * n, 0);
+    for (std::size_t i = 0; i < n; ++i)
+      std::memcpy(normals_pc2.data.data() + 32 * i, normals.data() + 3 * i, 12);
+
+    pcl::PolygonMesh output = mesh;
+    if (!pcl::concatenateFields(mesh.cloud, normals_pc2, output.cloud))
+      throw std::runtime_error("Failed to concatenate normals into mesh vertex cloud");  // :42-43
+    return { output };
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// plugins: same aliases, sections and YAML keys as the reference (src/plugins.cpp)
+// ---------------------------------------------------------------------------------------------------------------------
+struct Plugin_PrincipalAxisDirectionGenerator : public noether::Plugin<noether::DirectionGenerator>
+{
+  std::unique_ptr<noether::DirectionGenerator> create(const YAML::Node& config,
+                                                      std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    // principal_axis_direction_generator.cpp:41-45
+    return std::make_unique<PrincipalAxisDirectionGenerator>(YAML::getMember<double>(config, "rotation_offset"));
+  }
+};
+
+struct Plugin_CentroidOriginGenerator : public noether::Plugin<noether::OriginGenerator>
+{
+  std::unique_ptr<noether::OriginGenerator> create(const YAML::Node& /*config*/,
+                                                   std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<CentroidOriginGenerator>();
+  }
+};
+
+struct Plugin_NormalsFromMeshFacesMeshModifier : public noether::Plugin<noether::MeshModifier>
+{
+  std::unique_ptr<noether::MeshModifier> create(const YAML::Node& /*config*/,
+                                                std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<NormalsFromMeshFacesMeshModifier>();
+  }
+};
+
+struct Plugin_PlaneSlicerRasterPlanner : public noether::Plugin<noether::ToolPathPlanner>
+{
+  std::unique_ptr<noether::ToolPathPlanner> create(const YAML::Node& config,
+                                                   std::shared_ptr<const noether::Factory> factory) const override final
+  {
+    // nested generators are created through the factory, so the reference's FixedDirection / FixedOrigin / PCARotated /
+    // Offset generators compose with this planner (plugins.cpp:257-266)
+    auto dir_gen = factory->createDirectionGenerator(YAML::getMember<YAML::Node>(config, "direction_generator"));
+    auto origin_gen = factory->createOriginGenerator(YAML::getMember<YAML::Node>(config, "origin_generator"));
+    auto tpp = std::make_unique<PlaneSlicerRasterPlanner>(std::move(dir_gen), std::move(origin_gen));
+    tpp->setLineSpacing(YAML::getMember<double>(config, "line_spacing"));
+    tpp->generateRastersBidirectionally(YAML::getMember<bool>(config, "bidirectional"));
+    return tpp;
+  }
+};
+
+struct Plugin_PlaneSlicerLegacyRasterPlanner : public noether::Plugin<noether::ToolPathPlanner>
+{
+  std::unique_ptr<noether::ToolPathPlanner> create(const YAML::Node& config,
+                                                   std::shared_ptr<const noether::Factory> factory) const override final
+  {
+    auto dir_gen = factory->createDirectionGenerator(YAML::getMember<YAML::Node>(config, "direction_generator"));
+    auto origin_gen = factory->createOriginGenerator(YAML::getMember<YAML::Node>(config, "origin_generator"));
+    auto tpp = std::make_unique<PlaneSlicerLegacyRasterPlanner>(std::move(dir_gen), std::move(origin_gen),
+                                                                YAML::getMember<double>(config, "point_spacing"),
+                                                                YAML::getMember<double>(config, "min_segment_size"),
+                                                                YAML::getMember<double>(config, "min_hole_size"));
+    tpp->setLineSpacing(YAML::getMember<double>(config, "line_spacing"));
+    tpp->generateRastersBidirectionally(YAML::getMember<bool>(config, "bidirectional"));
+    return tpp;
+  }
+};
+
+}  // namespace noether_b200
+
+EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
+EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)
+EXPORT_ORIGIN_GENERATOR_PLUGIN(noether_b200::Plugin_CentroidOriginGenerator, Centroid)
+EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerRasterPlanner, PlaneSlicer)
+EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerLegacyRasterPlanner, PlaneSlicerLegacy)

@@ -1,0 +1,459 @@
+// The reference's own planner / mesh-modifier tests, re-expressed through the plugin boundary of noether_b200:
+//
+//   RasterPlannerTestFixture.FlatSquareMesh      noether_tpp/test/tool_path_planner_utest.cpp:74-120
+//   RasterPlannerTestFixture.SemiPlanarMeshFile  noether_tpp/test/tool_path_planner_utest.cpp:122-177
+//   MeshModifier field retention                 noether_tpp/test/mesh_modifier_utest.cpp:104-113,154-183
+//
+// The components are created the way the reference tests create them: by alias, from a YAML node, through a
+// noether::Factory that resolves plugins out of a shared library (tool_path_planner_utest.cpp:51-59).  Here that
+// library is plugin/b200_plugins.cpp compiled against plugin/compat (the development image has no PCL / Eigen /
+// yaml-cpp / boost_plugin_loader); `FixedDirection` and `FixedOrigin`, which the reference tests take from the
+// reference's plugin library, are supplied by this executable.  Needs a B200: run by tests/test_plugin_shim.py.
+//
+//   usage: plugin_shim_test <libnoether_b200_plugins.so> <wavy_mesh_with_hole.ply>
+#include <noether_tpp/plugin_interface.h>
+#include <noether_tpp/serialization.h>
+
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+
+namespace
+{
+int g_failures = 0;
+#define CHECK(cond)                                                                                                    \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    if (!(cond))                                                                                                       \
+    {                                                                                                                  \
+      std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);                                                  \
+      ++g_failures;                                                                                                    \
+    }                                                                                                                  \
+  } while (0)
+
+Eigen::Vector3d readVector(const YAML::Node& n)
+{
+  return Eigen::Vector3d(YAML::getMember<double>(n, "x"), YAML::getMember<double>(n, "y"), YAML::getMember<double>(n, "z"));
+}
+YAML::Node vectorNode(double x, double y, double z)
+{
+  YAML::Node n;
+  n["x"] = x;
+  n["y"] = y;
+  n["z"] = z;
+  return n;
+}
+
+// ---- the two reference generators the reference tests configure (fixed_direction_generator.cpp, fixed_origin_generator.cpp)
+struct FixedDirectionGenerator : noether::DirectionGenerator
+{
+  Eigen::Vector3d dir;
+  Eigen::Vector3d generate(const pcl::PolygonMesh&) const override { return dir; }
+};
+struct FixedOriginGenerator : noether::OriginGenerator
+{
+  Eigen::Vector3d origin;
+  Eigen::Vector3d generate(const pcl::PolygonMesh&) const override { return origin; }
+};
+struct Plugin_FixedDirection : noether::Plugin<noether::DirectionGenerator>
+{
+  std::unique_ptr<noether::DirectionGenerator> create(const YAML::Node& config,
+                                                      std::shared_ptr<const noether::Factory>) const override
+  {
+    auto g = std::make_unique<FixedDirectionGenerator>();
+    g->dir = readVector(YAML::getMember<YAML::Node>(config, "direction"));
+    return g;
+  }
+};
+struct Plugin_FixedOrigin : noether::Plugin<noether::OriginGenerator>
+{
+  std::unique_ptr<noether::OriginGenerator> create(const YAML::Node& config,
+                                                   std::shared_ptr<const noether::Factory>) const override
+  {
+    auto g = std::make_unique<FixedOriginGenerator>();
+    g->origin = readVector(YAML::getMember<YAML::Node>(config, "origin"));
+    return g;
+  }
+};
+}  // namespace
+EXPORT_DIRECTION_GENERATOR_PLUGIN(Plugin_FixedDirection, FixedDirection)
+EXPORT_ORIGIN_GENERATOR_PLUGIN(Plugin_FixedOrigin, FixedOrigin)
+
+namespace
+{
+// ---- fixtures ---------------------------------------------------------------------------------------------------------
+void addField(pcl::PCLPointCloud2& c, const char* name, unsigned offset, std::uint8_t type = pcl::PCLPointField::FLOAT32)
+{
+  pcl::PCLPointField f;
+  f.name = name;
+  f.offset = offset;
+  f.datatype = type;
+  f.count = 1;
+  c.fields.push_back(f);
+}
+
+/** createPlaneMesh (utils.cpp:249-291): 4 pcl::PointNormal vertices (48-byte records), polygons {0,1,3} {1,2,3};
+ *  R (row-major 3x3) and t place it in space as the reference test's random transform does */
+pcl::PolygonMesh planeMesh(float lx, float ly, const double R[9], const double t[3])
+{
+  pcl::PolygonMesh mesh;
+  pcl::PCLPointCloud2& c = mesh.cloud;
+  c.width = 4;
+  c.height = 1;
+  c.point_step = 48;
+  c.row_step = 4 * 48;
+  c.is_dense = 1;
+  addField(c, "x", 0), addField(c, "y", 4), addField(c, "z", 8);
+  addField(c, "normal_x", 16), addField(c, "normal_y", 20), addField(c, "normal_z", 24), addField(c, "curvature", 32);
+  const float pts[4][3] = { { -lx / 2, ly / 2, 0 }, { -lx / 2, -ly / 2, 0 }, { lx / 2, -ly / 2, 0 }, { lx / 2, ly / 2, 0 } };
+  c.data.assign(4 * 48, 0);
+  for (int i = 0; i < 4; ++i)
+  {
+    float rec[12] = { 0 };
+    for (int r = 0; r < 3; ++r)
+    {
+      rec[r] = static_cast<float>(R[3 * r] * pts[i][0] + R[3 * r + 1] * pts[i][1] + R[3 * r + 2] * pts[i][2] + t[r]);
+      rec[4 + r] = static_cast<float>(R[3 * r + 2]);  // R * (0, 0, 1)
+    }
+    std::memcpy(c.data.data() + 48 * i, rec, 48);
+  }
+  pcl::Vertices a, b;
+  a.vertices = { 0, 1, 3 };
+  b.vertices = { 1, 2, 3 };
+  mesh.polygons = { a, b };
+  return mesh;
+}
+
+/** wavy_mesh_with_hole.ply (binary little endian: x y z nx ny nz float, r g b a uchar; faces uchar n + int[n]) as
+ *  pcl::io::loadPolygonFile lays it out: PointXYZRGBNormal, 48-byte records */
+pcl::PolygonMesh loadPly(const std::string& path)
+{
+  std::ifstream f(path, std::ios::binary);
+  if (!f)
+    throw std::runtime_error("cannot open " + path);
+  std::string line;
+  std::size_t nv = 0, nf = 0;
+  while (std::getline(f, line))
+  {
+    std::istringstream ss(line);
+    std::string a, b;
+    ss >> a >> b;
+    if (a == "element" && b == "vertex")
+      ss >> nv;
+    if (a == "element" && b == "face")
+      ss >> nf;
+    if (a == "end_header")
+      break;
+  }
+  pcl::PolygonMesh mesh;
+  pcl::PCLPointCloud2& c = mesh.cloud;
+  c.width = static_cast<unsigned>(nv);
+  c.height = 1;
+  c.point_step = 48;
+  c.row_step = c.point_step * c.width;
+  addField(c, "x", 0), addField(c, "y", 4), addField(c, "z", 8);
+  addField(c, "normal_x", 16), addField(c, "normal_y", 20), addField(c, "normal_z", 24);
+  addField(c, "rgb", 32), addField(c, "curvature", 36);
+  c.data.assign(nv * 48, 0);
+  for (std::size_t i = 0; i < nv; ++i)
+  {
+    char rec[28];
+    f.read(rec, 28);
+    std::memcpy(c.data.data() + 48 * i, rec, 12);            // x y z
+    std::memcpy(c.data.data() + 48 * i + 16, rec + 12, 12);  // normals
+    std::memcpy(c.data.data() + 48 * i + 32, rec + 24, 4);   // rgba
+  }
+  for (std::size_t i = 0; i < nf; ++i)
+  {
+    unsigned char n;
+    f.read(reinterpret_cast<char*>(&n), 1);
+    pcl::Vertices v;
+    for (int k = 0; k < n; ++k)
+    {
+      std::int32_t id;
+      f.read(reinterpret_cast<char*>(&id), 4);
+      v.vertices.push_back(static_cast<pcl::index_t>(id));
+    }
+    mesh.polygons.push_back(v);
+  }
+  if (!f)
+    throw std::runtime_error("truncated PLY " + path);
+  return mesh;
+}
+
+/** the reference tests' parameter YAML (tool_path_planner_utest.cpp:259-275), including the stale keys the plugin must
+ *  ignore */
+YAML::Node planeSlicerConfig(const char* alias, double line_spacing, const Eigen::Vector3d& dir, const Eigen::Vector3d& origin)
+{
+  YAML::Node config;
+  config["name"] = alias;
+  config["line_spacing"] = line_spacing;
+  config["point_spacing"] = 0.25;
+  config["min_segment_size"] = 0.5;
+  config["min_hole_size"] = 0.0;
+  config["search_radius"] = 0.1;
+  config["bidirectional"] = true;
+  YAML::Node dg;
+  dg["name"] = "FixedDirection";
+  dg["direction"] = vectorNode(dir.x(), dir.y(), dir.z());
+  config["direction_generator"] = dg;
+  YAML::Node og;
+  og["name"] = "FixedOrigin";
+  og["origin"] = vectorNode(origin.x(), origin.y(), origin.z());
+  config["origin_generator"] = og;
+  return config;
+}
+
+Eigen::Vector3d sub(const Eigen::Vector3d& a, const Eigen::Vector3d& b) { return { a.x() - b.x(), a.y() - b.y(), a.z() - b.z() }; }
+double dot(const Eigen::Vector3d& a, const Eigen::Vector3d& b) { return a.x() * b.x() + a.y() * b.y() + a.z() * b.z(); }
+double norm(const Eigen::Vector3d& a) { return std::sqrt(dot(a, a)); }
+
+// ---- tests --------------------------------------------------------------------------------------------------------------
+void testFlatSquareMesh(const noether::Factory& factory, const char* alias)
+{
+  std::printf("[FlatSquareMesh / %s]\n", alias);
+  // a rigid transform with no special axis (the reference draws one from mt19937(0))
+  const double a = 0.7, b = -1.1, c = 2.3;
+  const double ca = std::cos(a), sa = std::sin(a), cb = std::cos(b), sb = std::sin(b), cc = std::cos(c), sc = std::sin(c);
+  const double R[9] = { cc * cb, cc * sb * sa - sc * ca, cc * sb * ca + sc * sa, sc * cb, sc * sb * sa + cc * ca,
+                        sc * sb * ca - cc * sa,  -sb, cb * sa, cb * ca };
+  const double t[3] = { 3.5, -1.25, 4.0 };
+  const pcl::PolygonMesh mesh = planeMesh(1.f, 1.f, R, t);
+  const Eigen::Vector3d direction(R[0], R[3], R[6]);  // R * UnitX
+  const unsigned n_lines = 10;
+  YAML::Node config = planeSlicerConfig(alias, 0.95 * 1.0 / n_lines, direction, Eigen::Vector3d(t[0], t[1], t[2]));
+  std::shared_ptr<const noether::ToolPathPlanner> planner = factory.createToolPathPlanner(config);
+  noether::ToolPaths tool_paths = planner->plan(mesh);
+  CHECK(tool_paths.size() == n_lines + 1);
+  for (const noether::ToolPath& path : tool_paths)
+  {
+    CHECK(path.size() == 1);
+    if (path.empty() || path.front().size() < 2)
+    {
+      CHECK(false);
+      continue;
+    }
+    const Eigen::Vector3d first = path.front().front().translation(), last = path.back().back().translation();
+    const Eigen::Vector3d d = sub(last, first);
+    CHECK(std::abs(dot(d, direction)) / norm(d) > std::cos(1.0 * M_PI / 180.0));
+    for (const auto& wp : path.front())
+    {
+      // every pose is a rigid transform whose z axis is the mesh normal R * UnitZ
+      const auto& m = wp.matrix();
+      CHECK(m(3, 0) == 0.0 && m(3, 1) == 0.0 && m(3, 2) == 0.0 && m(3, 3) == 1.0);
+      CHECK(std::abs(m(0, 2) - R[2]) < 1e-6 && std::abs(m(1, 2) - R[5]) < 1e-6 && std::abs(m(2, 2) - R[8]) < 1e-6);
+    }
+  }
+}
+
+void testSemiPlanarMeshFile(const noether::Factory& factory, const pcl::PolygonMesh& mesh, const char* alias, bool legacy)
+{
+  std::printf("[SemiPlanarMeshFile / %s]\n", alias);
+  const Eigen::Vector3d direction(1, 0, 0);
+  const unsigned n_lines = 10;
+  YAML::Node config = planeSlicerConfig(alias, 10.5 / n_lines, direction, Eigen::Vector3d(0, 0, 0));
+  std::shared_ptr<const noether::ToolPathPlanner> planner = factory.createToolPathPlanner(config);
+  noether::ToolPaths tool_paths = planner->plan(mesh);
+  CHECK(tool_paths.size() == n_lines);
+  // planImpl returns the rasters in lattice order; the reference's RasterOrganizationModifier (applied by the real
+  // RasterPlanner::plan) may reverse that order, so the hole rows are 4,5,6 counted from one end or the other
+  unsigned two_from_front = 0, two_from_back = 0;
+  for (std::size_t i = 0; i < tool_paths.size(); ++i)
+  {
+    const noether::ToolPath& path = tool_paths[i];
+    CHECK(path.size() >= 1);
+    CHECK(!path.empty() && path.front().size() >= 2);
+    if (i > 3 && i < 7)
+      two_from_front += path.size() == 2;
+    if (tool_paths.size() - 1 - i > 3 && tool_paths.size() - 1 - i < 7)
+      two_from_back += path.size() == 2;
+    if (path.empty() || path.front().empty())
+      continue;
+    // direction check of the reference (10 degrees); segments of a raster may be stored in either order before the
+    // organisation modifier runs, so take the extreme waypoints along the direction
+    double lo = 1e300, hi = -1e300;
+    Eigen::Vector3d pl, ph;
+    for (const auto& seg : path)
+      for (const auto& wp : seg)
+      {
+        const double k = dot(wp.translation(), direction);
+        if (k < lo)
+          lo = k, pl = wp.translation();
+        if (k > hi)
+          hi = k, ph = wp.translation();
+      }
+    const Eigen::Vector3d d = sub(ph, pl);
+    CHECK(std::abs(dot(d, direction)) / norm(d) > std::cos(10.0 * M_PI / 180.0));
+  }
+  CHECK(two_from_front == 3 || two_from_back == 3);
+  (void)legacy;
+}
+
+void testNormalsFieldRetention(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[MeshModifier field retention / NormalsFromMeshFaces]\n");
+  YAML::Node config;
+  config["name"] = "NormalsFromMeshFaces";
+  std::shared_ptr<const noether::MeshModifier> mod = factory.createMeshModifier(config);
+  const std::vector<pcl::PolygonMesh> out = mod->modify(mesh);
+  CHECK(out.size() == 1);
+  if (out.empty())
+    return;
+  const pcl::PolygonMesh& m = out.front();
+  CHECK(m.polygons.size() == mesh.polygons.size());
+  CHECK(m.cloud.width * m.cloud.height == mesh.cloud.width * mesh.cloud.height);
+  CHECK(m.cloud.data.size() == static_cast<std::size_t>(m.cloud.point_step) * m.cloud.width * m.cloud.height);
+  // every input field is still present, with its datatype and count (mesh_modifier_utest.cpp:104-113)
+  for (const auto& f : mesh.cloud.fields)
+  {
+    bool found = false;
+    for (const auto& g : m.cloud.fields)
+      found = found || (g.name == f.name && g.datatype == f.datatype && g.count == f.count);
+    CHECK(found);
+  }
+  // the new normals are unit vectors that agree with the file's own vertex normals on this smooth surface
+  unsigned off_new = 0, off_old = 0, off_xyz_new = 0, off_xyz_old = 0;
+  for (const auto& g : m.cloud.fields)
+  {
+    if (g.name == "normal_x")
+      off_new = g.offset;
+    if (g.name == "x")
+      off_xyz_new = g.offset;
+  }
+  for (const auto& g : mesh.cloud.fields)
+  {
+    if (g.name == "normal_x")
+      off_old = g.offset;
+    if (g.name == "x")
+      off_xyz_old = g.offset;
+  }
+  double worst = 1.0;
+  bool xyz_same = true;
+  const std::size_t n = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+  for (std::size_t i = 0; i < n; ++i)
+  {
+    float a[3], b[3];
+    std::memcpy(a, m.cloud.data.data() + i * m.cloud.point_step + off_new, 12);
+    std::memcpy(b, mesh.cloud.data.data() + i * mesh.cloud.point_step + off_old, 12);
+    const double na = std::sqrt(double(a[0]) * a[0] + double(a[1]) * a[1] + double(a[2]) * a[2]);
+    CHECK(std::abs(na - 1.0) < 1e-5);
+    worst = std::min(worst, (double(a[0]) * b[0] + double(a[1]) * b[1] + double(a[2]) * b[2]) / na);
+    xyz_same = xyz_same && std::memcmp(m.cloud.data.data() + i * m.cloud.point_step + off_xyz_new,
+                                       mesh.cloud.data.data() + i * mesh.cloud.point_step + off_xyz_old, 12) == 0;
+  }
+  CHECK(xyz_same);
+  CHECK(worst > 0.9);
+  // and the planner accepts the modifier's output cloud (normals first, 80-byte records)
+  YAML::Node pc = planeSlicerConfig("PlaneSlicer", 1.05, Eigen::Vector3d(1, 0, 0), Eigen::Vector3d(0, 0, 0));
+  CHECK(factory.createToolPathPlanner(pc)->plan(m).size() == 10);
+}
+
+void testGeneratorsAndErrors(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[PrincipalAxis / Centroid / error behaviour]\n");
+  YAML::Node dg;
+  dg["name"] = "PrincipalAxis";
+  dg["rotation_offset"] = 0.0;
+  const Eigen::Vector3d d = factory.createDirectionGenerator(dg)->generate(mesh);
+  CHECK(std::abs(norm(d) - 1.0) < 1e-6);
+  CHECK(std::abs(d.z()) < 0.2);  // the second principal axis of this 10.5 x 10.5 x 4 surface lies near the xy plane
+  YAML::Node og;
+  og["name"] = "Centroid";
+  const Eigen::Vector3d o = factory.createOriginGenerator(og)->generate(mesh);
+  CHECK(std::abs(o.x() - 5.25) < 0.5 && std::abs(o.y() - 5.25) < 0.5);
+  // PlaneSlicer with this library's own generators: one upload, PCA direction and centroid taken on the device
+  YAML::Node config;
+  config["name"] = "PlaneSlicer";
+  config["line_spacing"] = 1.05;
+  config["bidirectional"] = true;
+  config["direction_generator"] = dg;
+  config["origin_generator"] = og;
+  const noether::ToolPaths tp = factory.createToolPathPlanner(config)->plan(mesh);
+  CHECK(tp.size() >= 9 && tp.size() <= 16);
+
+  // missing YAML key: the reference's message (serialization.h:13-14)
+  YAML::Node bad = planeSlicerConfig("PlaneSlicer", 1.0, Eigen::Vector3d(1, 0, 0), Eigen::Vector3d(0, 0, 0));
+  YAML::Node bad2;
+  bad2["name"] = "PlaneSlicer";
+  bad2["direction_generator"] = bad["direction_generator"];
+  bad2["origin_generator"] = bad["origin_generator"];
+  bad2["bidirectional"] = true;
+  try
+  {
+    factory.createToolPathPlanner(bad2);
+    CHECK(false);
+  }
+  catch (const std::exception& e)
+  {
+    CHECK(std::string(e.what()) == "Required member 'line_spacing' not found in YAML node");
+  }
+  // mesh without normals: the reference's message (plane_slicer_raster_planner.cpp:520-528)
+  pcl::PolygonMesh stripped = mesh;
+  for (auto& f : stripped.cloud.fields)
+    if (f.name.rfind("normal_", 0) == 0)
+      f.name = "was_" + f.name;
+  try
+  {
+    factory.createToolPathPlanner(bad)->plan(stripped);
+    CHECK(false);
+  }
+  catch (const std::exception& e)
+  {
+    CHECK(std::string(e.what()).find("does not have vertex normals") != std::string::npos);
+  }
+  // a quad face is refused rather than mis-sliced
+  pcl::PolygonMesh quad = mesh;
+  quad.polygons[0].vertices.push_back(quad.polygons[1].vertices[2]);
+  try
+  {
+    factory.createToolPathPlanner(bad)->plan(quad);
+    CHECK(false);
+  }
+  catch (const std::exception& e)
+  {
+    CHECK(std::string(e.what()).find("triangle") != std::string::npos);
+  }
+}
+}  // namespace
+
+int main(int argc, char** argv)
+{
+  if (argc < 3)
+  {
+    std::printf("usage: %s <plugin library> <wavy_mesh_with_hole.ply>\n", argv[0]);
+    return 2;
+  }
+  void* lib = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+  if (!lib)
+  {
+    std::printf("dlopen failed: %s\n", dlerror());
+    return 2;
+  }
+  auto loader = std::make_shared<boost_plugin_loader::PluginLoader>();
+  loader->libraries = { lib, dlopen(nullptr, RTLD_NOW) };  // our plugin library first, then this executable's generators
+  const noether::Factory factory(loader);
+  try
+  {
+    for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "Centroid", "NormalsFromMeshFaces" })
+      CHECK(dlsym(lib, alias) != nullptr);
+    const pcl::PolygonMesh ply = loadPly(argv[2]);
+    CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);
+    testFlatSquareMesh(factory, "PlaneSlicer");
+    testSemiPlanarMeshFile(factory, ply, "PlaneSlicer", false);
+    testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);
+    testNormalsFieldRetention(factory, ply);
+    testGeneratorsAndErrors(factory, ply);
+  }
+  catch (const std::exception& e)
+  {
+    std::printf("  FAILED with exception: %s\n", e.what());
+    ++g_failures;
+  }
+  std::printf(g_failures ? "%d check(s) FAILED\n" : "all checks passed\n", g_failures);
+  return g_failures ? 1 : 0;
+}

@@ -45,12 +45,10 @@ def main():
 
     def step():
         ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
-        up = ctx.timings()
         r = ctx.plan(prm)
-        pl = ctx.timings()
         n = (r.n_paths, r.n_segments, r.n_waypoints)
         r.free()
-        return up, pl, n
+        return ctx.timings(), n
 
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
     for _ in range(2):
@@ -58,12 +56,15 @@ def main():
     flush.zero_()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    up, pl, n = step()
+    ctx.timer_start()
+    st, n = step()
+    total = ctx.timer_stop()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print(name, desc)
     print("paths/segments/waypoints", n)
-    print("stages ms", {**up, **pl})
+    print("stages ms", {k: round(v, 4) for k, v in st.items()})
+    print("step ms (events) %.4f, sum of stages %.4f" % (total, sum(st.values())))
     ctx.close()
 
 
