@@ -260,30 +260,64 @@ void requireMesh(const nb2_context* c)
     fail(NB2_ERR_NO_MESH, "no mesh has been uploaded to this context");
 }
 
-void ensurePca(nb2_context* c)
+const char* kNoNormalsMessage =
+    "The input mesh does not have vertex normals, which are required for the plane slice raster tool path planner. Use a "
+    "MeshModifier to generate vertex normals for the mesh, or provide a different mesh with vertex normals.";
+
+/** k_extents once per resident mesh (the eigen axes were finalised on the device right after the ingest pass) */
+void ensureExtents(nb2_context* c)
+{
+  if (c->frame_pca_done || c->V < 3)
+    return;
+  launchExtents(c);
+  c->timer.mark("extents", c->stream);
+  c->frame_pca_done = true;
+}
+
+/** Checks that were postponed because the mesh was adopted from device memory without a synchronisation */
+void deferredMeshChecks(nb2_context* c, const FrameDev& f)
+{
+  if (!c->checks_deferred)
+    return;
+  c->checks_deferred = false;
+  if (f.non_finite)
+  {
+    c->V = 0;
+    fail(NB2_ERR_NON_FINITE, std::to_string(f.non_finite) + " vertices have non-finite coordinates");
+  }
+}
+
+float fromOrderedBits(unsigned u)
+{
+  const unsigned v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  float f;
+  std::memcpy(&f, &v, 4);
+  return f;
+}
+
+/** Host copy of the PCA frame (mean, axes, OBB extents): one read-back of the device frame state */
+void ensureHostPca(nb2_context* c)
 {
   requireMesh(c);
-  if (c->V < 3)
-    fail(NB2_ERR_TOO_FEW_POINTS, "[pcl::PCA::initCompute] number of points < 3");
   if (c->pca_valid)
     return;
-  // extents of the cloud in the PCA frame (second, smaller pass)
-  launchExtents(c, c->pca.mean, c->pca.evecs);
-  c->timer.mark("extents", c->stream);
-  c->hostSmall.ensure(4096);
-  unsigned* hb = c->hostSmall.as<unsigned>();
-  NB2_CUDA(cudaMemcpyAsync(hb, c->extents.ptr, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  ensureExtents(c);
+  c->hostSmall.ensure(4096 + sizeof(FrameDev));
+  auto* hf = c->hostSmall.as<FrameDev>();
+  NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
-  float h[6];
-  for (int i = 0; i < 6; ++i)
-  {
-    // inverse of the kernel's order-preserving float -> unsigned map
-    const unsigned u = (hb[i] & 0x80000000u) ? (hb[i] & 0x7fffffffu) : ~hb[i];
-    std::memcpy(&h[i], &u, 4);
-  }
-  for (int i = 0; i < 3; ++i)
-    c->pca.scales[i] = h[3 + i] - h[i];
+  deferredMeshChecks(c, *hf);
+  c->pca = hf->pca;
+  if (!hf->have_scales && c->V >= 3)
+    for (int i = 0; i < 3; ++i)
+      c->pca.scales[i] = fromOrderedBits(hf->ext[3 + i]) - fromOrderedBits(hf->ext[i]);
   c->pca_valid = true;
+}
+
+void requirePcaPoints(const nb2_context* c)
+{
+  if (c->V < 3)
+    fail(NB2_ERR_TOO_FEW_POINTS, "[pcl::PCA::initCompute] number of points < 3");
 }
 
 nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
@@ -293,56 +327,80 @@ nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
   return r;
 }
 
-/** planImpl's plane loop on the device */
-nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, bool emit_edges,
-                      bool download = true)
+/**
+ * planImpl's plane loop on the device.  The lattice comes either from the device-side construction (`fp`: PCA axes,
+ * generators and lattice arithmetic run as single-thread kernels, no host round trip) or from the caller
+ * (`explicit_lat`, nb2_slice).  One synchronisation mid-way — the hit count sizes the buckets — and one at the end.
+ */
+nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* explicit_lat, uint64_t plane_begin,
+                      uint64_t plane_end, bool emit_edges, bool download = true)
 {
   requireMesh(c);
   if (!c->has_normals)
-    fail(NB2_ERR_NO_NORMALS, "The input mesh does not have vertex normals, which are required for the plane slice raster "
-                             "tool path planner. Use a MeshModifier to generate vertex normals for the mesh, or provide a "
-                             "different mesh with vertex normals.");
-  plane_end = std::min<uint64_t>(plane_end, lat.num_planes);
-  if (plane_begin >= plane_end || c->F == 0)
-    return emptyResult(c, lat);
-  const uint64_t nP = plane_end - plane_begin;
+    fail(NB2_ERR_NO_NORMALS, kNoNormalsMessage);
+  if (fp)
+    ensureExtents(c);
 
-  LatticeDev L{};
-  for (int i = 0; i < 3; ++i)
+  c->hostSmall.ensure(8192 + sizeof(FrameDev));
+  auto* hf = c->hostSmall.as<FrameDev>();
+  unsigned* h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
+  for (int attempt = 0;; ++attempt)
   {
-    L.n[i] = lat.cut_normal[i];
-    L.start[i] = lat.start_loc[i];
-    L.dir[i] = lat.cut_direction[i];
+    // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
+    //           [12] largest out-of-range vertex index
+    unsigned init[16] = { 0 };
+    init[11] = 0xffffffffu;
+    NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + 4, init + 4, 12 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    if (fp)
+    {
+      FrameParams p = *fp;
+      p.plane_cap = c->plane_cap;
+      launchFrameLattice(c, p);
+    }
+    else
+      launchFrameSet(c, *explicit_lat, plane_begin, plane_end, c->plane_cap);
+    c->timer.mark("lattice", c->stream);
+    launchClassify(c);
+    c->timer.mark("classify", c->stream);
+    launchCountHits(c);
+    c->timer.mark("count", c->stream);
+    launchScanPlanes(c);
+    c->timer.mark("scan", c->stream);
+
+    NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 9 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+    deferredMeshChecks(c, *hf);
+    if (hf->lattice_status != 0)
+      fail(NB2_ERR_INVALID_ARGUMENT, latticeErrorMessage(hf->lattice_status));
+    if (!hf->plane_cap_exceeded)
+      break;
+    if (attempt > 0 || hf->planes_wanted >= (1ull << 31))
+      fail(NB2_ERR_INTERNAL, "could not size the per-plane arrays");
+    unsigned cap = c->plane_cap;
+    while (cap < hf->planes_wanted)
+      cap *= 2;
+    c->plane_cap = cap;  // grow and run the three kernels again
   }
-  L.spacing = lat.line_spacing;
-  L.num_planes = static_cast<long long>(lat.num_planes);
-  L.plane_begin = static_cast<long long>(plane_begin);
-  L.plane_end = static_cast<long long>(plane_end);
+  if (hf->have_scales)
+  {
+    c->pca = hf->pca;
+    c->pca_valid = true;
+  }
+  const nb2_lattice lat = hf->lat;
+  const LatticeDev L = hf->L;
+  c->last_lattice = lat;
+  c->have_lattice = true;
+  const uint64_t nP = static_cast<uint64_t>(L.plane_end - L.plane_begin);
+  plane_begin = static_cast<uint64_t>(L.plane_begin);
 
-  // counters: [0] moments ticket, [1] extents ticket, [4] H, [5] n_max, [8] link ticket, [10] status, [11] failing plane
-  unsigned init[16] = { 0 };
-  init[11] = 0xffffffffu;
-  NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + 4, init + 4, 12 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
-
-  c->timer.mark("setup", c->stream);
-  launchClassify(c, L);
-  c->timer.mark("classify", c->stream);
-  launchCountHits(c, L);
-  c->timer.mark("count", c->stream);
-  launchScanPlanes(c, L);
-  c->timer.mark("scan", c->stream);
-
-  c->hostSmall.ensure(4096);
-  unsigned* h = c->hostSmall.as<unsigned>();
-  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 9 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  NB2_CUDA(cudaStreamSynchronize(c->stream));
   const uint64_t H = h[0];
   const uint32_t n_max = h[1];
-  if (h[8] >= c->V)  // counters[12]: largest out-of-range vertex index met by k_count_hits
+  if (c->F && h[8] >= c->V)  // counters[12]: largest out-of-range vertex index met by k_count_hits
     fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[8]) + " but the cloud has " +
                                        std::to_string(c->V) + " points");
   c->tri_checked = true;
-  if (H == 0)
+  if (nP == 0 || H == 0)
     return emptyResult(c, lat);
   if (H >= (1ull << 30))
     fail(NB2_ERR_INVALID_ARGUMENT, "more than 2^30 triangle/plane intersections in one slab; shard the plan");
@@ -365,13 +423,12 @@ nb2_result* sliceImpl(nb2_context* c, const nb2_lattice& lat, uint64_t plane_beg
   c->timer.mark("waypoints", c->stream);
 
   // totals, per-plane meta and status
-  c->hostSmall.ensure(64 + sizeof(unsigned) * 2 * nP);
-  h = c->hostSmall.as<unsigned>();
-  auto* h64 = reinterpret_cast<unsigned long long*>(h);
+  c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * nP);
+  h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
   unsigned* hstat = h + 2;
   unsigned* hmeta = h + 16;
   // counters[6..7] = waypoint / segment totals (k_scan_meta), counters[10..11] = link status
-  NB2_CUDA(cudaMemcpyAsync(h64, c->counters.as<unsigned>() + 6, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 6, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(hstat, c->counters.as<unsigned>() + 10, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
@@ -519,7 +576,7 @@ void nb2_context_destroy(nb2_context* c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
-  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->counters, &c->vertK, &c->planeCnt,
+  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->scanState })
@@ -558,6 +615,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
 
   c->V = 0;
   c->pca_valid = false;
+  c->frame_pca_done = false;
   const uint64_t V = m->n_points, F = m->n_triangles;
   c->timer_upload.begin(c->stream);
   // Inputs that already live in this GPU's memory are used in place (no copy; the caller keeps them alive until the
@@ -610,16 +668,27 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     c->timer_upload.mark("validate", c->stream);
   }
 
-  c->hostSmall.ensure(4096);
+  // mean, covariance and eigen axes are finalised on the device, straight from the reduction's total
+  launchFramePca(c, reinterpret_cast<const float*>(c->blob.as<uint8_t>() + m->offset_xyz));
+  c->timer_upload.mark("frame", c->stream);
+  c->frame_pca_done = false;
+  c->pca_valid = false;
+  std::memset(&c->pca, 0, sizeof(c->pca));
+  if (tri_adopted || onThisDevice(m->cloud_data))
+  {
+    // device-resident input: nothing is read back here; non-finite coordinates and out-of-range indices are reported
+    // by the next call that synchronises (nb2_plan, nb2_mesh_pca, nb2_normals_from_mesh_faces, ...)
+    c->checks_deferred = true;
+    c->tri_checked = false;
+    return NB2_OK;
+  }
+  c->checks_deferred = false;
+  c->hostSmall.ensure(4096 + sizeof(FrameDev));
   auto* h = c->hostSmall.as<uint8_t>();
   const int grid = static_cast<int>(std::min<uint64_t>((V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
   NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  // pivot = first vertex
-  NB2_CUDA(cudaMemcpyAsync(h + 1024, c->blob.as<uint8_t>() + m->offset_xyz, 12, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
-  float pivot[3];
-  std::memcpy(pivot, h + 1024, 12);
   MomentPartial total;
   std::memcpy(&total, h, sizeof(total));
   unsigned max_index;
@@ -635,19 +704,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(max_index) + " but the cloud has " +
                                        std::to_string(V) + " points");
   }
-  c->tri_checked = !tri_adopted;
-  std::memset(&c->pca, 0, sizeof(c->pca));
-  if (V >= 3)
-    finalizeMoments(total, V, pivot, c->pca);
-  else
-  {
-    const double n = static_cast<double>(V);
-    for (int i = 0; i < 3; ++i)
-    {
-      c->pca.mean64[i] = pivot[i] + total.s[i] / n;
-      c->pca.mean[i] = static_cast<float>(c->pca.mean64[i]);
-    }
-  }
+  c->tri_checked = true;
   NB2_API_END
 }
 
@@ -693,7 +750,9 @@ int nb2_mesh_pca(nb2_context* c, nb2_pca* out)
     fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard g(c->device);
-  ensurePca(c);
+  requireMesh(c);
+  requirePcaPoints(c);
+  ensureHostPca(c);
   *out = c->pca;
   NB2_API_END
 }
@@ -706,8 +765,8 @@ int nb2_principal_axis_direction(nb2_context* c, double rotation_offset, double 
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard g(c->device);
   requireMesh(c);
-  if (c->V < 3)
-    fail(NB2_ERR_TOO_FEW_POINTS, "[pcl::PCA::initCompute] number of points < 3");
+  requirePcaPoints(c);
+  ensureHostPca(c);
   principalAxisDirection(c->pca, rotation_offset, out);
   NB2_API_END
 }
@@ -718,7 +777,8 @@ int nb2_centroid_origin(nb2_context* c, double out[3])
   if (!c || !out)
     fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
   std::lock_guard<std::mutex> lock(c->mu);
-  requireMesh(c);
+  DeviceGuard g(c->device);
+  ensureHostPca(c);
   for (int i = 0; i < 3; ++i)
     out[i] = static_cast<double>(c->pca.mean[i]);
   NB2_API_END
@@ -802,7 +862,7 @@ int nb2_slice(nb2_context* c, const nb2_lattice* lat, uint64_t plane_begin, uint
   if (!(lat->line_spacing > 0.0))
     fail(NB2_ERR_INVALID_ARGUMENT, "line_spacing must be a positive finite number");
   c->timer.begin(c->stream);
-  *out = sliceImpl(c, *lat, plane_begin, plane_end, true);
+  *out = sliceImpl(c, nullptr, lat, plane_begin, plane_end, true);
   NB2_API_END
 }
 
@@ -816,39 +876,29 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   DeviceGuard g(c->device);
   requireMesh(c);
   if (!c->has_normals)
-    fail(NB2_ERR_NO_NORMALS, "The input mesh does not have vertex normals, which are required for the plane slice raster "
-                             "tool path planner. Use a MeshModifier to generate vertex normals for the mesh, or provide a "
-                             "different mesh with vertex normals.");
+    fail(NB2_ERR_NO_NORMALS, kNoNormalsMessage);
+  requirePcaPoints(c);
+  if (!(prm->line_spacing > 0.0) || !std::isfinite(prm->line_spacing))
+    fail(NB2_ERR_INVALID_ARGUMENT, "line_spacing must be a positive finite number");
+  if (prm->shard_count > 1 && (prm->shard_rank < 0 || prm->shard_rank >= prm->shard_count))
+    fail(NB2_ERR_INVALID_ARGUMENT, "shard_rank out of range");
   c->timer.begin(c->stream);
-  ensurePca(c);
-  double dir[3], origin[3];
-  if (prm->direction_mode == NB2_DIRECTION_PRINCIPAL_AXIS)
-    principalAxisDirection(c->pca, prm->rotation_offset, dir);
-  else
-    std::copy(prm->direction, prm->direction + 3, dir);
-  if (prm->origin_mode == NB2_ORIGIN_CENTROID)
-    for (int i = 0; i < 3; ++i)
-      origin[i] = static_cast<double>(c->pca.mean[i]);
-  else
-    std::copy(prm->origin, prm->origin + 3, origin);
-
-  nb2_lattice lat{};
-  const int rc = makeLattice(c->pca, dir, origin, prm->line_spacing, prm->bidirectional, lat);
-  if (rc != NB2_OK)
-    return rc;
-  c->last_lattice = lat;
-  c->have_lattice = true;
-
-  uint64_t kb = 0, ke = lat.num_planes;
-  if (prm->shard_count > 1)
+  FrameParams fp{};
+  fp.line_spacing = prm->line_spacing;
+  fp.bidirectional = prm->bidirectional;
+  fp.direction_mode = prm->direction_mode;
+  fp.origin_mode = prm->origin_mode;
+  for (int i = 0; i < 3; ++i)
   {
-    if (prm->shard_rank < 0 || prm->shard_rank >= prm->shard_count)
-      fail(NB2_ERR_INVALID_ARGUMENT, "shard_rank out of range");
-    kb = lat.num_planes * static_cast<uint64_t>(prm->shard_rank) / prm->shard_count;
-    ke = lat.num_planes * (static_cast<uint64_t>(prm->shard_rank) + 1) / prm->shard_count;
+    fp.direction[i] = prm->direction[i];
+    fp.origin[i] = prm->origin[i];
   }
+  fp.sin_rotation = std::sin(prm->rotation_offset);
+  fp.cos_rotation = std::cos(prm->rotation_offset);
+  fp.shard_rank = prm->shard_rank;
+  fp.shard_count = prm->shard_count > 1 ? prm->shard_count : 1;
   const bool download = prm->download != 0;
-  nb2_result* r = sliceImpl(c, lat, kb, ke, prm->emit_edges != 0 || prm->legacy != 0, download);
+  nb2_result* r = sliceImpl(c, &fp, nullptr, 0, NB2_ALL_PLANES, prm->emit_edges != 0 || prm->legacy != 0, download);
   r->params = *prm;
   try
   {

@@ -208,10 +208,15 @@ __device__ __forceinline__ unsigned orderedBits(float f)
 /** Float extents in the PCA frame: proj_c = e_c . (x - mean) with Eigen's 3-term order a0 + (a1 + a2); min/max are
  *  order independent so any reduction tree reproduces pcl::getMinMax3D exactly. */
 __global__ void __launch_bounds__(256)
-    k_extents(const float4* __restrict__ pos, unsigned long long V, float mx_, float my_, float mz_, float e00, float e01,
-              float e02, float e10, float e11, float e12, float e20, float e21, float e22, unsigned* __restrict__ out6)
+    k_extents(const float4* __restrict__ pos, unsigned long long V, FrameDev* __restrict__ frame)
 {
   __shared__ float s_mn[3][8], s_mx[3][8];
+  // mean and axes as k_frame_pca left them (E column-major: axis c = (E[3c], E[3c+1], E[3c+2]))
+  const float mx_ = frame->pca.mean[0], my_ = frame->pca.mean[1], mz_ = frame->pca.mean[2];
+  const float e00 = frame->pca.evecs[0], e01 = frame->pca.evecs[1], e02 = frame->pca.evecs[2];
+  const float e10 = frame->pca.evecs[3], e11 = frame->pca.evecs[4], e12 = frame->pca.evecs[5];
+  const float e20 = frame->pca.evecs[6], e21 = frame->pca.evecs[7], e22 = frame->pca.evecs[8];
+  unsigned* const out6 = frame->ext;
   float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   auto project = [&](const float4 p) {
@@ -274,11 +279,17 @@ __global__ void __launch_bounds__(256)
  * monotone), so "inside" is a prefix of the planes and one integer per vertex encodes the whole per-plane sweep of
  * vtkCutter.  A triangle is cut by plane k  <=>  min K < k <= max K over its vertices, with case bit i = (k <= K_i).
  */
-__global__ void __launch_bounds__(256) k_classify(const float4* __restrict__ pos, unsigned long long V, LatticeDev L,
-                                                  int* __restrict__ vertK)
+__global__ void __launch_bounds__(256) k_classify(const float4* __restrict__ pos, unsigned long long V,
+                                                  const FrameDev* __restrict__ frame, int* __restrict__ vertK,
+                                                  unsigned* __restrict__ planeCnt)
 {
+  const LatticeDev L = frame->L;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   const long long P = L.num_planes;
+  // zero the per-plane hit counters of this slab for k_count_hits
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i <= L.plane_end - L.plane_begin;
+       i += static_cast<long long>(stride))
+    planeCnt[i] = 0u;
   const double inv_spacing = 1.0 / L.spacing;
   for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
   {
@@ -340,25 +351,21 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
   ++c->launches;
 }
 
-void launchExtents(nb2_context* c, const float mean[3], const float E[9])
+void launchExtents(nb2_context* c)
 {
   const int grid = gridFor(c->V, 256, c->sm_count * 8);
-  c->extents.ensure(sizeof(unsigned) * 8);
-  // slots 0..2 = ordered bits of the minima (start at the largest pattern), 3..5 = of the maxima (start at 0)
-  NB2_CUDA(cudaMemsetAsync(c->extents.ptr, 0xff, 3 * sizeof(unsigned), c->stream));
-  NB2_CUDA(cudaMemsetAsync(c->extents.as<unsigned>() + 3, 0, 3 * sizeof(unsigned), c->stream));
-  // E is column-major: axis c = (E[3c], E[3c+1], E[3c+2])
-  k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, mean[0], mean[1], mean[2], E[0], E[1], E[2], E[3],
-                                         E[4], E[5], E[6], E[7], E[8], c->extents.as<unsigned>());
+  k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, c->frame.as<FrameDev>());
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchClassify(nb2_context* c, const LatticeDev& L)
+void launchClassify(nb2_context* c)
 {
   c->vertK.ensure(sizeof(int) * c->V);
+  c->planeCnt.ensure(sizeof(unsigned) * (static_cast<size_t>(c->plane_cap) + 1));
   const int grid = gridFor(c->V, 256, c->sm_count * 16);
-  k_classify<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, L, c->vertK.as<int>());
+  k_classify<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, c->frame.as<FrameDev>(), c->vertK.as<int>(),
+                                          c->planeCnt.as<unsigned>());
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -62,11 +62,15 @@ __device__ __forceinline__ void planeSpan(int ka, int kb, int kc, const LatticeD
 
 __global__ void __launch_bounds__(kCountThreads)
     k_count_hits(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
-                 const int* __restrict__ vertK, LatticeDev L, unsigned* __restrict__ planeCnt, int use_smem, int aligned,
-                 unsigned* __restrict__ maxIndex)
+                 const int* __restrict__ vertK, const FrameDev* __restrict__ frame, unsigned* __restrict__ planeCnt,
+                 int aligned, unsigned* __restrict__ maxIndex)
 {
   __shared__ unsigned s_bins[kSmemBins];
+  const LatticeDev L = frame->L;
   const long long nP = L.plane_end - L.plane_begin;
+  if (nP <= 0)
+    return;
+  const bool use_smem = nP <= kSmemBins;
   if (use_smem)
   {
     for (int i = threadIdx.x; i < nP; i += blockDim.x)
@@ -123,9 +127,10 @@ __global__ void __launch_bounds__(kCountThreads)
 
 /** Single-block exclusive scan of the per-plane counters.  out[0] = total hits, out[1] = largest plane. */
 __global__ void __launch_bounds__(1024)
-    k_scan_planes(const unsigned* __restrict__ cnt, long long nP, unsigned* __restrict__ off, unsigned* __restrict__ cursor,
-                  unsigned* __restrict__ out2)
+    k_scan_planes(const unsigned* __restrict__ cnt, const FrameDev* __restrict__ frame, unsigned* __restrict__ off,
+                  unsigned* __restrict__ cursor, unsigned* __restrict__ out2)
 {
+  const long long nP = frame->L.plane_end - frame->L.plane_begin;
   __shared__ unsigned s_warp[32];
   __shared__ unsigned s_carry;
   __shared__ unsigned s_max[32];
@@ -1074,26 +1079,23 @@ size_t globalWorkBytes(unsigned hits)
 }
 }  // namespace
 
-void launchCountHits(nb2_context* c, const LatticeDev& L)
+void launchCountHits(nb2_context* c)
 {
-  const long long nP = L.plane_end - L.plane_begin;
-  c->planeCnt.ensure(sizeof(unsigned) * (nP + 1));
-  NB2_CUDA(cudaMemsetAsync(c->planeCnt.ptr, 0, sizeof(unsigned) * (nP + 1), c->stream));
   const int grid = gridFor((c->F + 3) / 4, kCountThreads, c->sm_count * 8);
   const int aligned = (reinterpret_cast<uintptr_t>(c->tri.ptr) & 15u) == 0 ? 1 : 0;
-  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(), L,
-                                                      c->planeCnt.as<unsigned>(), nP <= kSmemBins ? 1 : 0, aligned,
+  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
+                                                      c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
                                                       c->counters.as<unsigned>() + 12);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchScanPlanes(nb2_context* c, const LatticeDev& L)
+void launchScanPlanes(nb2_context* c)
 {
-  const long long nP = L.plane_end - L.plane_begin;
-  c->planeOff.ensure(sizeof(unsigned) * (nP + 1));
-  c->planeCursor.ensure(sizeof(unsigned) * (nP + 1));
-  k_scan_planes<<<1, 1024, 0, c->stream>>>(c->planeCnt.as<unsigned>(), nP, c->planeOff.as<unsigned>(),
+  const size_t n = static_cast<size_t>(c->plane_cap) + 1;
+  c->planeOff.ensure(sizeof(unsigned) * n);
+  c->planeCursor.ensure(sizeof(unsigned) * n);
+  k_scan_planes<<<1, 1024, 0, c->stream>>>(c->planeCnt.as<unsigned>(), c->frame.as<FrameDev>(), c->planeOff.as<unsigned>(),
                                            c->planeCursor.as<unsigned>(), c->counters.as<unsigned>() + 4);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;

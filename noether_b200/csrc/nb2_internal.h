@@ -91,6 +91,34 @@ struct LatticeDev
   long long plane_end;
 };
 
+/** Inputs of the device-side lattice construction (k_frame_lattice) */
+struct FrameParams
+{
+  double line_spacing;
+  double direction[3];
+  double origin[3];
+  double sin_rotation, cos_rotation;  // of PrincipalAxis' rotation_offset, evaluated by the host libm
+  int bidirectional;
+  int direction_mode, origin_mode;
+  int shard_rank, shard_count;
+  unsigned plane_cap;  // planes the per-plane arrays are sized for
+};
+
+/** Frame state kept in device memory between the kernels of a plan; read back once, with the hit count */
+struct FrameDev
+{
+  nb2_pca pca;
+  nb2_lattice lat;
+  LatticeDev L;
+  unsigned ext[6];  // ordered bits of the min / max of the cloud in the PCA frame (k_extents)
+  int have_scales;
+  int lattice_status;  // frame::kLattice*
+  int plane_cap_exceeded;
+  int pad_;
+  unsigned long long planes_wanted;
+  unsigned long long non_finite;
+};
+
 constexpr int kMomentBlocks = 1184;  // fixed (not SM-count derived) so that sums are identical on any device
 constexpr int kMomentThreads = 256;
 
@@ -132,8 +160,12 @@ struct nb2_context
   nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
   nb2::DevBuf extents;   // float[6] min/max in PCA frame (+ block partials)
   nb2::DevBuf counters;  // misc device counters (zeroed per plan)
-  bool pca_valid = false;
+  nb2::DevBuf frame;     // FrameDev
+  bool frame_pca_done = false;  // k_frame_pca + k_extents have run for the resident mesh
+  bool checks_deferred = false; // mesh adopted from device memory: non-finite / index checks happen at the next sync
+  bool pca_valid = false;       // host copy below is current
   nb2_pca pca{};
+  unsigned plane_cap = 1u << 16;
   // slicing workspace
   nb2::DevBuf vertK;       // int32[V]
   nb2::DevBuf planeCnt;    // uint32[P + 1]
@@ -205,10 +237,14 @@ struct nb2_result
 namespace nb2
 {
 void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, int32_t off_nrm);
-void launchExtents(nb2_context* c, const float mean[3], const float evecs[9]);
-void launchClassify(nb2_context* c, const LatticeDev& L);
-void launchCountHits(nb2_context* c, const LatticeDev& L);
-void launchScanPlanes(nb2_context* c, const LatticeDev& L);  // writes {H, n_max} to counters[0..1]
+void launchFramePca(nb2_context* c, const float* pivot_dev);
+void launchFrameLattice(nb2_context* c, const FrameParams& prm);
+void launchFrameSet(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, unsigned plane_cap);
+void launchExtents(nb2_context* c);
+// the three kernels before the plan's only mid-way synchronisation read the lattice from device memory (FrameDev::L)
+void launchClassify(nb2_context* c);
+void launchCountHits(nb2_context* c);
+void launchScanPlanes(nb2_context* c);  // writes {H, n_max} to counters[4..5]
 void launchEmitHits(nb2_context* c, const LatticeDev& L);
 void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H);
 void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges);
@@ -218,7 +254,7 @@ void launchVertexNormals(nb2_context* c);
 void launchValidateTriangles(nb2_context* c);
 
 // host-side frame arithmetic (frame.cpp)
-void finalizeMoments(const MomentPartial& total, uint64_t V, const float pivot[3], nb2_pca& out);
+const char* latticeErrorMessage(int code);
 void eigenSolver3f(const float A[9], float evals[3], float evecs[9]);
 void principalAxisDirection(const nb2_pca& pca, double rotation_offset, double out[3]);
 int makeLattice(const nb2_pca& pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
