@@ -163,6 +163,15 @@ def main():
     ap.add_argument("--cpu-planes", type=int, default=24, help="lattice planes sampled by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
 
     from noether_b200.dist import RankInfo
     info = RankInfo.from_env()
@@ -203,7 +212,7 @@ def main():
             "e2e": {"value": value, "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     # -----------------------------------------------------------------------------------------------------------------
@@ -277,7 +286,8 @@ def main():
         if info.world > 1:
             out = ctx.gather(local, 0)
             n = (out.n_paths, out.n_segments, out.n_waypoints) if out is not None else (0, 0, 0)
-            d2h = local.n_waypoints * 24 + local.n_segments * 4
+            # the slabs travel GPU to GPU; only the root copies tool paths to the host (all of them)
+            d2h = (out.n_waypoints * 24 + out.n_segments * 4) if out is not None else 0
             local.free()
             if out is not None:
                 out.free()
@@ -391,7 +401,7 @@ def main():
         "cpu_baseline": cpu,
         "normals_from_mesh_faces_ms": normals_ms,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -229,8 +229,11 @@ int nb2_timer_stop(nb2_context* ctx, float* ms);
 #define NB2_UNIQUE_ID_BYTES 128
 int nb2_comm_unique_id(uint8_t out[NB2_UNIQUE_ID_BYTES]);
 int nb2_comm_init(nb2_context* ctx, const uint8_t unique_id[NB2_UNIQUE_ID_BYTES], int rank, int world_size);
-/* Collective: every rank passes its slab result; on `root` *gathered receives the concatenation in rank (= plane)
- * order, on other ranks NULL.  Post-ops, when requested in the original params, are applied to the gathered result. */
+/* Collective: every rank passes the result of its sharded nb2_plan (shard_count > 1; such a result keeps its tool paths
+ * in the GPU's output buffers, valid until the next plan on that context).  The slabs travel GPU to GPU (grouped
+ * ncclSend / ncclRecv of the SoA arrays); on `root` *gathered receives the concatenation in rank (= plane) order, on
+ * other ranks NULL.  Legacy modifiers and raster post-ops, when requested in the params, are applied to the gathered
+ * result. */
 int nb2_result_gather(nb2_context* ctx, const nb2_result* local, int root, nb2_result** gathered);
 int nb2_comm_destroy(nb2_context* ctx);
 

@@ -401,7 +401,17 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
                                        std::to_string(c->V) + " points");
   c->tri_checked = true;
   if (nP == 0 || H == 0)
-    return emptyResult(c, lat);
+  {
+    nb2_result* r = emptyResult(c, lat);
+    if (!download)
+    {
+      r->device_resident = true;
+      r->dev_edges = emit_edges;
+      r->slab_begin = plane_begin;
+      r->slab_planes = 0;
+    }
+    return r;
+  }
   if (H >= (1ull << 30))
     fail(NB2_ERR_INVALID_ARGUMENT, "more than 2^30 triangle/plane intersections in one slab; shard the plan");
   if (n_max >= (1u << 19))
@@ -459,6 +469,11 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     r->path_offsets = r->segment_offsets = nullptr;
     r->path_plane = nullptr;
     r->positions = r->normals = nullptr;
+    r->device_resident = true;
+    r->dev_w_cap = w_cap;
+    r->dev_edges = emit_edges;
+    r->slab_begin = plane_begin;
+    r->slab_planes = nP;
     return r;
   }
   nb2_result* r = allocResult(c, Pn, St, Wt, emit_edges, false);
@@ -897,7 +912,8 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   fp.cos_rotation = std::cos(prm->rotation_offset);
   fp.shard_rank = prm->shard_rank;
   fp.shard_count = prm->shard_count > 1 ? prm->shard_count : 1;
-  const bool download = prm->download != 0;
+  // a slab of a sharded plan stays in HBM: nb2_result_gather sends it to the root GPU-to-GPU
+  const bool download = prm->download != 0 && prm->shard_count <= 1;
   nb2_result* r = sliceImpl(c, &fp, nullptr, 0, NB2_ALL_PLANES, prm->emit_edges != 0 || prm->legacy != 0, download);
   r->params = *prm;
   try
@@ -962,6 +978,9 @@ int nb2_result_poses(const nb2_result* r, double* out16)
   NB2_API_BEGIN
   if (!r || (!out16 && r->n_waypoints))
     fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (r->n_waypoints && !r->positions)
+    fail(NB2_ERR_INVALID_ARGUMENT, "the tool paths of this result were left on the device (download = 0 or a slab of a "
+                                   "sharded plan): gather or re-plan with download = 1");
   expandPoses(*r, out16);
   NB2_API_END
 }

@@ -83,7 +83,7 @@ void check(ncclResult_t r, const char* what)
 
 struct SlabHeader
 {
-  unsigned long long paths, segments, waypoints, edges;
+  unsigned long long paths, segments, waypoints, edges, planes, plane_begin;
 };
 }  // namespace
 
@@ -162,6 +162,9 @@ int nb2_result_gather(nb2_context* c, const nb2_result* local, int root, nb2_res
     *gathered = nullptr;
     if (!c->nccl_comm)
       fail(NB2_ERR_NCCL, "nb2_comm_init has not been called on this context");
+    if (!local->device_resident || local->owner != c)
+      fail(NB2_ERR_INVALID_ARGUMENT, "nb2_result_gather takes the slab result of a sharded nb2_plan (shard_count > 1) on "
+                                     "this context");
     std::lock_guard<std::mutex> lock(c->mu);
     NB2_CUDA(cudaSetDevice(c->device));
     auto comm = static_cast<ncclComm_t>(c->nccl_comm);
@@ -174,145 +177,167 @@ int nb2_result_gather(nb2_context* c, const nb2_result* local, int root, nb2_res
     // 1. everybody learns every slab's sizes
     c->hostSmall.ensure(4096 + sizeof(SlabHeader) * (world + 1));
     auto* hh = reinterpret_cast<SlabHeader*>(c->hostSmall.as<uint8_t>() + 4096);
-    hh[world] = { local->n_paths, local->n_segments, local->n_waypoints, local->edge_lo ? 1ull : 0ull };
+    hh[world] = { local->n_paths, local->n_segments, local->n_waypoints, local->dev_edges ? 1ull : 0ull,
+                  local->slab_planes, local->slab_begin };
     c->scanState.ensure(sizeof(SlabHeader) * (world + 1));
     auto* dh = c->scanState.as<SlabHeader>();
     NB2_CUDA(cudaMemcpyAsync(dh + world, hh + world, sizeof(SlabHeader), cudaMemcpyHostToDevice, st));
     check(N.AllGather(dh + world, dh, sizeof(SlabHeader), ncclUint8, comm, st), "ncclAllGather(sizes)");
     NB2_CUDA(cudaMemcpyAsync(hh, dh, sizeof(SlabHeader) * world, cudaMemcpyDeviceToHost, st));
     NB2_CUDA(cudaStreamSynchronize(st));
+    const std::vector<SlabHeader> hv(hh, hh + world);  // the pinned staging area is reused below
+    hh = nullptr;
 
-    uint64_t P = 0, S = 0, W = 0;
+    uint64_t P = 0, S = 0, W = 0, K = 0;
     bool edges = true;
     for (int r = 0; r < world; ++r)
     {
-      P += hh[r].paths;
-      S += hh[r].segments;
-      W += hh[r].waypoints;
-      edges = edges && hh[r].edges;
+      P += hv[r].paths;
+      S += hv[r].segments;
+      W += hv[r].waypoints;
+      K += hv[r].planes;
+      edges = edges && hv[r].edges;
     }
 
-    // 2. stage this slab on the device: positions | normals | edge_lo | edge_hi | segment lengths | path plane | path segs
-    //    (float / uint32 words; path planes as two words each)
-    auto words = [&](const SlabHeader& h) {
-      return 6 * h.waypoints + (edges ? 2 * h.waypoints : 0) + h.segments + 3 * h.paths;
-    };
-    const uint64_t my_words = words(hh[rank]);
-    std::vector<uint32_t> pack(my_words ? my_words : 1);
-    {
-      uint32_t* p = pack.data();
-      std::memcpy(p, local->positions, 12 * local->n_waypoints);
-      p += 3 * local->n_waypoints;
-      std::memcpy(p, local->normals, 12 * local->n_waypoints);
-      p += 3 * local->n_waypoints;
-      if (edges)
-      {
-        std::memcpy(p, local->edge_lo, 4 * local->n_waypoints);
-        p += local->n_waypoints;
-        std::memcpy(p, local->edge_hi, 4 * local->n_waypoints);
-        p += local->n_waypoints;
-      }
-      for (uint64_t s = 0; s < local->n_segments; ++s)
-        *p++ = local->segment_offsets[s + 1] - local->segment_offsets[s];
-      for (uint64_t q = 0; q < local->n_paths; ++q)
-      {
-        const uint64_t plane = static_cast<uint64_t>(local->path_plane[q]);
-        *p++ = static_cast<uint32_t>(plane & 0xffffffffull);
-        *p++ = static_cast<uint32_t>(plane >> 32);
-        *p++ = local->path_offsets[q + 1] - local->path_offsets[q];
-      }
-    }
-    uint64_t total_words = 0;
-    std::vector<uint64_t> word_off(world + 1, 0);
-    for (int r = 0; r < world; ++r)
-    {
-      word_off[r] = total_words;
-      total_words += words(hh[r]);
-    }
-    word_off[world] = total_words;
-
-    // the per-rank send buffer lives in linkScratch (free between plans); the root's receive area follows it
-    const size_t send_bytes = sizeof(uint32_t) * (my_words + 1);
-    const size_t recv_bytes = rank == root ? sizeof(uint32_t) * (total_words + 1) : 0;
-    c->linkScratch.ensure(((send_bytes + 255) & ~size_t(255)) + recv_bytes);
-    auto* d_send = c->linkScratch.as<uint32_t>();
-    auto* d_recv = reinterpret_cast<uint32_t*>(c->linkScratch.as<uint8_t>() + ((send_bytes + 255) & ~size_t(255)));
-    if (my_words)
-      NB2_CUDA(cudaMemcpyAsync(d_send, pack.data(), sizeof(uint32_t) * my_words, cudaMemcpyHostToDevice, st));
-
-    // 3. grouped point-to-point gather (NCCL has no gatherv)
-    check(N.GroupStart(), "ncclGroupStart");
-    if (rank == root)
-    {
-      for (int r = 0; r < world; ++r)
-      {
-        const uint64_t n = word_off[r + 1] - word_off[r];
-        if (r == root || n == 0)
-          continue;
-        check(N.Recv(d_recv + word_off[r], n, ncclUint32, r, comm, st), "ncclRecv");
-      }
-    }
-    else if (my_words)
-    {
-      check(N.Send(d_send, my_words, ncclUint32, root, comm, st), "ncclSend");
-    }
-    check(N.GroupEnd(), "ncclGroupEnd");
+    // 2. the slab arrays go GPU to GPU, straight out of the buffers the plan wrote (NVLink; NCCL has no gatherv, so a
+    //    group of point-to-point transfers): positions, normals, [edge_lo, edge_hi], segment lengths, per-plane counts
+    const uint64_t Wl = local->n_waypoints, Sl = local->n_segments, Kl = local->slab_planes;
+    const float* d_pos = c->outPos.as<float>();
+    const float* d_nrm = c->outNrm.as<float>();
+    const uint32_t* d_elo = c->outEdge.as<uint32_t>();
+    const uint32_t* d_ehi = c->outEdge.as<uint32_t>() + local->dev_w_cap;
+    const unsigned* d_seg = c->outSegLen.as<unsigned>();
+    const unsigned* d_meta = c->planeMeta.as<unsigned>();
     if (rank != root)
     {
+      check(N.GroupStart(), "ncclGroupStart");
+      if (Wl)
+      {
+        check(N.Send(d_pos, 3 * Wl, ncclFloat32, root, comm, st), "ncclSend(positions)");
+        check(N.Send(d_nrm, 3 * Wl, ncclFloat32, root, comm, st), "ncclSend(normals)");
+        if (edges)
+        {
+          check(N.Send(d_elo, Wl, ncclUint32, root, comm, st), "ncclSend(edge_lo)");
+          check(N.Send(d_ehi, Wl, ncclUint32, root, comm, st), "ncclSend(edge_hi)");
+        }
+      }
+      if (Sl)
+        check(N.Send(d_seg, Sl, ncclUint32, root, comm, st), "ncclSend(segments)");
+      if (Kl)
+        check(N.Send(d_meta, 2 * Kl, ncclUint32, root, comm, st), "ncclSend(planes)");
+      check(N.GroupEnd(), "ncclGroupEnd");
       NB2_CUDA(cudaStreamSynchronize(st));
       return NB2_OK;
     }
-    if (my_words)
-      NB2_CUDA(cudaMemcpyAsync(d_recv + word_off[root], d_send, sizeof(uint32_t) * my_words, cudaMemcpyDeviceToDevice, st));
 
-    // 4. root: unpack into one result, slabs in rank order = plane order
-    std::vector<uint32_t> all(total_words ? total_words : 1);
-    if (total_words)
-      NB2_CUDA(cudaMemcpyAsync(all.data(), d_recv, sizeof(uint32_t) * total_words, cudaMemcpyDeviceToHost, st));
-    NB2_CUDA(cudaStreamSynchronize(st));
+    // root: receive area (the hit records are dead between plans): pos | nrm | elo | ehi | seg | meta, slabs in rank order
+    const size_t words = 6 * W + (edges ? 2 * W : 0) + S + 2 * K + 64;
+    c->hitRec.ensure(sizeof(uint32_t) * words);
+    uint32_t* base = c->hitRec.as<uint32_t>();
+    float* r_pos = reinterpret_cast<float*>(base);
+    float* r_nrm = r_pos + 3 * W;
+    uint32_t* r_elo = reinterpret_cast<uint32_t*>(r_nrm + 3 * W);
+    uint32_t* r_ehi = r_elo + (edges ? W : 0);
+    uint32_t* r_seg = r_ehi + (edges ? W : 0);
+    uint32_t* r_meta = r_seg + S;
+    std::vector<uint64_t> w_off(world + 1, 0), s_off(world + 1, 0), k_off(world + 1, 0);
+    for (int r = 0; r < world; ++r)
+    {
+      w_off[r + 1] = w_off[r] + hv[r].waypoints;
+      s_off[r + 1] = s_off[r] + hv[r].segments;
+      k_off[r + 1] = k_off[r] + hv[r].planes;
+    }
+    check(N.GroupStart(), "ncclGroupStart");
+    for (int r = 0; r < world; ++r)
+    {
+      if (r == root)
+        continue;
+      const uint64_t Wr = hv[r].waypoints, Sr = hv[r].segments, Kr = hv[r].planes;
+      if (Wr)
+      {
+        check(N.Recv(r_pos + 3 * w_off[r], 3 * Wr, ncclFloat32, r, comm, st), "ncclRecv(positions)");
+        check(N.Recv(r_nrm + 3 * w_off[r], 3 * Wr, ncclFloat32, r, comm, st), "ncclRecv(normals)");
+        if (edges)
+        {
+          check(N.Recv(r_elo + w_off[r], Wr, ncclUint32, r, comm, st), "ncclRecv(edge_lo)");
+          check(N.Recv(r_ehi + w_off[r], Wr, ncclUint32, r, comm, st), "ncclRecv(edge_hi)");
+        }
+      }
+      if (Sr)
+        check(N.Recv(r_seg + s_off[r], Sr, ncclUint32, r, comm, st), "ncclRecv(segments)");
+      if (Kr)
+        check(N.Recv(r_meta + 2 * k_off[r], 2 * Kr, ncclUint32, r, comm, st), "ncclRecv(planes)");
+    }
+    check(N.GroupEnd(), "ncclGroupEnd");
+    // the root's own slab joins the others on the device
+    if (Wl)
+    {
+      NB2_CUDA(cudaMemcpyAsync(r_pos + 3 * w_off[root], d_pos, 12 * Wl, cudaMemcpyDeviceToDevice, st));
+      NB2_CUDA(cudaMemcpyAsync(r_nrm + 3 * w_off[root], d_nrm, 12 * Wl, cudaMemcpyDeviceToDevice, st));
+      if (edges)
+      {
+        NB2_CUDA(cudaMemcpyAsync(r_elo + w_off[root], d_elo, 4 * Wl, cudaMemcpyDeviceToDevice, st));
+        NB2_CUDA(cudaMemcpyAsync(r_ehi + w_off[root], d_ehi, 4 * Wl, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    if (Sl)
+      NB2_CUDA(cudaMemcpyAsync(r_seg + s_off[root], d_seg, 4 * Sl, cudaMemcpyDeviceToDevice, st));
+    if (Kl)
+      NB2_CUDA(cudaMemcpyAsync(r_meta + 2 * k_off[root], d_meta, 8 * Kl, cudaMemcpyDeviceToDevice, st));
 
+    // 3. one device -> pinned-host copy per array, into the final result
     nb2_result* out = allocResult(c, P, S, W, edges, false);
     out->params = local->params;
     out->lattice = local->lattice;
-    uint64_t p_acc = 0, s_acc = 0, w_acc = 0;
-    for (int r = 0; r < world; ++r)
+    c->hostSmall.ensure(4096 + 8 * K + 64);
+    uint32_t* h_meta = reinterpret_cast<uint32_t*>(c->hostSmall.as<uint8_t>() + 4096);
+    try
     {
-      const SlabHeader& h = hh[r];
-      const uint32_t* p = all.data() + word_off[r];
-      std::memcpy(out->positions + 3 * w_acc, p, 12 * h.waypoints);
-      p += 3 * h.waypoints;
-      std::memcpy(out->normals + 3 * w_acc, p, 12 * h.waypoints);
-      p += 3 * h.waypoints;
-      if (edges)
+      if (W)
       {
-        std::memcpy(out->edge_lo + w_acc, p, 4 * h.waypoints);
-        p += h.waypoints;
-        std::memcpy(out->edge_hi + w_acc, p, 4 * h.waypoints);
-        p += h.waypoints;
+        NB2_CUDA(cudaMemcpyAsync(out->positions, r_pos, 12 * W, cudaMemcpyDeviceToHost, st));
+        NB2_CUDA(cudaMemcpyAsync(out->normals, r_nrm, 12 * W, cudaMemcpyDeviceToHost, st));
+        if (edges)
+        {
+          NB2_CUDA(cudaMemcpyAsync(out->edge_lo, r_elo, 4 * W, cudaMemcpyDeviceToHost, st));
+          NB2_CUDA(cudaMemcpyAsync(out->edge_hi, r_ehi, 4 * W, cudaMemcpyDeviceToHost, st));
+        }
       }
-      uint64_t w_run = w_acc;
-      for (uint64_t s = 0; s < h.segments; ++s)
-      {
-        out->segment_offsets[s_acc + s] = static_cast<uint32_t>(w_run);
-        w_run += *p++;
-      }
-      uint64_t s_run = s_acc;
-      for (uint64_t q = 0; q < h.paths; ++q)
-      {
-        const uint64_t plane = static_cast<uint64_t>(p[0]) | (static_cast<uint64_t>(p[1]) << 32);
-        out->path_plane[p_acc + q] = static_cast<int64_t>(plane);
-        out->path_offsets[p_acc + q] = static_cast<uint32_t>(s_run);
-        s_run += p[2];
-        p += 3;
-      }
-      p_acc += h.paths;
-      s_acc += h.segments;
-      w_acc += h.waypoints;
+      if (S)
+        NB2_CUDA(cudaMemcpyAsync(out->segment_offsets + 1, r_seg, 4 * S, cudaMemcpyDeviceToHost, st));
+      if (K)
+        NB2_CUDA(cudaMemcpyAsync(h_meta, r_meta, 8 * K, cudaMemcpyDeviceToHost, st));
+      NB2_CUDA(cudaStreamSynchronize(st));
     }
-    out->path_offsets[P] = static_cast<uint32_t>(S);
-    out->segment_offsets[S] = static_cast<uint32_t>(W);
+    catch (...)
+    {
+      freeResult(out);
+      throw;
+    }
+    // segment lengths -> offsets; planes with segments -> tool paths (slabs in rank order = plane order)
+    out->segment_offsets[0] = 0;
+    for (uint64_t s2 = 0; s2 < S; ++s2)
+      out->segment_offsets[s2 + 1] += out->segment_offsets[s2];
+    uint64_t p_acc = 0, s_acc = 0;
+    for (int r = 0; r < world; ++r)
+      for (uint64_t k = 0; k < hv[r].planes; ++k)
+      {
+        const unsigned sk = h_meta[2 * (k_off[r] + k) + 1];
+        if (!sk)
+          continue;
+        out->path_offsets[p_acc] = static_cast<uint32_t>(s_acc);
+        out->path_plane[p_acc] = static_cast<int64_t>(hv[r].plane_begin + k);
+        s_acc += sk;
+        ++p_acc;
+      }
+    out->path_offsets[p_acc] = static_cast<uint32_t>(s_acc);
+    if (p_acc != P || s_acc != S)
+    {
+      freeResult(out);
+      fail(NB2_ERR_INTERNAL, "gathered slab metadata is inconsistent");
+    }
 
-    // 5. the modifiers that need the whole set of tool paths
+    // 4. the modifiers that need the whole set of tool paths
     try
     {
       const nb2_plan_params& prm = out->params;

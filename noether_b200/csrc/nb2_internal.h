@@ -227,6 +227,13 @@ struct nb2_result
   double* poses = nullptr;              // 16 W, only for legacy (resampled) results
   bool post_ops_applied = false;
   bool legacy = false;
+  // A slab of a sharded plan stays in the owner's device buffers (outPos / outNrm / outEdge / outSegLen / planeMeta)
+  // until nb2_result_gather ships it to the root over NCCL; valid until the next plan on that context.
+  bool device_resident = false;
+  uint64_t dev_w_cap = 0;      // outEdge holds edge_lo at [0, W) and edge_hi at [dev_w_cap, dev_w_cap + W)
+  uint64_t slab_begin = 0;     // first lattice plane of the slab
+  uint64_t slab_planes = 0;    // planes in the slab (entries of planeMeta)
+  bool dev_edges = false;
   nb2_plan_params params{};
   nb2_lattice lattice{};
 };

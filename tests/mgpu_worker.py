@@ -1,0 +1,63 @@
+"""Worker of tests/test_multi_gpu.py: one rank per GPU (torchrun).  Every rank plans its plane slab of the same mesh,
+the slabs are gathered to rank 0 over NCCL, and rank 0 checks the gathered tool paths against its own unsharded plan,
+array by array, bit for bit."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    from noether_b200.dist import RankInfo, broadcast_bytes, init_process_group
+
+    info = RankInfo.from_env()
+    torch.cuda.set_device(info.local_rank)
+    init_process_group(info, "nccl")
+    ctx = nb.Context(info.local_rank)
+    uid = broadcast_bytes(ctx.comm_unique_id() if info.rank == 0 else None, 0, info.world)
+    ctx.comm_init(uid, info.rank, info.world)
+
+    xyz, tri = meshes.wavy(300, 240)
+    xyz, tri = meshes.cut_hole(xyz, tri)
+    ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
+    nrm = ctx.normals_from_mesh_faces(xyz.shape[0])
+    blob = meshes.pack_blob(xyz, nrm, tri)
+    for legacy in (False, True):
+        if legacy:
+            planner = nb.PlaneSlicerLegacyRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx),
+                                                        nb.CentroidOriginGenerator(ctx), 0.004, 0.01, 0.0, ctx)
+        else:
+            planner = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx),
+                                                  nb.CentroidOriginGenerator(ctx), ctx)
+        planner.set_line_spacing(0.0031)
+        planner.generate_rasters_bidirectionally(True)
+        local = planner.plan(blob, info.rank, info.world)
+        assert local.n_waypoints > 0 and local.positions.shape[0] == 0, "a slab stays on the device until the gather"
+        got = ctx.gather(local, 0)
+        local.free()
+        if info.rank == 0:
+            ctx._mesh_key = None
+            ref = planner.plan(blob)
+            assert got.n_paths == ref.n_paths > 100 and got.n_segments == ref.n_segments > got.n_paths
+            for name in ("path_offsets", "segment_offsets", "path_plane", "positions", "normals"):
+                a, b = getattr(got, name), getattr(ref, name)
+                assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8)), name
+            assert np.array_equal(got.poses(), ref.poses())
+            print(f"gather ok (legacy={legacy}): {got.n_paths} paths, {got.n_segments} segments, {got.n_waypoints} waypoints "
+                  f"from {info.world} slabs", flush=True)
+        else:
+            assert got is None
+    torch.distributed.barrier()
+    ctx.close()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
