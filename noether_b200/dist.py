@@ -97,3 +97,18 @@ def gather_slabs(local: SlabPaths, info: RankInfo, root: int = 0) -> SlabPaths |
     if info.rank != root:
         return None
     return concatenate_slabs(out)
+
+
+def lpt_assign(sizes: list[int], world: int) -> list[list[int]]:
+    """Whole-mesh sharding of a batch (partitioning B): longest-processing-time-first on the triangle
+    counts — meshes in decreasing size, each to the rank with the least work so far.  Returns, per rank, the indices of
+    its meshes in the order it should plan them.  Deterministic (ties: lower mesh index first, lower rank first), so
+    every rank computes the same assignment without communicating."""
+    order = sorted(range(len(sizes)), key=lambda i: (-sizes[i], i))
+    load = [0] * world
+    out: list[list[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        out[r].append(i)
+        load[r] += sizes[i]
+    return out

@@ -166,3 +166,35 @@ def rigid_transform(xyz, T):
     T = np.asarray(T, np.float64)
     p = xyz.astype(np.float64) @ T[:3, :3].T + T[:3, 3]
     return p.astype(np.float32)
+
+
+def cfg5_mesh(k: int):
+    """SURVEY.md §8(d) cfg5, mesh k of the batch: wavy(nx_k, ny_k) with nx_k = round(1250 f_k), ny_k = round(800 f_k),
+    f_k = sqrt(0.75 + 0.5 u_k) (1.5 - 2.5 M triangles), amplitude A_k = 0.01 + 0.03 u'_k, moved by a seeded random rigid
+    transform (translation within +-1 m, any rotation).  Returns (xyz, tri, T)."""
+    rng = np.random.Generator(np.random.MT19937(1234 + k))
+    u, u2 = rng.random(), rng.random()
+    f = np.sqrt(0.75 + 0.5 * u)
+    nx, ny = int(round(1250 * f)), int(round(800 * f))
+    xyz, tri = wavy(nx, ny, amp=0.01 + 0.03 * u2)
+    # rotation from a random unit quaternion, translation in [-1, 1]^3
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    T = np.eye(4)
+    T[:3, :3] = R
+    T[:3, 3] = rng.uniform(-1.0, 1.0, size=3)
+    return rigid_transform(xyz, T), tri, T
+
+
+def cfg5_triangle_counts(n_meshes: int = 64) -> list[int]:
+    """Triangle count of every mesh of the cfg5 batch without building it (the LPT assignment needs only these)."""
+    out = []
+    for k in range(n_meshes):
+        rng = np.random.Generator(np.random.MT19937(1234 + k))
+        f = np.sqrt(0.75 + 0.5 * rng.random())
+        out.append(2 * int(round(1250 * f)) * int(round(800 * f)))
+    return out

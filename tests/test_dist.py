@@ -84,3 +84,19 @@ def test_slab_ranges_partition_the_lattice():
                 assert a[1] == b[0]
             sizes = [e - b for b, e in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_lpt_assignment_of_the_mesh_batch():
+    """cfg5: 64 meshes of 1.5 - 2.5 M triangles over 8 GPUs, whole meshes, longest-processing-time first."""
+    from noether_b200 import meshes
+    from noether_b200.dist import lpt_assign
+    sizes = meshes.cfg5_triangle_counts(64)
+    assert len(sizes) == 64 and min(sizes) >= 1_450_000 and max(sizes) <= 2_550_000
+    shares = lpt_assign(sizes, 8)
+    flat = sorted(i for s in shares for i in s)
+    assert flat == list(range(64))                       # every mesh planned exactly once
+    loads = [sum(sizes[i] for i in s) for s in shares]
+    assert max(loads) - min(loads) <= max(sizes)         # LPT bound
+    assert max(loads) <= 1.05 * sum(sizes) / 8           # within 5 % of perfect balance on this batch
+    assert lpt_assign(sizes, 8) == shares                # deterministic: every rank derives the same assignment
+    assert lpt_assign([5, 5, 5], 1) == [[0, 1, 2]]

@@ -439,3 +439,84 @@ def test_cfg2_properties(ctx, orc):
                                             scan_mode=orc.SCAN_BINNED, frame=oracle_pca_from_capi(orc, ctx.pca()))
     assert bytes(lat_o) == bytes(lat)
     assert_same_paths(gpu, paths.flat(), "cfg2", poses=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] (cfg4) and configs[4] (cfg5) at full size
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cfg4_normals_and_pca_on_50m_triangle_scan_mesh(ctx, orc):
+    """NormalsFromMeshFaces + PrincipalAxis / Centroid on the 50 M-triangle mesh with scanner-like (permuted) vertex and
+    face order: normals bit-exact against the oracle's face-ordered float sums, PCA frame against its fp64 moments."""
+    import torch
+    from noether_b200 import meshes
+    if torch.cuda.mem_get_info()[0] < 24 * 2**30:
+        pytest.skip("needs 24 GB of free device memory")
+    xyz, tri = meshes.wavy(6250, 4000)
+    assert tri.shape[0] == 50_000_000 and xyz.shape[0] == 25_010_251
+    xyz, tri = meshes.permute(xyz, tri, seed=42)
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob, force=True)
+    nrm = ctx.normals_from_mesh_faces(blob.n_vertices)
+    ref = orc.normals_from_mesh_faces(xyz, tri)
+    assert np.array_equal(bits(nrm), bits(ref))
+    # unit length, and close to the analytic normal of z = A sin(2 pi x / L) sin(2 pi y / L)
+    assert np.abs(np.linalg.norm(nrm.astype(np.float64), axis=1) - 1.0).max() < 1e-6
+    A, lam = 0.02, 0.25
+    sub = np.random.default_rng(0).integers(0, xyz.shape[0], 200_000)
+    x, y = xyz[sub, 0].astype(np.float64), xyz[sub, 1].astype(np.float64)
+    interior = (x > 1e-3) & (x < 1 - 1e-3) & (y > 1e-3) & (y < 0.8 - 1e-3)
+    w = 2 * np.pi / lam
+    g = np.stack([-A * w * np.cos(w * x) * np.sin(w * y), -A * w * np.sin(w * x) * np.cos(w * y), np.ones_like(x)], 1)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    cosang = (g * nrm[sub].astype(np.float64)).sum(1)[interior]
+    assert np.arccos(np.clip(cosang, -1, 1)).max() < 2e-3
+    # PCA frame: centroid, axes and OBB extents against the fp64 oracle
+    g_pca = ctx.pca()
+    o = orc.pca(xyz, orc.MOMENTS_F64)
+    diag = float(np.linalg.norm(xyz.max(0) - xyz.min(0)))
+    assert np.abs(np.array(g_pca.mean) - o.mean).max() <= 1e-7 * diag
+    assert np.abs(np.array(g_pca.scales) - o.scales).max() <= 1e-6 * diag
+    ev = np.array(g_pca.evecs, np.float32).reshape(3, 3).T
+    for i in range(3):
+        assert abs(float(ev[:, i] @ o.evecs[:, i])) > 1 - 1e-9
+    d = ctx.principal_axis_direction(0.0)
+    assert abs(abs(d[1]) - 1.0) < 1e-4          # Lx = 1.0 > Ly = 0.8: the second principal axis is y
+    assert np.abs(ctx.centroid_origin() - np.array(o.mean, np.float64)).max() <= 1e-7 * diag
+
+
+def test_cfg5_share_of_the_mesh_batch(ctx, orc):
+    """Whole-mesh sharding: the meshes rank 0 of 8 receives under the LPT assignment, planned back to back on one context
+    at 2 mm spacing; structure checks on all of them, bit-exact oracle comparison on the first."""
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    from noether_b200.dist import lpt_assign
+    share = lpt_assign(meshes.cfg5_triangle_counts(64), 8)[0]
+    assert len(share) == 8
+    pl = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx), nb.CentroidOriginGenerator(ctx), ctx)
+    pl.set_line_spacing(0.002)
+    for n, k in enumerate(share[:4]):
+        xyz, tri, T = meshes.cfg5_mesh(k)
+        assert 1_450_000 <= tri.shape[0] <= 2_550_000
+        ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
+        nrm = ctx.normals_from_mesh_faces(xyz.shape[0])
+        gpu = pl.plan(meshes.pack_blob(xyz, nrm, tri))
+        lat = ctx.last_lattice()
+        # rasters step along the long side (1 m) of the part whatever its pose: about 500 planes, one chain each.  (The
+        # first / last lattice plane may graze the boundary column, which is no longer exactly planar once the posed
+        # vertices are rounded to float32: it is then cut into fragments, as the reference would cut it.)
+        assert 480 <= gpu.n_paths <= 520 and np.all(gpu.segments_per_path()[1:-1] == 1)
+        assert np.all(np.diff(gpu.path_plane) == 1)
+        nvec = np.array(lat.cut_normal)
+        assert abs(abs(float(nvec @ T[:3, 0])) - 1.0) < 1e-3      # cut normal = the part's own x axis
+        seg_of_wp = np.repeat(np.arange(gpu.n_segments), np.diff(gpu.segment_offsets.astype(np.int64)))
+        path_of_seg = np.repeat(np.arange(gpu.n_paths), gpu.segments_per_path())
+        plane = gpu.path_plane[path_of_seg[seg_of_wp]]
+        o = np.array(lat.start_loc)[None, :] + (plane[:, None] * lat.line_spacing) * nvec[None, :]
+        dist = ((gpu.positions.astype(np.float64) - o) * nvec[None, :]).sum(1)
+        assert np.abs(dist).max() < 1e-6                          # float32 storage of coordinates up to ~2 m
+        if n == 0:
+            paths, lat_o, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.002, True, slice_mode=orc.SLICE_INTENT,
+                                                    scan_mode=orc.SCAN_BINNED, frame=oracle_pca_from_capi(orc, ctx.pca()))
+            assert bytes(lat_o) == bytes(lat)
+            assert_same_paths(gpu, paths.flat(), f"cfg5 mesh {k}", poses=False)
+        gpu.free()
