@@ -875,6 +875,393 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Fast path of S5 for the planes met in practice: the work area is in shared memory (16-bit indices), no cut point has
+// more than two proper line ends and no contour closes on itself.  Same decisions as linkPlane above (which remains the
+// specification and handles every other plane: the fast path returns false before writing any output and the caller
+// re-runs the plane through linkPlane), organised for instruction count: one thread per cut LINE (its two endpoints
+// are independent work, and adjacent 16- / 32-bit entries move as one 32- / 64-bit access), fused sweeps, splitters
+// every 8th line.
+// -----------------------------------------------------------------------------------------------------------------
+constexpr unsigned kFastSplitMask = 7u;
+
+__device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLocal, unsigned n, unsigned cap,
+                              unsigned* s_misc)
+{
+  using Idx = uint16_t;
+  constexpr unsigned kNone = 0xffffu;
+  const unsigned E = 2 * n;
+  const unsigned tid = threadIdx.x, nth = blockDim.x;
+  const unsigned off = P.planeOff[kLocal];
+  const unsigned mask = cap - 1;
+  const float4* __restrict__ rec = P.rec + 2ull * off;
+
+  // work area (same footprint as PlaneWork<uint16_t>): positions | tags | slots | twin; the position region is reused
+  // for the list-ranking arrays once the cut points are merged
+  float* const px = reinterpret_cast<float*>(smem);
+  float* const py = px + E;
+  float* const pz = py + E;
+  unsigned* const etag = reinterpret_cast<unsigned*>(smem + ((12ull * E + 15) & ~size_t(15)));
+  Slot* const slots = reinterpret_cast<Slot*>(etag + E);
+  Idx* const twin = reinterpret_cast<Idx*>(slots + cap);
+  Idx* const lst = reinterpret_cast<Idx*>(smem);  // [E]  owner splitter during the walk, then last dart of the list
+  Idx* const rnk = lst + E;                        // [E]  hops from the owner, then hops to the last dart
+  Idx* const chainEnd = rnk + E;                   // [E]
+  const unsigned nsCap = E / 4 + 8;                // splitters the compact arrays hold (more: leave to linkPlane)
+  Idx* const cDart = chainEnd + E;                 // 7 compact arrays of nsCap entries: 3.5 E + 112 bytes <= 6 E
+  Idx* const cNext0 = cDart + nsCap;
+  Idx* const cNext1 = cNext0 + nsCap;
+  Idx* const cDist0 = cNext1 + nsCap;
+  Idx* const cDist1 = cDist0 + nsCap;
+  Idx* const cLast0 = cDist1 + nsCap;
+  Idx* const cLast1 = cLast0 + nsCap;
+  if (7u * nsCap * sizeof(Idx) > 6u * E)
+    return false;  // tiny planes: not worth a special case
+
+  if (tid < kMiscWords)
+    s_misc[tid] = 0;
+
+  // ---- A: stage the records; empty hash; no twins yet -----------------------------------------------------------------
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const float4 r0 = __ldg(rec + 2 * j), r1 = __ldg(rec + 2 * j + 1);
+    *reinterpret_cast<float2*>(px + 2 * j) = make_float2(r0.x, r1.x);
+    *reinterpret_cast<float2*>(py + 2 * j) = make_float2(r0.y, r1.y);
+    *reinterpret_cast<float2*>(pz + 2 * j) = make_float2(r0.z, r1.z);
+    *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(__float_as_uint(r0.w), __float_as_uint(r1.w));
+    *reinterpret_cast<unsigned*>(twin + 2 * j) = 0xffffffffu;
+  }
+  for (unsigned s = tid; s < cap; s += nth)
+    *reinterpret_cast<uint2*>(slots + s) = make_uint2(kEmpty, kEmpty);
+  __syncthreads();
+
+  // ---- H1: merge cut points with equal float coordinates; smallest rank per point ------------------------------------
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const float2 x2 = *reinterpret_cast<const float2*>(px + 2 * j), y2 = *reinterpret_cast<const float2*>(py + 2 * j),
+                 z2 = *reinterpret_cast<const float2*>(pz + 2 * j);
+    const uint2 t2 = *reinterpret_cast<const uint2*>(etag + 2 * j);
+    unsigned sl[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+    {
+      const float x = w ? x2.y : x2.x, y = w ? y2.y : y2.x, z = w ? z2.y : z2.x;
+      const unsigned e = 2 * j + w;
+      unsigned s = hashPoint(x, y, z) & mask;
+      while (true)
+      {
+        unsigned f = *reinterpret_cast<volatile unsigned*>(&slots[s].first);
+        if (f == kEmpty)
+        {
+          f = atomicCAS(&slots[s].first, kEmpty, e);
+          if (f == kEmpty)
+            break;
+        }
+        if (px[f] == x && py[f] == y && pz[f] == z)
+          break;
+        s = (s + 1) & mask;
+      }
+      atomicMin(&slots[s].tag, w ? t2.y : t2.x);
+      sl[w] = s;
+    }
+    *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(sl[0], sl[1]);
+  }
+  __syncthreads();
+
+  // ---- H2: pair the two line ends meeting at each point.  A used slot holds its key holder (< 2^16), which reads as
+  //          "no arrivals yet" in the pairing-cell encoding, so the cells need no clearing. ------------------------------
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const uint2 sl = *reinterpret_cast<const uint2*>(etag + 2 * j);
+    if (sl.x == sl.y)
+      continue;  // both ends merged into one point: the line is dropped (vtkTriangle::Contour: pts[0] != pts[1])
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+    {
+      const unsigned e = 2 * j + w;
+      unsigned* cell = &slots[w ? sl.y : sl.x].first;
+      unsigned old = *reinterpret_cast<volatile unsigned*>(cell);
+      while (true)
+      {
+        const unsigned seen = atomicCAS(cell, old, (((old >> kCellShift) + 1u) << kCellShift) | e);
+        if (seen == old)
+          break;
+        old = seen;
+      }
+      const unsigned arrivals = old >> kCellShift;
+      if (arrivals == 1u)
+      {
+        const unsigned prev = old & kCellMask;
+        twin[e] = static_cast<Idx>(prev);
+        twin[prev] = static_cast<Idx>(e);
+      }
+      else if (arrivals >= 2u)
+        s_misc[6] = 1u;  // a point with more than two line ends: linkPlane's business
+    }
+  }
+  __syncthreads();
+  if (s_misc[6])
+    return false;
+
+  // ---- F: merged ranks, dropped lines, list-ranking set-up and splitter selection, one sweep ---------------------------
+  // (the position region is dead from here on)
+  for (unsigned j0 = 0; j0 < n; j0 += nth)
+  {
+    const unsigned j = j0 + tid;
+    bool sel0 = false, sel1 = false;
+    if (j < n)
+    {
+      const uint2 sl = *reinterpret_cast<const uint2*>(etag + 2 * j);
+      *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(slots[sl.x].tag, slots[sl.y].tag);
+      *reinterpret_cast<unsigned*>(lst + 2 * j) = 0xffffffffu;
+      *reinterpret_cast<unsigned*>(chainEnd + 2 * j) = 0xffffffffu;
+      if (sl.x == sl.y)
+        *reinterpret_cast<unsigned*>(twin + 2 * j) = (2 * j) | ((2 * j + 1) << 16);  // dead markers: twin == self
+      else
+      {
+        const unsigned tw = *reinterpret_cast<const unsigned*>(twin + 2 * j);
+        const bool every = (j & kFastSplitMask) == 0u;
+        sel0 = every || (tw & 0xffffu) == kNone;   // a dart that starts at an open end heads a list
+        sel1 = every || (tw >> 16) == kNone;
+      }
+    }
+    const unsigned m0 = __ballot_sync(kFull, sel0), m1 = __ballot_sync(kFull, sel1);
+    unsigned base = 0;
+    if ((tid & 31u) == 0u && (m0 | m1))
+      base = atomicAdd(&s_misc[2], __popc(m0) + __popc(m1));
+    base = __shfl_sync(kFull, base, 0);
+    const unsigned below = (1u << (tid & 31u)) - 1u;
+    if (sel0)
+    {
+      const unsigned c = base + __popc(m0 & below);
+      if (c < nsCap)
+        cDart[c] = static_cast<Idx>(2 * j), lst[2 * j] = static_cast<Idx>(c);
+    }
+    if (sel1)
+    {
+      const unsigned c = base + __popc(m0) + __popc(m1 & below);
+      if (c < nsCap)
+        cDart[c] = static_cast<Idx>(2 * j + 1), lst[2 * j + 1] = static_cast<Idx>(c);
+    }
+  }
+  __syncthreads();
+  const unsigned Ns = s_misc[2];
+  if (Ns > nsCap)
+    return false;  // a crowd of short chains: linkPlane's general layout takes it
+
+  // ---- R1: every splitter walks its sublist up to the next splitter (or the end of the list) --------------------------
+  for (unsigned c = tid; c < Ns; c += nth)
+  {
+    unsigned d = cDart[c], j = 0;
+    while (true)
+    {
+      if (j)
+        lst[d] = static_cast<Idx>(c);
+      rnk[d] = static_cast<Idx>(j);
+      const unsigned nd = twin[d ^ 1u];
+      if (nd == kNone)  // d ends at an open end: last dart of the list
+      {
+        cNext0[c] = static_cast<Idx>(kNone);
+        cDist0[c] = static_cast<Idx>(j);
+        cLast0[c] = static_cast<Idx>(d);
+        break;
+      }
+      if (((nd >> 1) & kFastSplitMask) == 0u)  // the next dart is a splitter (a list head has no predecessor)
+      {
+        cNext0[c] = lst[nd];
+        cDist0[c] = static_cast<Idx>(j + 1u);
+        cLast0[c] = static_cast<Idx>(kNone);
+        break;
+      }
+      d = nd;
+      ++j;
+    }
+  }
+  __syncthreads();
+
+  // ---- R2: pointer jumping on the splitters ----------------------------------------------------------------------------
+  Idx *nxA = cNext0, *nxB = cNext1, *dsA = cDist0, *dsB = cDist1, *laA = cLast0, *laB = cLast1;
+  {
+    unsigned rounds = 1;
+    while ((1u << rounds) < Ns + 1u)
+      ++rounds;
+    ++rounds;
+    for (unsigned r = 0; r < rounds; ++r)
+    {
+      unsigned pending = 0;
+      for (unsigned c = tid; c < Ns; c += nth)
+      {
+        const unsigned nx = nxA[c];
+        unsigned nn = kNone, ds = dsA[c], la = laA[c];
+        if (nx != kNone)
+        {
+          nn = nxA[nx];
+          ds += dsA[nx];
+          la = laA[nx];
+          pending |= (nn != kNone);
+        }
+        nxB[c] = static_cast<Idx>(nn);
+        dsB[c] = static_cast<Idx>(ds);
+        laB[c] = static_cast<Idx>(la);
+      }
+      if (pending)
+        s_misc[5] = r + 1;
+      __syncthreads();
+      Idx* t;
+      t = nxA, nxA = nxB, nxB = t;
+      t = dsA, dsA = dsB, dsB = t;
+      t = laA, laA = laB, laB = t;
+      const unsigned more = s_misc[5];
+      __syncthreads();  // everyone has read the flag before the next round may overwrite it
+      if (more != r + 1)
+        break;
+    }
+  }
+
+  // ---- R3: owner / hops -> last dart / hops to it, in place; open ends become chain heads -------------------------------
+  struct Head
+  {
+    double key;    // first point . cut_direction
+    unsigned e;    // head dart
+    unsigned tag;  // rank (2 * triangle + line end) of the chain's first line end: tie-break of the order
+  };
+  Head* const heads = reinterpret_cast<Head*>(slots);  // the hash is dead; 16 B per head, cap >= E >= 2 * heads
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const unsigned tw = *reinterpret_cast<const unsigned*>(twin + 2 * j);
+    if ((tw & 0xffffu) == 2 * j)  // dropped line
+    {
+      *reinterpret_cast<unsigned*>(lst + 2 * j) = (2 * j) | ((2 * j + 1) << 16);
+      *reinterpret_cast<unsigned*>(rnk + 2 * j) = 0u;
+      continue;
+    }
+    const unsigned ow = *reinterpret_cast<const unsigned*>(lst + 2 * j);
+    const unsigned lo = *reinterpret_cast<const unsigned*>(rnk + 2 * j);
+    const unsigned c0 = ow & 0xffffu, c1 = ow >> 16;
+    bool cyclic = c0 == kNone || c1 == kNone;
+    unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
+    if (!cyclic)
+    {
+      cyclic = nxA[c0] != kNone || nxA[c1] != kNone;
+      l0 = laA[c0], l1 = laA[c1];
+      r0 = dsA[c0] - (lo & 0xffffu), r1 = dsA[c1] - (lo >> 16);
+    }
+    if (cyclic)
+    {
+      s_misc[7] = 1u;  // a closed contour: linkPlane walks those
+      continue;
+    }
+    *reinterpret_cast<unsigned*>(lst + 2 * j) = l0 | (l1 << 16);
+    *reinterpret_cast<unsigned*>(rnk + 2 * j) = (r0 & 0xffffu) | (r1 << 16);
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+    {
+      if ((w ? (tw >> 16) : (tw & 0xffffu)) != kNone)
+        continue;
+      // dart e starts at an open end: it heads one of the two lists of its chain; keep the list that runs along the
+      // cut direction (first -> last point), ties to the lower rank
+      const unsigned e = 2 * j + w, tail = w ? l1 : l0;
+      const float4 a = __ldg(rec + e), b = __ldg(rec + (tail ^ 1u));
+      const unsigned tagFirst = __float_as_uint(a.w), tagLast = __float_as_uint(b.w);
+      const double d = dotLR(dsub(static_cast<double>(b.x), static_cast<double>(a.x)),
+                             dsub(static_cast<double>(b.y), static_cast<double>(a.y)),
+                             dsub(static_cast<double>(b.z), static_cast<double>(a.z)), P.L.dir);
+      if (d > 0.0 || (d == 0.0 && tagFirst < tagLast))
+      {
+        const unsigned h = atomicAdd(&s_misc[0], 1u);
+        heads[h].key = dotLR(static_cast<double>(a.x), static_cast<double>(a.y), static_cast<double>(a.z), P.L.dir);
+        heads[h].e = e;
+        heads[h].tag = tagFirst;
+      }
+    }
+  }
+  __syncthreads();
+  if (s_misc[7])
+    return false;
+
+  // ---- C: order of the chains ---------------------------------------------------------------------------------------------
+  const unsigned S = s_misc[0];
+  unsigned* const headOrder = reinterpret_cast<unsigned*>(cDart);  // the splitter arrays are dead: room for E / 4 heads ...
+  unsigned* const lenSorted = reinterpret_cast<unsigned*>(twin);   // ... and E / 2 here (twin is dead as well)
+  if (4ull * S > 7ull * nsCap * sizeof(Idx))
+    return false;
+  for (unsigned h = tid; h < S; h += nth)
+  {
+    unsigned ord = 0;
+    const double key = heads[h].key;
+    const unsigned tg = heads[h].tag;
+    for (unsigned g = 0; g < S; ++g)
+    {
+      const double kg = heads[g].key;
+      ord += (kg < key) || (kg == key && heads[g].tag < tg);
+    }
+    headOrder[h] = ord;
+    lenSorted[ord] = static_cast<unsigned>(rnk[heads[h].e]) + 2u;  // lines + 1 points
+  }
+  __syncthreads();
+  if (tid < 32)
+  {
+    unsigned carry = 0;
+    for (unsigned base = 0; base < S; base += 32)
+    {
+      const unsigned i = base + tid;
+      const unsigned v = i < S ? lenSorted[i] : 0u;
+      unsigned x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned y = __shfl_up_sync(kFull, x, o);
+        if (tid >= static_cast<unsigned>(o))
+          x += y;
+      }
+      if (i < S)
+        lenSorted[i] = carry + x - v;
+      carry += __shfl_sync(kFull, x, 31);
+    }
+    if (tid == 0)
+    {
+      P.planeMeta[2 * kLocal] = carry;
+      P.planeMeta[2 * kLocal + 1] = S;
+    }
+  }
+  __syncthreads();
+  const unsigned long long baseW = 2ull * off, baseS = off;
+
+  // ---- O: output ------------------------------------------------------------------------------------------------------------
+  for (unsigned h = tid; h < S; h += nth)
+  {
+    const unsigned ord = headOrder[h];
+    const unsigned e = heads[h].e;
+    const unsigned lines = static_cast<unsigned>(rnk[e]) + 1u;
+    chainEnd[lst[e]] = static_cast<Idx>(lenSorted[ord] + lines);  // plane-local index of the chain's last point
+    P.segLen[baseS + ord] = lines + 1u;
+  }
+  __syncthreads();
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const unsigned la = *reinterpret_cast<const unsigned*>(lst + 2 * j);
+    const unsigned rk = *reinterpret_cast<const unsigned*>(rnk + 2 * j);
+    const uint2 tg = *reinterpret_cast<const uint2*>(etag + 2 * j);
+    const unsigned ce0 = chainEnd[la & 0xffffu], ce1 = chainEnd[la >> 16];
+    // exactly one of the two darts of a line belongs to the selected direction of its chain (none for a dropped line)
+    if (ce0 != kNone)
+    {
+      const unsigned r = rk & 0xffffu;
+      P.wpTag[baseW + ce0 - 1u - r] = tg.x;
+      if (r == 0)
+        P.wpTag[baseW + ce0] = tg.y;
+    }
+    if (ce1 != kNone)
+    {
+      const unsigned r = rk >> 16;
+      P.wpTag[baseW + ce1 - 1u - r] = tg.y;
+      if (r == 0)
+        P.wpTag[baseW + ce1] = tg.x;
+    }
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -902,8 +1289,13 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
     unsigned cap = 16;
     while (cap < E)
       cap <<= 1;
-    if (n <= P.smemHitCap)
+    if (n <= P.smemHitCap && linkPlaneFast(P, smem, kLocal, n, cap, s_misc))
     {
+      // done
+    }
+    else if (n <= P.smemHitCap)
+    {
+      __syncthreads();
       PlaneWork<uint16_t> W;
       W.eposBytes = 12ull * E;
       W.epos = reinterpret_cast<float*>(smem);
