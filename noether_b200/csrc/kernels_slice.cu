@@ -885,7 +885,18 @@ __device__ void linkPlane(const LinkParams& P, const PlaneWork<Idx>& W, long lon
 // -----------------------------------------------------------------------------------------------------------------
 constexpr unsigned kFastSplitMask = 7u;
 
-__device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLocal, unsigned n, unsigned cap,
+/** Cheap hash of a float3 whose upper half serves as a 16-bit fingerprint (-0 folded onto +0: operator== semantics) */
+__device__ __forceinline__ unsigned hashPointFast(float x, float y, float z)
+{
+  const unsigned a = __float_as_uint(x == 0.f ? 0.f : x), b = __float_as_uint(y == 0.f ? 0.f : y),
+                 c = __float_as_uint(z == 0.f ? 0.f : z);
+  unsigned h = a * 0x9E3779B1u + b * 0x85EBCA77u + c * 0xC2B2AE3Du;
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  return h ^ (h >> 13);
+}
+
+__device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLocal, unsigned n, unsigned cap8,
                               unsigned* s_misc)
 {
   using Idx = uint16_t;
@@ -893,35 +904,41 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   const unsigned E = 2 * n;
   const unsigned tid = threadIdx.x, nth = blockDim.x;
   const unsigned off = P.planeOff[kLocal];
-  const unsigned mask = cap - 1;
   const float4* __restrict__ rec = P.rec + 2ull * off;
 
-  // work area (same footprint as PlaneWork<uint16_t>): positions | tags | slots | twin; the position region is reused
-  // for the list-ranking arrays once the cut points are merged
+  // Work area, same footprint as PlaneWork<uint16_t> (12 E | 4 E | 8 cap8 | 2 E bytes):
+  //   [0, 12 E)    endpoint positions px py pz while the cut points are merged; afterwards twin | lst | rnk | chainEnd
+  //                (2 E each) and the seven compact splitter arrays (4 E); the pairing cells alias lst + rnk
+  //   etag         own rank of each endpoint; the key holder's entry becomes the smallest rank of its point
+  //   slots        4-byte slots {key holder : 16, fingerprint : 16}, twice as many as the generic path's 8-byte ones
+  //   slotIdx      slot of each endpoint (16 bit)
   float* const px = reinterpret_cast<float*>(smem);
   float* const py = px + E;
   float* const pz = py + E;
   unsigned* const etag = reinterpret_cast<unsigned*>(smem + ((12ull * E + 15) & ~size_t(15)));
-  Slot* const slots = reinterpret_cast<Slot*>(etag + E);
-  Idx* const twin = reinterpret_cast<Idx*>(slots + cap);
-  Idx* const lst = reinterpret_cast<Idx*>(smem);  // [E]  owner splitter during the walk, then last dart of the list
-  Idx* const rnk = lst + E;                        // [E]  hops from the owner, then hops to the last dart
-  Idx* const chainEnd = rnk + E;                   // [E]
-  const unsigned nsCap = E / 4 + 8;                // splitters the compact arrays hold (more: leave to linkPlane)
-  Idx* const cDart = chainEnd + E;                 // 7 compact arrays of nsCap entries: 3.5 E + 112 bytes <= 6 E
-  Idx* const cNext0 = cDart + nsCap;
-  Idx* const cNext1 = cNext0 + nsCap;
-  Idx* const cDist0 = cNext1 + nsCap;
-  Idx* const cDist1 = cDist0 + nsCap;
-  Idx* const cLast0 = cDist1 + nsCap;
-  Idx* const cLast1 = cLast0 + nsCap;
-  if (7u * nsCap * sizeof(Idx) > 6u * E)
-    return false;  // tiny planes: not worth a special case
+  unsigned* const slots = etag + E;
+  const unsigned cap = 2 * cap8, mask = cap - 1;
+  Idx* const slotIdx = reinterpret_cast<Idx*>(slots + cap);
+  Idx* const twin = reinterpret_cast<Idx*>(smem);
+  Idx* const lst = twin + E;       // owner splitter during the walk, then last dart of the list
+  Idx* const rnk = lst + E;        // hops from the owner, then hops to the last dart
+  Idx* const chainEnd = rnk + E;
+  unsigned* const pair = reinterpret_cast<unsigned*>(lst);  // [E] pairing cells, indexed by the key holder of the point
+  // compact splitter arrays in [8 E, 12 E): one 64-bit entry {next splitter : 16, last dart : 16, hops : 16} and the
+  // splitter's dart, 10 bytes per splitter
+  const unsigned nsCap = (2u * E) / 5u;  // splitters they hold (more: leave the plane to linkPlane)
+  unsigned long long* const cEnt = reinterpret_cast<unsigned long long*>(chainEnd + E);
+  Idx* const cDart = reinterpret_cast<Idx*>(cEnt + nsCap);
+  auto packEnt = [](unsigned next, unsigned last, unsigned hops) {
+    return static_cast<unsigned long long>(next | (last << 16)) | (static_cast<unsigned long long>(hops) << 32);
+  };
+  if (n < 64 || cap > 65536u)
+    return false;  // tiny planes are not worth a special case; 16-bit slot indices need cap <= 2^16
 
   if (tid < kMiscWords)
     s_misc[tid] = 0;
 
-  // ---- A: stage the records; empty hash; no twins yet -----------------------------------------------------------------
+  // ---- A: stage the records; empty hash ---------------------------------------------------------------------------------
   for (unsigned j = tid; j < n; j += nth)
   {
     const float4 r0 = __ldg(rec + 2 * j), r1 = __ldg(rec + 2 * j + 1);
@@ -929,13 +946,14 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
     *reinterpret_cast<float2*>(py + 2 * j) = make_float2(r0.y, r1.y);
     *reinterpret_cast<float2*>(pz + 2 * j) = make_float2(r0.z, r1.z);
     *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(__float_as_uint(r0.w), __float_as_uint(r1.w));
-    *reinterpret_cast<unsigned*>(twin + 2 * j) = 0xffffffffu;
   }
-  for (unsigned s = tid; s < cap; s += nth)
+  for (unsigned s = 2 * tid; s < cap; s += 2 * nth)  // (the slot array is 8-byte aligned)
     *reinterpret_cast<uint2*>(slots + s) = make_uint2(kEmpty, kEmpty);
   __syncthreads();
 
   // ---- H1: merge cut points with equal float coordinates; smallest rank per point ------------------------------------
+  // A probe compares the 16-bit fingerprint first and touches the positions only on a match; the table is at most a
+  // quarter full, so the longest probe sequence of a warp stays short.
   for (unsigned j = tid; j < n; j += nth)
   {
     const float2 x2 = *reinterpret_cast<const float2*>(px + 2 * j), y2 = *reinterpret_cast<const float2*>(py + 2 * j),
@@ -947,39 +965,56 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
     {
       const float x = w ? x2.y : x2.x, y = w ? y2.y : y2.x, z = w ? z2.y : z2.x;
       const unsigned e = 2 * j + w;
-      unsigned s = hashPoint(x, y, z) & mask;
+      const unsigned h = hashPointFast(x, y, z);
+      const unsigned fp = h >> 16, key = e | (fp << 16);
+      unsigned s = h & mask, f = e;
       while (true)
       {
-        unsigned f = *reinterpret_cast<volatile unsigned*>(&slots[s].first);
-        if (f == kEmpty)
+        unsigned v = *reinterpret_cast<volatile unsigned*>(slots + s);
+        if (v == kEmpty)
         {
-          f = atomicCAS(&slots[s].first, kEmpty, e);
-          if (f == kEmpty)
-            break;
+          v = atomicCAS(slots + s, kEmpty, key);
+          if (v == kEmpty)
+            break;  // claimed: e is the key holder of a new point
         }
-        if (px[f] == x && py[f] == y && pz[f] == z)
-          break;
+        if ((v >> 16) == fp)
+        {
+          const unsigned g = v & 0xffffu;
+          if (px[g] == x && py[g] == y && pz[g] == z)
+          {
+            f = g;
+            break;
+          }
+        }
         s = (s + 1) & mask;
       }
-      atomicMin(&slots[s].tag, w ? t2.y : t2.x);
+      if (f != e)
+        atomicMin(etag + f, w ? t2.y : t2.x);
       sl[w] = s;
     }
-    *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(sl[0], sl[1]);
+    *reinterpret_cast<unsigned*>(slotIdx + 2 * j) = sl[0] | (sl[1] << 16);
   }
   __syncthreads();
 
-  // ---- H2: pair the two line ends meeting at each point.  A used slot holds its key holder (< 2^16), which reads as
-  //          "no arrivals yet" in the pairing-cell encoding, so the cells need no clearing. ------------------------------
+  // ---- H2: pair the two line ends meeting at each point (the positions are dead: their region now holds the pairing
+  //          cells, the twins and the list-ranking arrays) -------------------------------------------------------------------
   for (unsigned j = tid; j < n; j += nth)
   {
-    const uint2 sl = *reinterpret_cast<const uint2*>(etag + 2 * j);
-    if (sl.x == sl.y)
+    pair[2 * j] = 0u;
+    pair[2 * j + 1] = 0u;
+    *reinterpret_cast<unsigned*>(twin + 2 * j) = 0xffffffffu;
+  }
+  __syncthreads();
+  for (unsigned j = tid; j < n; j += nth)
+  {
+    const unsigned sl = *reinterpret_cast<const unsigned*>(slotIdx + 2 * j);
+    if ((sl & 0xffffu) == (sl >> 16))
       continue;  // both ends merged into one point: the line is dropped (vtkTriangle::Contour: pts[0] != pts[1])
 #pragma unroll
     for (int w = 0; w < 2; ++w)
     {
       const unsigned e = 2 * j + w;
-      unsigned* cell = &slots[w ? sl.y : sl.x].first;
+      unsigned* cell = pair + (slots[w ? (sl >> 16) : (sl & 0xffffu)] & 0xffffu);
       unsigned old = *reinterpret_cast<volatile unsigned*>(cell);
       while (true)
       {
@@ -1004,24 +1039,25 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
     return false;
 
   // ---- F: merged ranks, dropped lines, list-ranking set-up and splitter selection, one sweep ---------------------------
-  // (the position region is dead from here on)
   for (unsigned j0 = 0; j0 < n; j0 += nth)
   {
     const unsigned j = j0 + tid;
     bool sel0 = false, sel1 = false;
     if (j < n)
     {
-      const uint2 sl = *reinterpret_cast<const uint2*>(etag + 2 * j);
-      *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(slots[sl.x].tag, slots[sl.y].tag);
+      const unsigned sl = *reinterpret_cast<const unsigned*>(slotIdx + 2 * j);
+      const unsigned f0 = slots[sl & 0xffffu] & 0xffffu, f1 = slots[sl >> 16] & 0xffffu;
+      // (a key holder rewrites its own entry with the value it already has: no hazard with the readers of that entry)
+      *reinterpret_cast<uint2*>(etag + 2 * j) = make_uint2(etag[f0], etag[f1]);
       *reinterpret_cast<unsigned*>(lst + 2 * j) = 0xffffffffu;
       *reinterpret_cast<unsigned*>(chainEnd + 2 * j) = 0xffffffffu;
-      if (sl.x == sl.y)
+      if (f0 == f1)
         *reinterpret_cast<unsigned*>(twin + 2 * j) = (2 * j) | ((2 * j + 1) << 16);  // dead markers: twin == self
       else
       {
         const unsigned tw = *reinterpret_cast<const unsigned*>(twin + 2 * j);
         const bool every = (j & kFastSplitMask) == 0u;
-        sel0 = every || (tw & 0xffffu) == kNone;   // a dart that starts at an open end heads a list
+        sel0 = every || (tw & 0xffffu) == kNone;  // a dart that starts at an open end heads a list
         sel1 = every || (tw >> 16) == kNone;
       }
     }
@@ -1061,16 +1097,12 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
       const unsigned nd = twin[d ^ 1u];
       if (nd == kNone)  // d ends at an open end: last dart of the list
       {
-        cNext0[c] = static_cast<Idx>(kNone);
-        cDist0[c] = static_cast<Idx>(j);
-        cLast0[c] = static_cast<Idx>(d);
+        cEnt[c] = packEnt(kNone, d, j);
         break;
       }
       if (((nd >> 1) & kFastSplitMask) == 0u)  // the next dart is a splitter (a list head has no predecessor)
       {
-        cNext0[c] = lst[nd];
-        cDist0[c] = static_cast<Idx>(j + 1u);
-        cLast0[c] = static_cast<Idx>(kNone);
+        cEnt[c] = packEnt(lst[nd], kNone, j + 1u);
         break;
       }
       d = nd;
@@ -1079,41 +1111,29 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   }
   __syncthreads();
 
-  // ---- R2: pointer jumping on the splitters ----------------------------------------------------------------------------
-  Idx *nxA = cNext0, *nxB = cNext1, *dsA = cDist0, *dsB = cDist1, *laA = cLast0, *laB = cLast1;
+  // ---- R2: pointer jumping on the splitters, in place: an entry is one 64-bit word, so whichever version of its
+  //          successor a thread reads (this round's or the previous one's) is a consistent {next, last, hops} triple ------
   {
     unsigned rounds = 1;
     while ((1u << rounds) < Ns + 1u)
       ++rounds;
     ++rounds;
+    volatile unsigned long long* ent = cEnt;
     for (unsigned r = 0; r < rounds; ++r)
     {
-      unsigned pending = 0;
+      int pending = 0;
       for (unsigned c = tid; c < Ns; c += nth)
       {
-        const unsigned nx = nxA[c];
-        unsigned nn = kNone, ds = dsA[c], la = laA[c];
+        const unsigned long long me = ent[c];
+        const unsigned nx = static_cast<unsigned>(me) & 0xffffu;
         if (nx != kNone)
         {
-          nn = nxA[nx];
-          ds += dsA[nx];
-          la = laA[nx];
-          pending |= (nn != kNone);
+          const unsigned long long o = ent[nx];
+          ent[c] = (o & 0xffffffffull) | ((me & 0xffffffff00000000ull) + (o & 0xffffffff00000000ull));
+          pending |= (static_cast<unsigned>(o) & 0xffffu) != kNone;
         }
-        nxB[c] = static_cast<Idx>(nn);
-        dsB[c] = static_cast<Idx>(ds);
-        laB[c] = static_cast<Idx>(la);
       }
-      if (pending)
-        s_misc[5] = r + 1;
-      __syncthreads();
-      Idx* t;
-      t = nxA, nxA = nxB, nxB = t;
-      t = dsA, dsA = dsB, dsB = t;
-      t = laA, laA = laB, laB = t;
-      const unsigned more = s_misc[5];
-      __syncthreads();  // everyone has read the flag before the next round may overwrite it
-      if (more != r + 1)
+      if (!__syncthreads_or(pending))
         break;
     }
   }
@@ -1125,7 +1145,7 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
     unsigned e;    // head dart
     unsigned tag;  // rank (2 * triangle + line end) of the chain's first line end: tie-break of the order
   };
-  Head* const heads = reinterpret_cast<Head*>(slots);  // the hash is dead; 16 B per head, cap >= E >= 2 * heads
+  Head* const heads = reinterpret_cast<Head*>(slots);  // the hash is dead; 16 B per head, 4 cap >= 8 E bytes
   for (unsigned j = tid; j < n; j += nth)
   {
     const unsigned tw = *reinterpret_cast<const unsigned*>(twin + 2 * j);
@@ -1142,9 +1162,10 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
     unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
     if (!cyclic)
     {
-      cyclic = nxA[c0] != kNone || nxA[c1] != kNone;
-      l0 = laA[c0], l1 = laA[c1];
-      r0 = dsA[c0] - (lo & 0xffffu), r1 = dsA[c1] - (lo >> 16);
+      const unsigned long long e0 = cEnt[c0], e1 = cEnt[c1];
+      cyclic = (static_cast<unsigned>(e0) & 0xffffu) != kNone || (static_cast<unsigned>(e1) & 0xffffu) != kNone;
+      l0 = (static_cast<unsigned>(e0) >> 16) & 0xffffu, l1 = (static_cast<unsigned>(e1) >> 16) & 0xffffu;
+      r0 = static_cast<unsigned>(e0 >> 32) - (lo & 0xffffu), r1 = static_cast<unsigned>(e1 >> 32) - (lo >> 16);
     }
     if (cyclic)
     {
@@ -1181,10 +1202,8 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
 
   // ---- C: order of the chains ---------------------------------------------------------------------------------------------
   const unsigned S = s_misc[0];
-  unsigned* const headOrder = reinterpret_cast<unsigned*>(cDart);  // the splitter arrays are dead: room for E / 4 heads ...
-  unsigned* const lenSorted = reinterpret_cast<unsigned*>(twin);   // ... and E / 2 here (twin is dead as well)
-  if (4ull * S > 7ull * nsCap * sizeof(Idx))
-    return false;
+  unsigned* const headOrder = reinterpret_cast<unsigned*>(cEnt);    // the splitter arrays are dead: 4 E bytes
+  unsigned* const lenSorted = reinterpret_cast<unsigned*>(slotIdx);  // 2 E bytes: room for the at most E / 2 chains
   for (unsigned h = tid; h < S; h += nth)
   {
     unsigned ord = 0;
