@@ -58,8 +58,10 @@ int nb2_context_device(const nb2_context* ctx);
  * Mesh ingest.  Replaces pcl::fromPCLPointCloud2 + pcl::io::mesh2vtk and the by-name field accessors
  * (plane_slicer_raster_planner.cpp:536-537,589-590; utils.cpp:65-117).  The shim resolves field names to byte
  * offsets; `cloud_data` is pcl::PCLPointCloud2::data, `triangles` is mesh.polygons flattened to uint32[3 * n].
- * Host pointers may be pageable or pinned.  The mesh stays resident in HBM (SoA float4 positions / normals,
- * uint32 x 3 faces) until the next upload.
+ * Host pointers may be pageable or pinned; pointers into this GPU's memory are adopted in place (no copy, no
+ * synchronisation: the caller keeps them alive until the next upload, and input errors surface at the next call that
+ * synchronises).  The mesh stays resident in HBM (SoA float4 positions, uint32 x 3 faces; normals are gathered from
+ * the cloud itself) until the next upload.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct nb2_mesh_view
 {

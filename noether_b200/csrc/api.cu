@@ -645,7 +645,6 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     return a.type == cudaMemoryTypeDevice && a.device == c->device;
   };
   c->pos.ensure(sizeof(float4) * V);
-  c->nrm.ensure(sizeof(float4) * V);
   if (onThisDevice(m->cloud_data))
     c->blob.adopt(const_cast<void*>(m->cloud_data));
   else
@@ -669,8 +668,9 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   c->V = V;
   c->F = F;
   c->has_normals = m->offset_normal >= 0;
-  if (!c->has_normals)
-    NB2_CUDA(cudaMemsetAsync(c->nrm.ptr, 0, sizeof(float4) * V, c->stream));
+  // normals are read in place, out of the cloud (SoA copies exist only for normals computed or set afterwards)
+  c->nrm_base = c->has_normals ? c->blob.as<uint8_t>() + m->offset_normal : nullptr;
+  c->nrm_stride = m->point_step;
   launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
   c->timer_upload.mark("ingest+moments", c->stream);
   // Triangles copied from the host are range-checked now (noise next to the PCIe copy).  Triangles adopted in place

@@ -93,7 +93,7 @@ __device__ void blockReducePartial(MomentPartial& p, MomentPartial* smem /*[warp
  */
 __global__ void __launch_bounds__(kMomentThreads)
     k_ingest_moments(const uint8_t* __restrict__ blob, unsigned long long V, unsigned point_step, unsigned off_xyz,
-                     int off_nrm, float4* __restrict__ pos, float4* __restrict__ nrm, MomentPartial* partials,
+                     float4* __restrict__ pos, MomentPartial* partials,
                      unsigned* done_counter)
 {
   __shared__ MomentPartial s_part[kMomentThreads / 32];
@@ -116,21 +116,12 @@ __global__ void __launch_bounds__(kMomentThreads)
   p.non_finite = 0;
 
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
-  {
-    const uint8_t* rec = blob + v * point_step;
-    const float* f = reinterpret_cast<const float*>(rec + off_xyz);
-    const float x = __ldg(f), y = __ldg(f + 1), z = __ldg(f + 2);
+  auto accumulate = [&](unsigned long long v, float x, float y, float z) {
     pos[v] = make_float4(x, y, z, 0.f);
-    if (off_nrm >= 0)
-    {
-      const float* g = reinterpret_cast<const float*>(rec + off_nrm);
-      nrm[v] = make_float4(__ldg(g), __ldg(g + 1), __ldg(g + 2), 0.f);
-    }
     if (!(isfinite(x) && isfinite(y) && isfinite(z)))
     {
       ++p.non_finite;
-      continue;
+      return;
     }
     const double dx = static_cast<double>(x) - px, dy = static_cast<double>(y) - py, dz = static_cast<double>(z) - pz;
     p.s[0] += dx;
@@ -148,6 +139,27 @@ __global__ void __launch_bounds__(kMomentThreads)
     p.mx[0] = fmaxf(p.mx[0], x);
     p.mx[1] = fmaxf(p.mx[1], y);
     p.mx[2] = fmaxf(p.mx[2], z);
+  };
+  // four vertices per step: their twelve loads are in flight together; they are accumulated in the order the one-at-a-
+  // time loop would have used, so the sums do not depend on the unrolling
+  unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; v + 3 * stride < V; v += 4 * stride)
+  {
+    float c[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      const float* f = reinterpret_cast<const float*>(blob + (v + u * stride) * point_step + off_xyz);
+      c[u][0] = __ldg(f), c[u][1] = __ldg(f + 1), c[u][2] = __ldg(f + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      accumulate(v + u * stride, c[u][0], c[u][1], c[u][2]);
+  }
+  for (; v < V; v += stride)
+  {
+    const float* f = reinterpret_cast<const float*>(blob + v * point_step + off_xyz);
+    accumulate(v, __ldg(f), __ldg(f + 1), __ldg(f + 2));
   }
 
   blockReducePartial(p, s_part);
@@ -317,15 +329,17 @@ __global__ void __launch_bounds__(256)
     nrm[v] = make_float4(packed[3 * v], packed[3 * v + 1], packed[3 * v + 2], 0.f);
 }
 
-__global__ void __launch_bounds__(256) k_pack_out(const float4* __restrict__ src, unsigned long long V, float* __restrict__ dst)
+/** three floats per vertex at src + v * stride -> packed float[3 V] */
+__global__ void __launch_bounds__(256)
+    k_pack_out(const uint8_t* __restrict__ src, unsigned stride, unsigned long long V, float* __restrict__ dst)
 {
   const unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v < V)
   {
-    const float4 a = src[v];
-    dst[3 * v] = a.x;
-    dst[3 * v + 1] = a.y;
-    dst[3 * v + 2] = a.z;
+    const float* a = reinterpret_cast<const float*>(src + v * stride);
+    dst[3 * v] = a[0];
+    dst[3 * v + 1] = a[1];
+    dst[3 * v + 2] = a[2];
   }
 }
 
@@ -344,8 +358,11 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
 {
   const int grid = gridFor(c->V, kMomentThreads, kMomentBlocks);
   c->partials.ensure(sizeof(MomentPartial) * (kMomentBlocks + 1));
-  k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz, off_nrm,
-                                                           c->pos.as<float4>(), c->nrm.as<float4>(),
+  // normals stay where they are: the slicer gathers the few it needs straight from the cloud (off_nrm is recorded by
+  // the caller in nrm_base / nrm_stride)
+  (void)off_nrm;
+  k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
+                                                           c->pos.as<float4>(),
                                                            c->partials.as<MomentPartial>(), c->counters.as<unsigned>());
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
@@ -373,7 +390,10 @@ void launchClassify(nb2_context* c)
 void launchSetNormals(nb2_context* c, const float* dev_packed)
 {
   const int grid = static_cast<int>((c->V + 255) / 256);
+  c->nrm.ensure(sizeof(float4) * c->V);
   k_set_normals<<<grid, 256, 0, c->stream>>>(dev_packed, c->V, c->nrm.as<float4>());
+  c->nrm_base = c->nrm.as<uint8_t>();
+  c->nrm_stride = 16;
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
@@ -383,12 +403,14 @@ void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed)
   const int grid = static_cast<int>((c->V + 255) / 256);
   if (xyz_packed)
   {
-    k_pack_out<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, xyz_packed);
+    k_pack_out<<<grid, 256, 0, c->stream>>>(c->pos.as<uint8_t>(), 16u, c->V, xyz_packed);
     ++c->launches;
   }
-  if (nrm_packed)
+  if (nrm_packed && !c->nrm_base)
+    NB2_CUDA(cudaMemsetAsync(nrm_packed, 0, sizeof(float) * 3 * c->V, c->stream));  // a mesh without normals
+  else if (nrm_packed)
   {
-    k_pack_out<<<grid, 256, 0, c->stream>>>(c->nrm.as<float4>(), c->V, nrm_packed);
+    k_pack_out<<<grid, 256, 0, c->stream>>>(c->nrm_base, c->nrm_stride, c->V, nrm_packed);
     ++c->launches;
   }
   NB2_CUDA(cudaGetLastError());

@@ -273,6 +273,9 @@ void launchVertexNormals(nb2_context* c)
   c->csrOff.ensure(sizeof(unsigned) * (V + 1));
   c->csrCursor.ensure(sizeof(unsigned) * (V + 1));
   c->csrAdj.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+  c->nrm.ensure(sizeof(float4) * V);
+  c->nrm_base = c->nrm.as<uint8_t>();  // the computed normals replace whatever the cloud carried
+  c->nrm_stride = 16;
   const uint64_t tiles = (V + 1 + kScanTile - 1) / kScanTile;
   c->scanState.ensure(sizeof(unsigned long long) * (tiles + 1));
 

@@ -1415,8 +1415,8 @@ __global__ void __launch_bounds__(1024)
  * first inserter's attributes are kept by vtkCutter).  The same kernel packs the per-plane segment lengths.
  */
 __global__ void __launch_bounds__(256)
-    k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const float4* __restrict__ nrm,
-                LatticeDev L, const unsigned* __restrict__ planeOff, const unsigned* __restrict__ planeMeta,
+    k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const uint8_t* __restrict__ nrmBase,
+                unsigned nrmStride, LatticeDev L, const unsigned* __restrict__ planeOff, const unsigned* __restrict__ planeMeta,
                 const uint2* __restrict__ prefix, const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen,
                 float* __restrict__ outPos, float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo,
                 uint32_t* __restrict__ outEdgeHi, unsigned* __restrict__ outSegLen, int emitEdges)
@@ -1442,7 +1442,13 @@ __global__ void __launch_bounds__(256)
   // positions and normals of all three vertices are requested together: the two the cut edge needs are only known
   // after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
   const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
-  const float4 nv[3] = { __ldg(nrm + ids[0]), __ldg(nrm + ids[1]), __ldg(nrm + ids[2]) };
+  float4 nv[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+  {
+    const float* q = reinterpret_cast<const float*>(nrmBase + static_cast<size_t>(ids[j]) * nrmStride);
+    nv[j] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+  }
   const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
   double s[3];
 #pragma unroll
@@ -1590,7 +1596,7 @@ void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32
   if (chunks > 65535u)
     fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects too many triangles");
   const dim3 grid(static_cast<unsigned>(nP), chunks > 0 ? chunks : 1u);
-  k_waypoints<<<grid, 256, 0, c->stream>>>(c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm.as<float4>(), L,
+  k_waypoints<<<grid, 256, 0, c->stream>>>(c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm_base, c->nrm_stride, L,
                                            c->planeOff.as<unsigned>(), c->planeMeta.as<unsigned>(),
                                            c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
                                            c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(),

@@ -154,7 +154,11 @@ struct nb2_context
   bool tri_checked = false;  // vertex indices of the resident triangles are known to be < V
   nb2::DevBuf blob;      // staging copy of the interleaved cloud
   nb2::DevBuf pos;       // float4[V]  (x, y, z, unused)
-  nb2::DevBuf nrm;       // float4[V]
+  nb2::DevBuf nrm;       // float4[V], only once normals were computed here or set by the caller
+  // Where the slicer reads vertex normals: the uploaded cloud itself (normal_x of vertex v at nrm_base + v * nrm_stride;
+  // the ingest pass does not copy them) or the SoA array above (stride 16).
+  const uint8_t* nrm_base = nullptr;
+  uint32_t nrm_stride = 0;
   nb2::DevBuf tri;       // uint32[3F]
   // moments / frame
   nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
@@ -256,7 +260,7 @@ void launchEmitHits(nb2_context* c, const LatticeDev& L);
 void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H);
 void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges);
 void launchSetNormals(nb2_context* c, const float* dev_packed);
-void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);
+void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);  // normals from nrm_base / nrm_stride
 void launchVertexNormals(nb2_context* c);
 void launchValidateTriangles(nb2_context* c);
 
