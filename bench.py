@@ -269,8 +269,7 @@ def main():
     prm.download = 0
 
     def device_step():
-        ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
-        r = ctx.plan(prm)
+        r = ctx.plan_mesh_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F, prm)
         counts = (r.n_paths, r.n_segments, r.n_waypoints)
         r.free()
         return counts

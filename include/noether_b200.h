@@ -184,6 +184,9 @@ void nb2_plan_params_default(nb2_plan_params* p);
 
 int nb2_slice(nb2_context* ctx, const nb2_lattice* lattice, uint64_t plane_begin, uint64_t plane_end, nb2_result** out);
 int nb2_plan(nb2_context* ctx, const nb2_plan_params* params, nb2_result** out);
+/* nb2_mesh_upload + nb2_plan in one call: exactly PlaneSlicerRasterPlanner::planImpl(mesh)
+ * (plane_slicer_raster_planner.cpp:518-631), what the plugin's planImpl binds. */
+int nb2_plan_mesh(nb2_context* ctx, const nb2_mesh_view* mesh, const nb2_plan_params* params, nb2_result** out);
 /* Lattice used by the last nb2_plan on this context. */
 int nb2_last_lattice(const nb2_context* ctx, nb2_lattice* out);
 

@@ -329,8 +329,12 @@ nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
 
 /**
  * planImpl's plane loop on the device.  The lattice comes either from the device-side construction (`fp`: PCA axes,
- * generators and lattice arithmetic run as single-thread kernels, no host round trip) or from the caller
- * (`explicit_lat`, nb2_slice).  One synchronisation mid-way — the hit count sizes the buckets — and one at the end.
+ * generators and lattice arithmetic run as single-thread kernels) or from the caller (`explicit_lat`, nb2_slice).
+ *
+ * Every kernel reads the sizes it depends on (plane count, hit count, largest plane) from device memory, so the whole
+ * plan is enqueued without waiting for any of them: the buffers behind the hit count are sized from the capacities of
+ * the previous plan on this context, and a kernel that finds a capacity too small writes nothing and raises a flag, on
+ * which the host grows the buffers and repeats that stage.  Only the first plan of a context waits for its hit count.
  */
 nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* explicit_lat, uint64_t plane_begin,
                       uint64_t plane_end, bool emit_edges, bool download = true)
@@ -344,13 +348,45 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   c->hostSmall.ensure(8192 + sizeof(FrameDev));
   auto* hf = c->hostSmall.as<FrameDev>();
   unsigned* h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
-  for (int attempt = 0;; ++attempt)
-  {
-    // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
-    //           [12] largest out-of-range vertex index
+  // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
+  //           [12] largest out-of-range vertex index, [13] capacity overflow bits
+  auto resetCounters = [&](int first) {
     unsigned init[16] = { 0 };
     init[11] = 0xffffffffu;
-    NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + 4, init + 4, 12 * sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + first, init + first, (16 - first) * sizeof(unsigned),
+                             cudaMemcpyHostToDevice, c->stream));
+  };
+  auto readSizes = [&]() {
+    NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+  };
+  const unsigned smem_cap = linkSmemHitCap(c);
+  auto setCapacities = [&](uint64_t H, uint32_t n_max) {
+    c->hit_cap = H + H / 4 + 1024;
+    c->scratch_hits = n_max > smem_cap ? n_max + n_max / 4 : 0u;
+    c->grid_nmax = n_max;
+  };
+  auto stageTwo = [&]() {
+    const uint64_t cap = c->hit_cap, w_cap = 2 * cap;
+    c->hitRec.ensure(sizeof(float4) * 2 * cap);
+    c->outPos.ensure(sizeof(float) * 3 * w_cap);
+    c->outNrm.ensure(sizeof(float) * 3 * w_cap);
+    if (emit_edges)
+      c->outEdge.ensure(sizeof(uint32_t) * 2 * w_cap);
+    c->outSegLen.ensure(sizeof(unsigned) * cap);
+    launchEmitHits(c, cap);
+    c->timer.mark("emit", c->stream);
+    launchLinkPlanes(c, cap, c->scratch_hits);
+    c->timer.mark("link", c->stream);
+    launchWaypoints(c, w_cap, emit_edges ? 1 : 0);
+    c->timer.mark("waypoints", c->stream);
+  };
+
+  bool sizes_known = false;
+  for (int attempt = 0;; ++attempt)
+  {
+    resetCounters(4);
     if (fp)
     {
       FrameParams p = *fp;
@@ -367,9 +403,24 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     launchScanPlanes(c);
     c->timer.mark("scan", c->stream);
 
-    NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
-    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 9 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    NB2_CUDA(cudaStreamSynchronize(c->stream));
+    sizes_known = false;
+    if (c->hit_cap == 0)
+    {
+      // first plan on this context: nothing to size the buffers from, wait for the hit count
+      readSizes();
+      sizes_known = true;
+      if (!hf->plane_cap_exceeded && hf->lattice_status == 0)
+      {
+        setCapacities(h[0], h[1]);
+        c->grid_planes = static_cast<uint32_t>(hf->L.plane_end - hf->L.plane_begin);
+      }
+    }
+    if (!sizes_known || (c->hit_cap && !hf->plane_cap_exceeded && hf->lattice_status == 0 && h[0] > 0))
+    {
+      stageTwo();
+      readSizes();
+      sizes_known = true;
+    }
     deferredMeshChecks(c, *hf);
     if (hf->lattice_status != 0)
       fail(NB2_ERR_INVALID_ARGUMENT, latticeErrorMessage(hf->lattice_status));
@@ -380,7 +431,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     unsigned cap = c->plane_cap;
     while (cap < hf->planes_wanted)
       cap *= 2;
-    c->plane_cap = cap;  // grow and run the three kernels again
+    c->plane_cap = cap;  // grow and run the plan again
   }
   if (hf->have_scales)
   {
@@ -396,6 +447,8 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
 
   const uint64_t H = h[0];
   const uint32_t n_max = h[1];
+  c->grid_planes = static_cast<uint32_t>(nP);  // launch geometry hints for the next plan
+  c->grid_nmax = n_max;
   if (c->F && h[8] >= c->V)  // counters[12]: largest out-of-range vertex index met by k_count_hits
     fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[8]) + " but the cloud has " +
                                        std::to_string(c->V) + " points");
@@ -416,32 +469,28 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     fail(NB2_ERR_INVALID_ARGUMENT, "more than 2^30 triangle/plane intersections in one slab; shard the plan");
   if (n_max >= (1u << 19))
     fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects 2^19 or more triangles; not supported");
+  if (h[9])  // counters[13]: a capacity did not suffice; the kernels left the buffers alone
+  {
+    setCapacities(H, n_max);
+    NB2_CUDA(cudaMemsetAsync(c->planeCursor.ptr, 0, sizeof(unsigned) * (static_cast<size_t>(c->plane_cap) + 1), c->stream));
+    resetCounters(6);
+    stageTwo();
+    readSizes();
+    if (h[9])
+      fail(NB2_ERR_INTERNAL, "buffer capacities could not be settled");
+  }
+  const uint64_t w_cap = 2 * c->hit_cap;
 
-  c->hitRec.ensure(sizeof(float4) * 2 * H);
-  launchEmitHits(c, L);
-  c->timer.mark("emit", c->stream);
-
-  const uint64_t w_cap = 2 * H, s_cap = H;
-  c->outPos.ensure(sizeof(float) * 3 * w_cap);
-  c->outNrm.ensure(sizeof(float) * 3 * w_cap);
-  if (emit_edges)
-    c->outEdge.ensure(sizeof(uint32_t) * 2 * w_cap);
-  c->outSegLen.ensure(sizeof(unsigned) * s_cap);
-  launchLinkPlanes(c, L, n_max, H);
-  c->timer.mark("link", c->stream);
-  launchWaypoints(c, L, w_cap, n_max, emit_edges ? 1 : 0);
-  c->timer.mark("waypoints", c->stream);
-
-  // totals, per-plane meta and status
+  // per-plane meta and status
   c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * nP);
   h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
-  unsigned* hstat = h + 2;
+  // (h[2..3] = counters[6..7] = waypoint / segment totals, h[6..7] = counters[10..11] = link status; re-read: the
+  //  staging area may have moved)
   unsigned* hmeta = h + 16;
-  // counters[6..7] = waypoint / segment totals (k_scan_meta), counters[10..11] = link status
-  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 6, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  NB2_CUDA(cudaMemcpyAsync(hstat, c->counters.as<unsigned>() + 10, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  const unsigned* hstat = h + 6;
   if (hstat[0])
   {
     const std::string where = " (lattice plane " + std::to_string(plane_begin + hstat[1]) + ")";
@@ -452,8 +501,8 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
                                 "not a DAG)" + where);
     fail(NB2_ERR_INTERNAL, "linking failed" + where);
   }
-  const uint64_t Wt = h[0];
-  const uint64_t St = h[1];
+  const uint64_t Wt = h[2];
+  const uint64_t St = h[3];
   uint64_t Pn = 0;
   for (uint64_t k = 0; k < nP; ++k)
     Pn += hmeta[2 * k + 1] > 0;
@@ -939,6 +988,14 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   }
   *out = r;
   NB2_API_END
+}
+
+int nb2_plan_mesh(nb2_context* c, const nb2_mesh_view* mesh, const nb2_plan_params* prm, nb2_result** out)
+{
+  if (out)
+    *out = nullptr;
+  const int rc = nb2_mesh_upload(c, mesh);
+  return rc != NB2_OK ? rc : nb2_plan(c, prm, out);
 }
 
 int nb2_last_lattice(const nb2_context* c, nb2_lattice* out)

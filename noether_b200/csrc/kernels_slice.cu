@@ -214,10 +214,20 @@ constexpr int kEmitList = 2048;  // hits contoured per round of a tile
 
 __global__ void __launch_bounds__(kEmitThreads, 4)
     k_emit_hits(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK,
-                const float4* __restrict__ pos, LatticeDev L, const unsigned* __restrict__ planeOff,
-                unsigned* __restrict__ cursor, float4* __restrict__ rec, int aligned)
+                const float4* __restrict__ pos, const FrameDev* __restrict__ frame, const unsigned* __restrict__ planeOff,
+                unsigned* __restrict__ cursor, float4* __restrict__ rec, int aligned, const unsigned* __restrict__ hits,
+                unsigned long long hitCap, unsigned* __restrict__ overflow)
 {
   __shared__ uint2 s_list[kEmitList];  // {triangle, slab-local plane}
+  // The buffers were sized before the hit count was known (from the previous plan on this context): when this plan
+  // has more hits than they hold, nothing is written; the host sees the flag, grows the buffers and repeats the stage.
+  if (*hits > hitCap)
+  {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      atomicOr(overflow, 1u);
+    return;
+  }
+  const LatticeDev L = frame->L;
   __shared__ unsigned s_warp[kEmitThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long Q = (F + 3) / 4;
@@ -326,7 +336,8 @@ struct LinkParams
 {
   const float4* rec;  // [2 * H] endpoint records {x, y, z, rank bits}, grouped by plane (k_emit_hits)
   const unsigned* planeOff;
-  LatticeDev L;
+  const FrameDev* frame;  // the lattice lives in device memory (no host round trip before this kernel)
+  LatticeDev L;           // ... and is copied here by the kernel
   unsigned* ticket;
   unsigned* planeMeta;  // [2 * nP] waypoints, segments of each plane
   // A plane with n hits yields at most 2 n waypoints and n segments, so plane k writes its waypoint ranks at
@@ -337,7 +348,9 @@ struct LinkParams
   unsigned* status;  // [0] error bits, [1] first failing plane
   uint8_t* scratch;  // global work areas for planes that do not fit shared memory
   unsigned long long scratchStride;
-  unsigned smemHitCap;  // largest plane (in hits) that fits the shared-memory work area
+  unsigned smemHitCap;   // largest plane (in hits) that fits the shared-memory work area
+  unsigned scratchHits;  // largest plane the global work areas were sized for
+  unsigned* overflow;    // bit 0: hit buffers too small (k_emit_hits), bit 1: a plane exceeds scratchHits
 };
 
 constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u;
@@ -1281,11 +1294,15 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   return true;
 }
 
-__global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
+__global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ unsigned s_misc[kMiscWords];
   __shared__ unsigned s_ticket;
+  if (*Pin.overflow & 1u)
+    return;  // k_emit_hits wrote nothing
+  LinkParams P = Pin;
+  P.L = Pin.frame->L;
   const long long nP = P.L.plane_end - P.L.plane_begin;
 
   while (true)
@@ -1302,6 +1319,16 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
     {
       if (threadIdx.x == 0)
         P.planeMeta[2 * kLocal] = P.planeMeta[2 * kLocal + 1] = 0u;
+      continue;
+    }
+    if (n > P.smemHitCap && n > P.scratchHits)
+    {
+      // larger than the global work areas were sized for: same protocol as the hit buffers
+      if (threadIdx.x == 0)
+      {
+        atomicOr(P.overflow, 2u);
+        P.planeMeta[2 * kLocal] = P.planeMeta[2 * kLocal + 1] = 0u;
+      }
       continue;
     }
     const unsigned E = 2 * n;
@@ -1349,8 +1376,10 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams P)
 /** Exclusive prefix of the per-plane waypoint and segment counts (one block; nP is at most a few thousand).
  *  prefix[k] = {waypoints, segments} before plane k; prefix[nP] = totals, also written to totals[0..1]. */
 __global__ void __launch_bounds__(1024)
-    k_scan_meta(const unsigned* __restrict__ planeMeta, long long nP, uint2* __restrict__ prefix, unsigned* __restrict__ totals)
+    k_scan_meta(const unsigned* __restrict__ planeMeta, const FrameDev* __restrict__ frame, uint2* __restrict__ prefix,
+                unsigned* __restrict__ totals)
 {
+  const long long nP = frame->L.plane_end - frame->L.plane_begin;
   __shared__ uint2 s_warp[32];
   __shared__ uint2 s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1414,57 +1443,69 @@ __global__ void __launch_bounds__(1024)
  * merged on — and interpolate the vertex normals along the cut edge (vtkDataSetAttributes::InterpolateEdge; only the
  * first inserter's attributes are kept by vtkCutter).  The same kernel packs the per-plane segment lengths.
  */
+constexpr unsigned kWpChunk = 1024u;  // waypoints per block and chunk (four per thread)
+
 __global__ void __launch_bounds__(256)
     k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const uint8_t* __restrict__ nrmBase,
-                unsigned nrmStride, LatticeDev L, const unsigned* __restrict__ planeOff, const unsigned* __restrict__ planeMeta,
-                const uint2* __restrict__ prefix, const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen,
-                float* __restrict__ outPos, float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo,
-                uint32_t* __restrict__ outEdgeHi, unsigned* __restrict__ outSegLen, int emitEdges)
+                unsigned nrmStride, const FrameDev* __restrict__ frame, const unsigned* __restrict__ sizes,
+                const unsigned* __restrict__ overflow, const unsigned* __restrict__ planeOff,
+                const unsigned* __restrict__ planeMeta, const uint2* __restrict__ prefix,
+                const unsigned* __restrict__ wpTag, const unsigned* __restrict__ segLen, float* __restrict__ outPos,
+                float* __restrict__ outNrm, uint32_t* __restrict__ outEdgeLo, uint32_t* __restrict__ outEdgeHi,
+                unsigned* __restrict__ outSegLen, int emitEdges)
 {
-  const unsigned k = blockIdx.x;
-  const unsigned Wk = __ldg(planeMeta + 2 * k);
-  const unsigned local = blockIdx.y * blockDim.x + threadIdx.x;
-  if (blockIdx.y * blockDim.x >= Wk)
+  if (*overflow)
     return;
-  const unsigned off = __ldg(planeOff + k);
-  const uint2 before = __ldg(prefix + k);
+  const LatticeDev L = frame->L;
+  const unsigned nP = static_cast<unsigned>(L.plane_end - L.plane_begin);
+  // blockIdx.x walks the planes, blockIdx.y the chunks of kWpChunk waypoints of a plane (at most 2 n_max waypoints;
+  // sizes[1] = n_max).  The grid was sized from the previous plan, so both loops normally run once; they cover any
+  // other size too.  A thread takes kWpChunk / 256 waypoints one after the other, which amortises the block's start-up
+  // (the lattice constants come from device memory).
+  const unsigned chunks = (2u * sizes[1] + kWpChunk - 1u) / kWpChunk;
+  for (unsigned k = blockIdx.x; k < nP; k += gridDim.x)
   {
+    const unsigned Wk = __ldg(planeMeta + 2 * k);
     const unsigned Sk = __ldg(planeMeta + 2 * k + 1);
-    if (local < Sk)
-      outSegLen[before.y + local] = __ldg(segLen + off + local);
-  }
-  if (local >= Wk)
-    return;
-  const unsigned long long i = static_cast<unsigned long long>(before.x) + local;
-  const unsigned tg = __ldg(wpTag + 2ull * off + local);
-  const unsigned t = tg >> 1;
-  const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
-  // positions and normals of all three vertices are requested together: the two the cut edge needs are only known
-  // after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
-  const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
-  float4 nv[3];
+    const unsigned off = __ldg(planeOff + k);
+    const uint2 before = __ldg(prefix + k);
+    const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
+    for (unsigned ci = blockIdx.y; ci < chunks && ci * kWpChunk < Wk; ci += gridDim.y)
+      for (unsigned local = ci * kWpChunk + threadIdx.x; local < min(Wk, (ci + 1u) * kWpChunk); local += 256u)
+      {
+        if (local < Sk)
+          outSegLen[before.y + local] = __ldg(segLen + off + local);
+        const unsigned long long i = static_cast<unsigned long long>(before.x) + local;
+        const unsigned tg = __ldg(wpTag + 2ull * off + local);
+        const unsigned t = tg >> 1;
+        const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
+        // positions and normals of all three vertices are requested together: the two the cut edge needs are only
+        // known after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
+        const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
+        float4 nv[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
-  {
-    const float* q = reinterpret_cast<const float*>(nrmBase + static_cast<size_t>(ids[j]) * nrmStride);
-    nv[j] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
-  }
-  const PlaneOrigin org = planeOrigin(L, L.plane_begin + static_cast<long long>(k));
-  double s[3];
+        for (int j = 0; j < 3; ++j)
+        {
+          const float* q = reinterpret_cast<const float*>(nrmBase + static_cast<size_t>(ids[j]) * nrmStride);
+          nv[j] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+        }
+        double s[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
-    s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
-  const CutPoint c = interpolateCut(contourCase(s), tg & 1u, ids, p, s, nv);
-  outPos[3 * i] = c.x;
-  outPos[3 * i + 1] = c.y;
-  outPos[3 * i + 2] = c.z;
-  outNrm[3 * i] = c.nx;
-  outNrm[3 * i + 1] = c.ny;
-  outNrm[3 * i + 2] = c.nz;
-  if (emitEdges)
-  {
-    outEdgeLo[i] = c.lo;
-    outEdgeHi[i] = c.hi;
+        for (int j = 0; j < 3; ++j)
+          s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+        const CutPoint c = interpolateCut(contourCase(s), tg & 1u, ids, p, s, nv);
+        outPos[3 * i] = c.x;
+        outPos[3 * i + 1] = c.y;
+        outPos[3 * i + 2] = c.z;
+        outNrm[3 * i] = c.nx;
+        outNrm[3 * i + 1] = c.ny;
+        outNrm[3 * i + 2] = c.nz;
+        if (emitEdges)
+        {
+          outEdgeLo[i] = c.lo;
+          outEdgeHi[i] = c.hi;
+        }
+      }
   }
 }
 
@@ -1518,56 +1559,59 @@ void launchScanPlanes(nb2_context* c)
   ++c->launches;
 }
 
-void launchEmitHits(nb2_context* c, const LatticeDev& L)
+// The kernels after the hit count read every size they need from device memory (FrameDev, counters), so the host can
+// enqueue them without waiting for the count: buffers are sized from capacities (hit_cap hits, scratch_hits hits per
+// plane for planes that miss shared memory) and the kernels raise counters[13] when a capacity does not suffice.
+void launchEmitHits(nb2_context* c, uint64_t hit_cap)
 {
   const int grid = gridFor((c->F + 3) / 4, kEmitThreads, c->sm_count * 8);
   const int aligned = (reinterpret_cast<uintptr_t>(c->tri.ptr) & 15u) == 0 ? 1 : 0;
-  k_emit_hits<<<grid, kEmitThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->vertK.as<int>(), c->pos.as<float4>(), L,
-                                                     c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
-                                                     c->hitRec.as<float4>(), aligned);
+  k_emit_hits<<<grid, kEmitThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->vertK.as<int>(), c->pos.as<float4>(),
+                                                     c->frame.as<FrameDev>(), c->planeOff.as<unsigned>(),
+                                                     c->planeCursor.as<unsigned>(), c->hitRec.as<float4>(), aligned,
+                                                     c->counters.as<unsigned>() + 4, hit_cap,
+                                                     c->counters.as<unsigned>() + 13);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H)
+unsigned linkSmemHitCap(const nb2_context* c)
 {
-  const long long nP = L.plane_end - L.plane_begin;
   // largest plane that fits the opt-in shared memory (uint16 indices additionally need 2 n < 65535)
   const size_t smem_budget = c->smem_optin > 1024 ? c->smem_optin - 1024 : 0;
-  unsigned hit_cap = 0;
+  unsigned lo = 0, hi = 32767;
+  while (lo < hi)
   {
-    unsigned lo = 0, hi = 32767;  // uint16 indices need 2 n < 65535
-    while (lo < hi)
-    {
-      const unsigned mid = (lo + hi + 1) / 2;
-      if (smemWorkBytes(mid) <= smem_budget)
-        lo = mid;
-      else
-        hi = mid - 1;
-    }
-    hit_cap = lo;
+    const unsigned mid = (lo + hi + 1) / 2;
+    if (smemWorkBytes(mid) <= smem_budget)
+      lo = mid;
+    else
+      hi = mid - 1;
   }
-  const unsigned smem_hits = n_max < hit_cap ? n_max : hit_cap;
-  const size_t smem_bytes = smemWorkBytes(smem_hits > 0 ? smem_hits : 1);
+  return lo;
+}
 
-  int grid = c->sm_count;
-  if (grid > nP)
-    grid = static_cast<int>(nP > 0 ? nP : 1);
+void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits)
+{
+  const unsigned smem_cap = linkSmemHitCap(c);
+  const size_t smem_bytes = smemWorkBytes(smem_cap > 0 ? smem_cap : 1);
+  const int grid = c->sm_count;
   size_t stride = 0;
-  if (n_max > hit_cap)
+  if (scratch_hits > smem_cap)
   {
-    stride = (globalWorkBytes(n_max) + 255) & ~size_t(255);
+    stride = (globalWorkBytes(scratch_hits) + 255) & ~size_t(255);
     c->linkScratch.ensure(stride * grid);
   }
-  c->planeMeta.ensure(sizeof(unsigned) * 2 * (nP + 1));
-  c->planePrefix.ensure(sizeof(uint2) * (nP + 1));
-  c->wpTag.ensure(sizeof(unsigned) * 2 * H);
-  c->segLen.ensure(sizeof(unsigned) * H);
+  const size_t planes = static_cast<size_t>(c->plane_cap) + 1;
+  c->planeMeta.ensure(sizeof(unsigned) * 2 * planes);
+  c->planePrefix.ensure(sizeof(uint2) * planes);
+  c->wpTag.ensure(sizeof(unsigned) * 2 * hit_cap);
+  c->segLen.ensure(sizeof(unsigned) * hit_cap);
 
   LinkParams P{};
   P.rec = c->hitRec.as<float4>();
   P.planeOff = c->planeOff.as<unsigned>();
-  P.L = L;
+  P.frame = c->frame.as<FrameDev>();
   P.ticket = c->counters.as<unsigned>() + 8;
   P.planeMeta = c->planeMeta.as<unsigned>();
   P.wpTag = c->wpTag.as<unsigned>();
@@ -1575,32 +1619,33 @@ void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint6
   P.status = c->counters.as<unsigned>() + 10;
   P.scratch = c->linkScratch.as<uint8_t>();
   P.scratchStride = stride;
-  P.smemHitCap = hit_cap;
+  P.smemHitCap = smem_cap;
+  P.scratchHits = scratch_hits > smem_cap ? scratch_hits : 0u;
+  P.overflow = c->counters.as<unsigned>() + 13;
 
   NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   k_link_planes<<<grid, kLinkThreads, smem_bytes, c->stream>>>(P);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
   // totals land in counters[6..7]
-  k_scan_meta<<<1, 1024, 0, c->stream>>>(c->planeMeta.as<unsigned>(), nP, c->planePrefix.as<uint2>(),
+  k_scan_meta<<<1, 1024, 0, c->stream>>>(c->planeMeta.as<unsigned>(), c->frame.as<FrameDev>(), c->planePrefix.as<uint2>(),
                                          c->counters.as<unsigned>() + 6);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges)
+void launchWaypoints(nb2_context* c, uint64_t w_cap, int emit_edges)
 {
-  // per-plane counts are only known on the device: cover the 2 n_max waypoints the largest plane could have
-  const long long nP = L.plane_end - L.plane_begin;
-  const unsigned chunks = (2u * n_max + 255u) / 256u;
-  if (chunks > 65535u)
-    fail(NB2_ERR_INVALID_ARGUMENT, "a single cutting plane intersects too many triangles");
-  const dim3 grid(static_cast<unsigned>(nP), chunks > 0 ? chunks : 1u);
-  k_waypoints<<<grid, 256, 0, c->stream>>>(c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm_base, c->nrm_stride, L,
-                                           c->planeOff.as<unsigned>(), c->planeMeta.as<unsigned>(),
-                                           c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
-                                           c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(),
-                                           c->outEdge.as<uint32_t>() + w_cap, c->outSegLen.as<unsigned>(), emit_edges);
+  // grid from the sizes of the previous plan on this context (the kernel loops when this plan is larger)
+  unsigned gx = c->grid_planes ? c->grid_planes : 1024u, gy = (2u * c->grid_nmax + kWpChunk - 1u) / kWpChunk;
+  gx = std::min(gx, 1u << 20);
+  gy = std::max(1u, std::min(gy, 4096u));
+  k_waypoints<<<dim3(gx, gy), 256, 0, c->stream>>>(
+      c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm_base, c->nrm_stride, c->frame.as<FrameDev>(),
+      c->counters.as<unsigned>() + 4, c->counters.as<unsigned>() + 13, c->planeOff.as<unsigned>(),
+      c->planeMeta.as<unsigned>(), c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
+      c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(), c->outEdge.as<uint32_t>() + w_cap,
+      c->outSegLen.as<unsigned>(), emit_edges);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -170,6 +170,10 @@ struct nb2_context
   bool pca_valid = false;       // host copy below is current
   nb2_pca pca{};
   unsigned plane_cap = 1u << 16;
+  // capacities the post-count stage was last sized for (0 = not yet known: the first plan waits for its hit count)
+  uint64_t hit_cap = 0;      // hits (triangle x plane)
+  uint32_t scratch_hits = 0; // hits of the largest plane, when it exceeds what fits shared memory
+  uint32_t grid_planes = 0, grid_nmax = 0;  // planes / largest plane of the last plan: launch geometry of k_waypoints
   // slicing workspace
   nb2::DevBuf vertK;       // int32[V]
   nb2::DevBuf planeCnt;    // uint32[P + 1]
@@ -256,9 +260,10 @@ void launchExtents(nb2_context* c);
 void launchClassify(nb2_context* c);
 void launchCountHits(nb2_context* c);
 void launchScanPlanes(nb2_context* c);  // writes {H, n_max} to counters[4..5]
-void launchEmitHits(nb2_context* c, const LatticeDev& L);
-void launchLinkPlanes(nb2_context* c, const LatticeDev& L, uint32_t n_max, uint64_t H);
-void launchWaypoints(nb2_context* c, const LatticeDev& L, uint64_t w_cap, uint32_t n_max, int emit_edges);
+void launchEmitHits(nb2_context* c, uint64_t hit_cap);
+unsigned linkSmemHitCap(const nb2_context* c);
+void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits);
+void launchWaypoints(nb2_context* c, uint64_t w_cap, int emit_edges);
 void launchSetNormals(nb2_context* c, const float* dev_packed);
 void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);  // normals from nrm_base / nrm_stride
 void launchVertexNormals(nb2_context* c);

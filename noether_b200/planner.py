@@ -102,6 +102,15 @@ class Context:
         _capi.check(self._lib.nb2_plan(self._h, C.byref(params), C.byref(r)))
         return ToolPaths(self, r)
 
+    def plan_mesh_raw(self, data_ptr: int, n_vertices: int, point_step: int, off_xyz: int, off_normal: int,
+                      tri_ptr: int, n_triangles: int, params: _capi.PlanParams) -> "ToolPaths":
+        """nb2_plan_mesh: upload (or adopt, for device pointers) and plan in one call — planImpl(mesh)."""
+        self._mesh_key = None
+        mv = _capi.MeshView(data_ptr, n_vertices, point_step, off_xyz, off_normal, 0, tri_ptr, n_triangles)
+        r = C.c_void_p()
+        _capi.check(self._lib.nb2_plan_mesh(self._h, C.byref(mv), C.byref(params), C.byref(r)))
+        return ToolPaths(self, r)
+
     def slice(self, lattice: _capi.Lattice, plane_begin: int = 0, plane_end: int | None = None) -> "ToolPaths":
         r = C.c_void_p()
         pe = _capi.NB2_ALL_PLANES if plane_end is None else plane_end

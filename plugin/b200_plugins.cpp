@@ -294,9 +294,9 @@ protected:
 
     Device& dev = Device::instance();
     std::lock_guard<std::mutex> lock(dev.mutex());
-    upload(dev.ctx(), mesh, true);
+    const MeshView m = makeView(mesh, true);
     nb2_result* r = nullptr;
-    Device::check(nb2_plan(dev.ctx(), &prm, &r));
+    Device::check(nb2_plan_mesh(dev.ctx(), &m.view, &prm, &r));
     std::unique_ptr<nb2_result, void (*)(nb2_result*)> guard(r, nb2_result_free);
     return toToolPaths(r);
   }

@@ -44,11 +44,10 @@ def main():
     prm.download = 0
 
     def step():
-        ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
-        r = ctx.plan(prm)
+        r = ctx.plan_mesh_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F, prm)
         n = (r.n_paths, r.n_segments, r.n_waypoints)
         r.free()
-        return ctx.timings(), n
+        return n
 
     flush = torch.empty(256 * 2**20, dtype=torch.uint8, device=dev)
     for _ in range(2):
@@ -57,8 +56,9 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     ctx.timer_start()
-    st, n = step()
+    n = step()
     total = ctx.timer_stop()
+    st = ctx.timings()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     print(name, desc)
