@@ -137,10 +137,24 @@ def cpu_reference_sample(xyz, nrm, tri, spacing, n_planes: int):
             "tri_per_s": tri.shape[0] / t_full}
 
 
+def ncu_traffic(workload: str, stage: str):
+    """DRAM bytes per launch of the stage's kernel from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic_<workload>.json, written by tools/ncu_summary.py), or None."""
+    kernel = {"ingest+moments": "k_ingest_moments", "extents": "k_extents", "classify": "k_classify", "count": "k_count_hits",
+              "scan": "k_scan_planes", "emit": "k_emit_hits", "link": "k_link_planes", "waypoints": "k_waypoints",
+              "frame": "k_frame_pca", "lattice": "k_frame_lattice"}.get(stage)
+    path = os.path.join(ROOT, "profiles", f"ncu_traffic_{workload}.json")
+    if kernel is None or not os.path.exists(path):
+        return None
+    with open(path) as f:
+        entry = json.load(f).get(kernel)
+    return entry["dram_bytes_per_launch"] if entry else None
+
+
 def algorithmic_bytes(stage: str, V: int, F: int, H: int, W: int, S: int, P: int, point_step: int) -> float | None:
     """Compulsory bytes of each kernel: what it must read and write once."""
     table = {
-        "ingest+moments": 24 * V + 24 * V,       # xyz + normal in, xyz + normal out (the blob's other fields are not needed)
+        "ingest+moments": 12 * V + 16 * V,       # xyz in, float4 position out (normals are gathered in place later)
         "validate": 12 * F,
         "extents": 12 * V,
         "classify": 12 * V + 4 * V,
@@ -356,7 +370,7 @@ def main():
     P_planes = int(lat.num_planes)
     n_paths, n_segments, n_waypoints = totals if info.world == 1 else totals
     stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
-    kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h", "setup")}
+    kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h", "setup", "validate")}
     dominant = max(kernel_stages, key=kernel_stages.get)
     # per-rank quantities for the dominant kernel's launch on this rank
     W_rank, S_rank = counts[2], counts[1]
@@ -365,7 +379,8 @@ def main():
     achieved = (B / 1e9) / (kernel_stages[dominant] / 1e3) if B else None
     B_plan = 12 * F + 24 * V + 24 * n_waypoints + 4 * (n_segments + 1) + 4 * (n_paths + 1)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": ncu_traffic(args.workload, dominant) if info.world == 1 else None,
                 "algorithmic_bytes_per_launch": B, "launch_ms": kernel_stages[dominant], "peak_source": peak_src,
                 "stage_ms": stage_ms,
                 "plan": {"algorithmic_bytes": B_plan, "achieved": (B_plan / 1e9) / (ms_per_step / 1e3),
