@@ -174,7 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-planes", type=int, default=24, help="lattice planes sampled by the CPU baseline")
+    ap.add_argument("--cpu-planes", type=int, default=160,
+                    help="lattice planes sampled by the CPU baseline (cfg3: about 76 ms each => ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything libraries print meanwhile (NCCL's version banner, ...) goes to stderr
@@ -204,7 +205,7 @@ def main():
         import oracle as orc
         orc.build()
         nrm = orc.normals_from_mesh_faces(xyz, tri)
-        per_step = max(2, args.cpu_planes // 3)
+        per_step = max(2, args.cpu_planes // 2)  # cfg3: 80 planes x 76 ms = ~6 s of single-thread work per step
         for _ in range(args.warmup):
             cpu_reference_sample(xyz, nrm, tri, spacing, 2)
         t0 = time.perf_counter()
