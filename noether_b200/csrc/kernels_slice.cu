@@ -11,11 +11,15 @@
 //                        points (float32 position + first-inserter rank) are appended to the plane's bucket
 //   S5  k_link_planes  : one persistent CTA per plane, shared memory only: merge cut points exactly as vtkMergePoints
 //                        does (float-coordinate equality, shared-memory hash), pair the lines at shared points, rank
-//                        the chains by pointer jumping, orient and order them, size the output through a decoupled
-//                        look-back across planes, and write, per output waypoint, the rank (triangle, line end) of the
-//                        cut point that inserted it first
+//                        the chains (Helman-JaJa list ranking), orient and order them, and write, per output
+//                        waypoint, the rank (triangle, line end) of the cut point that inserted it first — into a
+//                        window of the output that belongs to the plane alone, so no plane waits for another one
+//   S5b k_scan_meta    : exclusive prefix of the per-plane waypoint / segment counts
 //   S6  k_waypoints    : one thread per output waypoint: re-contour the first inserter, interpolate the vertex normals
-//                        along the cut edge, write position / normal / generating mesh edge
+//                        along the cut edge, write packed position / normal / generating mesh edge
+//
+// Every kernel from S2 on reads the lattice, the plane count and the hit count from device memory, so a plan is enqueued
+// without the host waiting for any of them.
 //
 // Output of S6 is the reference's planImpl result before convertToPoses expands it to 4x4 matrices.
 #include "device_math.cuh"
