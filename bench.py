@@ -59,12 +59,14 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index  # index, comma-separated list of indices, or None (this rank does not sample)
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False) if gpu_index is not None else None
         self.proc = None
 
     def start(self):
+        if self.gpu is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=self.file, stderr=subprocess.DEVNULL)
@@ -72,6 +74,8 @@ class ClockSampler:
             self.proc = None
 
     def stop(self) -> dict:
+        if self.gpu is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampled by rank 0"]}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -314,7 +318,9 @@ def main():
     # ---- value: device-resident ------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         device_step()
-    sampler = ClockSampler(info.local_rank)
+    # one sampler for the whole job (rank 0 polls every GPU of the job): a poller per rank makes eight nvidia-smi
+    # processes contend for the driver with the ranks they are supposed to observe
+    sampler = ClockSampler(",".join(str(i) for i in range(info.world)) if info.rank == 0 else None)
     stage_acc: dict[str, list[float]] = {}
     launches0 = ctx.kernel_launches()
     # L2 is flushed between timed iterations (a 256 MB write, outside the timed intervals): exactly K steps are timed,

@@ -520,3 +520,83 @@ def test_cfg5_share_of_the_mesh_batch(ctx, orc):
             assert bytes(lat_o) == bytes(lat)
             assert_same_paths(gpu, paths.flat(), f"cfg5 mesh {k}", poses=False)
         gpu.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# randomised parity: many small meshes, every knob drawn at random, GPU against the oracle bit for bit
+# ---------------------------------------------------------------------------------------------------------------------
+def _fuzz_case(seed, orc, big=False):
+    from noether_b200 import meshes
+    rng = np.random.default_rng(1000 + seed)
+    # small meshes: planes of a few dozen hits (the linker's general path); big ones: hundreds per plane (its fast path)
+    nx, ny = (int(rng.integers(120, 380)), int(rng.integers(120, 380))) if big else (int(rng.integers(6, 70)), int(rng.integers(6, 70)))
+    lx, ly = float(rng.uniform(0.3, 2.0)), float(rng.uniform(0.3, 2.0))
+    if abs(lx - ly) < 0.1:
+        lx += 0.25  # keep the in-plane principal axes distinguishable
+    xyz, tri = meshes.wavy(nx, ny, lx=lx, ly=ly, amp=float(rng.uniform(0.0, 0.08)), lam=float(rng.uniform(0.2, 1.5)))
+    if rng.random() < 0.5:
+        xyz, tri = meshes.cut_hole(xyz, tri, centre_frac=(rng.uniform(0.3, 0.7), rng.uniform(0.3, 0.7)),
+                                   radius_frac=float(rng.uniform(0.08, 0.3)))
+    aligned = rng.random() < 0.25  # lattice planes through whole rows of vertices: vertex hits, in-plane edges
+    if not aligned and rng.random() < 0.7:
+        T = np.eye(4)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        T[:3, 3] = rng.uniform(-3, 3, size=3)
+        xyz = meshes.rigid_transform(xyz, T)
+    nrm = orc.normals_from_mesh_faces(xyz, tri)
+    if rng.random() < 0.5:
+        xyz, tri, nrm = meshes.permute(xyz, tri, seed=int(rng.integers(1 << 30)), normals=nrm)
+    layout = ["PointNormal", "NormalsFirst", "Packed24"][int(rng.integers(3))]
+    kw = dict(bidirectional=bool(rng.random() < 0.8))
+    if aligned:
+        # z == 0 would make the PCA normal ill-defined; keep the waves, cut along y through vertex columns
+        kw.update(direction=[0.0, 1.0, 0.0], origin=[float(xyz[:, 0].min()), 0.0, 0.0],
+                  spacing=float(np.float32(lx / nx)) * int(rng.integers(1, 4)))
+    else:
+        kw["spacing"] = float(rng.uniform(0.6, 6.0) * min(lx / nx, ly / ny) * rng.choice([1.0, 3.0]))
+        mode = rng.random()
+        if mode < 0.4:
+            kw["rotation_offset"] = float(rng.uniform(-np.pi, np.pi)) if rng.random() < 0.5 else 0.0
+        else:
+            d = rng.normal(size=3)
+            kw["direction"] = (d / np.linalg.norm(d)).tolist()
+        if rng.random() < 0.5:
+            kw["origin"] = (xyz.mean(0) + rng.uniform(-0.2, 0.2, size=3)).tolist()
+    return meshes.pack_blob(xyz, nrm, tri, layout), xyz, nrm, tri, kw
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_fuzz_plans_match_oracle(ctx, orc, block):
+    import noether_b200 as nb
+    from noether_b200 import _capi
+    refused = 0
+    big = block >= 4
+    for seed in (range(200 + 12 * block, 212 + 12 * block) if big else range(25 * block, 25 * block + 25)):
+        blob, xyz, nrm, tri, kw = _fuzz_case(seed, orc, big)
+        dg = (nb.FixedDirectionGenerator(kw["direction"]) if "direction" in kw
+              else nb.PrincipalAxisDirectionGenerator(kw.get("rotation_offset", 0.0), ctx))
+        og = nb.FixedOriginGenerator(kw["origin"]) if "origin" in kw else nb.CentroidOriginGenerator(ctx)
+        planner = nb.PlaneSlicerRasterPlanner(dg, og, ctx)
+        planner.set_line_spacing(kw["spacing"])
+        planner.generate_rasters_bidirectionally(kw["bidirectional"])
+        try:
+            gpu = planner.plan(blob)
+        except _capi.Nb2Error as e:
+            # a direction (nearly) parallel to the mesh normal has no cutting planes; a cut point shared by more line
+            # ends than the linker re-pairs is reported, never mis-linked
+            assert e.status in (_capi.NB2_ERR_INVALID_ARGUMENT, _capi.NB2_ERR_NON_MANIFOLD), f"seed {seed}: {e}"
+            refused += 1
+            continue
+        paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, kw["spacing"], kw["bidirectional"],
+                                              direction=kw.get("direction"), origin=kw.get("origin"),
+                                              rotation_offset=kw.get("rotation_offset", 0.0), slice_mode=orc.SLICE_INTENT,
+                                              scan_mode=orc.SCAN_BINNED, frame=oracle_pca_from_capi(orc, ctx.pca()))
+        assert bytes(ctx.last_lattice()) == bytes(lat), f"seed {seed}: lattice"
+        assert_same_paths(gpu, paths.flat(), f"seed {seed} {kw}")
+        gpu.free()
+    assert refused <= 3
