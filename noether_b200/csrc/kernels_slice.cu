@@ -970,46 +970,50 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
 
   // ---- H1: merge cut points with equal float coordinates; smallest rank per point ------------------------------------
   // A probe compares the 16-bit fingerprint first and touches the positions only on a match; the table is at most a
-  // quarter full, so the longest probe sequence of a warp stays short.
-  for (unsigned j = tid; j < n; j += nth)
+  // quarter full.  Probe sequences differ in length, so a lane does not wait for its neighbours: the moment its
+  // endpoint is placed it takes its next one (endpoints tid, tid + nth, ...), which keeps the lanes of a warp busy.
   {
-    const float2 x2 = *reinterpret_cast<const float2*>(px + 2 * j), y2 = *reinterpret_cast<const float2*>(py + 2 * j),
-                 z2 = *reinterpret_cast<const float2*>(pz + 2 * j);
-    const uint2 t2 = *reinterpret_cast<const uint2*>(etag + 2 * j);
-    unsigned sl[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w)
-    {
-      const float x = w ? x2.y : x2.x, y = w ? y2.y : y2.x, z = w ? z2.y : z2.x;
-      const unsigned e = 2 * j + w;
+    unsigned e = tid, s = 0, fp = 0, tg = 0;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool active = e < E;
+    auto fetch = [&]() {
+      x = px[e], y = py[e], z = pz[e];
+      tg = etag[e];
       const unsigned h = hashPointFast(x, y, z);
-      const unsigned fp = h >> 16, key = e | (fp << 16);
-      unsigned s = h & mask, f = e;
-      while (true)
+      fp = h >> 16;
+      s = h & mask;
+    };
+    if (active)
+      fetch();
+    while (active)
+    {
+      unsigned v = *reinterpret_cast<volatile unsigned*>(slots + s);
+      if (v == kEmpty)
+        v = atomicCAS(slots + s, kEmpty, e | (fp << 16));
+      unsigned f = e;
+      bool placed = v == kEmpty;  // claimed: e is the key holder of a new point
+      if (!placed && (v >> 16) == fp)
       {
-        unsigned v = *reinterpret_cast<volatile unsigned*>(slots + s);
-        if (v == kEmpty)
+        const unsigned g = v & 0xffffu;
+        if (px[g] == x && py[g] == y && pz[g] == z)
         {
-          v = atomicCAS(slots + s, kEmpty, key);
-          if (v == kEmpty)
-            break;  // claimed: e is the key holder of a new point
+          f = g;
+          placed = true;
         }
-        if ((v >> 16) == fp)
-        {
-          const unsigned g = v & 0xffffu;
-          if (px[g] == x && py[g] == y && pz[g] == z)
-          {
-            f = g;
-            break;
-          }
-        }
-        s = (s + 1) & mask;
       }
-      if (f != e)
-        atomicMin(etag + f, w ? t2.y : t2.x);
-      sl[w] = s;
+      if (placed)
+      {
+        if (f != e)
+          atomicMin(etag + f, tg);
+        slotIdx[e] = static_cast<Idx>(s);
+        e += nth;
+        active = e < E;
+        if (active)
+          fetch();
+      }
+      else
+        s = (s + 1) & mask;
     }
-    *reinterpret_cast<unsigned*>(slotIdx + 2 * j) = sl[0] | (sl[1] << 16);
   }
   __syncthreads();
 
