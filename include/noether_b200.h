@@ -106,6 +106,10 @@ typedef struct nb2_pca
 int nb2_mesh_pca(nb2_context* ctx, nb2_pca* out);
 int nb2_principal_axis_direction(nb2_context* ctx, double rotation_offset, double out_direction[3]);
 int nb2_centroid_origin(nb2_context* ctx, double out_origin[3]);
+/* PCARotatedDirectionGenerator::generate (pca_rotated_direction_generator.cpp:13-25): the direction of a nested
+ * generator rotated by rotation_angle about the smallest principal axis of the resident mesh. */
+int nb2_pca_rotated_direction(nb2_context* ctx, double rotation_angle, const double nominal_direction[3],
+                              double out_direction[3]);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * NormalsFromMeshFacesMeshModifier::modify (normals_from_mesh_faces_modifier.cpp:15-46; getFaceNormal

@@ -835,6 +835,20 @@ int nb2_principal_axis_direction(nb2_context* c, double rotation_offset, double 
   NB2_API_END
 }
 
+int nb2_pca_rotated_direction(nb2_context* c, double rotation_angle, const double nominal[3], double out[3])
+{
+  NB2_API_BEGIN
+  if (!c || !nominal || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  requirePcaPoints(c);
+  ensureHostPca(c);
+  pcaRotatedDirection(c->pca, rotation_angle, nominal, out);
+  NB2_API_END
+}
+
 int nb2_centroid_origin(nb2_context* c, double out[3])
 {
   NB2_API_BEGIN

@@ -13,6 +13,11 @@ void principalAxisDirection(const nb2_pca& pca, double rotation_offset, double o
   frame::principalAxisDirection(pca, std::sin(rotation_offset), std::cos(rotation_offset), out);
 }
 
+void pcaRotatedDirection(const nb2_pca& pca, double rotation_angle, const double nominal[3], double out[3])
+{
+  frame::pcaRotatedDirection(pca, std::sin(rotation_angle), std::cos(rotation_angle), nominal, out);
+}
+
 const char* latticeErrorMessage(int code)
 {
   switch (code)

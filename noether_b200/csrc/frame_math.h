@@ -275,6 +275,32 @@ NB2_HD inline void principalAxisDirection(const nb2_pca& pca, double sin_r, doub
     out[i] = sum3(R[i][0] * e1.x, R[i][1] * e1.y, R[i][2] * e1.z);
 }
 
+/** PCARotatedDirectionGenerator::generate (pca_rotated_direction_generator.cpp:13-25): `nominal` (as is, not normalised)
+ *  rotated about the smallest principal axis */
+NB2_HD inline void pcaRotatedDirection(const nb2_pca& pca, double sin_r, double cos_r, const double nominal[3], double out[3])
+{
+  const D3 v = { nominal[0], nominal[1], nominal[2] };
+  const D3 axis = normalized(fromFloat(pca.evecs + 6));
+  const D3 sin_axis = sin_r * axis;
+  const double c = cos_r;
+  const D3 cos1_axis = (1.0 - c) * axis;
+  double R[3][3];
+  double tmp = cos1_axis.x * axis.y;
+  R[0][1] = tmp - sin_axis.z;
+  R[1][0] = tmp + sin_axis.z;
+  tmp = cos1_axis.x * axis.z;
+  R[0][2] = tmp + sin_axis.y;
+  R[2][0] = tmp - sin_axis.y;
+  tmp = cos1_axis.y * axis.z;
+  R[1][2] = tmp - sin_axis.x;
+  R[2][1] = tmp + sin_axis.x;
+  R[0][0] = cos1_axis.x * axis.x + c;
+  R[1][1] = cos1_axis.y * axis.y + c;
+  R[2][2] = cos1_axis.z * axis.z + c;
+  for (int i = 0; i < 3; ++i)
+    out[i] = sum3(R[i][0] * v.x, R[i][1] * v.y, R[i][2] * v.z);
+}
+
 constexpr int kLatticeOk = 0, kLatticeBadSpacing = 1, kLatticeNoNormal = 2, kLatticeTooManyPlanes = 3;
 
 NB2_HD inline bool finite64(double x) { return x - x == 0.0; }

@@ -273,6 +273,7 @@ void launchValidateTriangles(nb2_context* c);
 const char* latticeErrorMessage(int code);
 void eigenSolver3f(const float A[9], float evals[3], float evecs[9]);
 void principalAxisDirection(const nb2_pca& pca, double rotation_offset, double out[3]);
+void pcaRotatedDirection(const nb2_pca& pca, double rotation_angle, const double nominal[3], double out[3]);
 int makeLattice(const nb2_pca& pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
                 nb2_lattice& L);
 

@@ -86,6 +86,12 @@ class Context:
         _capi.check(self._lib.nb2_principal_axis_direction(self._h, rotation_offset, out))
         return np.array(out)
 
+    def pca_rotated_direction(self, rotation_angle: float, nominal) -> np.ndarray:
+        v = (C.c_double * 3)(*[float(x) for x in nominal])
+        out = (C.c_double * 3)()
+        _capi.check(self._lib.nb2_pca_rotated_direction(self._h, rotation_angle, v, out))
+        return np.array(out)
+
     def centroid_origin(self) -> np.ndarray:
         out = (C.c_double * 3)()
         _capi.check(self._lib.nb2_centroid_origin(self._h, out))
@@ -280,6 +286,22 @@ class PrincipalAxisDirectionGenerator(DirectionGenerator):
         return ctx.principal_axis_direction(self.rotation_offset)
 
 
+class PCARotatedDirectionGenerator(DirectionGenerator):
+    """pca_rotated_direction_generator.cpp:13-25 — a nested generator's direction rotated about the smallest principal
+    axis (device PCA)"""
+
+    def __init__(self, dir_gen: DirectionGenerator, rotation_angle: float, context: Context | None = None):
+        self.dir_gen = dir_gen
+        self.rotation_angle = float(rotation_angle)
+        self._ctx = context
+
+    def generate(self, mesh):
+        nominal = self.dir_gen.generate(mesh)
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        return ctx.pca_rotated_direction(self.rotation_angle, nominal)
+
+
 class CentroidOriginGenerator(OriginGenerator):
     """centroid_origin_generator.cpp:8-17 — mean of the vertices from the device moment reduction"""
 
@@ -411,6 +433,9 @@ class Factory:
             return PrincipalAxisDirectionGenerator(_member(config, "rotation_offset"), self._ctx)
         if name == "FixedDirection":
             return FixedDirectionGenerator(_vec3(_member(config, "direction")))
+        if name == "PCARotated":  # plugins.cpp:91-107
+            return PCARotatedDirectionGenerator(self.create_direction_generator(_member(config, "direction_generator")),
+                                                _member(config, "rotation_offset"), self._ctx)
         raise RuntimeError(f"Failed to find plugin '{name}' in section 'dg'")
 
     def create_origin_generator(self, config: dict) -> OriginGenerator:

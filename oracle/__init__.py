@@ -80,6 +80,7 @@ def lib():
     L.orc_pca.argtypes = [f32p, C.c_uint64, C.c_int, C.POINTER(PcaResult)]
     L.orc_centroid.argtypes = [f32p, C.c_uint64, C.c_int, f64p]
     L.orc_principal_axis_direction.argtypes = [C.POINTER(PcaResult), C.c_double, f64p]
+    L.orc_pca_rotated_direction.argtypes = [C.POINTER(PcaResult), C.c_double, f64p, f64p]
     L.orc_eigen_solver_3f.argtypes = [f32p, f32p, f32p]
     L.orc_make_lattice.argtypes = [C.POINTER(PcaResult), f64p, f64p, C.c_double, C.c_int, C.POINTER(Lattice)]
     L.orc_normals_from_mesh_faces.argtypes = [f32p, C.c_uint64, u32p, C.c_uint64, f32p]
@@ -173,6 +174,14 @@ def principal_axis_direction(p: Pca, rotation_offset: float = 0.0) -> np.ndarray
     out = np.zeros(3)
     _check(lib().orc_principal_axis_direction(C.byref(p.raw), rotation_offset,
                                               out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def pca_rotated_direction(p: Pca, rotation_angle: float, nominal) -> np.ndarray:
+    """PCARotatedDirectionGenerator::generate given the nested generator's direction."""
+    _, v = _f64(nominal)
+    out = np.zeros(3)
+    _check(lib().orc_pca_rotated_direction(C.byref(p.raw), rotation_angle, v, out.ctypes.data_as(C.POINTER(C.c_double))))
     return out
 
 

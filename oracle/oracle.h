@@ -60,6 +60,9 @@ typedef struct orc_pca_result
 int orc_pca(const float* xyz, uint64_t n_vertices, int moments_mode, orc_pca_result* out);
 int orc_centroid(const float* xyz, uint64_t n_vertices, int moments_mode, double out[3]);
 int orc_principal_axis_direction(const orc_pca_result* pca, double rotation_offset, double out[3]);
+/* PCARotatedDirectionGenerator::generate (pca_rotated_direction_generator.cpp:13-25): the nominal direction of a nested
+ * generator rotated about the smallest principal axis */
+int orc_pca_rotated_direction(const orc_pca_result* pca, double rotation_angle, const double nominal[3], double out[3]);
 /* Eigen 3.4 SelfAdjointEigenSolver<Matrix3f>::compute restated; cov column-major, evecs column-major ascending */
 int orc_eigen_solver_3f(const float cov[9], float evals_ascending[3], float evecs_ascending[9]);
 

@@ -40,6 +40,7 @@ void eigenSolver3f(const float A[9], float evals[3], float evecs[9]);
 int pca(const float* xyz, uint64_t V, int mode, orc_pca_result* out);
 int centroid(const float* xyz, uint64_t V, int mode, double out[3]);
 int principalAxisDirection(const orc_pca_result* pca, double rotation_offset, double out[3]);
+int pcaRotatedDirection(const orc_pca_result* pca, double rotation_angle, const double nominal[3], double out[3]);
 int makeLattice(const orc_pca_result* pca,
                 const double cut_direction[3],
                 const double cut_origin[3],

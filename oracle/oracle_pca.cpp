@@ -412,6 +412,19 @@ int principalAxisDirection(const orc_pca_result* pca, double rotation_offset, do
   return ORC_OK;
 }
 
+int pcaRotatedDirection(const orc_pca_result* pca, double rotation_angle, const double nominal[3], double out[3])
+{
+  // pca_rotated_direction_generator.cpp:24: AngleAxisd(rotation_angle_, pca_vecs.col(2).normalized()) * nominal_dir
+  // (the nominal direction is NOT normalised, unlike PrincipalAxis' e1)
+  const V3d e2 = { pca->evecs[6], pca->evecs[7], pca->evecs[8] };
+  const V3d v = { nominal[0], nominal[1], nominal[2] };
+  const V3d r = angleAxisRotate(rotation_angle, eigenNormalized(e2), v);
+  out[0] = r.x;
+  out[1] = r.y;
+  out[2] = r.z;
+  return ORC_OK;
+}
+
 int makeLattice(const orc_pca_result* pca,
                 const double cut_direction_[3],
                 const double cut_origin_[3],

@@ -334,6 +334,10 @@ int orc_principal_axis_direction(const orc_pca_result* pca_, double rot, double 
 {
   return principalAxisDirection(pca_, rot, out);
 }
+int orc_pca_rotated_direction(const orc_pca_result* pca_, double angle, const double nominal[3], double out[3])
+{
+  return pcaRotatedDirection(pca_, angle, nominal, out);
+}
 int orc_eigen_solver_3f(const float cov[9], float evals[3], float evecs[9])
 {
   eigenSolver3f(cov, evals, evecs);

@@ -8,6 +8,7 @@
 //   PlaneSlicer           tpp      Plugin_PlaneSlicerRasterPlanner        src/plugins.cpp:252-278
 //   PlaneSlicerLegacy     tpp      Plugin_PlaneSlicerLegacyRasterPlanner  src/plugins.cpp:151-179
 //   PrincipalAxis         dg       PrincipalAxisDirectionGenerator        src/plugins.cpp:89
+//   PCARotated            dg       Plugin_PCARotatedDirectionGenerator    src/plugins.cpp:91-107
 //   Centroid              og       CentroidOriginGenerator                src/plugins.cpp:111
 //   NormalsFromMeshFaces  mesh     NormalsFromMeshFacesMeshModifier       src/plugins.cpp:62
 //
@@ -218,6 +219,33 @@ private:
   double rotation_offset_;
 };
 
+/** PCARotatedDirectionGenerator (pca_rotated_direction_generator.cpp:13-25): the direction of a nested generator rotated
+ *  about the smallest principal axis; the PCA runs on the GPU. */
+class PCARotatedDirectionGenerator : public noether::DirectionGenerator
+{
+public:
+  PCARotatedDirectionGenerator(noether::DirectionGenerator::ConstPtr dir_gen, double rotation_angle)
+    : dir_gen_(std::move(dir_gen)), rotation_angle_(rotation_angle)
+  {
+  }
+
+  Eigen::Vector3d generate(const pcl::PolygonMesh& mesh) const override final
+  {
+    const Eigen::Vector3d nominal = dir_gen_->generate(mesh);  // may use the device itself: call it before locking
+    const double v[3] = { nominal.x(), nominal.y(), nominal.z() };
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    upload(dev.ctx(), mesh, false);
+    double d[3];
+    Device::check(nb2_pca_rotated_direction(dev.ctx(), rotation_angle_, v, d));
+    return Eigen::Vector3d(d[0], d[1], d[2]);
+  }
+
+private:
+  noether::DirectionGenerator::ConstPtr dir_gen_;
+  double rotation_angle_;
+};
+
 /** CentroidOriginGenerator (centroid_origin_generator.cpp:8-17) */
 class CentroidOriginGenerator : public noether::OriginGenerator
 {
@@ -393,6 +421,17 @@ struct Plugin_PrincipalAxisDirectionGenerator : public noether::Plugin<noether::
   }
 };
 
+struct Plugin_PCARotatedDirectionGenerator : public noether::Plugin<noether::DirectionGenerator>
+{
+  std::unique_ptr<noether::DirectionGenerator> create(const YAML::Node& config,
+                                                      std::shared_ptr<const noether::Factory> factory) const override final
+  {
+    // plugins.cpp:91-107: a nested generator (created through the factory) and `rotation_offset`
+    auto dir_gen = factory->createDirectionGenerator(YAML::getMember<YAML::Node>(config, "direction_generator"));
+    return std::make_unique<PCARotatedDirectionGenerator>(std::move(dir_gen), YAML::getMember<double>(config, "rotation_offset"));
+  }
+};
+
 struct Plugin_CentroidOriginGenerator : public noether::Plugin<noether::OriginGenerator>
 {
   std::unique_ptr<noether::OriginGenerator> create(const YAML::Node& /*config*/,
@@ -448,6 +487,7 @@ struct Plugin_PlaneSlicerLegacyRasterPlanner : public noether::Plugin<noether::T
 
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)
+EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PCARotatedDirectionGenerator, PCARotated)
 EXPORT_ORIGIN_GENERATOR_PLUGIN(noether_b200::Plugin_CentroidOriginGenerator, Centroid)
 EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerRasterPlanner, PlaneSlicer)
 EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerLegacyRasterPlanner, PlaneSlicerLegacy)

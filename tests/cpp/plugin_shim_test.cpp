@@ -362,6 +362,18 @@ void testGeneratorsAndErrors(const noether::Factory& factory, const pcl::Polygon
   const Eigen::Vector3d d = factory.createDirectionGenerator(dg)->generate(mesh);
   CHECK(std::abs(norm(d) - 1.0) < 1e-6);
   CHECK(std::abs(d.z()) < 0.2);  // the second principal axis of this 10.5 x 10.5 x 4 surface lies near the xy plane
+  {
+    // PCARotated (plugins.cpp:91-107): a nested generator's direction rotated about the smallest principal axis
+    YAML::Node rot;
+    rot["name"] = "PCARotated";
+    rot["direction_generator"] = dg;
+    rot["rotation_offset"] = 0.0;
+    const Eigen::Vector3d r0 = factory.createDirectionGenerator(rot)->generate(mesh);
+    CHECK(std::abs(r0.x() - d.x()) < 1e-12 && std::abs(r0.y() - d.y()) < 1e-12 && std::abs(r0.z() - d.z()) < 1e-12);
+    rot["rotation_offset"] = M_PI / 2;
+    const Eigen::Vector3d r90 = factory.createDirectionGenerator(rot)->generate(mesh);
+    CHECK(std::abs(dot(r90, d)) < 1e-9 && std::abs(norm(r90) - 1.0) < 1e-9);
+  }
   YAML::Node og;
   og["name"] = "Centroid";
   const Eigen::Vector3d o = factory.createOriginGenerator(og)->generate(mesh);
@@ -439,7 +451,7 @@ int main(int argc, char** argv)
   const noether::Factory factory(loader);
   try
   {
-    for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "Centroid", "NormalsFromMeshFaces" })
+    for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces" })
       CHECK(dlsym(lib, alias) != nullptr);
     const pcl::PolygonMesh ply = loadPly(argv[2]);
     CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);

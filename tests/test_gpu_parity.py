@@ -600,3 +600,31 @@ def test_fuzz_plans_match_oracle(ctx, orc, block):
         assert_same_paths(gpu, paths.flat(), f"seed {seed} {kw}")
         gpu.free()
     assert refused <= 3
+
+
+def test_pca_rotated_direction_generator(ctx, orc, ply_mesh):
+    """PCARotatedDirectionGenerator (pca_rotated_direction_generator.cpp:13-25) through the factory, bit-exact against the
+    oracle given the same frame; composes with the planner like any foreign generator."""
+    import noether_b200 as nb
+    xyz, nrm, tri = ply_mesh.xyz(), ply_mesh.normals(), ply_mesh.tri
+    f = nb.Factory(ctx)
+    for nested, angle in (({"name": "FixedDirection", "direction": [1.0, 0.25, 0.0]}, 0.7),
+                          ({"name": "PrincipalAxis", "rotation_offset": 0.3}, -1.9)):
+        gen = f.create_direction_generator({"name": "PCARotated", "direction_generator": nested, "rotation_offset": angle})
+        got = gen.generate(ply_mesh)
+        frame = oracle_pca_from_capi(orc, ctx.pca())
+        nominal = (np.array(nested["direction"], np.float64) if nested["name"] == "FixedDirection"
+                   else orc.principal_axis_direction(frame, nested["rotation_offset"]))
+        want = orc.pca_rotated_direction(frame, angle, nominal)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+        assert abs(np.linalg.norm(got) - np.linalg.norm(nominal)) < 1e-12
+    cfg = {"name": "PlaneSlicer", "line_spacing": 1.05, "bidirectional": True,
+           "direction_generator": {"name": "PCARotated", "rotation_offset": 0.5,
+                                   "direction_generator": {"name": "PrincipalAxis", "rotation_offset": 0.0}},
+           "origin_generator": {"name": "Centroid"}}
+    gpu = f.create_tool_path_planner(cfg).plan(ply_mesh)
+    frame = oracle_pca_from_capi(orc, ctx.pca())
+    d = orc.pca_rotated_direction(frame, 0.5, orc.principal_axis_direction(frame, 0.0))
+    paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, 1.05, True, direction=d, slice_mode=orc.SLICE_INTENT, frame=frame)
+    assert bytes(ctx.last_lattice()) == bytes(lat)
+    assert_same_paths(gpu, paths.flat(), "PCARotated plan")

@@ -332,3 +332,22 @@ def test_closed_loops_match_the_stripper(orc):
     np.testing.assert_array_equal(a.pose, b.pose)
     s0, s1 = int(a.seg_off[0]), int(a.seg_off[1])
     np.testing.assert_array_equal(a.pos[s0], a.pos[s1 - 1])
+
+
+def test_kat_pca_rotated_direction(orc):
+    """PCARotatedDirectionGenerator: rotation about the smallest principal axis (pca_rotated_direction_generator.cpp:24)."""
+    from noether_b200 import meshes
+    xyz, _ = meshes.wavy(40, 25)
+    p = orc.pca(xyz, orc.MOMENTS_F64)
+    e2 = p.evecs[:, 2].astype(np.float64)
+    e2 /= np.linalg.norm(e2)
+    v = np.array([0.3, -1.2, 0.4])
+    for ang in (0.0, 0.5, -2.0, np.pi):
+        r = orc.pca_rotated_direction(p, ang, v)
+        want = v * np.cos(ang) + np.cross(e2, v) * np.sin(ang) + e2 * (e2 @ v) * (1 - np.cos(ang))  # Rodrigues
+        assert np.abs(r - want).max() < 1e-14
+    assert np.array_equal(orc.pca_rotated_direction(p, 0.0, v), v * 1.0) or np.abs(orc.pca_rotated_direction(p, 0.0, v) - v).max() < 1e-16
+    # with the nominal direction = normalised e1 it is PrincipalAxis with the same offset
+    e1 = p.evecs[:, 1].astype(np.float64)
+    e1 /= np.linalg.norm(e1)
+    assert np.abs(orc.pca_rotated_direction(p, 0.9, e1) - orc.principal_axis_direction(p, 0.9)).max() < 1e-15

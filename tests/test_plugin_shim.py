@@ -22,7 +22,7 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
     syms = subprocess.run(["nm", "-D", "--defined-only", PLUGIN], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in syms.splitlines() if line.strip()}
     # aliases of noether_tpp/src/plugins.cpp:62,89,111,179,278
-    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "Centroid", "NormalsFromMeshFaces"):
+    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces"):
         assert alias in exported
     # each plugin object sits in the ELF section boost_plugin_loader enumerates for its kind
     # (NOETHER_*_SECTION, noether_tpp/CMakeLists.txt:126-131)

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3] (cfg4): NormalsFromMeshFaces + PCA frame on the 50 M-triangle mesh with permuted vertex /
+face order, device-resident input; prints CUDA-event stage times and the achieved fraction of the HBM roofline
+(B_normals = 12 F + 24 V, B_pca = 12 V).
+
+    python tools/profile_normals.py [cfg4|cfg3|cfg2]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+SIZES = {"cfg4": (6250, 4000, True), "cfg3": (2500, 2000, False), "cfg2": (800, 625, False)}
+
+
+def main():
+    import torch
+
+    import noether_b200 as nb
+    from noether_b200 import meshes
+
+    name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
+    nx, ny, permuted = SIZES[name]
+    xyz, tri = meshes.wavy(nx, ny)
+    if permuted:
+        xyz, tri = meshes.permute(xyz, tri, seed=42)
+    V, F = xyz.shape[0], tri.shape[0]
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    dev = torch.device("cuda", 0)
+    d_cloud = torch.from_numpy(blob.data).to(dev)
+    d_tri = torch.from_numpy(tri.reshape(-1).view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    ctx = nb.Context(0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    out = []
+    for it in range(4):
+        ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
+        ctx.timer_start()
+        ctx.normals_from_mesh_faces(V, download=False)
+        t_n = ctx.timer_stop()
+        st = ctx.timings()
+        ctx.timer_start()
+        ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
+        ctx.pca()
+        t_p = ctx.timer_stop()
+        out.append((t_n, t_p, st))
+    t_n = min(o[0] for o in out[1:])
+    t_p = min(o[1] for o in out[1:])
+    b_n, b_p = 12 * F + 24 * V, 12 * V
+    print(json.dumps({"workload": name, "V": V, "F": F, "permuted": permuted,
+                      "normals_ms": t_n, "normals_GBps": b_n / t_n / 1e6, "normals_frac_of_peak": b_n / t_n / 1e6 / peak,
+                      "pca_frame_ms": t_p, "pca_GBps": b_p / t_p / 1e6, "pca_frac_of_peak": b_p / t_p / 1e6 / peak,
+                      "stages_ms": {k: round(v, 4) for k, v in out[-1][2].items()}}))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
