@@ -298,11 +298,24 @@ def main():
     planner.generate_rasters_bidirectionally(True)
     planner.emit_edges = False
 
+    trace = os.environ.get("NB2_BENCH_TRACE") == "1"
+
     def e2e_step():
         ctx._mesh_key = None  # every step uploads the mesh again from the pinned host buffers
-        local = planner.plan(pinned_mesh, info.rank, info.world)
+        # N > 1: every rank copies 1 / N of the mesh over its own PCIe link, NVLink all-gathers the shares
+        t0 = time.perf_counter()
+        t1 = t0
+        if trace and os.environ.get("NB2_BENCH_SPLIT") == "1":
+            ctx.upload(pinned_mesh, force=True, sharded=info.world > 1)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+        local = planner.plan(pinned_mesh, info.rank, info.world, sharded_upload=info.world > 1)
+        t2 = time.perf_counter()
         if info.world > 1:
             out = ctx.gather(local, 0)
+            if trace:
+                print(f"[rank {info.rank}] upload {1e3 * (t1 - t0):.3f} ms, plan {1e3 * (t2 - t1):.3f} ms, "
+                      f"gather {1e3 * (time.perf_counter() - t2):.3f} ms", file=sys.stderr)
             n = (out.n_paths, out.n_segments, out.n_waypoints) if out is not None else (0, 0, 0)
             # the slabs travel GPU to GPU; only the root copies tool paths to the host (all of them)
             d2h = (out.n_waypoints * 24 + out.n_segments * 4) if out is not None else 0
@@ -364,9 +377,11 @@ def main():
         totals, d2h_bytes = e2e_step()
         torch.cuda.synchronize()
         e2e_total += 1e3 * (time.perf_counter() - t0)
+        if trace:
+            print(f"[rank {info.rank}] e2e step {1e3 * (time.perf_counter() - t0):.3f} ms", file=sys.stderr)
     barrier()
     e2e_ms = max_over_ranks(e2e_total, info.world, dev) / args.steps
-    h2d_bytes = int(blob.data.size + tri.size * 4)
+    h2d_bytes = int(blob.data.size + tri.size * 4)  # per job: with N ranks each copies 1 / N of it
 
     if info.rank != 0:
         return

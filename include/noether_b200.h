@@ -244,6 +244,10 @@ int nb2_comm_init(nb2_context* ctx, const uint8_t unique_id[NB2_UNIQUE_ID_BYTES]
  * other ranks NULL.  Legacy modifiers and raster post-ops, when requested in the params, are applied to the gathered
  * result. */
 int nb2_result_gather(nb2_context* ctx, const nb2_result* local, int root, nb2_result** gathered);
+/* Collective nb2_mesh_upload for a sharded job whose ranks all hold the same host mesh: every rank copies 1 / world of the
+ * cloud and of the triangle list over its own PCIe link, and an in-place ncclAllGather over NVLink gives each GPU the
+ * whole mesh.  Without a communicator (or for device-resident input) it is nb2_mesh_upload. */
+int nb2_mesh_upload_sharded(nb2_context* ctx, const nb2_mesh_view* mesh);
 int nb2_comm_destroy(nb2_context* ctx);
 
 #ifdef __cplusplus

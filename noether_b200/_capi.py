@@ -38,7 +38,7 @@ DECLARED_SYMBOLS = [
     "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_plan_params_default", "nb2_slice",
     "nb2_plan", "nb2_plan_mesh", "nb2_last_lattice", "nb2_result_get", "nb2_result_poses", "nb2_result_free", "nb2_last_timings",
     "nb2_kernel_launches", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
-    "nb2_result_gather", "nb2_comm_destroy",
+    "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",
 ]
 
 
@@ -105,6 +105,7 @@ def load():
     L.nb2_context_destroy.restype = None
     L.nb2_context_device.argtypes = [vp]
     L.nb2_mesh_upload.argtypes = [vp, C.POINTER(MeshView)]
+    L.nb2_mesh_upload_sharded.argtypes = [vp, C.POINTER(MeshView)]
     L.nb2_mesh_set_normals.argtypes = [vp, C.c_void_p]
     L.nb2_mesh_download.argtypes = [vp, C.c_void_p, C.c_void_p]
     L.nb2_mesh_pca.argtypes = [vp, C.POINTER(Pca)]

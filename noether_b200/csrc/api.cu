@@ -659,9 +659,8 @@ void nb2_context_destroy(nb2_context* c)
 
 int nb2_context_device(const nb2_context* c) { return c ? c->device : -1; }
 
-int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
+static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
 {
-  NB2_API_BEGIN
   if (!c || !m)
     fail(NB2_ERR_INVALID_ARGUMENT, "context or mesh is NULL");
   std::lock_guard<std::mutex> lock(c->mu);
@@ -698,8 +697,18 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     c->blob.adopt(const_cast<void*>(m->cloud_data));
   else
   {
-    c->blob.ensure(V * m->point_step);
-    NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, V * m->point_step, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = V * m->point_step;
+    if (sharded)
+    {
+      // every rank copies 1 / world of the bytes over its own PCIe link; NVLink does the rest (comm.cpp)
+      c->blob.ensure(shardedCapacity(c, bytes));
+      shardedHostToDevice(c, c->blob.ptr, m->cloud_data, bytes);
+    }
+    else
+    {
+      c->blob.ensure(bytes);
+      NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
   }
   bool tri_adopted = false;
   if (F && onThisDevice(m->triangles))
@@ -709,9 +718,18 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
   }
   else
   {
-    c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
-    if (F)
-      NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, sizeof(uint32_t) * 3 * F, cudaMemcpyHostToDevice, c->stream));
+    const size_t bytes = sizeof(uint32_t) * 3 * F;
+    if (sharded && F)
+    {
+      c->tri.ensure(shardedCapacity(c, bytes));
+      shardedHostToDevice(c, c->tri.ptr, m->triangles, bytes);
+    }
+    else
+    {
+      c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+      if (F)
+        NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
   }
   c->timer_upload.mark("h2d", c->stream);
   c->V = V;
@@ -744,7 +762,7 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
     // by the next call that synchronises (nb2_plan, nb2_mesh_pca, nb2_normals_from_mesh_faces, ...)
     c->checks_deferred = true;
     c->tri_checked = false;
-    return NB2_OK;
+    return;
   }
   c->checks_deferred = false;
   c->hostSmall.ensure(4096 + sizeof(FrameDev));
@@ -769,6 +787,22 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
                                        std::to_string(V) + " points");
   }
   c->tri_checked = true;
+}
+
+int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
+{
+  NB2_API_BEGIN
+  uploadImpl(c, m, false);
+  NB2_API_END
+}
+
+int nb2_mesh_upload_sharded(nb2_context* c, const nb2_mesh_view* m)
+{
+  NB2_API_BEGIN
+  if (!c || c->comm_world <= 1 || !c->nccl_comm)
+    uploadImpl(c, m, false);  // no communicator: an ordinary upload
+  else
+    uploadImpl(c, m, true);
   NB2_API_END
 }
 

@@ -8,6 +8,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 
 namespace nb2
@@ -88,6 +89,36 @@ struct SlabHeader
 }  // namespace
 
 void directionOfTravelInPlace(nb2_result& r);
+
+static size_t shardChunk(const nb2_context* c, size_t bytes)
+{
+  const size_t world = static_cast<size_t>(c->comm_world > 1 ? c->comm_world : 1);
+  const size_t per = (bytes + world - 1) / world;
+  return (per + 255) & ~size_t(255);
+}
+
+size_t shardedCapacity(const nb2_context* c, size_t bytes)
+{
+  return shardChunk(c, bytes) * static_cast<size_t>(c->comm_world > 1 ? c->comm_world : 1);
+}
+
+void shardedHostToDevice(nb2_context* c, void* dst, const void* src, size_t bytes)
+{
+  if (c->comm_world <= 1 || !c->nccl_comm)
+  {
+    NB2_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return;
+  }
+  const size_t chunk = shardChunk(c, bytes);
+  const size_t begin = chunk * static_cast<size_t>(c->comm_rank);
+  const size_t mine = begin < bytes ? std::min(chunk, bytes - begin) : 0;
+  auto* d = static_cast<uint8_t*>(dst);
+  if (mine)
+    NB2_CUDA(cudaMemcpyAsync(d + begin, static_cast<const uint8_t*>(src) + begin, mine, cudaMemcpyHostToDevice, c->stream));
+  // in place: each rank's contribution already sits at its own offset of the receive buffer
+  check(api().AllGather(d + begin, d, chunk, ncclUint8, static_cast<ncclComm_t>(c->nccl_comm), c->stream),
+        "ncclAllGather(mesh shares)");
+}
 }  // namespace nb2
 
 using namespace nb2;

@@ -277,6 +277,12 @@ void pcaRotatedDirection(const nb2_pca& pca, double rotation_angle, const double
 int makeLattice(const nb2_pca& pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
                 nb2_lattice& L);
 
+// PCIe-parallel upload for a sharded job (comm.cpp): rank r copies bytes [r * chunk, (r + 1) * chunk) of `src` to the
+// same offsets of `dst`, then an in-place ncclAllGather over NVLink completes every rank's copy.  `dst` must hold
+// shardedCapacity(bytes) bytes (the chunk is padded to a multiple of 256).
+size_t shardedCapacity(const nb2_context* c, size_t bytes);
+void shardedHostToDevice(nb2_context* c, void* dst, const void* src, size_t bytes);
+
 // result storage (api.cu)
 nb2_result* allocResult(nb2_context* c, uint64_t n_paths, uint64_t n_segments, uint64_t n_waypoints, bool edges, bool poses);
 void freeResult(nb2_result* r);

@@ -45,7 +45,9 @@ class Context:
             pass
 
     # -- mesh -------------------------------------------------------------------------------------------------
-    def upload(self, mesh: MeshBlob, force: bool = False):
+    def upload(self, mesh: MeshBlob, force: bool = False, sharded: bool = False):
+        """nb2_mesh_upload; sharded=True (collective, after comm_init): every rank copies 1 / world of the bytes and the
+        shares are all-gathered over NVLink (nb2_mesh_upload_sharded)."""
         key = (id(mesh.data), id(mesh.tri), mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal)
         if not force and key == self._mesh_key:
             return
@@ -54,7 +56,8 @@ class Context:
         tri = np.ascontiguousarray(mesh.tri, dtype=np.uint32)
         mv = _capi.MeshView(data.ctypes.data, mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal, 0,
                             tri.ctypes.data if tri.size else None, tri.shape[0])
-        _capi.check(self._lib.nb2_mesh_upload(self._h, C.byref(mv)))
+        fn = self._lib.nb2_mesh_upload_sharded if sharded else self._lib.nb2_mesh_upload
+        _capi.check(fn(self._h, C.byref(mv)))
         self._mesh_key = key
         self._keep = (data, tri)
 
@@ -356,9 +359,9 @@ class PlaneSlicerRasterPlanner:
             p.origin[:] = [float(v) for v in o]
         return p
 
-    def plan(self, mesh: MeshBlob, shard_rank: int = 0, shard_count: int = 1) -> ToolPaths:
+    def plan(self, mesh: MeshBlob, shard_rank: int = 0, shard_count: int = 1, sharded_upload: bool = False) -> ToolPaths:
         ctx = self._ctx or default_context()
-        ctx.upload(mesh)
+        ctx.upload(mesh, sharded=sharded_upload)
         p = self._params(mesh)
         p.shard_rank, p.shard_count = shard_rank, shard_count
         return ctx.plan(p)

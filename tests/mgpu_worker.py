@@ -29,6 +29,11 @@ def main():
     ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
     nrm = ctx.normals_from_mesh_faces(xyz.shape[0])
     blob = meshes.pack_blob(xyz, nrm, tri)
+    # PCIe-parallel upload: each rank copies 1 / world of the bytes, NVLink all-gathers the shares; every rank must end
+    # up with exactly the mesh an ordinary upload gives it
+    ctx.upload(blob, force=True, sharded=True)
+    gx, gn = ctx.download(blob.n_vertices)
+    assert np.array_equal(gx.view(np.uint32), xyz.view(np.uint32)) and np.array_equal(gn.view(np.uint32), nrm.view(np.uint32))
     for legacy in (False, True):
         if legacy:
             planner = nb.PlaneSlicerLegacyRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx),
@@ -38,7 +43,8 @@ def main():
                                                   nb.CentroidOriginGenerator(ctx), ctx)
         planner.set_line_spacing(0.0031)
         planner.generate_rasters_bidirectionally(True)
-        local = planner.plan(blob, info.rank, info.world)
+        ctx._mesh_key = None
+        local = planner.plan(blob, info.rank, info.world, sharded_upload=True)
         assert local.n_waypoints > 0 and local.positions.shape[0] == 0, "a slab stays on the device until the gather"
         got = ctx.gather(local, 0)
         local.free()
