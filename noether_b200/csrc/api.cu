@@ -568,6 +568,59 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   return r;
 }
 
+/** JoinCloseSegments + MinimumSegmentLength + UniformSpacing on the slab `raw` left on the device (kernels_legacy.cu);
+ *  consumes `raw`, returns the resampled result (explicit poses) on the host. */
+nb2_result* legacyOnDevice(nb2_context* c, nb2_result* raw, const nb2_plan_params& prm)
+{
+  const uint64_t nP = raw->slab_planes, plane_begin = raw->slab_begin;
+  const nb2_lattice lat = raw->lattice;
+  uint64_t totals[3] = { 0, 0, 0 };
+  std::vector<uint32_t> planeL;
+  if (nP && raw->n_waypoints)
+    launchLegacy(c, nP, raw->n_waypoints, raw->n_segments, prm.point_spacing, prm.min_segment_size, prm.min_hole_size,
+                 totals, planeL);
+  nb2_result* out = allocResult(c, totals[0], totals[1], totals[2], true, true);
+  out->legacy = true;
+  out->post_ops_applied = false;
+  out->params = prm;
+  out->lattice = lat;
+  try
+  {
+    if (totals[2])
+    {
+      NB2_CUDA(cudaMemcpyAsync(out->poses, c->legPose.ptr, sizeof(double) * 16 * totals[2], cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaMemcpyAsync(out->positions, c->legPos.ptr, sizeof(float) * 3 * totals[2], cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaMemcpyAsync(out->normals, c->legNrm.ptr, sizeof(float) * 3 * totals[2], cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaMemcpyAsync(out->segment_offsets + 1, c->legSegLen.ptr, sizeof(unsigned) * totals[1], cudaMemcpyDeviceToHost,
+                               c->stream));
+    }
+    c->timer.mark("d2h", c->stream);
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  catch (...)
+  {
+    freeResult(out);
+    throw;
+  }
+  for (uint64_t s = 0; s < totals[1]; ++s)
+    out->segment_offsets[s + 1] += out->segment_offsets[s];
+  std::memset(out->edge_lo, 0xff, sizeof(uint32_t) * totals[2]);  // resampled waypoints lie on no single mesh edge
+  std::memset(out->edge_hi, 0xff, sizeof(uint32_t) * totals[2]);
+  uint64_t p = 0, s_acc = 0;
+  for (uint64_t k = 0; k < nP && !planeL.empty(); ++k)
+  {
+    if (!planeL[4 * k])
+      continue;
+    out->path_offsets[p] = static_cast<uint32_t>(s_acc);
+    out->path_plane[p] = static_cast<int64_t>(plane_begin + k);
+    s_acc += planeL[4 * k + 1];
+    ++p;
+  }
+  out->path_offsets[p] = static_cast<uint32_t>(s_acc);
+  freeResult(raw);
+  return out;
+}
+
 }  // namespace
 
 void directionOfTravelInPlace(nb2_result& r);
@@ -641,7 +694,8 @@ void nb2_context_destroy(nb2_context* c)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
   for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
-                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->planeMeta, &c->outPos, &c->outNrm,
+                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
+                     &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->scanState })
     b->release();
@@ -1011,15 +1065,33 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   fp.shard_count = prm->shard_count > 1 ? prm->shard_count : 1;
   // a slab of a sharded plan stays in HBM: nb2_result_gather sends it to the root GPU-to-GPU
   const bool download = prm->download != 0 && prm->shard_count <= 1;
-  nb2_result* r = sliceImpl(c, &fp, nullptr, 0, NB2_ALL_PLANES, prm->emit_edges != 0 || prm->legacy != 0, download);
+  // the legacy planner's modifiers run on the device, on the slicer's result while it is still in HBM: only the
+  // resampled poses are copied to the host (a sharded plan applies them on the root after the gather, toolpath.cpp)
+  const bool device_legacy = prm->legacy != 0 && download;
+  if (device_legacy && !(prm->point_spacing > 0.0))
+    fail(NB2_ERR_INVALID_ARGUMENT, "point_spacing must be positive");
+  nb2_result* r = sliceImpl(c, &fp, nullptr, 0, NB2_ALL_PLANES, prm->emit_edges != 0 || (prm->legacy != 0 && !device_legacy),
+                            device_legacy ? false : download);
   r->params = *prm;
+  if (device_legacy)
+  {
+    try
+    {
+      r = legacyOnDevice(c, r, *prm);
+    }
+    catch (...)
+    {
+      freeResult(r);
+      throw;
+    }
+  }
   try
   {
     const bool sharded = prm->shard_count > 1;
     // sharded plans defer the modifiers to nb2_result_gather: they need the whole set of tool paths
     if (!sharded && download)
     {
-      if (prm->legacy && r->n_paths)
+      if (prm->legacy && !device_legacy && r->n_paths)
         legacyModifiers(r, prm->point_spacing, prm->min_segment_size, prm->min_hole_size);
       if (prm->raster_post_ops && r->n_paths)
       {

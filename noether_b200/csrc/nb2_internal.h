@@ -189,6 +189,12 @@ struct nb2_context
   nb2::DevBuf outEdge;     // uint32[2 * Wcap]
   nb2::DevBuf outSegLen;   // uint32[Scap]
   nb2::DevBuf linkScratch; // global scratch for planes too large for shared memory
+  // legacy modifiers on the device (kernels_legacy.cu)
+  nb2::DevBuf legCum;     // double[W] running chord length of every waypoint inside its (merged) segment
+  nb2::DevBuf legSeg;     // uint4[S] surviving merged segments {begin, end, samples, first sample} relative to their plane
+  nb2::DevBuf legPlane;   // uint4[2 (P + 1)] per plane {has path, segments, samples} and its exclusive prefix
+  nb2::DevBuf legPose;    // double[16 W'] resampled poses
+  nb2::DevBuf legPos, legNrm, legSegLen;
   // normals workspace
   nb2::DevBuf faceNrm;   // float4[F]
   nb2::DevBuf valence;   // uint32[V + 1]
@@ -286,6 +292,10 @@ void shardedHostToDevice(nb2_context* c, void* dst, const void* src, size_t byte
 // result storage (api.cu)
 nb2_result* allocResult(nb2_context* c, uint64_t n_paths, uint64_t n_segments, uint64_t n_waypoints, bool edges, bool poses);
 void freeResult(nb2_result* r);
+
+// legacy modifiers on the device (kernels_legacy.cu): returns {paths, segments, samples} and the per-plane counts
+void launchLegacy(nb2_context* c, uint64_t nP, uint64_t W, uint64_t S, double point_spacing, double min_segment_size,
+                  double min_hole_size, uint64_t totals[3], std::vector<uint32_t>& host_planeL);
 
 // host-side tool path post-ops (toolpath.cpp)
 void rasterOrganization(nb2_result*& r);

@@ -275,13 +275,18 @@ Seg resample(const Seg& in, double spacing)
   double s = rem < spacing / 2.0 ? spacing / 2.0 + rem / 2.0 : rem / 2.0;
   for (; s < l; s += spacing)
   {
+    // first knot within machine epsilon of s (the reference scans all knots; kd is non-decreasing, so the first
+    // candidate is the first knot above s - eps)
     size_t hit = n;
-    for (size_t i = 0; i < n; ++i)
-      if (std::abs(kd[i] - s) < std::numeric_limits<double>::epsilon())
-      {
-        hit = i;
-        break;
-      }
+    {
+      const double eps = std::numeric_limits<double>::epsilon();
+      for (size_t i = std::lower_bound(kd.begin(), kd.end(), s - eps) - kd.begin(); i < n && kd[i] <= s + eps; ++i)
+        if (std::abs(kd[i] - s) < eps)
+        {
+          hit = i;
+          break;
+        }
+    }
     if (hit != n)
     {
       const size_t span = std::min(hit, n - 2);

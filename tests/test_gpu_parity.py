@@ -628,3 +628,51 @@ def test_pca_rotated_direction_generator(ctx, orc, ply_mesh):
     paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, 1.05, True, direction=d, slice_mode=orc.SLICE_INTENT, frame=frame)
     assert bytes(ctx.last_lattice()) == bytes(lat)
     assert_same_paths(gpu, paths.flat(), "PCARotated plan")
+
+
+@pytest.mark.parametrize("min_hole,min_seg", [(0.0, 0.03), (0.0, 0.12), (0.35, 0.03), (0.35, 0.3)])
+def test_legacy_modifiers_on_device_match_oracle(ctx, orc, min_hole, min_seg):
+    """JoinCloseSegments / MinimumSegmentLength / UniformSpacing run on the GPU (kernels_legacy.cu) on the slicer's
+    result while it is still in HBM.  Against the oracle's sequential double arithmetic: same structure, poses bit for
+    bit.  The mesh has a hole (two segments per raster there): min_hole_size 0.35 bridges it where it is narrow,
+    min_segment_size drops the short rasters near the rim."""
+    import noether_b200 as nb
+    blob, xyz, nrm, tri = _wavy_mesh(160, 128, hole=True)
+    pl = nb.PlaneSlicerLegacyRasterPlanner(nb.FixedDirectionGenerator([0.0, 1.0, 0.0]), nb.FixedOriginGenerator([0.0, 0.0, 0.0]),
+                                           0.013, min_seg, min_hole, ctx)
+    pl.set_line_spacing(0.0171)
+    if min_hole == 0.0 and min_seg == 0.03:
+        # without a length filter a two-point sliver at the rim of the hole reaches UniformSpacing, which refuses it
+        # (uniform_spacing_modifier.cpp:20-21): same error from the device path and from the oracle
+        from noether_b200 import _capi
+        import oracle
+        p0 = nb.PlaneSlicerLegacyRasterPlanner(nb.FixedDirectionGenerator([0.0, 1.0, 0.0]),
+                                               nb.FixedOriginGenerator([0.0, 0.0, 0.0]), 0.013, 0.0, 0.0, ctx)
+        p0.set_line_spacing(0.0171)
+        try:
+            p0.plan(blob).free()
+            gpu_refuses = False
+        except _capi.Nb2Error as e:
+            gpu_refuses = e.status == _capi.NB2_ERR_SEGMENT_TOO_SHORT
+        try:
+            orc.plan_plane_slicer_legacy(xyz, nrm, tri, 0.0171, 0.013, 0.0, 0.0, True, [0, 1, 0], [0, 0, 0],
+                                         slice_mode=orc.SLICE_INTENT, frame=oracle_pca_from_capi(orc, ctx.pca()))
+            orc_refuses = False
+        except oracle.OracleError:
+            orc_refuses = True
+        assert gpu_refuses == orc_refuses
+    gpu = pl.plan(blob)
+    paths, lat, _ = orc.plan_plane_slicer_legacy(xyz, nrm, tri, 0.0171, 0.013, min_seg, min_hole, True, [0, 1, 0], [0, 0, 0],
+                                                 slice_mode=orc.SLICE_INTENT, frame=oracle_pca_from_capi(orc, ctx.pca()))
+    ref = paths.flat()
+    assert gpu.legacy and gpu.n_paths == ref.num_paths > 40
+    np.testing.assert_array_equal(gpu.path_offsets.astype(np.uint64), ref.path_off)
+    np.testing.assert_array_equal(gpu.segment_offsets.astype(np.uint64), ref.seg_off)
+    np.testing.assert_array_equal(gpu.path_plane, ref.path_plane)
+    if min_hole == 0.0:
+        assert (gpu.segments_per_path() == 2).sum() > 10      # the hole splits rasters ...
+    else:
+        assert (gpu.segments_per_path() == 2).sum() < (np.diff(ref.path_off.astype(np.int64)) >= 1).sum()
+    np.testing.assert_array_equal(gpu.poses(), ref.pose)      # bit for bit
+    np.testing.assert_array_equal(bits(gpu.positions), bits(ref.pos))
+    np.testing.assert_array_equal(bits(gpu.normals), bits(ref.nrm))
