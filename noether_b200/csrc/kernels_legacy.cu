@@ -9,9 +9,10 @@
 // running sum of the chord lengths plus a linear interpolation inside the span (the closed form the host restatement
 // in toolpath.cpp uses as well).  The reference's arithmetic is sequential along a segment — the running sum of chord
 // lengths, the sample distances s += point_spacing, the z axis propagated from pose to pose — so the unit of
-// parallelism is the segment: one thread per tool path (L1) or per surviving segment (L3) walks its waypoints in
-// order, in double, with the host code's operation order (host_math.h), and the rasters of a plan (hundreds to
-// thousands) supply the parallelism.  Only the resampled poses ever leave the GPU.
+// parallelism is the segment: one warp per tool path (L1) or per surviving segment (L3).  Whatever is independent per
+// waypoint (chord lengths, span lookups, the x and y columns) is spread over the lanes; the sequential recurrences are
+// evaluated with the reference's additions in the reference's order (host_math.h), so the poses are bit-identical to
+// the sequential code.  Only the resampled poses ever leave the GPU.
 //
 //   L1  k_legacy_measure  : per tool path: join consecutive segments closer than min_hole_size, running chord length of
 //                           every waypoint (kept for L3), drop segments shorter than min_segment_size, count samples
@@ -42,12 +43,19 @@ __device__ __forceinline__ double firstSample(double l, double spacing)
   return rem < spacing / 2.0 ? spacing / 2.0 + rem / 2.0 : rem / 2.0;
 }
 
+/**
+ * L1: one WARP per tool path.  The chord lengths of 32 consecutive waypoints are computed in parallel (coalesced
+ * loads); only their running sum is sequential, and every lane forms its own prefix by adding the warp's chord
+ * lengths in waypoint order — ((acc + d0) + d1) + ... — i.e. with exactly the additions, in exactly the order, of
+ * the reference's loop, so the result is bit-identical to the sequential sum.
+ */
 __global__ void __launch_bounds__(128)
     k_legacy_measure(const float* __restrict__ pos, const unsigned* __restrict__ segLen, const unsigned* __restrict__ planeMeta,
                      const uint2* __restrict__ prefix, unsigned nP, double min_hole, double min_len, double spacing,
                      double* __restrict__ cum, uint4* __restrict__ mseg, uint4* __restrict__ planeL, unsigned* __restrict__ err)
 {
-  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
   if (k >= nP)
     return;
   const unsigned Sk = planeMeta[2 * k + 1];
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(128)
   unsigned kept = 0, samples = 0;
   unsigned long long w = before.x;  // first waypoint of the next original segment
   unsigned j = 0;
-  while (j < Sk)
+  while (j < Sk)  // (uniform across the warp: every lane evaluates the same scalars)
   {
     // merged segment: original segments j .. as long as the gap to the next one is below min_hole_size
     const unsigned long long mb = w;
@@ -70,32 +78,47 @@ __global__ void __launch_bounds__(128)
       ++j;
     }
     w = me;
-    // running chord length, sequential as computeLength / the knot distances of the reference
+    // running chord length, in the order of computeLength / the knot distances of the reference
     double acc = 0.0;
-    D3 prev = pointOf(pos, mb);
-    cum[mb] = 0.0;
-    for (unsigned long long i = mb + 1; i < me; ++i)
+    if (lane == 0)
+      cum[mb] = 0.0;
+    for (unsigned long long base = mb + 1; base < me; base += 32)
     {
-      const D3 p = pointOf(pos, i);
-      acc += norm(p - prev);
-      cum[i] = acc;
-      prev = p;
+      const unsigned long long i = base + lane;
+      double d = 0.0;
+      if (i < me)
+        d = norm(pointOf(pos, i) - pointOf(pos, i - 1));
+      double run = acc;
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t)
+      {
+        const double v = __shfl_sync(kFull, d, t);
+        if (t <= static_cast<int>(lane))
+          run += v;
+      }
+      if (i < me)
+        cum[i] = run;
+      const unsigned long long last = min(static_cast<unsigned long long>(31), me - 1 - base);
+      acc = __shfl_sync(kFull, run, static_cast<int>(last));
     }
     if (acc < min_len)
       continue;  // MinimumSegmentLength drops it
     if (me - mb < 3)
     {
-      atomicOr(err, 1u);  // uniform_spacing_modifier.cpp:20-21 throws: fewer than degree + 2 waypoints
+      if (lane == 0)
+        atomicOr(err, 1u);  // uniform_spacing_modifier.cpp:20-21 throws: fewer than degree + 2 waypoints
       continue;
     }
     unsigned cnt = 2;  // u = 0 and u = 1
     for (double s = firstSample(acc, spacing); s < acc; s += spacing)
       ++cnt;
-    mseg[before.y + kept] = make_uint4(static_cast<unsigned>(mb - before.x), static_cast<unsigned>(me - before.x), cnt, samples);
+    if (lane == 0)
+      mseg[before.y + kept] = make_uint4(static_cast<unsigned>(mb - before.x), static_cast<unsigned>(me - before.x), cnt, samples);
     ++kept;
     samples += cnt;
   }
-  planeL[k] = make_uint4(kept ? 1u : 0u, kept, samples, 0u);
+  if (lane == 0)
+    planeL[k] = make_uint4(kept ? 1u : 0u, kept, samples, 0u);
 }
 
 /** Exclusive prefix over the planes of {surviving paths, segments, samples}; totals at [nP]. */
@@ -149,6 +172,13 @@ __global__ void __launch_bounds__(1024) k_legacy_scan(const uint4* __restrict__ 
     out[nP] = s_carry;
 }
 
+/**
+ * L3: one WARP per surviving segment.
+ *   a. the sample distances s_k (s += spacing, sequential) are generated by every lane in lockstep; the lanes then look
+ *      their samples' spans up side by side (bisection in the running chord lengths): position and span direction
+ *   b. the reference z is propagated from sample to sample out of registers (the only sequential dependency)
+ *   c. all lanes finish their poses: x = tangent, y = z_prev x x, columns normalised
+ */
 __global__ void __launch_bounds__(128)
     k_legacy_resample(const float* __restrict__ pos, const float* __restrict__ nrm, const double* __restrict__ cum,
                       const unsigned* __restrict__ planeMeta, const uint2* __restrict__ prefix,
@@ -156,9 +186,9 @@ __global__ void __launch_bounds__(128)
                       unsigned nP, unsigned maxSegsPerPlane, double spacing, double* __restrict__ outPose,
                       float* __restrict__ outPos, float* __restrict__ outNrm, unsigned* __restrict__ outSegLen)
 {
-  // thread = (plane, surviving segment of that plane)
-  const unsigned long long tid = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const unsigned k = static_cast<unsigned>(tid / maxSegsPerPlane), m = static_cast<unsigned>(tid % maxSegsPerPlane);
+  const unsigned long long wid = (static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned k = static_cast<unsigned>(wid / maxSegsPerPlane), m = static_cast<unsigned>(wid % maxSegsPerPlane);
   if (k >= nP || m >= planeL[k].y)
     return;
   const uint2 before = prefix[k];
@@ -166,62 +196,114 @@ __global__ void __launch_bounds__(128)
   const unsigned long long mb = static_cast<unsigned long long>(before.x) + sg.x, me = static_cast<unsigned long long>(before.x) + sg.y;
   const unsigned long long n = me - mb;
   const uint4 lp = planeLPrefix[k];
-  unsigned long long o = static_cast<unsigned long long>(lp.z) + sg.w;  // first output sample of this segment
-  outSegLen[lp.y + m] = sg.z;
+  const unsigned long long o0 = static_cast<unsigned long long>(lp.z) + sg.w;  // first output sample of this segment
+  const unsigned cnt = sg.z;
+  if (lane == 0)
+    outSegLen[lp.y + m] = cnt;
   const double* kd = cum + mb;
   const double l = kd[n - 1];
-
-  // reference z: the z column of the first waypoint's pose (createTransform: normal.normalized())
-  D3 ref_z = normalized(D3{ static_cast<double>(nrm[3 * mb]), static_cast<double>(nrm[3 * mb + 1]), static_cast<double>(nrm[3 * mb + 2]) });
-  auto emit = [&](const D3& p, const D3& tangent) {
-    const D3 x = tangent;
-    const D3 y = cross(ref_z, x);
-    const D3 z = cross(x, y);
-    const D3 xn = normalized(x), yn = normalized(y), zn = normalized(z);
-    double* T = outPose + 16ull * o;
-    T[0] = xn.x, T[1] = xn.y, T[2] = xn.z, T[3] = 0.0;
-    T[4] = yn.x, T[5] = yn.y, T[6] = yn.z, T[7] = 0.0;
-    T[8] = zn.x, T[9] = zn.y, T[10] = zn.z, T[11] = 0.0;
-    T[12] = p.x, T[13] = p.y, T[14] = p.z, T[15] = 1.0;
-    outPos[3 * o] = static_cast<float>(p.x), outPos[3 * o + 1] = static_cast<float>(p.y), outPos[3 * o + 2] = static_cast<float>(p.z);
-    outNrm[3 * o] = static_cast<float>(zn.x), outNrm[3 * o + 1] = static_cast<float>(zn.y), outNrm[3 * o + 2] = static_cast<float>(zn.z);
-    ref_z = zn;
-    ++o;
-  };
   auto P = [&](unsigned long long i) { return pointOf(pos, mb + i); };
+  // position -> T[12..14], span direction -> T[0..2] (normalised in step c)
+  auto stage = [&](unsigned long long o, const D3& p, const D3& tangent) {
+    double* T = outPose + 16ull * o;
+    T[0] = tangent.x, T[1] = tangent.y, T[2] = tangent.z;
+    T[12] = p.x, T[13] = p.y, T[14] = p.z;
+  };
 
-  emit(P(0), P(1) - P(0));  // u = 0
-  // the sample distances only grow, so the lookups share one cursor: `at` = first knot >= s - eps
-  const double eps = DBL_EPSILON;
-  unsigned long long at = 0;
-  for (double s = firstSample(l, spacing); s < l; s += spacing)
+  // ---- a: positions and span directions ------------------------------------------------------------------------------
+  if (lane == 0)
   {
-    while (at < n && kd[at] < s - eps)
-      ++at;
-    // estimateSplineParameterAtDistance (splines.cpp:107-144): a knot within epsilon of s is hit exactly ...
-    unsigned long long hit = n;
-    for (unsigned long long i = at; i < n && kd[i] <= s + eps; ++i)
-      if (fabs(kd[i] - s) < eps)
-      {
-        hit = i;
-        break;
-      }
-    if (hit != n)
-    {
-      const unsigned long long span = hit < n - 2 ? hit : n - 2;
-      emit(P(hit), P(span + 1) - P(span));
-      continue;
-    }
-    // ... otherwise the span is the one ending at the first knot >= s
-    unsigned long long hi = at;
-    while (kd[hi] < s)
-      ++hi;
-    const unsigned long long lo = hi - 1;
-    const double f = (s - kd[lo]) / (kd[hi] - kd[lo]);
-    const D3 a = P(lo), b = P(hi);
-    emit(a + f * (b - a), b - a);
+    stage(o0, P(0), P(1) - P(0));                        // u = 0
+    stage(o0 + cnt - 1, P(n - 1), P(n - 1) - P(n - 2));  // u = 1
   }
-  emit(P(n - 1), P(n - 1) - P(n - 2));  // u = 1
+  {
+    // a1: the sample distances are a sequential recurrence (s += spacing): every lane runs it, lane q mod 32 parks s_q in
+    //     the (not yet written) last element of sample q's pose
+    unsigned q = 0;
+    for (double s = firstSample(l, spacing); s < l; s += spacing, ++q)
+      if ((q & 31u) == lane)
+        outPose[16ull * (o0 + 1 + q) + 15] = s;
+    __syncwarp();
+    // a2: the lanes look their samples up side by side
+    const double eps = DBL_EPSILON;
+    for (q = lane; q + 2 < cnt; q += 32)
+    {
+      const double s = outPose[16ull * (o0 + 1 + q) + 15];
+      // first knot >= s - eps (bisection; kd is non-decreasing, kd[0] = 0 < s - eps, kd[n - 1] = l > s)
+      unsigned long long lo_i = 0, hi_i = n - 1;
+      while (hi_i - lo_i > 1)
+      {
+        const unsigned long long mid = (lo_i + hi_i) >> 1;
+        if (kd[mid] < s - eps)
+          lo_i = mid;
+        else
+          hi_i = mid;
+      }
+      const unsigned long long at = hi_i;
+      // estimateSplineParameterAtDistance (splines.cpp:107-144): a knot within epsilon of s is hit exactly ...
+      unsigned long long hit = n;
+      for (unsigned long long i = at; i < n && kd[i] <= s + eps; ++i)
+        if (fabs(kd[i] - s) < eps)
+        {
+          hit = i;
+          break;
+        }
+      if (hit != n)
+      {
+        const unsigned long long span = hit < n - 2 ? hit : n - 2;
+        stage(o0 + 1 + q, P(hit), P(span + 1) - P(span));
+        continue;
+      }
+      // ... otherwise the span is the one ending at the first knot >= s
+      unsigned long long hi = at;
+      while (kd[hi] < s)
+        ++hi;
+      const unsigned long long lo = hi - 1;
+      const double f = (s - kd[lo]) / (kd[hi] - kd[lo]);
+      const D3 a = P(lo), b = P(hi);
+      stage(o0 + 1 + q, a + f * (b - a), b - a);
+    }
+  }
+  __syncwarp();
+
+  // ---- b + c: poses.  The reference z is propagated from sample to sample (uniform_spacing_modifier.cpp:39-48):
+  //      z_k = normalised x_k x (z_{k-1} x x_k), starting from the z column of the segment's first waypoint
+  //      (createTransform: normal.normalized()).  Per chunk of 32 samples every lane loads one span direction; the
+  //      recurrence then runs out of registers (shuffles), all lanes in lockstep, and lane t keeps the z it needs ------
+  D3 ref_z = normalized(D3{ static_cast<double>(nrm[3 * mb]), static_cast<double>(nrm[3 * mb + 1]), static_cast<double>(nrm[3 * mb + 2]) });
+  for (unsigned base = 0; base < cnt; base += 32)
+  {
+    const unsigned q = base + lane;
+    const bool mine = q < cnt;
+    double* T = outPose + 16ull * (o0 + (mine ? q : 0));
+    D3 x = { 1.0, 0.0, 0.0 };
+    if (mine)
+      x = D3{ T[0], T[1], T[2] };
+    D3 my_prev = ref_z, my_z = ref_z;
+    const unsigned m_chunk = min(32u, cnt - base);
+    for (unsigned t = 0; t < m_chunk; ++t)
+    {
+      const D3 xt = { __shfl_sync(kFull, x.x, t), __shfl_sync(kFull, x.y, t), __shfl_sync(kFull, x.z, t) };
+      const D3 zn = normalized(cross(xt, cross(ref_z, xt)));
+      if (lane == t)
+      {
+        my_prev = ref_z;
+        my_z = zn;
+      }
+      ref_z = zn;
+    }
+    if (mine)
+    {
+      const unsigned long long o = o0 + q;
+      const D3 xn = normalized(x), yn = normalized(cross(my_prev, x));
+      T[0] = xn.x, T[1] = xn.y, T[2] = xn.z, T[3] = 0.0;
+      T[4] = yn.x, T[5] = yn.y, T[6] = yn.z, T[7] = 0.0;
+      T[8] = my_z.x, T[9] = my_z.y, T[10] = my_z.z, T[11] = 0.0;
+      T[15] = 1.0;
+      outPos[3 * o] = static_cast<float>(T[12]), outPos[3 * o + 1] = static_cast<float>(T[13]), outPos[3 * o + 2] = static_cast<float>(T[14]);
+      outNrm[3 * o] = static_cast<float>(my_z.x), outNrm[3 * o + 1] = static_cast<float>(my_z.y), outNrm[3 * o + 2] = static_cast<float>(my_z.z);
+    }
+  }
 }
 }  // namespace
 
@@ -239,7 +321,7 @@ void launchLegacy(nb2_context* c, uint64_t nP, uint64_t W, uint64_t S, double po
   unsigned* err = c->counters.as<unsigned>() + 14;
   NB2_CUDA(cudaMemsetAsync(err, 0, sizeof(unsigned), c->stream));
   const unsigned np = static_cast<unsigned>(nP);
-  k_legacy_measure<<<(np + 127) / 128, 128, 0, c->stream>>>(c->outPos.as<float>(), c->outSegLen.as<unsigned>(),
+  k_legacy_measure<<<(np + 3) / 4, 128, 0, c->stream>>>(c->outPos.as<float>(), c->outSegLen.as<unsigned>(),
                                                             c->planeMeta.as<unsigned>(), c->planePrefix.as<uint2>(), np,
                                                             min_hole_size, min_segment_size, point_spacing,
                                                             c->legCum.as<double>(), c->legSeg.as<uint4>(), planeL, err);
@@ -273,8 +355,8 @@ void launchLegacy(nb2_context* c, uint64_t nP, uint64_t W, uint64_t S, double po
   c->legPos.ensure(sizeof(float) * 3 * totals[2]);
   c->legNrm.ensure(sizeof(float) * 3 * totals[2]);
   c->legSegLen.ensure(sizeof(unsigned) * totals[1]);
-  const unsigned long long threads = nP * static_cast<unsigned long long>(max_segs);
-  k_legacy_resample<<<static_cast<unsigned>((threads + 127) / 128), 128, 0, c->stream>>>(
+  const unsigned long long warps = nP * static_cast<unsigned long long>(max_segs);
+  k_legacy_resample<<<static_cast<unsigned>((warps + 3) / 4), 128, 0, c->stream>>>(
       c->outPos.as<float>(), c->outNrm.as<float>(), c->legCum.as<double>(), c->planeMeta.as<unsigned>(),
       c->planePrefix.as<uint2>(), c->legSeg.as<uint4>(), planeL, planeLPrefix, np, max_segs, point_spacing,
       c->legPose.as<double>(), c->legPos.as<float>(), c->legNrm.as<float>(), c->legSegLen.as<unsigned>());

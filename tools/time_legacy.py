@@ -26,3 +26,4 @@ for legacy in (False, True):
         t2 = time.perf_counter()
         print(name, 'legacy' if legacy else 'plain', 'plan %.1f ms' % (1e3 * (t1 - t0)), 'poses %.1f ms' % (1e3 * (t2 - t1)), r.n_paths, r.n_segments, r.n_waypoints)
         r.free()
+print({k: round(v, 4) for k, v in ctx.timings().items()})
