@@ -1359,8 +1359,14 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
       W.cap = cap;
       linkPlane<uint16_t>(P, W, kLocal, n, s_misc);
     }
+    else if (n <= 16384u && linkPlaneFast(P, P.scratch + P.scratchStride * blockIdx.x, kLocal, n, cap, s_misc))
+    {
+      // a plane too large for shared memory but within 16-bit indices: the fast path again, its work area in this
+      // CTA's slice of the global scratch (L2 resident)
+    }
     else
     {
+      __syncthreads();
       uint8_t* g = P.scratch + P.scratchStride * blockIdx.x;
       PlaneWork<uint32_t> W;
       W.eposBytes = 32ull * E;  // 8 index arrays of 4 E bytes

@@ -219,11 +219,13 @@ def test_slice_plane_slabs_concatenate(ctx, orc):
     np.testing.assert_array_equal(np.concatenate(planes), gpu.path_plane)
 
 
-def test_large_plane_uses_global_scratch(ctx, orc):
-    # one plane with more hits than fit the shared-memory work area (> 4096): the global-memory fallback
-    blob, xyz, nrm, tri = _wavy_mesh(8, 2600, lx=0.05, ly=2.0)
+@pytest.mark.parametrize("ny,longest", [(2600, 4200), (9000, 17000)])
+def test_large_plane_uses_global_scratch(ctx, orc, ny, longest):
+    # planes with more hits than fit the shared-memory work area (about 4600): 5200 hits take the linker's fast path with
+    # its work area in global memory (16-bit indices), 18000 hits the general path with 32-bit indices
+    blob, xyz, nrm, tri = _wavy_mesh(8, ny, lx=0.05, ly=2.0)
     gpu, ref, lat = _slice_both(ctx, orc, blob, xyz, nrm, tri, 0.0125, [0, 1, 0], [0.0281, 1.0, 0])
-    assert np.diff(ref.seg_off.astype(np.int64)).max() > 4200
+    assert np.diff(ref.seg_off.astype(np.int64)).max() > longest
     assert_same_paths(gpu, ref, "large plane")
 
 
