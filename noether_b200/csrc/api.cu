@@ -697,7 +697,7 @@ void nb2_context_destroy(nb2_context* c)
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
-                     &c->csrAdj, &c->scanState })
+                     &c->csrAdj, &c->csrRank, &c->scanState })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)

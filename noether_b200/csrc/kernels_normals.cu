@@ -20,7 +20,8 @@ constexpr unsigned kFull = 0xffffffffu;
 
 __global__ void __launch_bounds__(256)
     k_face_normals(const uint32_t* __restrict__ tri, unsigned long long F, const float4* __restrict__ pos,
-                   float4* __restrict__ faceNrm, unsigned* __restrict__ valence)
+                   float4* __restrict__ faceNrm, unsigned* __restrict__ valence, uint16_t* __restrict__ rank,
+                   unsigned* __restrict__ rankOverflow)
 {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long f = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; f < F; f += stride)
@@ -43,9 +44,14 @@ __global__ void __launch_bounds__(256)
       nz = __fdiv_rn(nz, s);
     }
     faceNrm[f] = make_float4(nx, ny, nz, 0.f);
-    atomicAdd(valence + a, 1u);
-    atomicAdd(valence + b, 1u);
-    atomicAdd(valence + c, 1u);
+    // the count doubles as the corner's slot inside its vertex's CSR row: the fill pass then needs no second round of
+    // atomics (the order inside a row is arbitrary; k_vertex_normals sorts each row by face id)
+    const unsigned ra = atomicAdd(valence + a, 1u), rb = atomicAdd(valence + b, 1u), rc = atomicAdd(valence + c, 1u);
+    if (max(ra, max(rb, rc)) >= 0xffffu)
+      *rankOverflow = 1u;  // a vertex with 65535 or more incident faces: the fill pass falls back to its own cursors
+    rank[3 * f] = static_cast<uint16_t>(ra);
+    rank[3 * f + 1] = static_cast<uint16_t>(rb);
+    rank[3 * f + 2] = static_cast<uint16_t>(rc);
   }
 }
 
@@ -133,8 +139,10 @@ __global__ void __launch_bounds__(kScanThreads)
 
 __global__ void __launch_bounds__(256)
     k_csr_fill(const uint32_t* __restrict__ tri, unsigned long long F, const unsigned* __restrict__ rowOff,
-               unsigned* __restrict__ cursor, uint32_t* __restrict__ adj)
+               unsigned* __restrict__ cursor, const uint16_t* __restrict__ rank, const unsigned* __restrict__ rankOverflow,
+               uint32_t* __restrict__ adj)
 {
+  const bool use_rank = *rankOverflow == 0u;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long f = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; f < F; f += stride)
   {
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(256)
     for (int k = 0; k < 3; ++k)
     {
       const uint32_t v = __ldg(tri + 3 * f + k);
-      const unsigned slot = __ldg(rowOff + v) + atomicAdd(cursor + v, 1u);
+      const unsigned slot = __ldg(rowOff + v) + (use_rank ? static_cast<unsigned>(rank[3 * f + k]) : atomicAdd(cursor + v, 1u));
       adj[slot] = static_cast<uint32_t>(f);
     }
   }
@@ -273,6 +281,7 @@ void launchVertexNormals(nb2_context* c)
   c->csrOff.ensure(sizeof(unsigned) * (V + 1));
   c->csrCursor.ensure(sizeof(unsigned) * (V + 1));
   c->csrAdj.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+  c->csrRank.ensure(sizeof(uint16_t) * 3 * std::max<uint64_t>(F, 1));
   c->nrm.ensure(sizeof(float4) * V);
   c->nrm_base = c->nrm.as<uint8_t>();  // the computed normals replace whatever the cloud carried
   c->nrm_stride = 16;
@@ -283,11 +292,13 @@ void launchVertexNormals(nb2_context* c)
   NB2_CUDA(cudaMemsetAsync(c->csrCursor.ptr, 0, sizeof(unsigned) * (V + 1), c->stream));
   NB2_CUDA(cudaMemsetAsync(c->scanState.ptr, 0, sizeof(unsigned long long) * (tiles + 1), c->stream));
   NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 13, 0, sizeof(unsigned), c->stream));
+  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 15, 0, sizeof(unsigned), c->stream));  // rank overflow flag
 
   if (F)
   {
     k_face_normals<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->tri.as<uint32_t>(), F, c->pos.as<float4>(),
-                                                                             c->faceNrm.as<float4>(), c->valence.as<unsigned>());
+                                                                             c->faceNrm.as<float4>(), c->valence.as<unsigned>(),
+                                                                             c->csrRank.as<uint16_t>(), c->counters.as<unsigned>() + 15);
     NB2_CUDA(cudaGetLastError());
     ++c->launches;
   }
@@ -301,7 +312,8 @@ void launchVertexNormals(nb2_context* c)
   if (F)
   {
     k_csr_fill<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->tri.as<uint32_t>(), F, c->csrOff.as<unsigned>(),
-                                                                         c->csrCursor.as<unsigned>(), c->csrAdj.as<uint32_t>());
+                                                                         c->csrCursor.as<unsigned>(), c->csrRank.as<uint16_t>(),
+                                                                         c->counters.as<unsigned>() + 15, c->csrAdj.as<uint32_t>());
     NB2_CUDA(cudaGetLastError());
     ++c->launches;
   }

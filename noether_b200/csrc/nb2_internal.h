@@ -201,6 +201,7 @@ struct nb2_context
   nb2::DevBuf csrOff;    // uint32[V + 1]
   nb2::DevBuf csrCursor; // uint32[V]
   nb2::DevBuf csrAdj;    // uint32[3F]
+  nb2::DevBuf csrRank;   // uint16[3F] slot of every triangle corner inside its vertex's CSR row
   nb2::DevBuf scanState; // uint64[num tiles] look-back status for the generic scan
   // host staging
   nb2::PinnedBuf hostSmall;  // small read-backs
