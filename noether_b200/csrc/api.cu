@@ -345,9 +345,8 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   if (fp)
     ensureExtents(c);
 
-  c->hostSmall.ensure(8192 + sizeof(FrameDev));
-  auto* hf = c->hostSmall.as<FrameDev>();
-  unsigned* h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
+  FrameDev* hf = nullptr;
+  unsigned* h = nullptr;
   // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
   //           [12] largest out-of-range vertex index, [13] capacity overflow bits
   auto resetCounters = [&](int first) {
@@ -356,9 +355,20 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + first, init + first, (16 - first) * sizeof(unsigned),
                              cudaMemcpyHostToDevice, c->stream));
   };
-  auto readSizes = [&]() {
+  // The per-plane {waypoints, segments} counts ride along with the sizes when the plane count of the previous plan is
+  // known (it sizes the copy; a plan with more planes fetches the rest afterwards): one synchronisation at the end
+  // of a plan instead of two.
+  const uint64_t meta_hint = std::min<uint64_t>(c->grid_planes, c->plane_cap);
+  c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * (meta_hint + 1));
+  hf = c->hostSmall.as<FrameDev>();
+  h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
+  bool meta_fetched = false;
+  auto readSizes = [&](bool with_meta = false) {
     NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    meta_fetched = with_meta && meta_hint > 0;
+    if (meta_fetched)
+      NB2_CUDA(cudaMemcpyAsync(h + 16, c->planeMeta.ptr, sizeof(unsigned) * 2 * meta_hint, cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaStreamSynchronize(c->stream));
   };
   const unsigned smem_cap = linkSmemHitCap(c);
@@ -418,7 +428,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     if (!sizes_known || (c->hit_cap && !hf->plane_cap_exceeded && hf->lattice_status == 0 && h[0] > 0))
     {
       stageTwo();
-      readSizes();
+      readSizes(true);
       sizes_known = true;
     }
     deferredMeshChecks(c, *hf);
@@ -475,21 +485,24 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     NB2_CUDA(cudaMemsetAsync(c->planeCursor.ptr, 0, sizeof(unsigned) * (static_cast<size_t>(c->plane_cap) + 1), c->stream));
     resetCounters(6);
     stageTwo();
-    readSizes();
+    readSizes(true);
     if (h[9])
       fail(NB2_ERR_INTERNAL, "buffer capacities could not be settled");
   }
   const uint64_t w_cap = 2 * c->hit_cap;
 
-  // per-plane meta and status
-  c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * nP);
-  h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
-  // (h[2..3] = counters[6..7] = waypoint / segment totals, h[6..7] = counters[10..11] = link status; re-read: the
-  //  staging area may have moved)
+  // per-plane meta and status (h[2..3] = counters[6..7] = waypoint / segment totals, h[6..7] = counters[10..11] = link
+  // status).  The meta came with the sizes unless this plan has more planes than the previous one.
   unsigned* hmeta = h + 16;
-  NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
-  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  if (!meta_fetched || nP > meta_hint)
+  {
+    c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * (nP + 1));  // (may move the staging area)
+    h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
+    hmeta = h + 16;
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+  }
   const unsigned* hstat = h + 6;
   if (hstat[0])
   {
