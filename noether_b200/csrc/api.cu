@@ -267,11 +267,11 @@ const char* kNoNormalsMessage =
 /** k_extents once per resident mesh (the eigen axes were finalised on the device right after the ingest pass) */
 void ensureExtents(nb2_context* c)
 {
-  if (c->frame_pca_done || c->V < 3)
+  if (c->extents_done || c->V < 3)
     return;
   launchExtents(c);
   c->timer.mark("extents", c->stream);
-  c->frame_pca_done = true;
+  c->extents_done = true;
 }
 
 /** Checks that were postponed because the mesh was adopted from device memory without a synchronisation */
@@ -706,7 +706,7 @@ void nb2_context_destroy(nb2_context* c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
-  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->extents, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
+  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
@@ -745,7 +745,7 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
 
   c->V = 0;
   c->pca_valid = false;
-  c->frame_pca_done = false;
+  c->extents_done = false;
   const uint64_t V = m->n_points, F = m->n_triangles;
   c->timer_upload.begin(c->stream);
   // Inputs that already live in this GPU's memory are used in place (no copy; the caller keeps them alive until the
@@ -820,7 +820,7 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
   // mean, covariance and eigen axes are finalised on the device, straight from the reduction's total
   launchFramePca(c, reinterpret_cast<const float*>(c->blob.as<uint8_t>() + m->offset_xyz));
   c->timer_upload.mark("frame", c->stream);
-  c->frame_pca_done = false;
+  c->extents_done = false;
   c->pca_valid = false;
   std::memset(&c->pca, 0, sizeof(c->pca));
   if (tri_adopted || onThisDevice(m->cloud_data))

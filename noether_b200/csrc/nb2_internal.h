@@ -162,10 +162,9 @@ struct nb2_context
   nb2::DevBuf tri;       // uint32[3F]
   // moments / frame
   nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
-  nb2::DevBuf extents;   // float[6] min/max in PCA frame (+ block partials)
   nb2::DevBuf counters;  // misc device counters (zeroed per plan)
   nb2::DevBuf frame;     // FrameDev
-  bool frame_pca_done = false;  // k_frame_pca + k_extents have run for the resident mesh
+  bool extents_done = false;    // k_extents has run for the resident mesh (OBB extents are in FrameDev::ext)
   bool checks_deferred = false; // mesh adopted from device memory: non-finite / index checks happen at the next sync
   bool pca_valid = false;       // host copy below is current
   nb2_pca pca{};
