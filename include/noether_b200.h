@@ -218,6 +218,11 @@ int nb2_result_get(const nb2_result* r, nb2_result_view* out);
 /* Expand to Eigen::Isometry3d storage: 16 doubles per waypoint, column-major, last row 0 0 0 1
  * (createTransform :380-394, then DirectionOfTravelOrientationModifier when post-ops were applied). */
 int nb2_result_poses(const nb2_result* r, double* out16);
+/* The same expansion, written segment by segment into storage the caller owns: segment_out[s] receives the
+ * 16 * (waypoints of segment s) doubles of segment s (s < n_segments) — e.g. the data() of each
+ * noether::ToolPathSegment (std::vector<Eigen::Isometry3d>), so the plugin fills noether::ToolPaths without an
+ * intermediate copy.  The segments are filled in parallel on the host cores. */
+int nb2_result_poses_segments(const nb2_result* r, double* const* segment_out);
 void nb2_result_free(nb2_result* r);
 
 /* Device timings (CUDA events on the context's stream, milliseconds) of the last nb2_mesh_upload followed by those of

@@ -1175,6 +1175,18 @@ int nb2_result_poses(const nb2_result* r, double* out16)
   NB2_API_END
 }
 
+int nb2_result_poses_segments(const nb2_result* r, double* const* segment_out)
+{
+  NB2_API_BEGIN
+  if (!r || (!segment_out && r->n_segments))
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (r->n_waypoints && !r->positions)
+    fail(NB2_ERR_INVALID_ARGUMENT, "the tool paths of this result were left on the device (download = 0 or a slab of a "
+                                   "sharded plan): gather or re-plan with download = 1");
+  expandPosesSegments(*r, segment_out);
+  NB2_API_END
+}
+
 void nb2_result_free(nb2_result* r)
 {
   if (!r)

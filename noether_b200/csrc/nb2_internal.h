@@ -300,5 +300,6 @@ void launchLegacy(nb2_context* c, uint64_t nP, uint64_t W, uint64_t S, double po
 // host-side tool path post-ops (toolpath.cpp)
 void rasterOrganization(nb2_result*& r);
 void expandPoses(const nb2_result& r, double* out16);
+void expandPosesSegments(const nb2_result& r, double* const* segment_out);
 void legacyModifiers(nb2_result*& r, double point_spacing, double min_segment_size, double min_hole_size);
 }  // namespace nb2

@@ -183,18 +183,31 @@ void rasterOrganization(nb2_result*& rp)
   rp = out;
 }
 
-void expandPoses(const nb2_result& r, double* out)
+namespace
+{
+/** dst(s) = where the poses of segment s go */
+template <typename Dst>
+void expandPosesTo(const nb2_result& r, Dst dst)
 {
   if (r.poses)
   {
-    std::memcpy(out, r.poses, sizeof(double) * 16 * r.n_waypoints);
+    parallelFor(r.n_segments, 64, [&](uint64_t sb, uint64_t se) {
+      for (uint64_t s = sb; s < se; ++s)
+      {
+        const uint32_t b = r.segment_offsets[s], e = r.segment_offsets[s + 1];
+        std::memcpy(dst(s), r.poses + 16ull * b, sizeof(double) * 16 * (e - b));
+      }
+    });
     return;
   }
   const bool dot_modifier = r.post_ops_applied;
-  parallelFor(r.n_segments, 64, [&](uint64_t sb, uint64_t se) {
+  // a chunk of work = a few thousand waypoints, whatever the segment sizes
+  const uint64_t grain = std::max<uint64_t>(1, 4096 / std::max<uint64_t>(1, r.n_waypoints / std::max<uint64_t>(1, r.n_segments)));
+  parallelFor(r.n_segments, grain, [&](uint64_t sb, uint64_t se) {
     for (uint64_t s = sb; s < se; ++s)
     {
       const uint32_t b = r.segment_offsets[s], e = r.segment_offsets[s + 1];
+      double* const out = dst(s) - 16ull * b;  // so that waypoint i lands at out + 16 i
       for (uint32_t i = b; i < e; ++i)
       {
         const D3 p = fromFloat(r.positions + 3 * i);
@@ -228,6 +241,17 @@ void expandPoses(const nb2_result& r, double* out)
       }
     }
   });
+}
+}  // namespace
+
+void expandPoses(const nb2_result& r, double* out)
+{
+  expandPosesTo(r, [&](uint64_t s) { return out + 16ull * r.segment_offsets[s]; });
+}
+
+void expandPosesSegments(const nb2_result& r, double* const* segment_out)
+{
+  expandPosesTo(r, [&](uint64_t s) { return segment_out[s]; });
 }
 
 // ---------------------------------------------------------------------------------------------------------------

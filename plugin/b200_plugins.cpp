@@ -168,28 +168,23 @@ noether::ToolPaths toToolPaths(const nb2_result* r)
 {
   nb2_result_view v{};
   Device::check(nb2_result_get(r, &v));
-  std::vector<double> poses(16 * v.n_waypoints);
-  Device::check(nb2_result_poses(r, poses.data()));
-  noether::ToolPaths out;
-  out.reserve(v.n_paths);
+  // Eigen::Isometry3d is exactly its 4x4 double matrix, column-major, last row 0 0 0 1 — the layout the library writes —
+  // so every segment's storage is handed over and filled in place (in parallel, no intermediate copy)
+  static_assert(sizeof(Eigen::Isometry3d) == 16 * sizeof(double), "Isometry3d is not a bare 4x4 double matrix");
+  noether::ToolPaths out(v.n_paths);
+  std::vector<double*> segment_out(v.n_segments);
   for (std::uint64_t p = 0; p < v.n_paths; ++p)
   {
-    noether::ToolPath path;
-    path.reserve(v.path_offsets[p + 1] - v.path_offsets[p]);
+    noether::ToolPath& path = out[p];
+    path.resize(v.path_offsets[p + 1] - v.path_offsets[p]);
     for (std::uint32_t s = v.path_offsets[p]; s < v.path_offsets[p + 1]; ++s)
     {
-      noether::ToolPathSegment seg;
-      seg.reserve(v.segment_offsets[s + 1] - v.segment_offsets[s]);
-      for (std::uint32_t w = v.segment_offsets[s]; w < v.segment_offsets[s + 1]; ++w)
-      {
-        Eigen::Isometry3d pose;  // 4x4 double, column-major, last row 0 0 0 1 — the layout nb2_result_poses writes
-        std::memcpy(pose.matrix().data(), poses.data() + 16 * static_cast<std::size_t>(w), 16 * sizeof(double));
-        seg.push_back(pose);
-      }
-      path.push_back(std::move(seg));
+      noether::ToolPathSegment& seg = path[s - v.path_offsets[p]];
+      seg.resize(v.segment_offsets[s + 1] - v.segment_offsets[s]);
+      segment_out[s] = seg.empty() ? nullptr : seg.front().matrix().data();
     }
-    out.push_back(std::move(path));
   }
+  Device::check(nb2_result_poses_segments(r, segment_out.data()));
   return out;
 }
 }  // namespace

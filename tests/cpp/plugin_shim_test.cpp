@@ -16,6 +16,7 @@
 
 #include <dlfcn.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -433,6 +434,77 @@ void testGeneratorsAndErrors(const noether::Factory& factory, const pcl::Polygon
 }
 }  // namespace
 
+/** wavy(nx, ny) of SURVEY.md §8(d) as a pcl::PolygonMesh (PointXYZ cloud, one pcl::Vertices per face) */
+pcl::PolygonMesh wavyMesh(unsigned nx, unsigned ny)
+{
+  const double lx = 1.0, ly = 0.8, amp = 0.02, lam = 0.25;
+  pcl::PolygonMesh mesh;
+  pcl::PCLPointCloud2& c = mesh.cloud;
+  c.width = (nx + 1) * (ny + 1);
+  c.height = 1;
+  c.point_step = 16;
+  c.row_step = c.point_step * c.width;
+  addField(c, "x", 0), addField(c, "y", 4), addField(c, "z", 8);
+  c.data.assign(static_cast<std::size_t>(c.width) * 16, 0);
+  for (unsigned r = 0; r <= ny; ++r)
+    for (unsigned q = 0; q <= nx; ++q)
+    {
+      const double x = q * (lx / nx), y = r * (ly / ny);
+      const float p[3] = { static_cast<float>(x), static_cast<float>(y),
+                           static_cast<float>(amp * std::sin(2 * M_PI * x / lam) * std::sin(2 * M_PI * y / lam)) };
+      std::memcpy(c.data.data() + 16 * (static_cast<std::size_t>(q) + static_cast<std::size_t>(nx + 1) * r), p, 12);
+    }
+  mesh.polygons.resize(2 * static_cast<std::size_t>(nx) * ny);
+  std::size_t f = 0;
+  for (int upper = 0; upper < 2; ++upper)
+    for (unsigned r = 0; r < ny; ++r)
+      for (unsigned q = 0; q < nx; ++q)
+      {
+        const pcl::index_t i = q + (nx + 1) * r;
+        mesh.polygons[f++].vertices = upper ? std::vector<pcl::index_t>{ i, i + nx + 2, i + nx + 1 }
+                                            : std::vector<pcl::index_t>{ i, i + 1, i + nx + 2 };
+      }
+  return mesh;
+}
+
+/** What a noether application sees: NormalsFromMeshFaces, then PlaneSlicer(PrincipalAxis, Centroid), both by alias,
+ *  pcl::PolygonMesh in, nested noether::ToolPaths out.  Wall clock, second of two runs. */
+void timePipeline(const noether::Factory& factory, unsigned nx, unsigned ny, double spacing)
+{
+  const pcl::PolygonMesh raw = wavyMesh(nx, ny);
+  YAML::Node mod;
+  mod["name"] = "NormalsFromMeshFaces";
+  YAML::Node dg, og, pc;
+  dg["name"] = "PrincipalAxis";
+  dg["rotation_offset"] = 0.0;
+  og["name"] = "Centroid";
+  pc["name"] = "PlaneSlicer";
+  pc["line_spacing"] = spacing;
+  pc["bidirectional"] = true;
+  pc["direction_generator"] = dg;
+  pc["origin_generator"] = og;
+  auto modifier = factory.createMeshModifier(mod);
+  auto planner = factory.createToolPathPlanner(pc);
+  for (int run = 0; run < 2; ++run)
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    const std::vector<pcl::PolygonMesh> meshes = modifier->modify(raw);
+    const auto t1 = std::chrono::steady_clock::now();
+    const noether::ToolPaths tp = planner->plan(meshes.front());
+    const auto t2 = std::chrono::steady_clock::now();
+    std::size_t wp = 0;
+    for (const auto& path : tp)
+      for (const auto& seg : path)
+        wp += seg.size();
+    if (run == 1)
+      std::printf("[pipeline %zu triangles, spacing %g] modify %.1f ms, plan %.1f ms -> %zu tool paths, %zu waypoints "
+                  "(nested Isometry3d vectors on the host)\n",
+                  raw.polygons.size(), spacing, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                  std::chrono::duration<double, std::milli>(t2 - t1).count(), tp.size(), wp);
+    CHECK(tp.size() > 10 && wp > 1000);
+  }
+}
+
 int main(int argc, char** argv)
 {
   if (argc < 3)
@@ -460,6 +532,11 @@ int main(int argc, char** argv)
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);
     testNormalsFieldRetention(factory, ply);
     testGeneratorsAndErrors(factory, ply);
+    if (argc > 3 && std::string(argv[3]) == "--time")
+    {
+      timePipeline(factory, 800, 625, 0.005);    // cfg2: 1 M triangles
+      timePipeline(factory, 2500, 2000, 0.001);  // cfg3: 10 M triangles
+    }
   }
   catch (const std::exception& e)
   {
