@@ -29,6 +29,8 @@
 #include <pcl/PolygonMesh.h>
 #include <pcl/common/io.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -36,6 +38,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace noether_b200
@@ -142,16 +145,40 @@ MeshView makeView(const pcl::PolygonMesh& mesh, bool want_normals)
       throw std::runtime_error("Normal fields are not contiguous floats");  // utils.cpp:104-105
     m.view.offset_normal = static_cast<std::int32_t>(nx.offset);
   }
-  m.triangles.reserve(3 * mesh.polygons.size());
-  for (const auto& p : mesh.polygons)
+  // pcl::Vertices is one heap block per face: flattening 10^7 of them is pointer chasing, so it is spread over the cores
+  const std::size_t F = mesh.polygons.size();
+  m.triangles.resize(3 * F);
+  std::atomic<int> bad{ 0 };  // 1: fewer than 3 vertices, 2: not a triangle
   {
-    if (p.vertices.size() < 3)
-      throw std::runtime_error("Polygon has fewer than 3 vertices");  // getFaceNormal, utils.cpp:137-142
-    if (p.vertices.size() != 3)
-      throw std::runtime_error("noether_b200 slices triangle meshes only; triangulate the mesh first");
-    for (const auto v : p.vertices)
-      m.triangles.push_back(static_cast<std::uint32_t>(v));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const std::size_t chunks = std::min<std::size_t>(hw, (F + 65535) / 65536);
+    std::vector<std::thread> workers;
+    auto work = [&](std::size_t b, std::size_t e) {
+      for (std::size_t f = b; f < e; ++f)
+      {
+        const auto& v = mesh.polygons[f].vertices;
+        if (v.size() != 3)
+        {
+          bad.store(v.size() < 3 ? 1 : 2);
+          return;
+        }
+        m.triangles[3 * f] = static_cast<std::uint32_t>(v[0]);
+        m.triangles[3 * f + 1] = static_cast<std::uint32_t>(v[1]);
+        m.triangles[3 * f + 2] = static_cast<std::uint32_t>(v[2]);
+      }
+    };
+    const std::size_t per = chunks ? (F + chunks - 1) / chunks : 0;
+    for (std::size_t c = 1; c < chunks; ++c)
+      workers.emplace_back(work, c * per, std::min(F, (c + 1) * per));
+    if (chunks)
+      work(0, std::min(F, per));
+    for (auto& t : workers)
+      t.join();
   }
+  if (bad.load() == 1)
+    throw std::runtime_error("Polygon has fewer than 3 vertices");  // getFaceNormal, utils.cpp:137-142
+  if (bad.load() == 2)
+    throw std::runtime_error("noether_b200 slices triangle meshes only; triangulate the mesh first");
   m.view.triangles = m.triangles.data();
   m.view.n_triangles = mesh.polygons.size();
   return m;
@@ -396,10 +423,16 @@ public:
     for (std::size_t i = 0; i < n; ++i)
       std::memcpy(normals_pc2.data.data() + 32 * i, normals.data() + 3 * i, 12);
 
-    pcl::PolygonMesh output = mesh;
+    // the output mesh: the input's header and polygons (one deep copy of the polygon list: the interface returns meshes
+    // by value) and the concatenated cloud.  Moved, not copied, into the result (`return { output }` would copy the
+    // 10^7 polygon vectors a second time).
+    std::vector<pcl::PolygonMesh> result(1);
+    pcl::PolygonMesh& output = result.front();
+    output.header = mesh.header;
+    output.polygons = mesh.polygons;
     if (!pcl::concatenateFields(mesh.cloud, normals_pc2, output.cloud))
       throw std::runtime_error("Failed to concatenate normals into mesh vertex cloud");  // :42-43
-    return { output };
+    return result;
   }
 };
 
