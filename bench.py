@@ -144,9 +144,9 @@ def cpu_reference_sample(xyz, nrm, tri, spacing, n_planes: int):
 def ncu_traffic(workload: str, stage: str):
     """DRAM bytes per launch of the stage's kernel from the committed `ncu --set full` capture of this workload
     (profiles/ncu_traffic_<workload>.json, written by tools/ncu_summary.py), or None."""
-    kernel = {"ingest+moments": "k_ingest_moments", "extents": "k_extents", "classify": "k_classify", "count": "k_count_hits",
-              "scan": "k_scan_planes", "emit": "k_emit_hits", "link": "k_link_planes", "waypoints": "k_waypoints",
-              "frame": "k_frame_pca", "lattice": "k_frame_lattice"}.get(stage)
+    kernel = {"ingest+moments": "k_ingest_moments", "extents": "k_extents", "extents+lattice": "k_extents",
+              "classify": "k_classify", "count": "k_count_hits", "count+scan": "k_count_hits", "emit": "k_emit_hits",
+              "link": "k_link_planes", "waypoints": "k_waypoints", "lattice": "k_frame_lattice"}.get(stage)
     path = os.path.join(ROOT, "profiles", f"ncu_traffic_{workload}.json")
     if kernel is None or not os.path.exists(path):
         return None
@@ -161,12 +161,13 @@ def algorithmic_bytes(stage: str, V: int, F: int, H: int, W: int, S: int, P: int
         "ingest+moments": 12 * V + 16 * V,       # xyz in, float4 position out (normals are gathered in place later)
         "validate": 12 * F,
         "extents": 12 * V,
+        "extents+lattice": 12 * V,
         "classify": 12 * V + 4 * V,
         "count": 12 * F + 4 * V,
+        "count+scan": 12 * F + 4 * V + 8 * P,
         "emit": 12 * F + 4 * V + 32 * H,          # triangles, vertex classes, two 16-byte endpoint records per hit
         "link": 32 * H + 8 * W + 4 * S,            # endpoint records in, one {rank, plane} word pair per waypoint out
         "waypoints": 8 * W + 12 * W + 24 * W + 24 * W,  # tags, first-inserter triangles, cut-edge vertex data, waypoints out
-        "scan": 8 * P,
     }
     return table.get(stage)
 

@@ -264,14 +264,16 @@ const char* kNoNormalsMessage =
     "The input mesh does not have vertex normals, which are required for the plane slice raster tool path planner. Use a "
     "MeshModifier to generate vertex normals for the mesh, or provide a different mesh with vertex normals.";
 
-/** k_extents once per resident mesh (the eigen axes were finalised on the device right after the ingest pass) */
-void ensureExtents(nb2_context* c)
+/** k_extents once per resident mesh (the eigen axes were finalised on the device by the ingest pass); true when the
+ *  kernel ran.  With `lattice_prm` its last block also runs the lattice step of the plan. */
+bool ensureExtents(nb2_context* c, const FrameParams* lattice_prm = nullptr)
 {
   if (c->extents_done || c->V < 3)
-    return;
-  launchExtents(c);
-  c->timer.mark("extents", c->stream);
+    return false;
+  launchExtents(c, lattice_prm);
+  c->timer.mark(lattice_prm ? "extents+lattice" : "extents", c->stream);
   c->extents_done = true;
+  return true;
 }
 
 /** Checks that were postponed because the mesh was adopted from device memory without a synchronisation */
@@ -342,13 +344,12 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   requireMesh(c);
   if (!c->has_normals)
     fail(NB2_ERR_NO_NORMALS, kNoNormalsMessage);
-  if (fp)
-    ensureExtents(c);
 
   FrameDev* hf = nullptr;
   unsigned* h = nullptr;
   // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
   //           [12] largest out-of-range vertex index, [13] capacity overflow bits
+  // (start-of-plan state: written by the lattice step on the device, resetPlanCounters)
   auto resetCounters = [&](int first) {
     unsigned init[16] = { 0 };
     init[11] = 0xffffffffu;
@@ -363,7 +364,23 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   hf = c->hostSmall.as<FrameDev>();
   h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
   bool meta_fetched = false;
+  // After a complete stage two the sizes need no copy at all: the last CTA of k_link_planes has written them (frame,
+  // counters, leading per-plane counts) into this pinned staging area, stamped with the plan's serial number.
+  LinkReport report;
+  report.frame = reinterpret_cast<unsigned*>(hf);
+  report.sizes = h;
+  report.meta = h + 16;
+  report.planes = static_cast<unsigned>(meta_hint);
   auto readSizes = [&](bool with_meta = false) {
+    if (with_meta)
+    {
+      NB2_CUDA(cudaStreamSynchronize(c->stream));
+      if (h[15] == report.stamp)
+      {
+        meta_fetched = meta_hint > 0;
+        return;
+      }
+    }
     NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     meta_fetched = with_meta && meta_hint > 0;
@@ -387,7 +404,9 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     c->outSegLen.ensure(sizeof(unsigned) * cap);
     launchEmitHits(c, cap);
     c->timer.mark("emit", c->stream);
-    launchLinkPlanes(c, cap, c->scratch_hits);
+    report.stamp = ++c->plan_serial ? c->plan_serial : ++c->plan_serial;  // never 0
+    h[15] = 0;
+    launchLinkPlanes(c, cap, c->scratch_hits, report);
     c->timer.mark("link", c->stream);
     launchWaypoints(c, w_cap, emit_edges ? 1 : 0);
     c->timer.mark("waypoints", c->stream);
@@ -396,22 +415,26 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   bool sizes_known = false;
   for (int attempt = 0;; ++attempt)
   {
-    resetCounters(4);
     if (fp)
     {
       FrameParams p = *fp;
       p.plane_cap = c->plane_cap;
-      launchFrameLattice(c, p);
+      // first plan on this mesh: the lattice step rides on the extents reduction
+      if (!ensureExtents(c, &p))
+      {
+        launchFrameLattice(c, p);
+        c->timer.mark("lattice", c->stream);
+      }
     }
     else
+    {
       launchFrameSet(c, *explicit_lat, plane_begin, plane_end, c->plane_cap);
-    c->timer.mark("lattice", c->stream);
+      c->timer.mark("lattice", c->stream);
+    }
     launchClassify(c);
     c->timer.mark("classify", c->stream);
     launchCountHits(c);
-    c->timer.mark("count", c->stream);
-    launchScanPlanes(c);
-    c->timer.mark("scan", c->stream);
+    c->timer.mark("count+scan", c->stream);
 
     sizes_known = false;
     if (c->hit_cap == 0)
@@ -810,16 +833,13 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
   // Triangles copied from the host are range-checked now (noise next to the PCIe copy).  Triangles adopted in place
   // from device memory are checked by the first kernel that streams them anyway (k_count_hits / the normals pass).
   c->tri_checked = false;
-  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, sizeof(unsigned), c->stream));
   if (!tri_adopted)
   {
+    NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, sizeof(unsigned), c->stream));
     launchValidateTriangles(c);
     c->timer_upload.mark("validate", c->stream);
   }
-
-  // mean, covariance and eigen axes are finalised on the device, straight from the reduction's total
-  launchFramePca(c, reinterpret_cast<const float*>(c->blob.as<uint8_t>() + m->offset_xyz));
-  c->timer_upload.mark("frame", c->stream);
+  // (mean, covariance and eigen axes were finalised on the device by the last block of the ingest pass)
   c->extents_done = false;
   c->pca_valid = false;
   std::memset(&c->pca, 0, sizeof(c->pca));

@@ -10,6 +10,7 @@
 //   S1      k_classify       : per vertex, the last lattice plane the vertex is "inside" of (scalar >= 0); replaces
 //                              the per-plane vtkPlane::EvaluateFunction sweep over all vertices (:600-608)
 #include "device_math.cuh"
+#include "frame_dev.cuh"
 #include "nb2_internal.h"
 
 #include <cfloat>
@@ -89,12 +90,13 @@ __device__ void blockReducePartial(MomentPartial& p, MomentPartial* smem /*[warp
 /**
  * One pass over the interleaved cloud.  Thread i handles vertices i, i + stride, ... (fixed grid => fixed summation
  * order => bit-reproducible moments).  Moments are taken about the first vertex (pivot) to avoid cancellation for
- * meshes far from the origin.  The last block to finish folds the block partials in index order.
+ * meshes far from the origin.  The last block to finish folds the block partials in index order and finalises the
+ * PCA frame (framePcaStep).
  */
 __global__ void __launch_bounds__(kMomentThreads)
     k_ingest_moments(const uint8_t* __restrict__ blob, unsigned long long V, unsigned point_step, unsigned off_xyz,
                      float4* __restrict__ pos, MomentPartial* partials,
-                     unsigned* done_counter)
+                     unsigned* done_counter, FrameDev* __restrict__ frame)
 {
   __shared__ MomentPartial s_part[kMomentThreads / 32];
   __shared__ bool s_last;
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(kMomentThreads)
   {
     partials[gridDim.x] = t;  // slot after the block partials holds the total
     *done_counter = 0;
+    // mean, covariance and eigen axes straight from the total: no kernel of its own for one thread of arithmetic
+    framedev::framePcaStep(t, piv, V, frame);
   }
 }
 
@@ -218,11 +222,14 @@ __device__ __forceinline__ unsigned orderedBits(float f)
 }
 
 /** Float extents in the PCA frame: proj_c = e_c . (x - mean) with Eigen's 3-term order a0 + (a1 + a2); min/max are
- *  order independent so any reduction tree reproduces pcl::getMinMax3D exactly. */
+ *  order independent so any reduction tree reproduces pcl::getMinMax3D exactly.  With `with_lattice` the last block
+ *  goes on to the lattice step of the plan (frame_dev.cuh). */
 __global__ void __launch_bounds__(256)
-    k_extents(const float4* __restrict__ pos, unsigned long long V, FrameDev* __restrict__ frame)
+    k_extents(const float4* __restrict__ pos, unsigned long long V, FrameDev* __restrict__ frame,
+              unsigned* __restrict__ counters, FrameParams prm, int with_lattice)
 {
   __shared__ float s_mn[3][8], s_mx[3][8];
+  __shared__ bool s_last;
   // mean and axes as k_frame_pca left them (E column-major: axis c = (E[3c], E[3c+1], E[3c+2]))
   const float mx_ = frame->pca.mean[0], my_ = frame->pca.mean[1], mz_ = frame->pca.mean[2];
   const float e00 = frame->pca.evecs[0], e01 = frame->pca.evecs[1], e02 = frame->pca.evecs[2];
@@ -283,6 +290,23 @@ __global__ void __launch_bounds__(256)
     else
       atomicMin(out6 + threadIdx.x, orderedBits(a));
   }
+  if (!with_lattice)
+    return;
+  // the plan's lattice follows from the extents: the last block to finish builds it (and puts the slicing counters
+  // into their start-of-plan state) instead of a single-thread kernel of its own
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    s_last = atomicAdd(counters + 1, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x != 0)
+    return;
+  __threadfence();
+  counters[1] = 0;
+  framedev::resetPlanCounters(counters);
+  framedev::frameLatticeStep(frame, prm);
 }
 
 /**
@@ -358,20 +382,23 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
 {
   const int grid = gridFor(c->V, kMomentThreads, kMomentBlocks);
   c->partials.ensure(sizeof(MomentPartial) * (kMomentBlocks + 1));
+  c->frame.ensure(sizeof(FrameDev));
   // normals stay where they are: the slicer gathers the few it needs straight from the cloud (off_nrm is recorded by
   // the caller in nrm_base / nrm_stride)
   (void)off_nrm;
   k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
                                                            c->pos.as<float4>(),
-                                                           c->partials.as<MomentPartial>(), c->counters.as<unsigned>());
+                                                           c->partials.as<MomentPartial>(), c->counters.as<unsigned>(),
+                                                           c->frame.as<FrameDev>());
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
 
-void launchExtents(nb2_context* c)
+void launchExtents(nb2_context* c, const FrameParams* lattice_prm)
 {
   const int grid = gridFor(c->V, 256, c->sm_count * 8);
-  k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, c->frame.as<FrameDev>());
+  k_extents<<<grid, 256, 0, c->stream>>>(c->pos.as<float4>(), c->V, c->frame.as<FrameDev>(), c->counters.as<unsigned>(),
+                                         lattice_prm ? *lattice_prm : FrameParams{}, lattice_prm ? 1 : 0);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -5,7 +5,7 @@
 //
 //   S2  k_count_hits   : each triangle projects onto the plane lattice through the per-vertex indices K_v
 //                        (k_classify) and bumps a per-plane hit counter; vertex indices are range-checked on the way
-//   S3  k_scan_planes  : exclusive scan of the per-plane counters -> bucket offsets (+ total hits, largest plane)
+//   S3  (last block of S2) : exclusive scan of the per-plane counters -> bucket offsets (+ total hits, largest plane)
 //   S4  k_emit_hits    : the triangles are streamed a second time; every (triangle, plane) hit is contoured exactly as
 //                        vtkTriangle::Contour does, where the triangle's vertices are hot in cache, and its two cut
 //                        points (float32 position + first-inserter rank) are appended to the plane's bucket
@@ -14,7 +14,7 @@
 //                        the chains (Helman-JaJa list ranking), orient and order them, and write, per output
 //                        waypoint, the rank (triangle, line end) of the cut point that inserted it first — into a
 //                        window of the output that belongs to the plane alone, so no plane waits for another one
-//   S5b k_scan_meta    : exclusive prefix of the per-plane waypoint / segment counts
+//   S5b (last CTA of S5)   : exclusive prefix of the per-plane waypoint / segment counts
 //   S6  k_waypoints    : one thread per output waypoint: re-contour the first inserter, interpolate the vertex normals
 //                        along the cut edge, write packed position / normal / generating mesh edge
 //
@@ -64,16 +64,94 @@ __device__ __forceinline__ void planeSpan(int ka, int kb, int kc, const LatticeD
   k1 = min(static_cast<long long>(hi), L.plane_end - 1);
 }
 
+/** Block-wide exclusive scan of the per-plane counters (any block size that is a multiple of 32; the counters are read
+ *  past L1, they were built with atomics by other blocks).  out[0] = total hits, out[1] = largest plane. */
+__device__ void scanPlanesBlock(const unsigned* cnt, long long nP, unsigned* __restrict__ off,
+                                unsigned* __restrict__ cursor, unsigned* __restrict__ out2)
+{
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_carry;
+  __shared__ unsigned s_max[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_carry = 0;
+  unsigned vmax = 0;
+  __syncthreads();
+  for (long long base = 0; base < nP; base += blockDim.x)
+  {
+    const long long i = base + threadIdx.x;
+    const unsigned v = (i < nP) ? __ldcg(cnt + i) : 0u;
+    vmax = max(vmax, v);
+    unsigned x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned y = __shfl_up_sync(kFull, x, o);
+      if (lane >= o)
+        x += y;
+    }
+    if (lane == 31)
+      s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+      unsigned w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned y = __shfl_up_sync(kFull, w, o);
+        if (lane >= o)
+          w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const unsigned carry = s_carry;
+    const unsigned incl = x + (warp ? s_warp[warp - 1] : 0u) + carry;
+    if (i < nP)
+    {
+      off[i] = incl - v;
+      cursor[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1)
+      s_carry = incl;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    vmax = max(vmax, __shfl_down_sync(kFull, vmax, o));
+  if (lane == 0)
+    s_max[warp] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    unsigned m = 0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w)
+      m = max(m, s_max[w]);
+    off[nP] = s_carry;
+    out2[0] = s_carry;
+    out2[1] = m;
+  }
+}
+
 __global__ void __launch_bounds__(kCountThreads)
     k_count_hits(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
                  const int* __restrict__ vertK, const FrameDev* __restrict__ frame, unsigned* __restrict__ planeCnt,
-                 int aligned, unsigned* __restrict__ maxIndex)
+                 int aligned, unsigned* __restrict__ maxIndex, unsigned* __restrict__ doneTicket,
+                 unsigned* __restrict__ planeOff, unsigned* __restrict__ planeCursor, unsigned* __restrict__ sizes)
 {
   __shared__ unsigned s_bins[kSmemBins];
+  __shared__ bool s_last;
   const LatticeDev L = frame->L;
   const long long nP = L.plane_end - L.plane_begin;
   if (nP <= 0)
+  {
+    // nothing to cut: k_classify zeroed planeCnt[0]; the sizes stay at their start-of-plan zeros
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      planeOff[0] = 0u;
     return;
+  }
   const bool use_smem = nP <= kSmemBins;
   if (use_smem)
   {
@@ -127,78 +205,20 @@ __global__ void __launch_bounds__(kCountThreads)
         atomicAdd(&planeCnt[i], v);
     }
   }
-}
-
-/** Single-block exclusive scan of the per-plane counters.  out[0] = total hits, out[1] = largest plane. */
-__global__ void __launch_bounds__(1024)
-    k_scan_planes(const unsigned* __restrict__ cnt, const FrameDev* __restrict__ frame, unsigned* __restrict__ off,
-                  unsigned* __restrict__ cursor, unsigned* __restrict__ out2)
-{
-  const long long nP = frame->L.plane_end - frame->L.plane_begin;
-  __shared__ unsigned s_warp[32];
-  __shared__ unsigned s_carry;
-  __shared__ unsigned s_max[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0)
-    s_carry = 0;
-  unsigned vmax = 0;
-  __syncthreads();
-  for (long long base = 0; base < nP; base += blockDim.x)
-  {
-    const long long i = base + threadIdx.x;
-    const unsigned v = (i < nP) ? cnt[i] : 0u;
-    vmax = max(vmax, v);
-    unsigned x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const unsigned y = __shfl_up_sync(kFull, x, o);
-      if (lane >= o)
-        x += y;
-    }
-    if (lane == 31)
-      s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0)
-    {
-      unsigned w = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const unsigned y = __shfl_up_sync(kFull, w, o);
-        if (lane >= o)
-          w += y;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    const unsigned carry = s_carry;
-    const unsigned incl = x + (warp ? s_warp[warp - 1] : 0u) + carry;
-    if (i < nP)
-    {
-      off[i] = incl - v;
-      cursor[i] = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1)
-      s_carry = incl;
-    __syncthreads();
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    vmax = max(vmax, __shfl_down_sync(kFull, vmax, o));
-  if (lane == 0)
-    s_max[warp] = vmax;
+  // S3: the last block to finish turns the counters into bucket offsets (+ total hits, largest plane)
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    unsigned m = 0;
-    for (int w = 0; w < (blockDim.x >> 5); ++w)
-      m = max(m, s_max[w]);
-    off[nP] = s_carry;
-    out2[0] = s_carry;
-    out2[1] = m;
+    __threadfence();
+    s_last = atomicAdd(doneTicket, 1u) == gridDim.x - 1;
   }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+  if (threadIdx.x == 0)
+    *doneTicket = 0u;
+  scanPlanesBlock(planeCnt, nP, planeOff, planeCursor, sizes);
 }
 
 /**
@@ -346,7 +366,7 @@ struct LinkParams
   unsigned* planeMeta;  // [2 * nP] waypoints, segments of each plane
   // A plane with n hits yields at most 2 n waypoints and n segments, so plane k writes its waypoint ranks at
   // wpTag[2 * planeOff[k] ...] and its segment lengths at segLen[planeOff[k] ...]: no plane waits for another one.
-  // k_scan_meta + k_waypoints close the gaps.
+  // scanMetaBlock + k_waypoints close the gaps.
   unsigned* wpTag;   // [2 * H] rank (2 * triangle + line end) of the first inserter of each waypoint
   unsigned* segLen;  // [H]
   unsigned* status;  // [0] error bits, [1] first failing plane
@@ -355,6 +375,17 @@ struct LinkParams
   unsigned smemHitCap;   // largest plane (in hits) that fits the shared-memory work area
   unsigned scratchHits;  // largest plane the global work areas were sized for
   unsigned* overflow;    // bit 0: hit buffers too small (k_emit_hits), bit 1: a plane exceeds scratchHits
+  unsigned* done;        // CTAs that ran out of planes (the last one scans the per-plane counts)
+  uint2* planePrefix;    // [nP + 1] {waypoints, segments} before each plane
+  unsigned* totals;      // [2] waypoints, segments of the slab
+  // The plan's report, written straight into pinned host memory by the last CTA (no copy engine between the plan and
+  // the host): the frame state, counters[4..13] and the leading per-plane counts, then the plan's stamp.
+  const unsigned* counters;
+  unsigned* reportFrame;   // [sizeof(FrameDev) / 4]
+  unsigned* reportSizes;   // [16]: counters[4..13], ..., [15] stamp
+  unsigned* reportMeta;    // [2 * reportPlanes]
+  unsigned reportPlanes;
+  unsigned stamp;
 };
 
 constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u;
@@ -1302,6 +1333,65 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   return true;
 }
 
+/** Exclusive prefix of the per-plane waypoint and segment counts (one block; nP is at most a few thousand; the counts
+ *  were written by other blocks and are read past L1).
+ *  prefix[k] = {waypoints, segments} before plane k; prefix[nP] = totals, also written to totals[0..1]. */
+__device__ void scanMetaBlock(const unsigned* planeMeta, long long nP, uint2* __restrict__ prefix,
+                              unsigned* __restrict__ totals)
+{
+  __shared__ uint2 s_warp[32];
+  __shared__ uint2 s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_carry = make_uint2(0u, 0u);
+  __syncthreads();
+  for (long long base = 0; base < nP; base += blockDim.x)
+  {
+    const long long i = base + threadIdx.x;
+    const uint2 v = (i < nP) ? __ldcg(reinterpret_cast<const uint2*>(planeMeta) + i) : make_uint2(0u, 0u);
+    uint2 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const unsigned yx = __shfl_up_sync(kFull, x.x, o), yy = __shfl_up_sync(kFull, x.y, o);
+      if (lane >= o)
+        x.x += yx, x.y += yy;
+    }
+    if (lane == 31)
+      s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0)
+    {
+      uint2 w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned yx = __shfl_up_sync(kFull, w.x, o), yy = __shfl_up_sync(kFull, w.y, o);
+        if (lane >= o)
+          w.x += yx, w.y += yy;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint2 carry = s_carry;
+    const uint2 wprev = warp ? s_warp[warp - 1] : make_uint2(0u, 0u);
+    const uint2 incl = make_uint2(x.x + wprev.x + carry.x, x.y + wprev.y + carry.y);
+    if (i < nP)
+      prefix[i] = make_uint2(incl.x - v.x, incl.y - v.y);
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1)
+      s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+  {
+    prefix[nP] = s_carry;
+    totals[0] = s_carry.x;
+    totals[1] = s_carry.y;
+  }
+}
+
+
 __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
 {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -1385,65 +1475,35 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
       P.planeMeta[2 * kLocal] = P.planeMeta[2 * kLocal + 1] = 0u;
     }
   }
-}
-
-/** Exclusive prefix of the per-plane waypoint and segment counts (one block; nP is at most a few thousand).
- *  prefix[k] = {waypoints, segments} before plane k; prefix[nP] = totals, also written to totals[0..1]. */
-__global__ void __launch_bounds__(1024)
-    k_scan_meta(const unsigned* __restrict__ planeMeta, const FrameDev* __restrict__ frame, uint2* __restrict__ prefix,
-                unsigned* __restrict__ totals)
-{
-  const long long nP = frame->L.plane_end - frame->L.plane_begin;
-  __shared__ uint2 s_warp[32];
-  __shared__ uint2 s_carry;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0)
-    s_carry = make_uint2(0u, 0u);
+  // S5b: the last CTA to run out of planes closes the per-plane counts into prefixes and totals for k_waypoints
   __syncthreads();
-  for (long long base = 0; base < nP; base += blockDim.x)
-  {
-    const long long i = base + threadIdx.x;
-    const uint2 v = (i < nP) ? make_uint2(planeMeta[2 * i], planeMeta[2 * i + 1]) : make_uint2(0u, 0u);
-    uint2 x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-      const unsigned yx = __shfl_up_sync(kFull, x.x, o), yy = __shfl_up_sync(kFull, x.y, o);
-      if (lane >= o)
-        x.x += yx, x.y += yy;
-    }
-    if (lane == 31)
-      s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0)
-    {
-      uint2 w = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-        const unsigned yx = __shfl_up_sync(kFull, w.x, o), yy = __shfl_up_sync(kFull, w.y, o);
-        if (lane >= o)
-          w.x += yx, w.y += yy;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    const uint2 carry = s_carry;
-    const uint2 wprev = warp ? s_warp[warp - 1] : make_uint2(0u, 0u);
-    const uint2 incl = make_uint2(x.x + wprev.x + carry.x, x.y + wprev.y + carry.y);
-    if (i < nP)
-      prefix[i] = make_uint2(incl.x - v.x, incl.y - v.y);
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1)
-      s_carry = incl;
-    __syncthreads();
-  }
   if (threadIdx.x == 0)
   {
-    prefix[nP] = s_carry;
-    totals[0] = s_carry.x;
-    totals[1] = s_carry.y;
+    __threadfence();
+    s_ticket = atomicAdd(P.done, 1u);
   }
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1)
+    return;
+  __threadfence();
+  if (threadIdx.x == 0)
+    *P.done = 0u;
+  scanMetaBlock(P.planeMeta, nP, P.planePrefix, P.totals);
+  if (!P.reportSizes)
+    return;
+  __syncthreads();
+  const unsigned* f = reinterpret_cast<const unsigned*>(P.frame);
+  for (unsigned i = threadIdx.x; i < sizeof(FrameDev) / 4u; i += blockDim.x)
+    P.reportFrame[i] = __ldcg(f + i);
+  if (threadIdx.x < 10)
+    P.reportSizes[threadIdx.x] = __ldcg(P.counters + 4 + threadIdx.x);
+  const long long words = 2 * min(nP, static_cast<long long>(P.reportPlanes));
+  for (long long i = threadIdx.x; i < words; i += blockDim.x)
+    P.reportMeta[i] = __ldcg(P.planeMeta + i);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    P.reportSizes[15] = P.stamp;
 }
 
 // =================================================================================================================
@@ -1555,20 +1615,15 @@ void launchCountHits(nb2_context* c)
 {
   const int grid = gridFor((c->F + 3) / 4, kCountThreads, c->sm_count * 8);
   const int aligned = (reinterpret_cast<uintptr_t>(c->tri.ptr) & 15u) == 0 ? 1 : 0;
-  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
-                                                      c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
-                                                      c->counters.as<unsigned>() + 12);
-  NB2_CUDA(cudaGetLastError());
-  ++c->launches;
-}
-
-void launchScanPlanes(nb2_context* c)
-{
   const size_t n = static_cast<size_t>(c->plane_cap) + 1;
   c->planeOff.ensure(sizeof(unsigned) * n);
   c->planeCursor.ensure(sizeof(unsigned) * n);
-  k_scan_planes<<<1, 1024, 0, c->stream>>>(c->planeCnt.as<unsigned>(), c->frame.as<FrameDev>(), c->planeOff.as<unsigned>(),
-                                           c->planeCursor.as<unsigned>(), c->counters.as<unsigned>() + 4);
+  // counters[2]: blocks done (the last one scans); {H, n_max} land in counters[4..5]
+  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
+                                                      c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
+                                                      c->counters.as<unsigned>() + 12, c->counters.as<unsigned>() + 2,
+                                                      c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
+                                                      c->counters.as<unsigned>() + 4);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
@@ -1605,7 +1660,7 @@ unsigned linkSmemHitCap(const nb2_context* c)
   return lo;
 }
 
-void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits)
+void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, const LinkReport& report)
 {
   const unsigned smem_cap = linkSmemHitCap(c);
   const size_t smem_bytes = smemWorkBytes(smem_cap > 0 ? smem_cap : 1);
@@ -1636,14 +1691,18 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits)
   P.smemHitCap = smem_cap;
   P.scratchHits = scratch_hits > smem_cap ? scratch_hits : 0u;
   P.overflow = c->counters.as<unsigned>() + 13;
+  P.done = c->counters.as<unsigned>() + 3;
+  P.planePrefix = c->planePrefix.as<uint2>();
+  P.totals = c->counters.as<unsigned>() + 6;
+  P.counters = c->counters.as<unsigned>();
+  P.reportFrame = report.frame;
+  P.reportSizes = report.sizes;
+  P.reportMeta = report.meta;
+  P.reportPlanes = report.planes;
+  P.stamp = report.stamp;
 
   NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   k_link_planes<<<grid, kLinkThreads, smem_bytes, c->stream>>>(P);
-  NB2_CUDA(cudaGetLastError());
-  ++c->launches;
-  // totals land in counters[6..7]
-  k_scan_meta<<<1, 1024, 0, c->stream>>>(c->planeMeta.as<unsigned>(), c->frame.as<FrameDev>(), c->planePrefix.as<uint2>(),
-                                         c->counters.as<unsigned>() + 6);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

@@ -163,6 +163,7 @@ struct nb2_context
   // moments / frame
   nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
   nb2::DevBuf counters;  // misc device counters (zeroed per plan)
+  unsigned plan_serial = 0;  // stamp of the report the link kernel writes into pinned host memory
   nb2::DevBuf frame;     // FrameDev
   bool extents_done = false;    // k_extents has run for the resident mesh (OBB extents are in FrameDev::ext)
   bool checks_deferred = false; // mesh adopted from device memory: non-finite / index checks happen at the next sync
@@ -258,17 +259,25 @@ struct nb2_result
 namespace nb2
 {
 void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, int32_t off_nrm);
-void launchFramePca(nb2_context* c, const float* pivot_dev);
 void launchFrameLattice(nb2_context* c, const FrameParams& prm);
 void launchFrameSet(nb2_context* c, const nb2_lattice& lat, uint64_t plane_begin, uint64_t plane_end, unsigned plane_cap);
-void launchExtents(nb2_context* c);
+// with lattice_prm the last block of k_extents also builds the plan's lattice and resets the slicing counters
+void launchExtents(nb2_context* c, const FrameParams* lattice_prm = nullptr);
 // the three kernels before the plan's only mid-way synchronisation read the lattice from device memory (FrameDev::L)
 void launchClassify(nb2_context* c);
-void launchCountHits(nb2_context* c);
-void launchScanPlanes(nb2_context* c);  // writes {H, n_max} to counters[4..5]
+void launchCountHits(nb2_context* c);  // + scan of the per-plane counters: writes {H, n_max} to counters[4..5]
 void launchEmitHits(nb2_context* c, uint64_t hit_cap);
 unsigned linkSmemHitCap(const nb2_context* c);
-void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits);
+/** Where the last CTA of k_link_planes leaves the plan's report (pinned host memory, device-visible addresses) */
+struct LinkReport
+{
+  unsigned* frame = nullptr;  // FrameDev
+  unsigned* sizes = nullptr;  // [16]: counters[4..13]; [15] = stamp once everything above is written
+  unsigned* meta = nullptr;   // [2 * planes] leading entries of planeMeta
+  unsigned planes = 0;
+  unsigned stamp = 0;
+};
+void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, const LinkReport& report);
 void launchWaypoints(nb2_context* c, uint64_t w_cap, int emit_edges);
 void launchSetNormals(nb2_context* c, const float* dev_packed);
 void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);  // normals from nrm_base / nrm_stride
