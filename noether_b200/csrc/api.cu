@@ -992,21 +992,12 @@ int nb2_normals_from_mesh_faces(nb2_context* c, float* normals_out)
   DeviceGuard g(c->device);
   requireMesh(c);
   c->timer.begin(c->stream);
-  if (!c->tri_checked && c->F)
-  {
-    launchValidateTriangles(c);
-    c->hostSmall.ensure(4096);
-    unsigned* h = c->hostSmall.as<unsigned>();
-    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-    NB2_CUDA(cudaStreamSynchronize(c->stream));
-    if (h[0] >= c->V)
-      fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[0]) + " but the cloud has " +
-                                         std::to_string(c->V) + " points");
-    c->tri_checked = true;
-    c->timer.mark("validate", c->stream);
-  }
+  // (vertex indices not checked yet, as for triangles adopted from device memory, are checked by the kernels
+  // themselves: offending faces are skipped and the largest index is read back with the final synchronisation)
   launchVertexNormals(c);
-  c->has_normals = true;
+  c->hostSmall.ensure(4096);
+  unsigned* h_max = c->hostSmall.as<unsigned>();
+  NB2_CUDA(cudaMemcpyAsync(h_max, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   if (normals_out)
   {
     c->outPos.ensure(sizeof(float) * 3 * c->V);
@@ -1016,6 +1007,15 @@ int nb2_normals_from_mesh_faces(nb2_context* c, float* normals_out)
     c->timer.mark("d2h", c->stream);
   }
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->F && h_max[0] >= c->V)
+  {
+    const uint64_t V = c->V;
+    c->V = 0;  // the mesh is unusable
+    fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h_max[0]) + " but the cloud has " +
+                                       std::to_string(V) + " points");
+  }
+  c->tri_checked = true;
+  c->has_normals = true;
   NB2_API_END
 }
 

@@ -7,6 +7,7 @@
 // and summed in ascending face order by the one thread that owns the vertex: no float atomics, order-deterministic.
 //
 //   N1  k_face_normals   : unit face normal per triangle (float, reference operation order) + vertex valence count
+//                          (+ range check of the vertex indices: offending faces are skipped and reported)
 //   N2  k_scan_u32       : single-pass decoupled look-back exclusive scan of the valences -> CSR row offsets
 //   N3  k_csr_fill       : scatter face ids into the rows (integer atomics on the row cursors only)
 //   N4  k_vertex_normals : per vertex: sort its (short) row, sum face normals in that order, normalise
@@ -19,14 +20,21 @@ namespace
 constexpr unsigned kFull = 0xffffffffu;
 
 __global__ void __launch_bounds__(256)
-    k_face_normals(const uint32_t* __restrict__ tri, unsigned long long F, const float4* __restrict__ pos,
-                   float4* __restrict__ faceNrm, unsigned* __restrict__ valence, uint16_t* __restrict__ rank,
-                   unsigned* __restrict__ rankOverflow)
+    k_face_normals(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
+                   const float4* __restrict__ pos, float4* __restrict__ faceNrm, unsigned* __restrict__ valence,
+                   uint16_t* __restrict__ rank, unsigned* __restrict__ rankOverflow, unsigned* __restrict__ maxIndex)
 {
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long f = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; f < F; f += stride)
   {
     const uint32_t a = __ldg(tri + 3 * f), b = __ldg(tri + 3 * f + 1), c = __ldg(tri + 3 * f + 2);
+    // range check of the vertex indices (the reference would read out of bounds; here the call fails instead): the
+    // face is left out of every later pass and the host reports the largest offending index
+    if (max(a, max(b, c)) >= V)
+    {
+      atomicMax(maxIndex, max(a, max(b, c)));
+      continue;
+    }
     const float4 p0 = __ldg(pos + a), p1 = __ldg(pos + b), pn = __ldg(pos + c);
     // edge_01.cross(edge_0n).normalized(), float, no contraction
     const float ux = __fsub_rn(p1.x, p0.x), uy = __fsub_rn(p1.y, p0.y), uz = __fsub_rn(p1.z, p0.z);
@@ -103,28 +111,37 @@ __global__ void __launch_bounds__(kScanThreads)
       warp_excl += t;
     tile_total += t;
   }
-  if (threadIdx.x == 0)
+  if (warp == 0)
   {
+    // look-back by one warp, 32 predecessor tiles per step: lane l reads tile j - l; the nearest tile that already
+    // knows its inclusive prefix ends the walk
+    volatile unsigned long long* st_v = state;
+    if (lane == 0 && tile > 0)
+      st_v[tile] = kScanAggregate | tile_total;
     unsigned long long excl = 0;
-    if (tile > 0)
+    for (long long j = static_cast<long long>(tile) - 1; j >= 0; j -= 32)
     {
-      *reinterpret_cast<volatile unsigned long long*>(state + tile) = kScanAggregate | tile_total;
-      long long j = static_cast<long long>(tile) - 1;
-      while (true)
-      {
-        unsigned long long st;
-        do
+      const long long idx = j - lane;
+      unsigned long long st = kScanPrefix;  // before tile 0: an empty prefix
+      if (idx >= 0)
+        while (((st = st_v[idx]) >> 62) == 0ull)
         {
-          st = *reinterpret_cast<volatile unsigned long long*>(state + j);
-        } while ((st >> 62) == 0ull);
-        excl += st & kScanMask;
-        if ((st >> 62) == 2ull)
-          break;
-        --j;
-      }
+        }
+      const unsigned closed = __ballot_sync(kFull, (st >> 62) == 2ull);
+      const int stop = closed ? __ffs(closed) - 1 : 31;
+      unsigned long long part = lane <= stop ? (st & kScanMask) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        part += __shfl_xor_sync(kFull, part, o);
+      excl += part;
+      if (closed)
+        break;
     }
-    *reinterpret_cast<volatile unsigned long long*>(state + tile) = kScanPrefix | (excl + tile_total);
-    s_prefix = excl;
+    if (lane == 0)
+    {
+      st_v[tile] = kScanPrefix | (excl + tile_total);
+      s_prefix = excl;
+    }
   }
   __syncthreads();
   unsigned run = static_cast<unsigned>(s_prefix) + warp_excl + (x - local);
@@ -138,18 +155,21 @@ __global__ void __launch_bounds__(kScanThreads)
 }
 
 __global__ void __launch_bounds__(256)
-    k_csr_fill(const uint32_t* __restrict__ tri, unsigned long long F, const unsigned* __restrict__ rowOff,
-               unsigned* __restrict__ cursor, const uint16_t* __restrict__ rank, const unsigned* __restrict__ rankOverflow,
-               uint32_t* __restrict__ adj)
+    k_csr_fill(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
+               const unsigned* __restrict__ rowOff, unsigned* __restrict__ cursor, const uint16_t* __restrict__ rank,
+               const unsigned* __restrict__ rankOverflow, uint32_t* __restrict__ adj)
 {
   const bool use_rank = *rankOverflow == 0u;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
   for (unsigned long long f = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; f < F; f += stride)
   {
+    const uint32_t id[3] = { __ldg(tri + 3 * f), __ldg(tri + 3 * f + 1), __ldg(tri + 3 * f + 2) };
+    if (max(id[0], max(id[1], id[2])) >= V)
+      continue;  // k_face_normals reported it
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
-      const uint32_t v = __ldg(tri + 3 * f + k);
+      const uint32_t v = id[k];
       const unsigned slot = __ldg(rowOff + v) + (use_rank ? static_cast<unsigned>(rank[3 * f + k]) : atomicAdd(cursor + v, 1u));
       adj[slot] = static_cast<uint32_t>(f);
     }
@@ -291,14 +311,14 @@ void launchVertexNormals(nb2_context* c)
   NB2_CUDA(cudaMemsetAsync(c->valence.ptr, 0, sizeof(unsigned) * (V + 1), c->stream));
   NB2_CUDA(cudaMemsetAsync(c->csrCursor.ptr, 0, sizeof(unsigned) * (V + 1), c->stream));
   NB2_CUDA(cudaMemsetAsync(c->scanState.ptr, 0, sizeof(unsigned long long) * (tiles + 1), c->stream));
-  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 13, 0, sizeof(unsigned), c->stream));
-  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 15, 0, sizeof(unsigned), c->stream));  // rank overflow flag
+  // counters[12] largest out-of-range vertex index, [13] scan ticket, [15] rank overflow flag
+  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, 4 * sizeof(unsigned), c->stream));
 
   if (F)
   {
-    k_face_normals<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->tri.as<uint32_t>(), F, c->pos.as<float4>(),
-                                                                             c->faceNrm.as<float4>(), c->valence.as<unsigned>(),
-                                                                             c->csrRank.as<uint16_t>(), c->counters.as<unsigned>() + 15);
+    k_face_normals<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        c->tri.as<uint32_t>(), F, V, c->pos.as<float4>(), c->faceNrm.as<float4>(), c->valence.as<unsigned>(),
+        c->csrRank.as<uint16_t>(), c->counters.as<unsigned>() + 15, c->counters.as<unsigned>() + 12);
     NB2_CUDA(cudaGetLastError());
     ++c->launches;
   }
@@ -311,7 +331,7 @@ void launchVertexNormals(nb2_context* c)
   c->timer.mark("scan", c->stream);
   if (F)
   {
-    k_csr_fill<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->tri.as<uint32_t>(), F, c->csrOff.as<unsigned>(),
+    k_csr_fill<<<gridFor(F, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->tri.as<uint32_t>(), F, V, c->csrOff.as<unsigned>(),
                                                                          c->csrCursor.as<unsigned>(), c->csrRank.as<uint16_t>(),
                                                                          c->counters.as<unsigned>() + 15, c->csrAdj.as<uint32_t>());
     NB2_CUDA(cudaGetLastError());

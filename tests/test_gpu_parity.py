@@ -47,6 +47,32 @@ def test_ingest_rejects_bad_input(ctx):
     assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT
 
 
+def test_device_resident_triangles_are_checked_by_the_normals_pass(ctx, orc):
+    """Triangles adopted in place from device memory are not validated at upload; the normals kernels skip the
+    offending faces and the call reports the largest out-of-range index."""
+    import torch
+    from noether_b200 import _capi, meshes
+    xyz, tri = meshes.wavy(40, 30)
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    dev = torch.device("cuda", 0)
+    d_cloud = torch.from_numpy(blob.data).to(dev)
+    bad = tri.copy()
+    bad[17, 1] = xyz.shape[0] + 5
+    bad[400, 0] = xyz.shape[0] + 2
+    d_bad = torch.from_numpy(bad.reshape(-1).view(np.int32)).to(dev)
+    d_ok = torch.from_numpy(tri.reshape(-1).view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    V, F = xyz.shape[0], tri.shape[0]
+    ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_bad.data_ptr(), F)
+    with pytest.raises(_capi.Nb2Error) as e:
+        ctx.normals_from_mesh_faces(V)
+    assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT and str(V + 5) in str(e.value)
+    # the same buffers with valid indices: bit-exact normals
+    ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_ok.data_ptr(), F)
+    nrm = ctx.normals_from_mesh_faces(V)
+    assert np.array_equal(bits(nrm), bits(orc.normals_from_mesh_faces(xyz, tri)))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # K1: PCA frame, generators
 # ---------------------------------------------------------------------------------------------------------------------
