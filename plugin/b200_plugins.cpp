@@ -31,6 +31,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -77,6 +79,19 @@ public:
       throw std::runtime_error(nb2_last_error());
   }
 
+  /** What the context holds, by content.  A noether pipeline hands the same mesh to several components in a row (the
+   *  normals modifier's output to the planner; the planner's mesh to its generators; a cross-hatch planner's mesh to
+   *  two plane slicers): a component whose mesh is already resident skips the upload. */
+  struct Resident
+  {
+    bool valid = false;
+    std::uint64_t n_points = 0, n_triangles = 0;
+    std::uint64_t h_xyz = 0, h_tri = 0, h_normals = 0;
+    bool has_normals = false;
+  };
+  Resident resident;
+  std::vector<std::uint32_t> triangles;  // flattened polygons of the last mesh seen (kept: no page faults next time)
+
 private:
   Device() = default;
   ~Device()
@@ -115,14 +130,120 @@ bool hasNormals(const pcl::PCLPointCloud2& cloud)  // utils.cpp:65-72
   return findField(cloud, "normal_x") && findField(cloud, "normal_y") && findField(cloud, "normal_z");
 }
 
-/** The mesh as the C ABI wants it; owns the flattened triangle list (pcl::Vertices is one heap block per face). */
+/** NOETHER_B200_TRACE=1: wall-clock laps of the host-side steps on stderr */
+class Trace
+{
+public:
+  explicit Trace(const char* what) : what_(what), on_(std::getenv("NOETHER_B200_TRACE") != nullptr), t_(now()) {}
+  void lap(const char* step)
+  {
+    if (!on_)
+      return;
+    const double t = now();
+    std::fprintf(stderr, "[noether_b200] %s: %s %.1f ms\n", what_, step, (t - t_) * 1e3);
+    t_ = t;
+  }
+
+private:
+  static double now()
+  {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  const char* what_;
+  bool on_;
+  double t_;
+};
+
+// 64-bit content hash: fixed-size chunks hashed independently (so the work spreads over the cores whatever their
+// number) and folded in chunk order.  Not cryptographic; it only has to tell apart the meshes of one pipeline run.
+constexpr std::size_t kHashChunk = 65536;
+inline std::uint64_t mix(std::uint64_t h, std::uint64_t w)
+{
+  h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 29);
+}
+inline std::uint64_t fold(const std::vector<std::uint64_t>& chunk_hashes, std::uint64_t seed)
+{
+  std::uint64_t h = seed;
+  for (std::uint64_t c : chunk_hashes)
+    h = mix(h, c);
+  return h;
+}
+
+/** fn(chunk index, begin, end) over [0, n) in chunks of kHashChunk, spread over the hardware threads */
+template <typename Fn>
+void forChunks(std::size_t n, Fn fn)
+{
+  const std::size_t chunks = (n + kHashChunk - 1) / kHashChunk;
+  const std::size_t workers = std::min<std::size_t>(std::max(1u, std::thread::hardware_concurrency()), chunks);
+  std::atomic<std::size_t> next{ 0 };
+  auto run = [&]() {
+    for (std::size_t c = next.fetch_add(1); c < chunks; c = next.fetch_add(1))
+      fn(c, c * kHashChunk, std::min(n, (c + 1) * kHashChunk));
+  };
+  std::vector<std::thread> pool;
+  for (std::size_t w = 1; w < workers; ++w)
+    pool.emplace_back(run);
+  run();
+  for (auto& t : pool)
+    t.join();
+}
+
+/** hash of n records of three 32-bit words found at base + i * stride */
+std::uint64_t hashTriples(const std::uint8_t* base, std::size_t stride, std::size_t n, std::uint64_t seed)
+{
+  std::vector<std::uint64_t> part((n + kHashChunk - 1) / kHashChunk);
+  forChunks(n, [&](std::size_t c, std::size_t b, std::size_t e) {
+    std::uint64_t h = seed + c;
+    for (std::size_t i = b; i < e; ++i)
+    {
+      std::uint32_t w[3];
+      std::memcpy(w, base + i * stride, 12);
+      h = mix(h, (static_cast<std::uint64_t>(w[0]) << 32) | w[1]);
+      h = mix(h, w[2]);
+    }
+    part[c] = h;
+  });
+  return fold(part, seed);
+}
+
+/** hashTriples of the positions and (off_nrm >= 0) of the normals of an interleaved cloud, in one pass over it */
+void hashCloud(const std::uint8_t* data, std::size_t stride, std::size_t n, std::size_t off_xyz, long off_nrm,
+               std::uint64_t& h_xyz, std::uint64_t& h_nrm)
+{
+  constexpr std::uint64_t kSeedXyz = 0x78797a21ull, kSeedNrm = 0x6e726d21ull;
+  std::vector<std::uint64_t> px((n + kHashChunk - 1) / kHashChunk), pn(off_nrm >= 0 ? px.size() : 0);
+  forChunks(n, [&](std::size_t c, std::size_t b, std::size_t e) {
+    std::uint64_t hx = kSeedXyz + c, hn = kSeedNrm + c;
+    for (std::size_t i = b; i < e; ++i)
+    {
+      std::uint32_t w[3];
+      std::memcpy(w, data + i * stride + off_xyz, 12);
+      hx = mix(hx, (static_cast<std::uint64_t>(w[0]) << 32) | w[1]);
+      hx = mix(hx, w[2]);
+      if (off_nrm >= 0)
+      {
+        std::memcpy(w, data + i * stride + off_nrm, 12);
+        hn = mix(hn, (static_cast<std::uint64_t>(w[0]) << 32) | w[1]);
+        hn = mix(hn, w[2]);
+      }
+    }
+    px[c] = hx;
+    if (off_nrm >= 0)
+      pn[c] = hn;
+  });
+  h_xyz = fold(px, kSeedXyz);
+  h_nrm = off_nrm >= 0 ? fold(pn, kSeedNrm) : 0;
+}
+
+/** The mesh as the C ABI wants it (triangles flattened into the device object's scratch) and its content hashes */
 struct MeshView
 {
   nb2_mesh_view view{};
-  std::vector<std::uint32_t> triangles;
+  Device::Resident content;
 };
 
-MeshView makeView(const pcl::PolygonMesh& mesh, bool want_normals)
+MeshView makeView(Device& dev, const pcl::PolygonMesh& mesh)
 {
   MeshView m;
   const pcl::PCLPointCloud2& cloud = mesh.cloud;
@@ -136,7 +257,7 @@ MeshView makeView(const pcl::PolygonMesh& mesh, bool want_normals)
   m.view.point_step = cloud.point_step;
   m.view.offset_xyz = x.offset;
   m.view.offset_normal = -1;
-  if (want_normals && hasNormals(cloud))
+  if (hasNormals(cloud))
   {
     const auto& nx = findFieldOrThrow(cloud, "normal_x");
     const auto& ny = findFieldOrThrow(cloud, "normal_y");
@@ -145,49 +266,67 @@ MeshView makeView(const pcl::PolygonMesh& mesh, bool want_normals)
       throw std::runtime_error("Normal fields are not contiguous floats");  // utils.cpp:104-105
     m.view.offset_normal = static_cast<std::int32_t>(nx.offset);
   }
-  // pcl::Vertices is one heap block per face: flattening 10^7 of them is pointer chasing, so it is spread over the cores
+  if (cloud.data.size() < m.view.n_points * cloud.point_step)
+    throw std::runtime_error("point cloud data is shorter than width * height * point_step");
+  // pcl::Vertices is one heap block per face: flattening 10^7 of them is pointer chasing, so it is spread over the
+  // cores; the same pass hashes the indices
   const std::size_t F = mesh.polygons.size();
-  m.triangles.resize(3 * F);
+  dev.triangles.resize(3 * F);
+  std::uint32_t* tri = dev.triangles.data();
   std::atomic<int> bad{ 0 };  // 1: fewer than 3 vertices, 2: not a triangle
-  {
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const std::size_t chunks = std::min<std::size_t>(hw, (F + 65535) / 65536);
-    std::vector<std::thread> workers;
-    auto work = [&](std::size_t b, std::size_t e) {
-      for (std::size_t f = b; f < e; ++f)
+  std::vector<std::uint64_t> part((F + kHashChunk - 1) / kHashChunk);
+  forChunks(F, [&](std::size_t c, std::size_t b, std::size_t e) {
+    std::uint64_t h = 0x7472697321ull + c;
+    for (std::size_t f = b; f < e; ++f)
+    {
+      const auto& v = mesh.polygons[f].vertices;
+      if (v.size() != 3)
       {
-        const auto& v = mesh.polygons[f].vertices;
-        if (v.size() != 3)
-        {
-          bad.store(v.size() < 3 ? 1 : 2);
-          return;
-        }
-        m.triangles[3 * f] = static_cast<std::uint32_t>(v[0]);
-        m.triangles[3 * f + 1] = static_cast<std::uint32_t>(v[1]);
-        m.triangles[3 * f + 2] = static_cast<std::uint32_t>(v[2]);
+        bad.store(v.size() < 3 ? 1 : 2);
+        return;
       }
-    };
-    const std::size_t per = chunks ? (F + chunks - 1) / chunks : 0;
-    for (std::size_t c = 1; c < chunks; ++c)
-      workers.emplace_back(work, c * per, std::min(F, (c + 1) * per));
-    if (chunks)
-      work(0, std::min(F, per));
-    for (auto& t : workers)
-      t.join();
-  }
+      const std::uint32_t i0 = static_cast<std::uint32_t>(v[0]), i1 = static_cast<std::uint32_t>(v[1]),
+                          i2 = static_cast<std::uint32_t>(v[2]);
+      tri[3 * f] = i0, tri[3 * f + 1] = i1, tri[3 * f + 2] = i2;
+      h = mix(h, (static_cast<std::uint64_t>(i0) << 32) | i1);
+      h = mix(h, i2);
+    }
+    part[c] = h;
+  });
   if (bad.load() == 1)
     throw std::runtime_error("Polygon has fewer than 3 vertices");  // getFaceNormal, utils.cpp:137-142
   if (bad.load() == 2)
     throw std::runtime_error("noether_b200 slices triangle meshes only; triangulate the mesh first");
-  m.view.triangles = m.triangles.data();
-  m.view.n_triangles = mesh.polygons.size();
+  m.view.triangles = tri;
+  m.view.n_triangles = F;
+
+  m.content.valid = true;
+  m.content.n_points = m.view.n_points;
+  m.content.n_triangles = F;
+  m.content.h_tri = fold(part, 0x7472697321ull);
+  m.content.has_normals = m.view.offset_normal >= 0;
+  hashCloud(cloud.data.data(), cloud.point_step, m.view.n_points, x.offset, m.view.offset_normal, m.content.h_xyz,
+            m.content.h_normals);
   return m;
 }
 
-void upload(nb2_context* ctx, const pcl::PolygonMesh& mesh, bool want_normals)
+/** Make `mesh` the context's resident mesh: nothing to do when it already is (same vertices, same triangles and, where
+ *  the caller needs them, the same normals), an upload otherwise.  Call with the device mutex held. */
+void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals)
 {
-  const MeshView m = makeView(mesh, want_normals);
-  Device::check(nb2_mesh_upload(ctx, &m.view));
+  Trace trace("ensureResident");
+  const MeshView m = makeView(dev, mesh);
+  trace.lap("flatten + fingerprint");
+  const Device::Resident& r = dev.resident;
+  const bool same_geometry = r.valid && r.n_points == m.content.n_points && r.n_triangles == m.content.n_triangles &&
+                             r.h_xyz == m.content.h_xyz && r.h_tri == m.content.h_tri;
+  const bool same_normals = r.has_normals == m.content.has_normals && (!r.has_normals || r.h_normals == m.content.h_normals);
+  if (same_geometry && (same_normals || !need_normals))
+    return;
+  dev.resident.valid = false;
+  Device::check(nb2_mesh_upload(dev.ctx(), &m.view));
+  dev.resident = m.content;
+  trace.lap("upload");
 }
 
 /** SoA result -> noether::ToolPaths (core/types.h:31-50): nested vectors of Eigen::Isometry3d */
@@ -231,7 +370,7 @@ public:
   {
     Device& dev = Device::instance();
     std::lock_guard<std::mutex> lock(dev.mutex());
-    upload(dev.ctx(), mesh, false);
+    ensureResident(dev, mesh, false);
     double d[3];
     Device::check(nb2_principal_axis_direction(dev.ctx(), rotation_offset_, d));
     return Eigen::Vector3d(d[0], d[1], d[2]);
@@ -257,7 +396,7 @@ public:
     const double v[3] = { nominal.x(), nominal.y(), nominal.z() };
     Device& dev = Device::instance();
     std::lock_guard<std::mutex> lock(dev.mutex());
-    upload(dev.ctx(), mesh, false);
+    ensureResident(dev, mesh, false);
     double d[3];
     Device::check(nb2_pca_rotated_direction(dev.ctx(), rotation_angle_, v, d));
     return Eigen::Vector3d(d[0], d[1], d[2]);
@@ -276,7 +415,7 @@ public:
   {
     Device& dev = Device::instance();
     std::lock_guard<std::mutex> lock(dev.mutex());
-    upload(dev.ctx(), mesh, false);
+    ensureResident(dev, mesh, false);
     double o[3];
     Device::check(nb2_centroid_origin(dev.ctx(), o));
     return Eigen::Vector3d(o[0], o[1], o[2]);
@@ -344,11 +483,15 @@ protected:
 
     Device& dev = Device::instance();
     std::lock_guard<std::mutex> lock(dev.mutex());
-    const MeshView m = makeView(mesh, true);
+    ensureResident(dev, mesh, true);
+    Trace trace("planImpl");
     nb2_result* r = nullptr;
-    Device::check(nb2_plan_mesh(dev.ctx(), &m.view, &prm, &r));
+    Device::check(nb2_plan(dev.ctx(), &prm, &r));
+    trace.lap("nb2_plan");
     std::unique_ptr<nb2_result, void (*)(nb2_result*)> guard(r, nb2_result_free);
-    return toToolPaths(r);
+    noether::ToolPaths out = toToolPaths(r);
+    trace.lap("ToolPaths");
+    return out;
   }
 
   bool bidirectional_ = true;
@@ -396,8 +539,14 @@ public:
     {
       Device& dev = Device::instance();
       std::lock_guard<std::mutex> lock(dev.mutex());
-      upload(dev.ctx(), mesh, false);
+      ensureResident(dev, mesh, false);
+      dev.resident.valid = false;
       Device::check(nb2_normals_from_mesh_faces(dev.ctx(), normals.data()));
+      // the context now holds this geometry with the computed normals: exactly the mesh returned below, which the
+      // pipeline hands to the planner next
+      dev.resident.has_normals = true;
+      dev.resident.h_normals = hashTriples(reinterpret_cast<const std::uint8_t*>(normals.data()), 12, n, 0x6e726d21ull);
+      dev.resident.valid = true;
     }
     // what pcl::toPCLPointCloud2(pcl::PointCloud<pcl::Normal>) yields: 32-byte points, zero curvature / padding
     pcl::PCLPointCloud2 normals_pc2;

@@ -469,6 +469,102 @@ pcl::PolygonMesh wavyMesh(unsigned nx, unsigned ny)
 
 /** What a noether application sees: NormalsFromMeshFaces, then PlaneSlicer(PrincipalAxis, Centroid), both by alias,
  *  pcl::PolygonMesh in, nested noether::ToolPaths out.  Wall clock, second of two runs. */
+bool samePoses(const noether::ToolPaths& a, const noether::ToolPaths& b)
+{
+  if (a.size() != b.size())
+    return false;
+  for (std::size_t p = 0; p < a.size(); ++p)
+  {
+    if (a[p].size() != b[p].size())
+      return false;
+    for (std::size_t s = 0; s < a[p].size(); ++s)
+    {
+      if (a[p][s].size() != b[p][s].size())
+        return false;
+      for (std::size_t w = 0; w < a[p][s].size(); ++w)
+        if (std::memcmp(a[p][s][w].matrix().data(), b[p][s][w].matrix().data(), 16 * sizeof(double)) != 0)
+          return false;
+    }
+  }
+  return true;
+}
+
+std::size_t fieldOffset(const pcl::PCLPointCloud2& cloud, const char* name)
+{
+  for (const auto& f : cloud.fields)
+    if (f.name == name)
+      return f.offset;
+  return 0;
+}
+
+/** The plugin library keeps the last mesh on the device and recognises it by content: a pipeline's components (and a
+ *  cross-hatch pair of planners) share one upload.  What must never happen is a stale hit. */
+void testResidentMeshReuse(const noether::Factory& factory, const pcl::PolygonMesh& raw)
+{
+  std::printf("[resident mesh reuse]\n");
+  YAML::Node mod;
+  mod["name"] = "NormalsFromMeshFaces";
+  const pcl::PolygonMesh m1 = factory.createMeshModifier(mod)->modify(raw).front();
+  YAML::Node dg, og, pc;
+  dg["name"] = "PrincipalAxis";
+  dg["rotation_offset"] = 0.0;
+  og["name"] = "Centroid";
+  pc["name"] = "PlaneSlicer";
+  pc["line_spacing"] = 0.7;
+  pc["bidirectional"] = true;
+  pc["direction_generator"] = dg;
+  pc["origin_generator"] = og;
+  auto planner = factory.createToolPathPlanner(pc);
+  // cross-hatch partner: the same slicer, its direction turned by 90 degrees about the smallest principal axis
+  YAML::Node rot, pc2;
+  rot["name"] = "PCARotated";
+  rot["rotation_offset"] = M_PI / 2;
+  rot["direction_generator"] = dg;
+  pc2["name"] = "PlaneSlicer";
+  pc2["line_spacing"] = 0.7;
+  pc2["bidirectional"] = true;
+  pc2["direction_generator"] = rot;
+  pc2["origin_generator"] = og;
+  auto crossed = factory.createToolPathPlanner(pc2);
+
+  const noether::ToolPaths a = planner->plan(m1);     // hit: the modifier left exactly this mesh on the device
+  const noether::ToolPaths ax = crossed->plan(m1);    // hit again (generator + planner)
+  CHECK(!a.empty() && !ax.empty() && !samePoses(a, ax));
+
+  // same sizes, one coordinate changed: must be seen as another mesh
+  pcl::PolygonMesh m2 = m1;
+  float z;
+  std::uint8_t* pz = m2.cloud.data.data() + 100 * m2.cloud.point_step + fieldOffset(m2.cloud, "z");
+  std::memcpy(&z, pz, 4);
+  z += 0.25f;
+  std::memcpy(pz, &z, 4);
+  const noether::ToolPaths b = planner->plan(m2);
+  CHECK(!samePoses(a, b));
+  // same geometry, other normals: the planner must not reuse the resident normals
+  pcl::PolygonMesh m3 = m1;
+  const std::size_t on = fieldOffset(m3.cloud, "normal_x");
+  for (std::size_t i = 0; i < static_cast<std::size_t>(m3.cloud.width) * m3.cloud.height; ++i)
+    for (int k = 0; k < 3; ++k)
+    {
+      float v;
+      std::uint8_t* q = m3.cloud.data.data() + i * m3.cloud.point_step + on + 4 * k;
+      std::memcpy(&v, q, 4);
+      v = -v;
+      std::memcpy(q, &v, 4);
+    }
+  const noether::ToolPaths c = planner->plan(m2);  // (hit on m2)
+  CHECK(samePoses(b, c));
+  const noether::ToolPaths d = planner->plan(m3);
+  CHECK(!samePoses(a, d));
+  // one triangle re-indexed
+  pcl::PolygonMesh m4 = m1;
+  std::swap(m4.polygons[7].vertices[0], m4.polygons[7].vertices[1]);
+  (void)planner->plan(m4);
+  // and back to the first mesh after all of that: identical to the first answers
+  CHECK(samePoses(a, planner->plan(m1)));
+  CHECK(samePoses(ax, crossed->plan(m1)));
+}
+
 void timePipeline(const noether::Factory& factory, unsigned nx, unsigned ny, double spacing)
 {
   const pcl::PolygonMesh raw = wavyMesh(nx, ny);
@@ -502,6 +598,26 @@ void timePipeline(const noether::Factory& factory, unsigned nx, unsigned ny, dou
                   raw.polygons.size(), spacing, std::chrono::duration<double, std::milli>(t1 - t0).count(),
                   std::chrono::duration<double, std::milli>(t2 - t1).count(), tp.size(), wp);
     CHECK(tp.size() > 10 && wp > 1000);
+    if (run == 1)
+    {
+      // the cross-hatch partner on the same mesh: direction generator and planner find the mesh resident
+      YAML::Node rot, pc2;
+      rot["name"] = "PCARotated";
+      rot["rotation_offset"] = M_PI / 2;
+      rot["direction_generator"] = dg;
+      pc2["name"] = "PlaneSlicer";
+      pc2["line_spacing"] = spacing;
+      pc2["bidirectional"] = true;
+      pc2["direction_generator"] = rot;
+      pc2["origin_generator"] = og;
+      auto crossed = factory.createToolPathPlanner(pc2);
+      const auto t3 = std::chrono::steady_clock::now();
+      const noether::ToolPaths tx = crossed->plan(meshes.front());
+      const auto t4 = std::chrono::steady_clock::now();
+      std::printf("  cross-hatch partner (PCARotated 90 deg) on the same mesh: plan %.1f ms -> %zu tool paths\n",
+                  std::chrono::duration<double, std::milli>(t4 - t3).count(), tx.size());
+      CHECK(tx.size() > 10);
+    }
   }
 }
 
@@ -532,6 +648,7 @@ int main(int argc, char** argv)
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);
     testNormalsFieldRetention(factory, ply);
     testGeneratorsAndErrors(factory, ply);
+    testResidentMeshReuse(factory, ply);
     if (argc > 3 && std::string(argv[3]) == "--time")
     {
       timePipeline(factory, 800, 625, 0.005);    // cfg2: 1 M triangles
