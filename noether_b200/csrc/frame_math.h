@@ -1,7 +1,7 @@
 // Frame arithmetic: everything between the device moment reduction and the lattice constants the slicing kernels
 // consume.  15 scalars in, a handful out, but every quirk matters for parity.  Written once, compiled for the host
 // (explicit C-ABI entry points such as nb2_make_lattice) and for the device (single-thread kernels that keep the plan
-// free of host round trips, kernels_frame.cu); IEEE arithmetic without contraction on both sides.
+// free of host round trips, frame_dev.cuh); IEEE arithmetic without contraction on both sides.
 //
 //   finalizeMoments         pcl::PCA::initCompute                      (3P; call site plane_slicer_raster_planner.cpp:540-541)
 //   eigenSolver3f           Eigen::SelfAdjointEigenSolver<Matrix3f>    (3P, Eigen 3.4 iterative QL path)

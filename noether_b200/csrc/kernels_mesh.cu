@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256)
 {
   __shared__ float s_mn[3][8], s_mx[3][8];
   __shared__ bool s_last;
-  // mean and axes as k_frame_pca left them (E column-major: axis c = (E[3c], E[3c+1], E[3c+2]))
+  // mean and axes as framePcaStep left them (E column-major: axis c = (E[3c], E[3c+1], E[3c+2]))
   const float mx_ = frame->pca.mean[0], my_ = frame->pca.mean[1], mz_ = frame->pca.mean[2];
   const float e00 = frame->pca.evecs[0], e01 = frame->pca.evecs[1], e02 = frame->pca.evecs[2];
   const float e10 = frame->pca.evecs[3], e11 = frame->pca.evecs[4], e12 = frame->pca.evecs[5];

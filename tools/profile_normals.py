@@ -3,7 +3,7 @@
 face order, device-resident input; prints CUDA-event stage times and the achieved fraction of the HBM roofline
 (B_normals = 12 F + 24 V, B_pca = 12 V).
 
-    python tools/profile_normals.py [cfg4|cfg3|cfg2]
+    python tools/profile_normals.py [cfg4|cfg4-grid-order|cfg3|cfg2]
 """
 import json
 import os
@@ -15,7 +15,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SIZES = {"cfg4": (6250, 4000, True), "cfg3": (2500, 2000, False), "cfg2": (800, 625, False)}
+SIZES = {"cfg4": (6250, 4000, True), "cfg4-grid-order": (6250, 4000, False), "cfg3": (2500, 2000, False),
+         "cfg2": (800, 625, False)}
 
 
 def main():
