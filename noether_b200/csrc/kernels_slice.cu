@@ -986,6 +986,19 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   if (tid < kMiscWords)
     s_misc[tid] = 0;
 
+  // The records of the plane this CTA will most likely take next (tickets advance in step: kLocal + grid size) are
+  // started towards L2 now, a whole plane ahead of their use; a wrong guess only warms L2 for another CTA.
+  {
+    const long long kNext = kLocal + gridDim.x;
+    if (kNext < P.L.plane_end - P.L.plane_begin)
+    {
+      const unsigned o = P.planeOff[kNext], m = P.planeOff[kNext + 1] - o;
+      const char* base = reinterpret_cast<const char*>(P.rec + 2ull * o);
+      for (unsigned b = tid * 128u; b < m * 32u; b += nth * 128u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b));
+    }
+  }
+
   // ---- A: stage the records; empty hash ---------------------------------------------------------------------------------
   for (unsigned j = tid; j < n; j += nth)
   {

@@ -1,0 +1,140 @@
+"""Opt-in randomised parity campaign (GPU against the oracle, bit for bit) beyond the fixed seeds of
+test_gpu_parity.py::test_fuzz_plans_match_oracle:
+
+    NB2_FUZZ=small:1000:600,big:5000:60,topo:0:300 python -m pytest tests/test_fuzz_campaign.py -m gpu -q -s
+
+Each item is kind:first_seed:count; kinds: small / big (the sheet generator of test_gpu_parity.py) and topo (closed tubes
+and tori, unwelded sheets, degenerate / duplicated triangles, fins).  Skipped unless NB2_FUZZ is set (the default suites stay short)."""
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import _fuzz_case
+from util import assert_same_paths, oracle_pca_from_capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _fuzz_case_topology(seed, orc):
+    """Meshes the sheet generator never produces: closed tubes and tori (closed contours), partly unwelded sheets
+    (cut points that merge on coordinates only), degenerate and duplicated triangles, fins (three triangles on an edge)."""
+    from noether_b200 import meshes
+    rng = np.random.default_rng(77000 + seed)
+    kind = int(rng.integers(4))
+    if kind == 0:      # tube: closed around, open at both ends
+        n, m = int(rng.integers(8, 48)), int(rng.integers(6, 60))
+        th = np.linspace(0, 2 * np.pi, n, endpoint=False)
+        zs = np.linspace(0, float(rng.uniform(1, 10)), m)
+        a, b, w = float(rng.uniform(0.3, 1.5)), float(rng.uniform(0.3, 1.5)), float(rng.uniform(0, 0.2))
+        xyz = np.array([[a * np.cos(t) * (1 + w * np.sin(3 * z)), b * np.sin(t), z] for z in zs for t in th], np.float32)
+        tri = np.array([t for j in range(m - 1) for i in range(n)
+                        for t in ([j * n + i, j * n + (i + 1) % n, (j + 1) * n + i],
+                                  [j * n + (i + 1) % n, (j + 1) * n + (i + 1) % n, (j + 1) * n + i])], np.uint32)
+    elif kind == 1:    # torus: closed both ways
+        n, m = int(rng.integers(8, 40)), int(rng.integers(8, 60))
+        R, r = float(rng.uniform(1.0, 3.0)), float(rng.uniform(0.2, 0.8))
+        xyz = np.array([[(R + r * np.cos(t)) * np.cos(p), (R + r * np.cos(t)) * np.sin(p), r * np.sin(t)]
+                        for p in np.linspace(0, 2 * np.pi, m, endpoint=False)
+                        for t in np.linspace(0, 2 * np.pi, n, endpoint=False)], np.float32)
+        tri = np.array([t for j in range(m) for i in range(n)
+                        for t in ([j * n + i, j * n + (i + 1) % n, ((j + 1) % m) * n + i],
+                                  [j * n + (i + 1) % n, ((j + 1) % m) * n + (i + 1) % n, ((j + 1) % m) * n + i])], np.uint32)
+    else:              # sheet, then damaged below
+        nx, ny = int(rng.integers(6, 50)), int(rng.integers(6, 50))
+        xyz, tri = meshes.wavy(nx, ny, lx=float(rng.uniform(0.5, 2.0)), ly=float(rng.uniform(0.3, 1.4)),
+                               amp=float(rng.uniform(0.0, 0.08)), lam=float(rng.uniform(0.2, 1.5)))
+    if kind >= 2 or rng.random() < 0.3:
+        # unweld: a random subset of triangles gets private copies of its vertices
+        sel = np.flatnonzero(rng.random(tri.shape[0]) < rng.uniform(0.05, 0.6))
+        extra = xyz[tri[sel].reshape(-1)]
+        tri = tri.copy()
+        tri[sel] = (xyz.shape[0] + np.arange(3 * sel.size, dtype=np.uint32)).reshape(-1, 3)
+        xyz = np.concatenate([xyz, extra])
+    if kind == 3:
+        t = [tri]
+        k = max(1, tri.shape[0] // 20)
+        pick = tri[rng.integers(0, tri.shape[0], k)]
+        t.append(np.stack([pick[:, 0], pick[:, 0], pick[:, 1]], 1))   # a vertex twice
+        t.append(pick[:, [1, 2, 0]])                                  # the same triangle again, rotated
+        if rng.random() < 0.5:                                        # fins: a third triangle on an existing edge
+            apex = xyz[pick[:, 0]] + np.float32(0.05) * rng.normal(size=(k, 3)).astype(np.float32)
+            fin = np.stack([pick[:, 0], pick[:, 1], xyz.shape[0] + np.arange(k, dtype=np.uint32)], 1)
+            xyz = np.concatenate([xyz, apex.astype(np.float32)])
+            t.append(fin.astype(np.uint32))
+        tri = np.concatenate(t).astype(np.uint32)
+        tri = tri[rng.permutation(tri.shape[0])]
+    if rng.random() < 0.6:
+        T = np.eye(4)
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        T[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        T[:3, 3] = rng.uniform(-3, 3, size=3)
+        xyz = meshes.rigid_transform(xyz, T)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    nrm = orc.normals_from_mesh_faces(xyz, tri)
+    ext = xyz.max(0) - xyz.min(0)
+    kw = dict(bidirectional=bool(rng.random() < 0.8), spacing=float(rng.uniform(0.02, 0.2) * np.linalg.norm(ext)))
+    d = rng.normal(size=3)
+    kw["direction"] = (d / np.linalg.norm(d)).tolist()
+    if rng.random() < 0.5:
+        kw["origin"] = (xyz.mean(0) + rng.uniform(-0.2, 0.2, size=3)).tolist()
+    layout = ["PointNormal", "NormalsFirst", "Packed24"][int(rng.integers(3))]
+    return meshes.pack_blob(xyz, nrm, tri, layout), xyz, nrm, tri, kw
+
+
+def _campaign():
+    spec = os.environ.get("NB2_FUZZ", "")
+    for item in filter(None, spec.split(",")):
+        kind, first, count = item.split(":")
+        yield kind, int(first), int(count)
+
+
+@pytest.mark.skipif(not os.environ.get("NB2_FUZZ"), reason="set NB2_FUZZ=kind:first_seed:count[,...] to run the campaign")
+def test_fuzz_campaign(ctx, orc):
+    import noether_b200 as nb
+    from noether_b200 import _capi
+    ran = refused = 0
+    failures = []
+    errors = {}
+    for kind, first, count in _campaign():
+        big = kind
+        for seed in range(first, first + count):
+            blob, xyz, nrm, tri, kw = (_fuzz_case_topology(seed, orc) if kind == "topo"
+                                       else _fuzz_case(seed, orc, kind == "big"))
+            dg = (nb.FixedDirectionGenerator(kw["direction"]) if "direction" in kw
+                  else nb.PrincipalAxisDirectionGenerator(kw.get("rotation_offset", 0.0), ctx))
+            og = nb.FixedOriginGenerator(kw["origin"]) if "origin" in kw else nb.CentroidOriginGenerator(ctx)
+            planner = nb.PlaneSlicerRasterPlanner(dg, og, ctx)
+            planner.set_line_spacing(kw["spacing"])
+            planner.generate_rasters_bidirectionally(kw["bidirectional"])
+            ran += 1
+            try:
+                gpu = planner.plan(blob)
+            except _capi.Nb2Error as e:
+                allowed = (_capi.NB2_ERR_INVALID_ARGUMENT, _capi.NB2_ERR_NON_MANIFOLD) + (
+                    (_capi.NB2_ERR_CLOSED_LOOP,) if kind == "topo" else ())
+                if e.status not in allowed:
+                    failures.append(f"seed {seed} big={big}: unexpected error {e}")
+                errors[e.status] = errors.get(e.status, 0) + 1
+                refused += 1
+                continue
+            try:
+                paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, kw["spacing"], kw["bidirectional"],
+                                                      direction=kw.get("direction"), origin=kw.get("origin"),
+                                                      rotation_offset=kw.get("rotation_offset", 0.0),
+                                                      slice_mode=orc.SLICE_INTENT, scan_mode=orc.SCAN_BINNED,
+                                                      frame=oracle_pca_from_capi(orc, ctx.pca()))
+                assert bytes(ctx.last_lattice()) == bytes(lat), "lattice"
+                assert_same_paths(gpu, paths.flat(), f"seed {seed} {kw}")
+            except AssertionError as e:
+                failures.append(f"seed {seed} big={big}: {str(e)[:300]}")
+            finally:
+                gpu.free()
+    print(f"fuzz campaign: {ran} cases, {refused} refused {errors}, {len(failures)} failures")
+    assert not failures, "\n".join(failures[:20])
+    if not any(kind == "topo" for kind, _, _ in _campaign()):
+        assert refused <= max(3, ran // 20)
