@@ -3,8 +3,10 @@ test_gpu_parity.py::test_fuzz_plans_match_oracle:
 
     NB2_FUZZ=small:1000:600,big:5000:60,topo:0:300 python -m pytest tests/test_fuzz_campaign.py -m gpu -q -s
 
-Each item is kind:first_seed:count; kinds: small / big (the sheet generator of test_gpu_parity.py) and topo (closed tubes
-and tori, unwelded sheets, degenerate / duplicated triangles, fins).  Skipped unless NB2_FUZZ is set (the default suites stay short)."""
+Each item is kind:first_seed:count; kinds: small / big (the sheet generator of test_gpu_parity.py) topo (closed tubes and
+tori, unwelded sheets, degenerate / duplicated triangles, fins) and legacy (PlaneSlicerLegacy with random point spacing,
+minimum segment size and hole size on the sheet generator's meshes; poses bit for bit) and normals (NormalsFromMeshFaces on
+the topology generator's meshes).  Skipped unless NB2_FUZZ is set (the default suites stay short)."""
 import os
 
 import numpy as np
@@ -103,12 +105,33 @@ def test_fuzz_campaign(ctx, orc):
     for kind, first, count in _campaign():
         big = kind
         for seed in range(first, first + count):
-            blob, xyz, nrm, tri, kw = (_fuzz_case_topology(seed, orc) if kind == "topo"
+            blob, xyz, nrm, tri, kw = (_fuzz_case_topology(seed, orc) if kind in ("topo", "normals")
                                        else _fuzz_case(seed, orc, kind == "big"))
+            if kind == "legacy" and "direction" not in kw and "rotation_offset" in kw:
+                pass  # (PrincipalAxis with a rotation offset is fine for the legacy planner too)
             dg = (nb.FixedDirectionGenerator(kw["direction"]) if "direction" in kw
                   else nb.PrincipalAxisDirectionGenerator(kw.get("rotation_offset", 0.0), ctx))
             og = nb.FixedOriginGenerator(kw["origin"]) if "origin" in kw else nb.CentroidOriginGenerator(ctx)
-            planner = nb.PlaneSlicerRasterPlanner(dg, og, ctx)
+            if kind == "normals":
+                # NormalsFromMeshFaces on the topology generator's meshes (degenerate faces, isolated and duplicated
+                # vertices, high valence at the fins): bit for bit against the face-ordered float sums
+                from noether_b200 import meshes
+                from util import bits
+                ran += 1
+                ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
+                got = ctx.normals_from_mesh_faces(xyz.shape[0])
+                if not np.array_equal(bits(got), bits(nrm)):
+                    failures.append(f"seed {seed} normals: {int((bits(got) != bits(nrm)).any(1).sum())} vertices differ")
+                continue
+            legacy = None
+            if kind == "legacy":
+                # PlaneSlicerLegacy: the three legacy modifiers run on the device on the slicer's result
+                lrng = np.random.default_rng(31000 + seed)
+                step = kw["spacing"] * float(lrng.uniform(0.15, 1.5))
+                legacy = (step, float(lrng.choice([0.0, 1.0, 3.0, 8.0])) * step, float(lrng.choice([0.0, 0.5, 2.0, 6.0])) * step)
+                planner = nb.PlaneSlicerLegacyRasterPlanner(dg, og, legacy[0], legacy[1], legacy[2], ctx)
+            else:
+                planner = nb.PlaneSlicerRasterPlanner(dg, og, ctx)
             planner.set_line_spacing(kw["spacing"])
             planner.generate_rasters_bidirectionally(kw["bidirectional"])
             ran += 1
@@ -117,10 +140,40 @@ def test_fuzz_campaign(ctx, orc):
             except _capi.Nb2Error as e:
                 allowed = (_capi.NB2_ERR_INVALID_ARGUMENT, _capi.NB2_ERR_NON_MANIFOLD) + (
                     (_capi.NB2_ERR_CLOSED_LOOP,) if kind == "topo" else ())
-                if e.status not in allowed:
+                if legacy and e.status == _capi.NB2_ERR_SEGMENT_TOO_SHORT:
+                    # UniformSpacing refuses two-point segments (uniform_spacing_modifier.cpp:20-21): so must the oracle
+                    import oracle
+                    try:
+                        orc.plan_plane_slicer_legacy(xyz, nrm, tri, kw["spacing"], legacy[0], legacy[1], legacy[2],
+                                                     kw["bidirectional"], kw.get("direction"), kw.get("origin"),
+                                                     rotation_offset=kw.get("rotation_offset", 0.0),
+                                                     slice_mode=orc.SLICE_INTENT, frame=oracle_pca_from_capi(orc, ctx.pca()))
+                        failures.append(f"seed {seed} legacy: the GPU refused a segment the oracle resamples")
+                    except oracle.OracleError:
+                        pass
+                elif e.status not in allowed:
                     failures.append(f"seed {seed} big={big}: unexpected error {e}")
                 errors[e.status] = errors.get(e.status, 0) + 1
                 refused += 1
+                continue
+            if legacy:
+                import oracle
+                try:
+                    paths, lat, _ = orc.plan_plane_slicer_legacy(
+                        xyz, nrm, tri, kw["spacing"], legacy[0], legacy[1], legacy[2], kw["bidirectional"],
+                        kw.get("direction"), kw.get("origin"), rotation_offset=kw.get("rotation_offset", 0.0),
+                        slice_mode=orc.SLICE_INTENT, frame=oracle_pca_from_capi(orc, ctx.pca()))
+                    ref = paths.flat()
+                    assert gpu.legacy and gpu.n_paths == ref.num_paths, "paths"
+                    np.testing.assert_array_equal(gpu.path_offsets.astype(np.uint64), ref.path_off)
+                    np.testing.assert_array_equal(gpu.segment_offsets.astype(np.uint64), ref.seg_off)
+                    np.testing.assert_array_equal(gpu.poses(), ref.pose)
+                except oracle.OracleError as e:
+                    failures.append(f"seed {seed} legacy {legacy}: oracle refuses ({e}) what the GPU planned")
+                except AssertionError as e:
+                    failures.append(f"seed {seed} legacy {legacy}: {str(e)[:300]}")
+                finally:
+                    gpu.free()
                 continue
             try:
                 paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, kw["spacing"], kw["bidirectional"],
@@ -136,5 +189,5 @@ def test_fuzz_campaign(ctx, orc):
                 gpu.free()
     print(f"fuzz campaign: {ran} cases, {refused} refused {errors}, {len(failures)} failures")
     assert not failures, "\n".join(failures[:20])
-    if not any(kind == "topo" for kind, _, _ in _campaign()):
-        assert refused <= max(3, ran // 20)
+    if all(kind in ("small", "big") for kind, _, _ in _campaign()):
+        assert refused <= max(3, ran // 20)  # (topo: fins are refused; legacy: two-point segments, as the oracle does)
