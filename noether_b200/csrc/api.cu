@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <memory>
@@ -344,16 +345,20 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   requireMesh(c);
   if (!c->has_normals)
     fail(NB2_ERR_NO_NORMALS, kNoNormalsMessage);
+  // a slab of a sharded plan is cut by a fraction of the triangles: the counting pass lists those for the contouring pass
+  c->list_quads = fp && fp->shard_count > 1;
+  if (const char* e = std::getenv("NB2_LIST_QUADS"))
+    c->list_quads = std::atoi(e) != 0;
 
   FrameDev* hf = nullptr;
   unsigned* h = nullptr;
   // counters: [4] H, [5] n_max, [6] waypoints, [7] segments, [8] link ticket, [10] status, [11] failing plane,
-  //           [12] largest out-of-range vertex index, [13] capacity overflow bits
+  //           [9] quads on the cut-quad list, [12] largest out-of-range vertex index, [13] capacity overflow bits
   // (start-of-plan state: written by the lattice step on the device, resetPlanCounters)
-  auto resetCounters = [&](int first) {
+  auto resetCounters = [&](int first, int last = 16) {
     unsigned init[16] = { 0 };
     init[11] = 0xffffffffu;
-    NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + first, init + first, (16 - first) * sizeof(unsigned),
+    NB2_CUDA(cudaMemcpyAsync(c->counters.as<unsigned>() + first, init + first, (last - first) * sizeof(unsigned),
                              cudaMemcpyHostToDevice, c->stream));
   };
   // The per-plane {waypoints, segments} counts ride along with the sizes when the plane count of the previous plan is
@@ -506,7 +511,8 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   {
     setCapacities(H, n_max);
     NB2_CUDA(cudaMemsetAsync(c->planeCursor.ptr, 0, sizeof(unsigned) * (static_cast<size_t>(c->plane_cap) + 1), c->stream));
-    resetCounters(6);
+    resetCounters(6, 9);  // (not [9]: the list of cut quads k_count_hits left stays valid)
+    resetCounters(10);
     stageTwo();
     readSizes(true);
     if (h[9])
@@ -730,7 +736,7 @@ void nb2_context_destroy(nb2_context* c)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
   for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
-                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
+                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->csrRank, &c->scanState })

@@ -135,11 +135,13 @@ __device__ void scanPlanesBlock(const unsigned* cnt, long long nP, unsigned* __r
   }
 }
 
+template <bool kListQuads>
 __global__ void __launch_bounds__(kCountThreads)
     k_count_hits(const uint32_t* __restrict__ tri, unsigned long long F, unsigned long long V,
                  const int* __restrict__ vertK, const FrameDev* __restrict__ frame, unsigned* __restrict__ planeCnt,
                  int aligned, unsigned* __restrict__ maxIndex, unsigned* __restrict__ doneTicket,
-                 unsigned* __restrict__ planeOff, unsigned* __restrict__ planeCursor, unsigned* __restrict__ sizes)
+                 unsigned* __restrict__ planeOff, unsigned* __restrict__ planeCursor, unsigned* __restrict__ sizes,
+                 unsigned* __restrict__ quadList, unsigned* __restrict__ quadCount)
 {
   __shared__ unsigned s_bins[kSmemBins];
   __shared__ bool s_last;
@@ -161,39 +163,101 @@ __global__ void __launch_bounds__(kCountThreads)
   }
   const unsigned long long Q = (F + 3) / 4;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  for (unsigned long long q = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < Q; q += stride)
+  if constexpr (!kListQuads)
   {
-    uint32_t id[12];
-    const int n = loadQuad(tri, F, q, aligned != 0, id);
-    // range check of the vertex indices (the reference would read out of bounds; here the plan fails instead)
-    uint32_t m = id[0];
-#pragma unroll
-    for (int i = 1; i < 12; ++i)
-      m = max(m, id[i]);
-    if (m >= V)
+    for (unsigned long long q = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < Q; q += stride)
     {
-      atomicMax(maxIndex, m);
-      continue;
-    }
-    int K[12];
+      uint32_t id[12];
+      const int n = loadQuad(tri, F, q, aligned != 0, id);
+      // range check of the vertex indices (the reference would read out of bounds; here the plan fails instead)
+      uint32_t m = id[0];
 #pragma unroll
-    for (int i = 0; i < 12; ++i)
-      K[i] = __ldg(vertK + id[i]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-    {
-      if (i >= n)
-        break;
-      long long k0, k1;
-      planeSpan(K[3 * i], K[3 * i + 1], K[3 * i + 2], L, k0, k1);
-      for (long long k = k0; k <= k1; ++k)
+      for (int i = 1; i < 12; ++i)
+        m = max(m, id[i]);
+      if (m >= V)
       {
-        if (use_smem)
-          atomicAdd(&s_bins[k - L.plane_begin], 1u);
-        else
-          atomicAdd(&planeCnt[k - L.plane_begin], 1u);
+        atomicMax(maxIndex, m);
+        continue;
+      }
+      int K[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        K[i] = __ldg(vertK + id[i]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        if (i >= n)
+          break;
+        long long k0, k1;
+        planeSpan(K[3 * i], K[3 * i + 1], K[3 * i + 2], L, k0, k1);
+        for (long long k = k0; k <= k1; ++k)
+        {
+          if (use_smem)
+            atomicAdd(&s_bins[k - L.plane_begin], 1u);
+          else
+            atomicAdd(&planeCnt[k - L.plane_begin], 1u);
+        }
       }
     }
+  }
+  else
+  {
+  // (the loop is uniform per block when the quads with hits are listed: the warps vote below)
+  for (unsigned long long q0 = static_cast<unsigned long long>(blockIdx.x) * blockDim.x; q0 < Q; q0 += stride)
+  {
+    const unsigned long long q = q0 + threadIdx.x;
+    bool any_hit = false;
+    if (q < Q)
+    {
+      uint32_t id[12];
+      const int n = loadQuad(tri, F, q, aligned != 0, id);
+      // range check of the vertex indices (the reference would read out of bounds; here the plan fails instead)
+      uint32_t m = id[0];
+#pragma unroll
+      for (int i = 1; i < 12; ++i)
+        m = max(m, id[i]);
+      if (m >= V)
+        atomicMax(maxIndex, m);
+      else
+      {
+        int K[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+          K[i] = __ldg(vertK + id[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+          if (i >= n)
+            break;
+          long long k0, k1;
+          planeSpan(K[3 * i], K[3 * i + 1], K[3 * i + 2], L, k0, k1);
+          any_hit |= k1 >= k0;
+          for (long long k = k0; k <= k1; ++k)
+          {
+            if (use_smem)
+              atomicAdd(&s_bins[k - L.plane_begin], 1u);
+            else
+              atomicAdd(&planeCnt[k - L.plane_begin], 1u);
+          }
+        }
+      }
+    }
+    {
+      // A slab of a sharded plan is cut by a fraction of the triangles only: the quads that are go on a list, so that
+      // k_emit_hits does not stream the whole triangle array again (one atomic per warp; the order is arbitrary)
+      const unsigned vote = __ballot_sync(kFull, any_hit);
+      if (vote)
+      {
+        const unsigned lane = threadIdx.x & 31u;
+        unsigned base = 0;
+        if (lane == 0)
+          base = atomicAdd(quadCount, __popc(vote));
+        base = __shfl_sync(kFull, base, 0);
+        if (any_hit)
+          quadList[base + __popc(vote & ((1u << lane) - 1u))] = static_cast<unsigned>(q);
+      }
+    }
+  }
   }
   if (use_smem)
   {
@@ -240,7 +304,8 @@ __global__ void __launch_bounds__(kEmitThreads, 4)
     k_emit_hits(const uint32_t* __restrict__ tri, unsigned long long F, const int* __restrict__ vertK,
                 const float4* __restrict__ pos, const FrameDev* __restrict__ frame, const unsigned* __restrict__ planeOff,
                 unsigned* __restrict__ cursor, float4* __restrict__ rec, int aligned, const unsigned* __restrict__ hits,
-                unsigned long long hitCap, unsigned* __restrict__ overflow)
+                unsigned long long hitCap, unsigned* __restrict__ overflow, const unsigned* __restrict__ quadList,
+                const unsigned* __restrict__ quadCount)
 {
   __shared__ uint2 s_list[kEmitList];  // {triangle, slab-local plane}
   // The buffers were sized before the hit count was known (from the previous plan on this context): when this plan
@@ -254,14 +319,16 @@ __global__ void __launch_bounds__(kEmitThreads, 4)
   const LatticeDev L = frame->L;
   __shared__ unsigned s_warp[kEmitThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned long long Q = (F + 3) / 4;
+  // all quads of the triangle stream, or (sharded plans) the quads k_count_hits listed as cut by this slab
+  const unsigned long long Q = quadList ? *quadCount : (F + 3) / 4;
   const unsigned long long tiles = (Q + kEmitThreads - 1) / kEmitThreads;
   for (unsigned long long tile = blockIdx.x; tile < tiles; tile += gridDim.x)
   {
-    const unsigned long long q = tile * kEmitThreads + threadIdx.x;
+    const unsigned long long slot = tile * kEmitThreads + threadIdx.x;
+    const unsigned long long q = (quadList && slot < Q) ? __ldg(quadList + slot) : slot;
     int k0[4];
     unsigned cnt[4] = { 0u, 0u, 0u, 0u };
-    if (q < Q)
+    if (slot < Q)
     {
       uint32_t id[12];
       const int n = loadQuad(tri, F, q, aligned != 0, id);
@@ -1631,12 +1698,25 @@ void launchCountHits(nb2_context* c)
   const size_t n = static_cast<size_t>(c->plane_cap) + 1;
   c->planeOff.ensure(sizeof(unsigned) * n);
   c->planeCursor.ensure(sizeof(unsigned) * n);
+  if (c->list_quads)
+    c->quadList.ensure(sizeof(unsigned) * ((c->F + 3) / 4 + 1));
   // counters[2]: blocks done (the last one scans); {H, n_max} land in counters[4..5]
-  k_count_hits<<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
-                                                      c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
-                                                      c->counters.as<unsigned>() + 12, c->counters.as<unsigned>() + 2,
-                                                      c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
-                                                      c->counters.as<unsigned>() + 4);
+  if (c->list_quads)
+    k_count_hits<true><<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
+                                                        c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
+                                                        c->counters.as<unsigned>() + 12, c->counters.as<unsigned>() + 2,
+                                                        c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
+                                                        c->counters.as<unsigned>() + 4,
+                                                        c->list_quads ? c->quadList.as<unsigned>() : nullptr,
+                                                        c->counters.as<unsigned>() + 9);
+  else
+    k_count_hits<false><<<grid, kCountThreads, 0, c->stream>>>(c->tri.as<uint32_t>(), c->F, c->V, c->vertK.as<int>(),
+                                                        c->frame.as<FrameDev>(), c->planeCnt.as<unsigned>(), aligned,
+                                                        c->counters.as<unsigned>() + 12, c->counters.as<unsigned>() + 2,
+                                                        c->planeOff.as<unsigned>(), c->planeCursor.as<unsigned>(),
+                                                        c->counters.as<unsigned>() + 4,
+                                                        c->list_quads ? c->quadList.as<unsigned>() : nullptr,
+                                                        c->counters.as<unsigned>() + 9);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
@@ -1652,7 +1732,9 @@ void launchEmitHits(nb2_context* c, uint64_t hit_cap)
                                                      c->frame.as<FrameDev>(), c->planeOff.as<unsigned>(),
                                                      c->planeCursor.as<unsigned>(), c->hitRec.as<float4>(), aligned,
                                                      c->counters.as<unsigned>() + 4, hit_cap,
-                                                     c->counters.as<unsigned>() + 13);
+                                                     c->counters.as<unsigned>() + 13,
+                                                     c->list_quads ? c->quadList.as<unsigned>() : nullptr,
+                                                     c->counters.as<unsigned>() + 9);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

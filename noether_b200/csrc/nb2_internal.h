@@ -183,6 +183,8 @@ struct nb2_context
   nb2::DevBuf wpTag;       // uint32[2 H] first-inserter rank of every waypoint, in per-plane windows
   nb2::DevBuf segLen;      // uint32[H] segment lengths, in per-plane windows
   nb2::DevBuf planePrefix; // uint2[P + 1] waypoints / segments before each plane
+  nb2::DevBuf quadList;    // uint32[F / 4] quads (groups of four triangles) cut by this slab, sharded plans only
+  bool list_quads = false; // k_count_hits lists them, k_emit_hits walks the list (set per plan)
   nb2::DevBuf planeMeta;   // uint32[2 * P]: waypoints, segments of each plane
   nb2::DevBuf outPos;      // float[3 * Wcap]
   nb2::DevBuf outNrm;      // float[3 * Wcap]
