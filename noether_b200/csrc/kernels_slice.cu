@@ -455,7 +455,7 @@ struct LinkParams
   unsigned stamp;
 };
 
-constexpr unsigned kErrNonManifold = 1u, kErrClosedLoop = 2u;
+constexpr unsigned kErrNonManifold = 1u;  // (bit 1, "closed loop", is reserved: closed contours are walked, not refused)
 // pairing cell of a hash slot: [31:20] number of line ends at the point, [19:0] last line end that arrived
 constexpr unsigned kCellShift = 20u, kCellMask = (1u << kCellShift) - 1u;
 constexpr unsigned kMaxCrowded = 16u;      // points with more than two incident lines handled per plane
