@@ -82,6 +82,32 @@ int nb2_mesh_set_normals(nb2_context* ctx, const float* normals);
 int nb2_mesh_download(nb2_context* ctx, float* xyz, float* normals);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Mesh ingest from a file image.  Replaces pcl::io::loadPolygonFile(path, mesh) for binary little-endian PLY files
+ * (noether_gui/src/widgets/tpp_widget.cpp:426; noether_tpp/test/tool_path_planner_utest.cpp:24 — vtkPLYReader ->
+ * pcl::io::vtk2mesh -> PCLPointCloud2 + one std::vector per face on one host core) followed by nb2_mesh_upload: the
+ * header is parsed on the host, the records go to the GPU in one copy and are decoded there (vertex properties x y z
+ * [nx ny nz | normal_x normal_y normal_z] as float32, any other scalar properties skipped; face list
+ * vertex_indices / vertex_index with 1-, 2- or 4-byte counts and indices).  Every face must be a triangle
+ * (NB2_ERR_NOT_TRIANGLES otherwise, like the rest of this path); ASCII and big-endian files are refused with a message.
+ * The mesh is then resident exactly as after nb2_mesh_upload (nb2_plan, nb2_normals_from_mesh_faces, ... follow).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct nb2_mesh_file_info
+{
+  uint64_t n_points;
+  uint64_t n_triangles;
+  int32_t has_normals; /* the file carries vertex normals (pcl::io::vtk2mesh would add normal_x/y/z fields) */
+  int32_t reserved_;
+} nb2_mesh_file_info;
+
+/* Header only, on the host (no device needed): sizes a caller can allocate for, and the refusals above. */
+int nb2_ply_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info);
+int nb2_mesh_upload_ply(nb2_context* ctx, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info /* may be NULL */);
+/* The same from a path: the file is memory-mapped and copied to the GPU straight out of the page cache. */
+int nb2_mesh_upload_ply_file(nb2_context* ctx, const char* path, nb2_mesh_file_info* info /* may be NULL */);
+/* Copy the resident triangle list back (uint32[3 * n_triangles]).  Test / debugging aid. */
+int nb2_mesh_download_triangles(nb2_context* ctx, uint32_t* triangles);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * PCA frame.  Replaces the pcl::PCA block of planImpl (plane_slicer_raster_planner.cpp:534-553), and feeds
  * PrincipalAxisDirectionGenerator::generate (principal_axis_direction_generator.cpp:14-26) and
  * CentroidOriginGenerator::generate (centroid_origin_generator.cpp:8-17).  One fused pass accumulates centroid,

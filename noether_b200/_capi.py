@@ -39,6 +39,7 @@ DECLARED_SYMBOLS = [
     "nb2_plan", "nb2_plan_mesh", "nb2_last_lattice", "nb2_result_get", "nb2_result_poses", "nb2_result_poses_segments", "nb2_result_free", "nb2_last_timings",
     "nb2_kernel_launches", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
     "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",
+    "nb2_ply_inspect", "nb2_mesh_upload_ply", "nb2_mesh_upload_ply_file", "nb2_mesh_download_triangles",
 ]
 
 
@@ -79,6 +80,10 @@ class ResultView(C.Structure):
                 ("raster_post_ops_applied", C.c_int32), ("legacy", C.c_int32)]
 
 
+class MeshFileInfo(C.Structure):
+    _fields_ = [("n_points", C.c_uint64), ("n_triangles", C.c_uint64), ("has_normals", C.c_int32), ("reserved_", C.c_int32)]
+
+
 class Nb2Error(RuntimeError):
     def __init__(self, status: int, msg: str):
         super().__init__(msg)
@@ -108,6 +113,10 @@ def load():
     L.nb2_mesh_upload_sharded.argtypes = [vp, C.POINTER(MeshView)]
     L.nb2_mesh_set_normals.argtypes = [vp, C.c_void_p]
     L.nb2_mesh_download.argtypes = [vp, C.c_void_p, C.c_void_p]
+    L.nb2_ply_inspect.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
+    L.nb2_mesh_upload_ply.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
+    L.nb2_mesh_upload_ply_file.argtypes = [vp, C.c_char_p, C.POINTER(MeshFileInfo)]
+    L.nb2_mesh_download_triangles.argtypes = [vp, C.c_void_p]
     L.nb2_mesh_pca.argtypes = [vp, C.POINTER(Pca)]
     L.nb2_principal_axis_direction.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.nb2_centroid_origin.argtypes = [vp, C.POINTER(C.c_double)]

@@ -9,6 +9,11 @@
 #include <exception>
 #include <memory>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace nb2
 {
 namespace
@@ -735,7 +740,7 @@ void nb2_context_destroy(nb2_context* c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
-  for (DevBuf* b : { &c->blob, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
+  for (DevBuf* b : { &c->blob, &c->fileImg, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
@@ -880,6 +885,146 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
                                        std::to_string(V) + " points");
   }
   c->tri_checked = true;
+}
+
+/** nb2_mesh_upload_ply: header on the host, records on the device (ply.cpp, kernels_ply.cu) */
+static void uploadPlyImpl(nb2_context* c, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  if (!c || !file_image)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or file image is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  const PlyLayout L = parsePlyHeader(static_cast<const uint8_t*>(file_image), n_bytes);
+  if (L.n_points == 0)
+    fail(NB2_ERR_TOO_FEW_POINTS, "mesh has no vertices");
+  c->V = 0;
+  c->pca_valid = false;
+  c->extents_done = false;
+  c->timer_upload.begin(c->stream);
+  // one PCIe copy of the records (the header stays behind; byte offsets keep referring to the file)
+  const uint64_t first = L.vertex_begin & ~uint64_t(255);
+  const uint64_t last = std::max(L.vertex_begin + L.n_points * L.point_step, L.face_begin + L.n_faces * L.face_step);
+  c->fileImg.ensure(((last - first + 15) & ~uint64_t(7)) + 8);
+  NB2_CUDA(cudaMemcpyAsync(c->fileImg.ptr, static_cast<const uint8_t*>(file_image) + first, last - first,
+                           cudaMemcpyHostToDevice, c->stream));
+  c->timer_upload.mark("h2d", c->stream);
+  PlyLayout D = L;
+  D.vertex_begin -= first;
+  D.face_begin -= first;
+  c->pos.ensure(sizeof(float4) * L.n_points);
+  launchPlyDecode(c, D);
+  c->timer_upload.mark("decode", c->stream);
+  const uint32_t step = L.has_normals ? 32u : 16u;
+  c->V = L.n_points;
+  c->F = L.n_faces;
+  c->has_normals = L.has_normals;
+  c->nrm_base = c->has_normals ? c->blob.as<uint8_t>() + 16 : nullptr;
+  c->nrm_stride = step;
+  launchIngestMoments(c, step, 0, c->has_normals ? 16 : -1);
+  c->timer_upload.mark("ingest+moments", c->stream);
+  std::memset(&c->pca, 0, sizeof(c->pca));
+  c->checks_deferred = false;
+  c->tri_checked = false;
+  c->hostSmall.ensure(4096 + sizeof(FrameDev));
+  auto* h = c->hostSmall.as<uint8_t>();
+  const int grid = static_cast<int>(std::min<uint64_t>((c->V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaMemcpyAsync(h + 516, c->counters.as<unsigned>() + 16, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  MomentPartial total;
+  std::memcpy(&total, h, sizeof(total));
+  unsigned max_index, not_triangles;
+  std::memcpy(&max_index, h + 512, 4);
+  std::memcpy(&not_triangles, h + 516, 4);
+  const uint64_t V = c->V;
+  if (not_triangles)
+  {
+    c->V = 0;
+    fail(NB2_ERR_NOT_TRIANGLES, "PLY: the file holds faces that are not triangles (the plane slicer path takes triangle meshes)");
+  }
+  if (total.non_finite)
+  {
+    c->V = 0;
+    fail(NB2_ERR_NON_FINITE, std::to_string(total.non_finite) + " vertices have non-finite coordinates");
+  }
+  if (c->F && max_index >= V)
+  {
+    c->V = 0;
+    fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(max_index) + " but the cloud has " +
+                                       std::to_string(V) + " points");
+  }
+  c->tri_checked = true;
+  if (info)
+  {
+    info->n_points = c->V;
+    info->n_triangles = c->F;
+    info->has_normals = c->has_normals ? 1 : 0;
+    info->reserved_ = 0;
+  }
+}
+
+int nb2_ply_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!file_image || !info)
+    fail(NB2_ERR_INVALID_ARGUMENT, "file image or info is NULL");
+  const PlyLayout L = parsePlyHeader(static_cast<const uint8_t*>(file_image), n_bytes);
+  info->n_points = L.n_points;
+  info->n_triangles = L.n_faces;
+  info->has_normals = L.has_normals ? 1 : 0;
+  info->reserved_ = 0;
+  NB2_API_END
+}
+
+int nb2_mesh_upload_ply(nb2_context* c, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  uploadPlyImpl(c, file_image, n_bytes, info);
+  NB2_API_END
+}
+
+int nb2_mesh_upload_ply_file(nb2_context* c, const char* path, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!path)
+    fail(NB2_ERR_INVALID_ARGUMENT, "path is NULL");
+  // the file is mapped, not read: the PCIe copy pulls the pages straight out of the page cache
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0)
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot open '") + path + "'");
+  struct stat st{};
+  if (::fstat(fd, &st) != 0 || st.st_size <= 0)
+  {
+    ::close(fd);
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot stat '") + path + "' (or the file is empty)");
+  }
+  void* map = ::mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (map == MAP_FAILED)
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot map '") + path + "'");
+  struct Unmap
+  {
+    void* p;
+    size_t n;
+    ~Unmap() { ::munmap(p, n); }
+  } unmap{ map, static_cast<size_t>(st.st_size) };
+  uploadPlyImpl(c, map, static_cast<uint64_t>(st.st_size), info);
+  NB2_API_END
+}
+
+int nb2_mesh_download_triangles(nb2_context* c, uint32_t* triangles)
+{
+  NB2_API_BEGIN
+  if (!c || !triangles)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or triangles is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  if (c->F)
+    NB2_CUDA(cudaMemcpyAsync(triangles, c->tri.ptr, sizeof(uint32_t) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  NB2_API_END
 }
 
 int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)

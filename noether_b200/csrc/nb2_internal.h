@@ -119,6 +119,23 @@ struct FrameDev
   unsigned long long non_finite;
 };
 
+/** Where a binary little-endian PLY file keeps what the slicer needs (ply.cpp parses the header on the host, the
+ *  records are decoded on the device by kernels_ply.cu) */
+struct PlyLayout
+{
+  uint64_t header_bytes;
+  uint64_t n_points, n_faces;
+  uint64_t vertex_begin, face_begin;  // byte offsets into the file image
+  uint32_t point_step;                // bytes per vertex record
+  uint32_t off_field[6];              // of the properties x y z nx ny nz inside a vertex record
+  uint8_t field_f64[6];               // stored as float64 (converted to float as vtkPLYReader does), else float32
+  bool has_normals;                   // nx, ny and nz are all present
+  uint32_t face_step;                 // bytes per face record when every face is a triangle
+  uint32_t face_pre;                  // bytes of scalar properties ahead of the vertex_indices list
+  uint32_t face_count_bytes, face_index_bytes;
+};
+PlyLayout parsePlyHeader(const uint8_t* data, uint64_t n_bytes);
+
 constexpr int kMomentBlocks = 1184;  // fixed (not SM-count derived) so that sums are identical on any device
 constexpr int kMomentThreads = 256;
 
@@ -160,6 +177,7 @@ struct nb2_context
   const uint8_t* nrm_base = nullptr;
   uint32_t nrm_stride = 0;
   nb2::DevBuf tri;       // uint32[3F]
+  nb2::DevBuf fileImg;   // image of a mesh file being decoded on the device (nb2_mesh_upload_ply)
   // moments / frame
   nb2::DevBuf partials;  // MomentPartial[kMomentBlocks] + final
   nb2::DevBuf counters;  // misc device counters (zeroed per plan)
@@ -285,6 +303,9 @@ void launchSetNormals(nb2_context* c, const float* dev_packed);
 void launchPackOut(nb2_context* c, float* xyz_packed, float* nrm_packed);  // normals from nrm_base / nrm_stride
 void launchVertexNormals(nb2_context* c);
 void launchValidateTriangles(nb2_context* c);
+// PLY records in c->fileImg -> c->blob (32-byte records {x y z 0 nx ny nz 0}, 16-byte ones without normals) and c->tri;
+// counters[16] counts faces that are not triangles, counters[12] receives the largest vertex index
+void launchPlyDecode(nb2_context* c, const PlyLayout& L);
 
 // host-side frame arithmetic (frame.cpp)
 const char* latticeErrorMessage(int code);

@@ -16,6 +16,8 @@ falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
+
 import numpy as np
 
 from . import _capi
@@ -67,6 +69,23 @@ class Context:
         self._mesh_key = None
         mv = _capi.MeshView(data_ptr, n_vertices, point_step, off_xyz, off_normal, 0, tri_ptr, n_triangles)
         _capi.check(self._lib.nb2_mesh_upload(self._h, C.byref(mv)))
+
+    def upload_ply(self, source) -> _capi.MeshFileInfo:
+        """pcl::io::loadPolygonFile + upload for a binary little-endian PLY (noether_gui/src/widgets/tpp_widget.cpp:426):
+        `source` is a path or the bytes of the file; the records are decoded on the device (nb2_mesh_upload_ply)."""
+        self._mesh_key = None
+        info = _capi.MeshFileInfo()
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            img = np.frombuffer(source, dtype=np.uint8) if not isinstance(source, np.ndarray) else np.ascontiguousarray(source).view(np.uint8)
+            _capi.check(self._lib.nb2_mesh_upload_ply(self._h, img.ctypes.data, img.size, C.byref(info)))
+        else:
+            _capi.check(self._lib.nb2_mesh_upload_ply_file(self._h, os.fspath(source).encode(), C.byref(info)))
+        return info
+
+    def download_triangles(self, n_triangles: int) -> np.ndarray:
+        tri = np.zeros((n_triangles, 3), np.uint32)
+        _capi.check(self._lib.nb2_mesh_download_triangles(self._h, tri.ctypes.data))
+        return tri
 
     def set_normals(self, normals: np.ndarray):
         n = np.ascontiguousarray(normals, dtype=np.float32)
@@ -164,6 +183,14 @@ class Context:
         out = C.c_void_p()
         _capi.check(self._lib.nb2_result_gather(self._h, local._r, root, C.byref(out)))
         return ToolPaths(self, out) if out.value else None
+
+
+def ply_inspect(data) -> _capi.MeshFileInfo:
+    """nb2_ply_inspect: vertex / triangle counts and normals flag of a binary little-endian PLY image (host only)."""
+    img = np.frombuffer(bytes(data), dtype=np.uint8)
+    info = _capi.MeshFileInfo()
+    _capi.check(_capi.load().nb2_ply_inspect(img.ctypes.data, img.size, C.byref(info)))
+    return info
 
 
 def make_lattice(pca: _capi.Pca, direction, origin, line_spacing: float, bidirectional: bool = True) -> _capi.Lattice:
@@ -363,6 +390,14 @@ class PlaneSlicerRasterPlanner:
         ctx = self._ctx or default_context()
         ctx.upload(mesh, sharded=sharded_upload)
         p = self._params(mesh)
+        p.shard_rank, p.shard_count = shard_rank, shard_count
+        return ctx.plan(p)
+
+
+    def plan_resident(self, shard_rank: int = 0, shard_count: int = 1) -> ToolPaths:
+        """plan() on the mesh the context already holds (e.g. after Context.upload_ply): no upload."""
+        ctx = self._ctx or default_context()
+        p = self._params(None)
         p.shard_rank, p.shard_count = shard_rank, shard_count
         return ctx.plan(p)
 

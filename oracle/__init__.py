@@ -102,6 +102,15 @@ def lib():
         getattr(L, n).argtypes = [C.c_void_p]
     for n in ("orc_join_close_segments", "orc_minimum_segment_length", "orc_uniform_spacing"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_double]
+    L.orc_read_ply.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    for n in ("orc_mesh_num_vertices", "orc_mesh_num_faces", "orc_mesh_num_indices"):
+        getattr(L, n).argtypes = [C.c_void_p]
+        getattr(L, n).restype = C.c_uint64
+    L.orc_mesh_has_normals.argtypes = [C.c_void_p]
+    L.orc_mesh_export.argtypes = [C.c_void_p, f32p, f32p, u32p, u32p]
+    L.orc_mesh_export.restype = None
+    L.orc_mesh_free.argtypes = [C.c_void_p]
+    L.orc_mesh_free.restype = None
     L.orc_fixture_random_transform.argtypes = [C.c_double, C.c_double, f64p]
     L.orc_fixture_random_transform.restype = None
     L.orc_fixture_plane_mesh.argtypes = [C.c_float, C.c_float, f64p, f32p, f32p, u32p]
@@ -381,3 +390,23 @@ def fixture_plane_mesh(lx, ly, T=None):
                                  xyz.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
                                  tri.ctypes.data_as(C.POINTER(C.c_uint32)))
     return xyz, nrm, tri
+
+
+def read_ply(data: bytes):
+    """pcl::io::loadPolygonFile for a PLY image (vtkPLYReader + vtk2mesh restated, oracle_ply.cpp): returns
+    (xyz float32 (V,3), normals float32 (V,3) or None, face_sizes uint32 (F,), indices uint32 (sum of sizes,))."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    h = C.c_void_p()
+    _check(lib().orc_read_ply(buf.ctypes.data, buf.size, C.byref(h)))
+    try:
+        nv, nf, ni = lib().orc_mesh_num_vertices(h), lib().orc_mesh_num_faces(h), lib().orc_mesh_num_indices(h)
+        xyz = np.zeros((nv, 3), np.float32)
+        nrm = np.zeros((nv, 3), np.float32) if lib().orc_mesh_has_normals(h) else None
+        fs = np.zeros(nf, np.uint32)
+        idx = np.zeros(ni, np.uint32)
+        lib().orc_mesh_export(h, xyz.ctypes.data_as(C.POINTER(C.c_float)),
+                              nrm.ctypes.data_as(C.POINTER(C.c_float)) if nrm is not None else None,
+                              fs.ctypes.data_as(C.POINTER(C.c_uint32)), idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    finally:
+        lib().orc_mesh_free(h)
+    return xyz, nrm, fs, idx

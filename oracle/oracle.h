@@ -142,6 +142,18 @@ int orc_join_close_segments(orc_paths* p, double distance);     /* join_close_se
 int orc_minimum_segment_length(orc_paths* p, double min_length); /* minimum_segment_length_modifier.cpp:12-37 */
 int orc_uniform_spacing(orc_paths* p, double point_spacing);     /* uniform_spacing_modifier.cpp:18-70, degree 1 */
 
+/* ---- mesh files: what pcl::io::loadPolygonFile yields for a PLY (noether_gui/src/widgets/tpp_widget.cpp:426;
+ *      vtkPLYReader + pcl::io::vtk2mesh restated, oracle_ply.cpp) ---- */
+typedef struct orc_mesh orc_mesh;
+int orc_read_ply(const uint8_t* data, uint64_t n_bytes, orc_mesh** out);
+uint64_t orc_mesh_num_vertices(const orc_mesh* m);
+uint64_t orc_mesh_num_faces(const orc_mesh* m);
+uint64_t orc_mesh_num_indices(const orc_mesh* m); /* sum of the face sizes */
+int orc_mesh_has_normals(const orc_mesh* m);
+/* any pointer may be NULL: xyz / nrm 3 floats per vertex, face_size one entry per face, index the concatenated ids */
+void orc_mesh_export(const orc_mesh* m, float* xyz, float* nrm, uint32_t* face_size, uint32_t* index);
+void orc_mesh_free(orc_mesh* m);
+
 /* ---- restated test fixtures ---- */
 /* createRandomTransform(translation_limit, rotation_limit): tool_path_planner_utest.cpp:32-46 (std::mt19937(0)) */
 void orc_fixture_random_transform(double translation_limit, double rotation_limit, double out16[16]);

@@ -66,3 +66,91 @@ def canonical_segments(flat):
             segs.append(min(seq, rev))
         out.append(sorted(segs))
     return out
+
+
+_PLY_NP = {"char": "i1", "uchar": "u1", "short": "<i2", "ushort": "<u2", "int": "<i4", "uint": "<u4", "float": "<f4",
+           "double": "<f8", "int8": "i1", "uint8": "u1", "int16": "<i2", "uint16": "<u2", "int32": "<i4",
+           "uint32": "<u4", "float32": "<f4", "float64": "<f8"}
+
+
+def write_ply(xyz, tri, normals=None, vertex_props=None, count_type="uchar", index_type="int", face_pre=(), face_post=(),
+              comments=(), fmt="binary_little_endian", faces=None, extra_elements_before=()):
+    """A PLY image (bytes).  vertex_props: ordered [(type, name)]; names x y z nx ny nz take the mesh data, anything else
+    a deterministic filler.  face_pre / face_post: [(type, name)] scalar properties around the vertex_indices list.
+    faces: explicit list of index lists (polygons of any size) instead of `tri`.  extra_elements_before: [(name, count,
+    [(type, name)])] scalar-only elements stored ahead of the vertex element."""
+    xyz = np.asarray(xyz, np.float32)
+    n = len(xyz)
+    if vertex_props is None:
+        vertex_props = [("float", a) for a in "xyz"] + ([("float", a) for a in ("nx", "ny", "nz")] if normals is not None else [])
+    polys = [list(map(int, f)) for f in (faces if faces is not None else np.asarray(tri).reshape(-1, 3))]
+    head = ["ply", f"format {fmt} 1.0"] + [f"comment {c}" for c in comments]
+    for name, count, props in extra_elements_before:
+        head.append(f"element {name} {count}")
+        head += [f"property {t} {p}" for t, p in props]
+    head.append(f"element vertex {n}")
+    head += [f"property {t} {p}" for t, p in vertex_props]
+    head.append(f"element face {len(polys)}")
+    head += [f"property {t} {p}" for t, p in face_pre]
+    head.append(f"property list {count_type} {index_type} vertex_indices")
+    head += [f"property {t} {p}" for t, p in face_post]
+    head.append("end_header")
+    out = bytearray(("\n".join(head) + "\n").encode("ascii"))
+    src = {"x": xyz[:, 0], "y": xyz[:, 1], "z": xyz[:, 2]}
+    if normals is not None:
+        nn = np.asarray(normals, np.float32)
+        src.update({"nx": nn[:, 0], "ny": nn[:, 1], "nz": nn[:, 2]})
+
+    def filler(k, count, t):
+        return ((np.arange(count) * (7 + k)) % 113).astype(_PLY_NP[t])
+
+    if fmt == "ascii":
+        lines = []
+        for name, count, props in extra_elements_before:
+            cols = [filler(k, count, t) for k, (t, _) in enumerate(props)]
+            lines += [" ".join(repr(c[i].item()) for c in cols) for i in range(count)]
+        cols = [src[p].astype(_PLY_NP[t]) if p in src else filler(k, n, t) for k, (t, p) in enumerate(vertex_props)]
+        lines += [" ".join(repr(float(c[i])) if c.dtype.kind == "f" else str(int(c[i])) for c in cols) for i in range(n)]
+        for i, f in enumerate(polys):
+            pre = [str(int(filler(k, len(polys), t)[i])) for k, (t, _) in enumerate(face_pre)]
+            post = [str(int(filler(k, len(polys), t)[i])) for k, (t, _) in enumerate(face_post)]
+            lines.append(" ".join(pre + [str(len(f))] + [str(v) for v in f] + post))
+        return bytes(out) + ("\n".join(lines) + "\n").encode("ascii")
+    swap = fmt == "binary_big_endian"
+
+    def packed(arr, t):
+        a = np.asarray(arr).astype(_PLY_NP[t])
+        return a.byteswap().tobytes() if swap else a.tobytes()
+
+    for name, count, props in extra_elements_before:
+        dt = np.dtype([(p, _PLY_NP[t]) for t, p in props])
+        rec = np.zeros(count, dt)
+        for k, (t, p) in enumerate(props):
+            rec[p] = filler(k, count, t)
+        out += rec.byteswap().tobytes() if swap else rec.tobytes()
+    dt = np.dtype([(p, _PLY_NP[t]) for t, p in vertex_props])
+    rec = np.zeros(n, dt)
+    for k, (t, p) in enumerate(vertex_props):
+        rec[p] = src[p].astype(_PLY_NP[t]) if p in src else filler(k, n, t)
+    out += rec.byteswap().tobytes() if swap else rec.tobytes()
+    uniform = len({len(f) for f in polys}) <= 1 and polys
+    if uniform:
+        k = len(polys[0])
+        fields = [(p, _PLY_NP[t]) for t, p in face_pre] + [("_n", _PLY_NP[count_type]), ("_i", _PLY_NP[index_type], (k,))] + \
+                 [(p, _PLY_NP[t]) for t, p in face_post]
+        rec = np.zeros(len(polys), np.dtype(fields))
+        for j, (t, p) in enumerate(face_pre):
+            rec[p] = filler(j, len(polys), t)
+        for j, (t, p) in enumerate(face_post):
+            rec[p] = filler(j, len(polys), t)
+        rec["_n"] = k
+        rec["_i"] = np.asarray(polys).astype(_PLY_NP[index_type])
+        out += rec.byteswap().tobytes() if swap else rec.tobytes()
+    else:
+        for i, f in enumerate(polys):
+            for j, (t, _) in enumerate(face_pre):
+                out += packed(filler(j, len(polys), t)[i:i + 1], t)
+            out += packed([len(f)], count_type) + packed(f, index_type)
+            for j, (t, _) in enumerate(face_post):
+                out += packed(filler(j, len(polys), t)[i:i + 1], t)
+    return bytes(out)
