@@ -251,6 +251,50 @@ int nb2_result_poses(const nb2_result* r, double* out16);
 int nb2_result_poses_segments(const nb2_result* r, double* const* segment_out);
 void nb2_result_free(nb2_result* r);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tool-path modifiers on the device (the noether::ToolPathModifier implementations most often chained after a raster
+ * plan, noether_tpp/src/tool_path_modifiers/).  The poses of a result are expanded (or uploaded) once, stay in HBM as
+ * Eigen::Isometry3d storage (16 doubles per waypoint) while the chain runs — one streaming kernel per modifier, each
+ * reading one pose buffer and writing the other — and come back to the host once, with the float positions / z axes.
+ * Arithmetic: Eigen 3.4's Transform operations in the reference's operand order, no FMA contraction.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef enum nb2_modifier_kind
+{
+  NB2_MOD_SNAKE_ORGANIZATION = 1,          /* snake_organization_modifier.cpp:5-22 */
+  NB2_MOD_LINEAR_APPROACH = 2,             /* linear_approach_modifier.cpp:33-55: v[0..2] = offset, n_points */
+  NB2_MOD_LINEAR_DEPARTURE = 3,            /* linear_departure_modifier.cpp:5-27: v[0..2] = offset, n_points */
+  NB2_MOD_OFFSET = 4,                      /* offset_modifier.cpp:8-22: v[0..15] = offset, column-major 4 x 4 */
+  NB2_MOD_FIXED_ORIENTATION = 5,           /* fixed_orientation_modifier.cpp:5-33: v[0..2] = reference x direction, normalised
+                                              here as the constructor does (:7); v[3] != 0: taken as is, as the YAML decoder
+                                              stores it (:52) */
+  NB2_MOD_UNIFORM_ORIENTATION = 6,         /* uniform_orientation_modifier.cpp:5-30 */
+  NB2_MOD_CONCATENATE = 7,                 /* concatenate_modifier.cpp:5-15 */
+  NB2_MOD_TOOL_DRAG_ORIENTATION = 8,       /* tool_drag_orientation_modifier.cpp:11-35: v[0] = angle_offset, v[1] = tool_radius */
+  NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION = 9,/* biased_tool_drag_orientation_modifier.cpp:12-35: v[0] = angle_offset, v[1] = tool_radius */
+  NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10 /* direction_of_travel_orientation_modifier.cpp:6-48 */
+} nb2_modifier_kind;
+
+typedef struct nb2_modifier
+{
+  int32_t kind;     /* nb2_modifier_kind */
+  int32_t n_points; /* LinearApproach / LinearDeparture */
+  double v[16];
+} nb2_modifier;
+
+/* noether::ToolPaths handed in by a caller (what ToolPathModifier::modify receives): path_offsets[n_paths + 1] index
+ * segments, segment_offsets[n_segments + 1] index waypoints, poses16 = 16 doubles per waypoint (column-major
+ * Eigen::Isometry3d).  The result owns a copy; its positions / normals are the float translation / z axis. */
+int nb2_result_from_poses(nb2_context* ctx, uint64_t n_paths, const uint32_t* path_offsets, uint64_t n_segments,
+                          const uint32_t* segment_offsets, const double* poses16, nb2_result** out);
+/* The same from segment-wise storage: segment_poses[s] points at the 16 * (waypoints of segment s) doubles of segment s —
+ * the data() of each noether::ToolPathSegment — so a plugin hands noether::ToolPaths over without flattening them first. */
+int nb2_result_from_pose_segments(nb2_context* ctx, uint64_t n_paths, const uint32_t* path_offsets, uint64_t n_segments,
+                                  const uint32_t* segment_offsets, const double* const* segment_poses, nb2_result** out);
+/* CompoundModifier::modify (compound_modifier.cpp) over the kinds above: applies chain[0], chain[1], ... to the tool
+ * paths of `in` (left untouched) and returns a result with explicit poses.  A result without explicit poses (a plan) is
+ * expanded on the device exactly as nb2_result_poses would. */
+int nb2_result_modify(nb2_context* ctx, const nb2_result* in, const nb2_modifier* chain, int n_chain, nb2_result** out);
+
 /* Device timings (CUDA events on the context's stream, milliseconds) of the last nb2_mesh_upload followed by those of
  * the last nb2_plan / nb2_slice / nb2_normals_from_mesh_faces on the context; `names` points at static strings.
  * Returns the number of stages written (<= capacity). */

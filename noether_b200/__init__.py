@@ -8,6 +8,10 @@ from . import _capi, meshes  # noqa: F401
 from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionGenerator,  # noqa: F401
                       FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,
-                      default_context, make_lattice)
+                      default_context, make_lattice,
+                      ToolPathModifier, SnakeOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
+                      OffsetModifier, FixedOrientationModifier, UniformOrientationModifier, ConcatenateModifier,
+                      DirectionOfTravelOrientationModifier, ToolDragOrientationToolPathModifier,
+                      BiasedToolDragOrientationToolPathModifier, CompoundModifier)
 
 __version__ = "0.1.0"

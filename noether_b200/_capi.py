@@ -40,7 +40,23 @@ DECLARED_SYMBOLS = [
     "nb2_kernel_launches", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
     "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",
     "nb2_ply_inspect", "nb2_mesh_upload_ply", "nb2_mesh_upload_ply_file", "nb2_mesh_download_triangles",
+    "nb2_result_from_poses", "nb2_result_from_pose_segments", "nb2_result_modify",
 ]
+
+NB2_MOD_SNAKE_ORGANIZATION = 1
+NB2_MOD_LINEAR_APPROACH = 2
+NB2_MOD_LINEAR_DEPARTURE = 3
+NB2_MOD_OFFSET = 4
+NB2_MOD_FIXED_ORIENTATION = 5
+NB2_MOD_UNIFORM_ORIENTATION = 6
+NB2_MOD_CONCATENATE = 7
+NB2_MOD_TOOL_DRAG_ORIENTATION = 8
+NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION = 9
+NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10
+
+
+class Modifier(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_points", C.c_int32), ("v", C.c_double * 16)]
 
 
 class MeshView(C.Structure):
@@ -144,6 +160,9 @@ def load():
     L.nb2_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
     L.nb2_result_gather.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     L.nb2_comm_destroy.argtypes = [vp]
+    L.nb2_result_from_poses.argtypes = [vp, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(vp)]
+    L.nb2_result_from_pose_segments.argtypes = [vp, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(vp)]
+    L.nb2_result_modify.argtypes = [vp, vp, C.POINTER(Modifier), C.c_int, C.POINTER(vp)]
     _lib = L
     return L
 

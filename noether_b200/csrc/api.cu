@@ -676,23 +676,6 @@ void directionOfTravelInPlace(nb2_result& r);
 
 using namespace nb2;
 
-#define NB2_API_BEGIN                                                                                                  \
-  try                                                                                                                  \
-  {
-#define NB2_API_END                                                                                                    \
-  }                                                                                                                    \
-  catch (const nb2::Error& e)                                                                                          \
-  {                                                                                                                    \
-    nb2::setLastError(e.msg);                                                                                          \
-    return e.status;                                                                                                   \
-  }                                                                                                                    \
-  catch (const std::exception& e)                                                                                      \
-  {                                                                                                                    \
-    nb2::setLastError(std::string("internal error: ") + e.what());                                                     \
-    return NB2_ERR_INTERNAL;                                                                                           \
-  }                                                                                                                    \
-  return NB2_OK;
-
 extern "C" {
 
 int nb2_abi_version(void) { return NB2_ABI_VERSION; }
@@ -744,7 +727,8 @@ void nb2_context_destroy(nb2_context* c)
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
-                     &c->csrAdj, &c->csrRank, &c->scanState })
+                     &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
+                     &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)

@@ -1,0 +1,204 @@
+// Host-side planning of a tool-path modifier chain (see modifier_plan.h): structure bookkeeping only — offsets, launch
+// tables, rotation constants.  The waypoints themselves never come to the host while the chain runs.
+#include "modifier_plan.h"
+#include "nb2_internal.h"
+
+#include <cmath>
+#include <string>
+
+namespace nb2
+{
+namespace mod
+{
+void angleAxisMatrix(double angle, const double axis[3], double R[9])
+{
+  // Eigen 3.4 AngleAxis::toRotationMatrix(): sin_axis = sin * axis, cos1_axis = (1 - cos) * axis, off-diagonal terms
+  // from tmp = cos1_axis[i] * axis[j] -/+ sin_axis[k], diagonal cos1_axis[i] * axis[i] + cos
+  const double s = std::sin(angle), c = std::cos(angle);
+  const double sa[3] = { s * axis[0], s * axis[1], s * axis[2] };
+  const double ca[3] = { (1.0 - c) * axis[0], (1.0 - c) * axis[1], (1.0 - c) * axis[2] };
+  double tmp = ca[0] * axis[1];
+  R[1] = tmp - sa[2];
+  R[3] = tmp + sa[2];
+  tmp = ca[0] * axis[2];
+  R[2] = tmp + sa[1];
+  R[6] = tmp - sa[1];
+  tmp = ca[1] * axis[2];
+  R[5] = tmp - sa[0];
+  R[7] = tmp + sa[0];
+  R[0] = ca[0] * axis[0] + c;
+  R[4] = ca[1] * axis[1] + c;
+  R[8] = ca[2] * axis[2] + c;
+}
+
+namespace
+{
+const double kUnitY[3] = { 0.0, 1.0, 0.0 };
+const double kUnitZ[3] = { 0.0, 0.0, 1.0 };
+
+void checkStructure(const Structure& s)
+{
+  if (s.path_off.empty() || s.seg_off.empty() || s.path_off.front() != 0 || s.seg_off.front() != 0 ||
+      s.path_off.back() != s.segments() || s.path_plane.size() != s.paths())
+    fail(NB2_ERR_INVALID_ARGUMENT, "tool path offsets are inconsistent");
+  for (size_t i = 0; i + 1 < s.path_off.size(); ++i)
+    if (s.path_off[i] > s.path_off[i + 1])
+      fail(NB2_ERR_INVALID_ARGUMENT, "path offsets must not decrease");
+  for (size_t i = 0; i + 1 < s.seg_off.size(); ++i)
+    if (s.seg_off[i] > s.seg_off[i + 1])
+      fail(NB2_ERR_INVALID_ARGUMENT, "segment offsets must not decrease");
+}
+
+uint32_t segLen(const Structure& s, uint32_t seg) { return s.seg_off[seg + 1] - s.seg_off[seg]; }
+
+/** segments of `cur` re-listed as `order` (source segment, flipped), each with n_pre / n_post extra points */
+void restructure(const Structure& cur, const std::vector<std::pair<uint32_t, bool>>& order, uint32_t n_pre, uint32_t n_post,
+                 Step& st)
+{
+  st.restructure = true;
+  st.out.path_off = cur.path_off;
+  st.out.path_plane = cur.path_plane;
+  st.out.seg_off.assign(1, 0u);
+  st.map.clear();
+  uint64_t w = 0;
+  for (const auto& o : order)
+  {
+    SegMap m{};
+    m.out_begin = static_cast<uint32_t>(w);
+    m.src_begin = cur.seg_off[o.first];
+    m.src_len = segLen(cur, o.first);
+    m.n_pre = n_pre;
+    m.n_post = n_post;
+    m.flipped = o.second ? 1u : 0u;
+    st.map.push_back(m);
+    w += static_cast<uint64_t>(m.src_len) + n_pre + n_post;
+    if (w > 0xfffffff0ull)
+      fail(NB2_ERR_INVALID_ARGUMENT, "modified tool paths exceed 2^32 waypoints");
+    st.out.seg_off.push_back(static_cast<uint32_t>(w));
+  }
+}
+}  // namespace
+
+std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, int n_chain)
+{
+  checkStructure(in);
+  if (n_chain < 0 || (n_chain > 0 && !chain))
+    fail(NB2_ERR_INVALID_ARGUMENT, "modifier chain is NULL");
+  std::vector<Step> prog;
+  Structure cur = in;
+  for (int k = 0; k < n_chain; ++k)
+  {
+    const nb2_modifier& m = chain[k];
+    Step st;
+    st.kind = m.kind;
+    st.n_points = m.n_points;
+    for (int i = 0; i < 16; ++i)
+      st.v[i] = m.v[i];
+    st.out = cur;
+    st.device = cur.waypoints() > 0;
+    const uint64_t P = cur.paths(), S = cur.segments();
+    switch (m.kind)
+    {
+      case NB2_MOD_SNAKE_ORGANIZATION:
+      {
+        std::vector<std::pair<uint32_t, bool>> order;
+        order.reserve(S);
+        bool any = false;
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          const uint32_t b = cur.path_off[p], e = cur.path_off[p + 1];
+          if (p & 1)
+          {
+            for (uint32_t s = e; s > b; --s)
+              order.emplace_back(s - 1, true);
+            any |= e > b;
+          }
+          else
+            for (uint32_t s = b; s < e; ++s)
+              order.emplace_back(s, false);
+        }
+        if (any)
+          restructure(cur, order, 0, 0, st);
+        else
+          st.device = false;
+        break;
+      }
+      case NB2_MOD_LINEAR_APPROACH:
+      case NB2_MOD_LINEAR_DEPARTURE:
+      {
+        if (m.n_points < 0)
+          fail(NB2_ERR_INVALID_ARGUMENT, "n_points must not be negative");
+        for (uint64_t s = 0; s < S; ++s)
+          if (segLen(cur, static_cast<uint32_t>(s)) == 0)
+            fail(NB2_ERR_INVALID_ARGUMENT, "empty tool path segment (front() / back() of an empty vector in the reference)");
+        if (m.n_points == 0)
+        {
+          st.device = false;
+          break;
+        }
+        std::vector<std::pair<uint32_t, bool>> order;
+        order.reserve(S);
+        for (uint64_t s = 0; s < S; ++s)
+          order.emplace_back(static_cast<uint32_t>(s), false);
+        const bool approach = m.kind == NB2_MOD_LINEAR_APPROACH;
+        restructure(cur, order, approach ? m.n_points : 0, approach ? 0 : m.n_points, st);
+        break;
+      }
+      case NB2_MOD_OFFSET:
+        break;
+      case NB2_MOD_FIXED_ORIENTATION:
+      {
+        // the constructor stores reference_x_direction.normalized() (fixed_orientation_modifier.cpp:7); the YAML decoder
+        // assigns the member directly (:52)
+        const D3 raw = { m.v[0], m.v[1], m.v[2] };
+        const D3 r = m.v[3] != 0.0 ? raw : normalized(raw);
+        st.v[0] = r.x, st.v[1] = r.y, st.v[2] = r.z;
+        break;
+      }
+      case NB2_MOD_UNIFORM_ORIENTATION:
+        // tool_paths.at(0).at(0).at(1) (uniform_orientation_modifier.cpp:8-9)
+        if (P == 0 || cur.path_off[1] == 0 || segLen(cur, 0) < 2)
+          fail(NB2_ERR_INVALID_ARGUMENT, "UniformOrientation needs two waypoints in the first segment of the first tool path "
+                                         "(vector::_M_range_check in the reference)");
+        angleAxisMatrix(M_PI, kUnitZ, st.R[0]);
+        break;
+      case NB2_MOD_CONCATENATE:
+        st.device = false;
+        st.out.path_off = { 0u, static_cast<uint32_t>(S) };
+        st.out.path_plane = { P ? cur.path_plane.front() : int64_t(-1) };
+        break;
+      case NB2_MOD_TOOL_DRAG_ORIENTATION:
+      case NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION:
+      {
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          uint64_t steps = 0;
+          for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+            steps += segLen(cur, s) > 1 ? segLen(cur, s) - 1 : 0;
+          if (steps < 1)
+            fail(NB2_ERR_TOO_FEW_POINTS, "Insufficient number of points to calculate average tool path direction");
+          if (segLen(cur, cur.path_off[p]) == 0)
+            fail(NB2_ERR_INVALID_ARGUMENT, "first segment of a tool path is empty (tool_path.at(0).at(0) in the reference)");
+        }
+        const double angle = m.v[0], radius = m.v[1];
+        angleAxisMatrix(1.0 * -angle, kUnitY, st.R[0]);
+        angleAxisMatrix(-1.0 * -angle, kUnitY, st.R[1]);
+        if (m.kind == NB2_MOD_TOOL_DRAG_ORIENTATION)
+          st.v[2] = radius * std::sin(angle);  // z_offset (tool_drag_orientation_modifier.cpp:28)
+        break;
+      }
+      case NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION:
+        for (uint64_t s = 0; s < S; ++s)
+          if (segLen(cur, static_cast<uint32_t>(s)) < 2)
+            fail(NB2_ERR_TOO_FEW_POINTS, "segment with a single waypoint (segment[i - 1] out of bounds in the reference)");
+        break;
+      default:
+        fail(NB2_ERR_INVALID_ARGUMENT, "unknown modifier kind " + std::to_string(m.kind));
+    }
+    cur = st.out;
+    prog.push_back(std::move(st));
+  }
+  return prog;
+}
+}  // namespace mod
+}  // namespace nb2

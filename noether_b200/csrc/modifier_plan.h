@@ -1,0 +1,44 @@
+// Host side of the tool-path modifier chain: from the structure of the input (offsets only — the poses stay on the
+// device) and the chain, the sequence of device passes with their launch tables and constants.
+#pragma once
+#include "../../include/noether_b200.h"
+#include "modifier_ops.h"
+
+#include <cstdint>
+#include <vector>
+
+namespace nb2
+{
+namespace mod
+{
+/** tool paths -> segments -> waypoints, as offsets */
+struct Structure
+{
+  std::vector<uint32_t> path_off;  // n_paths + 1, indexes segments
+  std::vector<uint32_t> seg_off;   // n_segments + 1, indexes waypoints
+  std::vector<int64_t> path_plane; // n_paths
+  uint64_t paths() const { return path_off.empty() ? 0 : path_off.size() - 1; }
+  uint64_t segments() const { return seg_off.empty() ? 0 : seg_off.size() - 1; }
+  uint64_t waypoints() const { return seg_off.empty() ? 0 : seg_off.back(); }
+};
+
+/** One modifier of the chain, ready to launch */
+struct Step
+{
+  int kind = 0;
+  bool device = false;       // false: bookkeeping only (Concatenate; empty inputs)
+  bool restructure = false;  // true: out-of-place gather through `map`; false: waypoint i -> waypoint i
+  Structure out;             // structure after the step
+  std::vector<SegMap> map;   // one entry per output segment (restructuring steps)
+  double R[2][9] = {};       // rotation for sign > 0 / sign < 0 (tool drag), R[0] for UniformOrientation (row-major)
+  double v[16] = {};         // constants of the per-waypoint operation (see modifiers.cu)
+  int n_points = 0;
+};
+
+/** Eigen::AngleAxisd(angle, axis).toRotationMatrix() for a unit axis, row-major (Eigen 3.4 Geometry/AngleAxis.h) */
+void angleAxisMatrix(double angle, const double axis[3], double R[9]);
+
+/** Throws nb2::Error (via fail) where the reference would throw or read out of bounds. */
+std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, int n_chain);
+}  // namespace mod
+}  // namespace nb2

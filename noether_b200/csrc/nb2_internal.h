@@ -32,6 +32,24 @@ void setLastError(const std::string& msg);
                                     std::to_string(__LINE__) + " (" #expr ")");                                        \
   } while (0)
 
+// every extern "C" entry point: exceptions -> status + thread-local message
+#define NB2_API_BEGIN                                                                                                  \
+  try                                                                                                                  \
+  {
+#define NB2_API_END                                                                                                    \
+  }                                                                                                                    \
+  catch (const nb2::Error& e)                                                                                          \
+  {                                                                                                                    \
+    nb2::setLastError(e.msg);                                                                                          \
+    return e.status;                                                                                                   \
+  }                                                                                                                    \
+  catch (const std::exception& e)                                                                                      \
+  {                                                                                                                    \
+    nb2::setLastError(std::string("internal error: ") + e.what());                                                     \
+    return NB2_ERR_INTERNAL;                                                                                           \
+  }                                                                                                                    \
+  return NB2_OK;
+
 // ---------------------------------------------------------------------------------------------------------------
 // growable device buffer (arena slot).  Capacity only grows; contents are not preserved across growth.
 // ---------------------------------------------------------------------------------------------------------------
@@ -215,6 +233,14 @@ struct nb2_context
   nb2::DevBuf legPlane;   // uint4[2 (P + 1)] per plane {has path, segments, samples} and its exclusive prefix
   nb2::DevBuf legPose;    // double[16 W'] resampled poses
   nb2::DevBuf legPos, legNrm, legSegLen;
+  // tool-path modifiers on the device (modifiers.cu)
+  nb2::DevBuf modPose[2];  // double[16 W] pose buffers the modifiers of a chain ping-pong between
+  nb2::DevBuf modSegOff;   // uint32[S + 1] segment offsets of the current structure
+  nb2::DevBuf modSegMap;   // mod::SegMap[S] source of every output segment (restructuring modifiers)
+  nb2::DevBuf modSegPath;  // uint32[S] tool path of every segment
+  nb2::DevBuf modPathOff;  // uint32[P + 1]
+  nb2::DevBuf modPathSign; // int32[P] tool-drag sign of every tool path
+  nb2::DevBuf modPos, modNrm;  // float[3 W] compact input / float views of the output
   // normals workspace
   nb2::DevBuf faceNrm;   // float4[F]
   nb2::DevBuf valence;   // uint32[V + 1]

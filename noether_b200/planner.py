@@ -228,6 +228,27 @@ class ToolPaths:
         self.post_ops_applied = bool(v.raster_post_ops_applied)
         self.legacy = bool(v.legacy)
 
+    @classmethod
+    def from_nested(cls, nested, context: "Context | None" = None) -> "ToolPaths":
+        """noether::ToolPaths given as list[tool path] of list[segment] of (n, 4, 4) poses (nb2_result_from_poses)."""
+        ctx = context or default_context()
+        path_off = [0]
+        seg_off = [0]
+        chunks = []
+        for path in nested:
+            for seg in path:
+                a = np.asarray(seg, np.float64).reshape(-1, 4, 4)
+                chunks.append(a.transpose(0, 2, 1).reshape(-1, 16))  # column-major storage
+                seg_off.append(seg_off[-1] + len(a))
+            path_off.append(len(seg_off) - 1)
+        poses = np.ascontiguousarray(np.concatenate(chunks) if chunks else np.zeros((0, 16)), np.float64)
+        po = np.asarray(path_off, np.uint32)
+        so = np.asarray(seg_off, np.uint32)
+        h = C.c_void_p()
+        _capi.check(ctx._lib.nb2_result_from_poses(ctx._h, len(po) - 1, po.ctypes.data, len(so) - 1, so.ctypes.data,
+                                                   poses.ctypes.data if len(poses) else None, C.byref(h)))
+        return cls(ctx, h)
+
     def free(self):
         if self._r:
             self._lib.nb2_result_free(self._r)
@@ -444,6 +465,150 @@ class NormalsFromMeshFacesMeshModifier:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# tool path modifiers on the device (noether_tpp/src/tool_path_modifiers/; nb2_result_modify)
+# ---------------------------------------------------------------------------------------------------------------------
+class ToolPathModifier:
+    """noether::ToolPathModifier (core/tool_path_modifier.h): modify(ToolPaths) -> ToolPaths.  `tool_paths` may be a
+    ToolPaths of this package (a plan stays compact until the chain expands it on the device) or nested pose lists."""
+
+    def __init__(self, context: Context | None = None):
+        self._ctx = context
+
+    def _records(self) -> list:
+        raise NotImplementedError
+
+    def modify(self, tool_paths) -> ToolPaths:
+        ctx = self._ctx or (tool_paths._ctx if isinstance(tool_paths, ToolPaths) else default_context())
+        if not isinstance(tool_paths, ToolPaths):
+            tool_paths = ToolPaths.from_nested(tool_paths, ctx)
+        recs = self._records()
+        arr = (_capi.Modifier * max(len(recs), 1))(*recs)
+        h = C.c_void_p()
+        _capi.check(ctx._lib.nb2_result_modify(ctx._h, tool_paths._r, arr, len(recs), C.byref(h)))
+        return ToolPaths(ctx, h)
+
+
+def _record(kind: int, v=(), n_points: int = 0) -> _capi.Modifier:
+    m = _capi.Modifier()
+    m.kind = kind
+    m.n_points = int(n_points)
+    for i, x in enumerate(v):
+        m.v[i] = float(x)
+    return m
+
+
+class SnakeOrganizationModifier(ToolPathModifier):
+    """snake_organization_modifier.cpp:5-22"""
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_SNAKE_ORGANIZATION)]
+
+
+class LinearApproachModifier(ToolPathModifier):
+    """linear_approach_modifier.cpp:23-55"""
+    _kind = _capi.NB2_MOD_LINEAR_APPROACH
+
+    def __init__(self, offset, n_points: int, context: Context | None = None):
+        super().__init__(context)
+        self.offset, self.n_points = np.asarray(offset, np.float64), int(n_points)
+
+    def _records(self):
+        return [_record(self._kind, self.offset, self.n_points)]
+
+
+class LinearDepartureModifier(LinearApproachModifier):
+    """linear_departure_modifier.cpp:5-27"""
+    _kind = _capi.NB2_MOD_LINEAR_DEPARTURE
+
+
+class OffsetModifier(ToolPathModifier):
+    """offset_modifier.cpp:6-22; offset = 4 x 4 isometry"""
+
+    def __init__(self, offset, context: Context | None = None):
+        super().__init__(context)
+        self.offset = np.asarray(offset, np.float64).reshape(4, 4)
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_OFFSET, self.offset.T.reshape(-1))]
+
+
+class FixedOrientationModifier(ToolPathModifier):
+    """fixed_orientation_modifier.cpp:5-33 (the constructor normalises the direction, the YAML decoder does not)"""
+
+    def __init__(self, reference_x_direction, context: Context | None = None, _as_is: bool = False):
+        super().__init__(context)
+        self.ref, self._as_is = np.asarray(reference_x_direction, np.float64), _as_is
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_FIXED_ORIENTATION, [*self.ref, 1.0 if self._as_is else 0.0])]
+
+
+class UniformOrientationModifier(ToolPathModifier):
+    """uniform_orientation_modifier.cpp:5-30"""
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_UNIFORM_ORIENTATION)]
+
+
+class ConcatenateModifier(ToolPathModifier):
+    """concatenate_modifier.cpp:5-15"""
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_CONCATENATE)]
+
+
+class DirectionOfTravelOrientationModifier(ToolPathModifier):
+    """direction_of_travel_orientation_modifier.cpp:6-48"""
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)]
+
+
+class ToolDragOrientationToolPathModifier(ToolPathModifier):
+    """tool_drag_orientation_modifier.cpp:6-35"""
+    _kind = _capi.NB2_MOD_TOOL_DRAG_ORIENTATION
+
+    def __init__(self, angle_offset: float, tool_radius: float, context: Context | None = None):
+        super().__init__(context)
+        self.angle_offset, self.tool_radius = float(angle_offset), float(tool_radius)
+
+    def _records(self):
+        return [_record(self._kind, [self.angle_offset, self.tool_radius])]
+
+
+class BiasedToolDragOrientationToolPathModifier(ToolDragOrientationToolPathModifier):
+    """biased_tool_drag_orientation_modifier.cpp:6-35"""
+    _kind = _capi.NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION
+
+
+class CompoundModifier(ToolPathModifier):
+    """compound_modifier.cpp: the modifiers in order; here one device-resident chain, one upload and one download"""
+
+    def __init__(self, modifiers, context: Context | None = None):
+        super().__init__(context)
+        self.modifiers = list(modifiers)
+
+    def _records(self):
+        return [r for m in self.modifiers for r in m._records()]
+
+
+def _isometry_from_yaml(node: dict) -> np.ndarray:
+    """Translation3d(x, y, z) * Quaterniond(qw, qx, qy, qz) (serialization.h:41-55; Eigen 3.4
+    QuaternionBase::toRotationMatrix, the quaternion is taken as given)"""
+    x, y, z, w = (float(_member(node, k)) for k in ("qx", "qy", "qz", "qw"))
+    tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    T = np.eye(4)
+    T[0, 0], T[0, 1], T[0, 2] = 1.0 - (tyy + tzz), txy - twz, txz + twy
+    T[1, 0], T[1, 1], T[1, 2] = txy + twz, 1.0 - (txx + tzz), tyz - twx
+    T[2, 0], T[2, 1], T[2, 2] = txz - twy, tyz + twx, 1.0 - (txx + tyy)
+    T[:3, 3] = [float(_member(node, k)) for k in ("x", "y", "z")]
+    return T
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Factory (aliases + YAML keys of plugins.cpp)
 # ---------------------------------------------------------------------------------------------------------------------
 def _member(config: dict, key: str):
@@ -499,6 +664,32 @@ class Factory:
         tpp.set_line_spacing(float(_member(config, "line_spacing")))
         tpp.generate_rasters_bidirectionally(bool(_member(config, "bidirectional")))
         return tpp
+
+    def create_tool_path_modifier(self, config: dict) -> ToolPathModifier:
+        """aliases and YAML keys of plugins.cpp:182-219 for the modifiers that run on the device"""
+        name = _member(config, "name")
+        c = self._ctx
+        if name == "SnakeOrganization":
+            return SnakeOrganizationModifier(c)
+        if name in ("LinearApproach", "LinearDeparture"):
+            cls = LinearApproachModifier if name == "LinearApproach" else LinearDepartureModifier
+            return cls(_vec3(_member(config, "offset")), int(_member(config, "n_points")), c)
+        if name == "Offset":
+            return OffsetModifier(_isometry_from_yaml(_member(config, "offset")), c)
+        if name == "FixedOrientation":
+            return FixedOrientationModifier(_vec3(_member(config, "ref_x_dir")), c, _as_is=True)
+        if name == "UniformOrientation":
+            return UniformOrientationModifier(c)
+        if name == "Concatenate":
+            return ConcatenateModifier(c)
+        if name == "DirectionOfTravelOrientation":
+            return DirectionOfTravelOrientationModifier(c)
+        if name in ("ToolDragOrientation", "BiasedToolDragOrientation"):
+            cls = ToolDragOrientationToolPathModifier if name == "ToolDragOrientation" else BiasedToolDragOrientationToolPathModifier
+            return cls(float(_member(config, "angle_offset")), float(_member(config, "tool_radius")), c)
+        if name == "CompoundToolPathModifier":
+            return CompoundModifier([self.create_tool_path_modifier(e) for e in _member(config, "modifiers")], c)
+        raise RuntimeError(f"Failed to find plugin '{name}' in section 'mod'")
 
     def create_mesh_modifier(self, config: dict) -> NormalsFromMeshFacesMeshModifier:
         name = _member(config, "name")

@@ -98,8 +98,15 @@ def lib():
         getattr(L, n).restype = C.c_uint64
     L.orc_paths_export.argtypes = [C.c_void_p, u64p, u64p, i64p, f32p, f32p, u32p, u32p, f64p]
     L.orc_paths_export.restype = None
-    for n in ("orc_raster_organization", "orc_direction_of_travel"):
+    for n in ("orc_raster_organization", "orc_direction_of_travel", "orc_snake_organization",
+              "orc_uniform_orientation", "orc_concatenate"):
         getattr(L, n).argtypes = [C.c_void_p]
+    for n in ("orc_linear_approach", "orc_linear_departure"):
+        getattr(L, n).argtypes = [C.c_void_p, f64p, C.c_int]
+    L.orc_offset.argtypes = [C.c_void_p, f64p]
+    L.orc_fixed_orientation.argtypes = [C.c_void_p, f64p]
+    for n in ("orc_tool_drag_orientation", "orc_biased_tool_drag_orientation"):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_double, C.c_double]
     for n in ("orc_join_close_segments", "orc_minimum_segment_length", "orc_uniform_spacing"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_double]
     L.orc_read_ply.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
@@ -320,6 +327,47 @@ class Paths:
 
     def uniform_spacing(self, point_spacing):
         _check(lib().orc_uniform_spacing(self._h, point_spacing))
+        return self
+
+    # tool-path modifiers chained after a raster plan, in place
+    def snake_organization(self):
+        _check(lib().orc_snake_organization(self._h))
+        return self
+
+    def linear_approach(self, offset, n_points):
+        v = np.ascontiguousarray(offset, np.float64)
+        _check(lib().orc_linear_approach(self._h, v.ctypes.data_as(C.POINTER(C.c_double)), int(n_points)))
+        return self
+
+    def linear_departure(self, offset, n_points):
+        v = np.ascontiguousarray(offset, np.float64)
+        _check(lib().orc_linear_departure(self._h, v.ctypes.data_as(C.POINTER(C.c_double)), int(n_points)))
+        return self
+
+    def offset(self, T):
+        m = np.ascontiguousarray(np.asarray(T, np.float64).T)  # column-major
+        _check(lib().orc_offset(self._h, m.ctypes.data_as(C.POINTER(C.c_double))))
+        return self
+
+    def fixed_orientation(self, ref_x):
+        v = np.ascontiguousarray(ref_x, np.float64)
+        _check(lib().orc_fixed_orientation(self._h, v.ctypes.data_as(C.POINTER(C.c_double))))
+        return self
+
+    def uniform_orientation(self):
+        _check(lib().orc_uniform_orientation(self._h))
+        return self
+
+    def concatenate(self):
+        _check(lib().orc_concatenate(self._h))
+        return self
+
+    def tool_drag_orientation(self, angle_offset, tool_radius):
+        _check(lib().orc_tool_drag_orientation(self._h, angle_offset, tool_radius))
+        return self
+
+    def biased_tool_drag_orientation(self, angle_offset, tool_radius):
+        _check(lib().orc_biased_tool_drag_orientation(self._h, angle_offset, tool_radius))
         return self
 
 

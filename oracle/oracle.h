@@ -142,6 +142,17 @@ int orc_join_close_segments(orc_paths* p, double distance);     /* join_close_se
 int orc_minimum_segment_length(orc_paths* p, double min_length); /* minimum_segment_length_modifier.cpp:12-37 */
 int orc_uniform_spacing(orc_paths* p, double point_spacing);     /* uniform_spacing_modifier.cpp:18-70, degree 1 */
 
+/* tool-path modifiers commonly chained after a raster plan */
+int orc_snake_organization(orc_paths* p);                                        /* snake_organization_modifier.cpp:5-22 */
+int orc_linear_approach(orc_paths* p, const double offset[3], int n_points);     /* linear_approach_modifier.cpp:33-55 */
+int orc_linear_departure(orc_paths* p, const double offset[3], int n_points);    /* linear_departure_modifier.cpp:5-27 */
+int orc_offset(orc_paths* p, const double offset16[16]);                         /* offset_modifier.cpp:8-22 (column-major 4x4) */
+int orc_fixed_orientation(orc_paths* p, const double ref_x[3]);                  /* fixed_orientation_modifier.cpp:5-33 */
+int orc_uniform_orientation(orc_paths* p);                                       /* uniform_orientation_modifier.cpp:5-30 */
+int orc_concatenate(orc_paths* p);                                               /* concatenate_modifier.cpp:5-15 */
+int orc_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius);        /* tool_drag_orientation_modifier.cpp:11-35 */
+int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius); /* biased_tool_drag_orientation_modifier.cpp:12-35 */
+
 /* ---- mesh files: what pcl::io::loadPolygonFile yields for a PLY (noether_gui/src/widgets/tpp_widget.cpp:426;
  *      vtkPLYReader + pcl::io::vtk2mesh restated, oracle_ply.cpp) ---- */
 typedef struct orc_mesh orc_mesh;

@@ -66,6 +66,13 @@ int directionOfTravel(orc_paths& p);
 int joinCloseSegments(orc_paths& p, double distance);
 int minimumSegmentLength(orc_paths& p, double min_length);
 int uniformSpacing(orc_paths& p, double point_spacing);
+int snakeOrganization(orc_paths& p);
+int linearApproachDeparture(orc_paths& p, const double offset[3], int n_points, bool departure);
+int offsetModifier(orc_paths& p, const double offset16[16]);
+int fixedOrientation(orc_paths& p, const double ref_x[3]);
+int uniformOrientation(orc_paths& p);
+int concatenate(orc_paths& p);
+int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased);
 
 inline V3d translation(const Waypoint& w) { return { w.T[12], w.T[13], w.T[14] }; }
 }  // namespace orc

@@ -132,6 +132,216 @@ int directionOfTravel(orc_paths& p)
   return ORC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tool-path modifiers applied after a raster plan.  Matrix products follow this oracle's Eigen
+// convention for fixed-size 3-term sums, a0 + (a1 + a2) (oracle_math.h); Transform arithmetic restated from Eigen 3.4
+// Geometry/Transform.h: operator*(Translation) = translate(): t += L v;  operator*(RotationBase) = rotate(): L = L R;
+// Transform * Transform (Isometry): L = La Lb, t = La tb + ta, last row 0 0 0 1.
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+inline double& at(Waypoint& w, int r, int c) { return w.T[4 * c + r]; }
+inline double at(const Waypoint& w, int r, int c) { return w.T[4 * c + r]; }
+
+/** L(w) * v */
+V3d linearTimes(const Waypoint& w, const V3d& v)
+{
+  V3d r;
+  for (int i = 0; i < 3; ++i)
+    r[i] = eigenSum3(at(w, i, 0) * v.x, at(w, i, 1) * v.y, at(w, i, 2) * v.z);
+  return r;
+}
+/** L(w) = L(w) * R   (R row-major 3x3) */
+void linearTimesMatrix(Waypoint& w, const double R[9])
+{
+  double out[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      out[r][c] = eigenSum3(at(w, r, 0) * R[0 * 3 + c], at(w, r, 1) * R[1 * 3 + c], at(w, r, 2) * R[2 * 3 + c]);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      at(w, r, c) = out[r][c];
+}
+/** Eigen::AngleAxisd(angle, axis).toRotationMatrix(), row-major (Eigen 3.4 Geometry/AngleAxis.h) */
+void angleAxisMatrix(double angle, const V3d& axis, double R[9])
+{
+  const double s = std::sin(angle), c = std::cos(angle);
+  const V3d sin_axis = s * axis;
+  const V3d cos1_axis = (1.0 - c) * axis;
+  double tmp;
+  tmp = cos1_axis.x * axis.y;
+  R[0 * 3 + 1] = tmp - sin_axis.z;
+  R[1 * 3 + 0] = tmp + sin_axis.z;
+  tmp = cos1_axis.x * axis.z;
+  R[0 * 3 + 2] = tmp + sin_axis.y;
+  R[2 * 3 + 0] = tmp - sin_axis.y;
+  tmp = cos1_axis.y * axis.z;
+  R[1 * 3 + 2] = tmp - sin_axis.x;
+  R[2 * 3 + 1] = tmp + sin_axis.x;
+  R[0 * 3 + 0] = cos1_axis.x * axis.x + c;
+  R[1 * 3 + 1] = cos1_axis.y * axis.y + c;
+  R[2 * 3 + 2] = cos1_axis.z * axis.z + c;
+}
+/** w.translate(v) */
+void translate(Waypoint& w, const V3d& v)
+{
+  const V3d d = linearTimes(w, v);
+  w.T[12] += d.x;
+  w.T[13] += d.y;
+  w.T[14] += d.z;
+}
+}  // namespace
+
+/** SnakeOrganizationModifier::modify (snake_organization_modifier.cpp:5-22) */
+int snakeOrganization(orc_paths& p)
+{
+  for (size_t i = 1; i < p.paths.size(); i += 2)
+  {
+    for (Segment& segment : p.paths[i].segments)
+      std::reverse(segment.begin(), segment.end());
+    std::reverse(p.paths[i].segments.begin(), p.paths[i].segments.end());
+  }
+  return ORC_OK;
+}
+
+/** LinearApproachModifier::modify (linear_approach_modifier.cpp:33-55) / LinearDepartureModifier::modify
+ *  (linear_departure_modifier.cpp:5-27) */
+int linearApproachDeparture(orc_paths& p, const double offset[3], int n_points, bool departure)
+{
+  const V3d off = { offset[0], offset[1], offset[2] };
+  for (Path& tool_path : p.paths)
+    for (Segment& segment : tool_path.segments)
+    {
+      if (segment.empty())
+      {
+        setError("empty segment (front() / back() of an empty vector in the reference)");
+        return ORC_ERR_INVALID;
+      }
+      const Waypoint anchor = departure ? segment.back() : segment.front();
+      Segment added;
+      for (int i = 0; i < n_points; ++i)
+      {
+        Waypoint pt = anchor;
+        translate(pt, off * (static_cast<double>(i + 1) / static_cast<double>(n_points)));
+        added.push_back(pt);  // pt.linear() = anchor.linear(): unchanged by translate
+      }
+      if (departure)
+        segment.insert(segment.end(), added.begin(), added.end());
+      else
+        segment.insert(segment.begin(), added.rbegin(), added.rend());
+    }
+  return ORC_OK;
+}
+
+/** OffsetModifier::modify (offset_modifier.cpp:8-22): w = w * offset */
+int offsetModifier(orc_paths& p, const double O[16])
+{
+  double R[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      R[r * 3 + c] = O[4 * c + r];
+  const V3d to = { O[12], O[13], O[14] };
+  for (Path& tool_path : p.paths)
+    for (Segment& segment : tool_path.segments)
+      for (Waypoint& w : segment)
+      {
+        const V3d d = linearTimes(w, to);  // lhs.linear() * rhs.translation() is evaluated before the sum
+        linearTimesMatrix(w, R);
+        w.T[12] = d.x + w.T[12];
+        w.T[13] = d.y + w.T[13];
+        w.T[14] = d.z + w.T[14];
+        w.T[3] = w.T[7] = w.T[11] = 0.0;  // makeAffine()
+        w.T[15] = 1.0;
+      }
+  return ORC_OK;
+}
+
+/** FixedOrientationModifier::modify (fixed_orientation_modifier.cpp:10-33); the constructor normalises the direction */
+int fixedOrientation(orc_paths& p, const double ref_x[3])
+{
+  const V3d ref = eigenNormalized(V3d{ ref_x[0], ref_x[1], ref_x[2] });
+  for (Path& tool_path : p.paths)
+    for (Segment& segment : tool_path.segments)
+      for (Waypoint& w : segment)
+      {
+        const V3d z = { w.T[8], w.T[9], w.T[10] };
+        const V3d y = eigenCross(z, ref);
+        const V3d x = eigenCross(y, z);
+        w.T[0] = x.x, w.T[1] = x.y, w.T[2] = x.z;
+        w.T[4] = y.x, w.T[5] = y.y, w.T[6] = y.z;
+      }
+  return ORC_OK;
+}
+
+/** UniformOrientationModifier::modify (uniform_orientation_modifier.cpp:5-30) */
+int uniformOrientation(orc_paths& p)
+{
+  if (p.paths.empty() || p.paths[0].segments.empty() || p.paths[0].segments[0].size() < 2)
+  {
+    setError("vector::_M_range_check (tool_paths.at(0).at(0).at(1))");
+    return ORC_ERR_INVALID;
+  }
+  const V3d ref = eigenNormalized(translation(p.paths[0].segments[0][1]) - translation(p.paths[0].segments[0][0]));
+  double R[9];
+  angleAxisMatrix(M_PI, V3d{ 0.0, 0.0, 1.0 }, R);
+  for (Path& tool_path : p.paths)
+    for (Segment& segment : tool_path.segments)
+      for (Waypoint& w : segment)
+      {
+        const double dp = eigenDot(ref, V3d{ w.T[0], w.T[1], w.T[2] });
+        if (dp < 0.0)
+          linearTimesMatrix(w, R);
+      }
+  return ORC_OK;
+}
+
+/** ConcatenateModifier::modify (concatenate_modifier.cpp:5-15) */
+int concatenate(orc_paths& p)
+{
+  Path combined;
+  combined.plane = p.paths.empty() ? -1 : p.paths.front().plane;
+  for (const Path& path : p.paths)
+    for (const Segment& segment : path.segments)
+      combined.segments.push_back(segment);
+  p.paths.clear();
+  p.paths.push_back(std::move(combined));
+  return ORC_OK;
+}
+
+/** ToolDragOrientationToolPathModifier::modify (tool_drag_orientation_modifier.cpp:11-35) and
+ *  BiasedToolDragOrientationToolPathModifier::modify (biased_tool_drag_orientation_modifier.cpp:12-35) */
+int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased)
+{
+  for (Path& tool_path : p.paths)
+  {
+    V3d dir;
+    if (!estimateToolPathDirection(tool_path, dir))
+      return ORC_ERR_TOO_FEW_POINTS;
+    const Waypoint& first = tool_path.segments.at(0).at(0);
+    const V3d y = { first.T[4], first.T[5], first.T[6] };
+    const V3d z = { first.T[8], first.T[9], first.T[10] };
+    const double sign = eigenDot(eigenCross(z, dir), y) > 0.0 ? 1.0 : -1.0;
+    double R[9];
+    angleAxisMatrix(sign * -angle_offset, V3d{ 0.0, 1.0, 0.0 }, R);
+    for (Segment& segment : tool_path.segments)
+      for (Waypoint& w : segment)
+      {
+        if (!biased)
+        {
+          const double z_offset = tool_radius * std::sin(angle_offset);
+          translate(w, V3d{ 0.0, 0.0, z_offset });
+          linearTimesMatrix(w, R);
+        }
+        else
+        {
+          linearTimesMatrix(w, R);
+          translate(w, V3d{ sign * tool_radius, 0.0, 0.0 });
+        }
+      }
+  }
+  return ORC_OK;
+}
+
 int joinCloseSegments(orc_paths& p, double distance)
 {
   for (Path& tool_path : p.paths)
@@ -463,6 +673,15 @@ void orc_paths_export(const orc_paths* p,
 
 int orc_raster_organization(orc_paths* p) { return rasterOrganization(*p); }
 int orc_direction_of_travel(orc_paths* p) { return directionOfTravel(*p); }
+int orc_snake_organization(orc_paths* p) { return snakeOrganization(*p); }
+int orc_linear_approach(orc_paths* p, const double offset[3], int n_points) { return linearApproachDeparture(*p, offset, n_points, false); }
+int orc_linear_departure(orc_paths* p, const double offset[3], int n_points) { return linearApproachDeparture(*p, offset, n_points, true); }
+int orc_offset(orc_paths* p, const double offset16[16]) { return offsetModifier(*p, offset16); }
+int orc_fixed_orientation(orc_paths* p, const double ref_x[3]) { return fixedOrientation(*p, ref_x); }
+int orc_uniform_orientation(orc_paths* p) { return uniformOrientation(*p); }
+int orc_concatenate(orc_paths* p) { return concatenate(*p); }
+int orc_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, false); }
+int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, true); }
 int orc_join_close_segments(orc_paths* p, double d) { return joinCloseSegments(*p, d); }
 int orc_minimum_segment_length(orc_paths* p, double l) { return minimumSegmentLength(*p, l); }
 int orc_uniform_spacing(orc_paths* p, double s) { return uniformSpacing(*p, s); }

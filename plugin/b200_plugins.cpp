@@ -586,6 +586,90 @@ public:
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+// tool path modifiers
+// ---------------------------------------------------------------------------------------------------------------------
+/** A noether::ToolPathModifier that runs on the GPU (nb2_result_modify): the poses go to the device once, every modifier
+ *  of the chain is one streaming kernel over them, and they come back once.  One object stands for one modifier of the
+ *  reference, or — built by the CompoundToolPathModifier plugin below — for a whole chain of them. */
+class DeviceToolPathModifier : public noether::ToolPathModifier
+{
+public:
+  explicit DeviceToolPathModifier(std::vector<nb2_modifier> chain) : chain_(std::move(chain)) {}
+  const std::vector<nb2_modifier>& chain() const { return chain_; }
+
+  noether::ToolPaths modify(noether::ToolPaths tool_paths) const override final
+  {
+    static_assert(sizeof(Eigen::Isometry3d) == 16 * sizeof(double), "Isometry3d is not a bare 4x4 double matrix");
+    std::vector<std::uint32_t> path_off(1, 0u), seg_off(1, 0u);
+    std::vector<const double*> seg_data;
+    std::uint64_t w = 0;
+    for (const noether::ToolPath& path : tool_paths)
+    {
+      for (const noether::ToolPathSegment& seg : path)
+      {
+        seg_data.push_back(seg.empty() ? nullptr : seg.front().matrix().data());
+        w += seg.size();
+        if (w > 0xfffffff0ull)
+          throw std::runtime_error("tool paths exceed 2^32 waypoints");
+        seg_off.push_back(static_cast<std::uint32_t>(w));
+      }
+      path_off.push_back(static_cast<std::uint32_t>(seg_data.size()));
+    }
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    Trace trace("ToolPathModifier::modify");
+    nb2_result* in = nullptr;
+    Device::check(nb2_result_from_pose_segments(dev.ctx(), tool_paths.size(), path_off.data(), seg_data.size(), seg_off.data(),
+                                                seg_data.data(), &in));
+    std::unique_ptr<nb2_result, void (*)(nb2_result*)> in_guard(in, nb2_result_free);
+    nb2_result* r = nullptr;
+    Device::check(nb2_result_modify(dev.ctx(), in, chain_.data(), static_cast<int>(chain_.size()), &r));
+    trace.lap("nb2_result_modify");
+    std::unique_ptr<nb2_result, void (*)(nb2_result*)> guard(r, nb2_result_free);
+    noether::ToolPaths out = toToolPaths(r);
+    trace.lap("ToolPaths");
+    return out;
+  }
+
+private:
+  std::vector<nb2_modifier> chain_;
+};
+
+namespace
+{
+nb2_modifier record(int kind)
+{
+  nb2_modifier m{};
+  m.kind = kind;
+  return m;
+}
+/** Eigen::Vector3d as serialization.h:59-83 reads it */
+void readVector3(const YAML::Node& node, double out[3])
+{
+  out[0] = YAML::getMember<double>(node, "x");
+  out[1] = YAML::getMember<double>(node, "y");
+  out[2] = YAML::getMember<double>(node, "z");
+}
+/** Eigen::Isometry3d as serialization.h:41-55 reads it: Translation3d(x, y, z) * Quaterniond(qw, qx, qy, qz), column-major
+ *  (the quaternion as given; Eigen 3.4 QuaternionBase::toRotationMatrix) */
+void readIsometry(const YAML::Node& node, double T[16])
+{
+  const double x = YAML::getMember<double>(node, "qx"), y = YAML::getMember<double>(node, "qy"),
+               z = YAML::getMember<double>(node, "qz"), w = YAML::getMember<double>(node, "qw");
+  const double tx = 2.0 * x, ty = 2.0 * y, tz = 2.0 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  T[0] = 1.0 - (tyy + tzz), T[4] = txy - twz, T[8] = txz + twy;
+  T[1] = txy + twz, T[5] = 1.0 - (txx + tzz), T[9] = tyz - twx;
+  T[2] = txz - twy, T[6] = tyz + twx, T[10] = 1.0 - (txx + tyy);
+  T[3] = T[7] = T[11] = 0.0;
+  readVector3(node, T + 12);
+  T[15] = 1.0;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
 // plugins: same aliases, sections and YAML keys as the reference (src/plugins.cpp)
 // ---------------------------------------------------------------------------------------------------------------------
 struct Plugin_PrincipalAxisDirectionGenerator : public noether::Plugin<noether::DirectionGenerator>
@@ -660,8 +744,111 @@ struct Plugin_PlaneSlicerLegacyRasterPlanner : public noether::Plugin<noether::T
   }
 };
 
+/** The tool path modifiers that run on the device, under the reference's aliases and YAML keys (plugins.cpp:182-199 and
+ *  the YAML::convert<>::decode of each modifier) */
+template <int KIND>
+struct Plugin_DeviceToolPathModifier : public noether::Plugin<noether::ToolPathModifier>
+{
+  std::unique_ptr<noether::ToolPathModifier> create(const YAML::Node& config,
+                                                    std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    nb2_modifier m = record(KIND);
+    switch (KIND)
+    {
+      case NB2_MOD_LINEAR_APPROACH:   // linear_approach_modifier.cpp:68-73
+      case NB2_MOD_LINEAR_DEPARTURE:  // linear_departure_modifier.cpp (same keys)
+        readVector3(YAML::getMember<YAML::Node>(config, "offset"), m.v);
+        m.n_points = YAML::getMember<int>(config, "n_points");
+        break;
+      case NB2_MOD_OFFSET:  // offset_modifier.cpp:37-41
+        readIsometry(YAML::getMember<YAML::Node>(config, "offset"), m.v);
+        break;
+      case NB2_MOD_FIXED_ORIENTATION:  // fixed_orientation_modifier.cpp:50-54: the member is assigned, not normalised
+        readVector3(YAML::getMember<YAML::Node>(config, "ref_x_dir"), m.v);
+        m.v[3] = 1.0;
+        break;
+      case NB2_MOD_TOOL_DRAG_ORIENTATION:         // tool_drag_orientation_modifier.cpp:51-57
+      case NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION:  // biased_tool_drag_orientation_modifier.cpp (same keys)
+        m.v[0] = YAML::getMember<double>(config, "angle_offset");
+        m.v[1] = YAML::getMember<double>(config, "tool_radius");
+        break;
+      default:  // SnakeOrganization, UniformOrientation, Concatenate, DirectionOfTravelOrientation: no keys
+        break;
+    }
+    return std::make_unique<DeviceToolPathModifier>(std::vector<nb2_modifier>{ m });
+  }
+};
+using Plugin_SnakeOrganization = Plugin_DeviceToolPathModifier<NB2_MOD_SNAKE_ORGANIZATION>;
+using Plugin_LinearApproach = Plugin_DeviceToolPathModifier<NB2_MOD_LINEAR_APPROACH>;
+using Plugin_LinearDeparture = Plugin_DeviceToolPathModifier<NB2_MOD_LINEAR_DEPARTURE>;
+using Plugin_Offset = Plugin_DeviceToolPathModifier<NB2_MOD_OFFSET>;
+using Plugin_FixedOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_FIXED_ORIENTATION>;
+using Plugin_UniformOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_UNIFORM_ORIENTATION>;
+using Plugin_Concatenate = Plugin_DeviceToolPathModifier<NB2_MOD_CONCATENATE>;
+using Plugin_ToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_TOOL_DRAG_ORIENTATION>;
+using Plugin_BiasedToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION>;
+using Plugin_DirectionOfTravelOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION>;
+
+/** CompoundModifier (compound_modifier.cpp) whose runs of consecutive device modifiers are fused into one device chain;
+ *  any other modifier the factory returns (the reference's own) is applied in its place in the sequence. */
+class CompoundToolPathModifier : public noether::ToolPathModifier
+{
+public:
+  explicit CompoundToolPathModifier(std::vector<noether::ToolPathModifier::ConstPtr> modifiers)
+  {
+    for (auto& m : modifiers)
+    {
+      const auto* dev = dynamic_cast<const DeviceToolPathModifier*>(m.get());
+      const auto* last = stages_.empty() ? nullptr : dynamic_cast<const DeviceToolPathModifier*>(stages_.back().get());
+      if (dev && last)
+      {
+        std::vector<nb2_modifier> chain = last->chain();
+        chain.insert(chain.end(), dev->chain().begin(), dev->chain().end());
+        stages_.back() = std::make_unique<DeviceToolPathModifier>(std::move(chain));
+      }
+      else
+        stages_.push_back(std::move(m));
+    }
+  }
+  noether::ToolPaths modify(noether::ToolPaths tool_paths) const override final
+  {
+    for (const auto& stage : stages_)
+      tool_paths = stage->modify(std::move(tool_paths));
+    return tool_paths;
+  }
+  std::size_t stages() const { return stages_.size(); }
+
+private:
+  std::vector<noether::ToolPathModifier::ConstPtr> stages_;
+};
+
+struct Plugin_CompoundToolPathModifier : public noether::Plugin<noether::ToolPathModifier>
+{
+  std::unique_ptr<noether::ToolPathModifier> create(const YAML::Node& config,
+                                                    std::shared_ptr<const noether::Factory> factory) const override final
+  {
+    // plugins.cpp:202-218
+    std::vector<noether::ToolPathModifier::ConstPtr> modifiers;
+    const YAML::Node modifiers_config = YAML::getMember<YAML::Node>(config, "modifiers");
+    for (const YAML::Node& entry : modifiers_config)
+      modifiers.push_back(factory->createToolPathModifier(entry));
+    return std::make_unique<CompoundToolPathModifier>(std::move(modifiers));
+  }
+};
+
 }  // namespace noether_b200
 
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_SnakeOrganization, SnakeOrganization)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_LinearApproach, LinearApproach)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_LinearDeparture, LinearDeparture)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_Offset, Offset)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_FixedOrientation, FixedOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_UniformOrientation, UniformOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_Concatenate, Concatenate)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_ToolDragOrientation, ToolDragOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_BiasedToolDragOrientation, BiasedToolDragOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_DirectionOfTravelOrientation, DirectionOfTravelOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PCARotatedDirectionGenerator, PCARotated)

@@ -53,6 +53,7 @@ public:
     return create<DirectionGeneratorPlugin>(config);
   }
   OriginGenerator::Ptr createOriginGenerator(const YAML::Node& config) const { return create<OriginGeneratorPlugin>(config); }
+  ToolPathModifier::Ptr createToolPathModifier(const YAML::Node& config) const { return create<ToolPathModifierPlugin>(config); }
 
 protected:
   std::shared_ptr<const boost_plugin_loader::PluginLoader> loader_;

@@ -44,6 +44,9 @@ public:
   }
   std::size_t size() const { return data_ ? data_->seq.size() : 0; }
   Node operator[](std::size_t i) const { return data_->seq.at(i); }
+  /** sequence iteration */
+  std::vector<Node>::const_iterator begin() const { return data_ ? data_->seq.begin() : empty().begin(); }
+  std::vector<Node>::const_iterator end() const { return data_ ? data_->seq.end() : empty().end(); }
 
   template <typename T>
   T as() const;
@@ -63,6 +66,11 @@ private:
     ss.precision(17);
     ss << v;
     data_->scalar = ss.str();
+  }
+  static const std::vector<Node>& empty()
+  {
+    static const std::vector<Node> none;
+    return none;
   }
   std::shared_ptr<Data> data_;
 };
@@ -85,6 +93,13 @@ inline double Node::as<double>() const
   if (!data_)
     throw std::runtime_error("bad conversion");
   return std::stod(data_->scalar);
+}
+template <>
+inline int Node::as<int>() const
+{
+  if (!data_)
+    throw std::runtime_error("bad conversion");
+  return std::stoi(data_->scalar);
 }
 template <>
 inline bool Node::as<bool>() const

@@ -621,6 +621,143 @@ void timePipeline(const noether::Factory& factory, unsigned nx, unsigned ny, dou
   }
 }
 
+// ---- ToolPathModifierTestFixture / OneTimeToolPathModifierTestFixture (tool_path_modifier_utest.cpp:14-96,120-214,261-304)
+//      for the modifiers this library runs on the device, created by alias from the reference's test YAML
+noether::ToolPaths gridToolPaths(unsigned p, unsigned s, unsigned w, bool identity)
+{
+  noether::ToolPaths paths(p);
+  for (unsigned pi = 0; pi < p; ++pi)
+  {
+    paths[pi].resize(s);
+    for (unsigned si = 0; si < s; ++si)
+    {
+      paths[pi][si].resize(w);
+      for (unsigned wi = 0; wi < w; ++wi)
+      {
+        double* T = paths[pi][si][wi].matrix().data();
+        for (int k = 0; k < 16; ++k)
+          T[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        if (!identity)
+        {
+          T[12] = static_cast<double>(si * w + wi);  // createRasterGridToolPath :138-170
+          T[13] = static_cast<double>(pi);
+        }
+      }
+    }
+  }
+  return paths;
+}
+
+bool sameToolPaths(const noether::ToolPaths& a, const noether::ToolPaths& b, double tol)
+{
+  if (a.size() != b.size())
+    return false;
+  for (std::size_t i = 0; i < a.size(); ++i)
+  {
+    if (a[i].size() != b[i].size())
+      return false;
+    for (std::size_t j = 0; j < a[i].size(); ++j)
+    {
+      if (a[i][j].size() != b[i][j].size())
+        return false;
+      for (std::size_t k = 0; k < a[i][j].size(); ++k)
+        for (int e = 0; e < 16; ++e)
+          if (!(std::fabs(a[i][j][k].matrix().data()[e] - b[i][j][k].matrix().data()[e]) <= tol))
+            return false;
+    }
+  }
+  return true;
+}
+
+void testToolPathModifiers(const noether::Factory& factory)
+{
+  std::printf("[ToolPathModifier plugins on the device]\n");
+  YAML::Node offset = vectorNode(0.1, 0.2, 0.3);
+  YAML::Node iso = vectorNode(0.0, 0.0, 0.0);
+  iso["qw"] = 1.0, iso["qx"] = 0.0, iso["qy"] = 0.0, iso["qz"] = 0.0;
+  std::vector<std::pair<YAML::Node, bool>> configs;  // (config, one-time modifier)
+  auto entry = [&](const char* name, bool one_time) -> YAML::Node& {
+    YAML::Node n;
+    n["name"] = name;
+    configs.emplace_back(n, one_time);
+    return configs.back().first;
+  };
+  entry("SnakeOrganization", false);
+  {
+    YAML::Node& n = entry("LinearApproach", false);
+    n["offset"] = offset, n["n_points"] = 5;
+  }
+  {
+    YAML::Node& n = entry("LinearDeparture", false);
+    n["offset"] = offset, n["n_points"] = 5;
+  }
+  entry("Offset", false)["offset"] = iso;
+  entry("FixedOrientation", true)["ref_x_dir"] = vectorNode(1.0, 0.0, 0.0);
+  entry("UniformOrientation", true);
+  entry("Concatenate", true);
+  entry("DirectionOfTravelOrientation", true);
+  {
+    YAML::Node& n = entry("ToolDragOrientation", false);
+    n["angle_offset"] = 0.1745, n["tool_radius"] = 0.025;
+  }
+  {
+    YAML::Node& n = entry("BiasedToolDragOrientation", false);
+    n["angle_offset"] = 0.1745, n["tool_radius"] = 0.025;
+  }
+  {
+    YAML::Node& n = entry("CompoundToolPathModifier", false);
+    YAML::Node list;
+    list.push_back(configs[1].first);
+    list.push_back(configs[2].first);
+    n["modifiers"] = list;
+  }
+  const std::vector<noether::ToolPaths> inputs = { gridToolPaths(4, 2, 10, true), gridToolPaths(4, 2, 10, false) };
+  for (const auto& c : configs)
+  {
+    const std::string name = c.first["name"].as<std::string>();
+    auto modifier = factory.createToolPathModifier(c.first);
+    CHECK(modifier != nullptr);
+    for (const noether::ToolPaths& input : inputs)
+    {
+      const noether::ToolPaths once = modifier->modify(input);
+      if (c.second)  // OneTimeToolPathModifierTestFixture: applying it again changes nothing
+        CHECK(sameToolPaths(once, modifier->modify(once), 1e-12));
+      if (name == "Concatenate")
+        CHECK(once.size() == 1 && once[0].size() == 8);
+      else
+        CHECK(once.size() == 4 && once[0].size() == 2);
+      const std::size_t want = name == "CompoundToolPathModifier" ? 20 : (name.rfind("Linear", 0) == 0 ? 15 : 10);
+      CHECK(once[0][0].size() == want);
+    }
+    std::printf("  %s ok\n", name.c_str());
+  }
+  // closed forms on the raster grid: snake reverses the odd tool paths; approach points lead up to the first waypoint
+  {
+    const noether::ToolPaths snake = factory.createToolPathModifier(configs[0].first)->modify(inputs[1]);
+    CHECK(snake[0][0][0].translation().x() == 0.0 && snake[1][0][0].translation().x() == 19.0 &&
+          snake[1][1][9].translation().x() == 0.0 && snake[2][1][9].translation().x() == 19.0);
+    const noether::ToolPaths lead = factory.createToolPathModifier(configs[1].first)->modify(inputs[1]);
+    CHECK(std::fabs(lead[0][0][0].translation().z() - 0.3) < 1e-15 && std::fabs(lead[0][0][4].translation().z() - 0.06) < 1e-15 &&
+          lead[0][0][5].translation().z() == 0.0 && lead[0][1][5].translation().x() == 10.0);
+  }
+  // error behaviour: a std::exception where the reference throws / reads out of range
+  {
+    noether::ToolPaths single(1);
+    single[0].resize(1);
+    single[0][0] = gridToolPaths(1, 1, 1, true)[0][0];
+    bool threw = false;
+    try
+    {
+      factory.createToolPathModifier(configs[8].first)->modify(single);
+    }
+    catch (const std::exception& e)
+    {
+      threw = std::string(e.what()).find("Insufficient number of points") != std::string::npos;
+    }
+    CHECK(threw);
+  }
+}
+
 int main(int argc, char** argv)
 {
   if (argc < 3)
@@ -649,6 +786,7 @@ int main(int argc, char** argv)
     testNormalsFieldRetention(factory, ply);
     testGeneratorsAndErrors(factory, ply);
     testResidentMeshReuse(factory, ply);
+    testToolPathModifiers(factory);
     if (argc > 3 && std::string(argv[3]) == "--time")
     {
       timePipeline(factory, 800, 625, 0.005);    // cfg2: 1 M triangles

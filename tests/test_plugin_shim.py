@@ -22,13 +22,17 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
     syms = subprocess.run(["nm", "-D", "--defined-only", PLUGIN], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in syms.splitlines() if line.strip()}
     # aliases of noether_tpp/src/plugins.cpp:62,89,111,179,278
-    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces"):
+    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
+                  # tool path modifiers that run on the device (plugins.cpp:182-199,219)
+                  "SnakeOrganization", "LinearApproach", "LinearDeparture", "Offset", "FixedOrientation", "UniformOrientation",
+                  "Concatenate", "ToolDragOrientation", "BiasedToolDragOrientation", "DirectionOfTravelOrientation",
+                  "CompoundToolPathModifier"):
         assert alias in exported
     # each plugin object sits in the ELF section boost_plugin_loader enumerates for its kind
     # (NOETHER_*_SECTION, noether_tpp/CMakeLists.txt:126-131)
     sections = subprocess.run(["readelf", "-S", "-W", PLUGIN], capture_output=True, text=True, check=True).stdout
     names = {tok for line in sections.splitlines() for tok in line.replace("]", " ").split()}
-    for section in ("tpp", "dg", "og", "mesh"):
+    for section in ("tpp", "dg", "og", "mesh", "mod"):
         assert section in names
     # the shim reaches the product through the C ABI only
     undefined = subprocess.run(["nm", "-D", "--undefined-only", PLUGIN], capture_output=True, text=True, check=True).stdout
