@@ -104,6 +104,16 @@ int nb2_ply_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info
 int nb2_mesh_upload_ply(nb2_context* ctx, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info /* may be NULL */);
 /* The same from a path: the file is memory-mapped and copied to the GPU straight out of the page cache. */
 int nb2_mesh_upload_ply_file(nb2_context* ctx, const char* path, nb2_mesh_file_info* info /* may be NULL */);
+/* Binary STL (pcl::io::loadPolygonFile -> vtkSTLReader with Merging on -> pcl::io::vtk2mesh): 80-byte header, a 4-byte
+ * facet count that is not trusted, 50-byte facets read until the file ends.  The facet corners are welded on the device
+ * exactly as vtkMergePoints does it in the reader — coincident corners (float equality, -0 == +0) become one point,
+ * numbered by first occurrence in the file; facets with two equal ids are dropped — and the welded mesh (PointXYZ cloud,
+ * no normals: follow with nb2_normals_from_mesh_faces) is resident as after nb2_mesh_upload.  ASCII STL is refused.
+ * nb2_stl_inspect reports the sizes before welding (3 points per facet): upper bounds a caller can allocate for. */
+int nb2_stl_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info);
+int nb2_mesh_upload_stl(nb2_context* ctx, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info /* may be NULL */);
+/* pcl::io::loadPolygonFile(path, mesh): dispatch on the extension (.ply / .stl); the file is memory-mapped. */
+int nb2_mesh_upload_file(nb2_context* ctx, const char* path, nb2_mesh_file_info* info /* may be NULL */);
 /* Copy the resident triangle list back (uint32[3 * n_triangles]).  Test / debugging aid. */
 int nb2_mesh_download_triangles(nb2_context* ctx, uint32_t* triangles);
 

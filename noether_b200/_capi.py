@@ -41,6 +41,7 @@ DECLARED_SYMBOLS = [
     "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",
     "nb2_ply_inspect", "nb2_mesh_upload_ply", "nb2_mesh_upload_ply_file", "nb2_mesh_download_triangles",
     "nb2_result_from_poses", "nb2_result_from_pose_segments", "nb2_result_modify",
+    "nb2_stl_inspect", "nb2_mesh_upload_stl", "nb2_mesh_upload_file",
 ]
 
 NB2_MOD_SNAKE_ORGANIZATION = 1
@@ -133,6 +134,9 @@ def load():
     L.nb2_mesh_upload_ply.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_upload_ply_file.argtypes = [vp, C.c_char_p, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_download_triangles.argtypes = [vp, C.c_void_p]
+    L.nb2_stl_inspect.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
+    L.nb2_mesh_upload_stl.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
+    L.nb2_mesh_upload_file.argtypes = [vp, C.c_char_p, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_pca.argtypes = [vp, C.POINTER(Pca)]
     L.nb2_principal_axis_direction.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]
     L.nb2_centroid_origin.argtypes = [vp, C.POINTER(C.c_double)]

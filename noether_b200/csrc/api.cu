@@ -728,7 +728,8 @@ void nb2_context_destroy(nb2_context* c)
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
-                     &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm })
+                     &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->stlSlots, &c->stlCorner,
+                     &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)
@@ -948,6 +949,78 @@ static void uploadPlyImpl(nb2_context* c, const void* file_image, uint64_t n_byt
   }
 }
 
+/** Facets a binary STL image holds, as vtkSTLReader::ReadBinarySTL counts them: the 4-byte count of the header is not
+ *  trusted, facets are read while 48 more bytes are there (the trailing 2-byte attribute may be cut off).  Text files
+ *  ("solid ..." whose size does not match the binary layout) are refused. */
+static uint64_t stlFacetCount(const uint8_t* data, uint64_t n_bytes)
+{
+  if (n_bytes < 84)
+    fail(NB2_ERR_INVALID_ARGUMENT, "STL: the file is shorter than a binary STL header (84 bytes)");
+  uint32_t declared;
+  std::memcpy(&declared, data + 80, 4);
+  const bool exact = n_bytes == 84 + 50ull * declared;
+  if (!exact && std::memcmp(data, "solid", 5) == 0)
+    fail(NB2_ERR_INVALID_ARGUMENT, "STL: ASCII files are not decoded on the device (binary STL only)");
+  const uint64_t body = n_bytes - 84;
+  const uint64_t facets = body / 50 + (body % 50 >= 48 ? 1 : 0);
+  if (facets > 1400000000ull)
+    fail(NB2_ERR_INVALID_ARGUMENT, "STL: more than 1.4e9 facets");
+  return facets;
+}
+
+/** nb2_mesh_upload_stl: one copy of the file image, welded on the device (kernels_stl.cu) */
+static void uploadStlImpl(nb2_context* c, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  if (!c || !file_image)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or file image is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  const uint64_t facets = stlFacetCount(static_cast<const uint8_t*>(file_image), n_bytes);
+  if (facets == 0)
+    fail(NB2_ERR_TOO_FEW_POINTS, "mesh has no vertices");
+  c->V = 0;
+  c->pca_valid = false;
+  c->extents_done = false;
+  c->timer_upload.begin(c->stream);
+  const uint64_t used = std::min<uint64_t>(n_bytes, 84 + 50 * facets);
+  c->fileImg.ensure(((used + 15) & ~uint64_t(7)) + 8);
+  NB2_CUDA(cudaMemcpyAsync(c->fileImg.ptr, file_image, used, cudaMemcpyHostToDevice, c->stream));
+  c->timer_upload.mark("h2d", c->stream);
+  uint64_t V = 0, F = 0;
+  launchStlDecode(c, facets, &V, &F);
+  c->timer_upload.mark("weld", c->stream);
+  c->pos.ensure(sizeof(float4) * std::max<uint64_t>(V, 1));
+  c->V = V;
+  c->F = F;
+  c->has_normals = false;
+  c->nrm_base = nullptr;
+  c->nrm_stride = 16;
+  launchIngestMoments(c, 16, 0, -1);
+  c->timer_upload.mark("ingest+moments", c->stream);
+  std::memset(&c->pca, 0, sizeof(c->pca));
+  c->checks_deferred = false;
+  c->hostSmall.ensure(4096 + sizeof(FrameDev));
+  auto* h = c->hostSmall.as<uint8_t>();
+  const int grid = static_cast<int>(std::min<uint64_t>((c->V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  MomentPartial total;
+  std::memcpy(&total, h, sizeof(total));
+  if (total.non_finite)
+  {
+    c->V = 0;
+    fail(NB2_ERR_NON_FINITE, std::to_string(total.non_finite) + " vertices have non-finite coordinates");
+  }
+  c->tri_checked = true;  // the ids were assigned here: all < V
+  if (info)
+  {
+    info->n_points = c->V;
+    info->n_triangles = c->F;
+    info->has_normals = 0;
+    info->reserved_ = 0;
+  }
+}
+
 int nb2_ply_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
 {
   NB2_API_BEGIN
@@ -994,6 +1067,66 @@ int nb2_mesh_upload_ply_file(nb2_context* c, const char* path, nb2_mesh_file_inf
     ~Unmap() { ::munmap(p, n); }
   } unmap{ map, static_cast<size_t>(st.st_size) };
   uploadPlyImpl(c, map, static_cast<uint64_t>(st.st_size), info);
+  NB2_API_END
+}
+
+int nb2_stl_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!file_image || !info)
+    fail(NB2_ERR_INVALID_ARGUMENT, "file image or info is NULL");
+  const uint64_t facets = stlFacetCount(static_cast<const uint8_t*>(file_image), n_bytes);
+  info->n_points = 3 * facets;  // before welding: upper bounds
+  info->n_triangles = facets;
+  info->has_normals = 0;
+  info->reserved_ = 0;
+  NB2_API_END
+}
+
+int nb2_mesh_upload_stl(nb2_context* c, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  uploadStlImpl(c, file_image, n_bytes, info);
+  NB2_API_END
+}
+
+int nb2_mesh_upload_file(nb2_context* c, const char* path, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!path)
+    fail(NB2_ERR_INVALID_ARGUMENT, "path is NULL");
+  // pcl::io::loadPolygonFile dispatches on the extension (vtk_lib_io.cpp)
+  const std::string p(path);
+  const size_t dot = p.find_last_of('.');
+  std::string ext = dot == std::string::npos ? std::string() : p.substr(dot);
+  for (char& ch : ext)
+    ch = static_cast<char>(std::tolower(static_cast<unsigned char>(ch)));
+  const bool ply = ext == ".ply", stl = ext == ".stl";
+  if (!ply && !stl)
+    fail(NB2_ERR_INVALID_ARGUMENT, "unsupported mesh file extension '" + ext + "' (binary .ply and .stl are decoded on the device)");
+  const int fd = ::open(path, O_RDONLY);
+  if (fd < 0)
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot open '") + path + "'");
+  struct stat st{};
+  if (::fstat(fd, &st) != 0 || st.st_size <= 0)
+  {
+    ::close(fd);
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot stat '") + path + "' (or the file is empty)");
+  }
+  void* map = ::mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (map == MAP_FAILED)
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string("cannot map '") + path + "'");
+  struct Unmap
+  {
+    void* p;
+    size_t n;
+    ~Unmap() { ::munmap(p, n); }
+  } unmap{ map, static_cast<size_t>(st.st_size) };
+  if (ply)
+    uploadPlyImpl(c, map, static_cast<uint64_t>(st.st_size), info);
+  else
+    uploadStlImpl(c, map, static_cast<uint64_t>(st.st_size), info);
   NB2_API_END
 }
 

@@ -293,6 +293,19 @@ void launchValidateTriangles(nb2_context* c)
   ++c->launches;
 }
 
+/** exclusive prefix sum of n 32-bit counters (out may not alias in); out[n - 1] of an input with a trailing 0 = total */
+void launchScanU32(nb2_context* c, const unsigned* in, unsigned* out, unsigned long long n)
+{
+  const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+  c->scanState.ensure(sizeof(unsigned long long) * (tiles + 1));
+  NB2_CUDA(cudaMemsetAsync(c->scanState.ptr, 0, sizeof(unsigned long long) * (tiles + 1), c->stream));
+  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 13, 0, sizeof(unsigned), c->stream));
+  k_scan_u32<<<static_cast<unsigned>(tiles), kScanThreads, 0, c->stream>>>(in, out, n, c->scanState.as<unsigned long long>(),
+                                                                           c->counters.as<unsigned>() + 13);
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+}
+
 void launchVertexNormals(nb2_context* c)
 {
   const uint64_t V = c->V, F = c->F;

@@ -200,7 +200,11 @@ __global__ void __launch_bounds__(kTile) k_mod_restructure(const double* __restr
   tileStore(dst, base, n, tile);
 }
 
-/** one warp per tool path: mean of the normalised steps in the reference's order, then the tool-drag sign */
+/** one warp per tool path: mean of the normalised steps in the reference's order, then the tool-drag sign.
+ *  The waypoints of a tool path are contiguous, so the warp walks them 32 at a time; a lane's step i -> i + 1 counts
+ *  when both ends lie in one segment.  The translations of the next 32 waypoints are requested before the current 32
+ *  steps are added up (lane-ordered shuffles: the additions are the reference's, in the reference's order), so the
+ *  sequential sum hides the load latency. */
 __global__ void __launch_bounds__(128) k_mod_path_sign(const double* __restrict__ poses, const unsigned* __restrict__ seg_off,
                                                        const unsigned* __restrict__ path_off, unsigned n_paths,
                                                        int* __restrict__ path_sign)
@@ -209,34 +213,55 @@ __global__ void __launch_bounds__(128) k_mod_path_sign(const double* __restrict_
   const unsigned lane = threadIdx.x & 31;
   if (p >= n_paths)
     return;
+  const unsigned s_begin = path_off[p], s_end = path_off[p + 1];
+  const unsigned w_begin = seg_off[s_begin], w_end = seg_off[s_end];
   D3 acc = { 0.0, 0.0, 0.0 };
   unsigned count = 0;
-  for (unsigned s = path_off[p]; s < path_off[p + 1]; ++s)
-  {
-    const unsigned b = seg_off[s], e = seg_off[s + 1];
-    if (e - b < 2)
-      continue;
-    const unsigned steps = e - b - 1;
-    for (unsigned i0 = 0; i0 < steps; i0 += 32)
+  unsigned s = s_begin;  // segment of this lane's waypoint (advanced monotonically)
+  // raw translations of waypoint i and i + 1 for the chunk being prefetched
+  D3 a_next = { 0.0, 0.0, 0.0 }, b_next = { 0.0, 0.0, 0.0 };
+  bool valid_next = false;
+  auto request = [&](unsigned i0) {
+    const unsigned i = i0 + lane;
+    valid_next = false;
+    if (i + 1 < w_end)
     {
-      const unsigned i = i0 + lane;
-      D3 u = { 0.0, 0.0, 0.0 };
-      if (i < steps)
-        u = normalized(translationOf(poses, b + i + 1) - translationOf(poses, b + i));
-      const unsigned m = min(32u, steps - i0);
-      for (unsigned k = 0; k < m; ++k)
+      while (i >= seg_off[s + 1])
+        ++s;
+      valid_next = i + 1 < seg_off[s + 1];
+      if (valid_next)
       {
-        const D3 uk = { __shfl_sync(0xffffffffu, u.x, k), __shfl_sync(0xffffffffu, u.y, k), __shfl_sync(0xffffffffu, u.z, k) };
-        acc = acc + uk;
+        a_next = translationOf(poses, i);
+        b_next = translationOf(poses, i + 1);
       }
-      count += m;
+    }
+  };
+  if (w_begin < w_end)
+    request(w_begin);
+  for (unsigned i0 = w_begin; i0 < w_end; i0 += 32)
+  {
+    const D3 a = a_next, b = b_next;
+    const bool valid = valid_next;
+    if (i0 + 32 < w_end)
+      request(i0 + 32);
+    D3 u = { 0.0, 0.0, 0.0 };
+    if (valid)
+      u = normalized(b - a);
+    count += __popc(__ballot_sync(0xffffffffu, valid));
+    // lanes without a step hold +0, and acc + (+0) == acc bit for bit (acc starts at +0 and can never become -0), so
+    // the 32 additions run as one unrolled chain: 96 independent shuffles ahead of 32 dependent additions per component
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+    {
+      const D3 uk = { __shfl_sync(0xffffffffu, u.x, k), __shfl_sync(0xffffffffu, u.y, k), __shfl_sync(0xffffffffu, u.z, k) };
+      acc = acc + uk;
     }
   }
   if (lane == 0)
   {
     // the host has checked count >= 1 and that the first segment is not empty
     const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
-    const double* first = poses + 16ull * seg_off[path_off[p]];
+    const double* first = poses + 16ull * w_begin;
     double F[16];
     for (int i = 0; i < 16; ++i)
       F[i] = first[i];

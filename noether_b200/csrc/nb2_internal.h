@@ -241,6 +241,12 @@ struct nb2_context
   nb2::DevBuf modPathOff;  // uint32[P + 1]
   nb2::DevBuf modPathSign; // int32[P] tool-drag sign of every tool path
   nb2::DevBuf modPos, modNrm;  // float[3 W] compact input / float views of the output
+  // STL welding workspace (kernels_stl.cu)
+  nb2::DevBuf stlSlots;      // uint32[slots] first corner of the point hashed to each slot
+  nb2::DevBuf stlCorner;     // uint32[3 T] slot, later point id, of every facet corner
+  nb2::DevBuf stlFlag;       // uint32[3 T + 1] first-occurrence flags, later per-facet keep flags
+  nb2::DevBuf stlPrefix;     // uint32[3 T + 1]
+  nb2::DevBuf stlKeepPrefix; // uint32[T + 1]
   // normals workspace
   nb2::DevBuf faceNrm;   // float4[F]
   nb2::DevBuf valence;   // uint32[V + 1]
@@ -332,6 +338,10 @@ void launchValidateTriangles(nb2_context* c);
 // PLY records in c->fileImg -> c->blob (32-byte records {x y z 0 nx ny nz 0}, 16-byte ones without normals) and c->tri;
 // counters[16] counts faces that are not triangles, counters[12] receives the largest vertex index
 void launchPlyDecode(nb2_context* c, const PlyLayout& L);
+// binary STL image in c->fileImg -> welded mesh in c->blob (16-byte records {x y z 0}) and c->tri (kernels_stl.cu)
+void launchStlDecode(nb2_context* c, uint64_t n_facets, uint64_t* n_points_out, uint64_t* n_kept_out);
+// single-pass decoupled look-back exclusive scan (kernels_normals.cu)
+void launchScanU32(nb2_context* c, const unsigned* in, unsigned* out, unsigned long long n);
 
 // host-side frame arithmetic (frame.cpp)
 const char* latticeErrorMessage(int code);

@@ -82,6 +82,25 @@ class Context:
             _capi.check(self._lib.nb2_mesh_upload_ply_file(self._h, os.fspath(source).encode(), C.byref(info)))
         return info
 
+    def upload_stl(self, source) -> _capi.MeshFileInfo:
+        """pcl::io::loadPolygonFile + upload for a binary STL: `source` is a path or the bytes of the file; the facet
+        corners are welded on the device as vtkSTLReader's point merging does (nb2_mesh_upload_stl)."""
+        self._mesh_key = None
+        info = _capi.MeshFileInfo()
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            img = np.frombuffer(source, dtype=np.uint8) if not isinstance(source, np.ndarray) else np.ascontiguousarray(source).view(np.uint8)
+            _capi.check(self._lib.nb2_mesh_upload_stl(self._h, img.ctypes.data, img.size, C.byref(info)))
+        else:
+            _capi.check(self._lib.nb2_mesh_upload_file(self._h, os.fspath(source).encode(), C.byref(info)))
+        return info
+
+    def upload_file(self, path) -> _capi.MeshFileInfo:
+        """pcl::io::loadPolygonFile(path, mesh): .ply or .stl by extension (nb2_mesh_upload_file)"""
+        self._mesh_key = None
+        info = _capi.MeshFileInfo()
+        _capi.check(self._lib.nb2_mesh_upload_file(self._h, os.fspath(path).encode(), C.byref(info)))
+        return info
+
     def download_triangles(self, n_triangles: int) -> np.ndarray:
         tri = np.zeros((n_triangles, 3), np.uint32)
         _capi.check(self._lib.nb2_mesh_download_triangles(self._h, tri.ctypes.data))
@@ -183,6 +202,14 @@ class Context:
         out = C.c_void_p()
         _capi.check(self._lib.nb2_result_gather(self._h, local._r, root, C.byref(out)))
         return ToolPaths(self, out) if out.value else None
+
+
+def stl_inspect(data) -> _capi.MeshFileInfo:
+    """facets of a binary STL image and the point count before welding (host only, nb2_stl_inspect)"""
+    img = np.frombuffer(data, dtype=np.uint8)
+    info = _capi.MeshFileInfo()
+    _capi.check(_capi.load().nb2_stl_inspect(img.ctypes.data, img.size, C.byref(info)))
+    return info
 
 
 def ply_inspect(data) -> _capi.MeshFileInfo:

@@ -110,6 +110,7 @@ def lib():
     for n in ("orc_join_close_segments", "orc_minimum_segment_length", "orc_uniform_spacing"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_double]
     L.orc_read_ply.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.orc_read_stl.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     for n in ("orc_mesh_num_vertices", "orc_mesh_num_faces", "orc_mesh_num_indices"):
         getattr(L, n).argtypes = [C.c_void_p]
         getattr(L, n).restype = C.c_uint64
@@ -438,6 +439,22 @@ def fixture_plane_mesh(lx, ly, T=None):
                                  xyz.ctypes.data_as(C.POINTER(C.c_float)), nrm.ctypes.data_as(C.POINTER(C.c_float)),
                                  tri.ctypes.data_as(C.POINTER(C.c_uint32)))
     return xyz, nrm, tri
+
+
+def read_stl(data: bytes):
+    """pcl::io::loadPolygonFile for a binary STL image (vtkSTLReader with Merging + vtk2mesh restated): returns
+    (xyz float32 (V,3), triangles uint32 (F,3))."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    h = C.c_void_p()
+    _check(lib().orc_read_stl(buf.ctypes.data, buf.size, C.byref(h)))
+    try:
+        nv, ni = lib().orc_mesh_num_vertices(h), lib().orc_mesh_num_indices(h)
+        xyz = np.zeros((nv, 3), np.float32)
+        idx = np.zeros(ni, np.uint32)
+        lib().orc_mesh_export(h, xyz.ctypes.data_as(C.POINTER(C.c_float)), None, None, idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    finally:
+        lib().orc_mesh_free(h)
+    return xyz, idx.reshape(-1, 3)
 
 
 def read_ply(data: bytes):

@@ -157,6 +157,8 @@ int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double t
  *      vtkPLYReader + pcl::io::vtk2mesh restated, oracle_ply.cpp) ---- */
 typedef struct orc_mesh orc_mesh;
 int orc_read_ply(const uint8_t* data, uint64_t n_bytes, orc_mesh** out);
+/* binary STL: vtkSTLReader (Merging on) + vtk2mesh restated (oracle_ply.cpp) */
+int orc_read_stl(const uint8_t* data, uint64_t n_bytes, orc_mesh** out);
 uint64_t orc_mesh_num_vertices(const orc_mesh* m);
 uint64_t orc_mesh_num_faces(const orc_mesh* m);
 uint64_t orc_mesh_num_indices(const orc_mesh* m); /* sum of the face sizes */

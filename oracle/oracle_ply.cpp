@@ -17,6 +17,7 @@
 #include "oracle.h"
 #include "oracle_internal.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -268,6 +269,79 @@ int orc_read_ply(const uint8_t* data, uint64_t n_bytes, orc_mesh** out)
           mesh->nrm[3 * r + 2] = static_cast<float>(scalar[inz]);
         }
       }
+    }
+  }
+  *out = mesh;
+  return ORC_OK;
+}
+
+/* pcl::io::loadPolygonFile for a binary STL (PCL 1.12 vtk_lib_io.cpp loadPolygonFileSTL -> vtkSTLReader -> vtk2mesh; VTK 9.1
+ * IO/Geometry/vtkSTLReader.cxx), restated:
+ *   * ReadBinarySTL: 80-byte header, 4-byte little-endian facet count (read but not relied upon), then 50-byte facets
+ *     {float n[3], v1[3], v2[3], v3[3]; uint16 attribute} for as long as fread(&facet, 48, 1, fp) succeeds; the three
+ *     corners of every facet are appended to the point list, one triangle per facet;
+ *   * Merging (on by default): every corner in facet order goes through vtkMergePoints::InsertUniquePoint — float
+ *     comparison x == x', y == y', z == z' inside the corner's bucket, so -0 equals +0, the first inserted point stays,
+ *     ids count first occurrences; a facet is kept when its three ids differ;
+ *   * vtk2mesh: points in id order as float xyz (no normals: the reader drops the facet normals), polygons in order.
+ * Text STL ("solid" with a size that does not match the binary layout) is outside this restatement, as it is outside
+ * the product.  PARITY STATUS: unpinned (the reference ships no STL fixture). */
+int orc_read_stl(const uint8_t* data, uint64_t n_bytes, orc_mesh** out)
+{
+  if (!data || !out)
+    return plyError("orc_read_stl: NULL argument");
+  if (n_bytes < 84)
+    return plyError("orc_read_stl: shorter than a binary STL header");
+  uint32_t declared;
+  std::memcpy(&declared, data + 80, 4);
+  if (n_bytes != 84 + 50ull * declared && std::memcmp(data, "solid", 5) == 0)
+    return plyError("orc_read_stl: ASCII STL");
+  auto* mesh = new orc_mesh();
+  struct Bucketed
+  {
+    std::vector<uint32_t> ids;
+  };
+  // any bucketing that sends equal coordinates (with -0 == +0) to one bucket reproduces vtkMergePoints' result
+  std::vector<std::vector<uint32_t>> buckets(1u << 16);
+  auto canon = [](float f) {
+    uint32_t b;
+    std::memcpy(&b, &f, 4);
+    return b == 0x80000000u ? 0u : b;
+  };
+  for (uint64_t at = 84; at + 48 <= n_bytes; at += 50)
+  {
+    uint32_t node[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      float x[3];
+      std::memcpy(x, data + at + 12 + 12 * k, 12);
+      for (int d = 0; d < 3; ++d)
+        if (!std::isfinite(x[d]))
+        {
+          delete mesh;
+          return plyError("orc_read_stl: non-finite coordinate (undefined bucket index in vtkMergePoints)");
+        }
+      const uint32_t h = (canon(x[0]) * 0x9e3779b1u) ^ (canon(x[1]) * 0x85ebca77u) ^ (canon(x[2]) * 0xc2b2ae3du);
+      std::vector<uint32_t>& bucket = buckets[(h ^ (h >> 16)) & 0xffffu];
+      uint32_t found = UINT32_MAX;
+      for (uint32_t id : bucket)
+        if (mesh->xyz[3 * id] == x[0] && mesh->xyz[3 * id + 1] == x[1] && mesh->xyz[3 * id + 2] == x[2])
+        {
+          found = id;
+          break;
+        }
+      if (found == UINT32_MAX)
+      {
+        found = static_cast<uint32_t>(mesh->xyz.size() / 3);
+        mesh->xyz.insert(mesh->xyz.end(), x, x + 3);
+        bucket.push_back(found);
+      }
+      node[k] = found;
+    }
+    if (node[0] != node[1] && node[0] != node[2] && node[1] != node[2])
+    {
+      mesh->face_size.push_back(3);
+      mesh->index.insert(mesh->index.end(), node, node + 3);
     }
   }
   *out = mesh;

@@ -48,7 +48,7 @@ W = tp.n_waypoints
 kernels = {}
 w_now = W
 for k, ms in stages.items():
-    if k in ("h2d compact", "h2d poses", "d2h", "float views"):
+    if k in ("h2d", "ingest+moments", "validate", "h2d compact", "h2d poses", "d2h", "float views"):  # (the first three: last upload)
         continue
     if k == "expand poses":
         b = 24 * W + 128 * W
