@@ -12,8 +12,8 @@
 //                       (plane_slicer_raster_planner.cpp:380-394) [+ DirectionOfTravelOrientationModifier]
 //   k_mod_map           Offset / FixedOrientation / UniformOrientation / ToolDrag / BiasedToolDrag / DirectionOfTravel
 //   k_mod_restructure   SnakeOrganization / LinearApproach / LinearDeparture (segment table -> gather)
-//   k_mod_path_sign     estimateToolPathDirection (utils.cpp:7-29) per tool path, one warp each, the reference's
-//                       additions in the reference's order; then the tool-drag sign of the path
+//   k_mod_path_sign     estimateToolPathDirection (utils.cpp:7-29) per tool path, one CTA each: normalisations on all
+//                       warps, the reference's additions in the reference's order; then the tool-drag sign of the path
 //   k_mod_finish        float translation / z axis of the final poses (what nb2_result_view::positions / normals hold)
 #include "modifier_plan.h"
 #include "nb2_internal.h"
@@ -200,64 +200,52 @@ __global__ void __launch_bounds__(kTile) k_mod_restructure(const double* __restr
   tileStore(dst, base, n, tile);
 }
 
-/** one warp per tool path: mean of the normalised steps in the reference's order, then the tool-drag sign.
- *  The waypoints of a tool path are contiguous, so the warp walks them 32 at a time; a lane's step i -> i + 1 counts
- *  when both ends lie in one segment.  The translations of the next 32 waypoints are requested before the current 32
- *  steps are added up (lane-ordered shuffles: the additions are the reference's, in the reference's order), so the
- *  sequential sum hides the load latency. */
-__global__ void __launch_bounds__(128) k_mod_path_sign(const double* __restrict__ poses, const unsigned* __restrict__ seg_off,
-                                                       const unsigned* __restrict__ path_off, unsigned n_paths,
-                                                       int* __restrict__ path_sign)
+/** one CTA per tool path: mean of the normalised steps in the reference's order, then the tool-drag sign.
+ *  The waypoints of a tool path are contiguous, so the CTA walks them 256 at a time; a thread's step i -> i + 1 counts
+ *  when both ends lie in one segment.  The normalisations (an fp64 square root and three divisions each: long dependent
+ *  instruction sequences) run on all eight warps; the sum itself has to be the reference's sequential one, so warp 0
+ *  then adds the 256 staged steps in order.  Threads without a step stage +0, and acc + (+0) == acc bit for bit (acc
+ *  starts at +0 and can never become -0), so the additions run as one unrolled chain. */
+constexpr int kSignThreads = 256;
+__global__ void __launch_bounds__(kSignThreads) k_mod_path_sign(const double* __restrict__ poses,
+                                                                const unsigned* __restrict__ seg_off,
+                                                                const unsigned* __restrict__ path_off, unsigned n_paths,
+                                                                int* __restrict__ path_sign)
 {
-  const unsigned p = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const unsigned lane = threadIdx.x & 31;
-  if (p >= n_paths)
-    return;
+  __shared__ double su[3][kSignThreads];
+  const unsigned p = blockIdx.x;
+  const unsigned tid = threadIdx.x;
   const unsigned s_begin = path_off[p], s_end = path_off[p + 1];
   const unsigned w_begin = seg_off[s_begin], w_end = seg_off[s_end];
   D3 acc = { 0.0, 0.0, 0.0 };
   unsigned count = 0;
-  unsigned s = s_begin;  // segment of this lane's waypoint (advanced monotonically)
-  // raw translations of waypoint i and i + 1 for the chunk being prefetched
-  D3 a_next = { 0.0, 0.0, 0.0 }, b_next = { 0.0, 0.0, 0.0 };
-  bool valid_next = false;
-  auto request = [&](unsigned i0) {
-    const unsigned i = i0 + lane;
-    valid_next = false;
+  unsigned s = s_begin;  // segment of this thread's waypoint (advanced monotonically)
+  for (unsigned i0 = w_begin; i0 < w_end; i0 += kSignThreads)
+  {
+    const unsigned i = i0 + tid;
+    bool valid = false;
+    D3 u = { 0.0, 0.0, 0.0 };
     if (i + 1 < w_end)
     {
       while (i >= seg_off[s + 1])
         ++s;
-      valid_next = i + 1 < seg_off[s + 1];
-      if (valid_next)
-      {
-        a_next = translationOf(poses, i);
-        b_next = translationOf(poses, i + 1);
-      }
+      valid = i + 1 < seg_off[s + 1];
+      if (valid)
+        u = normalized(translationOf(poses, i + 1) - translationOf(poses, i));
     }
-  };
-  if (w_begin < w_end)
-    request(w_begin);
-  for (unsigned i0 = w_begin; i0 < w_end; i0 += 32)
-  {
-    const D3 a = a_next, b = b_next;
-    const bool valid = valid_next;
-    if (i0 + 32 < w_end)
-      request(i0 + 32);
-    D3 u = { 0.0, 0.0, 0.0 };
-    if (valid)
-      u = normalized(b - a);
-    count += __popc(__ballot_sync(0xffffffffu, valid));
-    // lanes without a step hold +0, and acc + (+0) == acc bit for bit (acc starts at +0 and can never become -0), so
-    // the 32 additions run as one unrolled chain: 96 independent shuffles ahead of 32 dependent additions per component
-#pragma unroll
-    for (int k = 0; k < 32; ++k)
+    su[0][tid] = u.x;
+    su[1][tid] = u.y;
+    su[2][tid] = u.z;
+    count += __syncthreads_count(valid);
+    if (tid < 32)
     {
-      const D3 uk = { __shfl_sync(0xffffffffu, u.x, k), __shfl_sync(0xffffffffu, u.y, k), __shfl_sync(0xffffffffu, u.z, k) };
-      acc = acc + uk;
+#pragma unroll 16
+      for (int k = 0; k < kSignThreads; ++k)
+        acc = acc + D3{ su[0][k], su[1][k], su[2][k] };
     }
+    __syncthreads();
   }
-  if (lane == 0)
+  if (tid == 0)
   {
     // the host has checked count >= 1 and that the first segment is not empty
     const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
@@ -520,7 +508,7 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
           uploadVector(c, c->modSegPath, segmentPaths(cur));
           uploadVector(c, c->modPathOff, cur.path_off);
           c->modPathSign.ensure(sizeof(int) * std::max(P, 1u));
-          k_mod_path_sign<<<(P + 3) / 4, 128, 0, c->stream>>>(buf[at], c->modSegOff.as<unsigned>(),
+          k_mod_path_sign<<<P, kSignThreads, 0, c->stream>>>(buf[at], c->modSegOff.as<unsigned>(),
                                                                c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>());
           NB2_CUDA(cudaGetLastError());
           ++c->launches;

@@ -6,7 +6,9 @@ test_gpu_parity.py::test_fuzz_plans_match_oracle:
 Each item is kind:first_seed:count; kinds: small / big (the sheet generator of test_gpu_parity.py) topo (closed tubes and
 tori, unwelded sheets, degenerate / duplicated triangles, fins) and legacy (PlaneSlicerLegacy with random point spacing,
 minimum segment size and hole size on the sheet generator's meshes; poses bit for bit) and normals (NormalsFromMeshFaces on
-the topology generator's meshes).  Skipped unless NB2_FUZZ is set (the default suites stay short)."""
+the topology generator's meshes), mods (random chains of the device tool-path modifiers on random ragged tool paths, poses
+bit for bit) and stl (random triangle soups with coincident, signed-zero and collapsing corners through the STL welder).
+Skipped unless NB2_FUZZ is set (the default suites stay short)."""
 import os
 
 import numpy as np
@@ -103,6 +105,8 @@ def test_fuzz_campaign(ctx, orc):
     failures = []
     errors = {}
     for kind, first, count in _campaign():
+        if kind in ("mods", "stl"):
+            continue  # test_fuzz_modifiers_and_stl below
         big = kind
         for seed in range(first, first + count):
             blob, xyz, nrm, tri, kw = (_fuzz_case_topology(seed, orc) if kind in ("topo", "normals")
@@ -189,5 +193,65 @@ def test_fuzz_campaign(ctx, orc):
                 gpu.free()
     print(f"fuzz campaign: {ran} cases, {refused} refused {errors}, {len(failures)} failures")
     assert not failures, "\n".join(failures[:20])
-    if all(kind in ("small", "big") for kind, _, _ in _campaign()):
+    if ran and all(kind in ("small", "big") for kind, _, _ in _campaign()):
         assert refused <= max(3, ran // 20)  # (topo: fins are refused; legacy: two-point segments, as the oracle does)
+
+
+@pytest.mark.skipif(not os.environ.get("NB2_FUZZ"), reason="set NB2_FUZZ=kind:first_seed:count[,...] to run the campaign")
+def test_fuzz_modifiers_and_stl(ctx, orc):
+    import test_modifiers as tm
+    import test_stl as ts
+    from noether_b200 import _capi, meshes
+    ran = refused = 0
+    failures = []
+    names = sorted(tm.MODIFIERS)
+    for kind, first, count in _campaign():
+        for seed in range(first, first + count):
+            if kind == "mods":
+                rng = np.random.default_rng(52000 + seed)
+                nested = tm.ragged_tool_paths(rng, n_paths=int(rng.integers(1, 12)))
+                if rng.random() < 0.2:   # a one-waypoint segment somewhere: several modifiers must refuse it
+                    nested[int(rng.integers(len(nested)))].append(nested[0][0][:1].copy())
+                chain = [names[int(i)] for i in rng.integers(0, len(names), size=int(rng.integers(1, 7)))]
+                ran += 1
+                try:
+                    ref = tm.oracle_apply(nested, chain)
+                    ref_ok = True
+                except Exception:
+                    ref_ok = False
+                try:
+                    po, so, poses, _ = tm.gpu_apply(ctx, nested, chain)
+                    gpu_ok = True
+                except _capi.Nb2Error:
+                    gpu_ok = False
+                if gpu_ok != ref_ok:
+                    failures.append(f"mods seed {seed} {chain}: gpu {'ok' if gpu_ok else 'refuses'}, oracle {'ok' if ref_ok else 'refuses'}")
+                elif not gpu_ok:
+                    refused += 1
+                else:
+                    try:
+                        tm.assert_matches_oracle((po, so, poses), ref, f"mods seed {seed} {chain}")
+                    except AssertionError as e:
+                        failures.append(str(e)[:300])
+            elif kind == "stl":
+                rng = np.random.default_rng(91000 + seed)
+                nx, ny = int(rng.integers(2, 40)), int(rng.integers(2, 40))
+                xyz, tri = meshes.wavy(nx, ny, amp=float(rng.uniform(0, 0.1)))
+                xyz = xyz.copy()
+                if rng.random() < 0.5:   # snap to a coarse lattice: many coincident vertices, collapsing facets, zeros
+                    q = np.float32(rng.choice([0.05, 0.125, 0.25]))
+                    xyz = (np.round(xyz / q) * q).astype(np.float32)
+                if rng.random() < 0.5:   # signed zeros
+                    xyz[rng.random(xyz.shape) < 0.2] *= np.float32(-0.0) if rng.random() < 0.5 else np.float32(1.0)
+                    z = xyz == 0
+                    xyz[z & (rng.random(xyz.shape) < 0.5)] = np.float32(-0.0)
+                if rng.random() < 0.5:
+                    xyz, tri = meshes.permute(xyz, tri, seed=int(rng.integers(1 << 30)))
+                raw = ts.write_stl(xyz, tri, count=int(rng.integers(0, 2 * len(tri) + 2)), tail=b"\x07" * int(rng.integers(0, 48)))
+                ran += 1
+                try:
+                    ts._check_against_oracle(ctx, orc, raw)
+                except AssertionError as e:
+                    failures.append(f"stl seed {seed}: {str(e)[:300]}")
+    print(f"fuzz campaign (modifiers / stl): {ran} cases, {refused} refused by both, {len(failures)} failures")
+    assert not failures, "\n".join(failures[:20])
