@@ -11,7 +11,8 @@ from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionG
                       default_context, make_lattice,
                       ToolPathModifier, SnakeOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
                       OffsetModifier, FixedOrientationModifier, UniformOrientationModifier, ConcatenateModifier,
-                      DirectionOfTravelOrientationModifier, ToolDragOrientationToolPathModifier,
+                      DirectionOfTravelOrientationModifier, MovingAverageOrientationSmoothingModifier,
+                      ToolDragOrientationToolPathModifier,
                       BiasedToolDragOrientationToolPathModifier, CompoundModifier)
 
 __version__ = "0.1.0"

@@ -192,6 +192,10 @@ std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, i
           if (segLen(cur, static_cast<uint32_t>(s)) < 2)
             fail(NB2_ERR_TOO_FEW_POINTS, "segment with a single waypoint (segment[i - 1] out of bounds in the reference)");
         break;
+      case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING:
+        if (m.n_points < 0)
+          fail(NB2_ERR_INVALID_ARGUMENT, "window_size must not be negative");
+        break;
       default:
         fail(NB2_ERR_INVALID_ARGUMENT, "unknown modifier kind " + std::to_string(m.kind));
     }

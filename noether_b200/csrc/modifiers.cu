@@ -14,8 +14,11 @@
 //   k_mod_restructure   SnakeOrganization / LinearApproach / LinearDeparture (segment table -> gather)
 //   k_mod_path_sign     estimateToolPathDirection (utils.cpp:7-29) per tool path, one CTA each: normalisations on all
 //                       warps, the reference's additions in the reference's order; then the tool-drag sign of the path
+//   k_mod_quaternions / k_mod_smooth   MovingAverageOrientationSmoothing: quaternions of all poses in parallel, then
+//                       the reference's in-place recurrence along each segment, one thread per segment (modifier_smooth.h)
 //   k_mod_finish        float translation / z axis of the final poses (what nb2_result_view::positions / normals hold)
 #include "modifier_plan.h"
+#include "modifier_smooth.h"
 #include "nb2_internal.h"
 
 #include <algorithm>
@@ -257,6 +260,77 @@ __global__ void __launch_bounds__(kSignThreads) k_mod_path_sign(const double* __
   }
 }
 
+/** MovingAverageOrientationSmoothing, pass 1: Quaterniond(pose.linear()) of every input pose (fully parallel) */
+__global__ void __launch_bounds__(256) k_mod_quaternions(const double* __restrict__ poses, unsigned W, double4* __restrict__ quat)
+{
+  const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W)
+    return;
+  double T[16];
+  const double2* g = reinterpret_cast<const double2*>(poses + 16ull * w);
+#pragma unroll
+  for (int i = 0; i < 6; ++i)  // the linear part lives in the first three columns
+  {
+    const double2 v = __ldg(g + i);
+    T[2 * i] = v.x;
+    T[2 * i + 1] = v.y;
+  }
+  double q[4];
+  rotationToQuaternion(T, q);
+  quat[w] = make_double4(q[0], q[1], q[2], q[3]);
+}
+
+/** pass 2: one thread per segment walks it in order.  quat[k] holds the quaternion of the input pose k until pose k has
+ *  been smoothed, then the quaternion of the smoothed pose (re-extracted from its rotation matrix, as the reference does
+ *  when a later window reads the modified pose).  dst receives the poses (translation copied, linear part replaced). */
+__global__ void __launch_bounds__(64) k_mod_smooth(const double* __restrict__ src, double* __restrict__ dst,
+                                                   const unsigned* __restrict__ seg_off, unsigned n_segments, int window,
+                                                   double4* __restrict__ quat, unsigned* __restrict__ nan_flag)
+{
+  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segments)
+    return;
+  const unsigned b = seg_off[s], e = seg_off[s + 1];
+  const int n = static_cast<int>(e - b);
+  const int n_each_side = window / 2;
+  for (int i = 0; i < n; ++i)
+  {
+    double q[4];
+    {
+      const double4 own = quat[b + i];
+      q[0] = own.x, q[1] = own.y, q[2] = own.z, q[3] = own.w;
+    }
+    if (i > 0 && i < n - 1)
+    {
+      const int start = max(i - n_each_side, 0), stop = min(i + n_each_side, n - 1);
+      const bool ok = quaternionMean(stop - start + 1,
+                                     [&](int k, double* out) {
+                                       const double4 v = quat[b + start + k];
+                                       out[0] = v.x, out[1] = v.y, out[2] = v.z, out[3] = v.w;
+                                     },
+                                     q);
+      if (!ok)
+      {
+        *nan_flag = 1u;
+        return;
+      }
+    }
+    double T[16];
+    const double* in = src + 16ull * (b + i);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      T[k] = in[k];
+    quaternionToRotation(q, T);
+    double* out = dst + 16ull * (b + i);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      out[k] = T[k];
+    double q2[4];
+    rotationToQuaternion(T, q2);
+    quat[b + i] = make_double4(q2[0], q2[1], q2[2], q2[3]);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_mod_finish(const double* __restrict__ poses, unsigned W, float* __restrict__ pos,
                                                     float* __restrict__ nrm)
 {
@@ -351,6 +425,7 @@ const char* stageName(int kind)
     case NB2_MOD_TOOL_DRAG_ORIENTATION: return "tool drag orientation";
     case NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION: return "biased tool drag orientation";
     case NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION: return "direction of travel orientation";
+    case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING: return "moving average orientation smoothing";
   }
   return "modifier";
 }
@@ -482,6 +557,7 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
     }
   }
 
+  bool smoothing = false;
   for (const Step& st : prog)
   {
     if (st.device)
@@ -499,6 +575,20 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
                                                                    st.v[2], st.n_points);
         NB2_CUDA(cudaGetLastError());
         ++c->launches;
+      }
+      else if (st.kind == NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING)
+      {
+        c->modQuat.ensure(sizeof(double4) * std::max(W_in, 1u));
+        unsigned* flag = c->counters.as<unsigned>() + 17;
+        NB2_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
+        k_mod_quaternions<<<(W_in + 255) / 256, 256, 0, c->stream>>>(buf[at], W_in, c->modQuat.as<double4>());
+        NB2_CUDA(cudaGetLastError());
+        ++c->launches;
+        k_mod_smooth<<<(S_in + 63) / 64, 64, 0, c->stream>>>(buf[at], buf[at ^ 1], c->modSegOff.as<unsigned>(), S_in,
+                                                              st.n_points, c->modQuat.as<double4>(), flag);
+        NB2_CUDA(cudaGetLastError());
+        ++c->launches;
+        smoothing = true;
       }
       else
       {
@@ -543,7 +633,14 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
       NB2_CUDA(cudaMemcpyAsync(r->normals, c->modNrm.ptr, sizeof(float) * 3 * W, cudaMemcpyDeviceToHost, c->stream));
       c->timer.mark("d2h", c->stream);
     }
+    c->hostSmall.ensure(4096);
+    unsigned* h_flag = c->hostSmall.as<unsigned>();
+    h_flag[0] = 0;
+    if (smoothing)
+      NB2_CUDA(cudaMemcpyAsync(h_flag, c->counters.as<unsigned>() + 17, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_flag[0])
+      fail(NB2_ERR_NON_FINITE, "Orientation contains NaN values");
   }
   catch (...)
   {

@@ -591,6 +591,17 @@ class DirectionOfTravelOrientationModifier(ToolPathModifier):
         return [_record(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)]
 
 
+class MovingAverageOrientationSmoothingModifier(ToolPathModifier):
+    """moving_average_orientation_smoothing_modifier.cpp:6-84 (in-place recurrence along each segment)"""
+
+    def __init__(self, window_size: int, context: Context | None = None):
+        super().__init__(context)
+        self.window_size = int(window_size)
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING, (), self.window_size)]
+
+
 class ToolDragOrientationToolPathModifier(ToolPathModifier):
     """tool_drag_orientation_modifier.cpp:6-35"""
     _kind = _capi.NB2_MOD_TOOL_DRAG_ORIENTATION
@@ -711,6 +722,8 @@ class Factory:
             return ConcatenateModifier(c)
         if name == "DirectionOfTravelOrientation":
             return DirectionOfTravelOrientationModifier(c)
+        if name == "MovingAverageOrientationSmoothing":  # window_size is read as a double and cast (:103)
+            return MovingAverageOrientationSmoothingModifier(int(float(_member(config, "window_size"))), c)
         if name in ("ToolDragOrientation", "BiasedToolDragOrientation"):
             cls = ToolDragOrientationToolPathModifier if name == "ToolDragOrientation" else BiasedToolDragOrientationToolPathModifier
             return cls(float(_member(config, "angle_offset")), float(_member(config, "tool_radius")), c)

@@ -104,6 +104,7 @@ def lib():
     for n in ("orc_linear_approach", "orc_linear_departure"):
         getattr(L, n).argtypes = [C.c_void_p, f64p, C.c_int]
     L.orc_offset.argtypes = [C.c_void_p, f64p]
+    L.orc_moving_average_orientation_smoothing.argtypes = [C.c_void_p, C.c_int]
     L.orc_fixed_orientation.argtypes = [C.c_void_p, f64p]
     for n in ("orc_tool_drag_orientation", "orc_biased_tool_drag_orientation"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_double, C.c_double]
@@ -365,6 +366,10 @@ class Paths:
 
     def tool_drag_orientation(self, angle_offset, tool_radius):
         _check(lib().orc_tool_drag_orientation(self._h, angle_offset, tool_radius))
+        return self
+
+    def moving_average_orientation_smoothing(self, window_size):
+        _check(lib().orc_moving_average_orientation_smoothing(self._h, int(window_size)))
         return self
 
     def biased_tool_drag_orientation(self, angle_offset, tool_radius):

@@ -73,6 +73,7 @@ int fixedOrientation(orc_paths& p, const double ref_x[3]);
 int uniformOrientation(orc_paths& p);
 int concatenate(orc_paths& p);
 int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased);
+int movingAverageOrientationSmoothing(orc_paths& p, int window_size);
 
 inline V3d translation(const Waypoint& w) { return { w.T[12], w.T[13], w.T[14] }; }
 }  // namespace orc

@@ -342,6 +342,267 @@ int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased)
   return ORC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MovingAverageOrientationSmoothingModifier (moving_average_orientation_smoothing_modifier.cpp:6-84).  Third-party
+// pieces restated from Eigen 3.4: Quaternion(Matrix3) (Geometry/Quaternion.h quaternionbase_assign_impl<Other,3,3>),
+// QuaternionBase::toRotationMatrix, JacobiSVD<Matrix4d>::compute with ComputeFullU (SVD/JacobiSVD.h: no
+// preconditioner for a square matrix, scaling by the largest |entry|, sweeps over p > q with the 2 * epsilon * maxDiag
+// threshold, real_2x2_jacobi_svd, sign fix, descending sort) and JacobiRotation (Jacobi/Jacobi.h).
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct Quat
+{
+  double x, y, z, w;
+  double& coeff(int i) { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+  double coeff(int i) const { return i == 0 ? x : (i == 1 ? y : (i == 2 ? z : w)); }
+};
+
+Quat quaternionFromLinear(const Waypoint& p)
+{
+  Quat q{};
+  double t = eigenSum3(at(p, 0, 0), at(p, 1, 1), at(p, 2, 2));  // mat.trace()
+  if (t > 0.0)
+  {
+    t = std::sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (at(p, 2, 1) - at(p, 1, 2)) * t;
+    q.y = (at(p, 0, 2) - at(p, 2, 0)) * t;
+    q.z = (at(p, 1, 0) - at(p, 0, 1)) * t;
+    return q;
+  }
+  int i = 0;
+  if (at(p, 1, 1) > at(p, 0, 0))
+    i = 1;
+  if (at(p, 2, 2) > at(p, i, i))
+    i = 2;
+  const int j = (i + 1) % 3;
+  const int k = (j + 1) % 3;
+  t = std::sqrt(at(p, i, i) - at(p, j, j) - at(p, k, k) + 1.0);
+  q.coeff(i) = 0.5 * t;
+  t = 0.5 / t;
+  q.w = (at(p, k, j) - at(p, j, k)) * t;
+  q.coeff(j) = (at(p, j, i) + at(p, i, j)) * t;
+  q.coeff(k) = (at(p, k, i) + at(p, i, k)) * t;
+  return q;
+}
+
+void setLinearFromQuaternion(Waypoint& p, const Quat& q)
+{
+  const double tx = 2.0 * q.x, ty = 2.0 * q.y, tz = 2.0 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  at(p, 0, 0) = 1.0 - (tyy + tzz);
+  at(p, 0, 1) = txy - twz;
+  at(p, 0, 2) = txz + twy;
+  at(p, 1, 0) = txy + twz;
+  at(p, 1, 1) = 1.0 - (txx + tzz);
+  at(p, 1, 2) = tyz - twx;
+  at(p, 2, 0) = txz - twy;
+  at(p, 2, 1) = tyz + twx;
+  at(p, 2, 2) = 1.0 - (txx + tyy);
+}
+
+/** Eigen::JacobiRotation<double> */
+struct Rotation
+{
+  double c = 1.0, s = 0.0;
+  Rotation transpose() const { return { c, -s }; }
+  Rotation operator*(const Rotation& o) const { return { c * o.c - s * o.s, c * o.s + s * o.c }; }
+  /** makeJacobi(x, y, z) for [x y; y z] */
+  void makeJacobi(double x, double y, double z)
+  {
+    const double deno = 2.0 * std::abs(y);
+    if (deno < std::numeric_limits<double>::min())
+    {
+      c = 1.0;
+      s = 0.0;
+      return;
+    }
+    const double tau = (x - z) / deno;
+    const double w = std::sqrt(tau * tau + 1.0);
+    const double t = tau > 0.0 ? 1.0 / (tau + w) : 1.0 / (tau - w);
+    const double sign_t = t > 0.0 ? 1.0 : -1.0;
+    const double n = 1.0 / std::sqrt(t * t + 1.0);
+    s = -sign_t * (y / std::abs(y)) * std::abs(t) * n;
+    c = n;
+  }
+};
+
+/** Square matrix of doubles with Eigen's in-plane rotations */
+template <int N>
+struct Square
+{
+  double v[N][N];
+  double& operator()(int r, int c) { return v[r][c]; }
+  double operator()(int r, int c) const { return v[r][c]; }
+  /** applyOnTheLeft(p, q, j): rows p and q */
+  void rotateRows(int p, int q, const Rotation& j)
+  {
+    if (j.c == 1.0 && j.s == 0.0)
+      return;
+    for (int i = 0; i < N; ++i)
+    {
+      const double xi = v[p][i], yi = v[q][i];
+      v[p][i] = j.c * xi + j.s * yi;
+      v[q][i] = -j.s * xi + j.c * yi;
+    }
+  }
+  /** applyOnTheRight(p, q, j): columns p and q, rotated by j.transpose() */
+  void rotateColumns(int p, int q, const Rotation& j)
+  {
+    const Rotation jt = j.transpose();
+    if (jt.c == 1.0 && jt.s == 0.0)
+      return;
+    for (int i = 0; i < N; ++i)
+    {
+      const double xi = v[i][p], yi = v[i][q];
+      v[i][p] = jt.c * xi + jt.s * yi;
+      v[i][q] = -jt.s * xi + jt.c * yi;
+    }
+  }
+};
+
+/** JacobiSVD<Matrix4d>(M, ComputeFullU).matrixU().col(0); false when M is not finite (Eigen: InvalidInput) */
+bool firstLeftSingularVector(Square<4> W, double u0[4])
+{
+  Square<4> U{};
+  for (int i = 0; i < 4; ++i)
+    U(i, i) = 1.0;
+  double scale = 0.0;
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+    {
+      if (!std::isfinite(W(r, c)))
+        return false;
+      scale = std::max(scale, std::abs(W(r, c)));
+    }
+  if (scale == 0.0)
+    scale = 1.0;
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c)
+      W(r, c) = W(r, c) / scale;
+  const double precision = 2.0 * std::numeric_limits<double>::epsilon();
+  const double consider_as_zero = std::numeric_limits<double>::min();
+  double max_diag = 0.0;
+  for (int i = 0; i < 4; ++i)
+    max_diag = std::max(max_diag, std::abs(W(i, i)));
+  for (bool finished = false; !finished;)
+  {
+    finished = true;
+    for (int p = 1; p < 4; ++p)
+      for (int q = 0; q < p; ++q)
+      {
+        const double threshold = std::max(consider_as_zero, precision * max_diag);
+        if (!(std::abs(W(p, q)) > threshold || std::abs(W(q, p)) > threshold))
+          continue;
+        finished = false;
+        // real_2x2_jacobi_svd
+        Square<2> m{};
+        m(0, 0) = W(p, p), m(0, 1) = W(p, q), m(1, 0) = W(q, p), m(1, 1) = W(q, q);
+        Rotation rot1;
+        const double t = m(0, 0) + m(1, 1);
+        const double d = m(1, 0) - m(0, 1);
+        if (std::abs(d) < std::numeric_limits<double>::min())
+        {
+          rot1.s = 0.0;
+          rot1.c = 1.0;
+        }
+        else
+        {
+          const double u = t / d;
+          const double tmp = std::sqrt(1.0 + u * u);
+          rot1.s = 1.0 / tmp;
+          rot1.c = u / tmp;
+        }
+        m.rotateRows(0, 1, rot1);
+        Rotation j_right;
+        j_right.makeJacobi(m(0, 0), m(0, 1), m(1, 1));
+        const Rotation j_left = rot1 * j_right.transpose();
+        W.rotateRows(p, q, j_left);
+        U.rotateColumns(p, q, j_left.transpose());
+        W.rotateColumns(p, q, j_right);
+        max_diag = std::max(max_diag, std::max(std::abs(W(p, p)), std::abs(W(q, q))));
+      }
+  }
+  double sv[4];
+  for (int i = 0; i < 4; ++i)
+  {
+    const double a = W(i, i);
+    sv[i] = std::abs(a);
+    if (a < 0.0)
+      for (int r = 0; r < 4; ++r)
+        U(r, i) = -U(r, i);
+  }
+  for (double& x : sv)
+    x *= scale;
+  for (int i = 0; i < 4; ++i)
+  {
+    int pos = 0;
+    double best = sv[i];
+    for (int k = 1; k < 4 - i; ++k)
+      if (sv[i + k] > best)
+      {
+        best = sv[i + k];
+        pos = k;
+      }
+    if (best == 0.0)
+      break;
+    if (pos)
+    {
+      pos += i;
+      std::swap(sv[i], sv[pos]);
+      for (int r = 0; r < 4; ++r)
+        std::swap(U(r, i), U(r, pos));
+    }
+  }
+  for (int r = 0; r < 4; ++r)
+    u0[r] = U(r, 0);
+  return true;
+}
+}  // namespace
+
+/** MovingAverageOrientationSmoothingModifier::modify (:70-84): every pose is replaced in place, so the window of a
+ *  pose holds the already smoothed poses before it */
+int movingAverageOrientationSmoothing(orc_paths& p, int window_size)
+{
+  for (Path& tp : p.paths)
+    for (Segment& tps : tp.segments)
+    {
+      const int n = static_cast<int>(tps.size());
+      for (int i = 0; i < n; ++i)
+      {
+        Quat out = quaternionFromLinear(tps[i]);
+        if (i > 0 && i < n - 1)
+        {
+          const int n_each_side = window_size / 2;
+          const int start_idx = std::max(i - n_each_side, 0);
+          const int stop_idx = std::min(i + n_each_side, n - 1);
+          Square<4> M{};
+          for (int k = start_idx; k < stop_idx + 1; ++k)
+          {
+            const Quat q = quaternionFromLinear(tps[k]);
+            for (int r = 0; r < 4; ++r)
+              for (int c = 0; c < 4; ++c)
+                M(r, c) += q.coeff(r) * q.coeff(c);
+          }
+          double u0[4];
+          const bool ok = firstLeftSingularVector(M, u0);
+          if (!ok || std::isnan(u0[0]) || std::isnan(u0[1]) || std::isnan(u0[2]) || std::isnan(u0[3]))
+          {
+            setError("Orientation contains NaN values");
+            return ORC_ERR_INVALID;
+          }
+          out = { u0[0], u0[1], u0[2], u0[3] };
+        }
+        setLinearFromQuaternion(tps[i], out);
+      }
+    }
+  return ORC_OK;
+}
+
 int joinCloseSegments(orc_paths& p, double distance)
 {
   for (Path& tool_path : p.paths)
@@ -682,6 +943,7 @@ int orc_uniform_orientation(orc_paths* p) { return uniformOrientation(*p); }
 int orc_concatenate(orc_paths* p) { return concatenate(*p); }
 int orc_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, false); }
 int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, true); }
+int orc_moving_average_orientation_smoothing(orc_paths* p, int window_size) { return movingAverageOrientationSmoothing(*p, window_size); }
 int orc_join_close_segments(orc_paths* p, double d) { return joinCloseSegments(*p, d); }
 int orc_minimum_segment_length(orc_paths* p, double l) { return minimumSegmentLength(*p, l); }
 int orc_uniform_spacing(orc_paths* p, double s) { return uniformSpacing(*p, s); }

@@ -772,6 +772,9 @@ struct Plugin_DeviceToolPathModifier : public noether::Plugin<noether::ToolPathM
         m.v[0] = YAML::getMember<double>(config, "angle_offset");
         m.v[1] = YAML::getMember<double>(config, "tool_radius");
         break;
+      case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING:  // moving_average_orientation_smoothing_modifier.cpp:99-105
+        m.n_points = static_cast<int>(static_cast<std::size_t>(YAML::getMember<double>(config, "window_size")));
+        break;
       default:  // SnakeOrganization, UniformOrientation, Concatenate, DirectionOfTravelOrientation: no keys
         break;
     }
@@ -788,6 +791,7 @@ using Plugin_Concatenate = Plugin_DeviceToolPathModifier<NB2_MOD_CONCATENATE>;
 using Plugin_ToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_TOOL_DRAG_ORIENTATION>;
 using Plugin_BiasedToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION>;
 using Plugin_DirectionOfTravelOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION>;
+using Plugin_MovingAverageOrientationSmoothing = Plugin_DeviceToolPathModifier<NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING>;
 
 /** CompoundModifier (compound_modifier.cpp) whose runs of consecutive device modifiers are fused into one device chain;
  *  any other modifier the factory returns (the reference's own) is applied in its place in the sequence. */
@@ -848,6 +852,7 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_Concatenate, Concatenate)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_ToolDragOrientation, ToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_BiasedToolDragOrientation, BiasedToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_DirectionOfTravelOrientation, DirectionOfTravelOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)

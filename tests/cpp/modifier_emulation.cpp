@@ -6,8 +6,10 @@
 // the arithmetic and the bookkeeping of the device path are checked before they reach a GPU; the kernels themselves are
 // compared with the oracle by the `-m gpu` tests.
 #include "../../noether_b200/csrc/modifier_plan.h"
+#include "../../noether_b200/csrc/modifier_smooth.h"
 #include "../../noether_b200/csrc/nb2_internal.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -65,6 +67,38 @@ void runMap(const Step& st, const Structure& cur, const std::vector<double>& src
     }
   }
   dst.resize(src.size());
+  if (st.kind == NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING)
+  {
+    // k_mod_quaternions
+    std::vector<double> quat(4ull * W);
+    for (uint32_t w = 0; w < W; ++w)
+      rotationToQuaternion(&src[16ull * w], &quat[4ull * w]);
+    // k_mod_smooth: one thread per segment
+    for (uint32_t s = 0; s < S; ++s)
+    {
+      const uint32_t b = cur.seg_off[s], e = cur.seg_off[s + 1];
+      const int n = static_cast<int>(e - b), n_each_side = st.n_points / 2;
+      for (int i = 0; i < n; ++i)
+      {
+        double q[4];
+        std::memcpy(q, &quat[4ull * (b + i)], sizeof(q));
+        if (i > 0 && i < n - 1)
+        {
+          const int start = std::max(i - n_each_side, 0), stop = std::min(i + n_each_side, n - 1);
+          const bool ok = quaternionMean(stop - start + 1,
+                                         [&](int k, double* out) { std::memcpy(out, &quat[4ull * (b + start + k)], 32); }, q);
+          if (!ok)
+            fail(NB2_ERR_NON_FINITE, "Orientation contains NaN values");
+        }
+        double T[16];
+        std::memcpy(T, &src[16ull * (b + i)], sizeof(T));
+        quaternionToRotation(q, T);
+        std::memcpy(&dst[16ull * (b + i)], T, sizeof(T));
+        rotationToQuaternion(T, &quat[4ull * (b + i)]);
+      }
+    }
+    return;
+  }
   for (uint32_t w = 0; w < W; ++w)
   {
     double T[16];

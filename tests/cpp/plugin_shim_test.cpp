@@ -696,6 +696,7 @@ void testToolPathModifiers(const noether::Factory& factory)
   entry("UniformOrientation", true);
   entry("Concatenate", true);
   entry("DirectionOfTravelOrientation", true);
+  entry("MovingAverageOrientationSmoothing", false)["window_size"] = 3;
   {
     YAML::Node& n = entry("ToolDragOrientation", false);
     n["angle_offset"] = 0.1745, n["tool_radius"] = 0.025;
@@ -748,7 +749,7 @@ void testToolPathModifiers(const noether::Factory& factory)
     bool threw = false;
     try
     {
-      factory.createToolPathModifier(configs[8].first)->modify(single);
+      factory.createToolPathModifier(configs[9].first)->modify(single);
     }
     catch (const std::exception& e)
     {

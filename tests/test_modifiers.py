@@ -151,12 +151,17 @@ MODIFIERS = {
                                   lambda: _rec(_capi.NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION, [0.1745, 0.025])),
     "DirectionOfTravelOrientation": (lambda p: p.direction_of_travel(),
                                      lambda: _rec(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)),
+    "MovingAverageOrientationSmoothing": (lambda p: p.moving_average_orientation_smoothing(3),   # the reference's test YAML
+                                          lambda: _rec(_capi.NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING, (), 3)),
+    "MovingAverageOrientationSmoothing8": (lambda p: p.moving_average_orientation_smoothing(8),
+                                           lambda: _rec(_capi.NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING, (), 8)),
 }
 CHAINS = [
     ["LinearApproach", "LinearDeparture"],  # the reference's CompoundToolPathModifier test entry (:86-89)
     ["SnakeOrganization", "Offset", "LinearApproach", "LinearDeparture", "Concatenate"],
     ["DirectionOfTravelOrientation", "UniformOrientation", "ToolDragOrientation", "SnakeOrganization", "LinearApproach1"],
     ["Offset", "BiasedToolDragOrientation", "FixedOrientationOblique", "Concatenate", "SnakeOrganization"],
+    ["DirectionOfTravelOrientation", "MovingAverageOrientationSmoothing8", "LinearApproach", "MovingAverageOrientationSmoothing"],
 ]
 
 
@@ -253,6 +258,46 @@ def test_oracle_one_time_modifiers_are_idempotent(name):
         twice = p.flat()
         np.testing.assert_array_equal(once.seg_off, twice.seg_off)
         np.testing.assert_allclose(once.pose, twice.pose, rtol=0, atol=1e-12, err_msg=f"{name} on {key}")
+
+
+def test_oracle_moving_average_matches_an_eigen_decomposition():
+    """Markley's mean = dominant eigenvector of sum q q^T; the oracle's restated JacobiSVD against numpy.linalg.eigh,
+    with the reference's in-place recurrence (a window holds the already smoothed poses before its centre)"""
+    def quat(R):
+        t = np.trace(R)
+        if t > 0:
+            t = np.sqrt(t + 1)
+            return np.array([(R[2, 1] - R[1, 2]) * 0.5 / t, (R[0, 2] - R[2, 0]) * 0.5 / t, (R[1, 0] - R[0, 1]) * 0.5 / t, 0.5 * t])
+        i = int(np.argmax(np.diag(R)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        t = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1)
+        q = np.zeros(4)
+        q[i], q[3], q[j], q[k] = 0.5 * t, (R[k, j] - R[j, k]) * 0.5 / t, (R[j, i] + R[i, j]) * 0.5 / t, (R[k, i] + R[i, k]) * 0.5 / t
+        return q
+
+    def rot(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+    nested = ragged_tool_paths(np.random.default_rng(4), 4)
+    for window in (3, 6):
+        f = orc.Paths.from_nested(nested).moving_average_orientation_smoothing(window).flat()
+        at = 0
+        for path in nested:
+            for seg in path:
+                seg = seg.copy()
+                n = len(seg)
+                for i in range(n):
+                    q = quat(seg[i][:3, :3])
+                    if 0 < i < n - 1:
+                        lo, hi = max(i - window // 2, 0), min(i + window // 2, n - 1)
+                        M = sum(np.outer(quat(seg[k][:3, :3]), quat(seg[k][:3, :3])) for k in range(lo, hi + 1))
+                        q = np.linalg.eigh(M)[1][:, -1]
+                    seg[i][:3, :3] = rot(q)
+                np.testing.assert_allclose(f.pose[at:at + n], seg, rtol=0, atol=1e-13)
+                at += n
 
 
 def test_oracle_refuses_what_the_reference_cannot_do():

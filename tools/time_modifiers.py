@@ -57,5 +57,16 @@ for k, ms in stages.items():
         b = 128 * w_now + 128 * w_next
         w_now = w_next
     kernels[k] = {"ms": round(ms, 4), "algorithmic_bytes": b, "GB/s": round(b / ms / 1e6, 1), "frac_of_peak": round(b / ms / 1e6 / peak, 3)}
+# the one sequential modifier: MovingAverageOrientationSmoothing (a recurrence along each segment, one thread per segment)
+smooth = nb.CompoundModifier([nb.MovingAverageOrientationSmoothingModifier(3)], ctx)
+sm_ms = None
+for it in range(2):
+    out = smooth.modify(tp)
+    ms = ctx.timings().get("moving average orientation smoothing")
+    sm_ms = ms if sm_ms is None else min(sm_ms, ms)
+    out.free()
+kernels["moving average orientation smoothing (window 3)"] = {
+    "ms": round(sm_ms, 3), "note": "%d segments = %d threads walking %d poses each in order (4 x 4 Jacobi SVD per pose)"
+    % (tp.n_segments, tp.n_segments, W // max(tp.n_segments, 1))}
 print(json.dumps({"workload": name, "waypoints_in": W, "waypoints_out": w_out, "segments": s_out, "wall_ms": round(wall, 2),
                   "stage_ms": {k: round(v, 4) for k, v in stages.items()}, "kernels": kernels, "hbm_peak_GB/s": peak}))
