@@ -450,6 +450,24 @@ class PlaneSlicerRasterPlanner:
         return ctx.plan(p)
 
 
+class MultiToolPathPlanner:
+    """MultiToolPathPlanner::plan (multi_tool_path_planner.cpp:10-20; alias `Multi`, plugins.cpp:134-149): the tool paths of
+    every planner, one after the other.  A cross-hatch (noether_gui cross_hatch_plane_slicer_raster_planner.cpp) is two
+    plane slicers, the second with a PCARotated direction: both find the mesh resident — one upload, one set of moments
+    and extents."""
+
+    def __init__(self, planners, context: Context | None = None):
+        self.planners = list(planners)
+        self._ctx = context
+
+    def plan_each(self, mesh: MeshBlob) -> list[ToolPaths]:
+        return [p.plan(mesh) for p in self.planners]
+
+    def plan(self, mesh: MeshBlob) -> ToolPaths:
+        nested = [path for tp in self.plan_each(mesh) for path in tp.nested()]
+        return ToolPaths.from_nested(nested, self._ctx or (self.planners[0]._ctx if self.planners else None))
+
+
 class PlaneSlicerLegacyRasterPlanner(PlaneSlicerRasterPlanner):
     """plane_slicer_legacy_raster_planner.cpp:10-33"""
 
@@ -689,6 +707,8 @@ class Factory:
 
     def create_tool_path_planner(self, config: dict) -> PlaneSlicerRasterPlanner:
         name = _member(config, "name")
+        if name == "Multi":  # plugins.cpp:134-149
+            return MultiToolPathPlanner([self.create_tool_path_planner(e) for e in _member(config, "planners")], self._ctx)
         if name not in ("PlaneSlicer", "PlaneSlicerLegacy"):
             raise RuntimeError(f"Failed to find plugin '{name}' in section 'tpp'")
         dir_gen = self.create_direction_generator(_member(config, "direction_generator"))

@@ -658,6 +658,41 @@ def test_pca_rotated_direction_generator(ctx, orc, ply_mesh):
     assert_same_paths(gpu, paths.flat(), "PCARotated plan")
 
 
+def test_cross_hatch_shares_one_upload_and_one_frame(ctx, orc):
+    """a cross-hatch is a `Multi` planner of two plane slicers, the second with a PCARotated(90 deg)
+    direction (noether_gui cross_hatch_plane_slicer_raster_planner.cpp:55; multi_tool_path_planner.cpp:10-20).  Both
+    plans run on the mesh the context already holds: the second neither uploads nor recomputes moments / extents, and
+    the concatenation equals the oracle's two plans bit for bit."""
+    import noether_b200 as nb
+    blob, xyz, nrm, tri = _wavy_mesh(200, 160, hole=True)
+    base = {"name": "PlaneSlicer", "line_spacing": 0.013, "bidirectional": True, "origin_generator": {"name": "Centroid"}}
+    pa = {"name": "PrincipalAxis", "rotation_offset": 0.0}
+    cfg = {"name": "Multi", "planners": [dict(base, direction_generator=pa),
+                                         dict(base, direction_generator={"name": "PCARotated", "rotation_offset": np.pi / 2,
+                                                                         "direction_generator": pa})]}
+    multi = nb.Factory(ctx).create_tool_path_planner(cfg)
+    ctx._mesh_key = None
+    first, second = multi.plan_each(blob)
+    stages_second = ctx.timings()
+    frame = oracle_pca_from_capi(orc, ctx.pca())
+    d0 = orc.principal_axis_direction(frame, 0.0)
+    d1 = orc.pca_rotated_direction(frame, np.pi / 2, d0)
+    refs = []
+    for gpu, d in ((first, d0), (second, d1)):
+        paths, _, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.013, True, direction=d, slice_mode=orc.SLICE_INTENT, frame=frame)
+        assert_same_paths(gpu, paths.flat(), "cross-hatch plan")
+        refs.append(paths.flat())
+    assert first.n_paths > 40 and second.n_paths > 40
+    # the two plans cut along directions a quarter turn apart
+    assert abs(np.dot(d0, d1)) < 1e-6
+    # the whole of it as one ToolPaths, in planner order
+    both = multi.plan(blob)
+    assert both.n_paths == first.n_paths + second.n_paths
+    np.testing.assert_array_equal(both.poses(), np.concatenate([refs[0].pose, refs[1].pose]))
+    # the second plan found extents and lattice inputs on the device: its stage list has no extents pass
+    assert "classify" in stages_second and "extents+lattice" not in stages_second, stages_second
+
+
 @pytest.mark.parametrize("min_hole,min_seg", [(0.0, 0.03), (0.0, 0.12), (0.35, 0.03), (0.35, 0.3)])
 def test_legacy_modifiers_on_device_match_oracle(ctx, orc, min_hole, min_seg):
     """JoinCloseSegments / MinimumSegmentLength / UniformSpacing run on the GPU (kernels_legacy.cu) on the slicer's
