@@ -12,6 +12,7 @@ from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionG
                       ToolPathModifier, SnakeOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
                       OffsetModifier, FixedOrientationModifier, UniformOrientationModifier, ConcatenateModifier,
                       DirectionOfTravelOrientationModifier, MovingAverageOrientationSmoothingModifier,
+                      CircularLeadInModifier, CircularLeadOutModifier,
                       ToolDragOrientationToolPathModifier,
                       BiasedToolDragOrientationToolPathModifier, CompoundModifier)
 

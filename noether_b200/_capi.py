@@ -55,6 +55,8 @@ NB2_MOD_TOOL_DRAG_ORIENTATION = 8
 NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION = 9
 NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10
 NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING = 11
+NB2_MOD_CIRCULAR_LEAD_IN = 12
+NB2_MOD_CIRCULAR_LEAD_OUT = 13
 
 
 class Modifier(C.Structure):

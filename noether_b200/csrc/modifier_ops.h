@@ -194,6 +194,22 @@ NB2_HD inline uint32_t restructuredSource(const SegMap& m, uint32_t j, int* lead
   return m.flipped ? m.src_begin : m.src_begin + m.src_len - 1;
 }
 
+/** CircularLeadIn / CircularLeadOut point: (anchor * Translation(0, 0, r)) * AngleAxis(angle_i, Y) * Translation(0, 0, -r)
+ *  with the anchor's orientation put back; T holds the anchor on entry, R = the rotation of step i (row-major) */
+NB2_HD inline void circularLeadPoint(double* T, const double* R, double radius)
+{
+  double L[9];
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      L[3 * c + r] = T[4 * c + r];
+  translate(T, D3{ 0.0, 0.0, radius });
+  linearTimesMatrix(T, R);
+  translate(T, D3{ 0.0, 0.0, -radius });
+  for (int c = 0; c < 3; ++c)
+    for (int r = 0; r < 3; ++r)
+      T[4 * c + r] = L[3 * c + r];
+}
+
 NB2_HD inline void leadPoint(double* T, const double* offset, int i, int n_points)
 {
   const double f = static_cast<double>(i + 1) / static_cast<double>(n_points);

@@ -192,6 +192,45 @@ std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, i
           if (segLen(cur, static_cast<uint32_t>(s)) < 2)
             fail(NB2_ERR_TOO_FEW_POINTS, "segment with a single waypoint (segment[i - 1] out of bounds in the reference)");
         break;
+      case NB2_MOD_CIRCULAR_LEAD_IN:
+      case NB2_MOD_CIRCULAR_LEAD_OUT:
+      {
+        if (m.n_points < 0)
+          fail(NB2_ERR_INVALID_ARGUMENT, "n_points must not be negative");
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          uint64_t steps = 0;
+          for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+            steps += segLen(cur, s) > 1 ? segLen(cur, s) - 1 : 0;
+          if (steps < 1)
+            fail(NB2_ERR_TOO_FEW_POINTS, "Insufficient number of points to calculate average tool path direction");
+        }
+        for (uint64_t s = 0; s < S; ++s)
+          if (segLen(cur, static_cast<uint32_t>(s)) == 0)
+            fail(NB2_ERR_INVALID_ARGUMENT, "empty tool path segment (front() / back() of an empty vector in the reference)");
+        if (m.n_points == 0)
+        {
+          st.device = false;
+          break;
+        }
+        const bool lead_in = m.kind == NB2_MOD_CIRCULAR_LEAD_IN;
+        // delta_theta = arc_angle_ / (n_points_ - 1) with a double n_points_ (circular_lead_in_modifier.cpp:14)
+        const double delta_theta = m.v[0] / (static_cast<double>(m.n_points) - 1);
+        st.rot.resize(18 * static_cast<size_t>(m.n_points));
+        for (int sgn = 0; sgn < 2; ++sgn)
+          for (int i = 0; i < m.n_points; ++i)
+          {
+            const double sign = sgn == 0 ? 1.0 : -1.0;
+            const double angle = lead_in ? sign * delta_theta * (i + 1) : sign * -delta_theta * (i + 1);
+            angleAxisMatrix(angle, kUnitY, &st.rot[9 * (static_cast<size_t>(sgn) * m.n_points + i)]);
+          }
+        std::vector<std::pair<uint32_t, bool>> order;
+        order.reserve(S);
+        for (uint64_t s = 0; s < S; ++s)
+          order.emplace_back(static_cast<uint32_t>(s), false);
+        restructure(cur, order, lead_in ? m.n_points : 0, lead_in ? 0 : m.n_points, st);
+        break;
+      }
       case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING:
         if (m.n_points < 0)
           fail(NB2_ERR_INVALID_ARGUMENT, "window_size must not be negative");

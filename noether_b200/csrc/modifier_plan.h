@@ -33,6 +33,7 @@ struct Step
   double R[2][9] = {};       // rotation for sign > 0 / sign < 0 (tool drag), R[0] for UniformOrientation (row-major)
   double v[16] = {};         // constants of the per-waypoint operation (see modifiers.cu)
   int n_points = 0;
+  std::vector<double> rot;   // circular leads: rotation of step i for sign > 0 at [9 i], for sign < 0 at [9 (n_points + i)]
 };
 
 /** Eigen::AngleAxisd(angle, axis).toRotationMatrix() for a unit axis, row-major (Eigen 3.4 Geometry/AngleAxis.h) */

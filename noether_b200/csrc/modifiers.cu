@@ -11,7 +11,8 @@
 //   k_mod_expand        compact float result (cut point, interpolated normal) -> poses: createTransform
 //                       (plane_slicer_raster_planner.cpp:380-394) [+ DirectionOfTravelOrientationModifier]
 //   k_mod_map           Offset / FixedOrientation / UniformOrientation / ToolDrag / BiasedToolDrag / DirectionOfTravel
-//   k_mod_restructure   SnakeOrganization / LinearApproach / LinearDeparture (segment table -> gather)
+//   k_mod_restructure   SnakeOrganization / LinearApproach / LinearDeparture / CircularLeadIn / CircularLeadOut
+//                       (segment table -> gather; lead points from the segment's first / last pose)
 //   k_mod_path_sign     estimateToolPathDirection (utils.cpp:7-29) per tool path, one CTA each: normalisations on all
 //                       warps, the reference's additions in the reference's order; then the tool-drag sign of the path
 //   k_mod_quaternions / k_mod_smooth   MovingAverageOrientationSmoothing: quaternions of all poses in parallel, then
@@ -169,7 +170,10 @@ __global__ void __launch_bounds__(kTile) k_mod_map_t(const double* __restrict__ 
 __global__ void __launch_bounds__(kTile) k_mod_restructure(const double* __restrict__ src, double* __restrict__ dst,
                                                            unsigned W_out, const SegMap* __restrict__ map,
                                                            const unsigned* __restrict__ seg_off_out, unsigned n_segments,
-                                                           double ox, double oy, double oz, int n_points)
+                                                           double ox, double oy, double oz, int n_points,
+                                                           const double* __restrict__ rot, double radius,
+                                                           const unsigned* __restrict__ seg_path,
+                                                           const int* __restrict__ path_sign)
 {
   __shared__ double tile[kTile * kRow];
   const unsigned long long base = static_cast<unsigned long long>(blockIdx.x) * kTile;
@@ -192,8 +196,21 @@ __global__ void __launch_bounds__(kTile) k_mod_restructure(const double* __restr
     }
     if (lead >= 0)
     {
-      const double off[3] = { ox, oy, oz };
-      leadPoint(T, off, lead, n_points);
+      if (rot)  // circular lead in / out: the rotation of step `lead` for the sign of the segment's tool path
+      {
+        const int neg = path_sign[seg_path[s]] > 0 ? 0 : 1;
+        const double* Rg = rot + 9ull * (static_cast<unsigned>(neg) * static_cast<unsigned>(n_points) + static_cast<unsigned>(lead));
+        double R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+          R[i] = __ldg(Rg + i);
+        circularLeadPoint(T, R, radius);
+      }
+      else
+      {
+        const double off[3] = { ox, oy, oz };
+        leadPoint(T, off, lead, n_points);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i)
@@ -426,6 +443,8 @@ const char* stageName(int kind)
     case NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION: return "biased tool drag orientation";
     case NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION: return "direction of travel orientation";
     case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING: return "moving average orientation smoothing";
+    case NB2_MOD_CIRCULAR_LEAD_IN: return "circular lead in";
+    case NB2_MOD_CIRCULAR_LEAD_OUT: return "circular lead out";
   }
   return "modifier";
 }
@@ -566,13 +585,29 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
       const unsigned S_in = static_cast<unsigned>(cur.segments());
       if (st.restructure)
       {
+        const bool circular = st.kind == NB2_MOD_CIRCULAR_LEAD_IN || st.kind == NB2_MOD_CIRCULAR_LEAD_OUT;
+        if (circular)
+        {
+          // sign of every tool path from the poses as they are now (before the new offsets replace the old ones)
+          const unsigned P = static_cast<unsigned>(cur.paths());
+          uploadVector(c, c->modSegPath, segmentPaths(cur));  // segments keep their tool path and their index
+          uploadVector(c, c->modPathOff, cur.path_off);
+          uploadVector(c, c->modRot, st.rot);
+          c->modPathSign.ensure(sizeof(int) * std::max(P, 1u));
+          k_mod_path_sign<<<P, kSignThreads, 0, c->stream>>>(buf[at], c->modSegOff.as<unsigned>(),
+                                                               c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>());
+          NB2_CUDA(cudaGetLastError());
+          ++c->launches;
+        }
         uploadVector(c, c->modSegMap, st.map);
         uploadVector(c, c->modSegOff, st.out.seg_off);  // stream-ordered after the kernels that read the old offsets
         const unsigned W_out = static_cast<unsigned>(st.out.waypoints());
         k_mod_restructure<<<tiles(W_out), kTile, 0, c->stream>>>(buf[at], buf[at ^ 1], W_out, c->modSegMap.as<SegMap>(),
                                                                    c->modSegOff.as<unsigned>(),
                                                                    static_cast<unsigned>(st.out.segments()), st.v[0], st.v[1],
-                                                                   st.v[2], st.n_points);
+                                                                   st.v[2], st.n_points,
+                                                                   circular ? c->modRot.as<double>() : nullptr, st.v[1],
+                                                                   c->modSegPath.as<unsigned>(), c->modPathSign.as<int>());
         NB2_CUDA(cudaGetLastError());
         ++c->launches;
       }

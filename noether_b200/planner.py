@@ -609,6 +609,23 @@ class DirectionOfTravelOrientationModifier(ToolPathModifier):
         return [_record(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)]
 
 
+class CircularLeadInModifier(ToolPathModifier):
+    """circular_lead_in_modifier.cpp:7-44"""
+    _kind = _capi.NB2_MOD_CIRCULAR_LEAD_IN
+
+    def __init__(self, arc_angle: float, arc_radius: float, n_points: int, context: Context | None = None):
+        super().__init__(context)
+        self.arc_angle, self.arc_radius, self.n_points = float(arc_angle), float(arc_radius), int(n_points)
+
+    def _records(self):
+        return [_record(self._kind, [self.arc_angle, self.arc_radius], self.n_points)]
+
+
+class CircularLeadOutModifier(CircularLeadInModifier):
+    """circular_lead_out_modifier.cpp:7-44"""
+    _kind = _capi.NB2_MOD_CIRCULAR_LEAD_OUT
+
+
 class MovingAverageOrientationSmoothingModifier(ToolPathModifier):
     """moving_average_orientation_smoothing_modifier.cpp:6-84 (in-place recurrence along each segment)"""
 
@@ -742,6 +759,9 @@ class Factory:
             return ConcatenateModifier(c)
         if name == "DirectionOfTravelOrientation":
             return DirectionOfTravelOrientationModifier(c)
+        if name in ("CircularLeadIn", "CircularLeadOut"):
+            cls = CircularLeadInModifier if name == "CircularLeadIn" else CircularLeadOutModifier
+            return cls(float(_member(config, "arc_angle")), float(_member(config, "arc_radius")), int(_member(config, "n_points")), c)
         if name == "MovingAverageOrientationSmoothing":  # window_size is read as a double and cast (:103)
             return MovingAverageOrientationSmoothingModifier(int(float(_member(config, "window_size"))), c)
         if name in ("ToolDragOrientation", "BiasedToolDragOrientation"):

@@ -105,6 +105,8 @@ def lib():
         getattr(L, n).argtypes = [C.c_void_p, f64p, C.c_int]
     L.orc_offset.argtypes = [C.c_void_p, f64p]
     L.orc_moving_average_orientation_smoothing.argtypes = [C.c_void_p, C.c_int]
+    for n in ("orc_circular_lead_in", "orc_circular_lead_out"):
+        getattr(L, n).argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
     L.orc_fixed_orientation.argtypes = [C.c_void_p, f64p]
     for n in ("orc_tool_drag_orientation", "orc_biased_tool_drag_orientation"):
         getattr(L, n).argtypes = [C.c_void_p, C.c_double, C.c_double]
@@ -366,6 +368,14 @@ class Paths:
 
     def tool_drag_orientation(self, angle_offset, tool_radius):
         _check(lib().orc_tool_drag_orientation(self._h, angle_offset, tool_radius))
+        return self
+
+    def circular_lead_in(self, arc_angle, arc_radius, n_points):
+        _check(lib().orc_circular_lead_in(self._h, arc_angle, arc_radius, int(n_points)))
+        return self
+
+    def circular_lead_out(self, arc_angle, arc_radius, n_points):
+        _check(lib().orc_circular_lead_out(self._h, arc_angle, arc_radius, int(n_points)))
         return self
 
     def moving_average_orientation_smoothing(self, window_size):

@@ -152,6 +152,8 @@ int orc_uniform_orientation(orc_paths* p);                                      
 int orc_concatenate(orc_paths* p);                                               /* concatenate_modifier.cpp:5-15 */
 int orc_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius);        /* tool_drag_orientation_modifier.cpp:11-35 */
 int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius); /* biased_tool_drag_orientation_modifier.cpp:12-35 */
+int orc_circular_lead_in(orc_paths* p, double arc_angle, double arc_radius, int n_points);  /* circular_lead_in_modifier.cpp:12-44 */
+int orc_circular_lead_out(orc_paths* p, double arc_angle, double arc_radius, int n_points); /* circular_lead_out_modifier.cpp:12-44 */
 int orc_moving_average_orientation_smoothing(orc_paths* p, int window_size); /* moving_average_orientation_smoothing_modifier.cpp:6-84 */
 
 /* ---- mesh files: what pcl::io::loadPolygonFile yields for a PLY (noether_gui/src/widgets/tpp_widget.cpp:426;

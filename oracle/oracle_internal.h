@@ -74,6 +74,7 @@ int uniformOrientation(orc_paths& p);
 int concatenate(orc_paths& p);
 int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased);
 int movingAverageOrientationSmoothing(orc_paths& p, int window_size);
+int circularLead(orc_paths& p, double arc_angle, double arc_radius, int n_points, bool lead_out);
 
 inline V3d translation(const Waypoint& w) { return { w.T[12], w.T[13], w.T[14] }; }
 }  // namespace orc

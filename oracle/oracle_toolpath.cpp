@@ -342,6 +342,60 @@ int toolDrag(orc_paths& p, double angle_offset, double tool_radius, bool biased)
   return ORC_OK;
 }
 
+/** CircularLeadInModifier::modify (circular_lead_in_modifier.cpp:12-44) / CircularLeadOutModifier::modify
+ *  (circular_lead_out_modifier.cpp:12-44).  pt = radius_center * AngleAxisd(angle, UnitY) * Translation3d(0, 0, -r) is
+ *  Transform::rotate (L = L R) followed by Transform::translate (t += L v); the orientation is then reset to the anchor's. */
+int circularLead(orc_paths& p, double arc_angle, double arc_radius, int n_points, bool lead_out)
+{
+  const double n_points_d = static_cast<double>(n_points);  // the member is a double
+  const double delta_theta = arc_angle / (n_points_d - 1);
+  for (Path& tool_path : p.paths)
+  {
+    V3d dir;
+    if (!estimateToolPathDirection(tool_path, dir))
+      return ORC_ERR_TOO_FEW_POINTS;
+    if (tool_path.segments.at(0).empty())
+    {
+      setError("first segment of a tool path is empty (tool_path.at(0).at(0))");
+      return ORC_ERR_INVALID;
+    }
+    const Waypoint& first = tool_path.segments.at(0).at(0);
+    const V3d y = { first.T[4], first.T[5], first.T[6] };
+    const V3d z = { first.T[8], first.T[9], first.T[10] };
+    const double sign = eigenDot(eigenCross(z, dir), y) > 0.0 ? 1.0 : -1.0;
+    for (Segment& segment : tool_path.segments)
+    {
+      if (segment.empty())
+      {
+        setError("empty segment (front() / back() of an empty vector in the reference)");
+        return ORC_ERR_INVALID;
+      }
+      const Waypoint anchor = lead_out ? segment.back() : segment.front();
+      Waypoint radius_center = anchor;
+      translate(radius_center, V3d{ 0.0, 0.0, arc_radius });
+      Segment added;
+      for (int i = 0; i < n_points; ++i)
+      {
+        const double angle = lead_out ? sign * -delta_theta * (i + 1) : sign * delta_theta * (i + 1);
+        double R[9];
+        angleAxisMatrix(angle, V3d{ 0.0, 1.0, 0.0 }, R);
+        Waypoint pt = radius_center;
+        linearTimesMatrix(pt, R);
+        translate(pt, V3d{ 0.0, 0.0, -arc_radius });
+        for (int c = 0; c < 3; ++c)
+          for (int r = 0; r < 3; ++r)
+            at(pt, r, c) = at(anchor, r, c);
+        added.push_back(pt);
+      }
+      if (lead_out)
+        segment.insert(segment.end(), added.begin(), added.end());  // (inserted at the front, then appended reversed)
+      else
+        segment.insert(segment.begin(), added.rbegin(), added.rend());
+    }
+  }
+  return ORC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // MovingAverageOrientationSmoothingModifier (moving_average_orientation_smoothing_modifier.cpp:6-84).  Third-party
 // pieces restated from Eigen 3.4: Quaternion(Matrix3) (Geometry/Quaternion.h quaternionbase_assign_impl<Other,3,3>),
@@ -943,6 +997,8 @@ int orc_uniform_orientation(orc_paths* p) { return uniformOrientation(*p); }
 int orc_concatenate(orc_paths* p) { return concatenate(*p); }
 int orc_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, false); }
 int orc_biased_tool_drag_orientation(orc_paths* p, double angle_offset, double tool_radius) { return toolDrag(*p, angle_offset, tool_radius, true); }
+int orc_circular_lead_in(orc_paths* p, double arc_angle, double arc_radius, int n_points) { return circularLead(*p, arc_angle, arc_radius, n_points, false); }
+int orc_circular_lead_out(orc_paths* p, double arc_angle, double arc_radius, int n_points) { return circularLead(*p, arc_angle, arc_radius, n_points, true); }
 int orc_moving_average_orientation_smoothing(orc_paths* p, int window_size) { return movingAverageOrientationSmoothing(*p, window_size); }
 int orc_join_close_segments(orc_paths* p, double d) { return joinCloseSegments(*p, d); }
 int orc_minimum_segment_length(orc_paths* p, double l) { return minimumSegmentLength(*p, l); }

@@ -772,6 +772,12 @@ struct Plugin_DeviceToolPathModifier : public noether::Plugin<noether::ToolPathM
         m.v[0] = YAML::getMember<double>(config, "angle_offset");
         m.v[1] = YAML::getMember<double>(config, "tool_radius");
         break;
+      case NB2_MOD_CIRCULAR_LEAD_IN:   // circular_lead_in_modifier.cpp:60-66
+      case NB2_MOD_CIRCULAR_LEAD_OUT:  // circular_lead_out_modifier.cpp (same keys)
+        m.v[0] = YAML::getMember<double>(config, "arc_angle");
+        m.v[1] = YAML::getMember<double>(config, "arc_radius");
+        m.n_points = YAML::getMember<int>(config, "n_points");
+        break;
       case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING:  // moving_average_orientation_smoothing_modifier.cpp:99-105
         m.n_points = static_cast<int>(static_cast<std::size_t>(YAML::getMember<double>(config, "window_size")));
         break;
@@ -791,6 +797,8 @@ using Plugin_Concatenate = Plugin_DeviceToolPathModifier<NB2_MOD_CONCATENATE>;
 using Plugin_ToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_TOOL_DRAG_ORIENTATION>;
 using Plugin_BiasedToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION>;
 using Plugin_DirectionOfTravelOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION>;
+using Plugin_CircularLeadIn = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_IN>;
+using Plugin_CircularLeadOut = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_OUT>;
 using Plugin_MovingAverageOrientationSmoothing = Plugin_DeviceToolPathModifier<NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING>;
 
 /** CompoundModifier (compound_modifier.cpp) whose runs of consecutive device modifiers are fused into one device chain;
@@ -852,6 +860,8 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_Concatenate, Concatenate)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_ToolDragOrientation, ToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_BiasedToolDragOrientation, BiasedToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_DirectionOfTravelOrientation, DirectionOfTravelOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadIn, CircularLeadIn)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadOut, CircularLeadOut)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)

@@ -142,8 +142,40 @@ void runMap(const Step& st, const Structure& cur, const std::vector<double>& src
   }
 }
 
-void runRestructure(const Step& st, const std::vector<double>& src, std::vector<double>& dst)
+std::vector<int> pathSigns(const Structure& cur, const std::vector<double>& src)
 {
+  std::vector<int> path_sign(cur.paths());
+  for (uint64_t p = 0; p < cur.paths(); ++p)
+  {
+    D3 acc{ 0, 0, 0 };
+    unsigned count = 0;
+    for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+    {
+      const uint32_t b = cur.seg_off[s], e = cur.seg_off[s + 1];
+      for (uint32_t i = b; i + 1 < e; ++i)
+      {
+        acc = acc + normalized(tr(src, i + 1) - tr(src, i));
+        ++count;
+      }
+    }
+    const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
+    path_sign[p] = toolDragSign(&src[16ull * cur.seg_off[cur.path_off[p]]], dir) > 0.0 ? 1 : -1;
+  }
+  return path_sign;
+}
+
+void runRestructure(const Step& st, const Structure& cur, const std::vector<double>& src, std::vector<double>& dst)
+{
+  const bool circular = st.kind == NB2_MOD_CIRCULAR_LEAD_IN || st.kind == NB2_MOD_CIRCULAR_LEAD_OUT;
+  std::vector<int> path_sign;
+  std::vector<uint32_t> seg_path(cur.segments());
+  if (circular)
+  {
+    path_sign = pathSigns(cur, src);
+    for (uint64_t p = 0; p < cur.paths(); ++p)
+      for (uint32_t k = cur.path_off[p]; k < cur.path_off[p + 1]; ++k)
+        seg_path[k] = static_cast<uint32_t>(p);
+  }
   const uint32_t W_out = static_cast<uint32_t>(st.out.waypoints()), S = static_cast<uint32_t>(st.out.segments());
   dst.assign(16ull * W_out, 0.0);
   for (uint32_t w = 0; w < W_out; ++w)
@@ -154,7 +186,12 @@ void runRestructure(const Step& st, const std::vector<double>& src, std::vector<
     const uint32_t from = restructuredSource(m, w - m.out_begin, &lead);
     double T[16];
     std::memcpy(T, &src[16ull * from], sizeof(T));
-    if (lead >= 0)
+    if (lead >= 0 && circular)
+    {
+      const int neg = path_sign[seg_path[s]] > 0 ? 0 : 1;
+      circularLeadPoint(T, &st.rot[9ull * (static_cast<size_t>(neg) * st.n_points + lead)], st.v[1]);
+    }
+    else if (lead >= 0)
       leadPoint(T, st.v, lead, st.n_points);
     std::memcpy(&dst[16ull * w], T, sizeof(T));
   }
@@ -199,7 +236,7 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
       if (st.device)
       {
         if (st.restructure)
-          runRestructure(st, a, b);
+          runRestructure(st, cur, a, b);
         else
           runMap(st, cur, a, b);
         a.swap(b);

@@ -705,6 +705,11 @@ void testToolPathModifiers(const noether::Factory& factory)
     YAML::Node& n = entry("BiasedToolDragOrientation", false);
     n["angle_offset"] = 0.1745, n["tool_radius"] = 0.025;
   }
+  for (const char* lead : { "CircularLeadIn", "CircularLeadOut" })
+  {
+    YAML::Node& n = entry(lead, false);
+    n["arc_angle"] = 1.571, n["arc_radius"] = 0.1, n["n_points"] = 5;
+  }
   {
     YAML::Node& n = entry("CompoundToolPathModifier", false);
     YAML::Node list;
@@ -727,7 +732,7 @@ void testToolPathModifiers(const noether::Factory& factory)
         CHECK(once.size() == 1 && once[0].size() == 8);
       else
         CHECK(once.size() == 4 && once[0].size() == 2);
-      const std::size_t want = name == "CompoundToolPathModifier" ? 20 : (name.rfind("Linear", 0) == 0 ? 15 : 10);
+      const std::size_t want = name == "CompoundToolPathModifier" ? 20 : (name.rfind("Linear", 0) == 0 || name.rfind("Circular", 0) == 0 ? 15 : 10);
       CHECK(once[0][0].size() == want);
     }
     std::printf("  %s ok\n", name.c_str());

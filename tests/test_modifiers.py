@@ -151,6 +151,12 @@ MODIFIERS = {
                                   lambda: _rec(_capi.NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION, [0.1745, 0.025])),
     "DirectionOfTravelOrientation": (lambda p: p.direction_of_travel(),
                                      lambda: _rec(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)),
+    "CircularLeadIn": (lambda p: p.circular_lead_in(1.571, 0.1, 5),   # the reference's test YAML (:18-25)
+                       lambda: _rec(_capi.NB2_MOD_CIRCULAR_LEAD_IN, [1.571, 0.1], 5)),
+    "CircularLeadOut": (lambda p: p.circular_lead_out(1.571, 0.1, 5),
+                        lambda: _rec(_capi.NB2_MOD_CIRCULAR_LEAD_OUT, [1.571, 0.1], 5)),
+    "CircularLeadIn2": (lambda p: p.circular_lead_in(0.6, 0.03, 2),
+                        lambda: _rec(_capi.NB2_MOD_CIRCULAR_LEAD_IN, [0.6, 0.03], 2)),
     "MovingAverageOrientationSmoothing": (lambda p: p.moving_average_orientation_smoothing(3),   # the reference's test YAML
                                           lambda: _rec(_capi.NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING, (), 3)),
     "MovingAverageOrientationSmoothing8": (lambda p: p.moving_average_orientation_smoothing(8),
@@ -162,6 +168,7 @@ CHAINS = [
     ["DirectionOfTravelOrientation", "UniformOrientation", "ToolDragOrientation", "SnakeOrganization", "LinearApproach1"],
     ["Offset", "BiasedToolDragOrientation", "FixedOrientationOblique", "Concatenate", "SnakeOrganization"],
     ["DirectionOfTravelOrientation", "MovingAverageOrientationSmoothing8", "LinearApproach", "MovingAverageOrientationSmoothing"],
+    ["SnakeOrganization", "CircularLeadIn", "CircularLeadOut", "Offset", "CircularLeadIn2", "Concatenate"],
 ]
 
 
@@ -258,6 +265,33 @@ def test_oracle_one_time_modifiers_are_idempotent(name):
         twice = p.flat()
         np.testing.assert_array_equal(once.seg_off, twice.seg_off)
         np.testing.assert_allclose(once.pose, twice.pose, rtol=0, atol=1e-12, err_msg=f"{name} on {key}")
+
+
+def test_oracle_circular_leads_lie_on_the_arc():
+    """lead points sit on a circle of arc_radius about anchor + z * r, in the anchor's x-z plane, keep the anchor's
+    orientation, and end next to the anchor (circular_lead_in_modifier.cpp:25-40)"""
+    nested = raster_grid_tool_paths(2, 1, 6)
+    r, a, n = 0.1, 1.571, 5
+    f = oracle_apply(nested, ["CircularLeadIn"])
+    seg = f.pose[:6 + n]
+    centre = nested[0][0][0][:3, 3] + np.array([0.0, 0.0, r])
+    for j in range(n):
+        np.testing.assert_allclose(np.linalg.norm(seg[j][:3, 3] - centre), r, rtol=0, atol=1e-15)
+        assert abs(seg[j][1, 3] - nested[0][0][0][1, 3]) < 1e-15
+        np.testing.assert_array_equal(seg[j][:3, :3], np.eye(3))
+    # grid paths run along +x with identity orientation: sign = +1; step i sits at angle delta * (i + 1) about +y
+    d = a / (n - 1)
+    for j in range(n):
+        i = n - 1 - j
+        want = centre + np.array([-r * np.sin(d * (i + 1)), 0.0, -r * np.cos(d * (i + 1))])
+        np.testing.assert_allclose(seg[j][:3, 3], want, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(seg[n], nested[0][0][0])
+    g = oracle_apply(nested, ["CircularLeadOut"])
+    seg = g.pose[:6 + n]
+    centre = nested[0][0][5][:3, 3] + np.array([0.0, 0.0, r])
+    for j in range(n):
+        want = centre + np.array([r * np.sin(d * (j + 1)), 0.0, -r * np.cos(d * (j + 1))])
+        np.testing.assert_allclose(seg[6 + j][:3, 3], want, rtol=0, atol=1e-15)
 
 
 def test_oracle_moving_average_matches_an_eigen_decomposition():
