@@ -282,6 +282,8 @@ typedef enum nb2_modifier_kind
   NB2_MOD_TOOL_DRAG_ORIENTATION = 8,       /* tool_drag_orientation_modifier.cpp:11-35: v[0] = angle_offset, v[1] = tool_radius */
   NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION = 9,/* biased_tool_drag_orientation_modifier.cpp:12-35: v[0] = angle_offset, v[1] = tool_radius */
   NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10, /* direction_of_travel_orientation_modifier.cpp:6-48 */
+  NB2_MOD_RASTER_ORGANIZATION = 14,        /* raster_organization_modifier.cpp:7-46 (decided on the host from the first /
+                                              last translation of every segment, read back from the device) */
   NB2_MOD_CIRCULAR_LEAD_IN = 12,           /* circular_lead_in_modifier.cpp:12-44: v[0] = arc_angle, v[1] = arc_radius, n_points */
   NB2_MOD_CIRCULAR_LEAD_OUT = 13,          /* circular_lead_out_modifier.cpp:12-44: v[0] = arc_angle, v[1] = arc_radius, n_points */
   NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING = 11 /* moving_average_orientation_smoothing_modifier.cpp:6-84:

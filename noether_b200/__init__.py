@@ -9,7 +9,7 @@ from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionG
                       FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,
                       default_context, make_lattice,
-                      ToolPathModifier, SnakeOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
+                      ToolPathModifier, SnakeOrganizationModifier, RasterOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
                       OffsetModifier, FixedOrientationModifier, UniformOrientationModifier, ConcatenateModifier,
                       DirectionOfTravelOrientationModifier, MovingAverageOrientationSmoothingModifier,
                       CircularLeadInModifier, CircularLeadOutModifier,

@@ -57,6 +57,7 @@ NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10
 NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING = 11
 NB2_MOD_CIRCULAR_LEAD_IN = 12
 NB2_MOD_CIRCULAR_LEAD_OUT = 13
+NB2_MOD_RASTER_ORGANIZATION = 14
 
 
 class Modifier(C.Structure):

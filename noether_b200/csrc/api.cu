@@ -728,7 +728,7 @@ void nb2_context_destroy(nb2_context* c)
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
-                     &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->stlSlots, &c->stlCorner,
+                     &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->modEnds, &c->stlSlots, &c->stlCorner,
                      &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix })
     b->release();
   c->hostSmall.release();

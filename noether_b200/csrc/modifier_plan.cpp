@@ -3,6 +3,7 @@
 #include "modifier_plan.h"
 #include "nb2_internal.h"
 
+#include <algorithm>
 #include <cmath>
 #include <string>
 
@@ -36,7 +37,7 @@ namespace
 const double kUnitY[3] = { 0.0, 1.0, 0.0 };
 const double kUnitZ[3] = { 0.0, 0.0, 1.0 };
 
-void checkStructure(const Structure& s)
+void checkStructureImpl(const Structure& s)
 {
   if (s.path_off.empty() || s.seg_off.empty() || s.path_off.front() != 0 || s.seg_off.front() != 0 ||
       s.path_off.back() != s.segments() || s.path_plane.size() != s.paths())
@@ -77,18 +78,87 @@ void restructure(const Structure& cur, const std::vector<std::pair<uint32_t, boo
     st.out.seg_off.push_back(static_cast<uint32_t>(w));
   }
 }
+
+/** RasterOrganizationModifier::modify (raster_organization_modifier.cpp:7-46) decided on the first / last translation
+ *  of every segment: segments whose (last - first) opposes the direction of tool path 0 are reversed, the segments of a
+ *  tool path are sorted by their first waypoint along that direction, the tool paths by their first waypoint along the
+ *  raster direction (estimateRasterDirection, utils.cpp:31-47).  Same arithmetic as the planner's own post-op
+ *  (toolpath.cpp::rasterOrganization). */
+void organizeRasters(const Structure& cur, const std::vector<double>& ends, const D3& ref, Step& st)
+{
+  const uint64_t P = cur.paths();
+  struct SegRef
+  {
+    uint32_t seg;
+    bool flipped;
+  };
+  auto first = [&](uint32_t s) { return D3{ ends[6 * s], ends[6 * s + 1], ends[6 * s + 2] }; };
+  auto last = [&](uint32_t s) { return D3{ ends[6 * s + 3], ends[6 * s + 4], ends[6 * s + 5] }; };
+  auto firstOf = [&](const SegRef& r) { return r.flipped ? last(r.seg) : first(r.seg); };
+  std::vector<std::vector<SegRef>> segs(P);
+  bool identity = true;
+  for (uint64_t p = 0; p < P; ++p)
+  {
+    auto& v = segs[p];
+    for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+    {
+      const bool flip = dot(last(s) - first(s), ref) < 0.0;
+      identity &= !flip;
+      v.push_back({ s, flip });
+    }
+    if (v.size() > 1)
+    {
+      const D3 base = firstOf(v[0]);
+      std::sort(v.begin(), v.end(), [&](const SegRef& a, const SegRef& b) {
+        return dot(firstOf(a) - base, ref) < dot(firstOf(b) - base, ref);
+      });
+      for (size_t i = 0; i < v.size(); ++i)
+        identity &= (v[i].seg == cur.path_off[p] + i);
+    }
+  }
+  std::vector<uint32_t> order(P);
+  for (uint64_t p = 0; p < P; ++p)
+    order[p] = static_cast<uint32_t>(p);
+  {
+    const D3 first_wp = firstOf(segs.front().front());
+    const D3 first_wp_last = firstOf(segs.back().front());
+    const D3 nref = normalized(ref);
+    D3 raster_dir = first_wp_last - first_wp;
+    raster_dir = raster_dir - dot(raster_dir, nref) * nref;
+    raster_dir = normalized(raster_dir);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      return dot(firstOf(segs[a].front()) - first_wp, raster_dir) < dot(firstOf(segs[b].front()) - first_wp, raster_dir);
+    });
+    for (uint32_t i = 0; i < order.size(); ++i)
+      identity &= (order[i] == i);
+  }
+  if (identity)
+  {
+    st.device = false;
+    return;
+  }
+  std::vector<std::pair<uint32_t, bool>> seq;
+  seq.reserve(cur.segments());
+  Structure reordered;
+  reordered.path_off.assign(1, 0u);
+  for (uint64_t p = 0; p < P; ++p)
+  {
+    for (const SegRef& r : segs[order[p]])
+      seq.emplace_back(r.seg, r.flipped);
+    reordered.path_off.push_back(static_cast<uint32_t>(seq.size()));
+    reordered.path_plane.push_back(cur.path_plane[order[p]]);
+  }
+  restructure(cur, seq, 0, 0, st);
+  st.out.path_off = reordered.path_off;
+  st.out.path_plane = reordered.path_plane;
+}
 }  // namespace
 
-std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, int n_chain)
+void checkStructure(const Structure& s) { checkStructureImpl(s); }
+
+Step buildStep(const Structure& cur, const nb2_modifier& m, Probe* probe)
 {
-  checkStructure(in);
-  if (n_chain < 0 || (n_chain > 0 && !chain))
-    fail(NB2_ERR_INVALID_ARGUMENT, "modifier chain is NULL");
-  std::vector<Step> prog;
-  Structure cur = in;
-  for (int k = 0; k < n_chain; ++k)
   {
-    const nb2_modifier& m = chain[k];
     Step st;
     st.kind = m.kind;
     st.n_points = m.n_points;
@@ -235,13 +305,36 @@ std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, i
         if (m.n_points < 0)
           fail(NB2_ERR_INVALID_ARGUMENT, "window_size must not be negative");
         break;
+      case NB2_MOD_RASTER_ORGANIZATION:
+      {
+        if (P == 0)
+          break;  // nothing to organise (the reference would read tool_paths.at(0))
+        uint64_t steps = 0;
+        for (uint32_t s = cur.path_off[0]; s < cur.path_off[1]; ++s)
+          steps += segLen(cur, s) > 1 ? segLen(cur, s) - 1 : 0;
+        if (steps < 1)
+          fail(NB2_ERR_TOO_FEW_POINTS, "Insufficient number of points to calculate average tool path direction");
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          if (cur.path_off[p] == cur.path_off[p + 1])
+            fail(NB2_ERR_INVALID_ARGUMENT, "tool path without segments (tool_path.at(0) in the reference)");
+          for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+            if (segLen(cur, s) == 0)
+              fail(NB2_ERR_INVALID_ARGUMENT, "empty tool path segment (front() / back() of an empty vector in the reference)");
+        }
+        if (!probe)
+          fail(NB2_ERR_INTERNAL, "RasterOrganization needs the poses");
+        std::vector<double> ends;
+        double dir0[3];
+        probe->rasterInputs(cur, ends, dir0);
+        organizeRasters(cur, ends, D3{ dir0[0], dir0[1], dir0[2] }, st);
+        break;
+      }
       default:
         fail(NB2_ERR_INVALID_ARGUMENT, "unknown modifier kind " + std::to_string(m.kind));
     }
-    cur = st.out;
-    prog.push_back(std::move(st));
+    return st;
   }
-  return prog;
 }
 }  // namespace mod
 }  // namespace nb2

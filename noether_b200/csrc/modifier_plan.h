@@ -36,10 +36,21 @@ struct Step
   std::vector<double> rot;   // circular leads: rotation of step i for sign > 0 at [9 i], for sign < 0 at [9 (n_points + i)]
 };
 
+/** What a data-dependent modifier needs to see of the poses (they live on the device): implemented by the executor */
+struct Probe
+{
+  virtual ~Probe() = default;
+  /** translation of the first and of the last waypoint of every segment (6 doubles per segment; zeros for an empty
+   *  segment) and estimateToolPathDirection of tool path 0 (utils.cpp:7-29) */
+  virtual void rasterInputs(const Structure& cur, std::vector<double>& seg_ends, double dir0[3]) = 0;
+};
+
 /** Eigen::AngleAxisd(angle, axis).toRotationMatrix() for a unit axis, row-major (Eigen 3.4 Geometry/AngleAxis.h) */
 void angleAxisMatrix(double angle, const double axis[3], double R[9]);
 
-/** Throws nb2::Error (via fail) where the reference would throw or read out of bounds. */
-std::vector<Step> buildProgram(const Structure& in, const nb2_modifier* chain, int n_chain);
+/** The pass for modifier `m` on tool paths of structure `cur`.  Throws nb2::Error (via fail) where the reference would
+ *  throw or read out of bounds.  RasterOrganization decides on the poses themselves: it asks `probe`. */
+Step buildStep(const Structure& cur, const nb2_modifier& m, Probe* probe);
+void checkStructure(const Structure& s);
 }  // namespace mod
 }  // namespace nb2

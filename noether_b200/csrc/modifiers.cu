@@ -230,7 +230,7 @@ constexpr int kSignThreads = 256;
 __global__ void __launch_bounds__(kSignThreads) k_mod_path_sign(const double* __restrict__ poses,
                                                                 const unsigned* __restrict__ seg_off,
                                                                 const unsigned* __restrict__ path_off, unsigned n_paths,
-                                                                int* __restrict__ path_sign)
+                                                                int* __restrict__ path_sign, double* __restrict__ path_dir)
 {
   __shared__ double su[3][kSignThreads];
   const unsigned p = blockIdx.x;
@@ -274,7 +274,31 @@ __global__ void __launch_bounds__(kSignThreads) k_mod_path_sign(const double* __
     for (int i = 0; i < 16; ++i)
       F[i] = first[i];
     path_sign[p] = toolDragSign(F, dir) > 0.0 ? 1 : -1;
+    if (path_dir)
+    {
+      path_dir[3 * p] = dir.x;
+      path_dir[3 * p + 1] = dir.y;
+      path_dir[3 * p + 2] = dir.z;
+    }
   }
+}
+
+/** first and last translation of every segment (RasterOrganization decides on them, on the host) */
+__global__ void __launch_bounds__(256) k_mod_segment_ends(const double* __restrict__ poses, const unsigned* __restrict__ seg_off,
+                                                          unsigned n_segments, double* __restrict__ ends)
+{
+  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segments)
+    return;
+  const unsigned b = seg_off[s], e = seg_off[s + 1];
+  D3 a = { 0.0, 0.0, 0.0 }, z = { 0.0, 0.0, 0.0 };
+  if (e > b)
+  {
+    a = translationOf(poses, b);
+    z = translationOf(poses, e - 1);
+  }
+  ends[6 * s] = a.x, ends[6 * s + 1] = a.y, ends[6 * s + 2] = a.z;
+  ends[6 * s + 3] = z.x, ends[6 * s + 4] = z.y, ends[6 * s + 5] = z.z;
 }
 
 /** MovingAverageOrientationSmoothing, pass 1: Quaterniond(pose.linear()) of every input pose (fully parallel) */
@@ -445,6 +469,7 @@ const char* stageName(int kind)
     case NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING: return "moving average orientation smoothing";
     case NB2_MOD_CIRCULAR_LEAD_IN: return "circular lead in";
     case NB2_MOD_CIRCULAR_LEAD_OUT: return "circular lead out";
+    case NB2_MOD_RASTER_ORGANIZATION: return "raster organization";
   }
   return "modifier";
 }
@@ -536,22 +561,24 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
   cur.path_off.assign(in->path_offsets, in->path_offsets + in->n_paths + 1);
   cur.seg_off.assign(in->segment_offsets, in->segment_offsets + in->n_segments + 1);
   cur.path_plane.assign(in->path_plane, in->path_plane + in->n_paths);
-  const std::vector<Step> prog = buildProgram(cur, chain, n_chain);
+  checkStructure(cur);
+  if (n_chain < 0 || (n_chain > 0 && !chain))
+    fail(NB2_ERR_INVALID_ARGUMENT, "modifier chain is NULL");
+  for (int k = 0; k < n_chain; ++k)
+    if (chain[k].kind < NB2_MOD_SNAKE_ORGANIZATION || chain[k].kind > NB2_MOD_RASTER_ORGANIZATION)
+      fail(NB2_ERR_INVALID_ARGUMENT, "unknown modifier kind " + std::to_string(chain[k].kind));
 
-  uint64_t w_max = cur.waypoints();
-  for (const Step& st : prog)
-    w_max = std::max(w_max, st.out.waypoints());
   c->timer.begin(c->stream);
   double* buf[2] = { nullptr, nullptr };
   int at = 0;
   const uint64_t W0 = cur.waypoints();
-  if (w_max)
-  {
-    c->modPose[0].ensure(sizeof(double) * 16 * w_max);
-    c->modPose[1].ensure(sizeof(double) * 16 * w_max);
-    buf[0] = c->modPose[0].as<double>();
-    buf[1] = c->modPose[1].as<double>();
-  }
+  const uint64_t w_max = W0;
+  // a pose buffer is (re)sized when it becomes the destination of a pass: its old contents are dead by then
+  auto ensurePoses = [&](int which, uint64_t waypoints) {
+    c->modPose[which].ensure(sizeof(double) * 16 * std::max<uint64_t>(waypoints, 1));
+    buf[which] = c->modPose[which].as<double>();
+  };
+  ensurePoses(0, W0);
   uploadVector(c, c->modSegOff, cur.seg_off);
   if (W0)
   {
@@ -576,11 +603,45 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
     }
   }
 
-  bool smoothing = false;
-  for (const Step& st : prog)
+  // RasterOrganization looks at the poses: segment ends and the direction of tool path 0 come back from the device
+  struct DeviceProbe : Probe
   {
+    nb2_context* c;
+    double* const* buf;
+    const int* at;
+    void rasterInputs(const Structure& cur, std::vector<double>& seg_ends, double dir0[3]) override
+    {
+      const unsigned S = static_cast<unsigned>(cur.segments());
+      c->modEnds.ensure(sizeof(double) * (6ull * S + 8));
+      c->modPathSign.ensure(sizeof(int) * 4);
+      const std::vector<uint32_t> path0 = { cur.path_off[0], cur.path_off[1] };
+      uploadVector(c, c->modPathOff, path0);
+      double* d_dir = c->modEnds.as<double>() + 6ull * S;
+      k_mod_path_sign<<<1, kSignThreads, 0, c->stream>>>(buf[*at], c->modSegOff.as<unsigned>(), c->modPathOff.as<unsigned>(), 1u,
+                                                          c->modPathSign.as<int>(), d_dir);
+      NB2_CUDA(cudaGetLastError());
+      k_mod_segment_ends<<<(S + 255) / 256, 256, 0, c->stream>>>(buf[*at], c->modSegOff.as<unsigned>(), S, c->modEnds.as<double>());
+      NB2_CUDA(cudaGetLastError());
+      c->launches += 2;
+      seg_ends.resize(6ull * S + 3);
+      NB2_CUDA(cudaMemcpyAsync(seg_ends.data(), c->modEnds.ptr, sizeof(double) * (6ull * S + 3), cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaStreamSynchronize(c->stream));
+      for (int k = 0; k < 3; ++k)
+        dir0[k] = seg_ends[6ull * S + k];
+      seg_ends.resize(6ull * S);
+    }
+  } probe;
+  probe.c = c;
+  probe.buf = buf;
+  probe.at = &at;
+
+  bool smoothing = false;
+  for (int k = 0; k < n_chain; ++k)
+  {
+    const Step st = buildStep(cur, chain[k], &probe);
     if (st.device)
     {
+      ensurePoses(at ^ 1, st.out.waypoints());
       const unsigned W_in = static_cast<unsigned>(cur.waypoints());
       const unsigned S_in = static_cast<unsigned>(cur.segments());
       if (st.restructure)
@@ -595,7 +656,7 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
           uploadVector(c, c->modRot, st.rot);
           c->modPathSign.ensure(sizeof(int) * std::max(P, 1u));
           k_mod_path_sign<<<P, kSignThreads, 0, c->stream>>>(buf[at], c->modSegOff.as<unsigned>(),
-                                                               c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>());
+                                                               c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>(), nullptr);
           NB2_CUDA(cudaGetLastError());
           ++c->launches;
         }
@@ -615,7 +676,8 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
       {
         c->modQuat.ensure(sizeof(double4) * std::max(W_in, 1u));
         unsigned* flag = c->counters.as<unsigned>() + 17;
-        NB2_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
+        if (!smoothing)
+          NB2_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned), c->stream));
         k_mod_quaternions<<<(W_in + 255) / 256, 256, 0, c->stream>>>(buf[at], W_in, c->modQuat.as<double4>());
         NB2_CUDA(cudaGetLastError());
         ++c->launches;
@@ -634,7 +696,7 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
           uploadVector(c, c->modPathOff, cur.path_off);
           c->modPathSign.ensure(sizeof(int) * std::max(P, 1u));
           k_mod_path_sign<<<P, kSignThreads, 0, c->stream>>>(buf[at], c->modSegOff.as<unsigned>(),
-                                                               c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>());
+                                                               c->modPathOff.as<unsigned>(), P, c->modPathSign.as<int>(), nullptr);
           NB2_CUDA(cudaGetLastError());
           ++c->launches;
         }

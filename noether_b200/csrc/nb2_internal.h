@@ -242,6 +242,7 @@ struct nb2_context
   nb2::DevBuf modPathSign; // int32[P] tool-drag sign of every tool path
   nb2::DevBuf modPos, modNrm;  // float[3 W] compact input / float views of the output
   nb2::DevBuf modRot;          // double[18 n_points] step rotations of a circular lead, for either sign of a tool path
+  nb2::DevBuf modEnds;         // double[6 S + 3] first / last translation of every segment, direction of tool path 0
   nb2::DevBuf modQuat;         // double4[W] quaternions of the poses (MovingAverageOrientationSmoothing)
   // STL welding workspace (kernels_stl.cu)
   nb2::DevBuf stlSlots;      // uint32[slots] first corner of the point hashed to each slot

@@ -549,6 +549,13 @@ class SnakeOrganizationModifier(ToolPathModifier):
         return [_record(_capi.NB2_MOD_SNAKE_ORGANIZATION)]
 
 
+class RasterOrganizationModifier(ToolPathModifier):
+    """raster_organization_modifier.cpp:7-46"""
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_RASTER_ORGANIZATION)]
+
+
 class LinearApproachModifier(ToolPathModifier):
     """linear_approach_modifier.cpp:23-55"""
     _kind = _capi.NB2_MOD_LINEAR_APPROACH
@@ -746,6 +753,8 @@ class Factory:
         c = self._ctx
         if name == "SnakeOrganization":
             return SnakeOrganizationModifier(c)
+        if name == "RasterOrganization":
+            return RasterOrganizationModifier(c)
         if name in ("LinearApproach", "LinearDeparture"):
             cls = LinearApproachModifier if name == "LinearApproach" else LinearDepartureModifier
             return cls(_vec3(_member(config, "offset")), int(_member(config, "n_points")), c)

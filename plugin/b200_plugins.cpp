@@ -797,6 +797,7 @@ using Plugin_Concatenate = Plugin_DeviceToolPathModifier<NB2_MOD_CONCATENATE>;
 using Plugin_ToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_TOOL_DRAG_ORIENTATION>;
 using Plugin_BiasedToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION>;
 using Plugin_DirectionOfTravelOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION>;
+using Plugin_RasterOrganization = Plugin_DeviceToolPathModifier<NB2_MOD_RASTER_ORGANIZATION>;
 using Plugin_CircularLeadIn = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_IN>;
 using Plugin_CircularLeadOut = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_OUT>;
 using Plugin_MovingAverageOrientationSmoothing = Plugin_DeviceToolPathModifier<NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING>;
@@ -860,6 +861,7 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_Concatenate, Concatenate)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_ToolDragOrientation, ToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_BiasedToolDragOrientation, BiasedToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_DirectionOfTravelOrientation, DirectionOfTravelOrientation)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_RasterOrganization, RasterOrganization)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadIn, CircularLeadIn)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadOut, CircularLeadOut)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)

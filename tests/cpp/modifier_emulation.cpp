@@ -213,7 +213,9 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
     cur.path_off.assign(path_off, path_off + n_paths + 1);
     cur.seg_off.assign(seg_off, seg_off + n_segments + 1);
     cur.path_plane.assign(n_paths, -1);
-    const std::vector<Step> prog = buildProgram(cur, chain, n_chain);
+    checkStructure(cur);
+    if (n_chain < 0 || (n_chain > 0 && !chain))
+      fail(NB2_ERR_INVALID_ARGUMENT, "modifier chain is NULL");
     const uint64_t W0 = cur.waypoints();
     std::vector<double> a(16 * W0), b;
     if (poses16)
@@ -231,8 +233,37 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
           dir = p - fromFloat(positions + 3ull * (w - 1));
         createTransform(p, n, dir, post_ops_applied != 0, &a[16ull * w]);
       }
-    for (const Step& st : prog)
+    // k_mod_segment_ends + k_mod_path_sign(path 0) as the device probe runs them
+    struct HostProbe : Probe
     {
+      const std::vector<double>* poses;
+      void rasterInputs(const Structure& cur, std::vector<double>& ends, double dir0[3]) override
+      {
+        const std::vector<double>& P = *poses;
+        ends.assign(6 * cur.segments(), 0.0);
+        for (uint32_t s = 0; s < cur.segments(); ++s)
+          if (cur.seg_off[s + 1] > cur.seg_off[s])
+          {
+            const D3 f = tr(P, cur.seg_off[s]), l = tr(P, cur.seg_off[s + 1] - 1);
+            ends[6 * s] = f.x, ends[6 * s + 1] = f.y, ends[6 * s + 2] = f.z;
+            ends[6 * s + 3] = l.x, ends[6 * s + 4] = l.y, ends[6 * s + 5] = l.z;
+          }
+        D3 acc{ 0, 0, 0 };
+        unsigned count = 0;
+        for (uint32_t s = cur.path_off[0]; s < cur.path_off[1]; ++s)
+          for (uint32_t i = cur.seg_off[s]; i + 1 < cur.seg_off[s + 1]; ++i)
+          {
+            acc = acc + normalized(tr(P, i + 1) - tr(P, i));
+            ++count;
+          }
+        const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
+        dir0[0] = dir.x, dir0[1] = dir.y, dir0[2] = dir.z;
+      }
+    } probe;
+    for (int k = 0; k < n_chain; ++k)
+    {
+      probe.poses = &a;
+      const Step st = buildStep(cur, chain[k], &probe);
       if (st.device)
       {
         if (st.restructure)

@@ -110,6 +110,7 @@ def ragged_tool_paths(rng, n_paths=7):
 def all_inputs():
     rng = np.random.default_rng(0)
     return {
+        "shuffled grid": shuffled(raster_grid_tool_paths(5, 3, 8), 5),
         "identity": arbitrary_tool_paths(4, 2, 10),
         "random": arbitrary_tool_paths(4, 2, 10, rng),
         "grid": raster_grid_tool_paths(4, 2, 10),
@@ -151,6 +152,7 @@ MODIFIERS = {
                                   lambda: _rec(_capi.NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION, [0.1745, 0.025])),
     "DirectionOfTravelOrientation": (lambda p: p.direction_of_travel(),
                                      lambda: _rec(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)),
+    "RasterOrganization": (lambda p: p.raster_organization(), lambda: _rec(_capi.NB2_MOD_RASTER_ORGANIZATION)),
     "CircularLeadIn": (lambda p: p.circular_lead_in(1.571, 0.1, 5),   # the reference's test YAML (:18-25)
                        lambda: _rec(_capi.NB2_MOD_CIRCULAR_LEAD_IN, [1.571, 0.1], 5)),
     "CircularLeadOut": (lambda p: p.circular_lead_out(1.571, 0.1, 5),
@@ -169,7 +171,30 @@ CHAINS = [
     ["Offset", "BiasedToolDragOrientation", "FixedOrientationOblique", "Concatenate", "SnakeOrganization"],
     ["DirectionOfTravelOrientation", "MovingAverageOrientationSmoothing8", "LinearApproach", "MovingAverageOrientationSmoothing"],
     ["SnakeOrganization", "CircularLeadIn", "CircularLeadOut", "Offset", "CircularLeadIn2", "Concatenate"],
+    ["SnakeOrganization", "RasterOrganization", "LinearApproach", "Offset", "RasterOrganization", "SnakeOrganization"],
 ]
+
+
+def shuffled(nested, seed=0, waypoints=False):
+    """shuffle() of the reference's modifier tests (tool_path_modifier_utest.cpp:216-241): segment order inside every tool
+    path, the order of tool paths 1..n, and (here, as a snake pattern does) the direction of some segments of the tool
+    paths after the first — tool path 0 defines the reference direction"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k, path in enumerate(nested):
+        segs = [seg[::-1].copy() if k and rng.random() < 0.5 else seg.copy() for seg in path]
+        rng.shuffle(segs)
+        out.append(segs)
+    rest = out[1:]
+    rng.shuffle(rest)
+    return [out[0]] + rest
+
+
+def test_oracle_raster_organization_restores_the_grid():
+    """OrganizationModifiersTest (tool_path_modifier_utest.cpp:361-399): the shuffled raster grid comes back exactly"""
+    grid = raster_grid_tool_paths(4, 3, 10)
+    f = oracle_apply(shuffled(grid, 3), ["RasterOrganization"])
+    np.testing.assert_array_equal(f.pose, np.concatenate([seg for path in grid for seg in path]))
 
 
 def oracle_apply(nested, names):
