@@ -89,6 +89,7 @@ NB2_HD inline void rotatePlane(double* x, int xs, double* y, int ys, const Jacob
 {
   if (j.c == 1.0 && j.s == 0.0)
     return;
+#pragma unroll
   for (int i = 0; i < 4; ++i)
   {
     const double xi = x[i * xs], yi = y[i * ys];
@@ -130,7 +131,10 @@ NB2_HD inline void jacobiSvdFirstLeftVector(double M[16], double u0[4])
   while (!finished && sweeps++ < 64)  // (Eigen has no sweep limit; 64 is never reached on finite input)
   {
     finished = true;
+    // (both loops unrolled: every index below is then a constant and M, U stay in registers on the device)
+#pragma unroll
     for (int p = 1; p < 4; ++p)
+#pragma unroll
       for (int q = 0; q < p; ++q)
       {
         const double threshold = fmax(considerAsZero, precision * maxDiag);
@@ -175,43 +179,35 @@ NB2_HD inline void jacobiSvdFirstLeftVector(double M[16], double u0[4])
   }
   // singular values positive, then sorted in descending order (columns of U follow)
   double sv[4];
+#pragma unroll
   for (int i = 0; i < 4; ++i)
   {
     const double a = M[5 * i];
     sv[i] = fabs(a);
     if (a < 0.0)
+    {
+#pragma unroll
       for (int r = 0; r < 4; ++r)
         U[4 * r + i] = -U[4 * r + i];
-  }
-  for (int i = 0; i < 4; ++i)
-    sv[i] *= scale;
-  for (int i = 0; i < 4; ++i)
-  {
-    int pos = i;
-    double best = sv[i];
-    for (int k = i + 1; k < 4; ++k)
-      if (sv[k] > best)
-      {
-        best = sv[k];
-        pos = k;
-      }
-    if (best == 0.0)
-      break;
-    if (pos != i)
-    {
-      const double tsv = sv[i];
-      sv[i] = sv[pos];
-      sv[pos] = tsv;
-      for (int r = 0; r < 4; ++r)
-      {
-        const double tu = U[4 * r + i];
-        U[4 * r + i] = U[4 * r + pos];
-        U[4 * r + pos] = tu;
-      }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    sv[i] *= scale;
+  // Only column 0 of the sorted U is wanted: it is the column of the first largest singular value (the selection sort
+  // moves exactly that column to the front in its first step, or stops at once when every singular value is zero).
+  int pos = 0;
+  double best = sv[0];
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+    if (sv[k] > best)
+    {
+      best = sv[k];
+      pos = k;
+    }
+#pragma unroll
   for (int r = 0; r < 4; ++r)
-    u0[r] = U[4 * r];
+    u0[r] = pos == 0 ? U[4 * r] : (pos == 1 ? U[4 * r + 1] : (pos == 2 ? U[4 * r + 2] : U[4 * r + 3]));
 }
 
 /** computeQuaternionMean over `count` quaternions read through `get(k)` (k = 0 .. count - 1, window order).
