@@ -284,6 +284,10 @@ typedef enum nb2_modifier_kind
   NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION = 10, /* direction_of_travel_orientation_modifier.cpp:6-48 */
   NB2_MOD_RASTER_ORGANIZATION = 14,        /* raster_organization_modifier.cpp:7-46 (decided on the host from the first /
                                               last translation of every segment, read back from the device) */
+  NB2_MOD_JOIN_CLOSE_SEGMENTS = 15,        /* join_close_segments_modifier.cpp:11-39: v[0] = distance (offsets only: the merged
+                                              segments are already adjacent in memory) */
+  NB2_MOD_MINIMUM_SEGMENT_LENGTH = 16,     /* minimum_segment_length_modifier.cpp:12-37, computeLength utils.cpp:213-234:
+                                              v[0] = minimum_length */
   NB2_MOD_CIRCULAR_LEAD_IN = 12,           /* circular_lead_in_modifier.cpp:12-44: v[0] = arc_angle, v[1] = arc_radius, n_points */
   NB2_MOD_CIRCULAR_LEAD_OUT = 13,          /* circular_lead_out_modifier.cpp:12-44: v[0] = arc_angle, v[1] = arc_radius, n_points */
   NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING = 11 /* moving_average_orientation_smoothing_modifier.cpp:6-84:

@@ -9,7 +9,8 @@ from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionG
                       FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,
                       default_context, make_lattice,
-                      ToolPathModifier, SnakeOrganizationModifier, RasterOrganizationModifier, LinearApproachModifier, LinearDepartureModifier,
+                      ToolPathModifier, SnakeOrganizationModifier, RasterOrganizationModifier,
+                      JoinCloseSegmentsToolPathModifier, MinimumSegmentLengthToolPathModifier, LinearApproachModifier, LinearDepartureModifier,
                       OffsetModifier, FixedOrientationModifier, UniformOrientationModifier, ConcatenateModifier,
                       DirectionOfTravelOrientationModifier, MovingAverageOrientationSmoothingModifier,
                       CircularLeadInModifier, CircularLeadOutModifier,

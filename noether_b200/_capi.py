@@ -58,6 +58,8 @@ NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING = 11
 NB2_MOD_CIRCULAR_LEAD_IN = 12
 NB2_MOD_CIRCULAR_LEAD_OUT = 13
 NB2_MOD_RASTER_ORGANIZATION = 14
+NB2_MOD_JOIN_CLOSE_SEGMENTS = 15
+NB2_MOD_MINIMUM_SEGMENT_LENGTH = 16
 
 
 class Modifier(C.Structure):

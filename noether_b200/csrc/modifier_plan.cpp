@@ -305,6 +305,98 @@ Step buildStep(const Structure& cur, const nb2_modifier& m, Probe* probe)
         if (m.n_points < 0)
           fail(NB2_ERR_INVALID_ARGUMENT, "window_size must not be negative");
         break;
+      case NB2_MOD_JOIN_CLOSE_SEGMENTS:
+      {
+        st.device = false;  // the segments of a tool path are adjacent in memory: joining two of them drops an offset
+        bool any = false;
+        for (uint64_t p = 0; p < P; ++p)
+          any |= cur.path_off[p + 1] - cur.path_off[p] >= 2;
+        if (!any || cur.waypoints() == 0)
+          break;
+        for (uint64_t p = 0; p < P; ++p)
+          if (cur.path_off[p + 1] - cur.path_off[p] >= 2)
+            for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+              if (segLen(cur, s) == 0)
+                fail(NB2_ERR_INVALID_ARGUMENT, "empty tool path segment (front() / back() of an empty vector in the reference)");
+        if (!probe)
+          fail(NB2_ERR_INTERNAL, "JoinCloseSegments needs the poses");
+        std::vector<double> ends;
+        double dir0[3];
+        probe->rasterInputs(cur, ends, dir0);
+        Structure out;
+        out.path_off.assign(1, 0u);
+        out.seg_off.assign(1, 0u);
+        out.path_plane = cur.path_plane;
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+          {
+            bool joined = false;
+            if (s > cur.path_off[p])
+            {
+              // segment->back() is the last waypoint of the previous source segment, whether or not that one was merged
+              const D3 back = { ends[6 * (s - 1) + 3], ends[6 * (s - 1) + 4], ends[6 * (s - 1) + 5] };
+              const D3 front = { ends[6 * s], ends[6 * s + 1], ends[6 * s + 2] };
+              joined = norm(back - front) < m.v[0];
+            }
+            if (joined)
+              out.seg_off.back() = cur.seg_off[s + 1];
+            else
+              out.seg_off.push_back(cur.seg_off[s + 1]);
+          }
+          out.path_off.push_back(static_cast<uint32_t>(out.seg_off.size() - 1));
+        }
+        st.out = out;
+        break;
+      }
+      case NB2_MOD_MINIMUM_SEGMENT_LENGTH:
+      {
+        if (S == 0)
+        {
+          // (tool paths without segments are erased)
+          st.device = false;
+          st.out.path_off.assign(1, 0u);
+          st.out.path_plane.clear();
+          break;
+        }
+        for (uint64_t s = 0; s < S; ++s)
+          if (segLen(cur, static_cast<uint32_t>(s)) == 0)
+            fail(NB2_ERR_INVALID_ARGUMENT, "empty tool path segment (segment.size() - 1 wraps around in computeLength)");
+        if (!probe)
+          fail(NB2_ERR_INTERNAL, "MinimumSegmentLength needs the poses");
+        std::vector<double> lengths;
+        probe->segmentLengths(cur, lengths);
+        std::vector<std::pair<uint32_t, bool>> keep;
+        Structure kept;
+        kept.path_off.assign(1, 0u);
+        for (uint64_t p = 0; p < P; ++p)
+        {
+          const size_t before = keep.size();
+          for (uint32_t s = cur.path_off[p]; s < cur.path_off[p + 1]; ++s)
+            if (!(lengths[s] < m.v[0]))
+              keep.emplace_back(s, false);
+          if (keep.size() > before)
+          {
+            kept.path_off.push_back(static_cast<uint32_t>(keep.size()));
+            kept.path_plane.push_back(cur.path_plane[p]);
+          }
+        }
+        if (keep.size() == S)
+        {
+          // nothing is dropped; only tool paths that had no segment to begin with disappear
+          st.device = false;
+          Structure out = cur;
+          out.path_off = kept.path_off;
+          out.path_plane = kept.path_plane;
+          st.out = out;
+          break;
+        }
+        restructure(cur, keep, 0, 0, st);
+        st.out.path_off = kept.path_off;
+        st.out.path_plane = kept.path_plane;
+        st.device = true;  // (even when nothing is left: the executor handles an empty destination)
+        break;
+      }
       case NB2_MOD_RASTER_ORGANIZATION:
       {
         if (P == 0)

@@ -43,6 +43,8 @@ struct Probe
   /** translation of the first and of the last waypoint of every segment (6 doubles per segment; zeros for an empty
    *  segment) and estimateToolPathDirection of tool path 0 (utils.cpp:7-29) */
   virtual void rasterInputs(const Structure& cur, std::vector<double>& seg_ends, double dir0[3]) = 0;
+  /** polyline length of every segment: the chord lengths added up in waypoint order (computeLength, utils.cpp:213-234) */
+  virtual void segmentLengths(const Structure& cur, std::vector<double>& lengths) = 0;
 };
 
 /** Eigen::AngleAxisd(angle, axis).toRotationMatrix() for a unit axis, row-major (Eigen 3.4 Geometry/AngleAxis.h) */

@@ -283,6 +283,33 @@ __global__ void __launch_bounds__(kSignThreads) k_mod_path_sign(const double* __
   }
 }
 
+/** computeLength (utils.cpp:213-234) of every segment, one CTA each: the chord lengths of 256 steps on all warps, then
+ *  `length += d` in waypoint order by warp 0 (threads past the end stage +0: adding it is exact) */
+__global__ void __launch_bounds__(kSignThreads) k_mod_segment_lengths(const double* __restrict__ poses,
+                                                                      const unsigned* __restrict__ seg_off,
+                                                                      double* __restrict__ lengths)
+{
+  __shared__ double sd[kSignThreads];
+  const unsigned s = blockIdx.x, tid = threadIdx.x;
+  const unsigned b = seg_off[s], e = seg_off[s + 1];
+  double length = 0.0;
+  for (unsigned i0 = b; i0 + 1 < e; i0 += kSignThreads)
+  {
+    const unsigned i = i0 + tid;
+    sd[tid] = i + 1 < e ? norm(translationOf(poses, i + 1) - translationOf(poses, i)) : 0.0;
+    __syncthreads();
+    if (tid < 32)
+    {
+#pragma unroll 16
+      for (int k = 0; k < kSignThreads; ++k)
+        length += sd[k];
+    }
+    __syncthreads();
+  }
+  if (tid == 0)
+    lengths[s] = length;
+}
+
 /** first and last translation of every segment (RasterOrganization decides on them, on the host) */
 __global__ void __launch_bounds__(256) k_mod_segment_ends(const double* __restrict__ poses, const unsigned* __restrict__ seg_off,
                                                           unsigned n_segments, double* __restrict__ ends)
@@ -470,6 +497,8 @@ const char* stageName(int kind)
     case NB2_MOD_CIRCULAR_LEAD_IN: return "circular lead in";
     case NB2_MOD_CIRCULAR_LEAD_OUT: return "circular lead out";
     case NB2_MOD_RASTER_ORGANIZATION: return "raster organization";
+    case NB2_MOD_JOIN_CLOSE_SEGMENTS: return "join close segments";
+    case NB2_MOD_MINIMUM_SEGMENT_LENGTH: return "minimum segment length";
   }
   return "modifier";
 }
@@ -565,7 +594,7 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
   if (n_chain < 0 || (n_chain > 0 && !chain))
     fail(NB2_ERR_INVALID_ARGUMENT, "modifier chain is NULL");
   for (int k = 0; k < n_chain; ++k)
-    if (chain[k].kind < NB2_MOD_SNAKE_ORGANIZATION || chain[k].kind > NB2_MOD_RASTER_ORGANIZATION)
+    if (chain[k].kind < NB2_MOD_SNAKE_ORGANIZATION || chain[k].kind > NB2_MOD_MINIMUM_SEGMENT_LENGTH)
       fail(NB2_ERR_INVALID_ARGUMENT, "unknown modifier kind " + std::to_string(chain[k].kind));
 
   c->timer.begin(c->stream);
@@ -630,6 +659,17 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
         dir0[k] = seg_ends[6ull * S + k];
       seg_ends.resize(6ull * S);
     }
+    void segmentLengths(const Structure& cur, std::vector<double>& lengths) override
+    {
+      const unsigned S = static_cast<unsigned>(cur.segments());
+      c->modEnds.ensure(sizeof(double) * (6ull * S + 8));
+      k_mod_segment_lengths<<<S, kSignThreads, 0, c->stream>>>(buf[*at], c->modSegOff.as<unsigned>(), c->modEnds.as<double>());
+      NB2_CUDA(cudaGetLastError());
+      ++c->launches;
+      lengths.resize(S);
+      NB2_CUDA(cudaMemcpyAsync(lengths.data(), c->modEnds.ptr, sizeof(double) * S, cudaMemcpyDeviceToHost, c->stream));
+      NB2_CUDA(cudaStreamSynchronize(c->stream));
+    }
   } probe;
   probe.c = c;
   probe.buf = buf;
@@ -663,7 +703,8 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
         uploadVector(c, c->modSegMap, st.map);
         uploadVector(c, c->modSegOff, st.out.seg_off);  // stream-ordered after the kernels that read the old offsets
         const unsigned W_out = static_cast<unsigned>(st.out.waypoints());
-        k_mod_restructure<<<tiles(W_out), kTile, 0, c->stream>>>(buf[at], buf[at ^ 1], W_out, c->modSegMap.as<SegMap>(),
+        if (W_out)  // (MinimumSegmentLength may leave nothing)
+          k_mod_restructure<<<tiles(W_out), kTile, 0, c->stream>>>(buf[at], buf[at ^ 1], W_out, c->modSegMap.as<SegMap>(),
                                                                    c->modSegOff.as<unsigned>(),
                                                                    static_cast<unsigned>(st.out.segments()), st.v[0], st.v[1],
                                                                    st.v[2], st.n_points,

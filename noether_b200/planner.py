@@ -556,6 +556,28 @@ class RasterOrganizationModifier(ToolPathModifier):
         return [_record(_capi.NB2_MOD_RASTER_ORGANIZATION)]
 
 
+class JoinCloseSegmentsToolPathModifier(ToolPathModifier):
+    """join_close_segments_modifier.cpp:6-39"""
+
+    def __init__(self, distance: float, context: Context | None = None):
+        super().__init__(context)
+        self.distance = float(distance)
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_JOIN_CLOSE_SEGMENTS, [self.distance])]
+
+
+class MinimumSegmentLengthToolPathModifier(ToolPathModifier):
+    """minimum_segment_length_modifier.cpp:7-37"""
+
+    def __init__(self, minimum_length: float, context: Context | None = None):
+        super().__init__(context)
+        self.minimum_length = float(minimum_length)
+
+    def _records(self):
+        return [_record(_capi.NB2_MOD_MINIMUM_SEGMENT_LENGTH, [self.minimum_length])]
+
+
 class LinearApproachModifier(ToolPathModifier):
     """linear_approach_modifier.cpp:23-55"""
     _kind = _capi.NB2_MOD_LINEAR_APPROACH
@@ -755,6 +777,10 @@ class Factory:
             return SnakeOrganizationModifier(c)
         if name == "RasterOrganization":
             return RasterOrganizationModifier(c)
+        if name == "JoinCloseSegments":
+            return JoinCloseSegmentsToolPathModifier(float(_member(config, "distance")), c)
+        if name == "MinimumSegmentLength":
+            return MinimumSegmentLengthToolPathModifier(float(_member(config, "minimum_length")), c)
         if name in ("LinearApproach", "LinearDeparture"):
             cls = LinearApproachModifier if name == "LinearApproach" else LinearDepartureModifier
             return cls(_vec3(_member(config, "offset")), int(_member(config, "n_points")), c)

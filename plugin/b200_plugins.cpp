@@ -772,6 +772,12 @@ struct Plugin_DeviceToolPathModifier : public noether::Plugin<noether::ToolPathM
         m.v[0] = YAML::getMember<double>(config, "angle_offset");
         m.v[1] = YAML::getMember<double>(config, "tool_radius");
         break;
+      case NB2_MOD_JOIN_CLOSE_SEGMENTS:  // join_close_segments_modifier.cpp:55-59
+        m.v[0] = YAML::getMember<double>(config, "distance");
+        break;
+      case NB2_MOD_MINIMUM_SEGMENT_LENGTH:  // minimum_segment_length_modifier.cpp:53-58
+        m.v[0] = YAML::getMember<double>(config, "minimum_length");
+        break;
       case NB2_MOD_CIRCULAR_LEAD_IN:   // circular_lead_in_modifier.cpp:60-66
       case NB2_MOD_CIRCULAR_LEAD_OUT:  // circular_lead_out_modifier.cpp (same keys)
         m.v[0] = YAML::getMember<double>(config, "arc_angle");
@@ -798,6 +804,8 @@ using Plugin_ToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_TOOL_DR
 using Plugin_BiasedToolDragOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_BIASED_TOOL_DRAG_ORIENTATION>;
 using Plugin_DirectionOfTravelOrientation = Plugin_DeviceToolPathModifier<NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION>;
 using Plugin_RasterOrganization = Plugin_DeviceToolPathModifier<NB2_MOD_RASTER_ORGANIZATION>;
+using Plugin_JoinCloseSegments = Plugin_DeviceToolPathModifier<NB2_MOD_JOIN_CLOSE_SEGMENTS>;
+using Plugin_MinimumSegmentLength = Plugin_DeviceToolPathModifier<NB2_MOD_MINIMUM_SEGMENT_LENGTH>;
 using Plugin_CircularLeadIn = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_IN>;
 using Plugin_CircularLeadOut = Plugin_DeviceToolPathModifier<NB2_MOD_CIRCULAR_LEAD_OUT>;
 using Plugin_MovingAverageOrientationSmoothing = Plugin_DeviceToolPathModifier<NB2_MOD_MOVING_AVERAGE_ORIENTATION_SMOOTHING>;
@@ -862,6 +870,8 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_ToolDragOrientation, ToolD
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_BiasedToolDragOrientation, BiasedToolDragOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_DirectionOfTravelOrientation, DirectionOfTravelOrientation)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_RasterOrganization, RasterOrganization)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_JoinCloseSegments, JoinCloseSegments)
+EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MinimumSegmentLength, MinimumSegmentLength)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadIn, CircularLeadIn)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadOut, CircularLeadOut)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)

@@ -259,6 +259,18 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
         const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
         dir0[0] = dir.x, dir0[1] = dir.y, dir0[2] = dir.z;
       }
+      void segmentLengths(const Structure& cur, std::vector<double>& lengths) override
+      {
+        const std::vector<double>& P = *poses;
+        lengths.assign(cur.segments(), 0.0);
+        for (uint32_t s = 0; s < cur.segments(); ++s)
+        {
+          double length = 0.0;
+          for (uint32_t i = cur.seg_off[s]; i + 1 < cur.seg_off[s + 1]; ++i)
+            length += norm(tr(P, i + 1) - tr(P, i));
+          lengths[s] = length;
+        }
+      }
     } probe;
     for (int k = 0; k < n_chain; ++k)
     {

@@ -153,6 +153,13 @@ MODIFIERS = {
     "DirectionOfTravelOrientation": (lambda p: p.direction_of_travel(),
                                      lambda: _rec(_capi.NB2_MOD_DIRECTION_OF_TRAVEL_ORIENTATION)),
     "RasterOrganization": (lambda p: p.raster_organization(), lambda: _rec(_capi.NB2_MOD_RASTER_ORGANIZATION)),
+    "JoinCloseSegments": (lambda p: p.join_close_segments(1.0),   # the reference's test YAML (:37-38)
+                          lambda: _rec(_capi.NB2_MOD_JOIN_CLOSE_SEGMENTS, [1.0])),
+    "JoinCloseSegments3": (lambda p: p.join_close_segments(3.0), lambda: _rec(_capi.NB2_MOD_JOIN_CLOSE_SEGMENTS, [3.0])),
+    "MinimumSegmentLength": (lambda p: p.minimum_segment_length(1.0),   # the reference's test YAML (:49-50)
+                             lambda: _rec(_capi.NB2_MOD_MINIMUM_SEGMENT_LENGTH, [1.0])),
+    "MinimumSegmentLength7": (lambda p: p.minimum_segment_length(7.5),
+                              lambda: _rec(_capi.NB2_MOD_MINIMUM_SEGMENT_LENGTH, [7.5])),
     "CircularLeadIn": (lambda p: p.circular_lead_in(1.571, 0.1, 5),   # the reference's test YAML (:18-25)
                        lambda: _rec(_capi.NB2_MOD_CIRCULAR_LEAD_IN, [1.571, 0.1], 5)),
     "CircularLeadOut": (lambda p: p.circular_lead_out(1.571, 0.1, 5),
@@ -172,6 +179,7 @@ CHAINS = [
     ["DirectionOfTravelOrientation", "MovingAverageOrientationSmoothing8", "LinearApproach", "MovingAverageOrientationSmoothing"],
     ["SnakeOrganization", "CircularLeadIn", "CircularLeadOut", "Offset", "CircularLeadIn2", "Concatenate"],
     ["SnakeOrganization", "RasterOrganization", "LinearApproach", "Offset", "RasterOrganization", "SnakeOrganization"],
+    ["JoinCloseSegments", "MinimumSegmentLength", "LinearDeparture", "JoinCloseSegments3", "MinimumSegmentLength7", "SnakeOrganization"],
 ]
 
 

@@ -26,7 +26,7 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
                   # tool path modifiers that run on the device (plugins.cpp:182-199,219)
                   "SnakeOrganization", "LinearApproach", "LinearDeparture", "Offset", "FixedOrientation", "UniformOrientation",
                   "Concatenate", "ToolDragOrientation", "BiasedToolDragOrientation", "DirectionOfTravelOrientation",
-                  "MovingAverageOrientationSmoothing", "CircularLeadIn", "CircularLeadOut", "RasterOrganization",
+                  "MovingAverageOrientationSmoothing", "CircularLeadIn", "CircularLeadOut", "RasterOrganization", "JoinCloseSegments", "MinimumSegmentLength",
                   "CompoundToolPathModifier"):
         assert alias in exported
     # each plugin object sits in the ELF section boost_plugin_loader enumerates for its kind
