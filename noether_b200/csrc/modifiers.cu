@@ -746,6 +746,8 @@ int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* 
       at ^= 1;
       c->timer.mark(stageName(st.kind), c->stream);
     }
+    else if (st.out.seg_off != cur.seg_off)
+      uploadVector(c, c->modSegOff, st.out.seg_off);  // a bookkeeping-only pass that moved segment boundaries (JoinCloseSegments)
     cur = st.out;
   }
 

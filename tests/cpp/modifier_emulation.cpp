@@ -237,8 +237,11 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
     struct HostProbe : Probe
     {
       const std::vector<double>* poses;
-      void rasterInputs(const Structure& cur, std::vector<double>& ends, double dir0[3]) override
+      const Structure* dev;  // the probe kernels read the device copy of the segment offsets
+      void rasterInputs(const Structure& asked, std::vector<double>& ends, double dir0[3]) override
       {
+        Structure cur = asked;
+        cur.seg_off = dev->seg_off;
         const std::vector<double>& P = *poses;
         ends.assign(6 * cur.segments(), 0.0);
         for (uint32_t s = 0; s < cur.segments(); ++s)
@@ -259,8 +262,10 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
         const D3 dir = normalized(acc / static_cast<double>(static_cast<int>(count)));
         dir0[0] = dir.x, dir0[1] = dir.y, dir0[2] = dir.z;
       }
-      void segmentLengths(const Structure& cur, std::vector<double>& lengths) override
+      void segmentLengths(const Structure& asked, std::vector<double>& lengths) override
       {
+        Structure cur = asked;
+        cur.seg_off = dev->seg_off;
         const std::vector<double>& P = *poses;
         lengths.assign(cur.segments(), 0.0);
         for (uint32_t s = 0; s < cur.segments(); ++s)
@@ -272,18 +277,28 @@ int emu_modify(uint64_t n_paths, const uint32_t* path_off, uint64_t n_segments, 
         }
       }
     } probe;
+    // `dev` stands for what the device holds: its segment offsets change only where the executor uploads them
+    Structure dev = cur;
     for (int k = 0; k < n_chain; ++k)
     {
       probe.poses = &a;
+      probe.dev = &dev;
+      dev.path_off = cur.path_off;  // (uploaded by the executor whenever a kernel needs them)
+      dev.path_plane = cur.path_plane;
       const Step st = buildStep(cur, chain[k], &probe);
       if (st.device)
       {
         if (st.restructure)
-          runRestructure(st, cur, a, b);
+        {
+          runRestructure(st, dev, a, b);
+          dev.seg_off = st.out.seg_off;
+        }
         else
-          runMap(st, cur, a, b);
+          runMap(st, dev, a, b);
         a.swap(b);
       }
+      else if (st.out.seg_off != cur.seg_off)
+        dev.seg_off = st.out.seg_off;
       cur = st.out;
     }
     g_last.s = cur;
