@@ -400,7 +400,8 @@ Step buildStep(const Structure& cur, const nb2_modifier& m, Probe* probe)
       case NB2_MOD_RASTER_ORGANIZATION:
       {
         if (P == 0)
-          break;  // nothing to organise (the reference would read tool_paths.at(0))
+          fail(NB2_ERR_INVALID_ARGUMENT, "RasterOrganization on empty tool paths (vector::_M_range_check: tool_paths.at(0) in the "
+                                         "reference; RasterPlanner::plan returns before it gets there)");
         uint64_t steps = 0;
         for (uint32_t s = cur.path_off[0]; s < cur.path_off[1]; ++s)
           steps += segLen(cur, s) > 1 ? segLen(cur, s) - 1 : 0;

@@ -208,11 +208,7 @@ def test_fuzz_modifiers_and_stl(ctx, orc):
     for kind, first, count in _campaign():
         for seed in range(first, first + count):
             if kind == "mods":
-                rng = np.random.default_rng(52000 + seed)
-                nested = tm.ragged_tool_paths(rng, n_paths=int(rng.integers(1, 12)))
-                if rng.random() < 0.2:   # a one-waypoint segment somewhere: several modifiers must refuse it
-                    nested[int(rng.integers(len(nested)))].append(nested[0][0][:1].copy())
-                chain = [names[int(i)] for i in rng.integers(0, len(names), size=int(rng.integers(1, 7)))]
+                nested, chain = tm.random_case(seed)   # (a one-waypoint segment now and then: several modifiers refuse it)
                 ran += 1
                 try:
                     ref = tm.oracle_apply(nested, chain)

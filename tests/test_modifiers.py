@@ -433,6 +433,39 @@ def test_emulated_chains_match_oracle(emu, chain):
         assert_matches_oracle(emu_apply(emu, nested, chain), oracle_apply(nested, chain), f"{chain} on {key}")
 
 
+def random_case(seed):
+    """the `mods` kind of the fuzz campaign: ragged random tool paths, sometimes with a one-waypoint segment, and a random
+    chain of 1 - 6 modifiers"""
+    names = sorted(MODIFIERS)
+    rng = np.random.default_rng(52000 + seed)
+    nested = ragged_tool_paths(rng, n_paths=int(rng.integers(1, 12)))
+    if rng.random() < 0.2:
+        nested[int(rng.integers(len(nested)))].append(nested[0][0][:1].copy())
+    chain = [names[int(i)] for i in rng.integers(0, len(names), size=int(rng.integers(1, 7)))]
+    return nested, chain
+
+
+def test_emulated_random_chains_match_oracle(emu):
+    """the seeds the GPU campaign draws, replayed through the host emulation: same results and the same refusals"""
+    refused = 0
+    for seed in range(3000, 3250):
+        nested, chain = random_case(seed)
+        try:
+            ref = oracle_apply(nested, chain)
+        except Exception:
+            ref = None
+        try:
+            got = emu_apply(emu, nested, chain)
+        except _capi.Nb2Error:
+            got = None
+        assert (got is None) == (ref is None), f"seed {seed} {chain}: emulation {'refuses' if got is None else 'ok'}, oracle {'refuses' if ref is None else 'ok'}"
+        if got is None:
+            refused += 1
+        else:
+            assert_matches_oracle(got, ref, f"seed {seed} {chain}")
+    assert 0 < refused < 60
+
+
 def test_emulated_refusals(emu):
     single = [[np.eye(4)[None]]]
     for name, status in (("UniformOrientation", _capi.NB2_ERR_INVALID_ARGUMENT),
