@@ -157,6 +157,32 @@ int nb2_pca_rotated_direction(nb2_context* ctx, double rotation_angle, const dou
 int nb2_normals_from_mesh_faces(nb2_context* ctx, float* normals_out);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Face subdivision mesh modifiers applied to the resident mesh:
+ *   nb2_face_midpoint_subdivision  = FaceMidpointSubdivisionMeshModifier::modify (face_subdivision_modifier.cpp:202-248;
+ *                                    YAML key n_iterations, plugins.cpp:58): every triangle becomes 4^n triangles, one new
+ *                                    vertex per edge (shared between the triangles that meet there);
+ *   nb2_face_subdivision_by_area   = FaceSubdivisionByAreaMeshModifier::modify (:250-339; YAML key max_area,
+ *                                    plugins.cpp:59): a triangle whose area exceeds max_area gets a centroid vertex and
+ *                                    three children, recursively.
+ * A new vertex is a byte copy of the record of its first source whose x y z, normal_x/y/z (when the cloud has them) and
+ * rgba (offset_rgba >= 0: offset of the field "rgba", utils.cpp:119-133; -1 = none) are the mean of the sources
+ * (copyPointToEnd / updatePointData, :58-114).  Vertex numbers, record bytes and face order are exactly those of the
+ * reference's sequential depth-first walk.  The subdivided mesh replaces the resident one (same record layout; moments
+ * and PCA axes recomputed), so nb2_plan / nb2_normals_from_mesh_faces can follow without a host round trip; the shim
+ * reads it back with nb2_mesh_download_cloud + nb2_mesh_download_triangles (sizes in `info`).
+ * Refusals: n_iterations = 0 (never terminates in the reference) or beyond the 2^31 triangle limit of this path;
+ * a non-finite triangle area (NB2_ERR_NON_FINITE, "Triangle area is not finite", :332-333); a by-area subdivision that
+ * would exceed max_points points (0 = the 2^31 limit; the reference has no limit and would exhaust memory).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int nb2_face_midpoint_subdivision(nb2_context* ctx, uint32_t n_iterations, int32_t offset_rgba, nb2_mesh_file_info* info /* may be NULL */);
+int nb2_face_subdivision_by_area(nb2_context* ctx, float max_area, int32_t offset_rgba, uint64_t max_points,
+                                 nb2_mesh_file_info* info /* may be NULL */);
+/* Copy the resident cloud back: n_points records of point_step bytes (pcl::PCLPointCloud2::data). */
+int nb2_mesh_download_cloud(nb2_context* ctx, void* cloud_data);
+/* Record layout of the resident cloud; any pointer may be NULL. */
+int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_t* offset_xyz, int32_t* offset_normal);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Plane lattice (plane_slicer_raster_planner.cpp:556-586 and getDistancesToMinMaxCuts :460-501).  Pure host
  * arithmetic in double, restated with the reference's quirks (OBB centred on the mean, `else if` min/max update,
  * floored start offset, ceil'ed plane count).

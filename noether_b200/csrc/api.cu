@@ -1,6 +1,7 @@
 // C ABI of libnoether_b200.so (include/noether_b200.h): context, mesh ingest, PCA frame, planning, results.
 #include "host_math.h"
 #include "nb2_internal.h"
+#include "subdivide_ops.h"
 
 #include <algorithm>
 #include <cmath>
@@ -729,7 +730,8 @@ void nb2_context_destroy(nb2_context* c)
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
                      &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->modEnds, &c->stlSlots, &c->stlCorner,
-                     &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix })
+                     &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix, &c->subBlob[0], &c->subBlob[1], &c->subTri[0], &c->subTri[1], &c->subLevels,
+                     &c->subKeys, &c->subVals, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)
@@ -1141,6 +1143,124 @@ int nb2_mesh_download_triangles(nb2_context* c, uint32_t* triangles)
   if (c->F)
     NB2_CUDA(cudaMemcpyAsync(triangles, c->tri.ptr, sizeof(uint32_t) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
+  NB2_API_END
+}
+
+int nb2_mesh_download_cloud(nb2_context* c, void* cloud_data)
+{
+  NB2_API_BEGIN
+  if (!c || !cloud_data)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or cloud_data is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  NB2_CUDA(cudaMemcpyAsync(cloud_data, c->blob.ptr, c->V * c->rec_step, cudaMemcpyDeviceToHost, c->stream));
+  NB2_CUDA(cudaStreamSynchronize(c->stream));
+  NB2_API_END
+}
+
+int nb2_mesh_record_layout(const nb2_context* c, uint32_t* point_step, uint32_t* offset_xyz, int32_t* offset_normal)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  requireMesh(c);
+  if (point_step)
+    *point_step = c->rec_step;
+  if (offset_xyz)
+    *offset_xyz = c->rec_off_xyz;
+  if (offset_normal)
+    *offset_normal = c->rec_off_nrm;
+  NB2_API_END
+}
+
+/** the subdivided mesh (in subBlob[slot] / subTri[slot]) becomes the resident one: same ingest as an upload of
+ *  device-resident arrays (adopted in place, moments and PCA axes recomputed) */
+static void adoptSubdivided(nb2_context* c, int slot, uint64_t V, uint64_t F, const sub::Layout& L, nb2_mesh_file_info* info)
+{
+  nb2_mesh_view v{};
+  v.cloud_data = c->subBlob[slot].ptr;
+  v.n_points = V;
+  v.point_step = L.step;
+  v.offset_xyz = L.off_xyz;
+  v.offset_normal = L.off_nrm;
+  v.triangles = c->subTri[slot].as<uint32_t>();
+  v.n_triangles = F;
+  uploadImpl(c, &v, false);
+  if (info)
+  {
+    info->n_points = V;
+    info->n_triangles = F;
+    info->has_normals = L.off_nrm >= 0;
+    info->reserved_ = 0;
+  }
+}
+
+/** which of the two output slots the resident mesh does NOT live in; the layout of the resident cloud */
+static int subdivisionSetup(nb2_context* c, int32_t offset_rgba, sub::Layout* L)
+{
+  requireMesh(c);
+  if (c->rec_step == 0 || c->rec_step % 4)
+    fail(NB2_ERR_INVALID_ARGUMENT, "the resident cloud has no record layout");
+  if (offset_rgba >= 0 && static_cast<uint32_t>(offset_rgba) + 4 > c->rec_step)
+    fail(NB2_ERR_INVALID_ARGUMENT, "rgba field lies outside the point record");
+  *L = sub::Layout{ c->rec_step, c->rec_off_xyz, c->rec_off_nrm, offset_rgba };
+  if (c->checks_deferred || !c->tri_checked)
+  {
+    // mesh adopted from device memory (e.g. the output of a previous subdivision): make sure its indices are in range
+    // before they are used as addresses
+    NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, sizeof(unsigned), c->stream));
+    launchValidateTriangles(c);
+    c->hostSmall.ensure(4096);
+    unsigned* h = c->hostSmall.as<unsigned>();
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->F && h[0] >= c->V)
+      fail(NB2_ERR_INVALID_ARGUMENT, "triangle references vertex " + std::to_string(h[0]) + " but the cloud has " +
+                                         std::to_string(c->V) + " points");
+    c->tri_checked = true;
+  }
+  return (c->blob.ptr == c->subBlob[0].ptr || c->tri.ptr == c->subTri[0].ptr) ? 1 : 0;
+}
+
+int nb2_face_midpoint_subdivision(nb2_context* c, uint32_t n_iterations, int32_t offset_rgba, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  if (n_iterations < 1 || n_iterations > static_cast<uint32_t>(sub::kMaxIterations))
+    fail(NB2_ERR_INVALID_ARGUMENT, "FaceMidpointSubdivision: n_iterations must be between 1 and " +
+                                       std::to_string(sub::kMaxIterations) + " (0 never terminates in the reference)");
+  sub::Layout L{};
+  int slot = 0;
+  uint64_t V = 0, F = 0;
+  {
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    slot = subdivisionSetup(c, offset_rgba, &L);
+    launchMidpointSubdivision(c, L, static_cast<int>(n_iterations), slot, &V, &F);
+  }
+  adoptSubdivided(c, slot, V, F, L, info);
+  NB2_API_END
+}
+
+int nb2_face_subdivision_by_area(nb2_context* c, float max_area, int32_t offset_rgba, uint64_t max_points, nb2_mesh_file_info* info)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  if (!(max_area == max_area))
+    fail(NB2_ERR_INVALID_ARGUMENT, "FaceSubdivisionByArea: max_area is NaN");
+  sub::Layout L{};
+  int slot = 0;
+  uint64_t V = 0, F = 0;
+  {
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    slot = subdivisionSetup(c, offset_rgba, &L);
+    launchAreaSubdivision(c, L, max_area, max_points, slot, &V, &F);
+  }
+  adoptSubdivided(c, slot, V, F, L, info);
   NB2_API_END
 }
 

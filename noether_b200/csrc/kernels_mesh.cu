@@ -385,7 +385,9 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
   c->frame.ensure(sizeof(FrameDev));
   // normals stay where they are: the slicer gathers the few it needs straight from the cloud (off_nrm is recorded by
   // the caller in nrm_base / nrm_stride)
-  (void)off_nrm;
+  c->rec_step = point_step;
+  c->rec_off_xyz = off_xyz;
+  c->rec_off_nrm = off_nrm;
   k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
                                                            c->pos.as<float4>(),
                                                            c->partials.as<MomentPartial>(), c->counters.as<unsigned>(),

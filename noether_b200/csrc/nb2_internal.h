@@ -250,6 +250,20 @@ struct nb2_context
   nb2::DevBuf stlFlag;       // uint32[3 T + 1] first-occurrence flags, later per-facet keep flags
   nb2::DevBuf stlPrefix;     // uint32[3 T + 1]
   nb2::DevBuf stlKeepPrefix; // uint32[T + 1]
+  // face subdivision (kernels_subdivide.cu): the subdivided cloud / triangles ping-pong between two slots, because the
+  // resident mesh (blob / tri adopt them in place) is the input of the next subdivision
+  nb2::DevBuf subBlob[2], subTri[2];
+  nb2::DevBuf subLevels;    // uint32[3 * triangles of levels 2 .. n] of the midpoint scheme
+  nb2::DevBuf subKeys;      // uint64[slots] edge keys of the level being resolved
+  nb2::DevBuf subVals;      // uint32[slots] smallest request sequence number of each edge
+  nb2::DevBuf subReq;       // uint32[3 * triangles of the level] slot of every request
+  nb2::DevBuf subNodeCnt, subNodeBase;  // uint32[nodes + 1] vertices created by every tree node (pre-order), their prefix
+  nb2::DevBuf subNodeMask;  // uint8[nodes] which of the node's three requests create a vertex
+  nb2::DevBuf subFresh;     // centroid records of the by-area sweep in creation order
+  nb2::DevBuf subRank;      // uint32[centroids] final number of each
+  // record layout of the resident cloud (set by every ingest)
+  uint32_t rec_step = 0, rec_off_xyz = 0;
+  int32_t rec_off_nrm = -1;
   // normals workspace
   nb2::DevBuf faceNrm;   // float4[F]
   nb2::DevBuf valence;   // uint32[V + 1]
@@ -343,6 +357,14 @@ void launchValidateTriangles(nb2_context* c);
 void launchPlyDecode(nb2_context* c, const PlyLayout& L);
 // binary STL image in c->fileImg -> welded mesh in c->blob (16-byte records {x y z 0}) and c->tri (kernels_stl.cu)
 void launchStlDecode(nb2_context* c, uint64_t n_facets, uint64_t* n_points_out, uint64_t* n_kept_out);
+// face subdivision of the resident mesh into subBlob[slot] / subTri[slot] (kernels_subdivide.cu); both synchronise
+namespace sub
+{
+struct Layout;
+}
+void launchMidpointSubdivision(nb2_context* c, const sub::Layout& L, int n_iterations, int slot, uint64_t* n_points, uint64_t* n_triangles);
+void launchAreaSubdivision(nb2_context* c, const sub::Layout& L, float max_area, uint64_t max_points, int slot, uint64_t* n_points,
+                           uint64_t* n_triangles);
 // single-pass decoupled look-back exclusive scan (kernels_normals.cu)
 void launchScanU32(nb2_context* c, const unsigned* in, unsigned* out, unsigned long long n);
 

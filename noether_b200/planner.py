@@ -106,6 +106,32 @@ class Context:
         _capi.check(self._lib.nb2_mesh_download_triangles(self._h, tri.ctypes.data))
         return tri
 
+    def download_cloud(self, n_vertices: int) -> np.ndarray:
+        """the resident cloud as PCLPointCloud2::data (n_vertices records of point_step bytes)"""
+        step, ox, on = self.record_layout()
+        data = np.zeros(n_vertices * step, np.uint8)
+        _capi.check(self._lib.nb2_mesh_download_cloud(self._h, data.ctypes.data))
+        return data
+
+    def record_layout(self) -> tuple[int, int, int]:
+        step, ox, on = C.c_uint32(), C.c_uint32(), C.c_int32()
+        _capi.check(self._lib.nb2_mesh_record_layout(self._h, C.byref(step), C.byref(ox), C.byref(on)))
+        return step.value, ox.value, on.value
+
+    def face_midpoint_subdivision(self, n_iterations: int, off_rgba: int = -1) -> _capi.MeshFileInfo:
+        """nb2_face_midpoint_subdivision on the resident mesh; the subdivided mesh becomes the resident one"""
+        self._mesh_key = None
+        info = _capi.MeshFileInfo()
+        _capi.check(self._lib.nb2_face_midpoint_subdivision(self._h, int(n_iterations), int(off_rgba), C.byref(info)))
+        return info
+
+    def face_subdivision_by_area(self, max_area: float, off_rgba: int = -1, max_points: int = 0) -> _capi.MeshFileInfo:
+        """nb2_face_subdivision_by_area on the resident mesh; the subdivided mesh becomes the resident one"""
+        self._mesh_key = None
+        info = _capi.MeshFileInfo()
+        _capi.check(self._lib.nb2_face_subdivision_by_area(self._h, float(max_area), int(off_rgba), int(max_points), C.byref(info)))
+        return info
+
     def set_normals(self, normals: np.ndarray):
         n = np.ascontiguousarray(normals, dtype=np.float32)
         _capi.check(self._lib.nb2_mesh_set_normals(self._h, n.ctypes.data))
@@ -509,6 +535,50 @@ class NormalsFromMeshFacesMeshModifier:
         return [out]
 
 
+class _FaceSubdivisionBase:
+    """Common part of the face subdivision mesh modifiers (face_subdivision_modifier.cpp): upload, subdivide on the
+    device, read the new cloud (same fields as the input, utils.cpp copyPointToEnd) and triangle list back.
+    `off_rgba` is the byte offset of the cloud's "rgba" field (-1: the cloud has none)."""
+
+    def __init__(self, context: Context | None = None, off_rgba: int = -1):
+        self._ctx = context
+        self._off_rgba = off_rgba
+
+    def _run(self, ctx: Context) -> _capi.MeshFileInfo:
+        raise NotImplementedError
+
+    def modify(self, mesh: MeshBlob) -> list[MeshBlob]:
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh, force=True)
+        info = self._run(ctx)
+        data = ctx.download_cloud(info.n_points)
+        tri = ctx.download_triangles(info.n_triangles)
+        return [MeshBlob(data, int(info.n_points), mesh.point_step, mesh.off_xyz, mesh.off_normal, tri)]
+
+
+class FaceMidpointSubdivisionMeshModifier(_FaceSubdivisionBase):
+    """face_subdivision_modifier.cpp:202-248 (plugin alias FaceMidpointSubdivision, YAML key n_iterations)."""
+
+    def __init__(self, n_iterations: int = 1, context: Context | None = None, off_rgba: int = -1):
+        super().__init__(context, off_rgba)
+        self.n_iterations = n_iterations
+
+    def _run(self, ctx):
+        return ctx.face_midpoint_subdivision(self.n_iterations, self._off_rgba)
+
+
+class FaceSubdivisionByAreaMeshModifier(_FaceSubdivisionBase):
+    """face_subdivision_modifier.cpp:250-339 (plugin alias FaceSubdivisionByArea, YAML key max_area)."""
+
+    def __init__(self, max_area: float, context: Context | None = None, off_rgba: int = -1, max_points: int = 0):
+        super().__init__(context, off_rgba)
+        self.max_area = max_area
+        self.max_points = max_points
+
+    def _run(self, ctx):
+        return ctx.face_subdivision_by_area(self.max_area, self._off_rgba, self.max_points)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # tool path modifiers on the device (noether_tpp/src/tool_path_modifiers/; nb2_result_modify)
 # ---------------------------------------------------------------------------------------------------------------------
@@ -810,5 +880,9 @@ class Factory:
         name = _member(config, "name")
         if name == "NormalsFromMeshFaces":
             return NormalsFromMeshFacesMeshModifier(self._ctx)
+        if name == "FaceMidpointSubdivision":  # n_iterations is read as a float and cast (face_subdivision_modifier.cpp:357)
+            return FaceMidpointSubdivisionMeshModifier(int(float(_member(config, "n_iterations"))), self._ctx)
+        if name == "FaceSubdivisionByArea":    # :371
+            return FaceSubdivisionByAreaMeshModifier(float(_member(config, "max_area")), self._ctx)
         raise RuntimeError(f"Failed to find plugin '{name}' in section 'mesh'")
 

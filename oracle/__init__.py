@@ -122,6 +122,16 @@ def lib():
     L.orc_mesh_export.restype = None
     L.orc_mesh_free.argtypes = [C.c_void_p]
     L.orc_mesh_free.restype = None
+    for n in ("orc_face_midpoint_subdivision", "orc_face_subdivision_by_area"):
+        getattr(L, n).argtypes = ([C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, u32p, C.c_uint64]
+                                  + ([C.c_uint32] if "midpoint" in n else [C.c_float, C.c_uint64]) + [C.POINTER(C.c_void_p)])
+    for n in ("orc_submesh_num_points", "orc_submesh_num_triangles"):
+        getattr(L, n).argtypes = [C.c_void_p]
+        getattr(L, n).restype = C.c_uint64
+    L.orc_submesh_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_submesh_export.restype = None
+    L.orc_submesh_free.argtypes = [C.c_void_p]
+    L.orc_submesh_free.restype = None
     L.orc_fixture_random_transform.argtypes = [C.c_double, C.c_double, f64p]
     L.orc_fixture_random_transform.restype = None
     L.orc_fixture_plane_mesh.argtypes = [C.c_float, C.c_float, f64p, f32p, f32p, u32p]
@@ -490,3 +500,32 @@ def read_ply(data: bytes):
     finally:
         lib().orc_mesh_free(h)
     return xyz, nrm, fs, idx
+
+
+def _subdivide(call, cloud, point_step, off_xyz, off_normal, off_rgba, tri, *args):
+    blob = np.ascontiguousarray(np.frombuffer(bytes(cloud), dtype=np.uint8))
+    n = blob.size // point_step
+    t, tp = _u32(np.asarray(tri).reshape(-1, 3))
+    h = C.c_void_p()
+    _check(call(blob.ctypes.data, n, point_step, off_xyz, off_normal, off_rgba, tp, t.shape[0], *args, C.byref(h)))
+    try:
+        nv, nf = lib().orc_submesh_num_points(h), lib().orc_submesh_num_triangles(h)
+        out = np.zeros(nv * point_step, np.uint8)
+        idx = np.zeros((nf, 3), np.uint32)
+        lib().orc_submesh_export(h, out.ctypes.data, idx.ctypes.data)
+    finally:
+        lib().orc_submesh_free(h)
+    return out, idx
+
+
+def face_midpoint_subdivision(cloud, point_step, off_xyz, off_normal, off_rgba, tri, n_iterations):
+    """FaceMidpointSubdivisionMeshModifier::modify (face_subdivision_modifier.cpp:202-248) on a raw PCLPointCloud2 blob:
+    returns (new blob uint8, triangles uint32 (F', 3))."""
+    return _subdivide(lib().orc_face_midpoint_subdivision, cloud, point_step, off_xyz, off_normal, off_rgba, tri,
+                      int(n_iterations))
+
+
+def face_subdivision_by_area(cloud, point_step, off_xyz, off_normal, off_rgba, tri, max_area, max_points=0):
+    """FaceSubdivisionByAreaMeshModifier::modify (face_subdivision_modifier.cpp:250-339)."""
+    return _subdivide(lib().orc_face_subdivision_by_area, cloud, point_step, off_xyz, off_normal, off_rgba, tri,
+                      C.c_float(max_area), int(max_points))

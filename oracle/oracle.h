@@ -43,6 +43,7 @@ extern "C" {
 #define ORC_ERR_CLOSED_LOOP 7         /* intent mode: cut lines forming a cycle */
 #define ORC_ERR_TOO_FEW_POINTS 8
 #define ORC_ERR_SEGMENT_TOO_SHORT 9 /* uniform_spacing_modifier.cpp:20-21 */
+#define ORC_ERR_NON_FINITE 10       /* face_subdivision_modifier.cpp:332-333 */
 
 const char* orc_last_error(void);
 
@@ -169,6 +170,21 @@ int orc_mesh_has_normals(const orc_mesh* m);
 /* any pointer may be NULL: xyz / nrm 3 floats per vertex, face_size one entry per face, index the concatenated ids */
 void orc_mesh_export(const orc_mesh* m, float* xyz, float* nrm, uint32_t* face_size, uint32_t* index);
 void orc_mesh_free(orc_mesh* m);
+
+/* ---- face subdivision mesh modifiers (face_subdivision_modifier.cpp, oracle_subdivide.cpp): the cloud is the raw
+ *      PCLPointCloud2::data (n_points records of point_step bytes; offsets of x, normal_x (-1 = none), rgba (-1 = none)),
+ *      the faces are triangles.  The result is a handle: new cloud (same record layout, more records) + triangles ---- */
+int orc_face_midpoint_subdivision(const uint8_t* cloud, uint64_t n_points, uint32_t point_step, uint32_t off_xyz, int32_t off_normal,
+                                  int32_t off_rgba, const uint32_t* triangles, uint64_t n_triangles, uint32_t n_iterations,
+                                  void** out); /* :202-248 */
+/* max_points: stop with ORC_ERR_INVALID once the cloud would grow beyond it (0 = no limit; the reference has none) */
+int orc_face_subdivision_by_area(const uint8_t* cloud, uint64_t n_points, uint32_t point_step, uint32_t off_xyz, int32_t off_normal,
+                                 int32_t off_rgba, const uint32_t* triangles, uint64_t n_triangles, float max_area,
+                                 uint64_t max_points, void** out); /* :250-339 */
+uint64_t orc_submesh_num_points(const void* h);
+uint64_t orc_submesh_num_triangles(const void* h);
+void orc_submesh_export(const void* h, uint8_t* cloud, uint32_t* triangles); /* either may be NULL */
+void orc_submesh_free(void* h);
 
 /* ---- restated test fixtures ---- */
 /* createRandomTransform(translation_limit, rotation_limit): tool_path_planner_utest.cpp:32-46 (std::mt19937(0)) */
