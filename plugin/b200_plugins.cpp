@@ -11,6 +11,8 @@
 //   PCARotated            dg       Plugin_PCARotatedDirectionGenerator    src/plugins.cpp:91-107
 //   Centroid              og       CentroidOriginGenerator                src/plugins.cpp:111
 //   NormalsFromMeshFaces  mesh     NormalsFromMeshFacesMeshModifier       src/plugins.cpp:62
+//   FaceMidpointSubdivision mesh   FaceMidpointSubdivisionMeshModifier    src/plugins.cpp:58
+//   FaceSubdivisionByArea mesh     FaceSubdivisionByAreaMeshModifier      src/plugins.cpp:59
 //
 // Built against the real headers inside a noether workspace (plugin/CMakeLists.txt).  In the development image those
 // packages do not exist; there the file is compiled against plugin/compat/ (minimal stand-ins declaring the same
@@ -585,6 +587,78 @@ public:
   }
 };
 
+/** The face subdivision mesh modifiers (face_subdivision_modifier.cpp:202-339) on the GPU: the mesh is subdivided where it
+ *  is resident and read back once — a cloud with the input's fields (new records are copies of their first source with
+ *  x y z / normals / rgba averaged) and 3-vertex polygons in the reference's depth-first order. */
+class FaceSubdivisionOnDevice : public noether::MeshModifier
+{
+public:
+  std::vector<pcl::PolygonMesh> modify(const pcl::PolygonMesh& mesh) const override final
+  {
+    std::int32_t offset_rgba = -1;  // has_color = the cloud has a field called "rgba" (:223,267)
+    for (const pcl::PCLPointField& f : mesh.cloud.fields)
+      if (f.name == "rgba")
+        offset_rgba = static_cast<std::int32_t>(f.offset);
+    std::vector<pcl::PolygonMesh> result(1);
+    pcl::PolygonMesh& output = result.front();
+    output.header = mesh.header;
+    output.cloud = mesh.cloud;  // fields, point_step, flags; the data is replaced below
+    std::vector<std::uint32_t> tri;
+    nb2_mesh_file_info info{};
+    {
+      Device& dev = Device::instance();
+      std::lock_guard<std::mutex> lock(dev.mutex());
+      ensureResident(dev, mesh, false);
+      dev.resident.valid = false;  // the context holds the subdivided mesh from here on
+      Device::check(subdivide(dev.ctx(), offset_rgba, &info));
+      output.cloud.data.resize(info.n_points * mesh.cloud.point_step);
+      tri.resize(3 * info.n_triangles);
+      Device::check(nb2_mesh_download_cloud(dev.ctx(), output.cloud.data.data()));
+      if (info.n_triangles)
+        Device::check(nb2_mesh_download_triangles(dev.ctx(), tri.data()));
+    }
+    // the flattened cloud of the reference (:218-220,241 / :262-264,305)
+    output.cloud.height = 1;
+    output.cloud.width = static_cast<std::uint32_t>(info.n_points);
+    output.cloud.row_step = output.cloud.width * output.cloud.point_step;
+    output.polygons.resize(info.n_triangles);
+    forChunks(info.n_triangles, [&](std::size_t, std::size_t b, std::size_t e) {
+      for (std::size_t f = b; f < e; ++f)
+        output.polygons[f].vertices = { tri[3 * f], tri[3 * f + 1], tri[3 * f + 2] };
+    });
+    return result;
+  }
+
+protected:
+  virtual int subdivide(nb2_context* ctx, std::int32_t offset_rgba, nb2_mesh_file_info* info) const = 0;
+};
+
+class FaceMidpointSubdivisionMeshModifier : public FaceSubdivisionOnDevice
+{
+public:
+  explicit FaceMidpointSubdivisionMeshModifier(unsigned n_iterations = 1) : n_iterations_(n_iterations) {}
+
+protected:
+  int subdivide(nb2_context* ctx, std::int32_t offset_rgba, nb2_mesh_file_info* info) const override
+  {
+    return nb2_face_midpoint_subdivision(ctx, n_iterations_, offset_rgba, info);
+  }
+  unsigned n_iterations_;
+};
+
+class FaceSubdivisionByAreaMeshModifier : public FaceSubdivisionOnDevice
+{
+public:
+  explicit FaceSubdivisionByAreaMeshModifier(float max_area) : max_area_(max_area) {}
+
+protected:
+  int subdivide(nb2_context* ctx, std::int32_t offset_rgba, nb2_mesh_file_info* info) const override
+  {
+    return nb2_face_subdivision_by_area(ctx, max_area_, offset_rgba, 0, info);
+  }
+  float max_area_;
+};
+
 // ---------------------------------------------------------------------------------------------------------------------
 // tool path modifiers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -708,6 +782,26 @@ struct Plugin_NormalsFromMeshFacesMeshModifier : public noether::Plugin<noether:
                                                 std::shared_ptr<const noether::Factory> /*factory*/) const override final
   {
     return std::make_unique<NormalsFromMeshFacesMeshModifier>();
+  }
+};
+
+/** FaceMidpointSubdivision: YAML key n_iterations, read as a float and cast (face_subdivision_modifier.cpp:354-359) */
+struct Plugin_FaceMidpointSubdivisionMeshModifier : public noether::Plugin<noether::MeshModifier>
+{
+  std::unique_ptr<noether::MeshModifier> create(const YAML::Node& config,
+                                                std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<FaceMidpointSubdivisionMeshModifier>(static_cast<unsigned>(YAML::getMember<float>(config, "n_iterations")));
+  }
+};
+
+/** FaceSubdivisionByArea: YAML key max_area (face_subdivision_modifier.cpp:368-373) */
+struct Plugin_FaceSubdivisionByAreaMeshModifier : public noether::Plugin<noether::MeshModifier>
+{
+  std::unique_ptr<noether::MeshModifier> create(const YAML::Node& config,
+                                                std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<FaceSubdivisionByAreaMeshModifier>(YAML::getMember<float>(config, "max_area"));
   }
 };
 
@@ -877,6 +971,8 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadOut, CircularL
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
+EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceMidpointSubdivisionMeshModifier, FaceMidpointSubdivision)
+EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceSubdivisionByAreaMeshModifier, FaceSubdivisionByArea)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PCARotatedDirectionGenerator, PCARotated)
 EXPORT_ORIGIN_GENERATOR_PLUGIN(noether_b200::Plugin_CentroidOriginGenerator, Centroid)

@@ -95,6 +95,13 @@ inline double Node::as<double>() const
   return std::stod(data_->scalar);
 }
 template <>
+inline float Node::as<float>() const
+{
+  if (!data_)
+    throw std::runtime_error("bad conversion");
+  return std::stof(data_->scalar);
+}
+template <>
 inline int Node::as<int>() const
 {
   if (!data_)

@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -764,6 +765,97 @@ void testToolPathModifiers(const noether::Factory& factory)
   }
 }
 
+/** FaceMidpointSubdivision / FaceSubdivisionByArea through the plugin boundary, with the YAML of the reference's own test
+ *  (mesh_modifier_utest.cpp:20-23: n_iterations 2, max_area 0.01): fields retained (:104-113), 4^n faces, one new vertex
+ *  per edge and iteration, every kept triangle within the area limit, surface area unchanged, and a plan on the output. */
+void testFaceSubdivision(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[MeshModifier FaceMidpointSubdivision / FaceSubdivisionByArea]\n");
+  unsigned off_xyz = 0;
+  for (const auto& g : mesh.cloud.fields)
+    if (g.name == "x")
+      off_xyz = g.offset;
+  auto point = [&](const pcl::PolygonMesh& m, std::uint32_t i) {
+    float p[3];
+    std::memcpy(p, m.cloud.data.data() + static_cast<std::size_t>(i) * m.cloud.point_step + off_xyz, 12);
+    return Eigen::Vector3d(p[0], p[1], p[2]);
+  };
+  auto faceArea = [&](const pcl::PolygonMesh& m, const pcl::Vertices& f) {
+    const Eigen::Vector3d a = point(m, f.vertices[0]), b = point(m, f.vertices[1]), c = point(m, f.vertices[2]);
+    const Eigen::Vector3d u(b.x() - a.x(), b.y() - a.y(), b.z() - a.z()), v(c.x() - a.x(), c.y() - a.y(), c.z() - a.z());
+    const Eigen::Vector3d n(u.y() * v.z() - u.z() * v.y(), u.z() * v.x() - u.x() * v.z(), u.x() * v.y() - u.y() * v.x());
+    return 0.5 * norm(n);
+  };
+  auto totalArea = [&](const pcl::PolygonMesh& m) {
+    double s = 0;
+    for (const auto& f : m.polygons)
+      s += faceArea(m, f);
+    return s;
+  };
+  auto checkCommon = [&](const pcl::PolygonMesh& m) {
+    CHECK(m.cloud.height == 1 && m.cloud.point_step == mesh.cloud.point_step);
+    CHECK(m.cloud.data.size() == static_cast<std::size_t>(m.cloud.point_step) * m.cloud.width);
+    CHECK(m.cloud.row_step == m.cloud.width * m.cloud.point_step);
+    CHECK(m.cloud.fields.size() == mesh.cloud.fields.size());
+    for (const auto& f : mesh.cloud.fields)
+    {
+      bool found = false;
+      for (const auto& g : m.cloud.fields)
+        found = found || (g.name == f.name && g.datatype == f.datatype && g.count == f.count && g.offset == f.offset);
+      CHECK(found);
+    }
+    // the input's records come first, untouched
+    CHECK(std::memcmp(m.cloud.data.data(), mesh.cloud.data.data(), mesh.cloud.data.size()) == 0);
+    std::uint32_t top = 0;
+    for (const auto& f : m.polygons)
+    {
+      CHECK(f.vertices.size() == 3);
+      for (auto v : f.vertices)
+        top = std::max<std::uint32_t>(top, v);
+    }
+    CHECK(top + 1 == m.cloud.width);  // every new vertex is referenced
+    CHECK(std::abs(totalArea(m) - totalArea(mesh)) < 1e-3 * totalArea(mesh));
+  };
+  std::size_t edges = 0;
+  {
+    std::vector<std::pair<std::uint32_t, std::uint32_t>> e;
+    for (const auto& f : mesh.polygons)
+      for (int k = 0; k < 3; ++k)
+        e.emplace_back(std::min<std::uint32_t>(f.vertices[k], f.vertices[(k + 1) % 3]), std::max<std::uint32_t>(f.vertices[k], f.vertices[(k + 1) % 3]));
+    std::sort(e.begin(), e.end());
+    edges = std::unique(e.begin(), e.end()) - e.begin();
+  }
+  {
+    YAML::Node config;
+    config["name"] = "FaceMidpointSubdivision";
+    config["n_iterations"] = 2;
+    const std::vector<pcl::PolygonMesh> out = factory.createMeshModifier(config)->modify(mesh);
+    CHECK(out.size() == 1);
+    const pcl::PolygonMesh& m = out.front();
+    checkCommon(m);
+    CHECK(m.polygons.size() == 16 * mesh.polygons.size());
+    // iteration 1 adds one vertex per edge; the refined mesh has 2 E + 3 F edges
+    CHECK(m.cloud.width == mesh.cloud.width + edges + (2 * edges + 3 * mesh.polygons.size()));
+    YAML::Node pc = planeSlicerConfig("PlaneSlicer", 1.05, Eigen::Vector3d(1, 0, 0), Eigen::Vector3d(0, 0, 0));
+    CHECK(factory.createToolPathPlanner(pc)->plan(m).size() == 10);
+  }
+  {
+    YAML::Node config;
+    config["name"] = "FaceSubdivisionByArea";
+    config["max_area"] = 0.01;
+    const std::vector<pcl::PolygonMesh> out = factory.createMeshModifier(config)->modify(mesh);
+    CHECK(out.size() == 1);
+    const pcl::PolygonMesh& m = out.front();
+    checkCommon(m);
+    CHECK(m.polygons.size() > mesh.polygons.size());
+    CHECK((m.polygons.size() - mesh.polygons.size()) == 2 * (m.cloud.width - mesh.cloud.width));  // a split adds 1 vertex, 2 faces
+    bool within = true;
+    for (const auto& f : m.polygons)
+      within = within && faceArea(m, f) <= 0.01 * (1 + 1e-5);
+    CHECK(within);
+  }
+}
+
 int main(int argc, char** argv)
 {
   if (argc < 3)
@@ -782,7 +874,8 @@ int main(int argc, char** argv)
   const noether::Factory factory(loader);
   try
   {
-    for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces" })
+    for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
+                                "FaceMidpointSubdivision", "FaceSubdivisionByArea" })
       CHECK(dlsym(lib, alias) != nullptr);
     const pcl::PolygonMesh ply = loadPly(argv[2]);
     CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);
@@ -790,6 +883,7 @@ int main(int argc, char** argv)
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicer", false);
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);
     testNormalsFieldRetention(factory, ply);
+    testFaceSubdivision(factory, ply);
     testGeneratorsAndErrors(factory, ply);
     testResidentMeshReuse(factory, ply);
     testToolPathModifiers(factory);

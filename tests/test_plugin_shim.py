@@ -23,6 +23,7 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
     exported = {line.split()[-1] for line in syms.splitlines() if line.strip()}
     # aliases of noether_tpp/src/plugins.cpp:62,89,111,179,278
     for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
+                  "FaceMidpointSubdivision", "FaceSubdivisionByArea",  # plugins.cpp:58-59
                   # tool path modifiers that run on the device (plugins.cpp:182-199,219)
                   "SnakeOrganization", "LinearApproach", "LinearDeparture", "Offset", "FixedOrientation", "UniformOrientation",
                   "Concatenate", "ToolDragOrientation", "BiasedToolDragOrientation", "DirectionOfTravelOrientation",
@@ -35,6 +36,10 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
     names = {tok for line in sections.splitlines() for tok in line.replace("]", " ").split()}
     for section in ("tpp", "dg", "og", "mesh", "mod"):
         assert section in names
+    # every symbol the plugin library needs resolves at load time (boost_plugin_loader dlopens it; a template the stand-in
+    # headers declare but do not define would only show up there)
+    import ctypes
+    ctypes.CDLL(PLUGIN, mode=os.RTLD_NOW)
     # the shim reaches the product through the C ABI only
     undefined = subprocess.run(["nm", "-D", "--undefined-only", PLUGIN], capture_output=True, text=True, check=True).stdout
     used = {line.split()[-1] for line in undefined.splitlines() if " nb2_" in line}
