@@ -731,7 +731,7 @@ void nb2_context_destroy(nb2_context* c)
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
                      &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->modEnds, &c->stlSlots, &c->stlCorner,
                      &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix, &c->subBlob[0], &c->subBlob[1], &c->subTri[0], &c->subTri[1], &c->subLevels,
-                     &c->subKeys, &c->subVals, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
+                     &c->subKeys, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)

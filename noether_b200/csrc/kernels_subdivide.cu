@@ -52,17 +52,16 @@ struct DevMin
        i < (n); i += stride__)
 
 __global__ void __launch_bounds__(256)
-    k_mid_insert(MidpointLevel lv, unsigned long long* __restrict__ keys, unsigned* __restrict__ vals, unsigned slot_mask,
-                 unsigned* __restrict__ req_slot)
+    k_mid_insert(MidpointLevel lv, unsigned long long* table, unsigned slot_mask, unsigned* __restrict__ req_slot)
 {
-  NB2_GRID_STRIDE(j, lv.n_nodes) midpointInsert(lv, j, keys, vals, slot_mask, req_slot, DevCas{}, DevMin{});
+  NB2_GRID_STRIDE(j, lv.n_nodes) midpointInsert(lv, j, table, slot_mask, req_slot, DevCas{}, DevMin{});
 }
 
 __global__ void __launch_bounds__(256)
-    k_mid_resolve(MidpointLevel lv, const unsigned* __restrict__ vals, const unsigned* __restrict__ req_slot,
+    k_mid_resolve(MidpointLevel lv, const unsigned long long* __restrict__ table, const unsigned* __restrict__ req_slot,
                   uint8_t* __restrict__ node_mask, unsigned* __restrict__ node_cnt, uint32_t* __restrict__ children)
 {
-  NB2_GRID_STRIDE(j, lv.n_nodes) midpointResolve(lv, j, vals, req_slot, node_mask, node_cnt, children);
+  NB2_GRID_STRIDE(j, lv.n_nodes) midpointResolve(lv, j, table, req_slot, node_mask, node_cnt, children);
 }
 
 __global__ void __launch_bounds__(256)
@@ -199,8 +198,7 @@ void launchMidpointSubdivision(nb2_context* c, const sub::Layout& L, int n_iter,
   uint64_t slots = 1024;
   while (slots < 6 * top_nodes)
     slots <<= 1;
-  c->subKeys.ensure(sizeof(unsigned long long) * slots);
-  c->subVals.ensure(sizeof(unsigned) * slots);
+  c->subKeys.ensure(2 * sizeof(unsigned long long) * slots);  // 16-byte slots { key, smallest sequence number }
   c->subReq.ensure(sizeof(unsigned) * 3 * std::max<uint64_t>(top_nodes, 1));
   c->subNodeCnt.ensure(sizeof(unsigned) * (nodes + 1));
   c->subNodeBase.ensure(sizeof(unsigned) * (nodes + 1));
@@ -225,13 +223,12 @@ void launchMidpointSubdivision(nb2_context* c, const sub::Layout& L, int n_iter,
         uint64_t lslots = 1024;
         while (lslots < 6 * lv.n_nodes)
           lslots <<= 1;
-        NB2_CUDA(cudaMemsetAsync(c->subKeys.ptr, 0xff, sizeof(unsigned long long) * lslots, st));
-        NB2_CUDA(cudaMemsetAsync(c->subVals.ptr, 0xff, sizeof(unsigned) * lslots, st));
+        NB2_CUDA(cudaMemsetAsync(c->subKeys.ptr, 0xff, 2 * sizeof(unsigned long long) * lslots, st));
         const int grid = gridFor(lv.n_nodes, c);
-        k_mid_insert<<<grid, 256, 0, st>>>(lv, c->subKeys.as<unsigned long long>(), c->subVals.as<unsigned>(),
-                                           static_cast<unsigned>(lslots - 1), c->subReq.as<unsigned>());
+        k_mid_insert<<<grid, 256, 0, st>>>(lv, c->subKeys.as<unsigned long long>(), static_cast<unsigned>(lslots - 1),
+                                           c->subReq.as<unsigned>());
         NB2_LAUNCHED(c);
-        k_mid_resolve<<<grid, 256, 0, st>>>(lv, c->subVals.as<unsigned>(), c->subReq.as<unsigned>(), c->subNodeMask.as<uint8_t>(),
+        k_mid_resolve<<<grid, 256, 0, st>>>(lv, c->subKeys.as<unsigned long long>(), c->subReq.as<unsigned>(), c->subNodeMask.as<uint8_t>(),
                                             c->subNodeCnt.as<unsigned>(), children);
         NB2_LAUNCHED(c);
       }

@@ -254,8 +254,7 @@ struct nb2_context
   // resident mesh (blob / tri adopt them in place) is the input of the next subdivision
   nb2::DevBuf subBlob[2], subTri[2];
   nb2::DevBuf subLevels;    // uint32[3 * triangles of levels 2 .. n] of the midpoint scheme
-  nb2::DevBuf subKeys;      // uint64[slots] edge keys of the level being resolved
-  nb2::DevBuf subVals;      // uint32[slots] smallest request sequence number of each edge
+  nb2::DevBuf subKeys;      // uint64[2 * slots]: 16-byte slots { edge key, smallest request sequence number } of the level
   nb2::DevBuf subReq;       // uint32[3 * triangles of the level] slot of every request
   nb2::DevBuf subNodeCnt, subNodeBase;  // uint32[nodes + 1] vertices created by every tree node (pre-order), their prefix
   nb2::DevBuf subNodeMask;  // uint8[nodes] which of the node's three requests create a vertex

@@ -28,6 +28,7 @@
 #include "host_math.h"
 
 #include <cstdint>
+#include <cstring>
 
 namespace nb2
 {
@@ -118,39 +119,92 @@ NB2_HD inline void storeF3(uint8_t* rec, uint32_t off, const F3& v)
   f[2] = v.z;
 }
 
-/** copyPointToEnd + updatePointData: dst = byte copy of src[0], then x y z / normal / rgba = mean of the n sources */
+/** 16 bytes moved at once (records whose step is a multiple of 16 are copied with a quarter of the memory instructions) */
+struct alignas(16) W4
+{
+  uint32_t w[4];
+};
+NB2_HD inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+NB2_HD inline uint32_t floatBits(float f)
+{
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+
+/** ((0 + p0) + p1 [+ p2]) / float(n) of a float triple at `off` */
+NB2_HD inline F3 meanF3(const uint8_t* const* src, int n, uint32_t off)
+{
+  const float count = static_cast<float>(n);
+  F3 mean{ 0.f, 0.f, 0.f };
+  for (int k = 0; k < n; ++k)
+  {
+    const F3 p = loadF3(src[k], off);
+    mean.x = mean.x + p.x;
+    mean.y = mean.y + p.y;
+    mean.z = mean.z + p.z;
+  }
+  return { mean.x / count, mean.y / count, mean.z / count };
+}
+
+/** copyPointToEnd + updatePointData: dst = byte copy of src[0] whose x y z / normal / rgba are the mean of the n sources.
+ *  The means are formed first and patched into the words of the copy as they pass, so that every byte of the new record
+ *  is written once. */
 NB2_HD inline void makeMeanRecord(uint8_t* dst, const uint8_t* const* src, int n, const Layout& L)
 {
-  {
-    const uint32_t* s = reinterpret_cast<const uint32_t*>(src[0]);
-    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    for (uint32_t w = 0; w < L.step / 4; ++w)
-      d[w] = s[w];
-  }
-  const float count = static_cast<float>(n);
-  for (int field = 0; field < 2; ++field)
-  {
-    if (field == 1 && L.off_nrm < 0)
-      break;
-    const uint32_t off = field == 0 ? L.off_xyz : static_cast<uint32_t>(L.off_nrm);
-    F3 mean{ 0.f, 0.f, 0.f };
-    for (int k = 0; k < n; ++k)
-    {
-      const F3 p = loadF3(src[k], off);
-      mean.x = mean.x + p.x;
-      mean.y = mean.y + p.y;
-      mean.z = mean.z + p.z;
-    }
-    storeF3(dst, off, { mean.x / count, mean.y / count, mean.z / count });
-  }
+  const F3 xyz = meanF3(src, n, L.off_xyz);
+  const bool has_nrm = L.off_nrm >= 0;
+  F3 nrm{ 0.f, 0.f, 0.f };
+  if (has_nrm)
+    nrm = meanF3(src, n, static_cast<uint32_t>(L.off_nrm));
+  uint8_t rgba[4] = { 0, 0, 0, 0 };
   if (L.off_rgba >= 0)
     for (int ch = 0; ch < 4; ++ch)
     {
       int mean = 0;
       for (int k = 0; k < n; ++k)
         mean += src[k][L.off_rgba + ch];
-      dst[L.off_rgba + ch] = static_cast<uint8_t>(mean / n);
+      rgba[ch] = static_cast<uint8_t>(mean / n);
     }
+  const bool rgba_word = L.off_rgba >= 0 && (L.off_rgba & 3) == 0;
+  const uint32_t rgba_bits = rgba[0] | (static_cast<uint32_t>(rgba[1]) << 8) | (static_cast<uint32_t>(rgba[2]) << 16) |
+                             (static_cast<uint32_t>(rgba[3]) << 24);
+  const uint32_t wx = L.off_xyz / 4, wn = has_nrm ? static_cast<uint32_t>(L.off_nrm) / 4 : 0u,
+                 wc = rgba_word ? static_cast<uint32_t>(L.off_rgba) / 4 : 0u;
+  auto patched = [&](uint32_t i, uint32_t v) {
+    if (i >= wx && i < wx + 3)
+      v = floatBits(i == wx ? xyz.x : (i == wx + 1 ? xyz.y : xyz.z));
+    if (has_nrm && i >= wn && i < wn + 3)
+      v = floatBits(i == wn ? nrm.x : (i == wn + 1 ? nrm.y : nrm.z));
+    if (rgba_word && i == wc)
+      v = rgba_bits;
+    return v;
+  };
+  if ((L.step & 15u) == 0 && aligned16(src[0]) && aligned16(dst))
+  {
+    const W4* s = reinterpret_cast<const W4*>(src[0]);
+    W4* d = reinterpret_cast<W4*>(dst);
+    for (uint32_t q = 0; q < L.step / 16; ++q)
+    {
+      W4 v = s[q];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (uint32_t c = 0; c < 4; ++c)
+        v.w[c] = patched(4 * q + c, v.w[c]);
+      d[q] = v;
+    }
+  }
+  else
+  {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src[0]);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (uint32_t i = 0; i < L.step / 4; ++i)
+      d[i] = patched(i, s[i]);
+  }
+  if (L.off_rgba >= 0 && !rgba_word)
+    for (int ch = 0; ch < 4; ++ch)
+      dst[L.off_rgba + ch] = rgba[ch];
 }
 
 /** 0.5f * ((v1 - v0).cross(v2 - v0)).norm()   (face_subdivision_modifier.cpp:330) */
@@ -172,11 +226,19 @@ struct MidpointLevel
   const uint32_t* tri;         // uint32[3 n_nodes] (provisional ids)
 };
 
+/** A slot of the level's hash table is 16 bytes — the edge key and, next to it, the smallest sequence number seen — so
+ *  that the insert's compare-and-swap and its atomicMin touch one 32-byte sector of HBM instead of two. */
+NB2_HD inline unsigned* slotValue(unsigned long long* table, unsigned long long s) { return reinterpret_cast<unsigned*>(table + 2 * s + 1); }
+NB2_HD inline const unsigned* slotValue(const unsigned long long* table, unsigned long long s)
+{
+  return reinterpret_cast<const unsigned*>(table + 2 * s + 1);
+}
+
 /** pass A1: the three edges of the node go into the level's hash table; every slot keeps its smallest sequence number.
  *  `cas` / `amin` are the atomics of the caller's world (device atomics, or plain host code). */
 template <typename Cas, typename Min>
-NB2_HD inline void midpointInsert(const MidpointLevel& lv, unsigned long long j, unsigned long long* keys, unsigned* vals,
-                                  unsigned slot_mask, unsigned* req_slot, Cas cas, Min amin)
+NB2_HD inline void midpointInsert(const MidpointLevel& lv, unsigned long long j, unsigned long long* table, unsigned slot_mask,
+                                  unsigned* req_slot, Cas cas, Min amin)
 {
   const unsigned long long node = midpointNode(lv.shape, lv.level, j);
   const uint32_t v[3] = { lv.tri[3 * j], lv.tri[3 * j + 1], lv.tri[3 * j + 2] };
@@ -187,19 +249,19 @@ NB2_HD inline void midpointInsert(const MidpointLevel& lv, unsigned long long j,
     unsigned s = hashKey(key) & slot_mask;
     for (;;)
     {
-      const unsigned long long seen = cas(keys + s, kEmptyKey, key);
+      const unsigned long long seen = cas(table + 2ull * s, kEmptyKey, key);
       if (seen == kEmptyKey || seen == key)
         break;
       s = (s + 1) & slot_mask;
     }
-    amin(vals + s, seq);
+    amin(slotValue(table, s), seq);
     req_slot[3 * j + k] = s;
   }
 }
 
 /** pass A2: midpoint ids of the node (provisional), which of its requests create a vertex, its four children */
-NB2_HD inline void midpointResolve(const MidpointLevel& lv, unsigned long long j, const unsigned* vals, const unsigned* req_slot,
-                                   uint8_t* node_mask, unsigned* node_cnt, uint32_t* children)
+NB2_HD inline void midpointResolve(const MidpointLevel& lv, unsigned long long j, const unsigned long long* table,
+                                   const unsigned* req_slot, uint8_t* node_mask, unsigned* node_cnt, uint32_t* children)
 {
   const unsigned long long node = midpointNode(lv.shape, lv.level, j);
   const uint32_t t[3] = { lv.tri[3 * j], lv.tri[3 * j + 1], lv.tri[3 * j + 2] };
@@ -207,7 +269,7 @@ NB2_HD inline void midpointResolve(const MidpointLevel& lv, unsigned long long j
   unsigned mask = 0;
   for (int k = 0; k < 3; ++k)
   {
-    const unsigned first = vals[req_slot[3 * j + k]];
+    const unsigned first = *slotValue(table, req_slot[3 * j + k]);
     m[k] = lv.V + first;
     if (first == static_cast<unsigned>(3 * node + k))
       mask |= 1u << k;
@@ -215,9 +277,20 @@ NB2_HD inline void midpointResolve(const MidpointLevel& lv, unsigned long long j
   node_mask[node] = static_cast<uint8_t>(mask);
   node_cnt[node] = popc3(mask);
   // { t0 m0 m2 } { m0 t1 m1 } { m2 m1 t2 } { m0 m1 m2 }   (face_subdivision_modifier.cpp:170-173)
-  const uint32_t out[12] = { t[0], m[0], m[2], m[0], t[1], m[1], m[2], m[1], t[2], m[0], m[1], m[2] };
-  for (int i = 0; i < 12; ++i)
-    children[12 * j + i] = out[i];
+  uint32_t* c = children + 12 * j;
+  if (aligned16(c))
+  {
+    W4* c4 = reinterpret_cast<W4*>(c);
+    c4[0] = W4{ { t[0], m[0], m[2], m[0] } };
+    c4[1] = W4{ { t[1], m[1], m[2], m[1] } };
+    c4[2] = W4{ { t[2], m[0], m[1], m[2] } };
+  }
+  else
+  {
+    const uint32_t out[12] = { t[0], m[0], m[2], m[0], t[1], m[1], m[2], m[1], t[2], m[0], m[1], m[2] };
+    for (int i = 0; i < 12; ++i)
+      c[i] = out[i];
+  }
 }
 
 /** pass C: the records of the vertices this node creates (sources were made by earlier levels) */

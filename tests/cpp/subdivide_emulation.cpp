@@ -96,13 +96,13 @@ int emu_midpoint(const uint8_t* cloud, uint64_t V, uint32_t step, uint32_t off_x
     uint64_t slots = 1024;
     while (slots < 6 * lv.n_nodes)
       slots <<= 1;
-    std::vector<unsigned long long> keys(slots, kEmptyKey);
-    std::vector<unsigned> vals(slots, 0xffffffffu), req(3 * lv.n_nodes + 1);
+    std::vector<unsigned long long> table(2 * slots, kEmptyKey);  // { key, smallest sequence number } pairs, all bits set
+    std::vector<unsigned> req(3 * lv.n_nodes + 1);
     scrambled(lv.n_nodes, [&](unsigned long long j) {
-      midpointInsert(lv, j, keys.data(), vals.data(), static_cast<unsigned>(slots - 1), req.data(), HostCas{}, HostMin{});
+      midpointInsert(lv, j, table.data(), static_cast<unsigned>(slots - 1), req.data(), HostCas{}, HostMin{});
     });
     scrambled(lv.n_nodes, [&](unsigned long long j) {
-      midpointResolve(lv, j, vals.data(), req.data(), node_mask.data(), node_cnt.data(), level_tri[l + 1].data());
+      midpointResolve(lv, j, table.data(), req.data(), node_mask.data(), node_cnt.data(), level_tri[l + 1].data());
     });
   }
   exclusiveScan(node_cnt, node_base);

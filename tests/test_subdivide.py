@@ -26,6 +26,8 @@ LAYOUTS = {
     "PointXYZRGBNormal": (48, 0, 16, 32),   # rgba at 32, curvature at 36
     "NormalsFirst": (48, 32, 0, -1),        # output of NormalsFromMeshFaces
     "PointXYZRGBA": (32, 0, -1, 16),
+    "Packed24": (24, 0, 12, -1),            # step not a multiple of 16: the word-by-word record copy
+    "OddRgba": (24, 4, -1, 17),             # rgba not on a word boundary (spills into the padding word)
 }
 
 

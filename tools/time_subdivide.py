@@ -5,6 +5,7 @@ the oracle's sequential walk on one host core for a bounded sample, and the resu
 sample.
 
     python tools/time_subdivide.py [cfg2|cfg3] > profiles/r01_subdivide_<cfg>.json
+    ncu ... python tools/time_subdivide.py cfg3 --profile     (launch list / --set full capture)
 """
 import json
 import os
@@ -31,6 +32,7 @@ def main():
     import oracle
     oracle.build()
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+    profile = "--profile" in sys.argv   # under ncu: one pass of each modifier, no oracle leg
     nx, ny = {"cfg2": (800, 625), "cfg3": (2500, 2000)}[name]
     xyz, tri = meshes.wavy(nx, ny)
     ctx = nb.Context(0)
@@ -43,7 +45,7 @@ def main():
     out = {"workload": name, "vertices": V, "triangles": F, "point_step": step, "peak_GBs": peak, "peak_source": peak_src}
     cell_area = 0.5 * (1.0 / nx) * (0.8 / ny)
 
-    def timed(fn, reps=3):
+    def timed(fn, reps=1 if profile else 3):
         best = None
         for _ in range(reps):
             ctx.upload(blob, force=True)
@@ -69,6 +71,9 @@ def main():
                       "triangles_out": info2.n_triangles, "algorithmic_MB": round(alg2 / 1e6, 1),
                       "achieved_GBs": round(alg2 / ms2 / 1e6, 1), "frac_of_peak": round(alg2 / ms2 / 1e6 / peak, 4),
                       "triangles_in_per_s": round(F / ms2 * 1e3)}
+    if profile:
+        print(json.dumps(out))
+        return
     # the oracle (sequential depth-first walk, std::map per edge) on the leading rows of the same mesh: one host core
     rows = max(1, min(ny, 1_000_000 // (2 * nx)))
     xs, ts = meshes.wavy(nx, rows, ly=0.8 * rows / ny)
