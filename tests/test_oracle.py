@@ -4,6 +4,8 @@ The reference's tests pin counts and topology only; everything n
 closed-form cases instead, and the third-party restatements (Eigen solver, stripper + sort + join) against numpy and
 against the intent-mode chains.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -351,3 +353,24 @@ def test_kat_pca_rotated_direction(orc):
     e1 = p.evecs[:, 1].astype(np.float64)
     e1 /= np.linalg.norm(e1)
     assert np.abs(orc.pca_rotated_direction(p, 0.9, e1) - orc.principal_axis_direction(p, 0.9)).max() < 1e-15
+
+
+def test_cpu_optimised_baseline_slabs_cover_the_plan(orc):
+    """tools/cpu_optimised.py (bench.py's second CPU figure): plane slabs over forked workers produce the plan of one
+    pass over the whole lattice — same tool paths, same waypoints"""
+    import json
+    import subprocess
+    import sys
+    from noether_b200 import meshes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "cpu_optimised.py"), "cfg2", "3"], capture_output=True,
+                       text=True, timeout=300, check=True)
+    o = json.loads(r.stdout.strip().splitlines()[-1])
+    xyz, tri = meshes.wavy(800, 625)
+    nrm = orc.normals_from_mesh_faces(xyz, tri)
+    whole, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.005, True, slice_mode=orc.SLICE_FAITHFUL, scan_mode=orc.SCAN_BINNED,
+                                          post_ops=False)
+    f = whole.flat()
+    assert o["workers"] == 3 and o["planes"] == int(lat.num_planes)
+    assert (o["tool_paths"], o["waypoints"]) == (f.num_paths, int(f.seg_off[-1]))
+    assert o["tri_per_s"] > 0
