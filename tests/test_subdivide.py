@@ -317,3 +317,93 @@ def test_gpu_subdivision_large_and_chained(ctx, orc):
     with pytest.raises(_capi.Nb2Error, match="not finite") as e:
         ctx.face_subdivision_by_area(1.0)
     assert e.value.status == _capi.NB2_ERR_NON_FINITE
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the oracle against an independent restatement (plain Python: recursion + dict, a list used as a stack; numpy float32
+# scalars for the arithmetic) written from the reference's text, not from the oracle's source
+# ---------------------------------------------------------------------------------------------------------------------
+class _PyCloud:
+    def __init__(self, cloud, layout):
+        self.step, self.ox, self.on, self.oc = LAYOUTS[layout]
+        self.rec = [bytes(r) for r in np.asarray(cloud, np.uint8).reshape(-1, self.step)]
+
+    def f3(self, i, off):
+        return np.frombuffer(self.rec[i], np.float32, 3, off)
+
+    def append_mean(self, sources):   # copyPointToEnd(first source) + updatePointData
+        rec = bytearray(self.rec[sources[0]])
+        n = np.float32(len(sources))
+        for off in (self.ox, self.on):
+            if off < 0:
+                continue
+            mean = np.zeros(3, np.float32)
+            for s in sources:
+                mean = mean + self.f3(s, off)
+            rec[off:off + 12] = (mean / n).astype(np.float32).tobytes()
+        if self.oc >= 0:
+            for ch in range(4):
+                rec[self.oc + ch] = sum(self.rec[s][self.oc + ch] for s in sources) // len(sources)
+        self.rec.append(bytes(rec))
+        return len(self.rec) - 1
+
+    def blob(self):
+        return np.frombuffer(b"".join(self.rec), np.uint8)
+
+
+def py_midpoint(cloud, layout, tri, n):
+    c, edge, faces = _PyCloud(cloud, layout), {}, []
+
+    def mid(a, b):
+        key = (min(a, b), max(a, b))
+        if key not in edge:
+            edge[key] = c.append_mean([a, b])
+        return edge[key]
+
+    def rec(t, depth):
+        m0, m1, m2 = mid(t[0], t[1]), mid(t[1], t[2]), mid(t[2], t[0])
+        sub = [(t[0], m0, m2), (m0, t[1], m1), (m2, m1, t[2]), (m0, m1, m2)]
+        if depth == 1:
+            faces.extend(sub)
+        else:
+            for s in sub:
+                rec(s, depth - 1)
+
+    for t in np.asarray(tri).tolist():
+        rec(tuple(t), n)
+    return c.blob(), np.array(faces, np.uint32).reshape(-1, 3)
+
+
+def py_by_area(cloud, layout, tri, max_area):
+    c, faces = _PyCloud(cloud, layout), []
+    stack = [tuple(t) for t in np.asarray(tri).tolist()]
+    max_area = np.float32(max_area)
+    while stack:
+        f = stack.pop()
+        v0, v1, v2 = (c.f3(i, c.ox) for i in f)
+        a, b = v1 - v0, v2 - v0
+        cr = np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], np.float32)
+        sq = cr * cr
+        area = np.float32(0.5) * np.sqrt(sq[0] + (sq[1] + sq[2]))
+        if not area > max_area:
+            faces.append(f)
+            continue
+        m = c.append_mean(list(f))
+        stack += [(f[0], f[1], m), (m, f[1], f[2]), (f[0], m, f[2])]
+    return c.blob(), np.array(faces, np.uint32).reshape(-1, 3)
+
+
+@pytest.mark.parametrize("layout", ["PointXYZ", "PointXYZRGBNormal", "OddRgba"])
+def test_oracle_matches_independent_python_restatement(orc, layout):
+    step, ox, on, oc = LAYOUTS[layout]
+    for case in ("one_triangle", "wavy", "degenerate", "soup"):
+        xyz, tri = CASES[case]
+        cloud = make_cloud(xyz, layout, seed=3)
+        for n in (1, 2):
+            assert_same_mesh(orc.face_midpoint_subdivision(cloud, step, ox, on, oc, tri, n), py_midpoint(cloud, layout, tri, n),
+                             f"{case} {layout} midpoint n={n}")
+        for max_area in area_limits(xyz, tri)[:3]:
+            with np.errstate(all="ignore"):
+                ref = py_by_area(cloud, layout, tri, max_area)
+            assert_same_mesh(orc.face_subdivision_by_area(cloud, step, ox, on, oc, tri, max_area), ref,
+                             f"{case} {layout} by area {max_area}")
