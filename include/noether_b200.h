@@ -170,6 +170,11 @@ int nb2_normals_from_mesh_faces(nb2_context* ctx, float* normals_out);
  * reference's sequential depth-first walk.  The subdivided mesh replaces the resident one (same record layout; moments
  * and PCA axes recomputed), so nb2_plan / nb2_normals_from_mesh_faces can follow without a host round trip; the shim
  * reads it back with nb2_mesh_download_cloud + nb2_mesh_download_triangles (sizes in `info`).
+ * The modifiers work on the cloud as uploaded (the reference's modifiers see nothing else either): normals computed on
+ * the device by nb2_normals_from_mesh_faces live beside the cloud and are not subdivided — upload the concatenated cloud
+ * the shim builds from them, or run nb2_normals_from_mesh_faces again on the subdivided mesh.  The subdivision and the
+ * hand-over of its result are two critical sections of the context: do not upload to the same context from another
+ * thread in between (the plugin shim serialises its calls per device anyway).
  * Refusals: n_iterations = 0 (never terminates in the reference) or beyond the 2^31 triangle limit of this path;
  * a non-finite triangle area (NB2_ERR_NON_FINITE, "Triangle area is not finite", :332-333); a by-area subdivision that
  * would exceed max_points points (0 = the 2^31 limit; the reference has no limit and would exhaust memory).
