@@ -133,3 +133,16 @@ def test_host_lattice_matches_oracle_bit_for_bit(capi, orc, seed):
         assert bytes(a) == bytes(b)
     with pytest.raises(capi.Nb2Error):
         make_lattice(g, [1, 0, 0], [0, 0, 0], -1.0, True)
+
+
+def test_entry_points_refuse_a_null_context(capi):
+    """argument checks happen before any device work: a NULL context is a status + message, never a crash"""
+    L = capi.load()
+    info = capi.MeshFileInfo()
+    for call in (lambda: L.nb2_face_midpoint_subdivision(None, 1, -1, C.byref(info)),
+                 lambda: L.nb2_face_subdivision_by_area(None, C.c_float(1.0), -1, 0, C.byref(info)),
+                 lambda: L.nb2_mesh_download_cloud(None, None),
+                 lambda: L.nb2_mesh_record_layout(None, None, None, None),
+                 lambda: L.nb2_mesh_download_triangles(None, None)):
+        assert call() == capi.NB2_ERR_INVALID_ARGUMENT
+        assert L.nb2_last_error()
