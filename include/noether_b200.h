@@ -188,6 +188,26 @@ int nb2_mesh_download_cloud(nb2_context* ctx, void* cloud_data);
 int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_t* offset_xyz, int32_t* offset_normal);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * EuclideanClusteringMeshModifier::modify (euclidean_clustering_modifier.cpp:40-64), device part: the
+ * connected components pcl::EuclideanClusterExtraction grows with one k-d tree radius search per point — two points are
+ * linked when FLANN's float squared distance ((dx^2) + dy^2) + dz^2 is strictly below float(tolerance^2).
+ * labels[v] (uint32[n_points], host memory) = the smallest point index of v's component = the seed PCL starts that
+ * cluster from, so ascending labels are PCL's clusters in order of discovery.  tolerance <= 0 finds no neighbours
+ * (labels[v] = v).  The size filter (min_cluster_size / max_cluster_size), PCL's reverse std::sort by size and
+ * extractSubMeshFromInlierVertices (subset_extractor.cpp:22-56) are index bookkeeping on the labels and are done by the
+ * caller (plugin shim), where the meshes are materialised.
+ * Refusals: a tolerance so large against the point spacing that the 27-cell neighbourhoods hold more than 4e11 candidate
+ * pairs (the reference's radius searches would each return a large
+ * part of the cloud as well).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int nb2_euclidean_cluster_labels(nb2_context* ctx, double tolerance, uint32_t* labels);
+/* Host only (no context): the order pcl::EuclideanClusterExtraction::extract leaves its clusters in —
+ * std::sort(clusters.rbegin(), clusters.rend(), comparePointClusters), largest first, equal sizes as the library's
+ * introsort leaves them — for clusters given in order of discovery (ascending label) with these sizes, after the size
+ * filter.  order[k] = index into cluster_sizes of the k-th mesh the reference returns. */
+int nb2_cluster_order(const uint32_t* cluster_sizes, uint64_t n_clusters, uint32_t* order);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Plane lattice (plane_slicer_raster_planner.cpp:556-586 and getDistancesToMinMaxCuts :460-501).  Pure host
  * arithmetic in double, restated with the reference's quirks (OBB centred on the mean, `else if` min/max update,
  * floored start offset, ceil'ed plane count).

@@ -7,7 +7,7 @@ interface used by tests and the benchmark; it only ever calls the C ABI.
 from . import _capi, meshes  # noqa: F401
 from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionGenerator,  # noqa: F401
                       FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, FaceMidpointSubdivisionMeshModifier,
-                      FaceSubdivisionByAreaMeshModifier, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
+                      FaceSubdivisionByAreaMeshModifier, EuclideanClusteringMeshModifier, cluster_order, cluster_submeshes, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,
                       default_context, make_lattice,
                       ToolPathModifier, SnakeOrganizationModifier, RasterOrganizationModifier,

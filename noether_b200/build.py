@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnoether_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "kernels_mesh.cu", "kernels_slice.cu", "kernels_normals.cu", "kernels_frame.cu", "kernels_legacy.cu", "kernels_ply.cu", "kernels_stl.cu", "kernels_subdivide.cu", "modifiers.cu", "modifier_plan.cpp", "ply.cpp", "frame.cpp", "toolpath.cpp",
+SOURCES = ["api.cu", "kernels_mesh.cu", "kernels_slice.cu", "kernels_normals.cu", "kernels_frame.cu", "kernels_legacy.cu", "kernels_ply.cu", "kernels_stl.cu", "kernels_subdivide.cu", "kernels_cluster.cu", "modifiers.cu", "modifier_plan.cpp", "ply.cpp", "frame.cpp", "toolpath.cpp",
            "comm.cpp"]
 
 NVCC_FLAGS = [

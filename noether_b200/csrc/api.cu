@@ -2,6 +2,7 @@
 #include "host_math.h"
 #include "nb2_internal.h"
 #include "subdivide_ops.h"
+#include "cluster_ops.h"
 
 #include <algorithm>
 #include <cmath>
@@ -731,7 +732,7 @@ void nb2_context_destroy(nb2_context* c)
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
                      &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->modEnds, &c->stlSlots, &c->stlCorner,
                      &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix, &c->subBlob[0], &c->subBlob[1], &c->subTri[0], &c->subTri[1], &c->subLevels,
-                     &c->subKeys, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
+                     &c->subKeys, &c->cluHead, &c->cluNext, &c->cluParent, &c->cluLabel, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)
@@ -1261,6 +1262,61 @@ int nb2_face_subdivision_by_area(nb2_context* c, float max_area, int32_t offset_
     launchAreaSubdivision(c, L, max_area, max_points, slot, &V, &F);
   }
   adoptSubdivided(c, slot, V, F, L, info);
+  NB2_API_END
+}
+
+int nb2_cluster_order(const uint32_t* cluster_sizes, uint64_t n_clusters, uint32_t* order)
+{
+  NB2_API_BEGIN
+  if (n_clusters && (!cluster_sizes || !order))
+    fail(NB2_ERR_INVALID_ARGUMENT, "cluster_sizes or order is NULL");
+  // pcl::EuclideanClusterExtraction::extract: std::sort(clusters.rbegin(), clusters.rend(), comparePointClusters) with
+  // comparePointClusters(a, b) = a.indices.size() < b.indices.size().  The order it leaves clusters of equal size in is
+  // whatever the library's introsort does; the very same call on (size, id) pairs takes the same decisions.
+  struct Entry
+  {
+    uint32_t size, id;
+  };
+  std::vector<Entry> v(n_clusters);
+  for (uint64_t i = 0; i < n_clusters; ++i)
+    v[i] = { cluster_sizes[i], static_cast<uint32_t>(i) };
+  std::sort(v.rbegin(), v.rend(), [](const Entry& a, const Entry& b) { return a.size < b.size; });
+  for (uint64_t i = 0; i < n_clusters; ++i)
+    order[i] = v[i].id;
+  NB2_API_END
+}
+
+int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* labels)
+{
+  NB2_API_BEGIN
+  if (!c || !labels)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or labels is NULL");
+  if (!(tolerance == tolerance))
+    fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: tolerance is NaN");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  const uint64_t V = c->V;
+  if (!(tolerance > 0.0))
+  {
+    // a radius search with radius <= 0 finds nothing, not even the query point: every point is its own cluster
+    for (uint64_t v = 0; v < V; ++v)
+      labels[v] = static_cast<uint32_t>(v);
+    return NB2_OK;
+  }
+  ensureHostPca(c);  // the AABB of the cloud (and the deferred checks of a device-adopted mesh)
+  clu::GridParams grid{};
+  grid.h = tolerance * (1.0 + 1.0 / 1024.0);
+  grid.r2 = static_cast<float>(tolerance * tolerance);
+  for (int i = 0; i < 3; ++i)
+  {
+    grid.mn[i] = static_cast<double>(c->pca.aabb_min[i]) - grid.h;  // one spare cell below the cloud
+    const double cells = (static_cast<double>(c->pca.aabb_max[i]) - grid.mn[i]) / grid.h;
+    if (!(cells < clu::kMaxCells))
+      fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: tolerance " + std::to_string(tolerance) +
+                                         " is less than 1e-18 of the extent of the cloud");
+  }
+  launchClusterLabels(c, grid, 4e11, labels);
   NB2_API_END
 }
 

@@ -1,0 +1,133 @@
+// Euclidean clustering of the resident cloud on the device: the connected components that
+// pcl::EuclideanClusterExtraction finds with one k-d tree radius search per point (euclidean_clustering_modifier.cpp:40-64),
+// computed as
+//
+//   C1  k_clu_insert   one thread per point: claim / find the hash slot of its grid cell, push the point on the cell's chain
+//   C2  k_clu_link     one thread per point: the points with a smaller index in the 27 surrounding cells, FLANN's float
+//                      distance test, lock-free union (larger root under smaller root)
+//   C3  k_clu_flatten  label = root = smallest point index of the component = PCL's seed of that cluster
+//
+// cluster_ops.h holds the per-point work (shared with the host emulation of the CPU tests).  Sizes, the size filter, PCL's
+// reverse std::sort by size and the sub-mesh extraction are index bookkeeping on the labels and stay on the host side of
+// the C ABI (plugin shim / Python mirror), where the meshes have to be materialised anyway.
+#include "nb2_internal.h"
+#include "cluster_ops.h"
+
+#include <algorithm>
+
+namespace nb2
+{
+namespace
+{
+using namespace clu;
+
+struct DevCas64
+{
+  __device__ unsigned long long operator()(unsigned long long* addr, unsigned long long expect, unsigned long long val) const
+  {
+    const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(addr);
+    if (seen != expect)
+      return seen;  // a cell's key never changes once written
+    return atomicCAS(addr, expect, val);
+  }
+};
+struct DevCas32
+{
+  __device__ unsigned operator()(unsigned* addr, unsigned expect, unsigned val) const { return atomicCAS(addr, expect, val); }
+};
+struct DevXchg
+{
+  __device__ unsigned operator()(unsigned* addr, unsigned val) const { return atomicExch(addr, val); }
+};
+struct DevPos
+{
+  const float4* pos;
+  __device__ void operator()(unsigned i, float& x, float& y, float& z) const
+  {
+    const float4 p = __ldg(pos + i);
+    x = p.x;
+    y = p.y;
+    z = p.z;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+    k_clu_insert(GridParams g, const float4* __restrict__ pos, unsigned V, unsigned long long* cell_key, unsigned* cell_head,
+                 unsigned slot_mask, unsigned* __restrict__ next, unsigned* __restrict__ parent, unsigned* occupied)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+  {
+    const float4 q = __ldg(pos + p);
+    if (insertPoint(g, p, q.x, q.y, q.z, cell_key, cell_head, slot_mask, next, parent, DevCas64{}, DevXchg{}))
+      atomicAdd(occupied, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_clu_link(GridParams g, const float4* __restrict__ pos, unsigned V, const unsigned long long* __restrict__ cell_key,
+               const unsigned* __restrict__ cell_head, unsigned slot_mask, const unsigned* __restrict__ next, unsigned* parent)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+    linkPoint(g, p, DevPos{ pos }, cell_key, cell_head, slot_mask, next, parent, DevCas32{});
+}
+
+__global__ void __launch_bounds__(256) k_clu_flatten(unsigned* parent, unsigned V, unsigned* __restrict__ label)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+    label[p] = findRoot(parent, p);
+}
+
+inline int gridFor(unsigned long long n, const nb2_context* c)
+{
+  const unsigned long long cap = static_cast<unsigned long long>(c->sm_count) * 16;
+  return static_cast<int>(std::max<unsigned long long>(1, std::min((n + 255) / 256, cap)));
+}
+}  // namespace
+
+/** labels of the resident cloud into `labels_host` (uint32[V]); `max_tests` bounds the distance tests (27 V V / cells) */
+void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host)
+{
+  const uint64_t V = c->V;
+  cudaStream_t st = c->stream;
+  uint64_t slots = 1024;
+  while (slots < 2 * V)
+    slots <<= 1;
+  c->subKeys.ensure(sizeof(unsigned long long) * slots);  // the subdivision's table buffer doubles as the cell table
+  c->cluHead.ensure(sizeof(unsigned) * slots);
+  c->cluNext.ensure(sizeof(unsigned) * V);
+  c->cluParent.ensure(sizeof(unsigned) * V);
+  c->cluLabel.ensure(sizeof(unsigned) * V);
+  unsigned* occupied = c->counters.as<unsigned>() + 21;
+  NB2_CUDA(cudaMemsetAsync(c->subKeys.ptr, 0xff, sizeof(unsigned long long) * slots, st));
+  NB2_CUDA(cudaMemsetAsync(c->cluHead.ptr, 0xff, sizeof(unsigned) * slots, st));
+  NB2_CUDA(cudaMemsetAsync(occupied, 0, sizeof(unsigned), st));
+  const unsigned n = static_cast<unsigned>(V);
+  k_clu_insert<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
+                                             static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), c->cluParent.as<unsigned>(),
+                                             occupied);
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  c->hostSmall.ensure(4096);
+  unsigned* h = c->hostSmall.as<unsigned>();
+  NB2_CUDA(cudaMemcpyAsync(h, occupied, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaStreamSynchronize(st));
+  const double cells = std::max(1u, h[0]);
+  const double tests = 27.0 * static_cast<double>(V) * (static_cast<double>(V) / cells);
+  if (tests > max_tests)
+    fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: the tolerance is large against the point spacing (" + std::to_string(V) +
+                                       " points in " + std::to_string(h[0]) + " grid cells, about " + std::to_string(tests) +
+                                       " distance tests); every radius search of the reference would return a large part of the cloud too");
+  k_clu_link<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
+                                           static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), c->cluParent.as<unsigned>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  k_clu_flatten<<<gridFor(V, c), 256, 0, st>>>(c->cluParent.as<unsigned>(), n, c->cluLabel.as<unsigned>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  NB2_CUDA(cudaMemcpyAsync(labels_host, c->cluLabel.ptr, sizeof(unsigned) * V, cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaStreamSynchronize(st));
+}
+}  // namespace nb2

@@ -260,6 +260,8 @@ struct nb2_context
   nb2::DevBuf subNodeMask;  // uint8[nodes] which of the node's three requests create a vertex
   nb2::DevBuf subFresh;     // centroid records of the by-area sweep in creation order
   nb2::DevBuf subRank;      // uint32[centroids] final number of each
+  // Euclidean clustering (kernels_cluster.cu): chain head per cell slot, chain link / union-find parent / label per point
+  nb2::DevBuf cluHead, cluNext, cluParent, cluLabel;
   // record layout of the resident cloud (set by every ingest)
   uint32_t rec_step = 0, rec_off_xyz = 0;
   int32_t rec_off_nrm = -1;
@@ -364,6 +366,12 @@ struct Layout;
 void launchMidpointSubdivision(nb2_context* c, const sub::Layout& L, int n_iterations, int slot, uint64_t* n_points, uint64_t* n_triangles);
 void launchAreaSubdivision(nb2_context* c, const sub::Layout& L, float max_area, uint64_t max_points, int slot, uint64_t* n_points,
                            uint64_t* n_triangles);
+// connected components of the resident cloud under FLANN's radius test (kernels_cluster.cu); synchronises
+namespace clu
+{
+struct GridParams;
+}
+void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host);
 // single-pass decoupled look-back exclusive scan (kernels_normals.cu)
 void launchScanU32(nb2_context* c, const unsigned* in, unsigned* out, unsigned long long n);
 

@@ -132,6 +132,12 @@ class Context:
         _capi.check(self._lib.nb2_face_subdivision_by_area(self._h, float(max_area), int(off_rgba), int(max_points), C.byref(info)))
         return info
 
+    def euclidean_cluster_labels(self, tolerance: float, n_vertices: int) -> np.ndarray:
+        """nb2_euclidean_cluster_labels: smallest point index of every point's connected component"""
+        labels = np.zeros(n_vertices, np.uint32)
+        _capi.check(self._lib.nb2_euclidean_cluster_labels(self._h, float(tolerance), labels.ctypes.data))
+        return labels
+
     def set_normals(self, normals: np.ndarray):
         n = np.ascontiguousarray(normals, dtype=np.float32)
         _capi.check(self._lib.nb2_mesh_set_normals(self._h, n.ctypes.data))
@@ -535,6 +541,67 @@ class NormalsFromMeshFacesMeshModifier:
         return [out]
 
 
+def cluster_order(sizes) -> np.ndarray:
+    """nb2_cluster_order (host only): PCL's reverse std::sort by size of clusters given in order of discovery"""
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    order = np.zeros(len(sizes), np.uint32)
+    _capi.check(_capi.load().nb2_cluster_order(sizes.ctypes.data, len(sizes), order.ctypes.data))
+    return order
+
+
+def cluster_submeshes(labels, mesh: MeshBlob, min_cluster_size: int, max_cluster_size: int) -> list:
+    """Host side of EuclideanClusteringMeshModifier::modify after the clustering itself: the size filter of
+    pcl::extractEuclideanClusters, PCL's size sort (cluster_order), extractSubMeshFromInlierVertices
+    (subset_extractor.cpp:22-56) and pcl::surface::SimplificationRemoveUnusedVertices.  Returns, in the reference's
+    output order, MeshBlob objects (sub-mesh with the used points in order of first use; the input itself when every point
+    is used) or None where the reference returns a default-constructed mesh (no face has all three vertices in the
+    cluster)."""
+    labels = np.asarray(labels, np.uint32)
+    V = mesh.n_vertices
+    seeds, sizes = np.unique(labels, return_counts=True)          # ascending seed = order of discovery
+    min_pts = int(np.uint32(np.int64(min_cluster_size) & 0xffffffff))   # setMinClusterSize takes an unsigned
+    max_pts = V if max_cluster_size <= 0 else int(max_cluster_size)     # euclidean_clustering_modifier.cpp:53
+    keep = (sizes >= min_pts) & (sizes <= max_pts)
+    seeds, sizes = seeds[keep], sizes[keep]
+    tri = np.ascontiguousarray(mesh.tri, np.uint32).reshape(-1, 3)
+    tri_label = labels[tri] if len(tri) else np.zeros((0, 3), np.uint32)
+    face_seed = np.where((tri_label[:, 0] == tri_label[:, 1]) & (tri_label[:, 0] == tri_label[:, 2]), tri_label[:, 0].astype(np.int64), -1)
+    rec = np.asarray(mesh.data, np.uint8).reshape(V, mesh.point_step)
+    out = []
+    for k in cluster_order(sizes):
+        kept = tri[face_seed == int(seeds[k])]
+        if len(kept) == 0:
+            out.append(None)
+            continue
+        flat = kept.ravel()
+        uniq, first = np.unique(flat, return_index=True)
+        used = uniq[np.argsort(first, kind="stable")]              # order of first use by the kept faces
+        if len(used) == V:
+            out.append(MeshBlob(np.asarray(mesh.data, np.uint8).copy(), V, mesh.point_step, mesh.off_xyz, mesh.off_normal, kept.copy()))
+            continue
+        new_index = np.zeros(V, np.uint32)
+        new_index[used] = np.arange(len(used), dtype=np.uint32)
+        out.append(MeshBlob(np.ascontiguousarray(rec[used]).reshape(-1), len(used), mesh.point_step, mesh.off_xyz, mesh.off_normal,
+                            new_index[kept]))
+    return out
+
+
+class EuclideanClusteringMeshModifier:
+    """euclidean_clustering_modifier.cpp:40-64 (plugin alias EuclideanClustering; YAML keys tolerance, min_cluster_size,
+    max_cluster_size): the clustering runs on the GPU (connected components under FLANN's radius test), the sub-meshes
+    are cut on the host from the labels.  An entry of the result is None where the reference returns an empty mesh."""
+
+    def __init__(self, tolerance: float, min_cluster_size: int = 1, max_cluster_size: int = -1, context: Context | None = None):
+        self._ctx = context
+        self.tolerance, self.min_cluster_size, self.max_cluster_size = tolerance, min_cluster_size, max_cluster_size
+
+    def modify(self, mesh: MeshBlob) -> list:
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        labels = ctx.euclidean_cluster_labels(self.tolerance, mesh.n_vertices)
+        return cluster_submeshes(labels, mesh, self.min_cluster_size, self.max_cluster_size)
+
+
 class _FaceSubdivisionBase:
     """Common part of the face subdivision mesh modifiers (face_subdivision_modifier.cpp): upload, subdivide on the
     device, read the new cloud (same fields as the input, utils.cpp copyPointToEnd) and triangle list back.
@@ -882,6 +949,9 @@ class Factory:
             return NormalsFromMeshFacesMeshModifier(self._ctx)
         if name == "FaceMidpointSubdivision":  # n_iterations is read as a float and cast (face_subdivision_modifier.cpp:357)
             return FaceMidpointSubdivisionMeshModifier(int(float(_member(config, "n_iterations"))), self._ctx)
+        if name == "EuclideanClustering":      # euclidean_clustering_modifier.cpp:79-85
+            return EuclideanClusteringMeshModifier(float(_member(config, "tolerance")), int(_member(config, "min_cluster_size")),
+                                                   int(_member(config, "max_cluster_size")), self._ctx)
         if name == "FaceSubdivisionByArea":    # :371
             return FaceSubdivisionByAreaMeshModifier(float(_member(config, "max_area")), self._ctx)
         raise RuntimeError(f"Failed to find plugin '{name}' in section 'mesh'")

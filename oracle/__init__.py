@@ -132,6 +132,18 @@ def lib():
     L.orc_submesh_export.restype = None
     L.orc_submesh_free.argtypes = [C.c_void_p]
     L.orc_submesh_free.restype = None
+    L.orc_euclidean_clustering.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, C.c_uint64, C.c_double, C.c_int,
+                                           C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.orc_clusters_count.argtypes = [C.c_void_p]
+    L.orc_clusters_count.restype = C.c_uint64
+    L.orc_clusters_labels.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_clusters_labels.restype = None
+    L.orc_cluster_info.argtypes = [C.c_void_p, C.c_uint64, u64p]
+    L.orc_cluster_info.restype = None
+    L.orc_cluster_export.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_cluster_export.restype = None
+    L.orc_clusters_free.argtypes = [C.c_void_p]
+    L.orc_clusters_free.restype = None
     L.orc_fixture_random_transform.argtypes = [C.c_double, C.c_double, f64p]
     L.orc_fixture_random_transform.restype = None
     L.orc_fixture_plane_mesh.argtypes = [C.c_float, C.c_float, f64p, f32p, f32p, u32p]
@@ -529,3 +541,38 @@ def face_subdivision_by_area(cloud, point_step, off_xyz, off_normal, off_rgba, t
     """FaceSubdivisionByAreaMeshModifier::modify (face_subdivision_modifier.cpp:250-339)."""
     return _subdivide(lib().orc_face_subdivision_by_area, cloud, point_step, off_xyz, off_normal, off_rgba, tri,
                       C.c_float(max_area), int(max_points))
+
+
+@dataclass
+class ClusterMesh:
+    indices: np.ndarray      # the cluster (ascending point indices)
+    cloud: np.ndarray        # uint8 records of the sub-mesh (empty when `empty`)
+    tri: np.ndarray          # (F', 3) uint32
+    whole_input: bool        # every point is used: the reference returns the input cloud unchanged
+    empty: bool              # no face survives: the reference returns a default-constructed mesh
+
+
+def euclidean_clustering(cloud, point_step, off_xyz, tri, tolerance, min_cluster_size=1, max_cluster_size=-1, brute=False):
+    """EuclideanClusteringMeshModifier::modify (euclidean_clustering_modifier.cpp:40-64): returns (list of ClusterMesh in
+    the reference's output order, labels uint32 (V,) = smallest index of every point's connected component)."""
+    blob = np.ascontiguousarray(np.frombuffer(bytes(cloud), dtype=np.uint8))
+    n = blob.size // point_step
+    t, tp = _u32(np.asarray(tri).reshape(-1, 3))
+    h = C.c_void_p()
+    _check(lib().orc_euclidean_clustering(blob.ctypes.data, n, point_step, off_xyz, tp, t.shape[0], float(tolerance),
+                                          int(min_cluster_size), int(max_cluster_size), int(bool(brute)), C.byref(h)))
+    try:
+        labels = np.zeros(n, np.uint32)
+        lib().orc_clusters_labels(h, labels.ctypes.data)
+        out = []
+        for k in range(lib().orc_clusters_count(h)):
+            info = (C.c_uint64 * 5)()
+            lib().orc_cluster_info(h, k, info)
+            idx = np.zeros(info[0], np.uint32)
+            pts = np.zeros(info[1] * point_step, np.uint8)
+            tr = np.zeros((info[2], 3), np.uint32)
+            lib().orc_cluster_export(h, k, idx.ctypes.data, pts.ctypes.data, tr.ctypes.data)
+            out.append(ClusterMesh(idx, pts, tr, bool(info[3]), bool(info[4])))
+    finally:
+        lib().orc_clusters_free(h)
+    return out, labels

@@ -186,6 +186,19 @@ uint64_t orc_submesh_num_triangles(const void* h);
 void orc_submesh_export(const void* h, uint8_t* cloud, uint32_t* triangles); /* either may be NULL */
 void orc_submesh_free(void* h);
 
+/* ---- EuclideanClusteringMeshModifier::modify (euclidean_clustering_modifier.cpp:40-64; pcl::EuclideanClusterExtraction,
+ *      extractSubMeshFromInlierVertices, SimplificationRemoveUnusedVertices restated in oracle_cluster.cpp).  The result is a
+ *      handle: the clusters in the order the reference returns their meshes.  force_brute: all-pairs neighbour search
+ *      whatever the size (the grid search must agree with it) ---- */
+int orc_euclidean_clustering(const uint8_t* cloud, uint64_t n_points, uint32_t point_step, uint32_t off_xyz, const uint32_t* tri,
+                             uint64_t n_triangles, double tolerance, int min_cluster_size, int max_cluster_size, int force_brute,
+                             void** out);
+uint64_t orc_clusters_count(const void* h);
+void orc_clusters_labels(const void* h, uint32_t* labels); /* smallest point index of every point's connected component */
+void orc_cluster_info(const void* h, uint64_t k, uint64_t out[5]); /* cluster size, sub-mesh points, sub-mesh triangles, whole input, empty */
+void orc_cluster_export(const void* h, uint64_t k, uint32_t* indices, uint8_t* cloud, uint32_t* tri); /* any may be NULL */
+void orc_clusters_free(void* h);
+
 /* ---- restated test fixtures ---- */
 /* createRandomTransform(translation_limit, rotation_limit): tool_path_planner_utest.cpp:32-46 (std::mt19937(0)) */
 void orc_fixture_random_transform(double translation_limit, double rotation_limit, double out16[16]);

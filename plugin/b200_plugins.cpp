@@ -13,6 +13,7 @@
 //   NormalsFromMeshFaces  mesh     NormalsFromMeshFacesMeshModifier       src/plugins.cpp:62
 //   FaceMidpointSubdivision mesh   FaceMidpointSubdivisionMeshModifier    src/plugins.cpp:58
 //   FaceSubdivisionByArea mesh     FaceSubdivisionByAreaMeshModifier      src/plugins.cpp:59
+//   EuclideanClustering   mesh     EuclideanClusteringMeshModifier        src/plugins.cpp:57
 //
 // Built against the real headers inside a noether workspace (plugin/CMakeLists.txt).  In the development image those
 // packages do not exist; there the file is compiled against plugin/compat/ (minimal stand-ins declaring the same
@@ -587,6 +588,113 @@ public:
   }
 };
 
+/** EuclideanClusteringMeshModifier (euclidean_clustering_modifier.cpp:40-64): the clustering itself — one k-d tree radius
+ *  search per point in the reference — runs on the GPU (nb2_euclidean_cluster_labels: connected components under FLANN's
+ *  radius test, label = smallest point index = PCL's seed).  The rest is index bookkeeping on the labels, done here where
+ *  the meshes are materialised: the size filter of pcl::extractEuclideanClusters, PCL's size sort (nb2_cluster_order),
+ *  extractSubMeshFromInlierVertices (subset_extractor.cpp:22-56) and SimplificationRemoveUnusedVertices. */
+class EuclideanClusteringMeshModifier : public noether::MeshModifier
+{
+public:
+  EuclideanClusteringMeshModifier(double tolerance, int min_cluster_size, int max_cluster_size)
+    : tolerance_(tolerance), min_cluster_size_(min_cluster_size), max_cluster_size_(max_cluster_size)
+  {
+  }
+
+  std::vector<pcl::PolygonMesh> modify(const pcl::PolygonMesh& mesh) const override final
+  {
+    const std::size_t V = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+    std::vector<std::uint32_t> labels(V);
+    {
+      Device& dev = Device::instance();
+      std::lock_guard<std::mutex> lock(dev.mutex());
+      ensureResident(dev, mesh, false);
+      Device::check(nb2_euclidean_cluster_labels(dev.ctx(), tolerance_, labels.data()));
+    }
+    // clusters in order of discovery (ascending seed) with their sizes; the size filter of extractEuclideanClusters
+    std::vector<std::uint32_t> size_of(V, 0);
+    for (std::size_t v = 0; v < V; ++v)
+      ++size_of[labels[v]];
+    const std::uint32_t min_pts = static_cast<std::uint32_t>(min_cluster_size_);  // setMinClusterSize takes pcl::uindex_t
+    const std::uint32_t max_pts = max_cluster_size_ <= 0 ? static_cast<std::uint32_t>(V) : static_cast<std::uint32_t>(max_cluster_size_);  // :53
+    std::vector<std::uint32_t> seeds, sizes;
+    for (std::size_t v = 0; v < V; ++v)
+      if (size_of[v] && size_of[v] >= min_pts && size_of[v] <= max_pts)
+      {
+        seeds.push_back(static_cast<std::uint32_t>(v));
+        sizes.push_back(size_of[v]);
+      }
+    std::vector<std::uint32_t> order(seeds.size());
+    Device::check(nb2_cluster_order(sizes.data(), sizes.size(), order.data()));
+    // faces by cluster, in face order (a face belongs to a cluster when its first three vertices do)
+    std::vector<std::int64_t> slot_of_seed(V, -1);
+    for (std::size_t k = 0; k < order.size(); ++k)
+      slot_of_seed[seeds[order[k]]] = static_cast<std::int64_t>(k);
+    std::vector<std::vector<std::uint32_t>> faces(order.size());
+    for (std::size_t f = 0; f < mesh.polygons.size(); ++f)
+    {
+      const auto& v = mesh.polygons[f].vertices;
+      const std::uint32_t l = labels[v[0]];
+      if (labels[v[1]] == l && labels[v[2]] == l && slot_of_seed[l] >= 0)
+        faces[static_cast<std::size_t>(slot_of_seed[l])].push_back(static_cast<std::uint32_t>(f));
+    }
+    std::vector<pcl::PolygonMesh> result(order.size());
+    std::vector<std::int64_t> new_index(V, -1);
+    for (std::size_t k = 0; k < order.size(); ++k)
+    {
+      pcl::PolygonMesh& out = result[k];
+      out.header = mesh.header;             // subset_extractor.cpp:52-53
+      out.cloud.header = mesh.cloud.header;
+      if (faces[k].empty())
+        continue;  // simplify() returns at once: the output stays a default-constructed mesh
+      std::vector<std::uint32_t> used;
+      for (std::uint32_t f : faces[k])
+        for (auto v : mesh.polygons[f].vertices)
+          if (new_index[v] < 0)
+          {
+            new_index[v] = static_cast<std::int64_t>(used.size());
+            used.push_back(static_cast<std::uint32_t>(v));
+          }
+      out.polygons.reserve(faces[k].size());
+      if (used.size() == V)
+      {
+        out.cloud = mesh.cloud;  // every point is used: the cloud as it is
+        for (std::uint32_t f : faces[k])
+          out.polygons.push_back(mesh.polygons[f]);
+      }
+      else
+      {
+        out.cloud.fields = mesh.cloud.fields;
+        out.cloud.point_step = mesh.cloud.point_step;
+        out.cloud.is_bigendian = mesh.cloud.is_bigendian;
+        out.cloud.height = 1;
+        out.cloud.width = static_cast<std::uint32_t>(used.size());
+        out.cloud.row_step = out.cloud.point_step * out.cloud.width;
+        out.cloud.is_dense = false;
+        out.cloud.data.resize(static_cast<std::size_t>(out.cloud.width) * out.cloud.point_step);
+        for (std::size_t i = 0; i < used.size(); ++i)
+          std::memcpy(out.cloud.data.data() + i * out.cloud.point_step,
+                      mesh.cloud.data.data() + static_cast<std::size_t>(used[i]) * mesh.cloud.point_step, mesh.cloud.point_step);
+        for (std::uint32_t f : faces[k])
+        {
+          pcl::Vertices p;
+          p.vertices.resize(mesh.polygons[f].vertices.size());
+          for (std::size_t i = 0; i < p.vertices.size(); ++i)
+            p.vertices[i] = static_cast<decltype(p.vertices)::value_type>(new_index[mesh.polygons[f].vertices[i]]);
+          out.polygons.push_back(std::move(p));
+        }
+      }
+      for (std::uint32_t v : used)
+        new_index[v] = -1;
+    }
+    return result;
+  }
+
+private:
+  double tolerance_;
+  int min_cluster_size_, max_cluster_size_;
+};
+
 /** The face subdivision mesh modifiers (face_subdivision_modifier.cpp:202-339) on the GPU: the mesh is subdivided where it
  *  is resident and read back once — a cloud with the input's fields (new records are copies of their first source with
  *  x y z / normals / rgba averaged) and 3-vertex polygons in the reference's depth-first order. */
@@ -785,6 +893,18 @@ struct Plugin_NormalsFromMeshFacesMeshModifier : public noether::Plugin<noether:
   }
 };
 
+/** EuclideanClustering: YAML keys tolerance, min_cluster_size, max_cluster_size (euclidean_clustering_modifier.cpp:79-85) */
+struct Plugin_EuclideanClusteringMeshModifier : public noether::Plugin<noether::MeshModifier>
+{
+  std::unique_ptr<noether::MeshModifier> create(const YAML::Node& config,
+                                                std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<EuclideanClusteringMeshModifier>(YAML::getMember<double>(config, "tolerance"),
+                                                             YAML::getMember<int>(config, "min_cluster_size"),
+                                                             YAML::getMember<int>(config, "max_cluster_size"));
+  }
+};
+
 /** FaceMidpointSubdivision: YAML key n_iterations, read as a float and cast (face_subdivision_modifier.cpp:354-359) */
 struct Plugin_FaceMidpointSubdivisionMeshModifier : public noether::Plugin<noether::MeshModifier>
 {
@@ -971,6 +1091,7 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CircularLeadOut, CircularL
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSmoothing, MovingAverageOrientationSmoothing)
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
+EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_EuclideanClusteringMeshModifier, EuclideanClustering)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceMidpointSubdivisionMeshModifier, FaceMidpointSubdivision)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceSubdivisionByAreaMeshModifier, FaceSubdivisionByArea)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)

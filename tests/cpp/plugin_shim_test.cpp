@@ -856,6 +856,76 @@ void testFaceSubdivision(const noether::Factory& factory, const pcl::PolygonMesh
   }
 }
 
+/** EuclideanClustering through the plugin boundary with the YAML of the reference's own test (mesh_modifier_utest.cpp:15-19:
+ *  tolerance 1.0, min 1, max -1): non-empty meshes with polygons and the input's fields (:130-183) — on this connected
+ *  surface one cluster that uses every point, i.e. the input itself; and two copies of the surface far apart come back as
+ *  two meshes, largest first, each renumbered from zero. */
+void testEuclideanClustering(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[MeshModifier EuclideanClustering]\n");
+  YAML::Node config;
+  config["name"] = "EuclideanClustering";
+  config["tolerance"] = 1.0;
+  config["min_cluster_size"] = 1;
+  config["max_cluster_size"] = -1;
+  auto modifier = factory.createMeshModifier(config);
+  {
+    const std::vector<pcl::PolygonMesh> out = modifier->modify(mesh);
+    CHECK(out.size() == 1);
+    if (!out.empty())
+    {
+      CHECK(out[0].polygons.size() == mesh.polygons.size());
+      CHECK(out[0].cloud.width * out[0].cloud.height == mesh.cloud.width * mesh.cloud.height);
+      CHECK(out[0].cloud.fields.size() == mesh.cloud.fields.size());
+      CHECK(out[0].cloud.data == mesh.cloud.data);
+    }
+  }
+  // the surface twice, the copy shifted by 100 in z and without its last 200 faces
+  unsigned off_z = 0;
+  for (const auto& g : mesh.cloud.fields)
+    if (g.name == "z")
+      off_z = g.offset;
+  pcl::PolygonMesh two = mesh;
+  const std::uint32_t V = mesh.cloud.width * mesh.cloud.height;
+  two.cloud.data.insert(two.cloud.data.end(), mesh.cloud.data.begin(), mesh.cloud.data.end());
+  two.cloud.width = 2 * V;
+  two.cloud.height = 1;
+  two.cloud.row_step = two.cloud.width * two.cloud.point_step;
+  for (std::uint32_t v = V; v < 2 * V; ++v)
+  {
+    float z;
+    std::memcpy(&z, two.cloud.data.data() + static_cast<std::size_t>(v) * two.cloud.point_step + off_z, 4);
+    z += 100.f;
+    std::memcpy(two.cloud.data.data() + static_cast<std::size_t>(v) * two.cloud.point_step + off_z, &z, 4);
+  }
+  for (std::size_t f = 0; f + 200 < mesh.polygons.size(); ++f)
+  {
+    pcl::Vertices p = mesh.polygons[f];
+    for (auto& v : p.vertices)
+      v += V;
+    two.polygons.push_back(p);
+  }
+  const std::vector<pcl::PolygonMesh> out = modifier->modify(two);
+  CHECK(out.size() == 2);
+  if (out.size() == 2)
+  {
+    // equal cluster sizes: whichever order the size sort leaves, one mesh has all faces and the other 200 fewer
+    const std::size_t a = out[0].polygons.size(), b = out[1].polygons.size();
+    CHECK(std::max(a, b) == mesh.polygons.size() && std::min(a, b) == mesh.polygons.size() - 200);
+    for (const auto& m : out)
+    {
+      CHECK(m.cloud.height == 1 && m.cloud.width <= V && m.cloud.width > 0);
+      CHECK(m.cloud.data.size() == static_cast<std::size_t>(m.cloud.width) * m.cloud.point_step);
+      CHECK(m.cloud.fields.size() == mesh.cloud.fields.size());
+      std::uint32_t top = 0;
+      for (const auto& f : m.polygons)
+        for (auto v : f.vertices)
+          top = std::max<std::uint32_t>(top, v);
+      CHECK(top + 1 == m.cloud.width);
+    }
+  }
+}
+
 int main(int argc, char** argv)
 {
   if (argc < 3)
@@ -875,7 +945,7 @@ int main(int argc, char** argv)
   try
   {
     for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
-                                "FaceMidpointSubdivision", "FaceSubdivisionByArea" })
+                                "FaceMidpointSubdivision", "FaceSubdivisionByArea", "EuclideanClustering" })
       CHECK(dlsym(lib, alias) != nullptr);
     const pcl::PolygonMesh ply = loadPly(argv[2]);
     CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);
@@ -887,6 +957,8 @@ int main(int argc, char** argv)
     testGeneratorsAndErrors(factory, ply);
     testResidentMeshReuse(factory, ply);
     testToolPathModifiers(factory);
+    if (argc > 3 && std::string(argv[3]) == "--clustering")
+      testEuclideanClustering(factory, ply);
     if (argc > 3 && std::string(argv[3]) == "--time")
     {
       timePipeline(factory, 800, 625, 0.005);    // cfg2: 1 M triangles
