@@ -567,9 +567,12 @@ def cluster_submeshes(labels, mesh: MeshBlob, min_cluster_size: int, max_cluster
     tri_label = labels[tri] if len(tri) else np.zeros((0, 3), np.uint32)
     face_seed = np.where((tri_label[:, 0] == tri_label[:, 1]) & (tri_label[:, 0] == tri_label[:, 2]), tri_label[:, 0].astype(np.int64), -1)
     rec = np.asarray(mesh.data, np.uint8).reshape(V, mesh.point_step)
+    by_seed = np.argsort(face_seed, kind="stable")                # faces grouped by cluster, face order kept inside a group
+    sorted_seed = face_seed[by_seed]
     out = []
     for k in cluster_order(sizes):
-        kept = tri[face_seed == int(seeds[k])]
+        lo, hi = np.searchsorted(sorted_seed, [int(seeds[k]), int(seeds[k]) + 1])
+        kept = tri[by_seed[lo:hi]]
         if len(kept) == 0:
             out.append(None)
             continue
