@@ -588,6 +588,91 @@ public:
   }
 };
 
+/** Host side of EuclideanClusteringMeshModifier::modify, from the labels the device computed (label = smallest point index
+ *  of the point's cluster): size filter, PCL's size sort, one sub-mesh per cluster.  No device involved. */
+std::vector<pcl::PolygonMesh> cutClusterMeshes(const pcl::PolygonMesh& mesh, const std::uint32_t* labels, int min_cluster_size,
+                                               int max_cluster_size)
+{
+  const std::size_t V = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+  // clusters in order of discovery (ascending seed) with their sizes; the size filter of extractEuclideanClusters
+  std::vector<std::uint32_t> size_of(V, 0);
+  for (std::size_t v = 0; v < V; ++v)
+    ++size_of[labels[v]];
+  const std::uint32_t min_pts = static_cast<std::uint32_t>(min_cluster_size);  // setMinClusterSize takes pcl::uindex_t
+  const std::uint32_t max_pts = max_cluster_size <= 0 ? static_cast<std::uint32_t>(V) : static_cast<std::uint32_t>(max_cluster_size);  // :53
+  std::vector<std::uint32_t> seeds, sizes;
+  for (std::size_t v = 0; v < V; ++v)
+    if (size_of[v] && size_of[v] >= min_pts && size_of[v] <= max_pts)
+    {
+      seeds.push_back(static_cast<std::uint32_t>(v));
+      sizes.push_back(size_of[v]);
+    }
+  std::vector<std::uint32_t> order(seeds.size());
+  Device::check(nb2_cluster_order(sizes.data(), sizes.size(), order.data()));
+  // faces by cluster, in face order (a face belongs to a cluster when its first three vertices do)
+  std::vector<std::int64_t> slot_of_seed(V, -1);
+  for (std::size_t k = 0; k < order.size(); ++k)
+    slot_of_seed[seeds[order[k]]] = static_cast<std::int64_t>(k);
+  std::vector<std::vector<std::uint32_t>> faces(order.size());
+  for (std::size_t f = 0; f < mesh.polygons.size(); ++f)
+  {
+    const auto& v = mesh.polygons[f].vertices;
+    const std::uint32_t l = labels[v[0]];
+    if (labels[v[1]] == l && labels[v[2]] == l && slot_of_seed[l] >= 0)
+      faces[static_cast<std::size_t>(slot_of_seed[l])].push_back(static_cast<std::uint32_t>(f));
+  }
+  std::vector<pcl::PolygonMesh> result(order.size());
+  std::vector<std::int64_t> new_index(V, -1);
+  for (std::size_t k = 0; k < order.size(); ++k)
+  {
+    pcl::PolygonMesh& out = result[k];
+    out.header = mesh.header;             // subset_extractor.cpp:52-53
+    out.cloud.header = mesh.cloud.header;
+    if (faces[k].empty())
+      continue;  // simplify() returns at once: the output stays a default-constructed mesh
+    std::vector<std::uint32_t> used;
+    for (std::uint32_t f : faces[k])
+      for (auto v : mesh.polygons[f].vertices)
+        if (new_index[v] < 0)
+        {
+          new_index[v] = static_cast<std::int64_t>(used.size());
+          used.push_back(static_cast<std::uint32_t>(v));
+        }
+    out.polygons.reserve(faces[k].size());
+    if (used.size() == V)
+    {
+      out.cloud = mesh.cloud;  // every point is used: the cloud as it is
+      for (std::uint32_t f : faces[k])
+        out.polygons.push_back(mesh.polygons[f]);
+    }
+    else
+    {
+      out.cloud.fields = mesh.cloud.fields;
+      out.cloud.point_step = mesh.cloud.point_step;
+      out.cloud.is_bigendian = mesh.cloud.is_bigendian;
+      out.cloud.height = 1;
+      out.cloud.width = static_cast<std::uint32_t>(used.size());
+      out.cloud.row_step = out.cloud.point_step * out.cloud.width;
+      out.cloud.is_dense = false;
+      out.cloud.data.resize(static_cast<std::size_t>(out.cloud.width) * out.cloud.point_step);
+      for (std::size_t i = 0; i < used.size(); ++i)
+        std::memcpy(out.cloud.data.data() + i * out.cloud.point_step,
+                    mesh.cloud.data.data() + static_cast<std::size_t>(used[i]) * mesh.cloud.point_step, mesh.cloud.point_step);
+      for (std::uint32_t f : faces[k])
+      {
+        pcl::Vertices p;
+        p.vertices.resize(mesh.polygons[f].vertices.size());
+        for (std::size_t i = 0; i < p.vertices.size(); ++i)
+          p.vertices[i] = static_cast<decltype(p.vertices)::value_type>(new_index[mesh.polygons[f].vertices[i]]);
+        out.polygons.push_back(std::move(p));
+      }
+    }
+    for (std::uint32_t v : used)
+      new_index[v] = -1;
+  }
+  return result;
+}
+
 /** EuclideanClusteringMeshModifier (euclidean_clustering_modifier.cpp:40-64): the clustering itself — one k-d tree radius
  *  search per point in the reference — runs on the GPU (nb2_euclidean_cluster_labels: connected components under FLANN's
  *  radius test, label = smallest point index = PCL's seed).  The rest is index bookkeeping on the labels, done here where
@@ -611,83 +696,7 @@ public:
       ensureResident(dev, mesh, false);
       Device::check(nb2_euclidean_cluster_labels(dev.ctx(), tolerance_, labels.data()));
     }
-    // clusters in order of discovery (ascending seed) with their sizes; the size filter of extractEuclideanClusters
-    std::vector<std::uint32_t> size_of(V, 0);
-    for (std::size_t v = 0; v < V; ++v)
-      ++size_of[labels[v]];
-    const std::uint32_t min_pts = static_cast<std::uint32_t>(min_cluster_size_);  // setMinClusterSize takes pcl::uindex_t
-    const std::uint32_t max_pts = max_cluster_size_ <= 0 ? static_cast<std::uint32_t>(V) : static_cast<std::uint32_t>(max_cluster_size_);  // :53
-    std::vector<std::uint32_t> seeds, sizes;
-    for (std::size_t v = 0; v < V; ++v)
-      if (size_of[v] && size_of[v] >= min_pts && size_of[v] <= max_pts)
-      {
-        seeds.push_back(static_cast<std::uint32_t>(v));
-        sizes.push_back(size_of[v]);
-      }
-    std::vector<std::uint32_t> order(seeds.size());
-    Device::check(nb2_cluster_order(sizes.data(), sizes.size(), order.data()));
-    // faces by cluster, in face order (a face belongs to a cluster when its first three vertices do)
-    std::vector<std::int64_t> slot_of_seed(V, -1);
-    for (std::size_t k = 0; k < order.size(); ++k)
-      slot_of_seed[seeds[order[k]]] = static_cast<std::int64_t>(k);
-    std::vector<std::vector<std::uint32_t>> faces(order.size());
-    for (std::size_t f = 0; f < mesh.polygons.size(); ++f)
-    {
-      const auto& v = mesh.polygons[f].vertices;
-      const std::uint32_t l = labels[v[0]];
-      if (labels[v[1]] == l && labels[v[2]] == l && slot_of_seed[l] >= 0)
-        faces[static_cast<std::size_t>(slot_of_seed[l])].push_back(static_cast<std::uint32_t>(f));
-    }
-    std::vector<pcl::PolygonMesh> result(order.size());
-    std::vector<std::int64_t> new_index(V, -1);
-    for (std::size_t k = 0; k < order.size(); ++k)
-    {
-      pcl::PolygonMesh& out = result[k];
-      out.header = mesh.header;             // subset_extractor.cpp:52-53
-      out.cloud.header = mesh.cloud.header;
-      if (faces[k].empty())
-        continue;  // simplify() returns at once: the output stays a default-constructed mesh
-      std::vector<std::uint32_t> used;
-      for (std::uint32_t f : faces[k])
-        for (auto v : mesh.polygons[f].vertices)
-          if (new_index[v] < 0)
-          {
-            new_index[v] = static_cast<std::int64_t>(used.size());
-            used.push_back(static_cast<std::uint32_t>(v));
-          }
-      out.polygons.reserve(faces[k].size());
-      if (used.size() == V)
-      {
-        out.cloud = mesh.cloud;  // every point is used: the cloud as it is
-        for (std::uint32_t f : faces[k])
-          out.polygons.push_back(mesh.polygons[f]);
-      }
-      else
-      {
-        out.cloud.fields = mesh.cloud.fields;
-        out.cloud.point_step = mesh.cloud.point_step;
-        out.cloud.is_bigendian = mesh.cloud.is_bigendian;
-        out.cloud.height = 1;
-        out.cloud.width = static_cast<std::uint32_t>(used.size());
-        out.cloud.row_step = out.cloud.point_step * out.cloud.width;
-        out.cloud.is_dense = false;
-        out.cloud.data.resize(static_cast<std::size_t>(out.cloud.width) * out.cloud.point_step);
-        for (std::size_t i = 0; i < used.size(); ++i)
-          std::memcpy(out.cloud.data.data() + i * out.cloud.point_step,
-                      mesh.cloud.data.data() + static_cast<std::size_t>(used[i]) * mesh.cloud.point_step, mesh.cloud.point_step);
-        for (std::uint32_t f : faces[k])
-        {
-          pcl::Vertices p;
-          p.vertices.resize(mesh.polygons[f].vertices.size());
-          for (std::size_t i = 0; i < p.vertices.size(); ++i)
-            p.vertices[i] = static_cast<decltype(p.vertices)::value_type>(new_index[mesh.polygons[f].vertices[i]]);
-          out.polygons.push_back(std::move(p));
-        }
-      }
-      for (std::uint32_t v : used)
-        new_index[v] = -1;
-    }
-    return result;
+    return cutClusterMeshes(mesh, labels.data(), min_cluster_size_, max_cluster_size_);
   }
 
 private:
@@ -1092,6 +1101,12 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSm
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_EuclideanClusteringMeshModifier, EuclideanClustering)
+/** test hook (tests/cpp/plugin_shim_test.cpp --cpu-only): the host side of EuclideanClustering without a device */
+extern "C" void noether_b200_cut_cluster_meshes(const pcl::PolygonMesh* mesh, const std::uint32_t* labels, int min_cluster_size,
+                                                int max_cluster_size, std::vector<pcl::PolygonMesh>* out)
+{
+  *out = noether_b200::cutClusterMeshes(*mesh, labels, min_cluster_size, max_cluster_size);
+}
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceMidpointSubdivisionMeshModifier, FaceMidpointSubdivision)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceSubdivisionByAreaMeshModifier, FaceSubdivisionByArea)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)

@@ -856,31 +856,9 @@ void testFaceSubdivision(const noether::Factory& factory, const pcl::PolygonMesh
   }
 }
 
-/** EuclideanClustering through the plugin boundary with the YAML of the reference's own test (mesh_modifier_utest.cpp:15-19:
- *  tolerance 1.0, min 1, max -1): non-empty meshes with polygons and the input's fields (:130-183) — on this connected
- *  surface one cluster that uses every point, i.e. the input itself; and two copies of the surface far apart come back as
- *  two meshes, largest first, each renumbered from zero. */
-void testEuclideanClustering(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+/** the surface twice, the copy shifted by 100 in z and without its last 200 faces */
+pcl::PolygonMesh twoSurfaces(const pcl::PolygonMesh& mesh)
 {
-  std::printf("[MeshModifier EuclideanClustering]\n");
-  YAML::Node config;
-  config["name"] = "EuclideanClustering";
-  config["tolerance"] = 1.0;
-  config["min_cluster_size"] = 1;
-  config["max_cluster_size"] = -1;
-  auto modifier = factory.createMeshModifier(config);
-  {
-    const std::vector<pcl::PolygonMesh> out = modifier->modify(mesh);
-    CHECK(out.size() == 1);
-    if (!out.empty())
-    {
-      CHECK(out[0].polygons.size() == mesh.polygons.size());
-      CHECK(out[0].cloud.width * out[0].cloud.height == mesh.cloud.width * mesh.cloud.height);
-      CHECK(out[0].cloud.fields.size() == mesh.cloud.fields.size());
-      CHECK(out[0].cloud.data == mesh.cloud.data);
-    }
-  }
-  // the surface twice, the copy shifted by 100 in z and without its last 200 faces
   unsigned off_z = 0;
   for (const auto& g : mesh.cloud.fields)
     if (g.name == "z")
@@ -905,7 +883,11 @@ void testEuclideanClustering(const noether::Factory& factory, const pcl::Polygon
       v += V;
     two.polygons.push_back(p);
   }
-  const std::vector<pcl::PolygonMesh> out = modifier->modify(two);
+  return two;
+}
+
+void checkTwoSurfaces(const std::vector<pcl::PolygonMesh>& out, const pcl::PolygonMesh& mesh, std::uint32_t V)
+{
   CHECK(out.size() == 2);
   if (out.size() == 2)
   {
@@ -924,6 +906,80 @@ void testEuclideanClustering(const noether::Factory& factory, const pcl::Polygon
       CHECK(top + 1 == m.cloud.width);
     }
   }
+}
+
+/** The host side of EuclideanClustering (size filter, PCL's size sort, sub-mesh cutting) through the plugin library's test
+ *  hook, with the labels the device would return for two surfaces far apart: no GPU needed. */
+void testClusterMeshesHost(void* lib, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[EuclideanClustering, host side]\n");
+  using Hook = void (*)(const pcl::PolygonMesh*, const std::uint32_t*, int, int, std::vector<pcl::PolygonMesh>*);
+  auto hook = reinterpret_cast<Hook>(dlsym(lib, "noether_b200_cut_cluster_meshes"));
+  CHECK(hook != nullptr);
+  if (!hook)
+    return;
+  const std::uint32_t V = mesh.cloud.width * mesh.cloud.height;
+  const pcl::PolygonMesh two = twoSurfaces(mesh);
+  std::vector<std::uint32_t> labels(2 * V, 0);
+  std::fill(labels.begin() + V, labels.end(), V);
+  std::vector<pcl::PolygonMesh> out;
+  hook(&two, labels.data(), 1, -1, &out);
+  checkTwoSurfaces(out, mesh, V);
+  // one cluster that uses every point: the input itself
+  std::vector<std::uint32_t> zeros(V, 0);
+  hook(&mesh, zeros.data(), 1, -1, &out);
+  CHECK(out.size() == 1 && out[0].polygons.size() == mesh.polygons.size() && out[0].cloud.data == mesh.cloud.data &&
+        out[0].cloud.width == mesh.cloud.width && out[0].cloud.height == mesh.cloud.height);
+  // every point its own cluster: V default-constructed meshes; with min_cluster_size 2 nothing is left
+  std::vector<std::uint32_t> iota(V);
+  for (std::uint32_t v = 0; v < V; ++v)
+    iota[v] = v;
+  hook(&mesh, iota.data(), 1, -1, &out);
+  CHECK(out.size() == V);
+  bool all_empty = true;
+  for (const auto& m : out)
+    all_empty = all_empty && m.polygons.empty() && m.cloud.data.empty() && m.cloud.fields.empty();
+  CHECK(all_empty);
+  hook(&mesh, iota.data(), 2, -1, &out);
+  CHECK(out.empty());
+  // the size filter and the size sort: the copy's cluster made one point larger by moving a point of the original over
+  labels[0] = V;   // point 0 now belongs to the second cluster (size V + 1 against V - 1): it comes first
+  hook(&two, labels.data(), 1, -1, &out);
+  CHECK(out.size() == 2 && out[0].polygons.size() == mesh.polygons.size() - 200);
+  hook(&two, labels.data(), static_cast<int>(V), -1, &out);
+  CHECK(out.size() == 1);
+  hook(&two, labels.data(), 1, static_cast<int>(V), &out);
+  CHECK(out.size() == 1 && out[0].polygons.size() < mesh.polygons.size());
+}
+
+/** EuclideanClustering through the plugin boundary with the YAML of the reference's own test (mesh_modifier_utest.cpp:15-19:
+ *  tolerance 1.0, min 1, max -1): non-empty meshes with polygons and the input's fields (:130-183) — on this connected
+ *  surface one cluster that uses every point, i.e. the input itself; and two copies of the surface far apart come back as
+ *  two meshes, largest first, each renumbered from zero. */
+void testEuclideanClustering(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[MeshModifier EuclideanClustering]\n");
+  YAML::Node config;
+  config["name"] = "EuclideanClustering";
+  config["tolerance"] = 1.0;
+  config["min_cluster_size"] = 1;
+  config["max_cluster_size"] = -1;
+  auto modifier = factory.createMeshModifier(config);
+  {
+    const std::vector<pcl::PolygonMesh> out = modifier->modify(mesh);
+    CHECK(out.size() == 1);
+    if (!out.empty())
+    {
+      CHECK(out[0].polygons.size() == mesh.polygons.size());
+      CHECK(out[0].cloud.width * out[0].cloud.height == mesh.cloud.width * mesh.cloud.height);
+      CHECK(out[0].cloud.fields.size() == mesh.cloud.fields.size());
+      CHECK(out[0].cloud.data == mesh.cloud.data);
+    }
+  }
+  const pcl::PolygonMesh two = twoSurfaces(mesh);
+  const std::uint32_t V = mesh.cloud.width * mesh.cloud.height;
+  const std::vector<pcl::PolygonMesh> out = modifier->modify(two);
+  checkTwoSurfaces(out, mesh, V);
 }
 
 int main(int argc, char** argv)
@@ -949,6 +1005,12 @@ int main(int argc, char** argv)
       CHECK(dlsym(lib, alias) != nullptr);
     const pcl::PolygonMesh ply = loadPly(argv[2]);
     CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);
+    if (argc > 3 && std::string(argv[3]) == "--cpu-only")
+    {
+      testClusterMeshesHost(lib, ply);
+      std::printf(g_failures ? "%d check(s) FAILED\n" : "all checks passed\n", g_failures);
+      return g_failures ? 1 : 0;
+    }
     testFlatSquareMesh(factory, "PlaneSlicer");
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicer", false);
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);

@@ -65,3 +65,13 @@ def test_clustering_through_the_plugin_boundary(golden_dir):
                         "--clustering"], capture_output=True, text=True, timeout=300)
     print(r.stdout, r.stderr)
     assert r.returncode == 0
+
+
+def test_clustering_host_side_of_the_shim(golden_dir):
+    """size filter, PCL's size sort and sub-mesh cutting of the plugin library's EuclideanClustering, driven through its test
+    hook with the labels the device would return: no GPU involved"""
+    _build()
+    r = subprocess.run([os.path.join(OUT, "plugin_shim_test"), PLUGIN, os.path.join(golden_dir, "wavy_mesh_with_hole.ply"),
+                        "--cpu-only"], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "all checks passed" in r.stdout
