@@ -32,7 +32,11 @@ def _slab(be):
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
-    workers = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 1)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    workers = int(sys.argv[2]) if len(sys.argv) > 2 else min(cores, 64)
     nx, ny, spacing = WORKLOADS[name]
     orc.build()
     xyz, tri = meshes.wavy(nx, ny)
