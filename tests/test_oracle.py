@@ -374,3 +374,101 @@ def test_cpu_optimised_baseline_slabs_cover_the_plan(orc):
     assert o["workers"] == 3 and o["planes"] == int(lat.num_planes)
     assert (o["tool_paths"], o["waypoints"]) == (f.num_paths, int(f.seg_off[-1]))
     assert o["tri_per_s"] > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# properties of the slicer oracle on random surfaces (SURVEY.md §8 c: the oracle is the de-facto specification, so it is
+# checked against what a cut must satisfy independently of how it is computed)
+# ---------------------------------------------------------------------------------------------------------------------
+def _random_surface(rng):
+    from noether_b200 import meshes
+    nx, ny = int(rng.integers(3, 22)), int(rng.integers(3, 22))
+    xyz, tri = meshes.wavy(nx, ny, amp=float(rng.uniform(0, 0.06)), lam=float(rng.uniform(0.15, 0.6)))
+    if rng.random() < 0.5 and min(nx, ny) >= 6:
+        xyz, tri = meshes.cut_hole(xyz, tri, radius_frac=float(rng.uniform(0.08, 0.3)))
+    if rng.random() < 0.5:
+        a = rng.uniform(-np.pi, np.pi, 3)
+        cx, sx, cy, sy, cz, sz = np.cos(a[0]), np.sin(a[0]), np.cos(a[1]), np.sin(a[1]), np.cos(a[2]), np.sin(a[2])
+        R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+             @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+        xyz = (xyz.astype(np.float64) @ R.T + rng.uniform(-1, 1, 3)).astype(np.float32)
+    if rng.random() < 0.5:
+        xyz, tri = meshes.permute(xyz, tri, seed=int(rng.integers(1 << 30)))
+    return xyz, tri
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_property_cut_points_lie_on_their_plane_and_edge_and_chains_are_the_components(orc, seed):
+    rng = np.random.default_rng(31000 + seed)
+    xyz, tri = _random_surface(rng)
+    nrm = orc.normals_from_mesh_faces(xyz, tri)
+    spacing = float(rng.uniform(0.03, 0.2))
+    paths, lat, _ = orc.plan_plane_slicer(xyz, nrm, tri, spacing, True, slice_mode=orc.SLICE_INTENT, scan_mode=orc.SCAN_BINNED,
+                                          post_ops=False)
+    f = paths.flat()
+    if f.num_paths == 0:
+        return
+    n = np.array(lat.cut_normal)
+    start = np.array(lat.start_loc)
+    diag = float(np.linalg.norm(xyz.max(0) - xyz.min(0)))
+    X = xyz.astype(np.float64)
+    seg_of_wp = np.repeat(np.arange(len(f.seg_off) - 1), np.diff(f.seg_off).astype(np.int64))
+    path_of_seg = np.repeat(np.arange(f.num_paths), np.diff(f.path_off).astype(np.int64))
+    plane = f.path_plane[path_of_seg[seg_of_wp]]
+    pos = f.pos.astype(np.float64)
+    # (1) on the plane: n . (x - (start + k s n)) = 0 up to the float32 rounding of the stored point
+    origin = start[None, :] + (plane[:, None] * lat.line_spacing) * n[None, :]
+    assert np.abs(((pos - origin) * n).sum(1)).max() <= 4e-7 * max(diag, np.abs(pos).max())
+    # (2) on its generating mesh edge, between the endpoints, and that edge is an edge of a triangle
+    lo, hi = X[f.edge_lo], X[f.edge_hi]
+    e = hi - lo
+    L = np.linalg.norm(e, axis=1)
+    t = ((pos - lo) * e).sum(1) / np.maximum(L * L, 1e-300)
+    assert (t >= -1e-6).all() and (t <= 1 + 1e-6).all()
+    off = np.linalg.norm(pos - (lo + t[:, None] * e), axis=1)
+    assert off.max() <= 4e-7 * max(diag, np.abs(pos).max())
+    edges = set()
+    for a, b, c in tri.tolist():
+        edges.update({(min(a, b), max(a, b)), (min(b, c), max(b, c)), (min(a, c), max(a, c))})
+    assert all((min(a, b), max(a, b)) in edges or a == b for a, b in zip(f.edge_lo.tolist(), f.edge_hi.tolist()))
+    # (3) per plane: segments = connected components of the cut graph built independently from the per-plane scalars
+    #     (triangles with vertices on both sides of the plane, joined through the cut points they share)
+    for p in range(f.num_paths):
+        k = int(f.path_plane[p])
+        o = start + k * lat.line_spacing * n
+        s = (X - o) @ n
+        inside = s >= 0
+        cut = [i for i, (a, b, c) in enumerate(tri.tolist()) if not (inside[a] == inside[b] == inside[c])]
+        parent = list(range(len(cut)))
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+        by_point = {}
+        for i, ti in enumerate(cut):
+            a, b, c = tri[ti].tolist()
+            for u, v in ((a, b), (b, c), (c, a)):
+                if inside[u] != inside[v]:
+                    lo_v, hi_v = (u, v) if s[u] < s[v] else (v, u)
+                    tt = (0.0 - s[lo_v]) / (s[hi_v] - s[lo_v])
+                    key = (X[lo_v] + tt * (X[hi_v] - X[lo_v])).astype(np.float32).tobytes()   # vtkMergePoints: float equality
+                    if key in by_point:
+                        ra, rb = find(by_point[key]), find(i)
+                        parent[ra] = rb
+                    else:
+                        by_point[key] = i
+        components = len({find(i) for i in range(len(cut))})
+        n_seg = int(f.path_off[p + 1] - f.path_off[p])
+        assert n_seg == components, f"plane {k}: {n_seg} segments, {components} components of the cut graph"
+    # (4) maximal open chains: inside a segment consecutive waypoints differ; no two segments of a plane share an end point
+    for p in range(f.num_paths):
+        ends = []
+        for sgm in range(int(f.path_off[p]), int(f.path_off[p + 1])):
+            a, b = int(f.seg_off[sgm]), int(f.seg_off[sgm + 1])
+            assert b - a >= 2
+            assert (np.abs(np.diff(f.pos[a:b], axis=0)).sum(1) > 0).all()
+            if f.pos[a].tobytes() != f.pos[b - 1].tobytes():      # an open chain
+                ends += [f.pos[a].tobytes(), f.pos[b - 1].tobytes()]
+        assert len(ends) == len(set(ends))
