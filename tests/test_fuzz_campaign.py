@@ -251,3 +251,65 @@ def test_fuzz_modifiers_and_stl(ctx, orc):
                     failures.append(f"stl seed {seed}: {str(e)[:300]}")
     print(f"fuzz campaign (modifiers / stl): {ran} cases, {refused} refused by both, {len(failures)} failures")
     assert not failures, "\n".join(failures[:20])
+
+
+@pytest.mark.skipif(not os.environ.get("NB2_FUZZ"), reason="set NB2_FUZZ=kind:first_seed:count[,...] to run the campaign")
+def test_fuzz_mesh_modifiers(ctx, orc):
+    """kinds `sub` (face subdivision: random triangle soups over few vertices, every cloud layout, both modifiers) and
+    `clu` (Euclidean clustering: random clouds, snapped lattices, tolerances around the point spacing)"""
+    import noether_b200 as nb
+    import test_subdivide as tsub
+    from noether_b200 import meshes
+    ran = 0
+    failures = []
+    names = sorted(tsub.LAYOUTS)
+    for kind, first, count in _campaign():
+        for seed in range(first, first + count):
+            rng = np.random.default_rng(77000 + seed)
+            if kind == "sub":
+                V, F = int(rng.integers(3, 200)), int(rng.integers(1, 600))
+                xyz = (rng.normal(size=(V, 3)) * rng.choice([1e-3, 1.0, 50.0])).astype(np.float32)
+                tri = rng.integers(0, V, size=(F, 3)).astype(np.uint32)
+                if rng.random() < 0.3:   # a real surface instead of a soup
+                    xyz, tri = meshes.wavy(int(rng.integers(2, 40)), int(rng.integers(2, 40)))
+                layout = names[int(rng.integers(len(names)))]
+                step, ox, on, oc = tsub.LAYOUTS[layout]
+                cloud = tsub.make_cloud(xyz, layout, seed=seed)
+                blob = tsub.gpu_blob(cloud, layout, tri)
+                ran += 1
+                try:
+                    n = int(rng.integers(1, 4))
+                    out = nb.FaceMidpointSubdivisionMeshModifier(n, ctx, off_rgba=oc).modify(blob)[0]
+                    tsub.assert_same_mesh((out.data, out.tri), orc.face_midpoint_subdivision(cloud, step, ox, on, oc, tri, n),
+                                          f"sub seed {seed} midpoint n={n} {layout}")
+                    max_area = float(rng.choice(tsub.area_limits(xyz, tri)))
+                    out = nb.FaceSubdivisionByAreaMeshModifier(max_area, ctx, off_rgba=oc).modify(blob)[0]
+                    tsub.assert_same_mesh((out.data, out.tri), orc.face_subdivision_by_area(cloud, step, ox, on, oc, tri, max_area),
+                                          f"sub seed {seed} by area {max_area} {layout}")
+                except AssertionError as e:
+                    failures.append(str(e)[:300])
+            elif kind == "clu":
+                V = int(rng.integers(1, 3000))
+                scale = float(rng.choice([1e-3, 1.0, 250.0]))
+                xyz = (rng.normal(size=(V, 3)) * scale).astype(np.float32)
+                if rng.random() < 0.4:
+                    xyz = (np.round(xyz / (0.2 * scale)) * (0.2 * scale)).astype(np.float32)
+                tri = rng.integers(0, V, size=(int(rng.integers(0, 2 * V)), 3)).astype(np.uint32)
+                blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+                tol = float(rng.choice([0.0, 0.05, 0.2, 0.2000001, 0.4, 1.0, 3.0])) * scale
+                mn, mx = int(rng.choice([1, 1, 2, 5])), int(rng.choice([-1, -1, 50]))
+                ran += 1
+                try:
+                    ref, labels = orc.euclidean_clustering(blob.data, 16, 0, tri, tol, mn, mx)
+                    ctx.upload(blob, force=True)
+                    assert np.array_equal(ctx.euclidean_cluster_labels(tol, V), labels), f"clu seed {seed}: labels differ"
+                    got = nb.EuclideanClusteringMeshModifier(tol, mn, mx, ctx).modify(blob)
+                    assert len(got) == len(ref), f"clu seed {seed}: {len(got)} meshes, oracle {len(ref)}"
+                    for k, (g, r) in enumerate(zip(got, ref)):
+                        assert (g is None) == r.empty, f"clu seed {seed}: mesh {k} emptiness"
+                        if g is not None:
+                            assert np.array_equal(g.tri, r.tri) and np.array_equal(np.asarray(g.data), r.cloud), f"clu seed {seed}: mesh {k}"
+                except AssertionError as e:
+                    failures.append(str(e)[:300])
+    print(f"fuzz campaign (mesh modifiers): {ran} cases, {len(failures)} failures")
+    assert not failures, "\n".join(failures[:20])
