@@ -247,3 +247,16 @@ def test_gpu_labels_random_clouds_and_large(ctx, orc):
     with pytest.raises(_capi.Nb2Error) as e:
         ctx.euclidean_cluster_labels(10.0, len(both))       # the whole cloud in a handful of cells
     assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT
+
+
+def test_emulated_labels_larger_clouds_grid_path_of_the_oracle(emu, orc):
+    """a few thousand points (the oracle then searches through its own grid): dense blobs, snapped lattices"""
+    for seed in range(8):
+        rng = np.random.default_rng(5200 + seed)
+        V = int(rng.integers(2100, 6000))
+        xyz = (rng.normal(size=(V, 3)) * [1.0, 0.6, 0.05]).astype(np.float32)
+        if seed % 2:
+            xyz = (np.round(xyz / 0.05) * 0.05).astype(np.float32)
+        blob = meshes.pack_blob(xyz, None, np.zeros((0, 3), np.uint32), "PointXYZ")
+        for tol in (0.02, 0.05, 0.0500001, 0.11):
+            assert np.array_equal(emu_labels(emu, xyz, tol), oracle_meshes(orc, blob, tol)[1]), f"seed {seed} tol {tol}"
