@@ -142,6 +142,9 @@ typedef struct nb2_pca
 int nb2_mesh_pca(nb2_context* ctx, nb2_pca* out);
 int nb2_principal_axis_direction(nb2_context* ctx, double rotation_offset, double out_direction[3]);
 int nb2_centroid_origin(nb2_context* ctx, double out_origin[3]);
+/* AABBCenterOriginGenerator::generate (aabb_center_origin_generator.cpp:9-17): pcl::getMinMax3D of the vertices (the float
+ * AABB of the ingest pass), then (max - min) / 2 — half the range of the box, as the reference computes it. */
+int nb2_aabb_center_origin(nb2_context* ctx, double out_origin[3]);
 /* PCARotatedDirectionGenerator::generate (pca_rotated_direction_generator.cpp:13-25): the direction of a nested
  * generator rotated by rotation_angle about the smallest principal axis of the resident mesh. */
 int nb2_pca_rotated_direction(nb2_context* ctx, double rotation_angle, const double nominal_direction[3],

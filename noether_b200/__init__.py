@@ -5,7 +5,7 @@ boost_plugin_loader shim in plugin/.  This Python package is the host-side mirro
 interface used by tests and the benchmark; it only ever calls the C ABI.
 """
 from . import _capi, meshes  # noqa: F401
-from .planner import (CentroidOriginGenerator, Context, Factory, FixedDirectionGenerator,  # noqa: F401
+from .planner import (AABBCenterOriginGenerator, CentroidOriginGenerator, Context, Factory, FixedDirectionGenerator,  # noqa: F401
                       FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, FaceMidpointSubdivisionMeshModifier,
                       FaceSubdivisionByAreaMeshModifier, EuclideanClusteringMeshModifier, cluster_order, cluster_submeshes, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,

@@ -43,7 +43,7 @@ DECLARED_SYMBOLS = [
     "nb2_result_from_poses", "nb2_result_from_pose_segments", "nb2_result_modify",
     "nb2_stl_inspect", "nb2_mesh_upload_stl", "nb2_mesh_upload_file",
     "nb2_face_midpoint_subdivision", "nb2_face_subdivision_by_area", "nb2_mesh_download_cloud", "nb2_mesh_record_layout",
-    "nb2_euclidean_cluster_labels", "nb2_cluster_order",
+    "nb2_euclidean_cluster_labels", "nb2_cluster_order", "nb2_aabb_center_origin",
 ]
 
 NB2_MOD_SNAKE_ORGANIZATION = 1
@@ -150,6 +150,7 @@ def load():
     L.nb2_mesh_download_cloud.argtypes = [vp, C.c_void_p]
     L.nb2_euclidean_cluster_labels.argtypes = [vp, C.c_double, C.c_void_p]
     L.nb2_cluster_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.nb2_aabb_center_origin.argtypes = [vp, C.POINTER(C.c_double)]
     L.nb2_mesh_record_layout.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     L.nb2_mesh_pca.argtypes = [vp, C.POINTER(Pca)]
     L.nb2_principal_axis_direction.argtypes = [vp, C.c_double, C.POINTER(C.c_double)]

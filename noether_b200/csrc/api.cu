@@ -1414,6 +1414,21 @@ int nb2_pca_rotated_direction(nb2_context* c, double rotation_angle, const doubl
   NB2_API_END
 }
 
+int nb2_aabb_center_origin(nb2_context* c, double out[3])
+{
+  NB2_API_BEGIN
+  if (!c || !out)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or out is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  ensureHostPca(c);
+  // AABBCenterOriginGenerator::generate (aabb_center_origin_generator.cpp:9-17): pcl::getMinMax3D, then
+  // (max - min) in float, cast to double, halved — half the RANGE of the box, not its centre; restated as it is
+  for (int i = 0; i < 3; ++i)
+    out[i] = static_cast<double>(c->pca.aabb_max[i] - c->pca.aabb_min[i]) / 2.0;
+  NB2_API_END
+}
+
 int nb2_centroid_origin(nb2_context* c, double out[3])
 {
   NB2_API_BEGIN

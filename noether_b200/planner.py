@@ -424,6 +424,21 @@ class CentroidOriginGenerator(OriginGenerator):
         return ctx.centroid_origin()
 
 
+class AABBCenterOriginGenerator(OriginGenerator):
+    """aabb_center_origin_generator.cpp:9-17 — (max - min) / 2 of the float AABB (the reference's own arithmetic: half
+    the range of the box), from the AABB the ingest pass leaves on the device"""
+
+    def __init__(self, context: Context | None = None):
+        self._ctx = context
+
+    def generate(self, mesh):
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        out = (C.c_double * 3)()
+        _capi.check(ctx._lib.nb2_aabb_center_origin(ctx._h, out))
+        return np.array(out[:], np.float64)
+
+
 class PlaneSlicerRasterPlanner:
     """RasterPlanner::plan for the plane slicer (raster_planner.cpp:16-35, plane_slicer_raster_planner.cpp:518-631)"""
 
@@ -887,6 +902,8 @@ class Factory:
         name = _member(config, "name")
         if name == "Centroid":
             return CentroidOriginGenerator(self._ctx)
+        if name == "AABBCenter":  # plugins.cpp:110
+            return AABBCenterOriginGenerator(self._ctx)
         if name == "FixedOrigin":
             return FixedOriginGenerator(_vec3(_member(config, "origin")))
         raise RuntimeError(f"Failed to find plugin '{name}' in section 'og'")

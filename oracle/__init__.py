@@ -79,6 +79,7 @@ def lib():
     L.orc_last_error.restype = C.c_char_p
     L.orc_pca.argtypes = [f32p, C.c_uint64, C.c_int, C.POINTER(PcaResult)]
     L.orc_centroid.argtypes = [f32p, C.c_uint64, C.c_int, f64p]
+    L.orc_aabb_center_origin.argtypes = [f32p, C.c_uint64, f64p]
     L.orc_principal_axis_direction.argtypes = [C.POINTER(PcaResult), C.c_double, f64p]
     L.orc_pca_rotated_direction.argtypes = [C.POINTER(PcaResult), C.c_double, f64p, f64p]
     L.orc_eigen_solver_3f.argtypes = [f32p, f32p, f32p]
@@ -209,6 +210,14 @@ def centroid(xyz, mode=MOMENTS_F32_SEQUENTIAL) -> np.ndarray:
     a, p = _f32(xyz)
     out = np.zeros(3)
     _check(lib().orc_centroid(p, a.shape[0], mode, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def aabb_center_origin(xyz) -> np.ndarray:
+    """AABBCenterOriginGenerator::generate (aabb_center_origin_generator.cpp:9-17)"""
+    a, p = _f32(xyz)
+    out = np.zeros(3)
+    _check(lib().orc_aabb_center_origin(p, a.shape[0], out.ctypes.data_as(C.POINTER(C.c_double))))
     return out
 
 

@@ -60,6 +60,8 @@ typedef struct orc_pca_result
 
 int orc_pca(const float* xyz, uint64_t n_vertices, int moments_mode, orc_pca_result* out);
 int orc_centroid(const float* xyz, uint64_t n_vertices, int moments_mode, double out[3]);
+/* aabb_center_origin_generator.cpp:9-17: (max - min) / 2 of the float AABB (half the range, as the reference has it) */
+int orc_aabb_center_origin(const float* xyz, uint64_t n_vertices, double out[3]);
 int orc_principal_axis_direction(const orc_pca_result* pca, double rotation_offset, double out[3]);
 /* PCARotatedDirectionGenerator::generate (pca_rotated_direction_generator.cpp:13-25): the nominal direction of a nested
  * generator rotated about the smallest principal axis */

@@ -547,3 +547,26 @@ int normalsFromMeshFaces(const float* xyz, uint64_t V, const uint32_t* tri, uint
 }
 
 }  // namespace orc
+
+// AABBCenterOriginGenerator::generate (aabb_center_origin_generator.cpp:9-17): pcl::getMinMax3D (float min / max over the
+// points), Array3f difference, cast to double, / 2.0.  TEST INFRASTRUCTURE ONLY.
+extern "C" int orc_aabb_center_origin(const float* xyz, uint64_t n, double out[3])
+{
+  if (!xyz || !out || n == 0)
+  {
+    orc::setError("invalid argument");
+    return ORC_ERR_INVALID;
+  }
+  for (int i = 0; i < 3; ++i)
+  {
+    float mn = xyz[i], mx = xyz[i];
+    for (uint64_t v = 1; v < n; ++v)
+    {
+      mn = std::min(mn, xyz[3 * v + i]);
+      mx = std::max(mx, xyz[3 * v + i]);
+    }
+    const float range = mx - mn;
+    out[i] = static_cast<double>(range) / 2.0;
+  }
+  return ORC_OK;
+}

@@ -10,6 +10,7 @@
 //   PrincipalAxis         dg       PrincipalAxisDirectionGenerator        src/plugins.cpp:89
 //   PCARotated            dg       Plugin_PCARotatedDirectionGenerator    src/plugins.cpp:91-107
 //   Centroid              og       CentroidOriginGenerator                src/plugins.cpp:111
+//   AABBCenter            og       AABBCenterOriginGenerator              src/plugins.cpp:110
 //   NormalsFromMeshFaces  mesh     NormalsFromMeshFacesMeshModifier       src/plugins.cpp:62
 //   FaceMidpointSubdivision mesh   FaceMidpointSubdivisionMeshModifier    src/plugins.cpp:58
 //   FaceSubdivisionByArea mesh     FaceSubdivisionByAreaMeshModifier      src/plugins.cpp:59
@@ -421,6 +422,22 @@ public:
     ensureResident(dev, mesh, false);
     double o[3];
     Device::check(nb2_centroid_origin(dev.ctx(), o));
+    return Eigen::Vector3d(o[0], o[1], o[2]);
+  }
+};
+
+/** AABBCenterOriginGenerator (aabb_center_origin_generator.cpp:9-17): (max - min) / 2 of the float AABB, which the ingest
+ *  pass leaves on the device */
+class AABBCenterOriginGenerator : public noether::OriginGenerator
+{
+public:
+  Eigen::Vector3d generate(const pcl::PolygonMesh& mesh) const override final
+  {
+    Device& dev = Device::instance();
+    std::lock_guard<std::mutex> lock(dev.mutex());
+    ensureResident(dev, mesh, false);
+    double o[3];
+    Device::check(nb2_aabb_center_origin(dev.ctx(), o));
     return Eigen::Vector3d(o[0], o[1], o[2]);
   }
 };
@@ -893,6 +910,15 @@ struct Plugin_CentroidOriginGenerator : public noether::Plugin<noether::OriginGe
   }
 };
 
+struct Plugin_AABBCenterOriginGenerator : public noether::Plugin<noether::OriginGenerator>
+{
+  std::unique_ptr<noether::OriginGenerator> create(const YAML::Node& /*config*/,
+                                                   std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<AABBCenterOriginGenerator>();
+  }
+};
+
 struct Plugin_NormalsFromMeshFacesMeshModifier : public noether::Plugin<noether::MeshModifier>
 {
   std::unique_ptr<noether::MeshModifier> create(const YAML::Node& /*config*/,
@@ -1112,5 +1138,6 @@ EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_FaceSubdivisionByAreaMeshModifi
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PrincipalAxisDirectionGenerator, PrincipalAxis)
 EXPORT_DIRECTION_GENERATOR_PLUGIN(noether_b200::Plugin_PCARotatedDirectionGenerator, PCARotated)
 EXPORT_ORIGIN_GENERATOR_PLUGIN(noether_b200::Plugin_CentroidOriginGenerator, Centroid)
+EXPORT_ORIGIN_GENERATOR_PLUGIN(noether_b200::Plugin_AABBCenterOriginGenerator, AABBCenter)
 EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerRasterPlanner, PlaneSlicer)
 EXPORT_TOOL_PATH_PLANNER_PLUGIN(noether_b200::Plugin_PlaneSlicerLegacyRasterPlanner, PlaneSlicerLegacy)

@@ -739,3 +739,17 @@ def test_legacy_modifiers_on_device_match_oracle(ctx, orc, min_hole, min_seg):
     np.testing.assert_array_equal(gpu.poses(), ref.pose)      # bit for bit
     np.testing.assert_array_equal(bits(gpu.positions), bits(ref.pos))
     np.testing.assert_array_equal(bits(gpu.normals), bits(ref.nrm))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: first B200 run happens at round end", strict=False)
+def test_aabb_center_origin_matches_oracle(ctx, orc, ply_mesh):
+    """AABBCenterOriginGenerator (aabb_center_origin_generator.cpp:9-17) from the AABB of the ingest pass, bit for bit, and as
+    the origin generator of a plan"""
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    for blob in (ply_mesh, meshes.pack_blob(*(lambda x, t: (x, None, t))(*meshes.wavy(64, 48)), "PointXYZ")):
+        got = nb.AABBCenterOriginGenerator(ctx).generate(blob)
+        assert np.array_equal(got, orc.aabb_center_origin(blob.xyz()))
+    gen = nb.Factory(ctx).create_origin_generator({"name": "AABBCenter"})
+    assert np.array_equal(gen.generate(ply_mesh), orc.aabb_center_origin(ply_mesh.xyz()))

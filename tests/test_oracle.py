@@ -472,3 +472,12 @@ def test_property_cut_points_lie_on_their_plane_and_edge_and_chains_are_the_comp
             if f.pos[a].tobytes() != f.pos[b - 1].tobytes():      # an open chain
                 ends += [f.pos[a].tobytes(), f.pos[b - 1].tobytes()]
         assert len(ends) == len(set(ends))
+
+
+def test_kat_aabb_center_origin_is_half_the_range(orc):
+    """aabb_center_origin_generator.cpp:15-16 returns (max - min) / 2, not the centre of the box: restated as it is"""
+    xyz = np.array([[1, 2, 3], [4, 0, 5], [-2, 1, 9]], np.float32)
+    assert orc.aabb_center_origin(xyz).tolist() == [3.0, 1.0, 3.0]
+    rng = np.random.default_rng(5)
+    x = (rng.normal(size=(1000, 3)) * 37).astype(np.float32)
+    assert np.array_equal(orc.aabb_center_origin(x), (x.max(0) - x.min(0)).astype(np.float64) / 2.0)

@@ -22,7 +22,7 @@ def test_plugin_library_builds_and_exports_the_reference_aliases():
     syms = subprocess.run(["nm", "-D", "--defined-only", PLUGIN], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in syms.splitlines() if line.strip()}
     # aliases of noether_tpp/src/plugins.cpp:62,89,111,179,278
-    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
+    for alias in ("PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "AABBCenter", "NormalsFromMeshFaces",
                   "FaceMidpointSubdivision", "FaceSubdivisionByArea", "EuclideanClustering",  # plugins.cpp:57-59
                   # tool path modifiers that run on the device (plugins.cpp:182-199,219)
                   "SnakeOrganization", "LinearApproach", "LinearDeparture", "Offset", "FixedOrientation", "UniformOrientation",
