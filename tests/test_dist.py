@@ -100,3 +100,20 @@ def test_lpt_assignment_of_the_mesh_batch():
     assert max(loads) <= 1.05 * sum(sizes) / 8           # within 5 % of perfect balance on this batch
     assert lpt_assign(sizes, 8) == shares                # deterministic: every rank derives the same assignment
     assert lpt_assign([5, 5, 5], 1) == [[0, 1, 2]]
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` (the reference's CPU algorithm through the oracle) needs no device and prints the
+    contract's keys"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg2", "--steps", "1",
+                        "--warmup", "1", "--cpu-planes", "8"], capture_output=True, text=True, timeout=600, check=True)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "triangles sliced/sec" and line["unit"] == "triangles/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
