@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NB2_ABI_VERSION 1
+#define NB2_ABI_VERSION 2
 
 typedef enum nb2_status
 {
@@ -114,8 +114,9 @@ int nb2_stl_inspect(const void* file_image, uint64_t n_bytes, nb2_mesh_file_info
 int nb2_mesh_upload_stl(nb2_context* ctx, const void* file_image, uint64_t n_bytes, nb2_mesh_file_info* info /* may be NULL */);
 /* pcl::io::loadPolygonFile(path, mesh): dispatch on the extension (.ply / .stl); the file is memory-mapped. */
 int nb2_mesh_upload_file(nb2_context* ctx, const char* path, nb2_mesh_file_info* info /* may be NULL */);
-/* Copy the resident triangle list back (uint32[3 * n_triangles]).  Test / debugging aid. */
-int nb2_mesh_download_triangles(nb2_context* ctx, uint32_t* triangles);
+/* Copy the resident triangle list back (uint32[3 * n_triangles]); `capacity_triangles` = triangles the buffer holds
+ * (refused with NB2_ERR_INVALID_ARGUMENT when the resident mesh has more). */
+int nb2_mesh_download_triangles(nb2_context* ctx, uint32_t* triangles, uint64_t capacity_triangles);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * PCA frame.  Replaces the pcl::PCA block of planImpl (plane_slicer_raster_planner.cpp:534-553), and feeds
@@ -185,8 +186,10 @@ int nb2_normals_from_mesh_faces(nb2_context* ctx, float* normals_out);
 int nb2_face_midpoint_subdivision(nb2_context* ctx, uint32_t n_iterations, int32_t offset_rgba, nb2_mesh_file_info* info /* may be NULL */);
 int nb2_face_subdivision_by_area(nb2_context* ctx, float max_area, int32_t offset_rgba, uint64_t max_points,
                                  nb2_mesh_file_info* info /* may be NULL */);
-/* Copy the resident cloud back: n_points records of point_step bytes (pcl::PCLPointCloud2::data). */
-int nb2_mesh_download_cloud(nb2_context* ctx, void* cloud_data);
+/* Copy the resident cloud back: n_points records of point_step bytes (pcl::PCLPointCloud2::data); `capacity_bytes` =
+ * size of the buffer (refused with NB2_ERR_INVALID_ARGUMENT when the resident cloud is larger: the record layout on the
+ * device is the uploaded one, nb2_mesh_record_layout, not necessarily the caller's). */
+int nb2_mesh_download_cloud(nb2_context* ctx, void* cloud_data, uint64_t capacity_bytes);
 /* Record layout of the resident cloud; any pointer may be NULL. */
 int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_t* offset_xyz, int32_t* offset_normal);
 
@@ -194,7 +197,7 @@ int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_
  * EuclideanClusteringMeshModifier::modify (euclidean_clustering_modifier.cpp:40-64), device part: the
  * connected components pcl::EuclideanClusterExtraction grows with one k-d tree radius search per point — two points are
  * linked when FLANN's float squared distance ((dx^2) + dy^2) + dz^2 is strictly below float(tolerance^2).
- * labels[v] (uint32[n_points], host memory) = the smallest point index of v's component = the seed PCL starts that
+ * labels[v] (uint32[n_points], host memory, `capacity_labels` entries) = the smallest point index of v's component = the seed PCL starts that
  * cluster from, so ascending labels are PCL's clusters in order of discovery.  tolerance <= 0 finds no neighbours
  * (labels[v] = v).  The size filter (min_cluster_size / max_cluster_size), PCL's reverse std::sort by size and
  * extractSubMeshFromInlierVertices (subset_extractor.cpp:22-56) are index bookkeeping on the labels and are done by the
@@ -203,7 +206,7 @@ int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_
  * pairs (the reference's radius searches would each return a large
  * part of the cloud as well).
  * ------------------------------------------------------------------------------------------------------------------ */
-int nb2_euclidean_cluster_labels(nb2_context* ctx, double tolerance, uint32_t* labels);
+int nb2_euclidean_cluster_labels(nb2_context* ctx, double tolerance, uint32_t* labels, uint64_t capacity_labels);
 /* Host only (no context): the order pcl::EuclideanClusterExtraction::extract leaves its clusters in —
  * std::sort(clusters.rbegin(), clusters.rend(), comparePointClusters), largest first, equal sizes as the library's
  * introsort leaves them — for clusters given in order of discovery (ascending label) with these sizes, after the size

@@ -141,14 +141,14 @@ def load():
     L.nb2_ply_inspect.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_upload_ply.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_upload_ply_file.argtypes = [vp, C.c_char_p, C.POINTER(MeshFileInfo)]
-    L.nb2_mesh_download_triangles.argtypes = [vp, C.c_void_p]
+    L.nb2_mesh_download_triangles.argtypes = [vp, C.c_void_p, C.c_uint64]
     L.nb2_stl_inspect.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_upload_stl.argtypes = [vp, C.c_void_p, C.c_uint64, C.POINTER(MeshFileInfo)]
     L.nb2_mesh_upload_file.argtypes = [vp, C.c_char_p, C.POINTER(MeshFileInfo)]
     L.nb2_face_midpoint_subdivision.argtypes = [vp, C.c_uint32, C.c_int32, C.POINTER(MeshFileInfo)]
     L.nb2_face_subdivision_by_area.argtypes = [vp, C.c_float, C.c_int32, C.c_uint64, C.POINTER(MeshFileInfo)]
-    L.nb2_mesh_download_cloud.argtypes = [vp, C.c_void_p]
-    L.nb2_euclidean_cluster_labels.argtypes = [vp, C.c_double, C.c_void_p]
+    L.nb2_mesh_download_cloud.argtypes = [vp, C.c_void_p, C.c_uint64]
+    L.nb2_euclidean_cluster_labels.argtypes = [vp, C.c_double, C.c_void_p, C.c_uint64]
     L.nb2_cluster_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     L.nb2_aabb_center_origin.argtypes = [vp, C.POINTER(C.c_double)]
     L.nb2_mesh_record_layout.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]

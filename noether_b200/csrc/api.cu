@@ -504,6 +504,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     if (!download)
     {
       r->device_resident = true;
+      r->plan_serial = c->plan_serial;
       r->dev_edges = emit_edges;
       r->slab_begin = plane_begin;
       r->slab_planes = 0;
@@ -568,6 +569,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     r->path_plane = nullptr;
     r->positions = r->normals = nullptr;
     r->device_resident = true;
+    r->plan_serial = c->plan_serial;
     r->dev_w_cap = w_cap;
     r->dev_edges = emit_edges;
     r->slab_begin = plane_begin;
@@ -732,7 +734,7 @@ void nb2_context_destroy(nb2_context* c)
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
                      &c->modSegPath, &c->modPathOff, &c->modPathSign, &c->modPos, &c->modNrm, &c->modQuat, &c->modRot, &c->modEnds, &c->stlSlots, &c->stlCorner,
                      &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix, &c->subBlob[0], &c->subBlob[1], &c->subTri[0], &c->subTri[1], &c->subLevels,
-                     &c->subKeys, &c->cluHead, &c->cluNext, &c->cluParent, &c->cluLabel, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
+                     &c->subKeys, &c->cluHead, &c->cluNext, &c->cluParent, &c->cluLabel, &c->cluCellSize, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
   c->hostSmall.release();
   for (auto& hb : c->hostPool)
@@ -1133,7 +1135,7 @@ int nb2_mesh_upload_file(nb2_context* c, const char* path, nb2_mesh_file_info* i
   NB2_API_END
 }
 
-int nb2_mesh_download_triangles(nb2_context* c, uint32_t* triangles)
+int nb2_mesh_download_triangles(nb2_context* c, uint32_t* triangles, uint64_t capacity_triangles)
 {
   NB2_API_BEGIN
   if (!c || !triangles)
@@ -1141,13 +1143,16 @@ int nb2_mesh_download_triangles(nb2_context* c, uint32_t* triangles)
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard g(c->device);
   requireMesh(c);
+  if (capacity_triangles < c->F)
+    fail(NB2_ERR_INVALID_ARGUMENT, "nb2_mesh_download_triangles: the buffer holds " + std::to_string(capacity_triangles) +
+                                       " triangles but the resident mesh has " + std::to_string(c->F));
   if (c->F)
     NB2_CUDA(cudaMemcpyAsync(triangles, c->tri.ptr, sizeof(uint32_t) * 3 * c->F, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
   NB2_API_END
 }
 
-int nb2_mesh_download_cloud(nb2_context* c, void* cloud_data)
+int nb2_mesh_download_cloud(nb2_context* c, void* cloud_data, uint64_t capacity_bytes)
 {
   NB2_API_BEGIN
   if (!c || !cloud_data)
@@ -1155,6 +1160,10 @@ int nb2_mesh_download_cloud(nb2_context* c, void* cloud_data)
   std::lock_guard<std::mutex> lock(c->mu);
   DeviceGuard g(c->device);
   requireMesh(c);
+  if (capacity_bytes < c->V * c->rec_step)
+    fail(NB2_ERR_INVALID_ARGUMENT, "nb2_mesh_download_cloud: the buffer holds " + std::to_string(capacity_bytes) +
+                                       " bytes but the resident cloud has " + std::to_string(c->V) + " records of " +
+                                       std::to_string(c->rec_step) + " bytes");
   NB2_CUDA(cudaMemcpyAsync(cloud_data, c->blob.ptr, c->V * c->rec_step, cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
   NB2_API_END
@@ -1286,7 +1295,7 @@ int nb2_cluster_order(const uint32_t* cluster_sizes, uint64_t n_clusters, uint32
   NB2_API_END
 }
 
-int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* labels)
+int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* labels, uint64_t capacity_labels)
 {
   NB2_API_BEGIN
   if (!c || !labels)
@@ -1297,6 +1306,9 @@ int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* lab
   DeviceGuard g(c->device);
   requireMesh(c);
   const uint64_t V = c->V;
+  if (capacity_labels < V)
+    fail(NB2_ERR_INVALID_ARGUMENT, "nb2_euclidean_cluster_labels: the buffer holds " + std::to_string(capacity_labels) +
+                                       " labels but the resident cloud has " + std::to_string(V) + " points");
   if (!(tolerance > 0.0))
   {
     // a radius search with radius <= 0 finds nothing, not even the query point: every point is its own cluster
@@ -1314,7 +1326,7 @@ int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* lab
     const double cells = (static_cast<double>(c->pca.aabb_max[i]) - grid.mn[i]) / grid.h;
     if (!(cells < clu::kMaxCells))
       fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: tolerance " + std::to_string(tolerance) +
-                                         " is less than 1e-18 of the extent of the cloud");
+                                         " is less than 2^-40 of the extent of the cloud");
   }
   launchClusterLabels(c, grid, 4e11, labels);
   NB2_API_END

@@ -21,7 +21,10 @@ namespace clu
 {
 constexpr unsigned long long kEmptyCell = ~0ull;
 constexpr unsigned kNone = 0xffffffffu;
-constexpr double kMaxCells = 4.0e18;  // cells per axis: what a long long cell coordinate holds
+// Cells per axis.  cellCoord divides in double (relative error about 2^-52) while the safety margin of the cell size is
+// 2^-10 of a cell: beyond about 2^41 cells per axis two points within the tolerance could land two cells apart and never
+// be compared.  2^40 keeps a factor of two in hand; wider grids are refused.
+constexpr double kMaxCells = 1099511627776.0;
 
 struct GridParams
 {
@@ -125,6 +128,20 @@ NB2_HD inline void unite(unsigned* parent, unsigned a, unsigned b, Cas32 cas)
     if (cas(parent + a, a, b) == a)
       return;
   }
+}
+
+/** slot of the cell that holds (x, y, z), or kNone when no point was inserted there */
+NB2_HD inline unsigned findCellSlot(const GridParams& g, long long x, long long y, long long z, const unsigned long long* cell_key,
+                                    unsigned slot_mask)
+{
+  if (x < 0 || y < 0 || z < 0)
+    return kNone;
+  const unsigned long long key = cellKey(x, y, z);
+  unsigned s = hashCell(key) & slot_mask;
+  unsigned long long seen;
+  while ((seen = cell_key[s]) != key && seen != kEmptyCell)
+    s = (s + 1) & slot_mask;
+  return seen == kEmptyCell ? kNone : s;
 }
 
 /** C2: point p against the points with a smaller index in its 27 surrounding cells */

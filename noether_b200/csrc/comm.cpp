@@ -139,6 +139,11 @@ int nb2_comm_unique_id(uint8_t out[NB2_UNIQUE_ID_BYTES])
     setLastError(e.msg);
     return e.status;
   }
+  catch (const std::exception& e)  // std::bad_alloc of the host vectors: nothing may unwind through the C ABI
+  {
+    setLastError(std::string("internal error: ") + e.what());
+    return NB2_ERR_INTERNAL;
+  }
   return NB2_OK;
 }
 
@@ -162,6 +167,11 @@ int nb2_comm_init(nb2_context* c, const uint8_t unique_id[NB2_UNIQUE_ID_BYTES], 
   {
     setLastError(e.msg);
     return e.status;
+  }
+  catch (const std::exception& e)  // std::bad_alloc of the host vectors: nothing may unwind through the C ABI
+  {
+    setLastError(std::string("internal error: ") + e.what());
+    return NB2_ERR_INTERNAL;
   }
   return NB2_OK;
 }
@@ -197,6 +207,10 @@ int nb2_result_gather(nb2_context* c, const nb2_result* local, int root, nb2_res
       fail(NB2_ERR_INVALID_ARGUMENT, "nb2_result_gather takes the slab result of a sharded nb2_plan (shard_count > 1) on "
                                      "this context");
     std::lock_guard<std::mutex> lock(c->mu);
+    // the slab lives in the context's output buffers until the next plan overwrites (or reallocates) them
+    if (local->plan_serial != c->plan_serial)
+      fail(NB2_ERR_INVALID_ARGUMENT, "nb2_result_gather: another plan ran on this context after the slab result was "
+                                     "produced; its device buffers no longer hold that slab");
     NB2_CUDA(cudaSetDevice(c->device));
     auto comm = static_cast<ncclComm_t>(c->nccl_comm);
     const int world = c->comm_world, rank = c->comm_rank;
@@ -392,6 +406,11 @@ int nb2_result_gather(nb2_context* c, const nb2_result* local, int root, nb2_res
   {
     setLastError(e.msg);
     return e.status;
+  }
+  catch (const std::exception& e)  // std::bad_alloc of the host vectors: nothing may unwind through the C ABI
+  {
+    setLastError(std::string("internal error: ") + e.what());
+    return NB2_ERR_INTERNAL;
   }
   return NB2_OK;
 }

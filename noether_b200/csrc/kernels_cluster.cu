@@ -73,6 +73,71 @@ __global__ void __launch_bounds__(256)
     linkPoint(g, p, DevPos{ pos }, cell_key, cell_head, slot_mask, next, parent, DevCas32{});
 }
 
+/** points per occupied cell slot (C1b) */
+__global__ void __launch_bounds__(256)
+    k_clu_cell_sizes(GridParams g, const float4* __restrict__ pos, unsigned V, const unsigned long long* __restrict__ cell_key,
+                     unsigned slot_mask, unsigned* __restrict__ cell_size)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+  {
+    const float4 q = __ldg(pos + p);
+    const unsigned s = findCellSlot(g, cellCoord(g, 0, q.x), cellCoord(g, 1, q.y), cellCoord(g, 2, q.z), cell_key, slot_mask);
+    if (s != kNone)
+      atomicAdd(cell_size + s, 1u);
+  }
+}
+
+/** The work k_clu_link is about to do, exactly (C1c): every point walks the chains of its 27 surrounding cells, so the number
+ *  of chain steps is the sum over the points of the sizes of those cells — whatever the distribution of the points over the
+ *  cells.  work[0] = that sum, work[1] = the longest walk of a single point (one thread does it serially). */
+__global__ void __launch_bounds__(256)
+    k_clu_work(GridParams g, const float4* __restrict__ pos, unsigned V, const unsigned long long* __restrict__ cell_key,
+               unsigned slot_mask, const unsigned* __restrict__ cell_size, unsigned long long* __restrict__ work)
+{
+  __shared__ unsigned long long s_sum[8], s_max[8];
+  unsigned long long sum = 0, mx = 0;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+  {
+    const float4 q = __ldg(pos + p);
+    const long long c[3] = { cellCoord(g, 0, q.x), cellCoord(g, 1, q.y), cellCoord(g, 2, q.z) };
+    unsigned long long mine = 0;
+    for (long long dz = -1; dz <= 1; ++dz)
+      for (long long dy = -1; dy <= 1; ++dy)
+        for (long long dx = -1; dx <= 1; ++dx)
+        {
+          const unsigned s = findCellSlot(g, c[0] + dx, c[1] + dy, c[2] + dz, cell_key, slot_mask);
+          if (s != kNone)
+            mine += cell_size[s];
+        }
+    sum += mine;
+    mx = mine > mx ? mine : mx;
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    sum += __shfl_down_sync(0xffffffffu, sum, o);
+    const unsigned long long other = __shfl_down_sync(0xffffffffu, mx, o);
+    mx = other > mx ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+    s_sum[threadIdx.x >> 5] = sum;
+    s_max[threadIdx.x >> 5] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    for (int w = 1; w < 8; ++w)
+    {
+      sum += s_sum[w];
+      mx = s_max[w] > mx ? s_max[w] : mx;
+    }
+    atomicAdd(work, sum);
+    atomicMax(work + 1, mx);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_clu_flatten(unsigned* parent, unsigned V, unsigned* __restrict__ label)
 {
   const unsigned stride = gridDim.x * blockDim.x;
@@ -87,7 +152,9 @@ inline int gridFor(unsigned long long n, const nb2_context* c)
 }
 }  // namespace
 
-/** labels of the resident cloud into `labels_host` (uint32[V]); `max_tests` bounds the distance tests (27 V V / cells) */
+/** labels of the resident cloud into `labels_host` (uint32[V]); `max_tests` bounds the chain steps of k_clu_link, counted
+ *  exactly on the device before that kernel is launched (a skewed cloud — most points in a few cells — cannot slip under an
+ *  average-occupancy estimate and turn the link pass quadratic) */
 void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host)
 {
   const uint64_t V = c->V;
@@ -100,26 +167,40 @@ void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_te
   c->cluNext.ensure(sizeof(unsigned) * V);
   c->cluParent.ensure(sizeof(unsigned) * V);
   c->cluLabel.ensure(sizeof(unsigned) * V);
+  c->cluCellSize.ensure(sizeof(unsigned) * slots + 2 * sizeof(unsigned long long));
+  unsigned long long* work = reinterpret_cast<unsigned long long*>(c->cluCellSize.as<unsigned>() + slots);
   unsigned* occupied = c->counters.as<unsigned>() + 21;
   NB2_CUDA(cudaMemsetAsync(c->subKeys.ptr, 0xff, sizeof(unsigned long long) * slots, st));
   NB2_CUDA(cudaMemsetAsync(c->cluHead.ptr, 0xff, sizeof(unsigned) * slots, st));
   NB2_CUDA(cudaMemsetAsync(occupied, 0, sizeof(unsigned), st));
+  NB2_CUDA(cudaMemsetAsync(c->cluCellSize.ptr, 0, sizeof(unsigned) * slots + 2 * sizeof(unsigned long long), st));
   const unsigned n = static_cast<unsigned>(V);
   k_clu_insert<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
                                              static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), c->cluParent.as<unsigned>(),
                                              occupied);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
+  k_clu_cell_sizes<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(),
+                                                 static_cast<unsigned>(slots - 1), c->cluCellSize.as<unsigned>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  k_clu_work<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(),
+                                           static_cast<unsigned>(slots - 1), c->cluCellSize.as<unsigned>(), work);
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
   c->hostSmall.ensure(4096);
   unsigned* h = c->hostSmall.as<unsigned>();
+  unsigned long long* hw = reinterpret_cast<unsigned long long*>(h + 2);
   NB2_CUDA(cudaMemcpyAsync(h, occupied, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaMemcpyAsync(hw, work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   NB2_CUDA(cudaStreamSynchronize(st));
-  const double cells = std::max(1u, h[0]);
-  const double tests = 27.0 * static_cast<double>(V) * (static_cast<double>(V) / cells);
-  if (tests > max_tests)
+  // one thread walks the chains of one point: beyond about a million steps that single walk takes a second
+  constexpr unsigned long long kMaxStepsPerPoint = 1ull << 20;
+  if (static_cast<double>(hw[0]) > max_tests || hw[1] > kMaxStepsPerPoint)
     fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: the tolerance is large against the point spacing (" + std::to_string(V) +
-                                       " points in " + std::to_string(h[0]) + " grid cells, about " + std::to_string(tests) +
-                                       " distance tests); every radius search of the reference would return a large part of the cloud too");
+                                       " points in " + std::to_string(h[0]) + " grid cells, " + std::to_string(hw[0]) +
+                                       " distance tests in all and " + std::to_string(hw[1]) +
+                                       " for the busiest point); every radius search of the reference would return a large part of the cloud too");
   k_clu_link<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
                                            static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), c->cluParent.as<unsigned>());
   NB2_CUDA(cudaGetLastError());

@@ -262,6 +262,7 @@ struct nb2_context
   nb2::DevBuf subRank;      // uint32[centroids] final number of each
   // Euclidean clustering (kernels_cluster.cu): chain head per cell slot, chain link / union-find parent / label per point
   nb2::DevBuf cluHead, cluNext, cluParent, cluLabel;
+  nb2::DevBuf cluCellSize;  // uint32[slots] points per cell slot, then 2 x uint64 {chain steps of the link pass, longest walk}
   // record layout of the resident cloud (set by every ingest)
   uint32_t rec_step = 0, rec_off_xyz = 0;
   int32_t rec_off_nrm = -1;
@@ -315,6 +316,7 @@ struct nb2_result
   // A slab of a sharded plan stays in the owner's device buffers (outPos / outNrm / outEdge / outSegLen / planeMeta)
   // until nb2_result_gather ships it to the root over NCCL; valid until the next plan on that context.
   bool device_resident = false;
+  unsigned plan_serial = 0;    // the owner's plan_serial when the slab was produced (a later plan overwrites the buffers)
   uint64_t dev_w_cap = 0;      // outEdge holds edge_lo at [0, W) and edge_hi at [dev_w_cap, dev_w_cap + W)
   uint64_t slab_begin = 0;     // first lattice plane of the slab
   uint64_t slab_planes = 0;    // planes in the slab (entries of planeMeta)

@@ -103,14 +103,14 @@ class Context:
 
     def download_triangles(self, n_triangles: int) -> np.ndarray:
         tri = np.zeros((n_triangles, 3), np.uint32)
-        _capi.check(self._lib.nb2_mesh_download_triangles(self._h, tri.ctypes.data))
+        _capi.check(self._lib.nb2_mesh_download_triangles(self._h, tri.ctypes.data, int(n_triangles)))
         return tri
 
     def download_cloud(self, n_vertices: int) -> np.ndarray:
         """the resident cloud as PCLPointCloud2::data (n_vertices records of point_step bytes)"""
         step, ox, on = self.record_layout()
         data = np.zeros(n_vertices * step, np.uint8)
-        _capi.check(self._lib.nb2_mesh_download_cloud(self._h, data.ctypes.data))
+        _capi.check(self._lib.nb2_mesh_download_cloud(self._h, data.ctypes.data, int(data.size)))
         return data
 
     def record_layout(self) -> tuple[int, int, int]:
@@ -135,7 +135,7 @@ class Context:
     def euclidean_cluster_labels(self, tolerance: float, n_vertices: int) -> np.ndarray:
         """nb2_euclidean_cluster_labels: smallest point index of every point's connected component"""
         labels = np.zeros(n_vertices, np.uint32)
-        _capi.check(self._lib.nb2_euclidean_cluster_labels(self._h, float(tolerance), labels.ctypes.data))
+        _capi.check(self._lib.nb2_euclidean_cluster_labels(self._h, float(tolerance), labels.ctypes.data, int(n_vertices)))
         return labels
 
     def set_normals(self, normals: np.ndarray):

@@ -316,7 +316,7 @@ MeshView makeView(Device& dev, const pcl::PolygonMesh& mesh)
 
 /** Make `mesh` the context's resident mesh: nothing to do when it already is (same vertices, same triangles and, where
  *  the caller needs them, the same normals), an upload otherwise.  Call with the device mutex held. */
-void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals)
+void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals, bool whole_records = false)
 {
   Trace trace("ensureResident");
   const MeshView m = makeView(dev, mesh);
@@ -325,7 +325,10 @@ void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals
   const bool same_geometry = r.valid && r.n_points == m.content.n_points && r.n_triangles == m.content.n_triangles &&
                              r.h_xyz == m.content.h_xyz && r.h_tri == m.content.h_tri;
   const bool same_normals = r.has_normals == m.content.has_normals && (!r.has_normals || r.h_normals == m.content.h_normals);
-  if (same_geometry && (same_normals || !need_normals))
+  // `whole_records`: the caller works on every byte of the cloud records (face subdivision copies them), and the
+  // fingerprints above cover positions, normals and indices only — the same geometry in another record layout, or with
+  // other colours / curvature, would pass them.  Such callers always upload.
+  if (!whole_records && same_geometry && (same_normals || !need_normals))
     return;
   dev.resident.valid = false;
   Device::check(nb2_mesh_upload(dev.ctx(), &m.view));
@@ -711,7 +714,7 @@ public:
       Device& dev = Device::instance();
       std::lock_guard<std::mutex> lock(dev.mutex());
       ensureResident(dev, mesh, false);
-      Device::check(nb2_euclidean_cluster_labels(dev.ctx(), tolerance_, labels.data()));
+      Device::check(nb2_euclidean_cluster_labels(dev.ctx(), tolerance_, labels.data(), labels.size()));
     }
     return cutClusterMeshes(mesh, labels.data(), min_cluster_size_, max_cluster_size_);
   }
@@ -742,14 +745,21 @@ public:
     {
       Device& dev = Device::instance();
       std::lock_guard<std::mutex> lock(dev.mutex());
-      ensureResident(dev, mesh, false);
+      // the records themselves are subdivided: the cloud on the device must be this very cloud, byte for byte (after
+      // NormalsFromMeshFaces the context holds the INPUT's records, not the concatenated cloud that modifier returned)
+      ensureResident(dev, mesh, false, /*whole_records=*/true);
       dev.resident.valid = false;  // the context holds the subdivided mesh from here on
       Device::check(subdivide(dev.ctx(), offset_rgba, &info));
+      std::uint32_t step = 0;
+      Device::check(nb2_mesh_record_layout(dev.ctx(), &step, nullptr, nullptr));
+      if (step != mesh.cloud.point_step)
+        throw std::runtime_error("noether_b200: the resident cloud has " + std::to_string(step) +
+                                 "-byte records but the mesh being subdivided has " + std::to_string(mesh.cloud.point_step));
       output.cloud.data.resize(info.n_points * mesh.cloud.point_step);
       tri.resize(3 * info.n_triangles);
-      Device::check(nb2_mesh_download_cloud(dev.ctx(), output.cloud.data.data()));
+      Device::check(nb2_mesh_download_cloud(dev.ctx(), output.cloud.data.data(), output.cloud.data.size()));
       if (info.n_triangles)
-        Device::check(nb2_mesh_download_triangles(dev.ctx(), tri.data()));
+        Device::check(nb2_mesh_download_triangles(dev.ctx(), tri.data(), info.n_triangles));
     }
     // the flattened cloud of the reference (:218-220,241 / :262-264,305)
     output.cloud.height = 1;

@@ -854,6 +854,35 @@ void testFaceSubdivision(const noether::Factory& factory, const pcl::PolygonMesh
       within = within && faceArea(m, f) <= 0.01 * (1 + 1e-5);
     CHECK(within);
   }
+  {
+    // The pipeline [NormalsFromMeshFaces -> FaceMidpointSubdivision]: the first modifier leaves the INPUT's records on the
+    // device and returns a concatenated cloud with another record layout (32-byte pcl::Normal + the input's fields); the
+    // subdivision must work on that returned cloud, not on what happens to be resident (same geometry, other records).
+    YAML::Node nc;
+    nc["name"] = "NormalsFromMeshFaces";
+    const std::vector<pcl::PolygonMesh> with_normals = factory.createMeshModifier(nc)->modify(mesh);
+    CHECK(with_normals.size() == 1);
+    const pcl::PolygonMesh& in = with_normals.front();
+    CHECK(in.cloud.point_step == mesh.cloud.point_step + 32);
+    YAML::Node config;
+    config["name"] = "FaceMidpointSubdivision";
+    config["n_iterations"] = 1;
+    const std::vector<pcl::PolygonMesh> out = factory.createMeshModifier(config)->modify(in);
+    CHECK(out.size() == 1);
+    const pcl::PolygonMesh& m = out.front();
+    CHECK(m.cloud.point_step == in.cloud.point_step && m.cloud.height == 1);
+    CHECK(m.cloud.data.size() == static_cast<std::size_t>(m.cloud.point_step) * m.cloud.width);
+    CHECK(m.cloud.width == in.cloud.width + edges);
+    CHECK(m.polygons.size() == 4 * in.polygons.size());
+    CHECK(m.cloud.data.size() >= in.cloud.data.size() &&
+          std::memcmp(m.cloud.data.data(), in.cloud.data.data(), in.cloud.data.size()) == 0);
+    // and the other way round: the same geometry in the ORIGINAL layout right after (the device now holds the subdivided
+    // 80-byte records)
+    const std::vector<pcl::PolygonMesh> again = factory.createMeshModifier(config)->modify(mesh);
+    CHECK(again.size() == 1 && again.front().cloud.point_step == mesh.cloud.point_step);
+    CHECK(again.front().cloud.data.size() == static_cast<std::size_t>(mesh.cloud.point_step) * (mesh.cloud.width + edges));
+    CHECK(std::memcmp(again.front().cloud.data.data(), mesh.cloud.data.data(), mesh.cloud.data.size()) == 0);
+  }
 }
 
 /** the surface twice, the copy shifted by 100 in z and without its last 200 faces */

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(capi):
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(declared) <= exported
-    assert L.nb2_abi_version() == 1
+    assert L.nb2_abi_version() == 2
 
 
 def test_header_is_plain_c(tmp_path):
@@ -141,8 +141,9 @@ def test_entry_points_refuse_a_null_context(capi):
     info = capi.MeshFileInfo()
     for call in (lambda: L.nb2_face_midpoint_subdivision(None, 1, -1, C.byref(info)),
                  lambda: L.nb2_face_subdivision_by_area(None, C.c_float(1.0), -1, 0, C.byref(info)),
-                 lambda: L.nb2_mesh_download_cloud(None, None),
+                 lambda: L.nb2_mesh_download_cloud(None, None, 0),
                  lambda: L.nb2_mesh_record_layout(None, None, None, None),
-                 lambda: L.nb2_mesh_download_triangles(None, None)):
+                 lambda: L.nb2_mesh_download_triangles(None, None, 0),
+                 lambda: L.nb2_euclidean_cluster_labels(None, C.c_double(1.0), None, 0)):
         assert call() == capi.NB2_ERR_INVALID_ARGUMENT
         assert L.nb2_last_error()
