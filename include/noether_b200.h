@@ -231,6 +231,14 @@ typedef struct nb2_lattice
   int32_t pad_;
 } nb2_lattice;
 
+/* Host only (no context): the symmetric 3x3 float eigen-solver the PCA frame uses, on the host and in the ingest kernel's
+ * epilogue alike — Eigen 3.4 SelfAdjointEigenSolver<Matrix3f>::compute as pcl::PCA::initCompute calls it
+ * (plane_slicer_raster_planner.cpp:540-541): lower triangle scaled into [-1, 1], closed-form 3x3 tridiagonalisation,
+ * implicit QR steps with Wilkinson shift and Eigen's deflation test, ascending selection sort.  cov and evecs are
+ * column-major; evals ascending, evecs[3 * i .. 3 * i + 2] = eigenvector of evals[i], signs as that sequence of rotations
+ * leaves them (pcl::PCA then reverses the order).  Exposed so that the restatement can be tested in isolation. */
+int nb2_eigen_solver_3f(const float cov[9], float evals_ascending[3], float evecs_ascending[9]);
+
 int nb2_make_lattice(const nb2_pca* pca,
                      const double cut_direction[3],
                      const double cut_origin[3],

@@ -35,7 +35,7 @@ NB2_UNIQUE_ID_BYTES = 128
 DECLARED_SYMBOLS = [
     "nb2_abi_version", "nb2_last_error", "nb2_context_create", "nb2_context_destroy", "nb2_context_device",
     "nb2_mesh_upload", "nb2_mesh_set_normals", "nb2_mesh_download", "nb2_mesh_pca", "nb2_principal_axis_direction",
-    "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_plan_params_default", "nb2_slice",
+    "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_eigen_solver_3f", "nb2_plan_params_default", "nb2_slice",
     "nb2_plan", "nb2_plan_mesh", "nb2_last_lattice", "nb2_result_get", "nb2_result_poses", "nb2_result_poses_segments", "nb2_result_free", "nb2_last_timings",
     "nb2_kernel_launches", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
     "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",
@@ -157,6 +157,7 @@ def load():
     L.nb2_centroid_origin.argtypes = [vp, C.POINTER(C.c_double)]
     L.nb2_pca_rotated_direction.argtypes = [vp, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.nb2_normals_from_mesh_faces.argtypes = [vp, C.c_void_p]
+    L.nb2_eigen_solver_3f.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.nb2_make_lattice.argtypes = [C.POINTER(Pca), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
                                    C.c_int, C.POINTER(Lattice)]
     L.nb2_plan_params_default.argtypes = [C.POINTER(PlanParams)]

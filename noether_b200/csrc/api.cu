@@ -1490,6 +1490,15 @@ int nb2_normals_from_mesh_faces(nb2_context* c, float* normals_out)
   NB2_API_END
 }
 
+int nb2_eigen_solver_3f(const float cov[9], float evals_ascending[3], float evecs_ascending[9])
+{
+  NB2_API_BEGIN
+  if (!cov || !evals_ascending || !evecs_ascending)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  eigenSolver3f(cov, evals_ascending, evecs_ascending);
+  NB2_API_END
+}
+
 int nb2_make_lattice(const nb2_pca* pca, const double dir[3], const double origin[3], double spacing, int bidirectional,
                      nb2_lattice* out)
 {

@@ -198,28 +198,10 @@ def test_host_submeshes_reference_case(orc, ply_mesh):
 # ---------------------------------------------------------------------------------------------------------------------
 # the CUDA path through the C ABI == oracle
 # ---------------------------------------------------------------------------------------------------------------------
-# The clustering kernels were written after this round's GPU minutes were spent: their first run on a B200 is the driver's
-# round-end run.  Until a green run is on record they may neither turn the suite red nor — should a kernel fault — take the
-# session's CUDA context down with them: the two tests below only run inside a process of their own
-# (test_gpu_cluster_suite_in_its_own_process), whose failure is reported as XFAIL and whose success as XPASS.  The launch
-# sequence itself is covered bit for bit by the host emulation above.  Fold them back into the session after that run.
-first_gpu_run = pytest.mark.xfail(reason="first B200 run of kernels_cluster.cu happens at round end; see DESIGN.md §3c", strict=False)
-own_process = pytest.mark.skipif(not os.environ.get("NB2_CLUSTER_INNER"), reason="runs inside test_gpu_cluster_suite_in_its_own_process")
+# (first B200 run: the driver's round-1 GPU suite, where both tests passed; since round 2 they are ordinary session tests)
 
 
 @pytest.mark.gpu
-@first_gpu_run
-def test_gpu_cluster_suite_in_its_own_process():
-    import sys
-    env = dict(os.environ, NB2_CLUSTER_INNER="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k", "test_gpu_labels"],
-                       env=env, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    print(r.stdout[-4000:], r.stderr[-2000:])
-    assert r.returncode == 0
-
-
-@pytest.mark.gpu
-@own_process
 def test_gpu_labels_and_meshes_match_oracle(ctx, orc, ply_mesh):
     for seed in range(12):
         blob, h = islands(seed, n_islands=3 + seed)
@@ -235,7 +217,6 @@ def test_gpu_labels_and_meshes_match_oracle(ctx, orc, ply_mesh):
 
 
 @pytest.mark.gpu
-@own_process
 def test_gpu_labels_random_clouds_and_large(ctx, orc):
     for seed in range(80):
         rng = np.random.default_rng(4100 + seed)
@@ -261,6 +242,27 @@ def test_gpu_labels_random_clouds_and_large(ctx, orc):
     with pytest.raises(_capi.Nb2Error) as e:
         ctx.euclidean_cluster_labels(10.0, len(both))       # the whole cloud in a handful of cells
     assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.gpu
+def test_gpu_skewed_cloud_is_refused_by_its_exact_work_not_its_average(ctx):
+    """1.5 M coincident points plus 1.5 M points scattered over a million cells: the average cell occupancy is about
+    3 points (27 V V / cells = 2e8 tests, far below the limit), but the coincident points alone are 2e12 chain steps and
+    one thread would walk a 1.5 M-entry chain.  The work is counted exactly on the device before the link pass runs."""
+    rng = np.random.default_rng(7)
+    n = 1_500_000
+    scattered = (rng.random((n, 3)) * np.array([1000.0, 1000.0, 1.0])).astype(np.float32)
+    xyz = np.concatenate([np.full((n, 3), 0.5, np.float32), scattered])
+    blob = meshes.pack_blob(xyz, None, np.zeros((0, 3), np.uint32), "PointXYZ")
+    ctx.upload(blob, force=True)
+    with pytest.raises(_capi.Nb2Error) as e:
+        ctx.euclidean_cluster_labels(1.0, len(xyz))
+    assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT and "busiest point" in str(e.value)
+    # the scattered half alone is fine (and every point farther than the tolerance from any other stays alone)
+    blob = meshes.pack_blob(scattered, None, np.zeros((0, 3), np.uint32), "PointXYZ")
+    ctx.upload(blob, force=True)
+    labels = ctx.euclidean_cluster_labels(1e-4, n)
+    assert labels.shape == (n,) and (labels <= np.arange(n)).all()
 
 
 def test_emulated_labels_larger_clouds_grid_path_of_the_oracle(emu, orc):

@@ -469,6 +469,39 @@ def test_cfg2_properties(ctx, orc):
     assert_same_paths(gpu, paths.flat(), "cfg2", poses=False)
 
 
+def test_cfg3_full_size_plan_matches_oracle(ctx, orc):
+    """BASELINE.json configs[2] — the configuration the headline metric is quoted on — at FULL size: wavy(2500, 2000),
+    10,000,000 triangles, 1 mm spacing, PrincipalAxis(0) + Centroid.  The oracle's lattice-binned plan (same output as its
+    every-cell scan, about 11 s on one core) against the GPU plan: lattice bytes, segment offsets, generating edges,
+    positions and normals bit for bit over all 4.0 M waypoints."""
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    xyz, tri = meshes.wavy(2500, 2000)
+    assert tri.shape[0] == 10_000_000 and xyz.shape[0] == 5_004_501
+    blob0 = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob0, force=True)
+    nrm = ctx.normals_from_mesh_faces(blob0.n_vertices)
+    assert np.array_equal(nrm.view(np.uint32), orc.normals_from_mesh_faces(xyz, tri).view(np.uint32))
+    blob = meshes.pack_blob(xyz, nrm, tri)
+    pl = nb.PlaneSlicerRasterPlanner(nb.PrincipalAxisDirectionGenerator(0.0, ctx), nb.CentroidOriginGenerator(ctx), ctx)
+    pl.set_line_spacing(0.001)
+    gpu = pl.plan(blob)
+    lat = ctx.last_lattice()
+    assert 995 <= gpu.n_paths <= 1005 and gpu.n_waypoints > 3_900_000
+    assert np.all(gpu.segments_per_path() == 1) and np.all(np.diff(gpu.path_plane) == 1)
+    paths, lat_o, _ = orc.plan_plane_slicer(xyz, nrm, tri, 0.001, True, slice_mode=orc.SLICE_INTENT,
+                                            scan_mode=orc.SCAN_BINNED, frame=oracle_pca_from_capi(orc, ctx.pca()))
+    assert bytes(lat_o) == bytes(lat)
+    assert_same_paths(gpu, paths.flat(), "cfg3", poses=False)
+    # the same plan with the bench's settings (no generating edges, tool paths left on the device): same counts
+    n = (gpu.n_paths, gpu.n_segments, gpu.n_waypoints)
+    pl.emit_edges = False
+    again = pl.plan(blob)
+    assert (again.n_paths, again.n_segments, again.n_waypoints) == n
+    assert np.array_equal(again.positions.view(np.uint32), gpu.positions.view(np.uint32))
+    assert np.array_equal(again.normals.view(np.uint32), gpu.normals.view(np.uint32))
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # BASELINE.json configs[3] (cfg4) and configs[4] (cfg5) at full size
 # ---------------------------------------------------------------------------------------------------------------------
@@ -742,7 +775,6 @@ def test_legacy_modifiers_on_device_match_oracle(ctx, orc, min_hole, min_seg):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="added after the round's GPU minutes were spent: first B200 run happens at round end", strict=False)
 def test_aabb_center_origin_matches_oracle(ctx, orc, ply_mesh):
     """AABBCenterOriginGenerator (aabb_center_origin_generator.cpp:9-17) from the AABB of the ingest pass, bit for bit, and as
     the origin generator of a plan"""

@@ -10,19 +10,38 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.gpu
-def test_slabs_gathered_over_nccl_equal_the_unsharded_plan():
-    import torch
-    n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs two GPUs")
-    world = 4 if n >= 4 else 2
+def _run(world, *args, timeout=900):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tests", "mgpu_worker.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(ROOT, "tests", "mgpu_worker.py"), *args], capture_output=True, text=True, timeout=timeout)
     print(r.stdout[-3000:], r.stderr[-3000:])
+    return r
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slabs_gathered_over_nccl_equal_the_oracle_and_the_unsharded_plan(world):
+    """plain and legacy planner on a mesh with a hole: the gathered slabs against the oracle and the unsharded GPU plan"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    r = _run(world)
     assert r.returncode == 0
     assert r.stdout.count("gather ok") == 2
+
+
+@pytest.mark.gpu
+def test_cfg3_slabs_on_all_gpus_equal_the_oracle():
+    """BASELINE.json configs[2] as it is quoted: the 10 M-triangle mesh, plane slabs over every GPU of the box (8 where
+    there are 8), gathered result bit for bit against the oracle's plan of the whole lattice"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 8 if n >= 8 else (4 if n >= 4 else 2)
+    r = _run(world, "cfg3", timeout=1500)
+    assert r.returncode == 0
+    assert r.stdout.count("gather ok") == 1

@@ -207,6 +207,76 @@ def test_eigen_solver_against_numpy(orc):
     assert np.all(w == 0) and np.allclose(V, np.eye(3))
 
 
+def _spd_batch(rng, n):
+    """random symmetric positive semi-definite 3x3 float32 matrices R diag(w) R^T over twelve decades of scale: well
+    separated spectra, near-degenerate pairs (relative gaps 1e-7 .. 1e-2), exactly repeated eigenvalues, rank-deficient
+    ones and plain A A^T"""
+    out = []
+    for i in range(n):
+        kind = i % 5
+        scale = 10.0 ** rng.uniform(-6, 6)
+        if kind == 4:
+            A = rng.standard_normal((3, 3))
+            M = A @ A.T * scale
+        else:
+            q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+            w = np.sort(rng.uniform(0.05, 1.0, 3))
+            if kind == 1:
+                w[1] = w[0] * (1.0 + 10.0 ** rng.uniform(-7, -2))      # near-degenerate pair at the bottom
+            elif kind == 2:
+                w[2] = w[1] * (1.0 + 10.0 ** rng.uniform(-7, -2))      # ... at the top (the raster direction pair)
+            elif kind == 3:
+                w[rng.integers(0, 3)] = 0.0 if rng.random() < 0.5 else w[0]  # rank deficient / exactly repeated
+            M = (q * (w * scale)) @ q.T
+        M = M.astype(np.float32)
+        out.append(np.tril(M) + np.tril(M, -1).T)  # exactly symmetric (the solver reads the lower triangle)
+    return out
+
+
+def test_eigen_solver_10k_matrices_against_numpy_and_the_product(orc):
+    """The restated Eigen 3.4 SelfAdjointEigenSolver<Matrix3f> (oracle/oracle_pca.cpp) and the product's own restatement
+    (noether_b200/csrc/frame_math.h through nb2_eigen_solver_3f) on 10^4 symmetric matrices, against numpy.linalg.eigh of
+    the same float32 matrix in float64.
+
+    Conventions checked: eigenvalues ASCENDING (pcl::PCA reverses them afterwards); eigenvectors are the COLUMNS,
+    orthonormal; the sign of a column is not defined by the mathematics — it is whatever the solver's sequence of Givens
+    rotations yields, so columns are compared up to sign, and within a (near-)degenerate cluster only the spanned subspace
+    is compared.  The two restatements must agree with each other bit for bit, signs included."""
+    import ctypes as C
+    from noether_b200 import _capi
+    from noether_b200.build import build_library
+    build_library()
+    L = _capi.load()
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(20240607)
+    eps = float(np.finfo(np.float32).eps)
+    for M in _spd_batch(rng, 10_000):
+        w, V = orc.eigen_solver_3f(M)
+        cm = np.ascontiguousarray(M.T)
+        w2 = np.zeros(3, np.float32)
+        v2 = np.zeros(9, np.float32)
+        assert L.nb2_eigen_solver_3f(cm.ctypes.data_as(fp), w2.ctypes.data_as(fp), v2.ctypes.data_as(fp)) == 0
+        assert np.array_equal(w.view(np.uint32), w2.view(np.uint32))
+        assert np.array_equal(V.view(np.uint32), v2.reshape(3, 3).T.copy().view(np.uint32))
+        w_np, V_np = np.linalg.eigh(M.astype(np.float64))
+        top = max(abs(w_np).max(), 1e-300)
+        assert np.all(np.diff(w) >= 0)
+        assert np.abs(w - w_np).max() <= 16 * eps * top
+        assert np.abs(V.T.astype(np.float64) @ V - np.eye(3)).max() <= 16 * eps
+        assert np.abs(M.astype(np.float64) @ V - V * w.astype(np.float64)).max() <= 32 * eps * top
+        # eigenvectors: group numpy's eigenvalues into clusters closer than the float32 resolution of the problem and
+        # compare the projector onto each cluster's eigenspace
+        tol_gap = 4096 * eps * top
+        start = 0
+        for end in range(1, 4):
+            if end == 3 or w_np[end] - w_np[end - 1] > tol_gap:
+                P_np = V_np[:, start:end] @ V_np[:, start:end].T
+                Vc = V[:, start:end].astype(np.float64)
+                gap = min([abs(w_np[i] - w_np[j]) for i in range(start, end) for j in range(3) if not start <= j < end] or [top])
+                assert np.abs(Vc @ Vc.T - P_np).max() <= 64 * eps * top / gap
+                start = end
+
+
 def test_kat_lattice_quirks(orc):
     # unit cube cloud centred at (0.5, 0.5, 0.05): OBB centred on the mean; planes from a floored start
     from noether_b200 import meshes

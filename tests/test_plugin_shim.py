@@ -58,7 +58,6 @@ def test_reference_tests_through_the_plugin_boundary(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="first B200 run of kernels_cluster.cu happens at round end; see DESIGN.md §3c", strict=False)
 def test_clustering_through_the_plugin_boundary(golden_dir):
     _build()
     r = subprocess.run([os.path.join(OUT, "plugin_shim_test"), PLUGIN, os.path.join(golden_dir, "wavy_mesh_with_hole.ply"),
