@@ -4,21 +4,40 @@
 // (vtkPlane::EvaluateFunction, vtkTriangle::Contour — third-party VTK 9.1).  Bit-exact
 // connectivity needs the same IEEE-754 double operations in the same order, so everything here goes through the
 // round-to-nearest intrinsics, which nvcc never fuses.  (The library is additionally compiled with -fmad=false.)
+//
+// The same functions compile for the host (plain IEEE operations; the host code is built with -ffp-contract=off), which
+// is how the CPU test suite replays the contouring and linking of the kernels without a GPU (tests/cpp/link_emulation.cpp).
 #pragma once
 #include "nb2_internal.h"
 
+#if defined(__CUDACC__)
+#define NB2_DEV __host__ __device__ __forceinline__
+#else
+#define NB2_DEV inline
+#endif
+
 namespace nb2
 {
-__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+#if defined(__CUDA_ARCH__)
+NB2_DEV double dmul(double a, double b) { return __dmul_rn(a, b); }
+NB2_DEV double dadd(double a, double b) { return __dadd_rn(a, b); }
+NB2_DEV double dsub(double a, double b) { return __dsub_rn(a, b); }
+NB2_DEV double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+NB2_DEV float d2f(double a) { return __double2float_rn(a); }
+#else
+NB2_DEV double dmul(double a, double b) { return a * b; }
+NB2_DEV double dadd(double a, double b) { return a + b; }
+NB2_DEV double dsub(double a, double b) { return a - b; }
+NB2_DEV double ddiv(double a, double b) { return a / b; }
+NB2_DEV float d2f(double a) { return static_cast<float>(a); }
+#endif
 
 /** Origin of lattice plane k: start_loc + (k * line_spacing_) * cut_normal  (plane_slicer_raster_planner.cpp:598) */
 struct PlaneOrigin
 {
   double x, y, z;
 };
-__device__ __forceinline__ PlaneOrigin planeOrigin(const LatticeDev& L, long long k)
+NB2_DEV PlaneOrigin planeOrigin(const LatticeDev& L, long long k)
 {
   const double is = dmul(static_cast<double>(k), L.spacing);
   PlaneOrigin o;
@@ -29,7 +48,7 @@ __device__ __forceinline__ PlaneOrigin planeOrigin(const LatticeDev& L, long lon
 }
 
 /** vtkPlane::EvaluateFunction: n0*(x0-o0) + n1*(x1-o1) + n2*(x2-o2), double, left to right */
-__device__ __forceinline__ double planeScalar(const LatticeDev& L, const PlaneOrigin& o, float x, float y, float z)
+NB2_DEV double planeScalar(const LatticeDev& L, const PlaneOrigin& o, float x, float y, float z)
 {
   const double a = dmul(L.n[0], dsub(static_cast<double>(x), o.x));
   const double b = dmul(L.n[1], dsub(static_cast<double>(y), o.y));
@@ -38,7 +57,7 @@ __device__ __forceinline__ double planeScalar(const LatticeDev& L, const PlaneOr
 }
 
 /** (a.x*d0 + a.y*d1) + a.z*d2 with float->double operands: orientation / ordering key of chains */
-__device__ __forceinline__ double dotLR(double ax, double ay, double az, const double d[3])
+NB2_DEV double dotLR(double ax, double ay, double az, const double d[3])
 {
   return dadd(dadd(dmul(ax, d[0]), dmul(ay, d[1])), dmul(az, d[2]));
 }
@@ -47,7 +66,7 @@ __device__ __forceinline__ double dotLR(double ax, double ay, double az, const d
 //   edges     = {0,1} {1,2} {2,0}                      -> edge e joins local vertices e and (e+1)%3
 //   lineCases = {-} {0,2} {1,0} {1,2} {2,1} {0,1} {2,0} {-}   (pairs of edge numbers, indexed by the case)
 // packed two bits per case so the lookup is register arithmetic instead of a local-memory table.
-__device__ __forceinline__ int lineCaseEdge(int index, int which)
+NB2_DEV int lineCaseEdge(int index, int which)
 {
   const unsigned packed = which == 0 ? 0x2250u : 0x0588u;
   return (packed >> (2 * index)) & 3;
@@ -55,7 +74,7 @@ __device__ __forceinline__ int lineCaseEdge(int index, int which)
 
 // register-array selects (constant indices only, so the arrays never spill to local memory)
 template <typename T>
-__device__ __forceinline__ T pick3(const T a[3], int i)
+NB2_DEV T pick3(const T a[3], int i)
 {
   return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]);
 }
@@ -69,7 +88,7 @@ struct CutPoint
 };
 
 /** Contour case index of a triangle for plane scalars s[0..2]: bit i set when s[i] >= 0 (vtkTriangle::Contour) */
-__device__ __forceinline__ int contourCase(const double s[3])
+NB2_DEV int contourCase(const double s[3])
 {
   return (s[0] >= 0.0 ? 1 : 0) | (s[1] >= 0.0 ? 2 : 0) | (s[2] >= 0.0 ? 4 : 0);
 }
@@ -78,7 +97,7 @@ __device__ __forceinline__ int contourCase(const double s[3])
  *  normals of the triangle's three vertices, already in registers).
  *  Restates vtkTriangle::Contour: interpolate from the lower- to the higher-scalar end, t = (0 - s_lo) / (s_hi - s_lo),
  *  x = x_lo + t (x_hi - x_lo) in double, stored as float; attributes a_lo (1 - t) + a_hi t in double, stored as float. */
-__device__ __forceinline__ CutPoint interpolateCut(int index, int which, const uint32_t ids[3], const float4 p[3],
+NB2_DEV CutPoint interpolateCut(int index, int which, const uint32_t ids[3], const float4 p[3],
                                                    const double s[3], const float4* nv)
 {
   const int edge = lineCaseEdge(index, which);
@@ -96,21 +115,21 @@ __device__ __forceinline__ CutPoint interpolateCut(int index, int which, const u
     e2 = v0;
     delta = -delta;
   }
-  const double t = (delta == 0.0) ? 0.0 : __ddiv_rn(dsub(0.0, pick3(s, e1)), delta);
+  const double t = (delta == 0.0) ? 0.0 : ddiv(dsub(0.0, pick3(s, e1)), delta);
   CutPoint c;
   const float4 a = pick3(p, e1), b = pick3(p, e2);
-  c.x = __double2float_rn(dadd(static_cast<double>(a.x), dmul(t, dsub(static_cast<double>(b.x), static_cast<double>(a.x)))));
-  c.y = __double2float_rn(dadd(static_cast<double>(a.y), dmul(t, dsub(static_cast<double>(b.y), static_cast<double>(a.y)))));
-  c.z = __double2float_rn(dadd(static_cast<double>(a.z), dmul(t, dsub(static_cast<double>(b.z), static_cast<double>(a.z)))));
+  c.x = d2f(dadd(static_cast<double>(a.x), dmul(t, dsub(static_cast<double>(b.x), static_cast<double>(a.x)))));
+  c.y = d2f(dadd(static_cast<double>(a.y), dmul(t, dsub(static_cast<double>(b.y), static_cast<double>(a.y)))));
+  c.z = d2f(dadd(static_cast<double>(a.z), dmul(t, dsub(static_cast<double>(b.z), static_cast<double>(a.z)))));
   c.lo = pick3(ids, e1);
   c.hi = pick3(ids, e2);
   if (nv != nullptr)
   {
     const float4 n1 = pick3(nv, e1), n2 = pick3(nv, e2);
     const double omt = dsub(1.0, t);
-    c.nx = __double2float_rn(dadd(dmul(static_cast<double>(n1.x), omt), dmul(static_cast<double>(n2.x), t)));
-    c.ny = __double2float_rn(dadd(dmul(static_cast<double>(n1.y), omt), dmul(static_cast<double>(n2.y), t)));
-    c.nz = __double2float_rn(dadd(dmul(static_cast<double>(n1.z), omt), dmul(static_cast<double>(n2.z), t)));
+    c.nx = d2f(dadd(dmul(static_cast<double>(n1.x), omt), dmul(static_cast<double>(n2.x), t)));
+    c.ny = d2f(dadd(dmul(static_cast<double>(n1.y), omt), dmul(static_cast<double>(n2.y), t)));
+    c.nz = d2f(dadd(dmul(static_cast<double>(n1.z), omt), dmul(static_cast<double>(n2.z), t)));
   }
   else
   {

@@ -1,0 +1,244 @@
+// TEST INFRASTRUCTURE.  Host replay of the contouring (k_emit_hits) and of the fast linking path (k_link_planes) of
+// noether_b200/csrc/kernels_slice.cu: the kernels' own per-element functions — device_math.cuh (plane scalars, vtkTriangle
+// case table, cut-point and normal interpolation) and link2_ops.h (every phase of the linker) — driven by loops instead of
+// CTAs, "threads" visited in a scrambled order and the plane's cut lines stored in a scrambled order (the order the
+// kernel's atomics leave them in is arbitrary), so that the CUDA path's logic is compared with the oracle bit for bit on
+// a machine without a GPU.  Planes the fast path declines (it returns before writing anything) are reported with the
+// reason; on the device those go to the general path.
+//
+// Build (tests/test_link_emulation.py): g++ -std=c++17 -O2 -fPIC -shared -ffp-contract=off -fno-fast-math
+//        -I/usr/local/cuda/include tests/cpp/link_emulation.cpp -o tests/cpp/build/liblink_emulation.so
+#include "../../noether_b200/csrc/device_math.cuh"
+#include "../../noether_b200/csrc/link2_ops.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+using namespace nb2;
+using namespace nb2::link2;
+
+namespace
+{
+struct HostOps
+{
+  static unsigned cas(unsigned* a, unsigned cmp, unsigned v)
+  {
+    const unsigned seen = *a;
+    if (seen == cmp)
+      *a = v;
+    return seen;
+  }
+  static unsigned add(unsigned* a, unsigned v)
+  {
+    const unsigned old = *a;
+    *a = old + v;
+    return old;
+  }
+  static void orr(unsigned* a, unsigned v) { *a |= v; }
+  static unsigned vload(const unsigned* a) { return *a; }
+  static Rec4 load(const Rec4* p) { return *p; }
+  static unsigned loadRank(const Rec4* p) { return bitsOf(p->w); }
+  static unsigned long long ld64(const unsigned long long* p) { return *p; }
+  static void st64(unsigned long long* p, unsigned long long v) { *p = v; }
+};
+
+struct Result
+{
+  std::vector<int64_t> path_plane;
+  std::vector<uint32_t> path_segments;  // segments per non-empty plane
+  std::vector<uint32_t> seg_len;
+  std::vector<float> pos, nrm;
+  std::vector<uint32_t> elo, ehi;
+  std::vector<int64_t> declined_plane;
+  std::vector<uint32_t> declined_reason;
+  uint64_t lines = 0;
+} g;
+
+/** visit 0 .. n-1 in a scrambled (but complete) order */
+template <typename F>
+void scrambled(unsigned n, unsigned seed, F f)
+{
+  if (n == 0)
+    return;
+  unsigned stride = 1;
+  for (unsigned cand : { 7919u, 104729u, 1299709u, 15485863u })
+    if (std::gcd(cand, n) == 1)
+      stride = cand % n ? cand % n : 1;
+  if (std::gcd(stride, n) != 1)
+    stride = 1;
+  unsigned i = seed % n;
+  for (unsigned k = 0; k < n; ++k)
+  {
+    f(i);
+    i = (i + stride) % n;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+/** Slice lattice planes [plane_begin, plane_end) of the mesh; nth "threads" per plane.  Returns the number of planes the
+ *  fast path declined (their waypoints are missing from the result). */
+int emu_slice(const float* xyz, const float* nrm, uint64_t V, const uint32_t* tri, uint64_t F, const double n[3],
+              const double start[3], double spacing, const double dir[3], int64_t num_planes, int64_t plane_begin,
+              int64_t plane_end, unsigned nth, unsigned seed, int want_edges)
+{
+  (void)V;
+  g = Result{};
+  LatticeDev L{};
+  for (int i = 0; i < 3; ++i)
+    L.n[i] = n[i], L.start[i] = start[i], L.dir[i] = dir[i];
+  L.spacing = spacing;
+  L.num_planes = num_planes;
+  L.plane_begin = plane_begin;
+  L.plane_end = plane_end;
+  std::vector<Rec4> rec, nrec;
+  std::vector<uint32_t> erec;
+  std::vector<uint8_t> area;
+  for (int64_t k = plane_begin; k < plane_end; ++k)
+  {
+    // ---- k_emit_hits for this plane: every triangle the plane cuts, contoured exactly as on the device -----------------
+    const PlaneOrigin org = planeOrigin(L, k);
+    std::vector<Rec4> r, nr;
+    std::vector<uint32_t> er;
+    for (uint64_t t = 0; t < F; ++t)
+    {
+      const uint32_t ids[3] = { tri[3 * t], tri[3 * t + 1], tri[3 * t + 2] };
+      float4 p[3], nv[3];
+      double s[3];
+      for (int j = 0; j < 3; ++j)
+      {
+        p[j] = make_float4(xyz[3 * ids[j]], xyz[3 * ids[j] + 1], xyz[3 * ids[j] + 2], 0.f);
+        nv[j] = make_float4(nrm[3 * ids[j]], nrm[3 * ids[j] + 1], nrm[3 * ids[j] + 2], 0.f);
+        s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+      }
+      const int index = contourCase(s);
+      if (index == 0 || index == 7)
+        continue;
+      for (int w = 0; w < 2; ++w)
+      {
+        const CutPoint c = interpolateCut(index, w, ids, p, s, nv);
+        Rec4 a{ c.x, c.y, c.z, 0.f };
+        const unsigned rank = static_cast<unsigned>(2 * t + w);
+        std::memcpy(&a.w, &rank, 4);
+        r.push_back(a);
+        nr.push_back(Rec4{ c.nx, c.ny, c.nz, 0.f });
+        er.push_back(c.lo);
+        er.push_back(c.hi);
+      }
+    }
+    const unsigned nl = static_cast<unsigned>(r.size() / 2);
+    if (nl == 0)
+      continue;
+    g.lines += nl;
+    // the bucket order is arbitrary on the device: scramble the lines
+    rec.resize(2 * nl);
+    nrec.resize(2 * nl);
+    erec.resize(4 * nl);
+    {
+      unsigned at = 0;
+      scrambled(nl, seed + static_cast<unsigned>(k) * 31u, [&](unsigned j) {
+        for (int w = 0; w < 2; ++w)
+        {
+          rec[2 * at + w] = r[2 * j + w];
+          nrec[2 * at + w] = nr[2 * j + w];
+          erec[4 * at + 2 * w] = er[4 * j + 2 * w];
+          erec[4 * at + 2 * w + 1] = er[4 * j + 2 * w + 1];
+        }
+        ++at;
+      });
+    }
+    // ---- the fast path of k_link_planes ------------------------------------------------------------------------------
+    if (nl > kMaxLines)
+    {
+      g.declined_plane.push_back(k);
+      g.declined_reason.push_back(F_CAPACITY);
+      continue;
+    }
+    area.assign(workBytes(nl) + 64, 0xcd);
+    uint8_t* base = area.data() + (16 - reinterpret_cast<uintptr_t>(area.data()) % 16) % 16;
+    const Work W = carve(base, nl);
+    auto declined = [&]() {
+      if (!W.misc[M_FAIL])
+        return false;
+      g.declined_plane.push_back(k);
+      g.declined_reason.push_back(W.misc[M_FAIL]);
+      return true;
+    };
+    unsigned phase = 0;
+    auto run = [&](auto fn) { scrambled(nth, seed + 17u * ++phase, [&](unsigned tid) { fn(tid); }); };
+    run([&](unsigned tid) { phaseInit<HostOps>(W, tid, nth); });
+    run([&](unsigned tid) { phaseInsert<HostOps>(W, rec.data(), tid, nth); });
+    if (declined())
+      continue;
+    run([&](unsigned tid) { phaseVerify<HostOps>(W, rec.data(), L.dir, tid, nth); });
+    if (declined())
+      continue;
+    if (W.misc[M_RETRY])
+      run([&](unsigned tid) { phaseRetry<HostOps>(W, rec.data(), tid, nth); });
+    run([&](unsigned tid) { phaseLink<HostOps>(W, tid, nth); });
+    if (declined())
+      continue;
+    run([&](unsigned tid) { phaseWalk<HostOps>(W, tid, nth); });
+    for (unsigned round = 0, rounds = jumpRounds(W.misc[M_NS]); round < rounds; ++round)
+    {
+      bool pending = false;
+      run([&](unsigned tid) { pending = phaseJump<HostOps>(W, tid, nth) || pending; });
+      if (!pending)
+        break;
+    }
+    run([&](unsigned tid) { phaseChains<HostOps>(W, tid, nth); });
+    if (declined())
+      continue;
+    run([&](unsigned tid) { phaseHeads<HostOps>(W, rec.data(), L.dir, tid, nth); });
+    if (declined())
+      continue;
+    run([&](unsigned tid) { phaseOrder<HostOps>(W, tid, nth); });
+    scanChainsSerial(W);
+    const unsigned Wk = W.misc[M_WK], Sk = W.misc[M_NH];
+    const size_t w0 = g.pos.size() / 3, s0 = g.seg_len.size();
+    g.pos.resize(3 * (w0 + Wk), -12345.f);
+    g.nrm.resize(3 * (w0 + Wk), -12345.f);
+    if (want_edges)
+    {
+      g.elo.resize(w0 + Wk, 0xdeadbeefu);
+      g.ehi.resize(w0 + Wk, 0xdeadbeefu);
+    }
+    g.seg_len.resize(s0 + Sk, 0u);
+    Out o{ g.pos.data() + 3 * w0, g.nrm.data() + 3 * w0, want_edges ? g.elo.data() + w0 : nullptr,
+           want_edges ? g.ehi.data() + w0 : nullptr, g.seg_len.data() + s0 };
+    run([&](unsigned tid) { phaseOutput<HostOps>(W, rec.data(), nrec.data(), want_edges ? erec.data() : nullptr, o, tid, nth); });
+    g.path_plane.push_back(k);
+    g.path_segments.push_back(Sk);
+  }
+  return static_cast<int>(g.declined_plane.size());
+}
+
+uint64_t emu_num_paths() { return g.path_plane.size(); }
+uint64_t emu_num_segments() { return g.seg_len.size(); }
+uint64_t emu_num_waypoints() { return g.pos.size() / 3; }
+uint64_t emu_num_lines() { return g.lines; }
+uint64_t emu_num_declined() { return g.declined_plane.size(); }
+
+void emu_export(int64_t* path_plane, uint32_t* path_segments, uint32_t* seg_len, float* pos, float* nrm, uint32_t* elo,
+                uint32_t* ehi, int64_t* declined_plane, uint32_t* declined_reason)
+{
+  auto copy = [](auto* dst, const auto& v) {
+    if (dst && !v.empty())
+      std::memcpy(dst, v.data(), v.size() * sizeof(v[0]));
+  };
+  copy(path_plane, g.path_plane);
+  copy(path_segments, g.path_segments);
+  copy(seg_len, g.seg_len);
+  copy(pos, g.pos);
+  copy(nrm, g.nrm);
+  copy(elo, g.elo);
+  copy(ehi, g.ehi);
+  copy(declined_plane, g.declined_plane);
+  copy(declined_reason, g.declined_reason);
+}
+
+uint64_t emu_work_bytes(unsigned n) { return workBytes(n); }
+}

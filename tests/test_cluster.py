@@ -239,9 +239,6 @@ def test_gpu_labels_random_clouds_and_large(ctx, orc):
     l1 = ctx.euclidean_cluster_labels(1.5 * h, len(both))
     assert np.array_equal(l1, np.repeat(np.array([0, len(xyz)], np.uint32), len(xyz)))
     assert not ctx.euclidean_cluster_labels(4 * h, len(both)).any()
-    with pytest.raises(_capi.Nb2Error) as e:
-        ctx.euclidean_cluster_labels(10.0, len(both))       # the whole cloud in a handful of cells
-    assert e.value.status == _capi.NB2_ERR_INVALID_ARGUMENT
 
 
 @pytest.mark.gpu
