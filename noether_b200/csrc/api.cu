@@ -394,16 +394,15 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
       }
     }
     NB2_CUDA(cudaMemcpyAsync(hf, c->frame.ptr, sizeof(FrameDev), cudaMemcpyDeviceToHost, c->stream));
-    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 11 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     meta_fetched = with_meta && meta_hint > 0;
     if (meta_fetched)
       NB2_CUDA(cudaMemcpyAsync(h + 16, c->planeMeta.ptr, sizeof(unsigned) * 2 * meta_hint, cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaStreamSynchronize(c->stream));
   };
-  const unsigned smem_cap = linkSmemHitCap(c);
   auto setCapacities = [&](uint64_t H, uint32_t n_max) {
     c->hit_cap = H + H / 4 + 1024;
-    c->scratch_hits = n_max > smem_cap ? n_max + n_max / 4 : 0u;
+    c->scratch_hits = n_max + n_max / 4;  // (any plane may need the first-generation paths' global work area)
     c->grid_nmax = n_max;
   };
   auto stageTwo = [&]() {
@@ -492,6 +491,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
 
   const uint64_t H = h[0];
   const uint32_t n_max = h[1];
+  c->last_general_planes = h[10];  // counters[14]: planes the linker's second-generation fast path declined
   c->grid_planes = static_cast<uint32_t>(nP);  // launch geometry hints for the next plan
   c->grid_nmax = n_max;
   if (c->F && h[8] >= c->V)  // counters[12]: largest out-of-range vertex index met by k_count_hits
@@ -536,7 +536,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     c->hostSmall.ensure(8192 + sizeof(FrameDev) + sizeof(unsigned) * 2 * (nP + 1));  // (may move the staging area)
     h = reinterpret_cast<unsigned*>(c->hostSmall.as<uint8_t>() + ((sizeof(FrameDev) + 63) & ~size_t(63)));
     hmeta = h + 16;
-    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 10 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    NB2_CUDA(cudaMemcpyAsync(h, c->counters.as<unsigned>() + 4, 11 * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaMemcpyAsync(hmeta, c->planeMeta.ptr, sizeof(unsigned) * 2 * nP, cudaMemcpyDeviceToHost, c->stream));
     NB2_CUDA(cudaStreamSynchronize(c->stream));
   }
@@ -707,6 +707,7 @@ int nb2_context_create(int device, nb2_context** out)
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->smem_per_sm = prop.sharedMemPerMultiprocessor;
   NB2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->counters.ensure(64 * sizeof(unsigned));
   NB2_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64 * sizeof(unsigned), c->stream));
@@ -728,7 +729,7 @@ void nb2_context_destroy(nb2_context* c)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
   for (DevBuf* b : { &c->blob, &c->fileImg, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
-                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
+                     &c->planeOff, &c->planeCursor, &c->hitRec, &c->linkProfile, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
                      &c->csrAdj, &c->csrRank, &c->scanState, &c->modPose[0], &c->modPose[1], &c->modSegOff, &c->modSegMap,
@@ -1713,6 +1714,21 @@ int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int ca
 }
 
 uint64_t nb2_kernel_launches(const nb2_context* c) { return c ? c->launches : 0; }
+uint64_t nb2_last_plan_general_path_planes(const nb2_context* c) { return c ? c->last_general_planes : 0; }
+
+int nb2_link_profile(nb2_context* c, uint64_t cycles[16])
+{
+  NB2_API_BEGIN
+  if (!c || !cycles)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  for (int i = 0; i < 16; ++i)
+    cycles[i] = 0;
+  if (c->linkProfile.ptr)
+    NB2_CUDA(cudaMemcpy(cycles, c->linkProfile.ptr, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  NB2_API_END
+}
 
 int nb2_timer_start(nb2_context* c)
 {

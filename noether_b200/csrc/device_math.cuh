@@ -93,6 +93,44 @@ NB2_DEV int contourCase(const double s[3])
   return (s[0] >= 0.0 ? 1 : 0) | (s[1] >= 0.0 ? 2 : 0) | (s[2] >= 0.0 ? 4 : 0);
 }
 
+/** Where endpoint `which` (0/1) of the line of case `index` lies: on the triangle edge from local vertex e1 (lower scalar) to
+ *  e2, at parameter t = (0 - s_lo) / (s_hi - s_lo) (vtkTriangle::Contour; t = 0 when the edge lies in the plane) */
+struct CutParam
+{
+  int e1, e2;
+  double t;
+};
+NB2_DEV CutParam cutParam(int index, int which, const double s[3])
+{
+  const int edge = lineCaseEdge(index, which);
+  const int v0 = edge, v1 = edge == 2 ? 0 : edge + 1;
+  double delta = dsub(pick3(s, v1), pick3(s, v0));
+  CutParam c;
+  if (delta > 0.0)
+  {
+    c.e1 = v0;
+    c.e2 = v1;
+  }
+  else
+  {
+    c.e1 = v1;
+    c.e2 = v0;
+    delta = -delta;
+  }
+  c.t = (delta == 0.0) ? 0.0 : ddiv(dsub(0.0, pick3(s, c.e1)), delta);
+  return c;
+}
+/** x_lo + t (x_hi - x_lo) in double, stored as float (the cut point's coordinate) */
+NB2_DEV float lerpPosition(float a, float b, double t)
+{
+  return d2f(dadd(static_cast<double>(a), dmul(t, dsub(static_cast<double>(b), static_cast<double>(a)))));
+}
+/** a_lo (1 - t) + a_hi t in double, stored as float (vtkDataSetAttributes::InterpolateEdge) */
+NB2_DEV float lerpAttribute(float a, float b, double t, double omt)
+{
+  return d2f(dadd(dmul(static_cast<double>(a), omt), dmul(static_cast<double>(b), t)));
+}
+
 /** Interpolate endpoint `which` (0/1) of the line of case `index`; normals only when nv != nullptr (nv = the vertex
  *  normals of the triangle's three vertices, already in registers).
  *  Restates vtkTriangle::Contour: interpolate from the lower- to the higher-scalar end, t = (0 - s_lo) / (s_hi - s_lo),

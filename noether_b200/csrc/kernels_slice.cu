@@ -23,9 +23,11 @@
 //
 // Output of S6 is the reference's planImpl result before convertToPoses expands it to 4x4 matrices.
 #include "device_math.cuh"
+#include "link2_ops.h"
 #include "nb2_internal.h"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace nb2
 {
@@ -442,6 +444,9 @@ struct LinkParams
   unsigned smemHitCap;   // largest plane (in hits) that fits the shared-memory work area
   unsigned scratchHits;  // largest plane the global work areas were sized for
   unsigned* overflow;    // bit 0: hit buffers too small (k_emit_hits), bit 1: a plane exceeds scratchHits
+  unsigned fastHitCap;   // largest plane (in cut lines) whose second-generation work area fits the CTA's shared memory
+  unsigned* generalCount;  // planes the second-generation fast path declined (diagnostics)
+  unsigned long long* phaseCycles;  // [16] diagnostics (NB2_LINK_PROFILE), normally null
   unsigned* done;        // CTAs that ran out of planes (the last one scans the per-plane counts)
   uint2* planePrefix;    // [nP + 1] {waypoints, segments} before each plane
   unsigned* totals;      // [2] waypoints, segments of the slab
@@ -463,7 +468,7 @@ constexpr unsigned kMaxCrowdedEnds = 32u;  // line ends at one such point
 // s_misc: [0] chains, [1] error bits, [2] splitters, [4] plane waypoints, [5] ranking flag, [6] crowded points,
 //         [7] closed loops present, [8..] crowded slot ids
 constexpr int kMiscWords = 8 + kMaxCrowded;
-constexpr int kLinkThreads = 1024;
+constexpr int kLinkThreads = 512;
 // list ranking: both darts of every (1 << kSplitShift)-th line of the bucket are splitters (Helman & JaJa)
 constexpr unsigned kSplitShift = 4u, kSplitMask = (1u << kSplitShift) - 1u;
 
@@ -1005,7 +1010,9 @@ __device__ __forceinline__ unsigned hashPointFast(float x, float y, float z)
 {
   const unsigned a = __float_as_uint(x == 0.f ? 0.f : x), b = __float_as_uint(y == 0.f ? 0.f : y),
                  c = __float_as_uint(z == 0.f ? 0.f : z);
-  unsigned h = a * 0x9E3779B1u + b * 0x85EBCA77u + c * 0xC2B2AE3Du;
+  // (rotated against one another: with plain sums the sign bits of two coordinates cancel, and the points (x, y, z) and
+  //  (-x, y, -z) of a point-symmetric part would always collide)
+  unsigned h = a * 0x9E3779B1u + __funnelshift_l(b, b, 11) * 0x85EBCA77u + __funnelshift_l(c, c, 22) * 0xC2B2AE3Du;
   h ^= h >> 15;
   h *= 0x2C1B3C6Du;
   return h ^ (h >> 13);
@@ -1413,6 +1420,181 @@ __device__ bool linkPlaneFast(const LinkParams& P, uint8_t* smem, long long kLoc
   return true;
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// S5, second generation (link2_ops.h): no shared-memory atomics, 4 bytes of hash per endpoint staged instead of 16 bytes
+// of coordinates, one dart per line, ranks from the chain heads; two planes resident per SM.
+// -----------------------------------------------------------------------------------------------------------------
+struct DevOps
+{
+  static __device__ __forceinline__ void orr(unsigned* a, unsigned v)
+  {
+    if ((*reinterpret_cast<volatile unsigned*>(a) & v) != v)
+      atomicOr(a, v);
+  }
+  static __device__ __forceinline__ unsigned add(unsigned* a, unsigned v) { return atomicAdd(a, v); }
+  static __device__ __forceinline__ unsigned cas(unsigned* a, unsigned cmp, unsigned v) { return atomicCAS(a, cmp, v); }
+  /** a place in a compacted list for every thread that wants one: one atomic per warp.  Warp-wide: all lanes call it. */
+  static __device__ __forceinline__ unsigned claim(unsigned* counter, bool wanted)
+  {
+    const unsigned m = __ballot_sync(kFull, wanted);
+    if (m == 0u)
+      return 0u;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0;
+    if (lane == static_cast<unsigned>(__ffs(m)) - 1u)
+      base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(kFull, base, __ffs(m) - 1);
+    return base + __popc(m & ((1u << lane) - 1u));
+  }
+  static __device__ __forceinline__ unsigned vload(const unsigned* a) { return *reinterpret_cast<const volatile unsigned*>(a); }
+  static __device__ __forceinline__ link2::Rec4 load(const link2::Rec4* p)
+  {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    return link2::Rec4{ v.x, v.y, v.z, v.w };
+  }
+  static __device__ __forceinline__ unsigned long long ld64(const unsigned long long* p)
+  {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+  }
+  static __device__ __forceinline__ void st64(unsigned long long* p, unsigned long long v)
+  {
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+  }
+};
+
+// NB2_LINK_PROFILE (environment, read once by the launcher): clock cycles per phase of the fast path, summed over the
+// planes by thread 0 of every CTA (diagnostics only; LinkParams::phaseCycles is null otherwise)
+struct PhaseClock
+{
+  unsigned long long* acc;
+  long long last;
+  __device__ explicit PhaseClock(unsigned long long* a) : acc(a), last(0)
+  {
+    if (acc && threadIdx.x == 0)
+      last = clock64();
+  }
+  __device__ __forceinline__ void lap(int phase)
+  {
+    if (acc && threadIdx.x == 0)
+    {
+      const long long now = clock64();
+      atomicAdd(acc + phase, static_cast<unsigned long long>(now - last));
+      last = now;
+    }
+  }
+};
+
+/** The second-generation fast path on one plane: false when the plane needs another path (what it wrote by then lies in
+ *  the plane's own output windows and is overwritten) */
+__device__ __forceinline__ bool linkPlane2(const LinkParams& P, uint8_t* smem, long long kLocal, unsigned n)
+{
+  using namespace link2;
+  const unsigned tid = threadIdx.x, nth = blockDim.x;
+  if (!fitsThreadSet(n, nth))
+    return false;
+  const unsigned off = P.planeOff[kLocal];
+  const Rec4* rec = reinterpret_cast<const Rec4*>(P.rec + 2ull * off);
+  const Work W = carve(smem, n);
+  PhaseClock clk(P.phaseCycles);
+  phaseInit<DevOps>(W, tid, nth);
+  __syncthreads();
+  clk.lap(0);
+  unsigned todo = phaseHash<DevOps>(W, rec, tid, nth);
+  __syncthreads();
+  clk.lap(1);
+  // Claim rounds with plain stores (no shared-memory compare-and-swap: one costs this SM about as much as a whole late
+  // round); the first claim rode along with the hashing.  phaseStragglers (compare-and-swap) is the bounded exit.
+  bool left = true;
+  for (unsigned round = 0; round < 32u && left; ++round)
+  {
+    if (round)
+    {
+      phaseClaim<DevOps>(W, todo, tid, nth);
+      __syncthreads();
+    }
+    todo = phaseSettle<DevOps>(W, todo, tid, nth);
+    left = __syncthreads_or(todo != 0u ? 1 : 0) != 0;
+  }
+  if (left)
+  {
+    phaseStragglers<DevOps>(W, todo, tid, nth);
+    __syncthreads();
+  }
+  clk.lap(2);
+  phasePair<DevOps>(W, tid, nth);
+  __syncthreads();
+  if (W.misc[M_ANYDEAD])
+  {
+    phaseDead<DevOps>(W, tid, nth);
+    __syncthreads();
+    if (W.misc[M_FAIL])
+      return false;
+  }
+  clk.lap(3);
+  phaseLink<DevOps>(W, tid, nth);
+  __syncthreads();
+  clk.lap(4);
+  if (W.misc[M_FAIL])
+    return false;
+  phaseWalk<DevOps>(W, tid, nth);
+  __syncthreads();
+  clk.lap(5);
+  for (unsigned round = 0, rounds = jumpRounds(W.misc[M_NS]); round < rounds; ++round)
+    if (!__syncthreads_or(phaseJump<DevOps>(W, tid, nth) ? 1 : 0))
+      break;
+  clk.lap(6);
+  phaseChains<DevOps>(W, tid, nth);
+  __syncthreads();
+  if (W.misc[M_FAIL])
+    return false;
+  phaseHeads<DevOps>(W, rec, P.L.dir, tid, nth);
+  __syncthreads();
+  if (W.misc[M_FAIL])
+    return false;
+  phaseOrder<DevOps>(W, tid, nth);
+  __syncthreads();
+  // exclusive prefix of the chain sizes (few chains per plane: one warp, serial over 32-wide chunks)
+  if (tid < 32)
+  {
+    const unsigned S = W.misc[M_NH];
+    unsigned carry = 0;
+    for (unsigned base = 0; base < S; base += 32)
+    {
+      const unsigned i = base + tid;
+      const unsigned v = i < S ? W.sortedLen[i] : 0u;
+      unsigned x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned y = __shfl_up_sync(kFull, x, o);
+        if (tid >= static_cast<unsigned>(o))
+          x += y;
+      }
+      if (i < S)
+        W.sortedLen[i] = carry + x - v;
+      carry += __shfl_sync(kFull, x, 31);
+    }
+    if (tid == 0)
+      W.misc[M_WK] = carry;
+  }
+  __syncthreads();
+  clk.lap(7);
+  Out o;
+  o.wpTag = P.wpTag + 2ull * off;  // the plane's own output windows (see LinkParams)
+  o.segLen = P.segLen + off;
+  phaseOutput<DevOps>(W, rec, o, tid, nth);
+  __syncthreads();
+  clk.lap(8);
+  if (W.misc[M_FAIL])
+    return false;
+  if (tid == 0)
+  {
+    P.planeMeta[2 * kLocal] = W.misc[M_WK];
+    P.planeMeta[2 * kLocal + 1] = W.misc[M_NH];
+  }
+  return true;
+}
+
 /** Exclusive prefix of the per-plane waypoint and segment counts (one block; nP is at most a few thousand; the counts
  *  were written by other blocks and are read past L1).
  *  prefix[k] = {waypoints, segments} before plane k; prefix[nP] = totals, also written to totals[0..1]. */
@@ -1472,7 +1654,7 @@ __device__ void scanMetaBlock(const unsigned* planeMeta, long long nP, uint2* __
 }
 
 
-__global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
+__global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ unsigned s_misc[kMiscWords];
@@ -1513,6 +1695,13 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
     unsigned cap = 16;
     while (cap < E)
       cap <<= 1;
+    if (n <= P.fastHitCap && linkPlane2(P, smem, kLocal, n))
+      continue;
+    // The second-generation path declined (a cut point with more than two line ends, a closed contour, inconsistently
+    // wound triangles, a crowd of zero-length lines, a plane beyond its work area): the first-generation paths take it
+    __syncthreads();
+    if (threadIdx.x == 0)
+      atomicAdd(P.generalCount, 1u);
     if (n <= P.smemHitCap && linkPlaneFast(P, smem, kLocal, n, cap, s_misc))
     {
       // done
@@ -1575,8 +1764,8 @@ __global__ void __launch_bounds__(kLinkThreads, 1) k_link_planes(LinkParams Pin)
   const unsigned* f = reinterpret_cast<const unsigned*>(P.frame);
   for (unsigned i = threadIdx.x; i < sizeof(FrameDev) / 4u; i += blockDim.x)
     P.reportFrame[i] = __ldcg(f + i);
-  if (threadIdx.x < 10)
-    P.reportSizes[threadIdx.x] = __ldcg(P.counters + 4 + threadIdx.x);
+  if (threadIdx.x < 11)
+    P.reportSizes[threadIdx.x] = __ldcg(P.counters + 4 + threadIdx.x);  // ([10] = counters[14]: planes the fast path declined)
   const long long words = 2 * min(nP, static_cast<long long>(P.reportPlanes));
   for (long long i = threadIdx.x; i < words; i += blockDim.x)
     P.reportMeta[i] = __ldcg(P.planeMeta + i);
@@ -1741,15 +1930,15 @@ void launchEmitHits(nb2_context* c, uint64_t hit_cap)
   ++c->launches;
 }
 
-unsigned linkSmemHitCap(const nb2_context* c)
+/** largest plane (cut lines) whose work area, as sized by `bytes_for`, fits `budget` bytes */
+template <typename F>
+static unsigned largestPlane(size_t budget, unsigned hi, F bytes_for)
 {
-  // largest plane that fits the opt-in shared memory (uint16 indices additionally need 2 n < 65535)
-  const size_t smem_budget = c->smem_optin > 1024 ? c->smem_optin - 1024 : 0;
-  unsigned lo = 0, hi = 32767;
+  unsigned lo = 0;
   while (lo < hi)
   {
-    const unsigned mid = (lo + hi + 1) / 2;
-    if (smemWorkBytes(mid) <= smem_budget)
+    const unsigned mid = lo + (hi - lo + 1) / 2;
+    if (bytes_for(mid) <= budget)
       lo = mid;
     else
       hi = mid - 1;
@@ -1759,13 +1948,39 @@ unsigned linkSmemHitCap(const nb2_context* c)
 
 void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, const LinkReport& report)
 {
-  const unsigned smem_cap = linkSmemHitCap(c);
-  const size_t smem_bytes = smemWorkBytes(smem_cap > 0 ? smem_cap : 1);
-  const int grid = c->sm_count;
-  size_t stride = 0;
-  if (scratch_hits > smem_cap)
+  // Shared memory per CTA: the second-generation work area for the largest plane expected (the previous plan's largest
+  // plane plus a margin; the first plan of a context knows its own), but no more than lets two CTAs share an SM — the
+  // planes of two CTAs hide each other's barriers and global-memory phases.  Larger planes get the whole SM; planes beyond
+  // even that, and planes the fast path declines, go to the first-generation paths: in shared memory when they fit
+  // there, in the CTA's slice of the global scratch otherwise.
+  const unsigned n_last = static_cast<unsigned>(std::min<uint64_t>(link2::kMaxLines, c->grid_nmax));
+  const unsigned n_hint = static_cast<unsigned>(std::min<uint64_t>(link2::kMaxLines, static_cast<uint64_t>(n_last) + n_last / 8 + 64));
+  const size_t per_sm = c->smem_per_sm ? c->smem_per_sm : (size_t(228) << 10);
+  const size_t two_per_sm = per_sm / 2 - 1024 - 512;  // (1 KB reserved per CTA, static shared memory)
+  const size_t optin = c->smem_optin > 2048 ? c->smem_optin - 2048 : 0;
+  size_t smem_bytes = std::max<size_t>(link2::workBytes(n_hint), size_t(16) << 10);
+  if (smem_bytes > two_per_sm)
   {
-    stride = (globalWorkBytes(scratch_hits) + 255) & ~size_t(255);
+    // the margin must not cost the second CTA: when the last plan's largest plane fits two to an SM, that is the budget
+    smem_bytes = link2::workBytes(n_last + 16) <= two_per_sm ? two_per_sm : std::min(smem_bytes, optin);
+  }
+  smem_bytes = std::min(smem_bytes, optin);
+  const unsigned fast_cap = largestPlane(smem_bytes, link2::kMaxLines, [](unsigned n) { return link2::workBytes(n); });
+  const unsigned smem_cap = largestPlane(smem_bytes, 32767u, [](unsigned n) { return smemWorkBytes(n); });
+  NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  // (planes of a few hundred cut lines do not fill 512 threads: smaller CTAs, more of them per SM)
+  const int threads = n_hint >= 2048u ? kLinkThreads : kLinkThreads / 2;
+  int per_sm_ctas = 1;
+  NB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_link_planes, threads, smem_bytes));
+  int grid = c->sm_count * std::max(1, per_sm_ctas);
+  // global scratch of the first-generation paths: any plane may end up there
+  const uint32_t scratch_n = std::max<uint32_t>(scratch_hits, n_hint);
+  size_t stride = 0;
+  if (scratch_n > smem_cap)
+  {
+    stride = (globalWorkBytes(scratch_n) + 255) & ~size_t(255);
+    while (grid > c->sm_count && stride * grid > (size_t(8) << 30))
+      grid -= c->sm_count;
     c->linkScratch.ensure(stride * grid);
   }
   const size_t planes = static_cast<size_t>(c->plane_cap) + 1;
@@ -1786,8 +2001,17 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   P.scratch = c->linkScratch.as<uint8_t>();
   P.scratchStride = stride;
   P.smemHitCap = smem_cap;
-  P.scratchHits = scratch_hits > smem_cap ? scratch_hits : 0u;
+  P.scratchHits = scratch_n > smem_cap ? scratch_n : 0u;
   P.overflow = c->counters.as<unsigned>() + 13;
+  P.fastHitCap = fast_cap;
+  P.generalCount = c->counters.as<unsigned>() + 14;
+  static const bool profile = std::getenv("NB2_LINK_PROFILE") != nullptr;
+  if (profile)
+  {
+    c->linkProfile.ensure(16 * sizeof(unsigned long long));
+    NB2_CUDA(cudaMemsetAsync(c->linkProfile.ptr, 0, 16 * sizeof(unsigned long long), c->stream));
+    P.phaseCycles = c->linkProfile.as<unsigned long long>();
+  }
   P.done = c->counters.as<unsigned>() + 3;
   P.planePrefix = c->planePrefix.as<uint2>();
   P.totals = c->counters.as<unsigned>() + 6;
@@ -1798,8 +2022,7 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   P.reportPlanes = report.planes;
   P.stamp = report.stamp;
 
-  NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  k_link_planes<<<grid, kLinkThreads, smem_bytes, c->stream>>>(P);
+  k_link_planes<<<grid, threads, smem_bytes, c->stream>>>(P);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

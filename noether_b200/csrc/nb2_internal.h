@@ -179,6 +179,7 @@ struct nb2_context
   int device = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
+  size_t smem_per_sm = 0;
   cudaStream_t stream = nullptr;
   mutable std::mutex mu;
   uint64_t launches = 0;
@@ -209,6 +210,7 @@ struct nb2_context
   // capacities the post-count stage was last sized for (0 = not yet known: the first plan waits for its hit count)
   uint64_t hit_cap = 0;      // hits (triangle x plane)
   uint32_t scratch_hits = 0; // hits of the largest plane, when it exceeds what fits shared memory
+  uint32_t last_general_planes = 0;  // planes of the last plan that the linker's second-generation fast path declined
   uint32_t grid_planes = 0, grid_nmax = 0;  // planes / largest plane of the last plan: launch geometry of k_waypoints
   // slicing workspace
   nb2::DevBuf vertK;       // int32[V]
@@ -226,6 +228,7 @@ struct nb2_context
   nb2::DevBuf outNrm;      // float[3 * Wcap]
   nb2::DevBuf outEdge;     // uint32[2 * Wcap]
   nb2::DevBuf outSegLen;   // uint32[Scap]
+  nb2::DevBuf linkProfile;   // uint64[16] cycles per phase of the linker's fast path (NB2_LINK_PROFILE diagnostics)
   nb2::DevBuf linkScratch; // global scratch for planes too large for shared memory
   // legacy modifiers on the device (kernels_legacy.cu)
   nb2::DevBuf legCum;     // double[W] running chord length of every waypoint inside its (merged) segment
@@ -339,7 +342,6 @@ void launchExtents(nb2_context* c, const FrameParams* lattice_prm = nullptr);
 void launchClassify(nb2_context* c);
 void launchCountHits(nb2_context* c);  // + scan of the per-plane counters: writes {H, n_max} to counters[4..5]
 void launchEmitHits(nb2_context* c, uint64_t hit_cap);
-unsigned linkSmemHitCap(const nb2_context* c);
 /** Where the last CTA of k_link_planes leaves the plan's report (pinned host memory, device-visible addresses) */
 struct LinkReport
 {

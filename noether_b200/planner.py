@@ -210,6 +210,16 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self._lib.nb2_kernel_launches(self._h))
 
+    def link_profile(self) -> list[int]:
+        """cycles per phase of the linker's fast path in the last plan (NB2_LINK_PROFILE=1 in the environment)"""
+        out = (C.c_uint64 * 16)()
+        _capi.check(self._lib.nb2_link_profile(self._h, out))
+        return [int(v) for v in out]
+
+    def general_path_planes(self) -> int:
+        """planes of the last plan whose cut lines the linker's general path joined (diagnostics)"""
+        return int(self._lib.nb2_last_plan_general_path_planes(self._h))
+
     def timer_start(self):
         _capi.check(self._lib.nb2_timer_start(self._h))
 

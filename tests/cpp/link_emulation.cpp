@@ -1,4 +1,5 @@
-// TEST INFRASTRUCTURE.  Host replay of the contouring (k_emit_hits) and of the fast linking path (k_link_planes) of
+// TEST INFRASTRUCTURE.  Host replay of the contouring (k_emit_hits), the fast linking path (k_link_planes) and the
+// waypoint pass (k_waypoints) of
 // noether_b200/csrc/kernels_slice.cu: the kernels' own per-element functions — device_math.cuh (plane scalars, vtkTriangle
 // case table, cut-point and normal interpolation) and link2_ops.h (every phase of the linker) — driven by loops instead of
 // CTAs, "threads" visited in a scrambled order and the plane's cut lines stored in a scrambled order (the order the
@@ -23,6 +24,7 @@ namespace
 {
 struct HostOps
 {
+  static void orr(unsigned* a, unsigned v) { *a |= v; }
   static unsigned cas(unsigned* a, unsigned cmp, unsigned v)
   {
     const unsigned seen = *a;
@@ -36,10 +38,14 @@ struct HostOps
     *a = old + v;
     return old;
   }
-  static void orr(unsigned* a, unsigned v) { *a |= v; }
+  static unsigned claim(unsigned* counter, bool wanted)
+  {
+    if (!wanted)
+      return 0u;
+    return (*counter)++;
+  }
   static unsigned vload(const unsigned* a) { return *a; }
   static Rec4 load(const Rec4* p) { return *p; }
-  static unsigned loadRank(const Rec4* p) { return bitsOf(p->w); }
   static unsigned long long ld64(const unsigned long long* p) { return *p; }
   static void st64(unsigned long long* p, unsigned long long v) { *p = v; }
 };
@@ -54,6 +60,9 @@ struct Result
   std::vector<int64_t> declined_plane;
   std::vector<uint32_t> declined_reason;
   uint64_t lines = 0;
+  std::vector<uint32_t> declined_misc;  // the first eight misc words of every declined plane (diagnostics)
+  unsigned max_rounds = 0;              // most claim rounds any plane needed
+  uint64_t stragglers = 0;              // endpoints the plain rounds left to the compare-and-swap loop
 } g;
 
 /** visit 0 .. n-1 in a scrambled (but complete) order */
@@ -151,7 +160,7 @@ int emu_slice(const float* xyz, const float* nrm, uint64_t V, const uint32_t* tr
       });
     }
     // ---- the fast path of k_link_planes ------------------------------------------------------------------------------
-    if (nl > kMaxLines)
+    if (nl > kMaxLines || !fitsThreadSet(nl, nth))
     {
       g.declined_plane.push_back(k);
       g.declined_reason.push_back(F_CAPACITY);
@@ -165,19 +174,38 @@ int emu_slice(const float* xyz, const float* nrm, uint64_t V, const uint32_t* tr
         return false;
       g.declined_plane.push_back(k);
       g.declined_reason.push_back(W.misc[M_FAIL]);
+      g.declined_misc.insert(g.declined_misc.end(), W.misc, W.misc + 8);
       return true;
     };
     unsigned phase = 0;
     auto run = [&](auto fn) { scrambled(nth, seed + 17u * ++phase, [&](unsigned tid) { fn(tid); }); };
+    std::vector<unsigned> todo(nth, 0u);  // (a register of each thread on the device)
     run([&](unsigned tid) { phaseInit<HostOps>(W, tid, nth); });
-    run([&](unsigned tid) { phaseInsert<HostOps>(W, rec.data(), tid, nth); });
+    run([&](unsigned tid) { todo[tid] = phaseHash<HostOps>(W, rec.data(), tid, nth); });
+    // (at least the round whose claim rode along with the hashing — the device always settles that one; also: few plain
+    //  rounds, the rest left to the compare-and-swap loop)
+    const unsigned plain_rounds = (seed & 1u) ? kPlainRounds : 1u + (seed % 6u);
+    for (unsigned round = 0; round < plain_rounds; ++round)
+    {
+      if (round)  // (the first claim is part of phaseHash)
+        run([&](unsigned tid) { phaseClaim<HostOps>(W, todo[tid], tid, nth); });
+      bool any = false;
+      run([&](unsigned tid) {
+        todo[tid] = phaseSettle<HostOps>(W, todo[tid], tid, nth);
+        any = any || todo[tid] != 0u;
+      });
+      g.max_rounds = std::max(g.max_rounds, round + 1);
+      if (!any)
+        break;
+    }
+    for (unsigned tid = 0; tid < nth; ++tid)
+      g.stragglers += static_cast<unsigned>(__builtin_popcount(todo[tid]));
+    run([&](unsigned tid) { phaseStragglers<HostOps>(W, todo[tid], tid, nth); });
+    run([&](unsigned tid) { phasePair<HostOps>(W, tid, nth); });
+    if (W.misc[M_ANYDEAD])
+      run([&](unsigned tid) { phaseDead<HostOps>(W, tid, nth); });
     if (declined())
       continue;
-    run([&](unsigned tid) { phaseVerify<HostOps>(W, rec.data(), L.dir, tid, nth); });
-    if (declined())
-      continue;
-    if (W.misc[M_RETRY])
-      run([&](unsigned tid) { phaseRetry<HostOps>(W, rec.data(), tid, nth); });
     run([&](unsigned tid) { phaseLink<HostOps>(W, tid, nth); });
     if (declined())
       continue;
@@ -198,18 +226,36 @@ int emu_slice(const float* xyz, const float* nrm, uint64_t V, const uint32_t* tr
     run([&](unsigned tid) { phaseOrder<HostOps>(W, tid, nth); });
     scanChainsSerial(W);
     const unsigned Wk = W.misc[M_WK], Sk = W.misc[M_NH];
-    const size_t w0 = g.pos.size() / 3, s0 = g.seg_len.size();
-    g.pos.resize(3 * (w0 + Wk), -12345.f);
-    g.nrm.resize(3 * (w0 + Wk), -12345.f);
-    if (want_edges)
+    std::vector<unsigned> tags(Wk, 0xffffffffu), lens(Sk, 0u);
+    Out o{ tags.data(), lens.data() };
+    run([&](unsigned tid) { phaseOutput<HostOps>(W, rec.data(), o, tid, nth); });
+    if (declined())
+      continue;
+    // ---- k_waypoints: the first inserter's triangle contoured again, normals interpolated along the cut edge ----------
+    for (unsigned i = 0; i < Wk; ++i)
     {
-      g.elo.resize(w0 + Wk, 0xdeadbeefu);
-      g.ehi.resize(w0 + Wk, 0xdeadbeefu);
+      const unsigned t = tags[i] >> 1;
+      if (t >= F)
+        return -2;  // a waypoint nobody named
+      const uint32_t ids[3] = { tri[3 * t], tri[3 * t + 1], tri[3 * t + 2] };
+      float4 p[3], nv[3];
+      double s[3];
+      for (int j = 0; j < 3; ++j)
+      {
+        p[j] = make_float4(xyz[3 * ids[j]], xyz[3 * ids[j] + 1], xyz[3 * ids[j] + 2], 0.f);
+        nv[j] = make_float4(nrm[3 * ids[j]], nrm[3 * ids[j] + 1], nrm[3 * ids[j] + 2], 0.f);
+        s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
+      }
+      const CutPoint c = interpolateCut(contourCase(s), static_cast<int>(tags[i] & 1u), ids, p, s, nv);
+      g.pos.insert(g.pos.end(), { c.x, c.y, c.z });
+      g.nrm.insert(g.nrm.end(), { c.nx, c.ny, c.nz });
+      if (want_edges)
+      {
+        g.elo.push_back(c.lo);
+        g.ehi.push_back(c.hi);
+      }
     }
-    g.seg_len.resize(s0 + Sk, 0u);
-    Out o{ g.pos.data() + 3 * w0, g.nrm.data() + 3 * w0, want_edges ? g.elo.data() + w0 : nullptr,
-           want_edges ? g.ehi.data() + w0 : nullptr, g.seg_len.data() + s0 };
-    run([&](unsigned tid) { phaseOutput<HostOps>(W, rec.data(), nrec.data(), want_edges ? erec.data() : nullptr, o, tid, nth); });
+    g.seg_len.insert(g.seg_len.end(), lens.begin(), lens.end());
     g.path_plane.push_back(k);
     g.path_segments.push_back(Sk);
   }
@@ -241,4 +287,7 @@ void emu_export(int64_t* path_plane, uint32_t* path_segments, uint32_t* seg_len,
 }
 
 uint64_t emu_work_bytes(unsigned n) { return workBytes(n); }
+unsigned emu_max_rounds() { return g.max_rounds; }
+uint64_t emu_stragglers() { return g.stragglers; }
+void emu_declined_misc(uint32_t* out) { std::memcpy(out, g.declined_misc.data(), 4 * g.declined_misc.size()); }
 }

@@ -65,6 +65,13 @@ def main():
     print("paths/segments/waypoints", n)
     print("stages ms", {k: round(v, 4) for k, v in st.items()})
     print("step ms (events) %.4f, sum of stages %.4f" % (total, sum(st.values())))
+    print("planes linked by the general path:", ctx.general_path_planes())
+    if os.environ.get("NB2_LINK_PROFILE"):
+        cyc = ctx.link_profile()
+        names = ["init", "hash", "claim rounds", "pair+dead", "link", "walk", "jump", "heads+order", "output"]
+        tot = max(1, sum(cyc))
+        print("linker phases (cycles of thread 0 summed over CTAs and planes):",
+              {n: f"{100 * c / tot:.1f}%" for n, c in zip(names, cyc)}, "total cycles", tot)
     ctx.close()
 
 
