@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NB2_ABI_VERSION 2
+#define NB2_ABI_VERSION 3
 
 typedef enum nb2_status
 {
@@ -70,12 +70,46 @@ typedef struct nb2_mesh_view
   uint32_t point_step;
   uint32_t offset_xyz;      /* offset of field "x"; "y","z" must follow contiguously (utils.cpp:82-83) */
   int32_t offset_normal;    /* offset of "normal_x" (normal_y, normal_z contiguous, utils.cpp:104-105); -1 = none */
-  uint32_t reserved_;
+  uint32_t flags;           /* NB2_MESH_*; 0 = the records travel and stay resident as they are */
   const uint32_t* triangles; /* 3 * n_triangles vertex indices */
   uint64_t n_triangles;
 } nb2_mesh_view;
+/* flags: only positions and normals of this cloud will be used on the device (planning, normals, clustering — not the
+ * face subdivisions, which copy whole records): a host cloud is compacted to {x y z [nx ny nz]} records on its way through
+ * the pinned staging ring, so a 48-byte PointNormal record costs 24 bytes of PCIe and HBM traffic.
+ * nb2_mesh_record_layout reports the resident layout. */
+#define NB2_MESH_GEOMETRY_ONLY 1u
 
+/* Host memory that is not pinned, and clouds to be compacted, travel through a ring of pinned slots filled by the host
+ * cores (one cudaMemcpyAsync per slot behind them); pinned arrays go out in one piece. */
 int nb2_mesh_upload(nb2_context* ctx, const nb2_mesh_view* mesh);
+
+/* The same upload with the mesh PRODUCED by the caller, piece by piece, straight into the pinned slots — for callers
+ * whose mesh is not two flat arrays (pcl::PolygonMesh::polygons is one std::vector per face: plugin/b200_plugins.cpp
+ * flattens, compacts and fingerprints in these callbacks, one pass over the host data in all).
+ *   cloud(user, first, count, dst)      writes records [first, first + count) as count * point_step bytes
+ *   triangles(user, first, count, dst)  writes triangles [first, first + count) as 3 * count indices
+ * are called from several library threads at once on disjoint ranges; `first` is a multiple of NB2_UPLOAD_GRAIN; a
+ * non-zero return aborts the upload (NB2_ERR_INVALID_ARGUMENT).  When everything is staged, accept(user) decides:
+ * non-zero, the staged mesh becomes the resident one (*committed = 1); zero, it is dropped and the resident mesh, with
+ * everything derived from it on the device (PCA, extents, computed normals), stays (*committed = 0) — the caller found,
+ * from what its callbacks saw, that the content is what the device already holds.  The staged mesh lands in a second
+ * pair of device buffers, so nothing resident is touched before accept().  accept may be NULL (always commit). */
+#define NB2_UPLOAD_GRAIN 65536u
+typedef struct nb2_mesh_stream
+{
+  uint64_t n_points;
+  uint32_t point_step;     /* bytes per record as written by `cloud` */
+  uint32_t offset_xyz;
+  int32_t offset_normal;   /* -1 = none */
+  uint32_t reserved_;
+  uint64_t n_triangles;
+  int (*cloud)(void* user, uint64_t first, uint64_t count, void* dst);
+  int (*triangles)(void* user, uint64_t first, uint64_t count, uint32_t* dst);
+  int (*accept)(void* user);
+  void* user;
+} nb2_mesh_stream;
+int nb2_mesh_upload_stream(nb2_context* ctx, const nb2_mesh_stream* mesh, int* committed /* may be NULL */);
 /* Replace the resident normals with packed float[3 * n_points] from the host (e.g. another modifier's output). */
 int nb2_mesh_set_normals(nb2_context* ctx, const float* normals);
 /* Copy the resident SoA back (packed float[3 * n]); either pointer may be NULL.  Test / debugging aid. */

@@ -29,12 +29,13 @@ NB2_DIRECTION_PRINCIPAL_AXIS = 1
 NB2_ORIGIN_EXPLICIT = 0
 NB2_ORIGIN_CENTROID = 1
 NB2_ALL_PLANES = 2**64 - 1
+NB2_MESH_GEOMETRY_ONLY = 1
 NB2_UNIQUE_ID_BYTES = 128
 
 # every symbol include/noether_b200.h declares (tests check the library exports all of them)
 DECLARED_SYMBOLS = [
     "nb2_abi_version", "nb2_last_error", "nb2_context_create", "nb2_context_destroy", "nb2_context_device",
-    "nb2_mesh_upload", "nb2_mesh_set_normals", "nb2_mesh_download", "nb2_mesh_pca", "nb2_principal_axis_direction",
+    "nb2_mesh_upload", "nb2_mesh_upload_stream", "nb2_mesh_set_normals", "nb2_mesh_download", "nb2_mesh_pca", "nb2_principal_axis_direction",
     "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_eigen_solver_3f", "nb2_plan_params_default", "nb2_slice",
     "nb2_plan", "nb2_plan_mesh", "nb2_last_lattice", "nb2_result_get", "nb2_result_poses", "nb2_result_poses_segments", "nb2_result_free", "nb2_last_timings",
     "nb2_kernel_launches", "nb2_last_plan_general_path_planes", "nb2_link_profile", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
@@ -70,7 +71,7 @@ class Modifier(C.Structure):
 
 class MeshView(C.Structure):
     _fields_ = [("cloud_data", C.c_void_p), ("n_points", C.c_uint64), ("point_step", C.c_uint32),
-                ("offset_xyz", C.c_uint32), ("offset_normal", C.c_int32), ("reserved_", C.c_uint32),
+                ("offset_xyz", C.c_uint32), ("offset_normal", C.c_int32), ("flags", C.c_uint32),
                 ("triangles", C.c_void_p), ("n_triangles", C.c_uint64)]
 
 

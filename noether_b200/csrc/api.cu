@@ -9,7 +9,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <atomic>
+#include <functional>
 #include <memory>
+#include <thread>
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -728,7 +731,7 @@ void nb2_context_destroy(nb2_context* c)
   if (c->stream)
     cudaStreamSynchronize(c->stream);
   nb2_comm_destroy(c);
-  for (DevBuf* b : { &c->blob, &c->fileImg, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
+  for (DevBuf* b : { &c->blob, &c->blobSpare, &c->triSpare, &c->fileImg, &c->pos, &c->nrm, &c->tri, &c->partials, &c->frame, &c->counters, &c->vertK, &c->planeCnt,
                      &c->planeOff, &c->planeCursor, &c->hitRec, &c->linkProfile, &c->wpTag, &c->segLen, &c->planePrefix, &c->quadList, &c->legCum, &c->legSeg, &c->legPlane, &c->legPose, &c->legPos,
                      &c->legNrm, &c->legSegLen, &c->planeMeta, &c->outPos, &c->outNrm,
                      &c->outEdge, &c->outSegLen, &c->linkScratch, &c->faceNrm, &c->valence, &c->csrOff, &c->csrCursor,
@@ -738,6 +741,10 @@ void nb2_context_destroy(nb2_context* c)
                      &c->subKeys, &c->cluHead, &c->cluNext, &c->cluParent, &c->cluLabel, &c->cluCellSize, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
   c->hostSmall.release();
+  c->stageRing.release();
+  for (auto& e : c->stageEvents)
+    cudaEventDestroy(e);
+  c->stageEvents.clear();
   for (auto& hb : c->hostPool)
     cudaFreeHost(hb.ptr);
   c->timer.destroy();
@@ -750,6 +757,153 @@ void nb2_context_destroy(nb2_context* c)
 }
 
 int nb2_context_device(const nb2_context* c) { return c ? c->device : -1; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host -> device staging.  A pageable source (pcl::PCLPointCloud2::data is a std::vector) reaches the GPU at a fraction
+// of the PCIe rate through cudaMemcpy's own bounce buffer, and what the plan needs of a PointNormal cloud is 24 of its 48
+// bytes per vertex.  So host input is produced in pieces by the host cores — copied, compacted to {x y z [nx ny nz]}
+// records, or generated by the caller (nb2_mesh_upload_stream: the plugin flattens one pcl::Vertices per face and
+// fingerprints the content in the same pass) — straight into a ring of pinned slots, and every slot goes out with its own
+// cudaMemcpyAsync while the cores fill the next ones.  One cudaMemcpyAsync per slot, all on the context's stream.
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct SourceError
+{
+  int code;
+};
+constexpr uint64_t kGrain = NB2_UPLOAD_GRAIN;
+constexpr size_t kSlotBytes = size_t(3) << 20;
+constexpr unsigned kSlots = 32;
+
+struct StageSource
+{
+  uint32_t step = 0;  // bytes per staged cloud record
+  std::function<int(uint64_t first, uint64_t count, void* dst)> cloud;
+  std::function<int(uint64_t first, uint64_t count, uint32_t* dst)> tri;
+};
+
+unsigned stagingWorkers()
+{
+  static const unsigned n = [] {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("NB2_STAGING_THREADS"))
+      hw = static_cast<unsigned>(std::max(1, std::atoi(e)));
+    return std::min(std::max(hw, 1u), kSlots - 4u);
+  }();
+  return n;
+}
+
+/** V records of S.step bytes to `d_cloud`, F triangles to `d_tri`, through the pinned ring; the copies are enqueued on
+ *  c->stream (not waited for).  Throws when a source reports an error. */
+void stageToDevice(nb2_context* c, const StageSource& S, uint64_t V, uint64_t F, void* d_cloud, void* d_tri)
+{
+  const uint64_t pts_per = std::max<uint64_t>(kGrain, (kSlotBytes / S.step) / kGrain * kGrain);
+  const uint64_t tri_per = (kSlotBytes / 12) / kGrain * kGrain;
+  const size_t slot_bytes = std::max<size_t>(pts_per * S.step, tri_per * 12);
+  c->stageRing.ensure(slot_bytes * kSlots);
+  if (c->stageEvents.empty())
+  {
+    c->stageEvents.resize(kSlots);
+    for (auto& e : c->stageEvents)
+      NB2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const uint64_t n_cloud = (V + pts_per - 1) / pts_per, n_tri = (F + tri_per - 1) / tri_per, n_items = n_cloud + n_tri;
+  std::vector<std::atomic<int>> enqueued(n_items);
+  for (auto& a : enqueued)
+    a.store(0, std::memory_order_relaxed);
+  std::atomic<uint64_t> next{ 0 };
+  std::atomic<int> error{ 0 };
+  std::atomic<int> cuda_error{ 0 };
+  uint8_t* const ring = c->stageRing.as<uint8_t>();
+  auto work = [&]() {
+    if (cudaSetDevice(c->device) != cudaSuccess)
+    {
+      cuda_error.store(1);
+      return;
+    }
+    for (;;)
+    {
+      const uint64_t i = next.fetch_add(1);
+      if (i >= n_items)
+        return;
+      const unsigned slot = static_cast<unsigned>(i % kSlots);
+      bool bad = error.load() || cuda_error.load();
+      if (!bad && i >= kSlots)
+      {
+        // the slot's previous tenant must have left for the device
+        while (!enqueued[i - kSlots].load(std::memory_order_acquire))
+          std::this_thread::yield();
+        if (enqueued[i - kSlots].load() == 1 && cudaEventSynchronize(c->stageEvents[slot]) != cudaSuccess)
+          cuda_error.store(1), bad = true;
+      }
+      int state = 2;  // 2 = nothing enqueued for this item
+      if (!bad)
+      {
+        uint8_t* dst = ring + slot * slot_bytes;
+        int rc;
+        void* d;
+        size_t bytes;
+        if (i < n_cloud)
+        {
+          const uint64_t first = i * pts_per, count = std::min(pts_per, V - first);
+          rc = S.cloud(first, count, dst);
+          d = static_cast<uint8_t*>(d_cloud) + first * S.step;
+          bytes = count * S.step;
+        }
+        else
+        {
+          const uint64_t first = (i - n_cloud) * tri_per, count = std::min(tri_per, F - first);
+          rc = S.tri(first, count, reinterpret_cast<uint32_t*>(dst));
+          d = static_cast<uint8_t*>(d_tri) + first * 12;
+          bytes = count * 12;
+        }
+        if (rc != 0)
+        {
+          int expected = 0;
+          error.compare_exchange_strong(expected, rc);
+        }
+        else if (cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                 cudaEventRecord(c->stageEvents[slot], c->stream) != cudaSuccess)
+          cuda_error.store(1);
+        else
+          state = 1;
+      }
+      enqueued[i].store(state, std::memory_order_release);
+    }
+  };
+  const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(stagingWorkers(), n_items));
+  std::vector<std::thread> pool;
+  for (unsigned w = 1; w < workers; ++w)
+    pool.emplace_back(work);
+  work();
+  for (auto& t : pool)
+    t.join();
+  if (cuda_error.load())
+  {
+    cudaStreamSynchronize(c->stream);
+    fail(NB2_ERR_CUDA, std::string("staged upload: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  if (error.load())
+  {
+    cudaStreamSynchronize(c->stream);
+    throw SourceError{ error.load() };
+  }
+}
+
+bool pinnedHost(const void* p)
+{
+  cudaPointerAttributes a{};
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess)
+  {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+}  // namespace
+
+static void readUploadVerdicts(nb2_context* c);
 
 static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
 {
@@ -785,52 +939,96 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
     return a.type == cudaMemoryTypeDevice && a.device == c->device;
   };
   c->pos.ensure(sizeof(float4) * V);
-  if (onThisDevice(m->cloud_data))
+  const bool cloud_on_device = onThisDevice(m->cloud_data), tri_on_device = F && onThisDevice(m->triangles);
+  // layout of the records as they will lie in HBM
+  uint32_t step = m->point_step, off_xyz = m->offset_xyz;
+  int32_t off_nrm = m->offset_normal;
+  const bool compact = (m->flags & NB2_MESH_GEOMETRY_ONLY) && !cloud_on_device && !sharded &&
+                       m->point_step > (m->offset_normal >= 0 ? 24u : 12u);
+  if (compact)
+  {
+    step = m->offset_normal >= 0 ? 24u : 12u;
+    off_xyz = 0;
+    off_nrm = m->offset_normal >= 0 ? 12 : -1;
+  }
+  // Host sources worth the staging threads: pageable memory (any size beyond a few slots) and clouds to be compacted;
+  // pinned memory otherwise goes out in one piece per array, straight from where it lies
+  const size_t cloud_bytes = V * m->point_step, tri_bytes = sizeof(uint32_t) * 3 * F;
+  const bool stage_cloud = !cloud_on_device && !sharded && (compact || (cloud_bytes >= 4 * kSlotBytes && !pinnedHost(m->cloud_data)));
+  const bool stage_tri = F && !tri_on_device && !sharded && tri_bytes >= 4 * kSlotBytes && !pinnedHost(m->triangles);
+  if (cloud_on_device)
     c->blob.adopt(const_cast<void*>(m->cloud_data));
+  else if (sharded)
+  {
+    // every rank copies 1 / world of the bytes over its own PCIe link; NVLink does the rest (comm.cpp)
+    c->blob.ensure(shardedCapacity(c, cloud_bytes));
+    shardedHostToDevice(c, c->blob.ptr, m->cloud_data, cloud_bytes);
+  }
   else
   {
-    const size_t bytes = V * m->point_step;
-    if (sharded)
-    {
-      // every rank copies 1 / world of the bytes over its own PCIe link; NVLink does the rest (comm.cpp)
-      c->blob.ensure(shardedCapacity(c, bytes));
-      shardedHostToDevice(c, c->blob.ptr, m->cloud_data, bytes);
-    }
-    else
-    {
-      c->blob.ensure(bytes);
-      NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, bytes, cudaMemcpyHostToDevice, c->stream));
-    }
+    c->blob.ensure(V * step);
+    if (!stage_cloud)
+      NB2_CUDA(cudaMemcpyAsync(c->blob.ptr, m->cloud_data, cloud_bytes, cudaMemcpyHostToDevice, c->stream));
   }
   bool tri_adopted = false;
-  if (F && onThisDevice(m->triangles))
+  if (tri_on_device)
   {
     c->tri.adopt(const_cast<uint32_t*>(m->triangles));
     tri_adopted = true;
   }
+  else if (sharded && F)
+  {
+    c->tri.ensure(shardedCapacity(c, tri_bytes));
+    shardedHostToDevice(c, c->tri.ptr, m->triangles, tri_bytes);
+  }
   else
   {
-    const size_t bytes = sizeof(uint32_t) * 3 * F;
-    if (sharded && F)
-    {
-      c->tri.ensure(shardedCapacity(c, bytes));
-      shardedHostToDevice(c, c->tri.ptr, m->triangles, bytes);
-    }
+    c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+    if (F && !stage_tri)
+      NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, tri_bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  if (stage_cloud || stage_tri)
+  {
+    StageSource S;
+    S.step = step;
+    const uint8_t* src = static_cast<const uint8_t*>(m->cloud_data);
+    const uint32_t in_step = m->point_step, in_xyz = m->offset_xyz;
+    const int32_t in_nrm = m->offset_normal;
+    if (compact)
+      S.cloud = [=](uint64_t first, uint64_t count, void* dst) {
+        uint8_t* o = static_cast<uint8_t*>(dst);
+        const uint8_t* p = src + first * in_step;
+        if (in_nrm >= 0)
+          for (uint64_t i = 0; i < count; ++i, p += in_step, o += 24)
+          {
+            std::memcpy(o, p + in_xyz, 12);
+            std::memcpy(o + 12, p + in_nrm, 12);
+          }
+        else
+          for (uint64_t i = 0; i < count; ++i, p += in_step, o += 12)
+            std::memcpy(o, p + in_xyz, 12);
+        return 0;
+      };
     else
-    {
-      c->tri.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
-      if (F)
-        NB2_CUDA(cudaMemcpyAsync(c->tri.ptr, m->triangles, bytes, cudaMemcpyHostToDevice, c->stream));
-    }
+      S.cloud = [=](uint64_t first, uint64_t count, void* dst) {
+        std::memcpy(dst, src + first * in_step, count * in_step);
+        return 0;
+      };
+    const uint32_t* tsrc = m->triangles;
+    S.tri = [=](uint64_t first, uint64_t count, uint32_t* dst) {
+      std::memcpy(dst, tsrc + 3 * first, 12 * count);
+      return 0;
+    };
+    stageToDevice(c, S, stage_cloud ? V : 0, stage_tri ? F : 0, c->blob.ptr, c->tri.ptr);
   }
   c->timer_upload.mark("h2d", c->stream);
   c->V = V;
   c->F = F;
-  c->has_normals = m->offset_normal >= 0;
+  c->has_normals = off_nrm >= 0;
   // normals are read in place, out of the cloud (SoA copies exist only for normals computed or set afterwards)
-  c->nrm_base = c->has_normals ? c->blob.as<uint8_t>() + m->offset_normal : nullptr;
-  c->nrm_stride = m->point_step;
-  launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
+  c->nrm_base = c->has_normals ? c->blob.as<uint8_t>() + off_nrm : nullptr;
+  c->nrm_stride = step;
+  launchIngestMoments(c, step, off_xyz, off_nrm);
   c->timer_upload.mark("ingest+moments", c->stream);
   // Triangles copied from the host are range-checked now (noise next to the PCIe copy).  Triangles adopted in place
   // from device memory are checked by the first kernel that streams them anyway (k_count_hits / the normals pass).
@@ -845,7 +1043,7 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
   c->extents_done = false;
   c->pca_valid = false;
   std::memset(&c->pca, 0, sizeof(c->pca));
-  if (tri_adopted || onThisDevice(m->cloud_data))
+  if (tri_adopted || cloud_on_device)
   {
     // device-resident input: nothing is read back here; non-finite coordinates and out-of-range indices are reported
     // by the next call that synchronises (nb2_plan, nb2_mesh_pca, nb2_normals_from_mesh_faces, ...)
@@ -853,6 +1051,13 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
     c->tri_checked = false;
     return;
   }
+  readUploadVerdicts(c);
+}
+
+/** end of a host upload: wait for the ingest pass and the index check, report what they found */
+static void readUploadVerdicts(nb2_context* c)
+{
+  const uint64_t V = c->V, F = c->F;
   c->checks_deferred = false;
   c->hostSmall.ensure(4096 + sizeof(FrameDev));
   auto* h = c->hostSmall.as<uint8_t>();
@@ -876,6 +1081,75 @@ static void uploadImpl(nb2_context* c, const nb2_mesh_view* m, bool sharded)
                                        std::to_string(V) + " points");
   }
   c->tri_checked = true;
+}
+
+/** nb2_mesh_upload_stream: the caller's callbacks fill the pinned slots; the staged mesh lands in the context's spare
+ *  pair of buffers and replaces the resident one only if `accept` says so */
+static void uploadStreamImpl(nb2_context* c, const nb2_mesh_stream* m, int* committed)
+{
+  if (!c || !m)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context or mesh is NULL");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  if (committed)
+    *committed = 0;
+  if (m->n_points == 0)
+    fail(NB2_ERR_TOO_FEW_POINTS, "mesh has no vertices");
+  if (!m->cloud || (m->n_triangles && !m->triangles))
+    fail(NB2_ERR_INVALID_ARGUMENT, "mesh source callback is NULL");
+  if (m->point_step == 0 || m->point_step % 4 || m->offset_xyz % 4 || m->offset_xyz + 12 > m->point_step)
+    fail(NB2_ERR_INVALID_ARGUMENT, "XYZ fields are not contiguous floats");
+  if (m->offset_normal >= 0 && (m->offset_normal % 4 || static_cast<uint32_t>(m->offset_normal) + 12 > m->point_step))
+    fail(NB2_ERR_INVALID_ARGUMENT, "Normal fields are not contiguous floats");
+  if (m->n_points >= (1ull << 31) || m->n_triangles >= (1ull << 31))
+    fail(NB2_ERR_INVALID_ARGUMENT, "meshes with 2^31 or more vertices / triangles are not supported");
+  const uint64_t V = m->n_points, F = m->n_triangles;
+  c->timer_upload.begin(c->stream);
+  c->blobSpare.ensure(V * m->point_step);
+  c->triSpare.ensure(sizeof(uint32_t) * 3 * std::max<uint64_t>(F, 1));
+  StageSource S;
+  S.step = m->point_step;
+  void* const user = m->user;
+  const auto cloud_fn = m->cloud;
+  const auto tri_fn = m->triangles;
+  S.cloud = [=](uint64_t first, uint64_t count, void* dst) { return cloud_fn(user, first, count, dst); };
+  S.tri = [=](uint64_t first, uint64_t count, uint32_t* dst) { return tri_fn(user, first, count, dst); };
+  try
+  {
+    stageToDevice(c, S, V, F, c->blobSpare.ptr, c->triSpare.ptr);
+  }
+  catch (const SourceError& e)
+  {
+    fail(NB2_ERR_INVALID_ARGUMENT, "mesh source callback reported error " + std::to_string(e.code));
+  }
+  if (m->accept && !m->accept(user))
+  {
+    // same content as the resident mesh: the resident mesh and everything derived from it stay
+    c->timer_upload.mark("h2d", c->stream);
+    return;
+  }
+  std::swap(c->blob, c->blobSpare);
+  std::swap(c->tri, c->triSpare);
+  c->V = 0;
+  c->pos.ensure(sizeof(float4) * V);
+  c->timer_upload.mark("h2d", c->stream);
+  c->V = V;
+  c->F = F;
+  c->has_normals = m->offset_normal >= 0;
+  c->nrm_base = c->has_normals ? c->blob.as<uint8_t>() + m->offset_normal : nullptr;
+  c->nrm_stride = m->point_step;
+  launchIngestMoments(c, m->point_step, m->offset_xyz, m->offset_normal);
+  c->timer_upload.mark("ingest+moments", c->stream);
+  c->tri_checked = false;
+  NB2_CUDA(cudaMemsetAsync(c->counters.as<unsigned>() + 12, 0, sizeof(unsigned), c->stream));
+  launchValidateTriangles(c);
+  c->timer_upload.mark("validate", c->stream);
+  c->extents_done = false;
+  c->pca_valid = false;
+  std::memset(&c->pca, 0, sizeof(c->pca));
+  readUploadVerdicts(c);
+  if (committed)
+    *committed = 1;
 }
 
 /** nb2_mesh_upload_ply: header on the host, records on the device (ply.cpp, kernels_ply.cu) */
@@ -1337,6 +1611,13 @@ int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
 {
   NB2_API_BEGIN
   uploadImpl(c, m, false);
+  NB2_API_END
+}
+
+int nb2_mesh_upload_stream(nb2_context* c, const nb2_mesh_stream* m, int* committed)
+{
+  NB2_API_BEGIN
+  uploadStreamImpl(c, m, committed);
   NB2_API_END
 }
 

@@ -189,6 +189,9 @@ struct nb2_context
   bool has_normals = false;
   bool tri_checked = false;  // vertex indices of the resident triangles are known to be < V
   nb2::DevBuf blob;      // staging copy of the interleaved cloud
+  nb2::DevBuf blobSpare, triSpare;  // nb2_mesh_upload_stream stages into these; they are swapped in when the mesh is accepted
+  nb2::PinnedBuf stageRing;         // pinned slots the host cores fill on the way to the device (api.cu, stageToDevice)
+  std::vector<cudaEvent_t> stageEvents;  // one per slot: its last copy has left
   nb2::DevBuf pos;       // float4[V]  (x, y, z, unused)
   nb2::DevBuf nrm;       // float4[V], only once normals were computed here or set by the caller
   // Where the slicer reads vertex normals: the uploaded cloud itself (normal_x of vertex v at nrm_base + v * nrm_stride;

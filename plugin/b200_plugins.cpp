@@ -161,6 +161,7 @@ private:
 // 64-bit content hash: fixed-size chunks hashed independently (so the work spreads over the cores whatever their
 // number) and folded in chunk order.  Not cryptographic; it only has to tell apart the meshes of one pipeline run.
 constexpr std::size_t kHashChunk = 65536;
+static_assert(kHashChunk == NB2_UPLOAD_GRAIN, "the streamed upload hands out ranges that begin on a fingerprint chunk");
 inline std::uint64_t mix(std::uint64_t h, std::uint64_t w)
 {
   h = (h ^ w) * 0x9E3779B97F4A7C15ull;
@@ -314,26 +315,170 @@ MeshView makeView(Device& dev, const pcl::PolygonMesh& mesh)
   return m;
 }
 
-/** Make `mesh` the context's resident mesh: nothing to do when it already is (same vertices, same triangles and, where
- *  the caller needs them, the same normals), an upload otherwise.  Call with the device mutex held. */
+/** The mesh handed to the device piece by piece (nb2_mesh_upload_stream): the library's staging threads call these on
+ *  disjoint ranges; each call compacts / flattens its range straight into pinned memory and fingerprints it on the way, so
+ *  the host data is read once in all. */
+struct StreamJob
+{
+  const pcl::PolygonMesh* mesh = nullptr;
+  std::size_t in_step = 0, off_xyz = 0;
+  long off_nrm = -1;
+  std::vector<std::uint64_t> hx, hn, ht;  // per kHashChunk
+  std::atomic<int> bad{ 0 };              // 1: fewer than 3 vertices, 2: not a triangle
+  Device* dev = nullptr;
+  bool need_normals = false;
+  Device::Resident content;
+  bool hit = false;
+
+  static int cloud(void* user, std::uint64_t first, std::uint64_t count, void* dst)
+  {
+    StreamJob& j = *static_cast<StreamJob*>(user);
+    constexpr std::uint64_t kSeedXyz = 0x78797a21ull, kSeedNrm = 0x6e726d21ull;
+    const std::uint8_t* p = j.mesh->cloud.data.data() + first * j.in_step;
+    std::uint8_t* o = static_cast<std::uint8_t*>(dst);
+    const bool nrm = j.off_nrm >= 0;
+    for (std::uint64_t b = first; b < first + count; b += kHashChunk)
+    {
+      const std::uint64_t c = b / kHashChunk, e = std::min(first + count, b + kHashChunk);
+      std::uint64_t hx = kSeedXyz + c, hn = kSeedNrm + c;
+      for (std::uint64_t i = b; i < e; ++i, p += j.in_step)
+      {
+        std::uint32_t w[3];
+        std::memcpy(w, p + j.off_xyz, 12);
+        std::memcpy(o, w, 12);
+        o += 12;
+        hx = mix(hx, (static_cast<std::uint64_t>(w[0]) << 32) | w[1]);
+        hx = mix(hx, w[2]);
+        if (nrm)
+        {
+          std::memcpy(w, p + j.off_nrm, 12);
+          std::memcpy(o, w, 12);
+          o += 12;
+          hn = mix(hn, (static_cast<std::uint64_t>(w[0]) << 32) | w[1]);
+          hn = mix(hn, w[2]);
+        }
+      }
+      j.hx[c] = hx;
+      if (nrm)
+        j.hn[c] = hn;
+    }
+    return 0;
+  }
+  static int triangles(void* user, std::uint64_t first, std::uint64_t count, std::uint32_t* dst)
+  {
+    StreamJob& j = *static_cast<StreamJob*>(user);
+    const auto& polygons = j.mesh->polygons;
+    for (std::uint64_t b = first; b < first + count; b += kHashChunk)
+    {
+      const std::uint64_t c = b / kHashChunk, e = std::min(first + count, b + kHashChunk);
+      std::uint64_t h = 0x7472697321ull + c;
+      for (std::uint64_t f = b; f < e; ++f, dst += 3)
+      {
+        const auto& v = polygons[f].vertices;
+        if (v.size() != 3)
+        {
+          j.bad.store(v.size() < 3 ? 1 : 2);
+          return 1;
+        }
+        const std::uint32_t i0 = static_cast<std::uint32_t>(v[0]), i1 = static_cast<std::uint32_t>(v[1]),
+                            i2 = static_cast<std::uint32_t>(v[2]);
+        dst[0] = i0, dst[1] = i1, dst[2] = i2;
+        h = mix(h, (static_cast<std::uint64_t>(i0) << 32) | i1);
+        h = mix(h, i2);
+      }
+      j.ht[c] = h;
+    }
+    return 0;
+  }
+  /** everything is staged: is it what the device already holds? */
+  static int accept(void* user)
+  {
+    StreamJob& j = *static_cast<StreamJob*>(user);
+    j.content.h_xyz = fold(j.hx, 0x78797a21ull);
+    j.content.h_normals = j.off_nrm >= 0 ? fold(j.hn, 0x6e726d21ull) : 0;
+    j.content.h_tri = fold(j.ht, 0x7472697321ull);
+    const Device::Resident& r = j.dev->resident;
+    const Device::Resident& m = j.content;
+    const bool same_geometry = r.valid && r.n_points == m.n_points && r.n_triangles == m.n_triangles && r.h_xyz == m.h_xyz &&
+                               r.h_tri == m.h_tri;
+    const bool same_normals = r.has_normals == m.has_normals && (!r.has_normals || r.h_normals == m.h_normals);
+    j.hit = same_geometry && (same_normals || !j.need_normals);
+    return j.hit ? 0 : 1;
+  }
+};
+
+/** Make `mesh` the context's resident mesh.  The mesh is streamed to the device while it is fingerprinted (one pass over
+ *  the host data); when the fingerprint says the device already holds these vertices, triangles and, where the caller
+ *  needs them, normals, the staged copy is dropped and the resident mesh stays, with everything derived from it (PCA,
+ *  extents, computed normals).  Call with the device mutex held. */
 void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals, bool whole_records = false)
 {
   Trace trace("ensureResident");
-  const MeshView m = makeView(dev, mesh);
-  trace.lap("flatten + fingerprint");
-  const Device::Resident& r = dev.resident;
-  const bool same_geometry = r.valid && r.n_points == m.content.n_points && r.n_triangles == m.content.n_triangles &&
-                             r.h_xyz == m.content.h_xyz && r.h_tri == m.content.h_tri;
-  const bool same_normals = r.has_normals == m.content.has_normals && (!r.has_normals || r.h_normals == m.content.h_normals);
-  // `whole_records`: the caller works on every byte of the cloud records (face subdivision copies them), and the
-  // fingerprints above cover positions, normals and indices only — the same geometry in another record layout, or with
-  // other colours / curvature, would pass them.  Such callers always upload.
-  if (!whole_records && same_geometry && (same_normals || !need_normals))
+  if (whole_records)
+  {
+    // the caller works on every byte of the cloud records (face subdivision copies them), and the fingerprints cover
+    // positions, normals and indices only — the same geometry in another record layout, or with other colours /
+    // curvature, would pass them.  Such callers always upload, records as they are.
+    const MeshView m = makeView(dev, mesh);
+    trace.lap("flatten + fingerprint");
+    dev.resident.valid = false;
+    Device::check(nb2_mesh_upload(dev.ctx(), &m.view));
+    dev.resident = m.content;
+    trace.lap("upload");
     return;
+  }
+  const pcl::PCLPointCloud2& cloud = mesh.cloud;
+  const auto& x = findFieldOrThrow(cloud, "x");
+  const auto& y = findFieldOrThrow(cloud, "y");
+  const auto& z = findFieldOrThrow(cloud, "z");
+  if ((y.offset - x.offset != 4) || (z.offset - y.offset != 4) || x.datatype != pcl::PCLPointField::FLOAT32)
+    throw std::runtime_error("XYZ fields are not contiguous floats");  // utils.cpp:82-83
+  StreamJob job;
+  job.mesh = &mesh;
+  job.dev = &dev;
+  job.need_normals = need_normals;
+  job.in_step = cloud.point_step;
+  job.off_xyz = x.offset;
+  if (hasNormals(cloud))
+  {
+    const auto& nx = findFieldOrThrow(cloud, "normal_x");
+    const auto& ny = findFieldOrThrow(cloud, "normal_y");
+    const auto& nz = findFieldOrThrow(cloud, "normal_z");
+    if ((ny.offset - nx.offset != 4) || (nz.offset - ny.offset != 4) || nx.datatype != pcl::PCLPointField::FLOAT32)
+      throw std::runtime_error("Normal fields are not contiguous floats");  // utils.cpp:104-105
+    job.off_nrm = static_cast<long>(nx.offset);
+  }
+  const std::uint64_t V = static_cast<std::uint64_t>(cloud.width) * cloud.height, F = mesh.polygons.size();  // utils.cpp:169
+  if (cloud.data.size() < V * cloud.point_step)
+    throw std::runtime_error("point cloud data is shorter than width * height * point_step");
+  job.hx.assign((V + kHashChunk - 1) / kHashChunk, 0);
+  job.hn.assign(job.off_nrm >= 0 ? job.hx.size() : 0, 0);
+  job.ht.assign((F + kHashChunk - 1) / kHashChunk, 0);
+  job.content.valid = true;
+  job.content.n_points = V;
+  job.content.n_triangles = F;
+  job.content.has_normals = job.off_nrm >= 0;
+  nb2_mesh_stream st{};
+  st.n_points = V;
+  st.point_step = job.off_nrm >= 0 ? 24u : 12u;  // what travels: {x y z [nx ny nz]}
+  st.offset_xyz = 0;
+  st.offset_normal = job.off_nrm >= 0 ? 12 : -1;
+  st.n_triangles = F;
+  st.cloud = &StreamJob::cloud;
+  st.triangles = &StreamJob::triangles;
+  st.accept = &StreamJob::accept;
+  st.user = &job;
+  int committed = 0;
+  const Device::Resident before = dev.resident;
   dev.resident.valid = false;
-  Device::check(nb2_mesh_upload(dev.ctx(), &m.view));
-  dev.resident = m.content;
-  trace.lap("upload");
+  const int rc = nb2_mesh_upload_stream(dev.ctx(), &st, &committed);
+  if (job.bad.load() == 1)
+    throw std::runtime_error("Polygon has fewer than 3 vertices");  // getFaceNormal, utils.cpp:137-142
+  if (job.bad.load() == 2)
+    throw std::runtime_error("noether_b200 slices triangle meshes only; triangulate the mesh first");
+  Device::check(rc);
+  dev.resident = committed ? job.content : before;
+  trace.lap(committed ? "streamed to the device" : "streamed, already resident");
 }
 
 /** SoA result -> noether::ToolPaths (core/types.h:31-50): nested vectors of Eigen::Isometry3d */

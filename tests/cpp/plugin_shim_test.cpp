@@ -622,6 +622,69 @@ void timePipeline(const noether::Factory& factory, unsigned nx, unsigned ny, dou
   }
 }
 
+/** bench.py's end-to-end leg (`e2e`): K plans through the reference-facing call — Factory::createToolPathPlanner("PlaneSlicer")
+ *  ->plan(pcl::PolygonMesh) -> nested noether::ToolPaths (core/types.h:31-50) — on host meshes the device has not seen:
+ *  two copies of the workload that differ in one coordinate alternate, so every plan flattens, fingerprints and uploads its
+ *  mesh, plans, downloads and fills the Isometry3d vectors.  Wall clock per plan; one JSON line on stdout. */
+int benchPlanner(const noether::Factory& factory, unsigned nx, unsigned ny, double spacing, int steps, int warmup)
+{
+  const pcl::PolygonMesh raw = wavyMesh(nx, ny);
+  YAML::Node mod;
+  mod["name"] = "NormalsFromMeshFaces";
+  YAML::Node dg, og, pc;
+  dg["name"] = "PrincipalAxis";
+  dg["rotation_offset"] = 0.0;
+  og["name"] = "Centroid";
+  pc["name"] = "PlaneSlicer";
+  pc["line_spacing"] = spacing;
+  pc["bidirectional"] = true;
+  pc["direction_generator"] = dg;
+  pc["origin_generator"] = og;
+  auto modifier = factory.createMeshModifier(mod);
+  auto planner = factory.createToolPathPlanner(pc);
+  std::vector<pcl::PolygonMesh> mesh(2);
+  mesh[0] = modifier->modify(raw).front();
+  mesh[1] = mesh[0];
+  {
+    // the partner: the first vertex moved by one ulp along z (same counts, another content fingerprint)
+    float z;
+    std::uint8_t* p = mesh[1].cloud.data.data() + 8;
+    std::memcpy(&z, p, 4);
+    z = std::nextafter(z, 1.0f);
+    std::memcpy(p, &z, 4);
+  }
+  std::vector<double> ms;
+  std::size_t wp = 0, paths = 0, segs = 0;
+  for (int i = 0; i < warmup + steps; ++i)
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    {
+      const noether::ToolPaths tp = planner->plan(mesh[i & 1]);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (i >= warmup)
+        ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+      paths = tp.size();
+      wp = segs = 0;
+      for (const auto& path : tp)
+      {
+        segs += path.size();
+        for (const auto& seg : path)
+          wp += seg.size();
+      }
+    }  // (the tool paths are released outside the timed interval, as a caller that keeps them would)
+  }
+  double sum = 0, best = 1e300;
+  for (double v : ms)
+    sum += v, best = std::min(best, v);
+  const std::size_t V = static_cast<std::size_t>(mesh[0].cloud.width) * mesh[0].cloud.height, F = mesh[0].polygons.size();
+  std::printf("{\"plugin_e2e\": true, \"triangles\": %zu, \"vertices\": %zu, \"point_step\": %u, \"steps\": %d, \"warmup\": %d, "
+              "\"ms_per_plan\": %.4f, \"ms_best\": %.4f, \"tool_paths\": %zu, \"segments\": %zu, \"waypoints\": %zu, "
+              "\"host_in_bytes\": %zu, \"host_out_bytes\": %zu}\n",
+              F, V, mesh[0].cloud.point_step, steps, warmup, sum / std::max<std::size_t>(1, ms.size()), best, paths, segs, wp,
+              V * mesh[0].cloud.point_step + 12 * F, wp * sizeof(Eigen::Isometry3d));
+  return wp > 0 ? 0 : 1;
+}
+
 // ---- ToolPathModifierTestFixture / OneTimeToolPathModifierTestFixture (tool_path_modifier_utest.cpp:14-96,120-214,261-304)
 //      for the modifiers this library runs on the device, created by alias from the reference's test YAML
 noether::ToolPaths gridToolPaths(unsigned p, unsigned s, unsigned w, bool identity)
@@ -1032,6 +1095,9 @@ int main(int argc, char** argv)
     for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
                                 "FaceMidpointSubdivision", "FaceSubdivisionByArea", "EuclideanClustering" })
       CHECK(dlsym(lib, alias) != nullptr);
+    if (argc > 8 && std::string(argv[3]) == "--bench")  // --bench nx ny spacing steps warmup
+      return benchPlanner(factory, static_cast<unsigned>(std::atoi(argv[4])), static_cast<unsigned>(std::atoi(argv[5])),
+                          std::atof(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]));
     const pcl::PolygonMesh ply = loadPly(argv[2]);
     CHECK(ply.cloud.width == 757 && ply.polygons.size() == 1347);
     if (argc > 3 && std::string(argv[3]) == "--cpu-only")

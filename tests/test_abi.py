@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(capi):
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     assert set(declared) <= exported
-    assert L.nb2_abi_version() == 2
+    assert L.nb2_abi_version() == 3
 
 
 def test_header_is_plain_c(tmp_path):
