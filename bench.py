@@ -172,13 +172,103 @@ def algorithmic_bytes(stage: str, V: int, F: int, H: int, W: int, S: int, P: int
     return table.get(stage)
 
 
+def side_workload(args, info, emit):
+    """BASELINE.json configs[3] and [4] behind the same command line: cfg4 = NormalsFromMeshFaces + PCA frame on the 50 M-triangle
+    mesh with scanner-like (permuted) vertex / face order, device-resident; cfg5 = the batch of 64 part meshes, whole meshes
+    per GPU (LPT on triangle counts), end to end from pinned host memory.  One JSON line with the contract's keys."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    peak, peak_src = measured_peaks()
+    if args.workload == "cfg4":
+        if info.rank != 0:
+            return
+        if args.impl == "reference":
+            import oracle as orc
+            from noether_b200 import meshes
+            orc.build()
+            # bounded sample: the same generator at 1/10 of the triangles (5 M), permuted; the passes are linear in the mesh size
+            xyz, tri = meshes.permute(*meshes.wavy(1976, 1265), seed=42)
+            t0 = time.perf_counter()
+            for _ in range(max(1, args.steps)):
+                orc.normals_from_mesh_faces(xyz, tri)
+                orc.pca(xyz, orc.MOMENTS_F32_SEQUENTIAL)
+            dt = (time.perf_counter() - t0) / max(1, args.steps)
+            value = tri.shape[0] / dt
+            emit({"impl": "reference", "metric": "triangles/s (NormalsFromMeshFaces + PCA frame)", "value": value, "unit": "triangles/s",
+                  "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt * 50e6 / tri.shape[0],
+                  "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                  "config": {"workload": "cfg4: wavy(6250,4000) 50M tris / 25M verts, permuted vertex and face order"},
+                  "cpu_baseline": {"value": value, "unit": "triangles/s", "cores": 1, "kind": "port",
+                                   "sample": f"the same generator at {tri.shape[0]} triangles (1/10), permuted; single-thread oracle, "
+                                             "rate carried over (the passes are linear in the mesh size)"},
+                  "e2e": {"value": value, "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+            return
+        import profile_normals
+        sampler = ClockSampler("0")
+        sampler.start()
+        r = profile_normals.measure("cfg4", iters=max(args.steps, 3) + 1)
+        clocks = sampler.stop()
+        ms = r["normals_ms_mean"] + r["pca_frame_ms_mean"]
+        B = 12 * r["F"] + 24 * r["V"]
+        emit({"metric": "triangles/s (NormalsFromMeshFaces + PCA frame)", "value": r["F"] / (ms / 1e3), "unit": "triangles/s",
+              "n_gpus": 1, "steps": max(args.steps, 3), "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": "cfg4: wavy(6250,4000) 50M tris / 25M verts, permuted vertex and face order (scan-like), "
+                                     "NormalsFromMeshFaces then the PrincipalAxis PCA frame, mesh resident in HBM",
+                         "l2": "inputs are 900 MB, larger than L2", "timing": "CUDA events on the library stream"},
+              "clocks": clocks, "e2e": None, "gpu_launches": int(r["launches_per_iteration"]),
+              "roofline": {"bound": "hbm", "kernel": "NormalsFromMeshFaces (4 kernels)", "achieved": B / r["normals_ms_mean"] / 1e6,
+                           "peak": peak, "unit": "GB/s", "frac": B / r["normals_ms_mean"] / 1e6 / peak, "traffic": None,
+                           "algorithmic_bytes_per_launch": B, "launch_ms": r["normals_ms_mean"], "peak_source": peak_src,
+                           "stage_ms": r["stages_ms"], "pca_frame_ms": r["pca_frame_ms_mean"], "pca_frac": r["pca_frac_of_peak"]},
+              "cpu_baseline": None})
+        return
+    # cfg5
+    if args.impl == "reference":
+        if info.rank != 0:
+            return
+        import oracle as orc
+        from noether_b200 import meshes
+        orc.build()
+        xyz, tri, _ = meshes.cfg5_mesh(0)
+        nrm = orc.normals_from_mesh_faces(xyz, tri)
+        s = cpu_reference_sample(xyz, nrm, tri, 0.002, 24)
+        emit({"impl": "reference", "metric": "triangles sliced/sec (batch of 64 part meshes)", "value": s["tri_per_s"], "unit": "triangles/s",
+              "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * s["t_plan_extrapolated_s"] * 64,
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+              "config": {"workload": "cfg5: 64 part meshes (1.5 - 2.5 M triangles), 2 mm spacing"},
+              "cpu_baseline": {"value": s["tri_per_s"], "unit": "triangles/s", "cores": 1, "kind": "port",
+                               "sample": f"mesh 0 of the batch, prologue + {s['planes_sampled']} of {s['planes']} planes, extrapolated"},
+              "e2e": {"value": s["tri_per_s"], "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    import bench_batch
+    sampler = ClockSampler(",".join(str(i) for i in range(info.world)) if info.rank == 0 else None)
+    sampler.start()
+    r = bench_batch.main(["--meshes", "64", "--threads", "2", "--repeat", str(max(args.steps, 3)), "--quiet"])
+    clocks = sampler.stop()
+    if info.rank != 0 or r is None:
+        return
+    e2e = {"value": r["triangles"] / r["batch_s_mean"], "unit": "triangles/s", "ms_per_step": 1e3 * r["batch_s_mean"],
+           "h2d_bytes_per_step": r["h2d_bytes"] * info.world, "d2h_bytes_per_step": None,
+           "boundary": "C ABI from Python, pinned host meshes in, compact SoA tool paths out; two contexts per GPU overlap copies and kernels"}
+    emit({"metric": "triangles sliced/sec (batch of 64 part meshes)", "value": e2e["value"], "unit": "triangles/s", "n_gpus": info.world,
+          "steps": r["repeat"], "warmup": 1, "ms_per_step": e2e["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": r["workload"], "parallelism": f"whole meshes x{info.world} (LPT), no exchange between ranks",
+                     "timing": "wall clock around the batch, max over ranks (the step is end to end: every mesh is uploaded, planned, downloaded)",
+                     "l2": "every mesh is a different input (56 MB each), 3.6 GB per batch"},
+          "clocks": clocks, "e2e": e2e, "gpu_launches": r["rank0_kernel_launches"], "roofline": None, "cpu_baseline": None})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg4", "cfg5"],
+                    help="cfg3 (default) is the configuration BASELINE.json's metric is quoted on; cfg2, cfg4 (NormalsFromMeshFaces "
+                         "+ PCA on the 50 M-triangle permuted mesh) and cfg5 (batch of 64 part meshes, whole meshes per GPU) are the "
+                         "other BASELINE.json configs")
     ap.add_argument("--cpu-planes", type=int, default=160,
                     help="lattice planes sampled by the CPU baseline (cfg3: about 76 ms each => ~12 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -198,6 +288,9 @@ def main():
     if info.world != args.gpus and info.world > 1:
         print(f"warning: WORLD_SIZE={info.world} but --gpus {args.gpus}", file=sys.stderr)
 
+    if args.workload in ("cfg4", "cfg5"):
+        side_workload(args, info, emit)
+        return
     xyz, tri, spacing, desc = build_workload(args.workload)
     V, F = xyz.shape[0], tri.shape[0]
 
@@ -387,6 +480,23 @@ def main():
     if info.rank != 0:
         return
 
+    # ---- e2e through the reference-facing boundary (N = 1): the C++ plugin, created by alias through the factory, planning a
+    # host pcl::PolygonMesh into nested noether::ToolPaths (plugin/b200_plugins.cpp; driver: tests/cpp/plugin_shim_test.cpp
+    # --bench).  Its own process: this one's context is closed first so that the two do not share the device.
+    plugin_e2e = None
+    if info.world == 1 and args.workload in WORKLOADS and os.environ.get("NB2_BENCH_NO_PLUGIN") != "1":
+        nx, ny = WORKLOADS[args.workload][:2]
+        exe = os.path.join(ROOT, "plugin", "build", "plugin_shim_test")
+        lib = os.path.join(ROOT, "plugin", "build", "libnoether_b200_plugins.so")
+        try:
+            if not (os.path.exists(exe) and os.path.exists(lib)):
+                subprocess.run(["make", "-C", os.path.join(ROOT, "plugin")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            r = subprocess.run([exe, lib, "-", "--bench", str(nx), str(ny), repr(spacing), str(args.steps), str(max(args.warmup, 3))],
+                               capture_output=True, text=True, timeout=600)
+            plugin_e2e = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        except Exception as e:
+            plugin_e2e = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- roofline of the dominant kernel (live CUDA-event stage times averaged over the timed steps) -------------
     peak, peak_src = measured_peaks()
     lat = ctx.last_lattice()
@@ -425,7 +535,6 @@ def main():
     # cut into plane slabs over all host cores; its own process (it forks), whole plan, N = 1 only
     cpu_opt = None
     if cpu is not None and info.world == 1 and args.workload in ("cfg2", "cfg3"):
-        import subprocess
         try:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_optimised.py"), args.workload],
                                capture_output=True, text=True, timeout=180)
@@ -437,6 +546,31 @@ def main():
         except Exception as e:  # a reported baseline must not take the bench line down with it
             cpu_opt = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
+    # e2e_compact: the C ABI called from Python with pinned host arrays in, the compact 24-byte-per-waypoint SoA result in
+    # pinned host memory out.  e2e (the headline): at N = 1 the C++ plugin call a noether application makes — pageable
+    # pcl::PolygonMesh in (one std::vector per face), nested std::vector<Eigen::Isometry3d> out (128 bytes per waypoint),
+    # every plan on a mesh the device has not seen; at N > 1 the sharded C-ABI path (the plugin drives one GPU).
+    e2e_compact = {"value": F / (e2e_ms / 1e3), "unit": "triangles/s", "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
+                   "boundary": "C ABI (nb2_plan_mesh) from Python: pinned host cloud + triangles in, SoA positions / normals / segment lengths out"}
+    if plugin_e2e and "ms_per_plan" in plugin_e2e:
+        has_nrm = blob.off_normal >= 0
+        e2e = {"value": F / (plugin_e2e["ms_per_plan"] / 1e3), "unit": "triangles/s", "ms_per_step": plugin_e2e["ms_per_plan"],
+               "ms_best": plugin_e2e["ms_best"],
+               # what crosses PCIe: the cloud compacted to {xyz, normal} records by the staging threads, the triangles, and back
+               # the compact result; the host-side bytes the call consumes and produces are listed next to it
+               "h2d_bytes_per_step": int(V * (24 if has_nrm else 12) + 12 * F),
+               "d2h_bytes_per_step": int(plugin_e2e["waypoints"] * 24 + plugin_e2e["segments"] * 4),
+               "host_in_bytes_per_step": plugin_e2e["host_in_bytes"], "host_out_bytes_per_step": plugin_e2e["host_out_bytes"],
+               "waypoints": plugin_e2e["waypoints"], "tool_paths": plugin_e2e["tool_paths"],
+               "boundary": "C++ plugin: Factory::createToolPathPlanner('PlaneSlicer')->plan(pcl::PolygonMesh) -> noether::ToolPaths "
+                           "(nested Eigen::Isometry3d vectors); two meshes with different fingerprints alternate, so every plan "
+                           "flattens, fingerprints, uploads, plans, downloads and expands; wall clock"}
+    else:
+        e2e = dict(e2e_compact)
+        if plugin_e2e:
+            e2e["plugin_boundary"] = plugin_e2e
+
     line = {
         "metric": "triangles sliced/sec", "value": F / (ms_per_step / 1e3), "unit": "triangles/s",
         "n_gpus": info.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -447,8 +581,8 @@ def main():
                    "l2": "flushed between timed iterations (256 MB write outside the timed intervals); inputs are %d MB" % (h2d_bytes // 2**20),
                    "timing": "CUDA events on the library stream, max over ranks; wall clock %.3f ms/step" % (wall_ms / args.steps)},
         "clocks": clocks,
-        "e2e": {"value": F / (e2e_ms / 1e3), "unit": "triangles/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes)},
+        "e2e": e2e,
+        "e2e_compact": e2e_compact,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -21,6 +21,9 @@
 #include <limits>
 #include <numeric>
 #include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace nb2
 {
@@ -234,12 +237,31 @@ void expandPosesTo(const nb2_result& r, Dst dst)
           x = normalized(cross(y, zz));
         }
         double* T = out + 16ull * i;
+#if defined(__SSE2__)
+        // 128 bytes per waypoint that nobody reads back soon: streaming stores skip the read-for-ownership of every
+        // cache line (the expansion is bound by host memory traffic: 512 MB for cfg3's four million waypoints)
+        if ((reinterpret_cast<uintptr_t>(T) & 15u) == 0)
+        {
+          _mm_stream_pd(T + 0, _mm_set_pd(x.y, x.x));
+          _mm_stream_pd(T + 2, _mm_set_pd(0.0, x.z));
+          _mm_stream_pd(T + 4, _mm_set_pd(y.y, y.x));
+          _mm_stream_pd(T + 6, _mm_set_pd(0.0, y.z));
+          _mm_stream_pd(T + 8, _mm_set_pd(z.y, z.x));
+          _mm_stream_pd(T + 10, _mm_set_pd(0.0, z.z));
+          _mm_stream_pd(T + 12, _mm_set_pd(p.y, p.x));
+          _mm_stream_pd(T + 14, _mm_set_pd(1.0, p.z));
+          continue;
+        }
+#endif
         T[0] = x.x, T[1] = x.y, T[2] = x.z, T[3] = 0.0;
         T[4] = y.x, T[5] = y.y, T[6] = y.z, T[7] = 0.0;
         T[8] = z.x, T[9] = z.y, T[10] = z.z, T[11] = 0.0;
         T[12] = p.x, T[13] = p.y, T[14] = p.z, T[15] = 1.0;
       }
     }
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
   });
 }
 }  // namespace

@@ -23,12 +23,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None):
+    """returns the result dict on rank 0 (None elsewhere); bench.py --workload cfg5 wraps it into the bench line"""
     ap = argparse.ArgumentParser()
     ap.add_argument("--meshes", type=int, default=64)
     ap.add_argument("--threads", type=int, default=2)
     ap.add_argument("--repeat", type=int, default=3)
-    args = ap.parse_args()
+    ap.add_argument("--quiet", action="store_true")
+    args = ap.parse_args(argv)
 
     import torch
 
@@ -92,15 +94,22 @@ def main():
         if info.world > 1:
             torch.distributed.barrier()
         times.append(max_over_ranks(run_once(), info.world, dev))
+    res = None
+    launches = sum(c.kernel_launches() for c in ctxs)
     if info.rank == 0:
         best = min(times)
         tris = sum(sizes)
-        print(json.dumps({"workload": f"cfg5: {args.meshes} meshes, {tris} triangles, 2 mm spacing, whole meshes by LPT",
-                          "n_gpus": info.world, "host_threads_per_gpu": len(ctxs), "batch_s": best,
-                          "meshes_per_s": args.meshes / best, "triangles_per_s": tris / best,
-                          "rank0_share": share, "rank0_paths_waypoints": [counts[k] for k in share][:3]}))
+        res = {"workload": f"cfg5: {args.meshes} meshes, {tris} triangles, 2 mm spacing, whole meshes by LPT",
+               "n_gpus": info.world, "host_threads_per_gpu": len(ctxs), "batch_s": best, "batch_s_mean": float(np.mean(times)),
+               "meshes_per_s": args.meshes / best, "triangles_per_s": tris / best, "triangles": int(tris),
+               "rank0_kernel_launches": int(launches), "repeat": args.repeat,
+               "h2d_bytes": int(sum(b[1].data.size + b[1].tri.size * 4 for b in batch)),
+               "rank0_share": share, "rank0_paths_waypoints": [counts[k] for k in share][:3]}
+        if not args.quiet:
+            print(json.dumps(res))
     for c in ctxs:
         c.close()
+    return res
 
 
 if __name__ == "__main__":

@@ -19,13 +19,14 @@ SIZES = {"cfg4": (6250, 4000, True), "cfg4-grid-order": (6250, 4000, False), "cf
          "cfg2": (800, 625, False)}
 
 
-def main():
+def measure(name="cfg4", iters=4):
+    """stage times of NormalsFromMeshFaces and of the PCA frame on the device-resident mesh: a dict (bench.py --workload cfg4
+    wraps it into the bench line)"""
     import torch
 
     import noether_b200 as nb
     from noether_b200 import meshes
 
-    name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
     nx, ny, permuted = SIZES[name]
     xyz, tri = meshes.wavy(nx, ny)
     if permuted:
@@ -40,7 +41,8 @@ def main():
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     out = []
-    for it in range(4):
+    launches0 = ctx.kernel_launches()
+    for it in range(max(2, iters)):
         ctx.upload_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F)
         ctx.timer_start()
         ctx.normals_from_mesh_faces(V, download=False)
@@ -54,11 +56,18 @@ def main():
     t_n = min(o[0] for o in out[1:])
     t_p = min(o[1] for o in out[1:])
     b_n, b_p = 12 * F + 24 * V, 12 * V
-    print(json.dumps({"workload": name, "V": V, "F": F, "permuted": permuted,
-                      "normals_ms": t_n, "normals_GBps": b_n / t_n / 1e6, "normals_frac_of_peak": b_n / t_n / 1e6 / peak,
-                      "pca_frame_ms": t_p, "pca_GBps": b_p / t_p / 1e6, "pca_frac_of_peak": b_p / t_p / 1e6 / peak,
-                      "stages_ms": {k: round(v, 4) for k, v in out[-1][2].items()}}))
+    res = {"workload": name, "V": V, "F": F, "permuted": permuted,
+           "normals_ms": t_n, "normals_GBps": b_n / t_n / 1e6, "normals_frac_of_peak": b_n / t_n / 1e6 / peak,
+           "pca_frame_ms": t_p, "pca_GBps": b_p / t_p / 1e6, "pca_frac_of_peak": b_p / t_p / 1e6 / peak,
+           "normals_ms_mean": float(np.mean([o[0] for o in out[1:]])), "pca_frame_ms_mean": float(np.mean([o[1] for o in out[1:]])),
+           "launches_per_iteration": (ctx.kernel_launches() - launches0) // max(2, iters), "peak_GBps": peak,
+           "stages_ms": {k: round(v, 4) for k, v in out[-1][2].items()}}
     ctx.close()
+    return res
+
+
+def main():
+    print(json.dumps(measure(sys.argv[1] if len(sys.argv) > 1 else "cfg4")))
 
 
 if __name__ == "__main__":
