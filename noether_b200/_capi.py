@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnoether_b200.so")
+LIB_PATH = os.environ.get("NOETHER_B200_LIB") or os.path.join(HERE, "libnoether_b200.so")  # (override: kernel-variant experiments)
 
 NB2_OK = 0
 NB2_ERR_INVALID_ARGUMENT = 1

@@ -445,6 +445,7 @@ struct LinkParams
   unsigned scratchHits;  // largest plane the global work areas were sized for
   unsigned* overflow;    // bit 0: hit buffers too small (k_emit_hits), bit 1: a plane exceeds scratchHits
   unsigned fastHitCap;   // largest plane (in cut lines) whose second-generation work area fits the CTA's shared memory
+  unsigned plainRounds;  // claim rounds with plain stores before the compare-and-swap loop takes what is left (>= 1)
   unsigned* generalCount;  // planes the second-generation fast path declined (diagnostics)
   unsigned long long* phaseCycles;  // [16] diagnostics (NB2_LINK_PROFILE), normally null
   unsigned* done;        // CTAs that ran out of planes (the last one scans the per-plane counts)
@@ -1502,10 +1503,13 @@ __device__ __forceinline__ bool linkPlane2(const LinkParams& P, uint8_t* smem, l
   unsigned todo = phaseHash<DevOps>(W, rec, tid, nth);
   __syncthreads();
   clk.lap(1);
-  // Claim rounds with plain stores (no shared-memory compare-and-swap: one costs this SM about as much as a whole late
-  // round); the first claim rode along with the hashing.  phaseStragglers (compare-and-swap) is the bounded exit.
+  // Claim rounds with plain stores; the first claim rode along with the hashing.  What the plain rounds leave unsettled
+  // finishes with compare-and-swap (phaseStragglers).  Measured on cfg3 (profiles/r02_summary.md): an ATOMS.CAS costs
+  // the SM tens of cycles per warp INSTRUCTION however few lanes are active, so compare-and-swap loops must stay out of
+  // code that every endpoint runs (a variant that probed with compare-and-swap inside an unrolled settle phase took 0.45
+  // - 0.8 ms); one plain round plus stragglers (0.226 ms) and many plain rounds (0.241 ms) are about level.
   bool left = true;
-  for (unsigned round = 0; round < 32u && left; ++round)
+  for (unsigned round = 0; round < P.plainRounds && left; ++round)
   {
     if (round)
     {
@@ -1513,6 +1517,8 @@ __device__ __forceinline__ bool linkPlane2(const LinkParams& P, uint8_t* smem, l
       __syncthreads();
     }
     todo = phaseSettle<DevOps>(W, todo, tid, nth);
+    if (round + 1u == P.plainRounds)
+      break;  // (the stragglers follow without a barrier: occupied slots are final, empty ones are taken by compare-and-swap)
     left = __syncthreads_or(todo != 0u ? 1 : 0) != 0;
   }
   if (left)
@@ -2004,6 +2010,11 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   P.scratchHits = scratch_n > smem_cap ? scratch_n : 0u;
   P.overflow = c->counters.as<unsigned>() + 13;
   P.fastHitCap = fast_cap;
+  static const unsigned plain_rounds = [] {
+    const char* e = std::getenv("NB2_LINK_PLAIN_ROUNDS");
+    return e ? static_cast<unsigned>(std::max(1, std::atoi(e))) : 1u;
+  }();
+  P.plainRounds = plain_rounds;
   P.generalCount = c->counters.as<unsigned>() + 14;
   static const bool profile = std::getenv("NB2_LINK_PROFILE") != nullptr;
   if (profile)
