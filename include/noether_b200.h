@@ -358,6 +358,12 @@ int nb2_result_poses(const nb2_result* r, double* out16);
  * noether::ToolPathSegment (std::vector<Eigen::Isometry3d>), so the plugin fills noether::ToolPaths without an
  * intermediate copy.  The segments are filled in parallel on the host cores. */
 int nb2_result_poses_segments(const nb2_result* r, double* const* segment_out);
+/* The same expansion on SoA arrays the caller holds (no context, no device): positions / normals float[3 * W], the
+ * segments' offsets uint32[n_segments + 1] into the waypoints; raster_post_ops_applied as in nb2_result_view; out16
+ * receives 16 * W doubles.  On x86-64 with AVX2 four waypoints are expanded per step, bit-identical to the scalar code
+ * (NB2_NO_AVX2 in the environment selects the scalar code: tests compare the two). */
+int nb2_expand_poses(const float* positions, const float* normals, const uint32_t* segment_offsets, uint64_t n_segments,
+                     int raster_post_ops_applied, double* out16);
 void nb2_result_free(nb2_result* r);
 
 /* ------------------------------------------------------------------------------------------------------------------
@@ -430,6 +436,10 @@ uint64_t nb2_last_plan_general_path_planes(const nb2_context* ctx);
  * cycles thread 0 of every CTA spent (9 phases: init, hashing, claim rounds, pairing + zero-length lines, pairing check
  * + splitters, walks, pointer jumping, chain heads + order, output); cycles[0..15] of the last plan, zeros otherwise. */
 int nb2_link_profile(nb2_context* ctx, uint64_t cycles[16]);
+/* Device time of the last nb2_plan / nb2_plan_mesh on this context: from a CUDA event recorded on the context's stream at
+ * the entry of the call (for nb2_plan_mesh: before the upload) to one recorded behind the plan's last slicing kernel —
+ * the copies of the result to the host and the host's own work after the call are not in it. */
+int nb2_last_plan_span(nb2_context* ctx, float* ms);
 /* Bracket any sequence of calls on this context with CUDA events on the context's stream.  nb2_timer_stop waits for the
  * stop event and returns the elapsed device time in milliseconds. */
 int nb2_timer_start(nb2_context* ctx);

@@ -89,10 +89,21 @@ void PinnedBuf::release()
   cap = 0;
 }
 
+// NB2_STAGE_TIMERS=0: no events between the kernels of a call (nb2_last_timings then reports nothing)
+static bool stageTimersOn()
+{
+  static const bool on = [] {
+    const char* e = std::getenv("NB2_STAGE_TIMERS");
+    return !e || std::atoi(e) != 0;
+  }();
+  return on;
+}
 void StageTimer::begin(cudaStream_t s)
 {
   used = 0;
   names.clear();
+  if (!stageTimersOn())
+    return;
   if (events.empty())
   {
     events.resize(24);
@@ -103,7 +114,7 @@ void StageTimer::begin(cudaStream_t s)
 }
 void StageTimer::mark(const char* name, cudaStream_t s)
 {
-  if (used + 2 > events.size())
+  if (!stageTimersOn() || used + 2 > events.size())
     return;
   ++used;
   names.push_back(name);
@@ -349,6 +360,26 @@ nb2_result* emptyResult(nb2_context* c, const nb2_lattice& L)
  * the previous plan on this context, and a kernel that finds a capacity too small writes nothing and raises a flag, on
  * which the host grows the buffers and repeats that stage.  Only the first plan of a context waits for its hit count.
  */
+/** nb2_last_plan_span: the begin event at the entry of the planning call, the end event behind the plan's last kernel */
+static void spanBegin(nb2_context* c)
+{
+  if (!c->ev_span_begin)
+  {
+    NB2_CUDA(cudaEventCreate(&c->ev_span_begin));
+    NB2_CUDA(cudaEventCreate(&c->ev_span_end));
+  }
+  c->span_valid = false;
+  NB2_CUDA(cudaEventRecord(c->ev_span_begin, c->stream));
+}
+static void spanEnd(nb2_context* c)
+{
+  if (c->ev_span_end)
+  {
+    NB2_CUDA(cudaEventRecord(c->ev_span_end, c->stream));
+    c->span_valid = true;
+  }
+}
+
 nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* explicit_lat, uint64_t plane_begin,
                       uint64_t plane_end, bool emit_edges, bool download = true)
 {
@@ -424,6 +455,7 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
     c->timer.mark("link", c->stream);
     launchWaypoints(c, w_cap, emit_edges ? 1 : 0);
     c->timer.mark("waypoints", c->stream);
+    spanEnd(c);
   };
 
   bool sizes_known = false;
@@ -712,6 +744,21 @@ int nb2_context_create(int device, nb2_context** out)
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->smem_per_sm = prop.sharedMemPerMultiprocessor;
   NB2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // part of L2 may be set aside for lines that kernels on this stream mark as persisting: the SoA positions, which the
+  // ingest pass writes and the extents / classification / contouring / waypoint passes of the same plan read again
+  c->l2_persist_max = 0;
+  // (measured on cfg3, profiles/r02_summary.md: extents and classification gain 5 us between them, but the contouring and
+  //  linking passes lose 40 us to the smaller remainder of L2, so the window is opt-in: NB2_L2_PERSIST=1)
+  if (prop.persistingL2CacheMaxSize > 0 && std::getenv("NB2_L2_PERSIST") && std::atoi(std::getenv("NB2_L2_PERSIST")) != 0)
+  {
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize) == cudaSuccess)
+    {
+      c->l2_persist_max = prop.persistingL2CacheMaxSize;
+      c->l2_window_max = prop.accessPolicyMaxWindowSize;
+    }
+    else
+      cudaGetLastError();
+  }
   c->counters.ensure(64 * sizeof(unsigned));
   NB2_CUDA(cudaMemsetAsync(c->counters.ptr, 0, 64 * sizeof(unsigned), c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
@@ -749,6 +796,11 @@ void nb2_context_destroy(nb2_context* c)
     cudaFreeHost(hb.ptr);
   c->timer.destroy();
   c->timer_upload.destroy();
+  if (c->ev_span_begin)
+  {
+    cudaEventDestroy(c->ev_span_begin);
+    cudaEventDestroy(c->ev_span_end);
+  }
   if (c->stream)
     cudaStreamDestroy(c->stream);
   if (prev >= 0)
@@ -1838,6 +1890,9 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   requireMesh(c);
   if (!c->has_normals)
     fail(NB2_ERR_NO_NORMALS, kNoNormalsMessage);
+  if (!c->span_open)
+    spanBegin(c);
+  c->span_open = false;
   requirePcaPoints(c);
   if (!(prm->line_spacing > 0.0) || !std::isfinite(prm->line_spacing))
     fail(NB2_ERR_INVALID_ARGUMENT, "line_spacing must be a positive finite number");
@@ -1909,8 +1964,42 @@ int nb2_plan_mesh(nb2_context* c, const nb2_mesh_view* mesh, const nb2_plan_para
 {
   if (out)
     *out = nullptr;
+  if (c)
+  {
+    // (the span of nb2_last_plan_span begins here: the upload's copies and ingest pass belong to the plan)
+    std::lock_guard<std::mutex> lock(c->mu);
+    DeviceGuard g(c->device);
+    c->span_open = false;
+    if (cudaSuccess == cudaGetLastError())
+    {
+      try
+      {
+        spanBegin(c);
+        c->span_open = true;
+      }
+      catch (const Error&)
+      {
+      }
+    }
+  }
   const int rc = nb2_mesh_upload(c, mesh);
+  if (rc != NB2_OK && c)
+    c->span_open = false;
   return rc != NB2_OK ? rc : nb2_plan(c, prm, out);
+}
+
+int nb2_last_plan_span(nb2_context* c, float* ms)
+{
+  NB2_API_BEGIN
+  if (!c || !ms)
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  if (!c->span_valid)
+    fail(NB2_ERR_INVALID_ARGUMENT, "no plan has run on this context");
+  NB2_CUDA(cudaEventSynchronize(c->ev_span_end));
+  NB2_CUDA(cudaEventElapsedTime(ms, c->ev_span_begin, c->ev_span_end));
+  NB2_API_END
 }
 
 int nb2_last_lattice(const nb2_context* c, nb2_lattice* out)
@@ -1966,6 +2055,23 @@ int nb2_result_poses_segments(const nb2_result* r, double* const* segment_out)
     fail(NB2_ERR_INVALID_ARGUMENT, "the tool paths of this result were left on the device (download = 0 or a slab of a "
                                    "sharded plan): gather or re-plan with download = 1");
   expandPosesSegments(*r, segment_out);
+  NB2_API_END
+}
+
+int nb2_expand_poses(const float* positions, const float* normals, const uint32_t* segment_offsets, uint64_t n_segments,
+                     int raster_post_ops_applied, double* out16)
+{
+  NB2_API_BEGIN
+  if (!segment_offsets || (n_segments && segment_offsets[n_segments] && (!positions || !normals || !out16)))
+    fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  nb2_result r;
+  r.n_segments = n_segments;
+  r.n_waypoints = n_segments ? segment_offsets[n_segments] : 0;
+  r.segment_offsets = const_cast<uint32_t*>(segment_offsets);
+  r.positions = const_cast<float*>(positions);
+  r.normals = const_cast<float*>(normals);
+  r.post_ops_applied = raster_post_ops_applied != 0;
+  expandPoses(r, out16);
   NB2_API_END
 }
 

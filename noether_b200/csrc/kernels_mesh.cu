@@ -388,6 +388,21 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
   c->rec_step = point_step;
   c->rec_off_xyz = off_xyz;
   c->rec_off_nrm = off_nrm;
+  // the positions written here are read again by every later pass of the plan: keep as much of the array as the
+  // set-aside part of L2 holds (the window covers the array; hitRatio thins it out to what fits)
+  if (c->l2_persist_max)
+  {
+    cudaStreamAttrValue attr{};
+    const size_t bytes = sizeof(float4) * c->V;
+    attr.accessPolicyWindow.base_ptr = c->pos.ptr;
+    const size_t window = std::min(bytes, c->l2_window_max);
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = window <= c->l2_persist_max ? 1.0f : static_cast<float>(c->l2_persist_max) / static_cast<float>(window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
+      cudaGetLastError();
+  }
   k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
                                                            c->pos.as<float4>(),
                                                            c->partials.as<MomentPartial>(), c->counters.as<unsigned>(),

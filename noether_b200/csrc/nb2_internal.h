@@ -180,6 +180,8 @@ struct nb2_context
   int sm_count = 148;
   size_t smem_optin = 0;
   size_t smem_per_sm = 0;
+  size_t l2_window_max = 0;   // largest access-policy window
+  size_t l2_persist_max = 0;  // bytes of L2 that may be set aside for persisting lines (0: not available / switched off)
   cudaStream_t stream = nullptr;
   mutable std::mutex mu;
   uint64_t launches = 0;
@@ -294,6 +296,9 @@ struct nb2_context
   nb2::StageTimer timer;         // last plan / slice / normals call
   nb2::StageTimer timer_upload;  // last mesh upload
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // nb2_timer_start / nb2_timer_stop
+  cudaEvent_t ev_span_begin = nullptr, ev_span_end = nullptr;  // nb2_last_plan_span: entry of the call .. end of its last kernel
+  bool span_open = false;   // nb2_plan_mesh recorded the begin event: nb2_plan must not move it
+  bool span_valid = false;
 
   // NCCL (dlopen'ed lazily)
   void* nccl_comm = nullptr;

@@ -21,8 +21,8 @@
 #include <limits>
 #include <numeric>
 #include <thread>
-#if defined(__SSE2__)
-#include <emmintrin.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
 #endif
 
 namespace nb2
@@ -189,6 +189,94 @@ void rasterOrganization(nb2_result*& rp)
 namespace
 {
 /** dst(s) = where the poses of segment s go */
+#if defined(__x86_64__)
+// createTransform (+ DirectionOfTravelOrientationModifier) for four waypoints at a time.  The expansion is bound by the
+// latency of double-precision square roots and divisions (three to five normalisations per waypoint); the vector forms
+// are IEEE operations like the scalar ones and nothing is contracted into FMA, so every lane equals the scalar code above
+// bit for bit (tests/test_toolpath_host.py compares the two).
+struct V3
+{
+  __m256d x, y, z;
+};
+__attribute__((target("avx2"))) inline V3 vcross(const V3& a, const V3& b)
+{
+  return { _mm256_sub_pd(_mm256_mul_pd(a.y, b.z), _mm256_mul_pd(a.z, b.y)), _mm256_sub_pd(_mm256_mul_pd(a.z, b.x), _mm256_mul_pd(a.x, b.z)),
+           _mm256_sub_pd(_mm256_mul_pd(a.x, b.y), _mm256_mul_pd(a.y, b.x)) };
+}
+__attribute__((target("avx2"))) inline V3 vnormalized(const V3& a)
+{
+  // Eigen 3.4 normalized(): v / sqrt(|v|^2) when |v|^2 > 0, otherwise v unchanged; |v|^2 = x x + (y y + z z)
+  const __m256d z = _mm256_add_pd(_mm256_mul_pd(a.x, a.x), _mm256_add_pd(_mm256_mul_pd(a.y, a.y), _mm256_mul_pd(a.z, a.z)));
+  const __m256d pos = _mm256_cmp_pd(z, _mm256_setzero_pd(), _CMP_GT_OQ);
+  const __m256d d = _mm256_blendv_pd(_mm256_set1_pd(1.0), _mm256_sqrt_pd(z), pos);  // (x / 1.0 == x exactly)
+  return { _mm256_div_pd(a.x, d), _mm256_div_pd(a.y, d), _mm256_div_pd(a.z, d) };
+}
+/** waypoints [i, i + 4) of a segment [b, e): poses to out + 16 i ... (i + 3 < e) */
+__attribute__((target("avx2"))) void expandFourAvx2(const float* positions, const float* normals, uint32_t b, uint32_t e, uint32_t i,
+                                                    bool dot_modifier, double* out)
+{
+  alignas(32) double px[4], py[4], pz[4], nx[4], ny[4], nz[4], dx[4], dy[4], dz[4];
+  for (int l = 0; l < 4; ++l)
+  {
+    const uint32_t w = i + l;
+    const float* p = positions + 3ull * w;
+    const float* n = normals + 3ull * w;
+    px[l] = p[0], py[l] = p[1], pz[l] = p[2];
+    nx[l] = n[0], ny[l] = n[1], nz[l] = n[2];
+    if (w + 1 < e)
+      dx[l] = static_cast<double>(p[3]) - px[l], dy[l] = static_cast<double>(p[4]) - py[l], dz[l] = static_cast<double>(p[5]) - pz[l];
+    else if (w > b)
+      dx[l] = px[l] - static_cast<double>(p[-3]), dy[l] = py[l] - static_cast<double>(p[-2]), dz[l] = pz[l] - static_cast<double>(p[-1]);
+    else
+      dx[l] = dy[l] = dz[l] = 0.0;
+  }
+  const V3 n{ _mm256_load_pd(nx), _mm256_load_pd(ny), _mm256_load_pd(nz) };
+  const V3 dir{ _mm256_load_pd(dx), _mm256_load_pd(dy), _mm256_load_pd(dz) };
+  V3 y = vcross(n, dir);
+  V3 x = vnormalized(vcross(y, n));
+  y = vnormalized(y);
+  const V3 z = vnormalized(n);
+  if (dot_modifier)
+  {
+    const V3 ref_x = vnormalized(dir);
+    const V3 zz = vnormalized(z);
+    y = vnormalized(vcross(zz, ref_x));
+    x = vnormalized(vcross(y, zz));
+  }
+  alignas(32) double c[9][4];
+  _mm256_store_pd(c[0], x.x), _mm256_store_pd(c[1], x.y), _mm256_store_pd(c[2], x.z);
+  _mm256_store_pd(c[3], y.x), _mm256_store_pd(c[4], y.y), _mm256_store_pd(c[5], y.z);
+  _mm256_store_pd(c[6], z.x), _mm256_store_pd(c[7], z.y), _mm256_store_pd(c[8], z.z);
+  for (int l = 0; l < 4; ++l)
+  {
+    double* T = out + 16ull * (i + l);
+    if ((reinterpret_cast<uintptr_t>(T) & 15u) == 0)
+    {
+      _mm_stream_pd(T + 0, _mm_set_pd(c[1][l], c[0][l]));
+      _mm_stream_pd(T + 2, _mm_set_pd(0.0, c[2][l]));
+      _mm_stream_pd(T + 4, _mm_set_pd(c[4][l], c[3][l]));
+      _mm_stream_pd(T + 6, _mm_set_pd(0.0, c[5][l]));
+      _mm_stream_pd(T + 8, _mm_set_pd(c[7][l], c[6][l]));
+      _mm_stream_pd(T + 10, _mm_set_pd(0.0, c[8][l]));
+      _mm_stream_pd(T + 12, _mm_set_pd(py[l], px[l]));
+      _mm_stream_pd(T + 14, _mm_set_pd(1.0, pz[l]));
+    }
+    else
+    {
+      T[0] = c[0][l], T[1] = c[1][l], T[2] = c[2][l], T[3] = 0.0;
+      T[4] = c[3][l], T[5] = c[4][l], T[6] = c[5][l], T[7] = 0.0;
+      T[8] = c[6][l], T[9] = c[7][l], T[10] = c[8][l], T[11] = 0.0;
+      T[12] = px[l], T[13] = py[l], T[14] = pz[l], T[15] = 1.0;
+    }
+  }
+}
+bool haveAvx2()
+{
+  static const bool yes = __builtin_cpu_supports("avx2") && !std::getenv("NB2_NO_AVX2");
+  return yes;
+}
+#endif
+
 template <typename Dst>
 void expandPosesTo(const nb2_result& r, Dst dst)
 {
@@ -211,7 +299,13 @@ void expandPosesTo(const nb2_result& r, Dst dst)
     {
       const uint32_t b = r.segment_offsets[s], e = r.segment_offsets[s + 1];
       double* const out = dst(s) - 16ull * b;  // so that waypoint i lands at out + 16 i
-      for (uint32_t i = b; i < e; ++i)
+      uint32_t i = b;
+#if defined(__x86_64__)
+      if (haveAvx2())
+        for (; i + 4 <= e; i += 4)
+          expandFourAvx2(r.positions, r.normals, b, e, i, dot_modifier, out);
+#endif
+      for (; i < e; ++i)
       {
         const D3 p = fromFloat(r.positions + 3 * i);
         const D3 n = fromFloat(r.normals + 3 * i);
@@ -237,7 +331,7 @@ void expandPosesTo(const nb2_result& r, Dst dst)
           x = normalized(cross(y, zz));
         }
         double* T = out + 16ull * i;
-#if defined(__SSE2__)
+#if defined(__x86_64__)
         // 128 bytes per waypoint that nobody reads back soon: streaming stores skip the read-for-ownership of every
         // cache line (the expansion is bound by host memory traffic: 512 MB for cfg3's four million waypoints)
         if ((reinterpret_cast<uintptr_t>(T) & 15u) == 0)
@@ -259,7 +353,7 @@ void expandPosesTo(const nb2_result& r, Dst dst)
         T[12] = p.x, T[13] = p.y, T[14] = p.z, T[15] = 1.0;
       }
     }
-#if defined(__SSE2__)
+#if defined(__x86_64__)
     _mm_sfence();
 #endif
   });

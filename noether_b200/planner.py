@@ -229,6 +229,13 @@ class Context:
         _capi.check(self._lib.nb2_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def last_plan_span_ms(self) -> float:
+        """Device time (ms) of the last plan on this context: CUDA events at the entry of the planning call and behind its
+        last slicing kernel (nb2_last_plan_span)."""
+        ms = C.c_float()
+        _capi.check(self._lib.nb2_last_plan_span(self._h, C.byref(ms)))
+        return float(ms.value)
+
     # -- multi-GPU --------------------------------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -32,7 +32,9 @@ def main():
     ctx = nb.Context(0)
     ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
     nrm = ctx.normals_from_mesh_faces(V)
-    blob = meshes.pack_blob(xyz, nrm, tri, "PointNormal")
+    # resident layout: what nb2_mesh_upload(NB2_MESH_GEOMETRY_ONLY) leaves in HBM ({xyz, normal} records of 24 bytes), or the
+    # 48-byte PointNormal records of the host cloud (NB2_PROFILE_LAYOUT=PointNormal)
+    blob = meshes.pack_blob(xyz, nrm, tri, os.environ.get("NB2_PROFILE_LAYOUT", "Packed24"))
     d_cloud = torch.from_numpy(blob.data).to(dev)
     d_tri = torch.from_numpy(tri.reshape(-1).view(np.int32)).to(dev)
     torch.cuda.synchronize()
@@ -64,7 +66,7 @@ def main():
     print(name, desc)
     print("paths/segments/waypoints", n)
     print("stages ms", {k: round(v, 4) for k, v in st.items()})
-    print("step ms (events) %.4f, sum of stages %.4f" % (total, sum(st.values())))
+    print("step ms (events) %.4f, sum of stages %.4f, library span %.4f" % (total, sum(st.values()), ctx.last_plan_span_ms()))
     print("planes linked by the general path:", ctx.general_path_planes())
     if os.environ.get("NB2_LINK_PROFILE"):
         cyc = ctx.link_profile()
