@@ -314,7 +314,11 @@ typedef struct nb2_plan_params
   int32_t shard_rank;
   int32_t shard_count; /* 0 or 1 = unsharded */
   /* 1 (default) = copy the tool paths to the host.  0 = leave them in HBM: the result carries the counts only and the
-   * host-side modifiers (legacy, raster post-ops) are skipped — used to time the device path on resident data. */
+   * host-side modifiers (legacy, raster post-ops) are skipped — used to time the device path on resident data.
+   * 2 = copy them BEHIND the call: nb2_plan returns once the segment structure is on the host; positions and normals
+   * follow in chunks while the caller sizes its containers (nb2_result_layout) and nb2_result_poses_segments expands
+   * the chunks that have landed (PCIe and the host cores overlap).  nb2_result_get and every other consumer of the result
+   * wait for the rest first.  Ignored (= 1) for legacy plans, raster_post_ops, emit_edges and sharded plans. */
   int32_t download;
   int32_t reserved_;
 } nb2_plan_params;
@@ -350,6 +354,10 @@ typedef struct nb2_result_view
 } nb2_result_view;
 
 int nb2_result_get(const nb2_result* r, nb2_result_view* out);
+/* The same view without waiting for a download = 2 result's positions / normals: counts, path_offsets, segment_offsets and
+ * path_plane are valid, the waypoint arrays may still be arriving (read them after nb2_result_get, or let
+ * nb2_result_poses_segments consume them). */
+int nb2_result_layout(const nb2_result* r, nb2_result_view* out);
 /* Expand to Eigen::Isometry3d storage: 16 doubles per waypoint, column-major, last row 0 0 0 1
  * (createTransform :380-394, then DirectionOfTravelOrientationModifier when post-ops were applied). */
 int nb2_result_poses(const nb2_result* r, double* out16);

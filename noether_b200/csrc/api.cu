@@ -236,10 +236,34 @@ bool contextAlive(nb2_context* c)
   return std::find(g_live.begin(), g_live.end(), c) != g_live.end();
 }
 
+void waitWaypoints(const nb2_result& r, uint64_t w_end)
+{
+  if (!r.lazy_chunks || !r.chunk_w)
+    return;
+  auto& landed = const_cast<nb2_result&>(r).chunks_landed;
+  const int want = static_cast<int>(std::min<uint64_t>(r.lazy_chunks, (w_end + r.chunk_w - 1) / r.chunk_w));
+  if (landed.load(std::memory_order_acquire) >= want)
+    return;
+  if (r.owner && contextAlive(r.owner) && want > 0)
+  {
+    // (the events are the owner's and are recorded again by its next lazy plan: the later point in the stream they then
+    //  stand for implies this one)
+    cudaSetDevice(r.owner->device);
+    if (cudaEventSynchronize(r.owner->chunkEvents[want - 1]) != cudaSuccess)
+      cudaGetLastError();
+  }
+  int seen = landed.load();
+  while (seen < want && !landed.compare_exchange_weak(seen, want, std::memory_order_release))
+  {
+  }
+}
+
 void freeResult(nb2_result* r)
 {
   if (!r)
     return;
+  if (r->lazy_chunks)
+    waitWaypoints(*r, r->n_waypoints);  // copies still in flight write into the block
   if (r->block && !r->owner)
     cudaFreeHost(r->block);
   if (r->block && r->owner)
@@ -381,7 +405,7 @@ static void spanEnd(nb2_context* c)
 }
 
 nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* explicit_lat, uint64_t plane_begin,
-                      uint64_t plane_end, bool emit_edges, bool download = true)
+                      uint64_t plane_end, bool emit_edges, bool download = true, bool lazy = false)
 {
   requireMesh(c);
   if (!c->has_normals)
@@ -615,7 +639,33 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
   r->lattice = lat;
   try
   {
-    if (Wt)
+    // lazy: the segment lengths first and alone behind the synchronisation below; positions and normals follow in chunks,
+    // each with an event, while the caller already sizes its containers and expands the chunks that have landed
+    const bool in_chunks = lazy && !emit_edges && Wt >= (1u << 18);
+    if (Wt && in_chunks)
+    {
+      NB2_CUDA(cudaMemcpyAsync(r->segment_offsets + 1, c->outSegLen.ptr, sizeof(unsigned) * St, cudaMemcpyDeviceToHost,
+                               c->stream));
+      c->timer.mark("d2h", c->stream);
+      NB2_CUDA(cudaStreamSynchronize(c->stream));
+      constexpr int kChunks = 16;
+      if (c->chunkEvents.empty())
+      {
+        c->chunkEvents.resize(kChunks);
+        for (auto& e : c->chunkEvents)
+          NB2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+      r->chunk_w = (Wt + kChunks - 1) / kChunks;
+      r->lazy_chunks = static_cast<int>((Wt + r->chunk_w - 1) / r->chunk_w);
+      for (int k = 0; k < r->lazy_chunks; ++k)
+      {
+        const uint64_t w0 = k * r->chunk_w, wn = std::min<uint64_t>(r->chunk_w, Wt - w0);
+        NB2_CUDA(cudaMemcpyAsync(r->positions + 3 * w0, c->outPos.as<float>() + 3 * w0, sizeof(float) * 3 * wn, cudaMemcpyDeviceToHost, c->stream));
+        NB2_CUDA(cudaMemcpyAsync(r->normals + 3 * w0, c->outNrm.as<float>() + 3 * w0, sizeof(float) * 3 * wn, cudaMemcpyDeviceToHost, c->stream));
+        NB2_CUDA(cudaEventRecord(c->chunkEvents[k], c->stream));
+      }
+    }
+    else if (Wt)
     {
       NB2_CUDA(cudaMemcpyAsync(r->positions, c->outPos.ptr, sizeof(float) * 3 * Wt, cudaMemcpyDeviceToHost, c->stream));
       NB2_CUDA(cudaMemcpyAsync(r->normals, c->outNrm.ptr, sizeof(float) * 3 * Wt, cudaMemcpyDeviceToHost, c->stream));
@@ -628,8 +678,11 @@ nb2_result* sliceImpl(nb2_context* c, const FrameParams* fp, const nb2_lattice* 
       NB2_CUDA(cudaMemcpyAsync(r->segment_offsets + 1, c->outSegLen.ptr, sizeof(unsigned) * St, cudaMemcpyDeviceToHost,
                                c->stream));
     }
-    c->timer.mark("d2h", c->stream);
-    NB2_CUDA(cudaStreamSynchronize(c->stream));
+    if (!in_chunks)
+    {
+      c->timer.mark("d2h", c->stream);
+      NB2_CUDA(cudaStreamSynchronize(c->stream));
+    }
   }
   catch (...)
   {
@@ -796,6 +849,9 @@ void nb2_context_destroy(nb2_context* c)
     cudaFreeHost(hb.ptr);
   c->timer.destroy();
   c->timer_upload.destroy();
+  for (auto& e : c->chunkEvents)
+    cudaEventDestroy(e);
+  c->chunkEvents.clear();
   if (c->ev_span_begin)
   {
     cudaEventDestroy(c->ev_span_begin);
@@ -825,8 +881,26 @@ struct SourceError
   int code;
 };
 constexpr uint64_t kGrain = NB2_UPLOAD_GRAIN;
-constexpr size_t kSlotBytes = size_t(3) << 20;
-constexpr unsigned kSlots = 32;
+constexpr size_t kSlotBytes = size_t(3) << 19;  // (1.5 MB x 24 slots measured best on the 16-core bench host: the ring stays in its 60 MB L3)
+constexpr unsigned kSlots = 24;
+// experiments: NB2_STAGING_SLOT_KB / NB2_STAGING_SLOTS shrink the ring (a ring that fits the host's last-level cache is
+// written and read by the copy engine without touching host DRAM)
+size_t slotBytes()
+{
+  static const size_t n = [] {
+    const char* e = std::getenv("NB2_STAGING_SLOT_KB");
+    return e ? std::max<size_t>(size_t(64) << 10, static_cast<size_t>(std::atoll(e)) << 10) : kSlotBytes;
+  }();
+  return n;
+}
+unsigned slotCount()
+{
+  static const unsigned n = [] {
+    const char* e = std::getenv("NB2_STAGING_SLOTS");
+    return e ? static_cast<unsigned>(std::min(64, std::max(2, std::atoi(e)))) : kSlots;
+  }();
+  return n;
+}
 
 struct StageSource
 {
@@ -841,7 +915,7 @@ unsigned stagingWorkers()
     unsigned hw = std::thread::hardware_concurrency();
     if (const char* e = std::getenv("NB2_STAGING_THREADS"))
       hw = static_cast<unsigned>(std::max(1, std::atoi(e)));
-    return std::min(std::max(hw, 1u), kSlots - 4u);
+    return std::min(std::max(hw, 1u), 60u);
   }();
   return n;
 }
@@ -850,13 +924,16 @@ unsigned stagingWorkers()
  *  c->stream (not waited for).  Throws when a source reports an error. */
 void stageToDevice(nb2_context* c, const StageSource& S, uint64_t V, uint64_t F, void* d_cloud, void* d_tri)
 {
-  const uint64_t pts_per = std::max<uint64_t>(kGrain, (kSlotBytes / S.step) / kGrain * kGrain);
-  const uint64_t tri_per = (kSlotBytes / 12) / kGrain * kGrain;
+  const unsigned kSlots = slotCount();
+  const uint64_t pts_per = std::max<uint64_t>(kGrain, (slotBytes() / S.step) / kGrain * kGrain);
+  const uint64_t tri_per = std::max<uint64_t>(kGrain, (slotBytes() / 12) / kGrain * kGrain);
   const size_t slot_bytes = std::max<size_t>(pts_per * S.step, tri_per * 12);
   c->stageRing.ensure(slot_bytes * kSlots);
-  if (c->stageEvents.empty())
+  if (c->stageEvents.size() < kSlots)
   {
-    c->stageEvents.resize(kSlots);
+    for (auto& e : c->stageEvents)
+      cudaEventDestroy(e);
+    c->stageEvents.assign(kSlots, nullptr);
     for (auto& e : c->stageEvents)
       NB2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
@@ -924,7 +1001,7 @@ void stageToDevice(nb2_context* c, const StageSource& S, uint64_t V, uint64_t F,
       enqueued[i].store(state, std::memory_order_release);
     }
   };
-  const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(stagingWorkers(), n_items));
+  const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(stagingWorkers(), kSlots > 4 ? kSlots - 2 : 2u), n_items));
   std::vector<std::thread> pool;
   for (unsigned w = 1; w < workers; ++w)
     pool.emplace_back(work);
@@ -1920,8 +1997,11 @@ int nb2_plan(nb2_context* c, const nb2_plan_params* prm, nb2_result** out)
   const bool device_legacy = prm->legacy != 0 && download;
   if (device_legacy && !(prm->point_spacing > 0.0))
     fail(NB2_ERR_INVALID_ARGUMENT, "point_spacing must be positive");
+  // download = 2: the tool paths' positions and normals land in host memory behind this call (nb2_result_poses_segments
+  // expands them as they arrive).  Plans whose result the host must post-process here are downloaded in one piece.
+  const bool lazy = prm->download == 2 && download && !prm->legacy && !prm->raster_post_ops;
   nb2_result* r = sliceImpl(c, &fp, nullptr, 0, NB2_ALL_PLANES, prm->emit_edges != 0 || (prm->legacy != 0 && !device_legacy),
-                            device_legacy ? false : download);
+                            device_legacy ? false : download, lazy);
   r->params = *prm;
   if (device_legacy)
   {
@@ -2013,11 +2093,13 @@ int nb2_last_lattice(const nb2_context* c, nb2_lattice* out)
   NB2_API_END
 }
 
-int nb2_result_get(const nb2_result* r, nb2_result_view* out)
+static int resultView(const nb2_result* r, nb2_result_view* out, bool layout_only)
 {
   NB2_API_BEGIN
   if (!r || !out)
     fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!layout_only)
+    waitWaypoints(*r, r->n_waypoints);  // the caller may read positions / normals as soon as this returns
   out->n_paths = r->n_paths;
   out->n_segments = r->n_segments;
   out->n_waypoints = r->n_waypoints;
@@ -2033,6 +2115,9 @@ int nb2_result_get(const nb2_result* r, nb2_result_view* out)
   out->legacy = r->legacy ? 1 : 0;
   NB2_API_END
 }
+
+int nb2_result_get(const nb2_result* r, nb2_result_view* out) { return resultView(r, out, false); }
+int nb2_result_layout(const nb2_result* r, nb2_result_view* out) { return resultView(r, out, true); }
 
 int nb2_result_poses(const nb2_result* r, double* out16)
 {

@@ -577,6 +577,8 @@ int nb2_result_from_pose_segments(nb2_context* c, uint64_t n_paths, const uint32
 int nb2_result_modify(nb2_context* c, const nb2_result* in, const nb2_modifier* chain, int n_chain, nb2_result** out)
 {
   NB2_API_BEGIN
+  if (in)
+    nb2::waitWaypoints(*in, in->n_waypoints);
   if (!c || !in || !out)
     fail(NB2_ERR_INVALID_ARGUMENT, "NULL argument");
   if (in->device_resident)

@@ -6,6 +6,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -296,6 +297,7 @@ struct nb2_context
   nb2::StageTimer timer;         // last plan / slice / normals call
   nb2::StageTimer timer_upload;  // last mesh upload
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;  // nb2_timer_start / nb2_timer_stop
+  std::vector<cudaEvent_t> chunkEvents;  // lazy result download: one event per chunk of waypoints (reused plan after plan)
   cudaEvent_t ev_span_begin = nullptr, ev_span_end = nullptr;  // nb2_last_plan_span: entry of the call .. end of its last kernel
   bool span_open = false;   // nb2_plan_mesh recorded the begin event: nb2_plan must not move it
   bool span_valid = false;
@@ -334,6 +336,11 @@ struct nb2_result
   bool dev_edges = false;
   nb2_plan_params params{};
   nb2_lattice lattice{};
+  // download = 2: positions / normals arrive in `lazy_chunks` pieces of `chunk_w` waypoints behind the call that made the
+  // result; chunk k is complete when the owner's chunkEvents[k] has happened (nb2::waitWaypoints)
+  int lazy_chunks = 0;
+  uint64_t chunk_w = 0;
+  std::atomic<int> chunks_landed{ 0 };
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -410,6 +417,8 @@ void launchLegacy(nb2_context* c, uint64_t nP, uint64_t W, uint64_t S, double po
                   double min_hole_size, uint64_t totals[3], std::vector<uint32_t>& host_planeL);
 
 // host-side tool path post-ops (toolpath.cpp)
+/** block until waypoints [0, w_end) of a lazily downloaded result are in host memory (no-op for ordinary results) */
+void waitWaypoints(const nb2_result& r, uint64_t w_end);
 void rasterOrganization(nb2_result*& r);
 void expandPoses(const nb2_result& r, double* out16);
 void expandPosesSegments(const nb2_result& r, double* const* segment_out);

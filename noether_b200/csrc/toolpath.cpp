@@ -15,6 +15,7 @@
 #include "nb2_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -29,6 +30,26 @@ namespace nb2
 {
 namespace
 {
+/** fn(0), fn(1), ... fn(n - 1), each once, started in that order by as many threads as the machine has */
+void parallelInOrder(uint64_t n, const std::function<void(uint64_t)>& fn)
+{
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0)
+    hw = 1;
+  const uint64_t workers = std::min<uint64_t>(hw, n);
+  std::atomic<uint64_t> next{ 0 };
+  auto run = [&]() {
+    for (uint64_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+      fn(i);
+  };
+  std::vector<std::thread> th;
+  for (uint64_t w = 1; w < workers; ++w)
+    th.emplace_back(run);
+  run();
+  for (auto& t : th)
+    t.join();
+}
+
 void parallelFor(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& fn)
 {
   unsigned hw = std::thread::hardware_concurrency();
@@ -292,9 +313,13 @@ void expandPosesTo(const nb2_result& r, Dst dst)
     return;
   }
   const bool dot_modifier = r.post_ops_applied;
-  // a chunk of work = a few thousand waypoints, whatever the segment sizes
+  // a piece of work = a few thousand waypoints, whatever the segment sizes; the pieces are handed out in order, so that a
+  // result whose positions and normals are still arriving from the device (download = 2) is expanded front to back, every
+  // worker on the part that has landed
   const uint64_t grain = std::max<uint64_t>(1, 4096 / std::max<uint64_t>(1, r.n_waypoints / std::max<uint64_t>(1, r.n_segments)));
-  parallelFor(r.n_segments, grain, [&](uint64_t sb, uint64_t se) {
+  parallelInOrder((r.n_segments + grain - 1) / grain, [&](uint64_t piece) {
+    const uint64_t sb = piece * grain, se = std::min<uint64_t>(r.n_segments, sb + grain);
+    waitWaypoints(r, r.segment_offsets[se]);
     for (uint64_t s = sb; s < se; ++s)
     {
       const uint32_t b = r.segment_offsets[s], e = r.segment_offsets[s + 1];

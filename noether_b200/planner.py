@@ -188,7 +188,7 @@ class Context:
         mv = _capi.MeshView(data_ptr, n_vertices, point_step, off_xyz, off_normal, 0, tri_ptr, n_triangles)
         r = C.c_void_p()
         _capi.check(self._lib.nb2_plan_mesh(self._h, C.byref(mv), C.byref(params), C.byref(r)))
-        return ToolPaths(self, r)
+        return ToolPaths(self, r, layout_only=params.download == 2)
 
     def slice(self, lattice: _capi.Lattice, plane_begin: int = 0, plane_end: int | None = None) -> "ToolPaths":
         r = C.c_void_p()
@@ -280,12 +280,14 @@ def make_lattice(pca: _capi.Pca, direction, origin, line_spacing: float, bidirec
 class ToolPaths:
     """noether::ToolPaths as returned by the C ABI: SoA arrays (views into the result's pinned block)."""
 
-    def __init__(self, ctx: Context, handle):
+    def __init__(self, ctx: Context, handle, layout_only: bool = False):
+        """layout_only: do not wait for the waypoint arrays of a download = 2 result (nb2_result_layout): counts and offsets
+        are valid at once, `positions` / `normals` after wait(); poses() consumes them as they land."""
         self._ctx = ctx
         self._lib = ctx._lib
         self._r = handle
         v = _capi.ResultView()
-        _capi.check(self._lib.nb2_result_get(self._r, C.byref(v)))
+        _capi.check((self._lib.nb2_result_layout if layout_only else self._lib.nb2_result_get)(self._r, C.byref(v)))
         self.n_paths, self.n_segments, self.n_waypoints = int(v.n_paths), int(v.n_segments), int(v.n_waypoints)
         P, S, W = self.n_paths, self.n_segments, self.n_waypoints
 
@@ -324,6 +326,11 @@ class ToolPaths:
         _capi.check(ctx._lib.nb2_result_from_poses(ctx._h, len(po) - 1, po.ctypes.data, len(so) - 1, so.ctypes.data,
                                                    poses.ctypes.data if len(poses) else None, C.byref(h)))
         return cls(ctx, h)
+
+    def wait(self):
+        """block until every waypoint of a download = 2 result is in host memory (nb2_result_get)"""
+        v = _capi.ResultView()
+        _capi.check(self._lib.nb2_result_get(self._r, C.byref(v)))
 
     def free(self):
         if self._r:

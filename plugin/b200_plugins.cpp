@@ -330,9 +330,24 @@ struct StreamJob
   Device::Resident content;
   bool hit = false;
 
+  std::atomic<long long> ns_cloud{ 0 }, ns_tri{ 0 };  // NOETHER_B200_TRACE: time the staging threads spent in the callbacks
+  bool timed = false;
+  struct Lap
+  {
+    std::atomic<long long>* acc;
+    std::chrono::steady_clock::time_point t0;
+    Lap(std::atomic<long long>* a) : acc(a), t0(a ? std::chrono::steady_clock::now() : std::chrono::steady_clock::time_point()) {}
+    ~Lap()
+    {
+      if (acc)
+        acc->fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+    }
+  };
+
   static int cloud(void* user, std::uint64_t first, std::uint64_t count, void* dst)
   {
     StreamJob& j = *static_cast<StreamJob*>(user);
+    Lap lap(j.timed ? &j.ns_cloud : nullptr);
     constexpr std::uint64_t kSeedXyz = 0x78797a21ull, kSeedNrm = 0x6e726d21ull;
     const std::uint8_t* p = j.mesh->cloud.data.data() + first * j.in_step;
     std::uint8_t* o = static_cast<std::uint8_t*>(dst);
@@ -367,6 +382,7 @@ struct StreamJob
   static int triangles(void* user, std::uint64_t first, std::uint64_t count, std::uint32_t* dst)
   {
     StreamJob& j = *static_cast<StreamJob*>(user);
+    Lap lap(j.timed ? &j.ns_tri : nullptr);
     const auto& polygons = j.mesh->polygons;
     for (std::uint64_t b = first; b < first + count; b += kHashChunk)
     {
@@ -468,6 +484,7 @@ void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals
   st.triangles = &StreamJob::triangles;
   st.accept = &StreamJob::accept;
   st.user = &job;
+  job.timed = std::getenv("NOETHER_B200_TRACE") != nullptr;
   int committed = 0;
   const Device::Resident before = dev.resident;
   dev.resident.valid = false;
@@ -479,13 +496,16 @@ void ensureResident(Device& dev, const pcl::PolygonMesh& mesh, bool need_normals
   Device::check(rc);
   dev.resident = committed ? job.content : before;
   trace.lap(committed ? "streamed to the device" : "streamed, already resident");
+  if (job.timed)
+    std::fprintf(stderr, "[noether_b200] ensureResident: staging threads spent %.1f ms on the cloud, %.1f ms on the triangles (summed over threads)\n",
+                 job.ns_cloud.load() * 1e-6, job.ns_tri.load() * 1e-6);
 }
 
 /** SoA result -> noether::ToolPaths (core/types.h:31-50): nested vectors of Eigen::Isometry3d */
 noether::ToolPaths toToolPaths(const nb2_result* r)
 {
   nb2_result_view v{};
-  Device::check(nb2_result_get(r, &v));
+  Device::check(nb2_result_layout(r, &v));  // (positions / normals may still be arriving: download = 2)
   // Eigen::Isometry3d is exactly its 4x4 double matrix, column-major, last row 0 0 0 1 — the layout the library writes —
   // so every segment's storage is handed over and filled in place (in parallel, no intermediate copy)
   static_assert(sizeof(Eigen::Isometry3d) == 16 * sizeof(double), "Isometry3d is not a bare 4x4 double matrix");
@@ -626,6 +646,7 @@ protected:
     prm.bidirectional = bidirectional_ ? 1 : 0;
     prm.raster_post_ops = 0;  // RasterPlanner::plan applies the reference's own modifiers after planImpl
     prm.emit_edges = 0;
+    prm.download = 2;         // the waypoints arrive while the ToolPaths containers are sized and filled
     fillLegacy(prm);
 
     // foreign generators run first: they may use the device themselves (through this library or not)

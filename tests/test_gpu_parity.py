@@ -785,3 +785,43 @@ def test_aabb_center_origin_matches_oracle(ctx, orc, ply_mesh):
         assert np.array_equal(got, orc.aabb_center_origin(blob.xyz()))
     gen = nb.Factory(ctx).create_origin_generator({"name": "AABBCenter"})
     assert np.array_equal(gen.generate(ply_mesh), orc.aabb_center_origin(ply_mesh.xyz()))
+
+
+@pytest.mark.gpu
+def test_lazy_download_equals_ordinary_download():
+    """download = 2 (positions / normals land behind nb2_plan, nb2_result_poses expands them as they arrive) gives the very
+    poses, positions and normals of the ordinary download — on a plan large enough to travel in chunks, from pageable host
+    arrays through the staging ring with the cloud compacted (NB2_MESH_GEOMETRY_ONLY)"""
+    import ctypes as C
+
+    import noether_b200 as nb
+    from noether_b200 import _capi, meshes
+    ctx = nb.Context(0)
+    xyz, tri = meshes.wavy(640, 500)
+    blob0 = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    ctx.upload(blob0, force=True)
+    nrm = ctx.normals_from_mesh_faces(xyz.shape[0])
+    blob = meshes.pack_blob(xyz, nrm, tri, "PointNormal")
+    t32 = np.ascontiguousarray(tri.reshape(-1), np.uint32)
+    prm = _capi.PlanParams()
+    _capi.load().nb2_plan_params_default(prm)
+    prm.line_spacing = 0.002
+    prm.raster_post_ops = 0
+    prm.emit_edges = 0
+    out = {}
+    for mode, flags in ((1, 0), (2, _capi.NB2_MESH_GEOMETRY_ONLY)):
+        prm.download = mode
+        mv = _capi.MeshView(blob.data.ctypes.data, xyz.shape[0], blob.point_step, blob.off_xyz, blob.off_normal, flags,
+                            t32.ctypes.data, tri.shape[0])
+        r = C.c_void_p()
+        _capi.check(ctx._lib.nb2_plan_mesh(ctx._h, C.byref(mv), C.byref(prm), C.byref(r)))
+        from noether_b200.planner import ToolPaths
+        tp = ToolPaths(ctx, r, layout_only=mode == 2)
+        assert tp.n_waypoints >= 1 << 18, "the plan is too small to be downloaded in chunks"
+        poses = tp.poses()       # (mode 2: consumes the chunks as they land)
+        tp.wait()
+        out[mode] = (poses, tp.positions.copy(), tp.normals.copy(), tp.segment_offsets.copy(), tp.path_plane.copy())
+        tp.free()
+    for a, b in zip(out[1], out[2]):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    ctx.close()
