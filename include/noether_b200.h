@@ -241,6 +241,17 @@ int nb2_mesh_record_layout(const nb2_context* ctx, uint32_t* point_step, uint32_
  * part of the cloud as well).
  * ------------------------------------------------------------------------------------------------------------------ */
 int nb2_euclidean_cluster_labels(nb2_context* ctx, double tolerance, uint32_t* labels, uint64_t capacity_labels);
+
+/* NormalEstimationPCLMeshModifier::modify (noether_tpp/src/mesh_modifiers/normal_estimation_pcl.cpp:15-50):
+ * pcl::NormalEstimation<PointXYZ, Normal> with setRadiusSearch(radius) and setViewPoint(vx, vy, vz) on the resident cloud.
+ * One k-d tree radius search per point in the reference; here a uniform grid of cells of the radius and one thread per
+ * point: FLANN's float distance test decides the neighbours (the same sets), their shifted second moments are summed in
+ * double, pcl::eigen33's closed-form solver gives the eigenvector of the smallest eigenvalue, flipped towards the viewpoint.
+ * normals: float[3 * n_points], NaN where the search returns fewer than 3 points; curvature: float[n_points] (may be
+ * NULL) = |lambda_0 / trace|.  The estimated normals become the resident normals (nb2_plan may follow).  Agreement with
+ * the reference is a tolerance on the angle (sums in double instead of float, CUDA's atan2f / cosf / sinf), not bit
+ * equality.  A radius that is large against the point spacing is refused like nb2_euclidean_cluster_labels' tolerance. */
+int nb2_normal_estimation_pcl(nb2_context* ctx, double radius, double vx, double vy, double vz, float* normals, float* curvature);
 /* Host only (no context): the order pcl::EuclideanClusterExtraction::extract leaves its clusters in —
  * std::sort(clusters.rbegin(), clusters.rend(), comparePointClusters), largest first, equal sizes as the library's
  * introsort leaves them — for clusters given in order of discovery (ascending label) with these sizes, after the size

@@ -6,7 +6,7 @@ interface used by tests and the benchmark; it only ever calls the C ABI.
 """
 from . import _capi, meshes  # noqa: F401
 from .planner import (AABBCenterOriginGenerator, CentroidOriginGenerator, Context, Factory, FixedDirectionGenerator,  # noqa: F401
-                      FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, FaceMidpointSubdivisionMeshModifier,
+                      FixedOriginGenerator, NormalsFromMeshFacesMeshModifier, NormalEstimationPCLMeshModifier, FaceMidpointSubdivisionMeshModifier,
                       FaceSubdivisionByAreaMeshModifier, EuclideanClusteringMeshModifier, cluster_order, cluster_submeshes, MultiToolPathPlanner, PlaneSlicerLegacyRasterPlanner,
                       PCARotatedDirectionGenerator, PlaneSlicerRasterPlanner, PrincipalAxisDirectionGenerator, ToolPaths,
                       default_context, make_lattice,

@@ -36,7 +36,7 @@ NB2_UNIQUE_ID_BYTES = 128
 DECLARED_SYMBOLS = [
     "nb2_abi_version", "nb2_last_error", "nb2_context_create", "nb2_context_destroy", "nb2_context_device",
     "nb2_mesh_upload", "nb2_mesh_upload_stream", "nb2_mesh_set_normals", "nb2_mesh_download", "nb2_mesh_pca", "nb2_principal_axis_direction",
-    "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_make_lattice", "nb2_eigen_solver_3f", "nb2_plan_params_default", "nb2_slice",
+    "nb2_centroid_origin", "nb2_pca_rotated_direction", "nb2_normals_from_mesh_faces", "nb2_normal_estimation_pcl", "nb2_make_lattice", "nb2_eigen_solver_3f", "nb2_plan_params_default", "nb2_slice",
     "nb2_plan", "nb2_plan_mesh", "nb2_last_lattice", "nb2_result_get", "nb2_result_layout", "nb2_result_poses", "nb2_result_poses_segments", "nb2_expand_poses", "nb2_result_free", "nb2_last_timings",
     "nb2_kernel_launches", "nb2_last_plan_general_path_planes", "nb2_link_profile", "nb2_last_plan_span", "nb2_timer_start", "nb2_timer_stop", "nb2_comm_unique_id", "nb2_comm_init",
     "nb2_result_gather", "nb2_mesh_upload_sharded", "nb2_comm_destroy",

@@ -1736,6 +1736,49 @@ int nb2_euclidean_cluster_labels(nb2_context* c, double tolerance, uint32_t* lab
   NB2_API_END
 }
 
+int nb2_normal_estimation_pcl(nb2_context* c, double radius, double vx, double vy, double vz, float* normals, float* curvature)
+{
+  NB2_API_BEGIN
+  if (!c)
+    fail(NB2_ERR_INVALID_ARGUMENT, "context is NULL");
+  if (!(radius == radius))
+    fail(NB2_ERR_INVALID_ARGUMENT, "NormalEstimationPCL: radius is NaN");
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceGuard g(c->device);
+  requireMesh(c);
+  const uint64_t V = c->V;
+  ensureHostPca(c);  // the AABB of the cloud (and the deferred checks of a device-adopted mesh)
+  clu::GridParams grid{};
+  // a radius search with radius <= 0 finds nothing, not even the query point: every normal is NaN.  The grid is then built
+  // with a nominal cell (nothing passes the distance test: r2 = 0 and the test is strict)
+  const double r = radius > 0.0 ? radius : 0.0;
+  grid.r2 = static_cast<float>(r * r);
+  double extent = 0.0;
+  for (int i = 0; i < 3; ++i)
+    extent = std::max(extent, static_cast<double>(c->pca.aabb_max[i]) - static_cast<double>(c->pca.aabb_min[i]));
+  grid.h = r > 0.0 ? r * (1.0 + 1.0 / 1024.0) : std::max(extent, 1.0);
+  for (int i = 0; i < 3; ++i)
+  {
+    grid.mn[i] = static_cast<double>(c->pca.aabb_min[i]) - grid.h;  // one spare cell below the cloud
+    const double cells = (static_cast<double>(c->pca.aabb_max[i]) - grid.mn[i]) / grid.h;
+    if (!(cells < clu::kMaxCells))
+      fail(NB2_ERR_INVALID_ARGUMENT, "NormalEstimationPCL: radius " + std::to_string(radius) + " is less than 2^-40 of the extent of the cloud");
+  }
+  const float vp[3] = { static_cast<float>(vx), static_cast<float>(vy), static_cast<float>(vz) };  // setViewPoint takes floats
+  if (!(r > 0.0))
+  {
+    // (no search at all: V NaN normals; the resident mesh keeps the normals it had)
+    const float nan = std::nanf("");
+    if (normals)
+      std::fill(normals, normals + 3 * V, nan);
+    if (curvature)
+      std::fill(curvature, curvature + V, nan);
+    return NB2_OK;
+  }
+  launchNormalEstimationPcl(c, grid, 4e11, vp, normals, curvature);
+  NB2_API_END
+}
+
 int nb2_mesh_upload(nb2_context* c, const nb2_mesh_view* m)
 {
   NB2_API_BEGIN

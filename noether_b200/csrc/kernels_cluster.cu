@@ -12,6 +12,7 @@
 // the C ABI (plugin shim / Python mirror), where the meshes have to be materialised anyway.
 #include "nb2_internal.h"
 #include "cluster_ops.h"
+#include "pcl_normal_ops.h"
 
 #include <algorithm>
 
@@ -145,6 +146,58 @@ __global__ void __launch_bounds__(256) k_clu_flatten(unsigned* parent, unsigned 
     label[p] = findRoot(parent, p);
 }
 
+/** NormalEstimationPCL (normal_estimation_pcl.cpp:15-50), one thread per point: the radius search over the 27 surrounding
+ *  cells (FLANN's float distance test, the query point included), the nine shifted sums in double, pcl_normal_ops.h for the
+ *  rest.  Fewer than three neighbours: NaN, as computePointNormal returns false. */
+__global__ void __launch_bounds__(256)
+    k_pcl_normals(GridParams g, const float4* __restrict__ pos, unsigned V, const unsigned long long* __restrict__ cell_key,
+                  const unsigned* __restrict__ cell_head, unsigned slot_mask, const unsigned* __restrict__ next, float vx, float vy,
+                  float vz, float4* __restrict__ nrm, float* __restrict__ curvature)
+{
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < V; p += stride)
+  {
+    const float4 P = __ldg(pos + p);
+    const long long c[3] = { cellCoord(g, 0, P.x), cellCoord(g, 1, P.y), cellCoord(g, 2, P.z) };
+    double S[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    unsigned k = 0;
+    for (long long dz = -1; dz <= 1; ++dz)
+      for (long long dy = -1; dy <= 1; ++dy)
+        for (long long dx = -1; dx <= 1; ++dx)
+        {
+          const unsigned s = findCellSlot(g, c[0] + dx, c[1] + dy, c[2] + dz, cell_key, slot_mask);
+          if (s == kNone)
+            continue;
+          for (unsigned q = cell_head[s]; q != kNone; q = next[q])
+          {
+            const float4 Q = __ldg(pos + q);
+            if (!isNeighbour(P.x, P.y, P.z, Q.x, Q.y, Q.z, g.r2))
+              continue;
+            // (float differences as computeMeanAndCovarianceMatrix forms them; their products are exact in double)
+            const double x = static_cast<double>(Q.x - P.x), y = static_cast<double>(Q.y - P.y), z = static_cast<double>(Q.z - P.z);
+            S[0] += x * x;
+            S[1] += x * y;
+            S[2] += x * z;
+            S[3] += y * y;
+            S[4] += y * z;
+            S[5] += z * z;
+            S[6] += x;
+            S[7] += y;
+            S[8] += z;
+            ++k;
+          }
+        }
+    float n[3] = { nanf(""), nanf(""), nanf("") }, curv = nanf("");
+    if (k >= 3u)
+    {
+      const float pp[3] = { P.x, P.y, P.z }, vp[3] = { vx, vy, vz };
+      pclne::normalFromSums(S, k, pp, vp, n, curv);
+    }
+    nrm[p] = make_float4(n[0], n[1], n[2], 0.f);
+    curvature[p] = curv;
+  }
+}
+
 inline int gridFor(unsigned long long n, const nb2_context* c)
 {
   const unsigned long long cap = static_cast<unsigned long long>(c->sm_count) * 16;
@@ -155,7 +208,9 @@ inline int gridFor(unsigned long long n, const nb2_context* c)
 /** labels of the resident cloud into `labels_host` (uint32[V]); `max_tests` bounds the chain steps of k_clu_link, counted
  *  exactly on the device before that kernel is launched (a skewed cloud — most points in a few cells — cannot slip under an
  *  average-occupancy estimate and turn the link pass quadratic) */
-void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host)
+/** C1 .. C1c: the cell table with every point chained to its cell, and the refusal of radii that are large against the point
+ *  spacing (`what` names the caller in the message).  Returns the number of slots of the table. */
+static uint64_t buildCellGrid(nb2_context* c, const clu::GridParams& g, double max_tests, const char* what)
 {
   const uint64_t V = c->V;
   cudaStream_t st = c->stream;
@@ -197,10 +252,20 @@ void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_te
   // one thread walks the chains of one point: beyond about a million steps that single walk takes a second
   constexpr unsigned long long kMaxStepsPerPoint = 1ull << 20;
   if (static_cast<double>(hw[0]) > max_tests || hw[1] > kMaxStepsPerPoint)
-    fail(NB2_ERR_INVALID_ARGUMENT, "EuclideanClustering: the tolerance is large against the point spacing (" + std::to_string(V) +
+    fail(NB2_ERR_INVALID_ARGUMENT, std::string(what) + ": the search radius is large against the point spacing (" + std::to_string(V) +
                                        " points in " + std::to_string(h[0]) + " grid cells, " + std::to_string(hw[0]) +
                                        " distance tests in all and " + std::to_string(hw[1]) +
                                        " for the busiest point); every radius search of the reference would return a large part of the cloud too");
+  return slots;
+}
+
+/** labels of the resident cloud into `labels_host` (uint32[V]) */
+void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host)
+{
+  const uint64_t V = c->V;
+  cudaStream_t st = c->stream;
+  const unsigned n = static_cast<unsigned>(V);
+  const uint64_t slots = buildCellGrid(c, g, max_tests, "EuclideanClustering");
   k_clu_link<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
                                            static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), c->cluParent.as<unsigned>());
   NB2_CUDA(cudaGetLastError());
@@ -209,6 +274,40 @@ void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_te
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
   NB2_CUDA(cudaMemcpyAsync(labels_host, c->cluLabel.ptr, sizeof(unsigned) * V, cudaMemcpyDeviceToHost, st));
+  NB2_CUDA(cudaStreamSynchronize(st));
+}
+
+/** NormalEstimationPCL on the resident cloud: the estimated normals become the resident normals (float4 SoA, as after
+ *  NormalsFromMeshFaces); packed copies go to the host (either may be NULL) */
+void launchNormalEstimationPcl(nb2_context* c, const clu::GridParams& g, double max_tests, const float viewpoint[3], float* normals_host,
+                               float* curvature_host)
+{
+  const uint64_t V = c->V;
+  cudaStream_t st = c->stream;
+  const unsigned n = static_cast<unsigned>(V);
+  c->timer.begin(st);
+  const uint64_t slots = buildCellGrid(c, g, max_tests, "NormalEstimationPCL");
+  c->timer.mark("cell grid", st);
+  c->nrm.ensure(sizeof(float4) * V);
+  c->cluLabel.ensure(sizeof(float) * V);  // (the clustering's label buffer holds the curvature)
+  k_pcl_normals<<<gridFor(V, c), 256, 0, st>>>(g, c->pos.as<float4>(), n, c->subKeys.as<unsigned long long>(), c->cluHead.as<unsigned>(),
+                                              static_cast<unsigned>(slots - 1), c->cluNext.as<unsigned>(), viewpoint[0], viewpoint[1],
+                                              viewpoint[2], c->nrm.as<float4>(), c->cluLabel.as<float>());
+  NB2_CUDA(cudaGetLastError());
+  ++c->launches;
+  c->timer.mark("radius search + normals", st);
+  c->nrm_base = c->nrm.as<uint8_t>();  // the estimated normals replace whatever the cloud carried
+  c->nrm_stride = 16;
+  c->has_normals = true;
+  if (normals_host)
+  {
+    c->outNrm.ensure(sizeof(float) * 3 * V);
+    launchPackOut(c, nullptr, c->outNrm.as<float>());
+    NB2_CUDA(cudaMemcpyAsync(normals_host, c->outNrm.ptr, sizeof(float) * 3 * V, cudaMemcpyDeviceToHost, st));
+  }
+  if (curvature_host)
+    NB2_CUDA(cudaMemcpyAsync(curvature_host, c->cluLabel.ptr, sizeof(float) * V, cudaMemcpyDeviceToHost, st));
+  c->timer.mark("d2h", st);
   NB2_CUDA(cudaStreamSynchronize(st));
 }
 }  // namespace nb2

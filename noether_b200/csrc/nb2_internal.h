@@ -391,6 +391,8 @@ namespace clu
 struct GridParams;
 }
 void launchClusterLabels(nb2_context* c, const clu::GridParams& g, double max_tests, uint32_t* labels_host);
+void launchNormalEstimationPcl(nb2_context* c, const clu::GridParams& g, double max_tests, const float viewpoint[3], float* normals_host,
+                               float* curvature_host);
 // single-pass decoupled look-back exclusive scan (kernels_normals.cu)
 void launchScanU32(nb2_context* c, const unsigned* in, unsigned* out, unsigned long long n);
 

@@ -175,6 +175,16 @@ class Context:
         _capi.check(self._lib.nb2_normals_from_mesh_faces(self._h, out.ctypes.data if download else None))
         return out
 
+    def normal_estimation_pcl(self, n_vertices: int, radius: float, viewpoint=(0.0, 0.0, 0.0)):
+        """nb2_normal_estimation_pcl on the resident cloud: (normals (n,3) float32 — NaN rows where the radius search finds
+        fewer than 3 points — and curvature (n,) float32); the estimated normals become the resident ones"""
+        nrm = np.zeros((n_vertices, 3), np.float32)
+        cur = np.zeros(n_vertices, np.float32)
+        _capi.check(self._lib.nb2_normal_estimation_pcl(self._h, C.c_double(radius), C.c_double(viewpoint[0]), C.c_double(viewpoint[1]),
+                                                        C.c_double(viewpoint[2]), nrm.ctypes.data_as(C.c_void_p),
+                                                        cur.ctypes.data_as(C.c_void_p)))
+        return nrm, cur
+
     # -- planning ---------------------------------------------------------------------------------------------
     def plan(self, params: _capi.PlanParams) -> "ToolPaths":
         r = C.c_void_p()
@@ -578,6 +588,30 @@ class NormalsFromMeshFacesMeshModifier:
         rec[:, 32:] = np.asarray(mesh.data).reshape(n, mesh.point_step)
         out = MeshBlob(data, n, step, 32 + mesh.off_xyz, 0, mesh.tri)
         return [out]
+
+
+class NormalEstimationPCLMeshModifier:
+    """normal_estimation_pcl.cpp:15-50 (alias NormalEstimationPCL, YAML keys radius, vx, vy, vz).  Returns [mesh] whose cloud is
+    concatenateFields(mesh.cloud, normals): the 32-byte pcl::Normal record (normal_x0 normal_y4 normal_z8 curvature16)
+    followed by the input's fields."""
+
+    def __init__(self, radius: float, vx: float = 0.0, vy: float = 0.0, vz: float = 0.0, context: Context | None = None):
+        self.radius, self.vx, self.vy, self.vz = float(radius), float(vx), float(vy), float(vz)
+        self._ctx = context
+
+    def modify(self, mesh: MeshBlob) -> list[MeshBlob]:
+        ctx = self._ctx or default_context()
+        ctx.upload(mesh)
+        normals, curvature = ctx.normal_estimation_pcl(mesh.n_vertices, self.radius, (self.vx, self.vy, self.vz))
+        ctx._mesh_key = None  # the resident normals are the estimated ones now, not the uploaded cloud's
+        n = mesh.n_vertices
+        step = 32 + mesh.point_step
+        data = np.zeros(n * step, np.uint8)
+        rec = data.reshape(n, step)
+        rec[:, 0:12] = normals.view(np.uint8).reshape(n, 12)
+        rec[:, 16:20] = curvature.view(np.uint8).reshape(n, 4)
+        rec[:, 32:] = np.asarray(mesh.data).reshape(n, mesh.point_step)
+        return [MeshBlob(data, n, step, 32 + mesh.off_xyz, 0, mesh.tri)]
 
 
 def cluster_order(sizes) -> np.ndarray:
@@ -991,6 +1025,9 @@ class Factory:
         name = _member(config, "name")
         if name == "NormalsFromMeshFaces":
             return NormalsFromMeshFacesMeshModifier(self._ctx)
+        if name == "NormalEstimationPCL":      # normal_estimation_pcl.cpp:67-75
+            return NormalEstimationPCLMeshModifier(float(_member(config, "radius")), float(_member(config, "vx")),
+                                                   float(_member(config, "vy")), float(_member(config, "vz")), self._ctx)
         if name == "FaceMidpointSubdivision":  # n_iterations is read as a float and cast (face_subdivision_modifier.cpp:357)
             return FaceMidpointSubdivisionMeshModifier(int(float(_member(config, "n_iterations"))), self._ctx)
         if name == "EuclideanClustering":      # euclidean_clustering_modifier.cpp:79-85

@@ -253,6 +253,22 @@ def make_lattice(p: Pca, cut_direction, cut_origin, line_spacing: float, bidirec
     return L
 
 
+def normal_estimation_pcl(xyz, radius, viewpoint=(0.0, 0.0, 0.0)):
+    """NormalEstimationPCLMeshModifier (normal_estimation_pcl.cpp:15-50): (normals (n,3) float32 with NaN rows where a radius
+    search returns fewer than 3 points, curvature (n,) float32, neighbour counts (n,) uint32)"""
+    a, ap = _f32(xyz)
+    n = a.shape[0]
+    nrm = np.zeros((n, 3), np.float32)
+    cur = np.zeros(n, np.float32)
+    cnt = np.zeros(n, np.uint32)
+    L = lib()
+    L.orc_normal_estimation_pcl.argtypes = [C.POINTER(C.c_float), C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    _check(L.orc_normal_estimation_pcl(ap, n, float(radius), float(viewpoint[0]), float(viewpoint[1]), float(viewpoint[2]),
+                                       nrm.ctypes.data, cur.ctypes.data, cnt.ctypes.data))
+    return nrm, cur, cnt
+
+
 def normals_from_mesh_faces(xyz, tri) -> np.ndarray:
     a, ap = _f32(xyz)
     t, tp = _u32(tri)

@@ -201,6 +201,13 @@ void orc_cluster_info(const void* h, uint64_t k, uint64_t out[5]); /* cluster si
 void orc_cluster_export(const void* h, uint64_t k, uint32_t* indices, uint8_t* cloud, uint32_t* tri); /* any may be NULL */
 void orc_clusters_free(void* h);
 
+/* ---- f4': NormalEstimationPCLMeshModifier::modify (normal_estimation_pcl.cpp:15-50; pcl::NormalEstimation with a radius search,
+ *      computeMeanAndCovarianceMatrix, pcl::eigen33, flipNormalTowardsViewpoint restated in oracle_normals_pcl.cpp).
+ *      normals float[3 * n] (NaN where a point has fewer than 3 neighbours), curvature float[n] or NULL, neighbour_count
+ *      uint32[n] or NULL (the size of every radius search, the query point included) ---- */
+int orc_normal_estimation_pcl(const float* xyz, uint64_t n_points, double radius, double vx, double vy, double vz, float* normals,
+                              float* curvature, uint32_t* neighbour_count);
+
 /* ---- restated test fixtures ---- */
 /* createRandomTransform(translation_limit, rotation_limit): tool_path_planner_utest.cpp:32-46 (std::mt19937(0)) */
 void orc_fixture_random_transform(double translation_limit, double rotation_limit, double out16[16]);

@@ -715,6 +715,51 @@ protected:
 // ---------------------------------------------------------------------------------------------------------------------
 // mesh modifier
 // ---------------------------------------------------------------------------------------------------------------------
+/** The output of the normal-producing mesh modifiers: the input's header and polygons and concatenateFields(mesh.cloud,
+ *  normals) — what pcl::toPCLPointCloud2(pcl::PointCloud<pcl::Normal>) yields (32-byte points: normal_x/y/z at 0/4/8,
+ *  curvature at 16, zero padding) in front of the input's fields (normals_from_mesh_faces_modifier.cpp:34-45,
+ *  normal_estimation_pcl.cpp:36-47).  curvature may be NULL (zero, as NormalsFromMeshFaces leaves it). */
+std::vector<pcl::PolygonMesh> withNormalRecords(const pcl::PolygonMesh& mesh, const float* normals, const float* curvature)
+{
+  const std::size_t n = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+  pcl::PCLPointCloud2 normals_pc2;
+  normals_pc2.header = mesh.cloud.header;
+  normals_pc2.width = mesh.cloud.width;
+  normals_pc2.height = mesh.cloud.height;
+  normals_pc2.is_bigendian = false;
+  normals_pc2.is_dense = true;
+  normals_pc2.point_step = 32;
+  normals_pc2.row_step = 32 * mesh.cloud.width;
+  const char* names[4] = { "normal_x", "normal_y", "normal_z", "curvature" };
+  const std::uint32_t offsets[4] = { 0, 4, 8, 16 };
+  for (int i = 0; i < 4; ++i)
+  {
+    pcl::PCLPointField f;
+    f.name = names[i];
+    f.offset = offsets[i];
+    f.datatype = pcl::PCLPointField::FLOAT32;
+    f.count = 1;
+    normals_pc2.fields.push_back(f);
+  }
+  normals_pc2.data.assign(32 * n, 0);
+  for (std::size_t i = 0; i < n; ++i)
+  {
+    std::memcpy(normals_pc2.data.data() + 32 * i, normals + 3 * i, 12);
+    if (curvature)
+      std::memcpy(normals_pc2.data.data() + 32 * i + 16, curvature + i, 4);
+  }
+  // the output mesh: the input's header and polygons (one deep copy of the polygon list: the interface returns meshes
+  // by value) and the concatenated cloud.  Moved, not copied, into the result (`return { output }` would copy the
+  // 10^7 polygon vectors a second time).
+  std::vector<pcl::PolygonMesh> result(1);
+  pcl::PolygonMesh& output = result.front();
+  output.header = mesh.header;
+  output.polygons = mesh.polygons;
+  if (!pcl::concatenateFields(mesh.cloud, normals_pc2, output.cloud))
+    throw std::runtime_error("Failed to concatenate normals into mesh vertex cloud");  // :42-43
+  return result;
+}
+
 /** NormalsFromMeshFacesMeshModifier (normals_from_mesh_faces_modifier.cpp:15-46): vertex normals on the GPU, then the
  *  reference's own field concatenation (pcl::concatenateFields) so the output cloud has the layout the reference
  *  produces: a 32-byte pcl::Normal record (normal_x, normal_y, normal_z, curvature) followed by the input's fields. */
@@ -737,41 +782,40 @@ public:
       dev.resident.h_normals = hashTriples(reinterpret_cast<const std::uint8_t*>(normals.data()), 12, n, 0x6e726d21ull);
       dev.resident.valid = true;
     }
-    // what pcl::toPCLPointCloud2(pcl::PointCloud<pcl::Normal>) yields: 32-byte points, zero curvature / padding
-    pcl::PCLPointCloud2 normals_pc2;
-    normals_pc2.header = mesh.cloud.header;
-    normals_pc2.width = mesh.cloud.width;
-    normals_pc2.height = mesh.cloud.height;
-    normals_pc2.is_bigendian = false;
-    normals_pc2.is_dense = true;
-    normals_pc2.point_step = 32;
-    normals_pc2.row_step = 32 * mesh.cloud.width;
-    const char* names[4] = { "normal_x", "normal_y", "normal_z", "curvature" };
-    const std::uint32_t offsets[4] = { 0, 4, 8, 16 };
-    for (int i = 0; i < 4; ++i)
-    {
-      pcl::PCLPointField f;
-      f.name = names[i];
-      f.offset = offsets[i];
-      f.datatype = pcl::PCLPointField::FLOAT32;
-      f.count = 1;
-      normals_pc2.fields.push_back(f);
-    }
-    normals_pc2.data.assign(32 * n, 0);
-    for (std::size_t i = 0; i < n; ++i)
-      std::memcpy(normals_pc2.data.data() + 32 * i, normals.data() + 3 * i, 12);
-
-    // the output mesh: the input's header and polygons (one deep copy of the polygon list: the interface returns meshes
-    // by value) and the concatenated cloud.  Moved, not copied, into the result (`return { output }` would copy the
-    // 10^7 polygon vectors a second time).
-    std::vector<pcl::PolygonMesh> result(1);
-    pcl::PolygonMesh& output = result.front();
-    output.header = mesh.header;
-    output.polygons = mesh.polygons;
-    if (!pcl::concatenateFields(mesh.cloud, normals_pc2, output.cloud))
-      throw std::runtime_error("Failed to concatenate normals into mesh vertex cloud");  // :42-43
-    return result;
+    return withNormalRecords(mesh, normals.data(), nullptr);
   }
+};
+
+/** NormalEstimationPCLMeshModifier (normal_estimation_pcl.cpp:15-50): pcl::NormalEstimation with a radius search and a view
+ *  point, one k-d tree search per point in the reference, on the GPU here (nb2_normal_estimation_pcl); the output cloud is the
+ *  reference's concatenation, curvature included. */
+class NormalEstimationPCLMeshModifier : public noether::MeshModifier
+{
+public:
+  NormalEstimationPCLMeshModifier(double radius, double vx, double vy, double vz) : radius_(radius), vx_(vx), vy_(vy), vz_(vz) {}
+  std::vector<pcl::PolygonMesh> modify(const pcl::PolygonMesh& mesh) const override final
+  {
+    const std::size_t n = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+    std::vector<float> normals(3 * n), curvature(n);
+    {
+      Device& dev = Device::instance();
+      std::lock_guard<std::mutex> lock(dev.mutex());
+      ensureResident(dev, mesh, false);
+      dev.resident.valid = false;
+      Device::check(nb2_normal_estimation_pcl(dev.ctx(), radius_, vx_, vy_, vz_, normals.data(), curvature.data()));
+      if (radius_ > 0.0)
+      {
+        // the context now holds this geometry with the estimated normals: the mesh returned below
+        dev.resident.has_normals = true;
+        dev.resident.h_normals = hashTriples(reinterpret_cast<const std::uint8_t*>(normals.data()), 12, n, 0x6e726d21ull);
+        dev.resident.valid = true;
+      }
+    }
+    return withNormalRecords(mesh, normals.data(), curvature.data());
+  }
+
+private:
+  double radius_, vx_, vy_, vz_;
 };
 
 /** Host side of EuclideanClusteringMeshModifier::modify, from the labels the device computed (label = smallest point index
@@ -1104,6 +1148,17 @@ struct Plugin_NormalsFromMeshFacesMeshModifier : public noether::Plugin<noether:
   }
 };
 
+/** NormalEstimationPCL: YAML keys radius, vx, vy, vz (normal_estimation_pcl.cpp:67-75) */
+struct Plugin_NormalEstimationPCLMeshModifier : public noether::Plugin<noether::MeshModifier>
+{
+  std::unique_ptr<noether::MeshModifier> create(const YAML::Node& config,
+                                                std::shared_ptr<const noether::Factory> /*factory*/) const override final
+  {
+    return std::make_unique<NormalEstimationPCLMeshModifier>(YAML::getMember<double>(config, "radius"), YAML::getMember<double>(config, "vx"),
+                                                             YAML::getMember<double>(config, "vy"), YAML::getMember<double>(config, "vz"));
+  }
+};
+
 /** EuclideanClustering: YAML keys tolerance, min_cluster_size, max_cluster_size (euclidean_clustering_modifier.cpp:79-85) */
 struct Plugin_EuclideanClusteringMeshModifier : public noether::Plugin<noether::MeshModifier>
 {
@@ -1303,6 +1358,7 @@ EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_MovingAverageOrientationSm
 EXPORT_TOOL_PATH_MODIFIER_PLUGIN(noether_b200::Plugin_CompoundToolPathModifier, CompoundToolPathModifier)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalsFromMeshFacesMeshModifier, NormalsFromMeshFaces)
 EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_EuclideanClusteringMeshModifier, EuclideanClustering)
+EXPORT_MESH_MODIFIER_PLUGIN(noether_b200::Plugin_NormalEstimationPCLMeshModifier, NormalEstimationPCL)
 /** test hook (tests/cpp/plugin_shim_test.cpp --cpu-only): the host side of EuclideanClustering without a device */
 extern "C" void noether_b200_cut_cluster_meshes(const pcl::PolygonMesh* mesh, const std::uint32_t* labels, int min_cluster_size,
                                                 int max_cluster_size, std::vector<pcl::PolygonMesh>* out)

@@ -355,6 +355,83 @@ void testNormalsFieldRetention(const noether::Factory& factory, const pcl::Polyg
   CHECK(factory.createToolPathPlanner(pc)->plan(m).size() == 10);
 }
 
+/** NormalEstimationPCL by alias with the reference test's YAML (mesh_modifier_utest.cpp:26-30: radius 0.5, view point 0 0 10):
+ *  every input field retained, a curvature field added, every normal a unit vector towards the view point or NaN (a radius
+ *  search with fewer than three points), close to the file's own vertex normals on this smooth surface; the planner accepts
+ *  the result where the normals are finite */
+void testNormalEstimationPCL(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
+{
+  std::printf("[MeshModifier NormalEstimationPCL]\n");
+  YAML::Node config;
+  config["name"] = "NormalEstimationPCL";
+  config["radius"] = 0.5;
+  config["vx"] = 0.0;
+  config["vy"] = 0.0;
+  config["vz"] = 10.0;
+  std::shared_ptr<const noether::MeshModifier> mod = factory.createMeshModifier(config);
+  const std::vector<pcl::PolygonMesh> out = mod->modify(mesh);
+  CHECK(out.size() == 1);
+  if (out.empty())
+    return;
+  const pcl::PolygonMesh& m = out.front();
+  CHECK(m.polygons.size() == mesh.polygons.size());
+  CHECK(m.cloud.width * m.cloud.height == mesh.cloud.width * mesh.cloud.height);
+  for (const auto& f : mesh.cloud.fields)
+  {
+    bool found = false;
+    for (const auto& g : m.cloud.fields)
+      found = found || (g.name == f.name && g.datatype == f.datatype && g.count == f.count);
+    CHECK(found);
+  }
+  unsigned off_new = ~0u, off_old = 0, off_curv = ~0u, off_xyz = 0;
+  for (const auto& g : m.cloud.fields)
+  {
+    if (g.name == "normal_x")
+      off_new = g.offset;
+    if (g.name == "curvature")
+      off_curv = g.offset;
+    if (g.name == "x")
+      off_xyz = g.offset;
+  }
+  for (const auto& g : mesh.cloud.fields)
+    if (g.name == "normal_x")
+      off_old = g.offset;
+  CHECK(off_new == 0 && off_curv == 16);
+  const std::size_t n = static_cast<std::size_t>(mesh.cloud.width) * mesh.cloud.height;
+  std::size_t finite = 0, close = 0;
+  double worst = 1.0;
+  bool towards = true, curv_ok = true;
+  for (std::size_t i = 0; i < n; ++i)
+  {
+    float a[3], b[3], p[3], c;
+    std::memcpy(a, m.cloud.data.data() + i * m.cloud.point_step + off_new, 12);
+    std::memcpy(&c, m.cloud.data.data() + i * m.cloud.point_step + off_curv, 4);
+    std::memcpy(p, m.cloud.data.data() + i * m.cloud.point_step + off_xyz, 12);
+    std::memcpy(b, mesh.cloud.data.data() + i * mesh.cloud.point_step + off_old, 12);
+    if (std::isnan(a[0]))  // fewer than three neighbours (curvature NaN too), or neighbours on a line (eigenvector 0 / 0)
+    {
+      curv_ok = curv_ok && (std::isnan(c) || c >= 0.f);
+      continue;
+    }
+    ++finite;
+    const double na = std::sqrt(double(a[0]) * a[0] + double(a[1]) * a[1] + double(a[2]) * a[2]);
+    CHECK(std::abs(na - 1.0) < 1e-4);
+    towards = towards && (double(0 - p[0]) * a[0] + double(0 - p[1]) * a[1] + double(10 - p[2]) * a[2]) >= 0.0;
+    curv_ok = curv_ok && (std::isnan(c) || (c >= 0.f && c <= 1.0f));
+    const double nb = std::sqrt(double(b[0]) * b[0] + double(b[1]) * b[1] + double(b[2]) * b[2]);
+    const double cs = (double(a[0]) * b[0] + double(a[1]) * b[1] + double(a[2]) * b[2]) / (na * nb);
+    worst = std::min(worst, cs);
+    close += cs > 0.9;
+  }
+  // (this mesh is coarse against the radius: a third of the searches return fewer than three points, and some of the rest
+  //  three or four points nearly on a line, whose "plane" is arbitrary — in the reference as here)
+  std::printf("  %zu of %zu normals finite, %zu within 26 degrees of the file's normals, smallest cosine %.3f\n", finite, n, close, worst);
+  CHECK(finite > n / 2);
+  CHECK(towards);
+  CHECK(curv_ok);
+  CHECK(close > finite * 8 / 10);
+}
+
 void testGeneratorsAndErrors(const noether::Factory& factory, const pcl::PolygonMesh& mesh)
 {
   std::printf("[PrincipalAxis / Centroid / error behaviour]\n");
@@ -1093,7 +1170,7 @@ int main(int argc, char** argv)
   try
   {
     for (const char* alias : { "PlaneSlicer", "PlaneSlicerLegacy", "PrincipalAxis", "PCARotated", "Centroid", "NormalsFromMeshFaces",
-                                "FaceMidpointSubdivision", "FaceSubdivisionByArea", "EuclideanClustering" })
+                                "FaceMidpointSubdivision", "FaceSubdivisionByArea", "EuclideanClustering", "NormalEstimationPCL" })
       CHECK(dlsym(lib, alias) != nullptr);
     if (argc > 8 && std::string(argv[3]) == "--bench")  // --bench nx ny spacing steps warmup
       return benchPlanner(factory, static_cast<unsigned>(std::atoi(argv[4])), static_cast<unsigned>(std::atoi(argv[5])),
@@ -1110,6 +1187,7 @@ int main(int argc, char** argv)
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicer", false);
     testSemiPlanarMeshFile(factory, ply, "PlaneSlicerLegacy", true);
     testNormalsFieldRetention(factory, ply);
+    testNormalEstimationPCL(factory, ply);
     testFaceSubdivision(factory, ply);
     testGeneratorsAndErrors(factory, ply);
     testResidentMeshReuse(factory, ply);

@@ -1,0 +1,194 @@
+"""NormalEstimationPCLMeshModifier (normal_estimation_pcl.cpp:15-50).
+
+CPU: the oracle (oracle/oracle_normals_pcl.cpp — PCL 1.12's NormalEstimation restated) against known answers and against an
+independent float64 eigen-decomposition; the device's per-point arithmetic (pcl_normal_ops.h, replayed on the host by
+tests/cpp/pcl_normals_emulation.cpp) against the oracle.  GPU: nb2_normal_estimation_pcl against the oracle.
+
+Parity here is a tolerance, not bit equality (BASELINE.json north_star: normals within 1e-5 rad): the device sums the shifted
+moments in double where PCL sums them in float in the order of FLANN's sorted neighbour list, and uses CUDA's atan2f / cosf /
+sinf.  The angle is measured where it is well defined: points whose neighbourhood has a clear smallest eigenvalue."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_RAD = 1e-5
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def emu():
+    src = os.path.join(ROOT, "tests", "cpp", "pcl_normals_emulation.cpp")
+    out = os.path.join(ROOT, "tests", "cpp", "build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libpcl_normals_emulation.so")
+    deps = [src] + [os.path.join(ROOT, "noether_b200", "csrc", f) for f in ("cluster_ops.h", "pcl_normal_ops.h", "host_math.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", src, "-o", lib], check=True)
+    L = C.CDLL(lib)
+    L.emu_pcl_normals.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
+    return L
+
+
+def emu_normals(L, xyz, radius, vp, seed=1):
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    n = xyz.shape[0]
+    nrm, cur, cnt = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint32)
+    assert L.emu_pcl_normals(xyz.ctypes.data, n, radius, vp[0], vp[1], vp[2], seed, nrm.ctypes.data, cur.ctypes.data, cnt.ctypes.data) == 0
+    return nrm, cur, cnt
+
+
+def angles(a, b):
+    """angle between corresponding rows (rad), NaN rows of both -> 0"""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    both_nan = np.isnan(a64).any(1) & np.isnan(b64).any(1)
+    cr = np.linalg.norm(np.cross(a64, b64), axis=1)
+    dt = (a64 * b64).sum(1)
+    ang = np.arctan2(cr, dt)
+    ang[both_nan] = 0.0
+    return ang
+
+
+def well_conditioned(xyz, radius, min_gap=0.05):
+    """points whose neighbourhood covariance has a smallest eigenvalue clearly separated from the middle one (the eigenvector
+    is then stable under the float noise of either implementation), from an independent float64 computation"""
+    x = xyz.astype(np.float64)
+    n = x.shape[0]
+    ok = np.zeros(n, bool)
+    gap = np.zeros(n)
+    ref = np.full((n, 3), np.nan)
+    r2 = np.float32(radius * radius)
+    x32 = xyz.astype(np.float32)
+    for i in range(n):
+        d = x32 - x32[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]      # FLANN's float accumulation
+        nb = np.nonzero(d2 < r2)[0]
+        if nb.size < 3:
+            continue
+        c = np.cov(x[nb].T, bias=True)
+        w, v = np.linalg.eigh(c)
+        ref[i] = v[:, 0]
+        gap[i] = (w[1] - w[0]) / max(w[2], 1e-300)
+        ok[i] = gap[i] > min_gap
+    return ok, ref, gap
+
+
+def tolerance(gap):
+    """1e-5 rad where the smallest eigenvalue is well separated (surfaces: the case the tolerance is stated for); the angle
+    between the eigenvectors of two matrices that differ by float noise grows as 1 / gap, and so does the allowance"""
+    return TOL_RAD / np.clip(gap, 1e-12, 1.0)
+
+
+def test_oracle_known_answers(orc):
+    # a flat grid: normal +-z towards the viewpoint, curvature 0; corners of a coarse grid with a small radius: NaN
+    g = np.stack(np.meshgrid(np.arange(12) * 0.1, np.arange(9) * 0.1, indexing="ij"), -1).reshape(-1, 2)
+    xyz = np.concatenate([g, np.zeros((g.shape[0], 1))], 1).astype(np.float32)
+    for vz, sign in ((10.0, 1.0), (-10.0, -1.0)):
+        n, c, k = orc.normal_estimation_pcl(xyz, 0.25, (0.0, 0.0, vz))
+        assert not np.isnan(n).any()
+        assert np.allclose(n, [0, 0, sign], atol=1e-6) and np.allclose(c, 0, atol=1e-6)
+    # neighbour counts against an all-pairs float scan, the query point included
+    d = xyz[:, None, :] - xyz[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    assert np.array_equal(k, (d2 < np.float32(0.25 * 0.25)).sum(1).astype(np.uint32))
+    # radius below the grid step: every search returns the query point alone -> NaN everywhere; radius <= 0 likewise
+    for r in (0.05, 0.0, -1.0):
+        n, c, k = orc.normal_estimation_pcl(xyz, r, (0, 0, 10))
+        assert np.isnan(n).all() and np.isnan(c).all() and k.max() <= 1
+    # exactly on the radius: FLANN's test is strict (0.1f * 0.1f accumulates to the float of 0.01 or not — the oracle and the
+    # all-pairs scan above use the same float arithmetic, which is the point); two neighbours only: still NaN (< 3)
+    line = np.array([[0, 0, 0], [0.1, 0, 0], [5, 5, 5]], np.float32)
+    n, c, k = orc.normal_estimation_pcl(line, 0.15, (0, 0, 10))
+    assert np.isnan(n).all() and list(k) == [2, 2, 1]
+
+
+def test_oracle_against_float64_eigenvectors(orc):
+    from noether_b200 import meshes
+    xyz, _ = meshes.wavy(40, 32)
+    radius = 0.07
+    n, c, k = orc.normal_estimation_pcl(xyz, radius, (0.0, 0.0, 10.0))
+    ok, ref, _ = well_conditioned(xyz, radius)
+    assert ok.sum() > 0.9 * xyz.shape[0]
+    # the normal is the float64 eigenvector up to sign and float noise; it points towards the viewpoint
+    cosang = np.abs((n[ok].astype(np.float64) * ref[ok]).sum(1))
+    assert np.degrees(np.arccos(np.clip(cosang, -1, 1))).max() < 0.05
+    to_vp = np.array([0.0, 0.0, 10.0]) - xyz[ok].astype(np.float64)
+    assert ((to_vp * n[ok]).sum(1) >= 0).all()
+    assert (c[ok] >= 0).all() and (c[ok] < 1.0 / 3.0 + 1e-6).all()
+
+
+def test_device_arithmetic_on_the_host_matches_the_oracle(orc, emu, golden_dir):
+    from noether_b200 import meshes
+    cases = []
+    xyz, _ = meshes.wavy(48, 40)
+    cases.append(("wavy", xyz, 0.06, (0.0, 0.0, 10.0)))
+    xyz2, _nrm, _sizes, _idx = orc.read_ply(open(os.path.join(golden_dir, "wavy_mesh_with_hole.ply"), "rb").read())
+    cases.append(("reference fixture, the reference test's parameters", xyz2, 0.5, (0.0, 0.0, 10.0)))
+    rng = np.random.default_rng(3)
+    cases.append(("scattered cloud", rng.uniform(-1, 1, (1500, 3)).astype(np.float32), 0.3, (3.0, -2.0, 1.0)))
+    for what, pts, radius, vp in cases:
+        no, co, ko = orc.normal_estimation_pcl(pts, radius, vp)
+        for seed in (1, 2):
+            ne, ce, ke = emu_normals(emu, pts, radius, vp, seed)
+            assert np.array_equal(ke, ko), what
+            # fewer than three neighbours: NaN on both sides.  (Three or more, but all on a line: the eigenvector is 0 / 0 or
+            # noise in either implementation — such points are not well conditioned and are left out below.)
+            assert np.isnan(ne[ko < 3]).all() and np.isnan(no[ko < 3]).all(), what
+            ok, _, gap = well_conditioned(pts, radius)
+            assert not np.isnan(ne[ok]).any() and not np.isnan(no[ok]).any(), what
+            # near (vp - p) . n = 0 the flip may go either way: compare up to sign there
+            a = np.minimum(angles(ne[ok], no[ok]), angles(-ne[ok], no[ok]))
+            assert (a <= tolerance(gap[ok])).all(), f"{what}: {a.max():.3e} rad"
+            flips = (np.sign((ne[ok] * no[ok]).sum(1)) < 0).sum()
+            assert flips <= max(1, ok.sum() // 1000), what
+            assert np.allclose(ce[ok], co[ok], rtol=1e-3, atol=1e-6), what
+
+
+@pytest.mark.gpu
+def test_gpu_matches_the_oracle(orc, golden_dir):
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    ctx = nb.Context(0)
+    cases = []
+    xyz, tri = meshes.wavy(300, 240)
+    cases.append(("wavy 300x240", xyz, tri, 0.012, (0.0, 0.0, 10.0)))
+    x2, t2 = meshes.permute(*meshes.cut_hole(*meshes.wavy(96, 80)), seed=4)
+    cases.append(("permuted, with a hole", x2, t2, 0.04, (0.0, 0.0, -5.0)))
+    x3, _n3, _s3, idx3 = orc.read_ply(open(os.path.join(golden_dir, "wavy_mesh_with_hole.ply"), "rb").read())
+    cases.append(("reference fixture, radius 0.5", x3, idx3.reshape(-1, 3), 0.5, (0.0, 0.0, 10.0)))
+    for what, pts, faces, radius, vp in cases:
+        blob = meshes.pack_blob(pts, None, faces, "PointXYZ")
+        out = nb.NormalEstimationPCLMeshModifier(radius, *vp, context=ctx).modify(blob)[0]
+        ng = out.normals()
+        cg = np.ndarray(shape=(pts.shape[0],), dtype=np.float32, buffer=out.data, offset=16, strides=(out.point_step,))
+        no, co, ko = orc.normal_estimation_pcl(pts, radius, vp)
+        assert np.isnan(ng[ko < 3]).all() and np.isnan(no[ko < 3]).all(), what
+        if pts.shape[0] <= 20000:
+            ok, _, gap = well_conditioned(pts, radius)
+            tol = tolerance(gap[ok])
+        else:   # (the all-pairs conditioning check is quadratic: a smooth height field sampled this densely is well conditioned)
+            ok = ko >= 6
+            tol = TOL_RAD
+        assert not np.isnan(ng[ok]).any() and not np.isnan(no[ok]).any(), what
+        a = np.minimum(angles(ng[ok], no[ok]), angles(-ng[ok], no[ok]))
+        assert (a <= tol).all(), f"{what}: {a.max():.3e} rad"
+        assert (np.sign((ng[ok] * no[ok]).sum(1)) < 0).sum() <= max(1, int(ok.sum()) // 1000), what
+        assert np.allclose(cg[ok], co[ok], rtol=1e-3, atol=1e-6), what
+        # the record layout: pcl::Normal first, then the input's fields, positions untouched
+        assert out.point_step == 32 + blob.point_step and out.off_normal == 0 and out.off_xyz == 32
+        assert np.array_equal(out.xyz(), pts)
+    # radius <= 0: nothing found, every normal NaN
+    blob = meshes.pack_blob(xyz, None, tri, "PointXYZ")
+    out = nb.NormalEstimationPCLMeshModifier(0.0, context=ctx).modify(blob)[0]
+    assert np.isnan(out.normals()).all()
+    ctx.close()
