@@ -47,16 +47,21 @@ class Context:
             pass
 
     # -- mesh -------------------------------------------------------------------------------------------------
-    def upload(self, mesh: MeshBlob, force: bool = False, sharded: bool = False):
+    def upload(self, mesh: MeshBlob, force: bool = False, sharded: bool = False, geometry_only: bool = False):
         """nb2_mesh_upload; sharded=True (collective, after comm_init): every rank copies 1 / world of the bytes and the
-        shares are all-gathered over NVLink (nb2_mesh_upload_sharded)."""
+        shares are all-gathered over NVLink (nb2_mesh_upload_sharded).  geometry_only=True (NB2_MESH_GEOMETRY_ONLY): only
+        positions and normals will be used on the device, so the host cores compact the cloud to 12- / 24-byte records on
+        its way through the pinned staging ring (callers that work on whole records — the face subdivisions — leave it off)."""
+        # (a resident mesh serves every caller that needs positions and normals, compacted or not; callers that need whole
+        #  records force their upload)
         key = (id(mesh.data), id(mesh.tri), mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal)
         if not force and key == self._mesh_key:
             return
         self._mesh_key = None
         data = np.ascontiguousarray(mesh.data)
         tri = np.ascontiguousarray(mesh.tri, dtype=np.uint32)
-        mv = _capi.MeshView(data.ctypes.data, mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal, 0,
+        mv = _capi.MeshView(data.ctypes.data, mesh.n_vertices, mesh.point_step, mesh.off_xyz, mesh.off_normal,
+                            _capi.NB2_MESH_GEOMETRY_ONLY if geometry_only else 0,
                             tri.ctypes.data if tri.size else None, tri.shape[0])
         fn = self._lib.nb2_mesh_upload_sharded if sharded else self._lib.nb2_mesh_upload
         _capi.check(fn(self._h, C.byref(mv)))
@@ -517,7 +522,7 @@ class PlaneSlicerRasterPlanner:
 
     def plan(self, mesh: MeshBlob, shard_rank: int = 0, shard_count: int = 1, sharded_upload: bool = False) -> ToolPaths:
         ctx = self._ctx or default_context()
-        ctx.upload(mesh, sharded=sharded_upload)
+        ctx.upload(mesh, sharded=sharded_upload, geometry_only=not sharded_upload)
         p = self._params(mesh)
         p.shard_rank, p.shard_count = shard_rank, shard_count
         return ctx.plan(p)
