@@ -447,13 +447,14 @@ int nb2_result_modify(nb2_context* ctx, const nb2_result* in, const nb2_modifier
 int nb2_last_timings(const nb2_context* ctx, const char** names, float* ms, int capacity);
 /* Number of kernel launches issued by this context since creation. */
 uint64_t nb2_kernel_launches(const nb2_context* ctx);
-/* Diagnostics: lattice planes of the last nb2_plan / nb2_slice that the linker's second-generation fast path left to the
- * first-generation paths (a cut point with more than two line ends, a closed contour, inconsistently wound triangles, a
- * crowd of zero-length lines, a plane beyond the work area).  Same result either way; those paths are slower. */
+/* Diagnostics: lattice planes of the last nb2_plan / nb2_slice whose cut lines the linker's general path joined because no
+ * fast path took them (a cut point with more than two line ends, a closed contour, inconsistently wound triangles, a plane
+ * beyond the fast paths' work area).  Same result either way; the general path is slower. */
 uint64_t nb2_last_plan_general_path_planes(const nb2_context* ctx);
-/* Diagnostics: with NB2_LINK_PROFILE set in the environment the linking kernel sums, per phase of its fast path, the clock
- * cycles thread 0 of every CTA spent (9 phases: init, hashing, claim rounds, pairing + zero-length lines, pairing check
- * + splitters, walks, pointer jumping, chain heads + order, output); cycles[0..15] of the last plan, zeros otherwise. */
+/* Diagnostics: with NB2_LINK_PROFILE and NB2_LINK_GEN=2 set in the environment the linking kernel sums, per phase of its
+ * second-generation fast path, the clock cycles thread 0 of every CTA spent (9 phases: init, hashing, claim rounds, pairing
+ * + zero-length lines, pairing check + splitters, walks, pointer jumping, chain heads + order, output); cycles[0..15] of the
+ * last plan, zeros otherwise. */
 int nb2_link_profile(nb2_context* ctx, uint64_t cycles[16]);
 /* Device time of the last nb2_plan / nb2_plan_mesh on this context: from a CUDA event recorded on the context's stream at
  * the entry of the call (for nb2_plan_mesh: before the upload) to one recorded behind the plan's last slicing kernel —

@@ -446,7 +446,7 @@ struct LinkParams
   unsigned* overflow;    // bit 0: hit buffers too small (k_emit_hits), bit 1: a plane exceeds scratchHits
   unsigned fastHitCap;   // largest plane (in cut lines) whose second-generation work area fits the CTA's shared memory
   unsigned plainRounds;  // claim rounds with plain stores before the compare-and-swap loop takes what is left (>= 1)
-  unsigned* generalCount;  // planes the second-generation fast path declined (diagnostics)
+  unsigned* generalCount;  // planes linked by the general path, the specification, because no fast path took them (diagnostics)
   unsigned long long* phaseCycles;  // [16] diagnostics (NB2_LINK_PROFILE), normally null
   unsigned* done;        // CTAs that ran out of planes (the last one scans the per-plane counts)
   uint2* planePrefix;    // [nP + 1] {waypoints, segments} before each plane
@@ -1660,7 +1660,7 @@ __device__ void scanMetaBlock(const unsigned* planeMeta, long long nP, uint2* __
 }
 
 
-__global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
+__device__ __forceinline__ void linkPlanesBody(const LinkParams& Pin)
 {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ unsigned s_misc[kMiscWords];
@@ -1706,8 +1706,6 @@ __global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
     // The second-generation path declined (a cut point with more than two line ends, a closed contour, inconsistently
     // wound triangles, a crowd of zero-length lines, a plane beyond its work area): the first-generation paths take it
     __syncthreads();
-    if (threadIdx.x == 0)
-      atomicAdd(P.generalCount, 1u);
     if (n <= P.smemHitCap && linkPlaneFast(P, smem, kLocal, n, cap, s_misc))
     {
       // done
@@ -1715,6 +1713,8 @@ __global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
     else if (n <= P.smemHitCap)
     {
       __syncthreads();
+      if (threadIdx.x == 0)
+        atomicAdd(P.generalCount, 1u);  // (diagnostics: planes no fast path took)
       PlaneWork<uint16_t> W;
       W.eposBytes = 12ull * E;
       W.epos = reinterpret_cast<float*>(smem);
@@ -1732,6 +1732,8 @@ __global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
     else
     {
       __syncthreads();
+      if (threadIdx.x == 0)
+        atomicAdd(P.generalCount, 1u);
       uint8_t* g = P.scratch + P.scratchStride * blockIdx.x;
       PlaneWork<uint32_t> W;
       W.eposBytes = 32ull * E;  // 8 index arrays of 4 E bytes
@@ -1780,6 +1782,12 @@ __global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin)
   if (threadIdx.x == 0)
     P.reportSizes[15] = P.stamp;
 }
+
+/** second-generation path (NB2_LINK_GEN=2): two CTAs of 512 threads share an SM and hide each other's barriers */
+__global__ void __launch_bounds__(kLinkThreads, 2) k_link_planes(LinkParams Pin) { linkPlanesBody(Pin); }
+/** first-generation paths (the default): a plane gets the whole SM — 1024 threads, all of its shared memory — which also
+ *  gives the shortest latency per plane, all that counts for the slab of a sharded plan (fewer planes than SMs) */
+__global__ void __launch_bounds__(2 * kLinkThreads, 1) k_link_planes_wide(LinkParams Pin) { linkPlanesBody(Pin); }
 
 // =================================================================================================================
 // S6: waypoints
@@ -1964,8 +1972,22 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   const size_t per_sm = c->smem_per_sm ? c->smem_per_sm : (size_t(228) << 10);
   const size_t two_per_sm = per_sm / 2 - 1024 - 512;  // (1 KB reserved per CTA, static shared memory)
   const size_t optin = c->smem_optin > 2048 ? c->smem_optin - 2048 : 0;
+  // Which fast path, and with it the launch shape.  Measured on cfg3 (profiles/r02_summary.md), link time in us for the whole
+  // lattice / a half / a third / an eighth of it (the slabs of 1, 2, 3, 8 GPUs):
+  //   first generation, one 1024-thread CTA per SM with all its shared memory   222 / 137 / 107 /  45
+  //   second generation, two 512-thread CTAs per SM                             226 / 160 / 152 / 158
+  // The second generation's plane takes twice as long (more, cheaper phases) and only breaks even when two planes overlap on
+  // every SM, so the first generation is the default; NB2_LINK_GEN=2 selects the second (its phases are the ones
+  // tests/cpp/link_emulation.cpp replays on the host).
+  static const int link_gen = [] {
+    const char* e = std::getenv("NB2_LINK_GEN");
+    return e && std::atoi(e) == 2 ? 2 : 1;
+  }();
+  const bool wide = link_gen == 1;
   size_t smem_bytes = std::max<size_t>(link2::workBytes(n_hint), size_t(16) << 10);
-  if (smem_bytes > two_per_sm)
+  if (wide)
+    smem_bytes = optin;
+  else if (smem_bytes > two_per_sm)
   {
     // the margin must not cost the second CTA: when the last plan's largest plane fits two to an SM, that is the budget
     smem_bytes = link2::workBytes(n_last + 16) <= two_per_sm ? two_per_sm : std::min(smem_bytes, optin);
@@ -1973,11 +1995,29 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   smem_bytes = std::min(smem_bytes, optin);
   const unsigned fast_cap = largestPlane(smem_bytes, link2::kMaxLines, [](unsigned n) { return link2::workBytes(n); });
   const unsigned smem_cap = largestPlane(smem_bytes, 32767u, [](unsigned n) { return smemWorkBytes(n); });
-  NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   // (planes of a few hundred cut lines do not fill 512 threads: smaller CTAs, more of them per SM)
-  const int threads = n_hint >= 2048u ? kLinkThreads : kLinkThreads / 2;
+  const int threads = wide ? 2 * kLinkThreads : (n_hint >= 2048u ? kLinkThreads : kLinkThreads / 2);
+  // attribute and occupancy are asked for when the configuration changes, not at every launch (host time between the
+  // launches of a plan is what a sharded plan's short kernels cannot hide)
   int per_sm_ctas = 1;
-  NB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_link_planes, threads, smem_bytes));
+  if (c->link_cfg_threads != threads || c->link_cfg_smem != smem_bytes || c->link_cfg_wide != wide)
+  {
+    if (wide)
+    {
+      NB2_CUDA(cudaFuncSetAttribute(k_link_planes_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+      NB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_link_planes_wide, threads, smem_bytes));
+    }
+    else
+    {
+      NB2_CUDA(cudaFuncSetAttribute(k_link_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+      NB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_ctas, k_link_planes, threads, smem_bytes));
+    }
+    c->link_cfg_threads = threads;
+    c->link_cfg_smem = smem_bytes;
+    c->link_cfg_wide = wide;
+    c->link_cfg_ctas = per_sm_ctas;
+  }
+  per_sm_ctas = c->link_cfg_ctas;
   int grid = c->sm_count * std::max(1, per_sm_ctas);
   // global scratch of the first-generation paths: any plane may end up there
   const uint32_t scratch_n = std::max<uint32_t>(scratch_hits, n_hint);
@@ -2033,7 +2073,12 @@ void launchLinkPlanes(nb2_context* c, uint64_t hit_cap, uint32_t scratch_hits, c
   P.reportPlanes = report.planes;
   P.stamp = report.stamp;
 
-  k_link_planes<<<grid, threads, smem_bytes, c->stream>>>(P);
+  if (link_gen == 1)
+    P.fastHitCap = 0;  // no plane is offered to the second-generation path
+  if (wide)
+    k_link_planes_wide<<<grid, threads, smem_bytes, c->stream>>>(P);
+  else
+    k_link_planes<<<grid, threads, smem_bytes, c->stream>>>(P);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

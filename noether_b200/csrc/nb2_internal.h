@@ -216,6 +216,9 @@ struct nb2_context
   // capacities the post-count stage was last sized for (0 = not yet known: the first plan waits for its hit count)
   uint64_t hit_cap = 0;      // hits (triangle x plane)
   uint32_t scratch_hits = 0; // hits of the largest plane, when it exceeds what fits shared memory
+  int link_cfg_threads = 0, link_cfg_ctas = 1;  // launch configuration k_link_planes was last prepared for
+  size_t link_cfg_smem = 0;
+  bool link_cfg_wide = false;
   uint32_t last_general_planes = 0;  // planes of the last plan that the linker's second-generation fast path declined
   uint32_t grid_planes = 0, grid_nmax = 0;  // planes / largest plane of the last plan: launch geometry of k_waypoints
   // slicing workspace

@@ -825,3 +825,20 @@ def test_lazy_download_equals_ordinary_download():
     for a, b in zip(out[1], out[2]):
         assert a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
     ctx.close()
+
+
+def test_second_generation_linker_matches_oracle():
+    """NB2_LINK_GEN=2 (the linker's second-generation fast path: plain-store claim rounds, one dart per line, two CTAs per SM;
+    not the default since the first generation measured faster) must give the same bits: the slicing tests of this file once
+    more, in a process of their own with the variable set (the library reads it once per process)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.environ.get("NB2_LINK_GEN") == "2":
+        pytest.skip("already inside the second-generation run")
+    env = dict(os.environ, NB2_LINK_GEN="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "test_slice_ or test_plan_end_to_end or test_cfg2_properties or test_large_plane or test_fuzz_plans"],
+                       env=env, capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -44,6 +44,10 @@ def main():
     prm.line_spacing = spacing
     prm.emit_edges = emit_edges
     prm.download = 0
+    # NB2_PROFILE_SHARDS=N: the slab rank N // 2 of an N-way sharded plan plans on this GPU (what a rank of an N-GPU job runs)
+    shards = int(os.environ.get("NB2_PROFILE_SHARDS", "1"))
+    if shards > 1:
+        prm.shard_count, prm.shard_rank = shards, shards // 2
 
     def step():
         r = ctx.plan_mesh_raw(d_cloud.data_ptr(), V, blob.point_step, blob.off_xyz, blob.off_normal, d_tri.data_ptr(), F, prm)
