@@ -510,7 +510,7 @@ def main():
     P_planes = int(lat.num_planes)
     n_paths, n_segments, n_waypoints = totals if info.world == 1 else totals
     stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
-    kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h", "setup", "validate")}
+    kernel_stages = {k: v for k, v in stage_ms.items() if k not in ("h2d", "d2h", "setup", "validate") and not k.startswith("host:")}
     dominant = max(kernel_stages, key=kernel_stages.get)
     # per-rank quantities for the dominant kernel's launch on this rank
     W_rank, S_rank = counts[2], counts[1]

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <exception>
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <memory>
 #include <thread>
@@ -393,6 +394,7 @@ static void spanBegin(nb2_context* c)
     NB2_CUDA(cudaEventCreate(&c->ev_span_end));
   }
   c->span_valid = false;
+  c->host_t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   NB2_CUDA(cudaEventRecord(c->ev_span_begin, c->stream));
 }
 static void spanEnd(nb2_context* c)
@@ -401,6 +403,8 @@ static void spanEnd(nb2_context* c)
   {
     NB2_CUDA(cudaEventRecord(c->ev_span_end, c->stream));
     c->span_valid = true;
+    c->host_enqueue_ms = static_cast<float>(
+        1e3 * (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - c->host_t0));
   }
 }
 
@@ -2224,8 +2228,17 @@ int nb2_last_timings(const nb2_context* c, const char** names, float* ms, int ca
   if (!c || !names || !ms)
     return 0;
   // stages of the last upload, then the stages of the last plan / slice / normals call
-  const int n = c->timer_upload.collect(names, ms, capacity);
-  return n + c->timer.collect(names + n, ms + n, capacity - n);
+  int n = c->timer_upload.collect(names, ms, capacity);
+  n += c->timer.collect(names + n, ms + n, capacity - n);
+  // not a device stage: the host time from the entry of the last planning call to its last kernel launch (when the host
+  // falls behind the device — short kernels, a busy host — the difference shows up as gaps between the kernels)
+  if (n < capacity && c->span_valid)
+  {
+    names[n] = "host:enqueue";
+    ms[n] = c->host_enqueue_ms;
+    ++n;
+  }
+  return n;
 }
 
 uint64_t nb2_kernel_launches(const nb2_context* c) { return c ? c->launches : 0; }

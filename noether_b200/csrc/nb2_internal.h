@@ -304,6 +304,8 @@ struct nb2_context
   cudaEvent_t ev_span_begin = nullptr, ev_span_end = nullptr;  // nb2_last_plan_span: entry of the call .. end of its last kernel
   bool span_open = false;   // nb2_plan_mesh recorded the begin event: nb2_plan must not move it
   bool span_valid = false;
+  double host_t0 = 0.0;          // steady clock at the entry of the planning call ...
+  float host_enqueue_ms = 0.f;   // ... and how long the host took to enqueue the plan's launches (reported as "host:enqueue")
 
   // NCCL (dlopen'ed lazily)
   void* nccl_comm = nullptr;

@@ -70,7 +70,7 @@ def main():
     print(name, desc)
     print("paths/segments/waypoints", n)
     print("stages ms", {k: round(v, 4) for k, v in st.items()})
-    print("step ms (events) %.4f, sum of stages %.4f, library span %.4f" % (total, sum(st.values()), ctx.last_plan_span_ms()))
+    print("step ms (events) %.4f, sum of stages %.4f, library span %.4f" % (total, sum(v for k, v in st.items() if not k.startswith("host:")), ctx.last_plan_span_ms()))
     print("planes linked by the general path:", ctx.general_path_planes())
     if os.environ.get("NB2_LINK_PROFILE"):
         cyc = ctx.link_profile()
