@@ -1194,7 +1194,7 @@ static void readUploadVerdicts(nb2_context* c)
   c->checks_deferred = false;
   c->hostSmall.ensure(4096 + sizeof(FrameDev));
   auto* h = c->hostSmall.as<uint8_t>();
-  const int grid = static_cast<int>(std::min<uint64_t>((V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  const int grid = c->ingest_grid;  // (the total lies behind the block partials of the last ingest pass)
   NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
@@ -1325,7 +1325,7 @@ static void uploadPlyImpl(nb2_context* c, const void* file_image, uint64_t n_byt
   c->tri_checked = false;
   c->hostSmall.ensure(4096 + sizeof(FrameDev));
   auto* h = c->hostSmall.as<uint8_t>();
-  const int grid = static_cast<int>(std::min<uint64_t>((c->V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  const int grid = c->ingest_grid;  // (the total lies behind the block partials of the last ingest pass)
   NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(h + 512, c->counters.as<unsigned>() + 12, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaMemcpyAsync(h + 516, c->counters.as<unsigned>() + 16, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
@@ -1414,7 +1414,7 @@ static void uploadStlImpl(nb2_context* c, const void* file_image, uint64_t n_byt
   c->checks_deferred = false;
   c->hostSmall.ensure(4096 + sizeof(FrameDev));
   auto* h = c->hostSmall.as<uint8_t>();
-  const int grid = static_cast<int>(std::min<uint64_t>((c->V + kMomentThreads - 1) / kMomentThreads, kMomentBlocks));
+  const int grid = c->ingest_grid;  // (the total lies behind the block partials of the last ingest pass)
   NB2_CUDA(cudaMemcpyAsync(h, c->partials.as<MomentPartial>() + grid, sizeof(MomentPartial), cudaMemcpyDeviceToHost, c->stream));
   NB2_CUDA(cudaStreamSynchronize(c->stream));
   MomentPartial total;

@@ -13,6 +13,8 @@
 #include "frame_dev.cuh"
 #include "nb2_internal.h"
 
+#include <cstdlib>
+
 #include <cfloat>
 
 namespace nb2
@@ -84,6 +86,62 @@ __device__ void blockReducePartial(MomentPartial& p, MomentPartial* smem /*[warp
       t.non_finite += smem[w].non_finite;
     }
     p = t;
+  }
+}
+
+/** What follows the per-thread accumulation of either ingest kernel: block partial, and in the last block to finish the
+ *  fold of the block partials in index order and the PCA frame (framePcaStep) */
+__device__ __forceinline__ void momentsEpilogue(MomentPartial& p, MomentPartial* s_part, bool& s_last, MomentPartial* partials,
+                                                unsigned* done_counter, FrameDev* __restrict__ frame, const float* piv,
+                                                unsigned long long V)
+{
+  blockReducePartial(p, s_part);
+  if (threadIdx.x == 0)
+  {
+    partials[blockIdx.x] = p;
+    __threadfence();
+    const unsigned ticket = atomicAdd(done_counter, 1u);
+    s_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+
+  // final fold by the last block: thread t sums partials t, t + blockDim, ... then the same fixed tree
+  MomentPartial t;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+  {
+    t.s[i] = 0.0;
+    t.mn[i] = FLT_MAX;
+    t.mx[i] = -FLT_MAX;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    t.q[i] = 0.0;
+  t.non_finite = 0;
+  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+  {
+    const MomentPartial o = partials[b];
+    for (int i = 0; i < 3; ++i)
+    {
+      t.s[i] += o.s[i];
+      t.mn[i] = fminf(t.mn[i], o.mn[i]);
+      t.mx[i] = fmaxf(t.mx[i], o.mx[i]);
+    }
+    for (int i = 0; i < 6; ++i)
+      t.q[i] += o.q[i];
+    t.non_finite += o.non_finite;
+  }
+  __syncthreads();
+  blockReducePartial(t, s_part);
+  if (threadIdx.x == 0)
+  {
+    partials[gridDim.x] = t;  // slot after the block partials holds the total
+    *done_counter = 0;
+    // mean, covariance and eigen axes straight from the total: no kernel of its own for one thread of arithmetic
+    framedev::framePcaStep(t, piv, V, frame);
   }
 }
 
@@ -164,54 +222,146 @@ __global__ void __launch_bounds__(kMomentThreads)
     accumulate(v, __ldg(f), __ldg(f + 1), __ldg(f + 2));
   }
 
-  blockReducePartial(p, s_part);
-  if (threadIdx.x == 0)
-  {
-    partials[blockIdx.x] = p;
-    __threadfence();
-    const unsigned ticket = atomicAdd(done_counter, 1u);
-    s_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_last)
-    return;
-  __threadfence();
+  momentsEpilogue(p, s_part, s_last, partials, done_counter, frame, piv, V);
+}
 
-  // final fold by the last block: thread t sums partials t, t + blockDim, ... then the same fixed tree
-  MomentPartial t;
+// ---------------------------------------------------------------------------------------------------------------------
+// K0 with bulk asynchronous copies.  The cloud is one contiguous run of records, so the pass above is pure streaming; its
+// rate is set by how many bytes a CTA keeps in flight.  Here one thread per CTA keeps kIngestStages tiles of records on
+// their way into shared memory with cp.async.bulk (the TMA engine, SASS UBLKCP; completion counted in bytes on an mbarrier
+// per stage) while all threads take their coordinates out of the tile that has landed: no registers hold loads in flight,
+// and the refill of a stage is issued the moment its last reader has passed the block barrier.
+// Tile t belongs to CTA t mod grid and record r of a tile to thread r mod 256, in tile order: a fixed assignment, so the
+// moments are bit-reproducible from run to run (the order differs from the kernel above: the sums differ in their last
+// bits between the two kernels, not between runs).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kIngestStages = 4;
+
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarTryWait(unsigned long long* bar, unsigned parity)
+{
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(smemAddr(bar)), "r"(parity)
+               : "memory");
+  return ok != 0u;
+}
+/** global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the mbarrier */
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+               "l"(src), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kMomentThreads)
+    k_ingest_moments_tma(const uint8_t* __restrict__ blob, unsigned long long V, unsigned point_step, unsigned off_xyz,
+                         unsigned tile_records, float4* __restrict__ pos, MomentPartial* partials, unsigned* done_counter,
+                         FrameDev* __restrict__ frame)
+{
+  extern __shared__ __align__(128) uint8_t s_tiles[];  // kIngestStages tiles of tile_records * point_step bytes
+  __shared__ __align__(8) unsigned long long s_full[kIngestStages];
+  __shared__ MomentPartial s_part[kMomentThreads / 32];
+  __shared__ bool s_last;
+
+  const float* piv = reinterpret_cast<const float*>(blob + off_xyz);
+  const double px = piv[0], py = piv[1], pz = piv[2];
+  MomentPartial p;
 #pragma unroll
   for (int i = 0; i < 3; ++i)
   {
-    t.s[i] = 0.0;
-    t.mn[i] = FLT_MAX;
-    t.mx[i] = -FLT_MAX;
+    p.s[i] = 0.0;
+    p.mn[i] = FLT_MAX;
+    p.mx[i] = -FLT_MAX;
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i)
-    t.q[i] = 0.0;
-  t.non_finite = 0;
-  for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x)
-  {
-    const MomentPartial o = partials[b];
-    for (int i = 0; i < 3; ++i)
+    p.q[i] = 0.0;
+  p.non_finite = 0;
+  auto accumulate = [&](unsigned long long v, float x, float y, float z) {
+    pos[v] = make_float4(x, y, z, 0.f);
+    if (!(isfinite(x) && isfinite(y) && isfinite(z)))
     {
-      t.s[i] += o.s[i];
-      t.mn[i] = fminf(t.mn[i], o.mn[i]);
-      t.mx[i] = fmaxf(t.mx[i], o.mx[i]);
+      ++p.non_finite;
+      return;
     }
-    for (int i = 0; i < 6; ++i)
-      t.q[i] += o.q[i];
-    t.non_finite += o.non_finite;
-  }
-  __syncthreads();
-  blockReducePartial(t, s_part);
+    const double dx = static_cast<double>(x) - px, dy = static_cast<double>(y) - py, dz = static_cast<double>(z) - pz;
+    p.s[0] += dx;
+    p.s[1] += dy;
+    p.s[2] += dz;
+    p.q[0] += dx * dx;
+    p.q[1] += dx * dy;
+    p.q[2] += dx * dz;
+    p.q[3] += dy * dy;
+    p.q[4] += dy * dz;
+    p.q[5] += dz * dz;
+    p.mn[0] = fminf(p.mn[0], x);
+    p.mn[1] = fminf(p.mn[1], y);
+    p.mn[2] = fminf(p.mn[2], z);
+    p.mx[0] = fmaxf(p.mx[0], x);
+    p.mx[1] = fmaxf(p.mx[1], y);
+    p.mx[2] = fmaxf(p.mx[2], z);
+  };
+
+  const unsigned tile_bytes = tile_records * point_step;  // a multiple of 1024 (256 records of a multiple of 4 bytes)
+  const unsigned long long full_tiles = V / tile_records;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const unsigned long long mine = full_tiles > blockIdx.x ? (full_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0ull;
   if (threadIdx.x == 0)
   {
-    partials[gridDim.x] = t;  // slot after the block partials holds the total
-    *done_counter = 0;
-    // mean, covariance and eigen axes straight from the total: no kernel of its own for one thread of arithmetic
-    framedev::framePcaStep(t, piv, V, frame);
+    for (int s = 0; s < kIngestStages; ++s)
+      mbarInit(&s_full[s], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();
+  auto issue = [&](unsigned long long k) {  // thread 0: tile k of this CTA into stage k % kIngestStages
+    const int s = static_cast<int>(k % kIngestStages);
+    const unsigned long long t = blockIdx.x + k * gridDim.x;
+    mbarExpectTx(&s_full[s], tile_bytes);
+    bulkLoad(s_tiles + static_cast<size_t>(s) * tile_bytes, blob + t * tile_bytes, tile_bytes, &s_full[s]);
+  };
+  if (threadIdx.x == 0)
+    for (unsigned long long k = 0; k < mine && k < kIngestStages; ++k)
+      issue(k);
+  for (unsigned long long k = 0; k < mine; ++k)
+  {
+    const int s = static_cast<int>(k % kIngestStages);
+    const unsigned parity = static_cast<unsigned>((k / kIngestStages) & 1ull);
+    while (!mbarTryWait(&s_full[s], parity))
+    {
+    }
+    const unsigned long long v0 = (blockIdx.x + k * gridDim.x) * tile_records;
+    const uint8_t* tile = s_tiles + static_cast<size_t>(s) * tile_bytes + off_xyz;
+    for (unsigned r = threadIdx.x; r < tile_records; r += kMomentThreads)
+    {
+      const float* f = reinterpret_cast<const float*>(tile + static_cast<size_t>(r) * point_step);
+      accumulate(v0 + r, f[0], f[1], f[2]);
+    }
+    __syncthreads();  // every reader of stage s has passed
+    if (threadIdx.x == 0 && k + kIngestStages < mine)
+    {
+      // (the refill is written by the asynchronous proxy: order it behind the generic-proxy reads above)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(k + kIngestStages);
+    }
+  }
+  // the records behind the last full tile (fewer than a tile), by the CTA next in line, straight from global memory
+  if (blockIdx.x == full_tiles % gridDim.x)
+    for (unsigned long long v = full_tiles * tile_records + threadIdx.x; v < V; v += kMomentThreads)
+    {
+      const float* f = reinterpret_cast<const float*>(blob + v * point_step + off_xyz);
+      accumulate(v, __ldg(f), __ldg(f + 1), __ldg(f + 2));
+    }
+  momentsEpilogue(p, s_part, s_last, partials, done_counter, frame, piv, V);
 }
 
 /** Monotone map float -> unsigned (a < b  <=>  orderedBits(a) < orderedBits(b)), and back */
@@ -403,10 +553,42 @@ void launchIngestMoments(nb2_context* c, uint32_t point_step, uint32_t off_xyz, 
     if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess)
       cudaGetLastError();
   }
-  k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
-                                                           c->pos.as<float4>(),
-                                                           c->partials.as<MomentPartial>(), c->counters.as<unsigned>(),
-                                                           c->frame.as<FrameDev>());
+  // bulk-copy staging (k_ingest_moments_tma) when asked for, the records can travel as 16-byte-aligned tiles and there are
+  // enough of them to fill the pipeline; the plain kernel otherwise
+  // Measured on cfg3 (profiles/r02_summary.md): 60 us either way — the pass already streams at 4.6 TB/s under ncu and the
+  // rest is its serial epilogue, so loads in flight are not what bounds it.  The bulk-copy variant is therefore opt-in
+  // (NB2_INGEST_TMA=1); the plain kernel's summation order, which does not depend on the record layout, stays the default.
+  static const bool tma_on = [] {
+    const char* e = std::getenv("NB2_INGEST_TMA");
+    return e && std::atoi(e) != 0;
+  }();
+  const unsigned tile_records = 2 * kMomentThreads;  // (fixed: the assignment of records to threads must not depend on the layout)
+  const size_t tile_bytes = static_cast<size_t>(tile_records) * point_step;
+  const bool tma = tma_on && point_step % 4 == 0 && (reinterpret_cast<uintptr_t>(c->blob.ptr) & 15u) == 0 &&
+                   c->V >= 64ull * tile_records && kIngestStages * tile_bytes <= (size_t(96) << 10);
+  if (tma)
+  {
+    const size_t smem = kIngestStages * tile_bytes;
+    if (c->ingest_smem < smem)
+    {
+      NB2_CUDA(cudaFuncSetAttribute(k_ingest_moments_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      c->ingest_smem = smem;
+    }
+    const unsigned long long tiles = c->V / tile_records;
+    const int g = static_cast<int>(std::min<unsigned long long>(std::max<unsigned long long>(tiles, 1ull), static_cast<unsigned long long>(kMomentBlocks)));
+    k_ingest_moments_tma<<<g, kMomentThreads, smem, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz, tile_records,
+                                                                 c->pos.as<float4>(), c->partials.as<MomentPartial>(),
+                                                                 c->counters.as<unsigned>(), c->frame.as<FrameDev>());
+    c->ingest_grid = g;
+  }
+  else
+  {
+    k_ingest_moments<<<grid, kMomentThreads, 0, c->stream>>>(c->blob.as<uint8_t>(), c->V, point_step, off_xyz,
+                                                             c->pos.as<float4>(),
+                                                             c->partials.as<MomentPartial>(), c->counters.as<unsigned>(),
+                                                             c->frame.as<FrameDev>());
+    c->ingest_grid = grid;
+  }
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }

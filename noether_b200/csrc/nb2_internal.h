@@ -216,6 +216,8 @@ struct nb2_context
   // capacities the post-count stage was last sized for (0 = not yet known: the first plan waits for its hit count)
   uint64_t hit_cap = 0;      // hits (triangle x plane)
   uint32_t scratch_hits = 0; // hits of the largest plane, when it exceeds what fits shared memory
+  size_t ingest_smem = 0;  // dynamic shared memory k_ingest_moments_tma was last prepared for
+  int ingest_grid = 0;     // grid of the last ingest pass (its block partials: partials[0 .. grid), total at [grid])
   int link_cfg_threads = 0, link_cfg_ctas = 1;  // launch configuration k_link_planes was last prepared for
   size_t link_cfg_smem = 0;
   bool link_cfg_wide = false;

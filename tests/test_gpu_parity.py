@@ -842,3 +842,20 @@ def test_second_generation_linker_matches_oracle():
                         "-k", "test_slice_ or test_plan_end_to_end or test_cfg2_properties or test_large_plane or test_fuzz_plans"],
                        env=env, capture_output=True, text=True, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_bulk_copy_ingest_variant():
+    """NB2_INGEST_TMA=1 (k_ingest_moments_tma: cp.async.bulk tiles into shared memory, an mbarrier per stage; opt-in because it
+    measured level with the plain kernel) gives the same positions, the same frame within the tolerance of the fp64 tree sums
+    and the same plans: the ingest, PCA and planning tests of this file once more in a process with the variable set"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.environ.get("NB2_INGEST_TMA") == "1":
+        pytest.skip("already inside the bulk-copy run")
+    env = dict(os.environ, NB2_INGEST_TMA="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                        "-k", "test_ingest_ or test_pca_ or test_lattice_ or test_plan_end_to_end or test_cfg2_properties or test_cfg3_full or test_lazy_download"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
