@@ -844,6 +844,9 @@ void nb2_context_destroy(nb2_context* c)
                      &c->stlFlag, &c->stlPrefix, &c->stlKeepPrefix, &c->subBlob[0], &c->subBlob[1], &c->subTri[0], &c->subTri[1], &c->subLevels,
                      &c->subKeys, &c->cluHead, &c->cluNext, &c->cluParent, &c->cluLabel, &c->cluCellSize, &c->subReq, &c->subNodeCnt, &c->subNodeBase, &c->subNodeMask, &c->subFresh, &c->subRank })
     b->release();
+  for (auto& b : c->areaPool)
+    b.release();
+  c->areaPool.clear();
   c->hostSmall.release();
   c->stageRing.release();
   for (auto& e : c->stageEvents)

@@ -286,18 +286,32 @@ void launchAreaSubdivision(nb2_context* c, const sub::Layout& L, float max_area,
   const uint64_t V = c->V, F = c->F;
   cudaStream_t st = c->stream;
   const uint64_t limit = std::min<uint64_t>(max_points ? max_points : ~0ull, (1ull << 31) - 1);
+  // The buffers of the levels come from a pool the context keeps (level i of this call reuses what level i of the last call
+  // allocated), so a second subdivision of a mesh of the same size allocates nothing
   std::vector<AreaLevelBuf> levels;
   struct Cleanup
   {
+    nb2_context* c;
     std::vector<AreaLevelBuf>& v;
     ~Cleanup()
     {
-      for (auto& l : v)
-        l.buf.release();
+      for (size_t i = 0; i < v.size(); ++i)
+      {
+        if (c->areaPool.size() <= i)
+          c->areaPool.resize(i + 1);
+        std::swap(c->areaPool[i], v[i].buf);
+      }
     }
-  } cleanup{ levels };
+  } cleanup{ c, levels };
+  auto newLevel = [&]() -> AreaLevelBuf& {
+    levels.emplace_back();
+    const size_t i = levels.size() - 1;
+    if (i < c->areaPool.size())
+      std::swap(c->areaPool[i], levels[i].buf);
+    return levels[i];
+  };
   levels.reserve(64);
-  levels.emplace_back();
+  newLevel();
   levels[0].alloc(F);
   if (F)
   {
@@ -335,7 +349,7 @@ void launchAreaSubdivision(nb2_context* c, const sub::Layout& L, float max_area,
       std::swap(c->subFresh, bigger);
       bigger.release();
     }
-    levels.emplace_back();
+    newLevel();
     AreaLevelBuf& parent = levels[levels.size() - 2];
     AreaLevelBuf& child = levels.back();
     child.alloc(3 * splits);

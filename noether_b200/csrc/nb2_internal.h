@@ -192,6 +192,7 @@ struct nb2_context
   bool has_normals = false;
   bool tri_checked = false;  // vertex indices of the resident triangles are known to be < V
   nb2::DevBuf blob;      // staging copy of the interleaved cloud
+  std::vector<nb2::DevBuf> areaPool;  // FaceSubdivisionByArea: the per-level buffers, kept between calls
   nb2::DevBuf blobSpare, triSpare;  // nb2_mesh_upload_stream stages into these; they are swapped in when the mesh is accepted
   nb2::PinnedBuf stageRing;         // pinned slots the host cores fill on the way to the device (api.cu, stageToDevice)
   std::vector<cudaEvent_t> stageEvents;  // one per slot: its last copy has left
