@@ -325,6 +325,19 @@ def main():
             "e2e": {"value": value, "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
+        # next to it, a whole plan actually measured on every host core: the same algorithm with the cells binned by lattice
+        # interval and the lattice cut into slabs over forked workers (tools/cpu_optimised.py) — not what the reference does
+        # (it is single-threaded and visits every cell per plane), but the fairer figure to hold a GPU number against
+        if args.workload in ("cfg2", "cfg3"):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cpu_optimised.py"), args.workload],
+                                   capture_output=True, text=True, timeout=180)
+                o = json.loads(r.stdout.strip().splitlines()[-1])
+                line["cpu_baseline_optimised"] = {
+                    "value": o["tri_per_s"], "unit": "triangles/s", "cores": o["workers"], "kind": "port",
+                    "sample": f"whole plan measured: prologue + all {o['planes']} lattice planes in {o['t_plan_s']:.2f} s"}
+            except Exception as e:
+                line["cpu_baseline_optimised"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         emit(line)
         return
 
