@@ -477,13 +477,28 @@ __global__ void __launch_bounds__(256) k_classify(const float4* __restrict__ pos
        i += static_cast<long long>(stride))
     planeCnt[i] = 0u;
   const double inv_spacing = 1.0 / L.spacing;
+  const double start_norm = fabs(L.start[0]) + fabs(L.start[1]) + fabs(L.start[2]);
+  // (the estimate takes the lattice normal for a unit vector; an explicit lattice may carry another: exact path then)
+  const bool unit_normal = fabs(L.n[0] * L.n[0] + L.n[1] * L.n[1] + L.n[2] * L.n[2] - 1.0) * static_cast<double>(P > 0 ? P : 1) < 2.5e-7;
   for (unsigned long long v = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V; v += stride)
   {
     const float4 p = __ldg(pos + v);
     // estimate
     const double d = L.n[0] * (static_cast<double>(p.x) - L.start[0]) + L.n[1] * (static_cast<double>(p.y) - L.start[1]) +
                      L.n[2] * (static_cast<double>(p.z) - L.start[2]);
-    double q = floor(d * inv_spacing);  // an estimate only: the loops below settle the exact index
+    const double t = d * inv_spacing;
+    double q = floor(t);  // an estimate only: the loops below settle the exact index
+    // The estimate and the reference's expression (the scalar against the origin of plane k, start + k * spacing * n) differ
+    // by rounding only: a few 2^-53 of (|p| + |start|) / spacing in units of the plane index (and k * spacing * (n.n - 1)).
+    // A vertex whose t lies at least `margin` away from both neighbouring integers is therefore settled by the estimate;
+    // the two exact evaluations below — most of this kernel's fp64 work — are needed by about two vertices in a million.
+    const double scale = (fabs(static_cast<double>(p.x)) + fabs(static_cast<double>(p.y)) + fabs(static_cast<double>(p.z)) + start_norm) * inv_spacing;
+    const double margin = 1e-6;
+    if (unit_normal && scale < 1e8 && q >= 0.0 && q < static_cast<double>(P - 1) && t - q > margin && (q + 1.0) - t > margin)
+    {
+      vertK[v] = static_cast<int>(q);
+      continue;
+    }
     q = fmin(fmax(q, -1.0), static_cast<double>(P - 1));
     long long k = static_cast<long long>(q);
     // exact fix-up against the reference's own expression
