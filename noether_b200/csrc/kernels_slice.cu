@@ -1803,6 +1803,10 @@ __global__ void __launch_bounds__(2 * kLinkThreads, 1) k_link_planes_wide(LinkPa
 constexpr unsigned kWpChunk = 1024u;  // waypoints per block and chunk (four per thread)
 
 // (five CTAs per SM: 48 registers; measured 119 us against 125 / 131 / 143 us at four / six / eight on cfg3)
+// kRec24: the cloud lies in HBM as 24-byte {x y z nx ny nz} records (what the staged upload leaves there): position and
+// normal of a vertex then come out of one record — three 8-byte loads, one or two sectors — instead of a 16-byte position
+// and three 4-byte normal components from two arrays (nrmBase points at the record's normal, 12 bytes behind its x)
+template <bool kRec24>
 __global__ void __launch_bounds__(256, 5)
     k_waypoints(const uint32_t* __restrict__ tri, const float4* __restrict__ pos, const uint8_t* __restrict__ nrmBase,
                 unsigned nrmStride, const FrameDev* __restrict__ frame, const unsigned* __restrict__ sizes,
@@ -1839,13 +1843,29 @@ __global__ void __launch_bounds__(256, 5)
         const uint32_t ids[3] = { __ldg(tri + 3ull * t), __ldg(tri + 3ull * t + 1), __ldg(tri + 3ull * t + 2) };
         // positions and normals of all three vertices are requested together: the two the cut edge needs are only
         // known after the plane scalars, and waiting for them would put a fourth dependent gather on every waypoint
-        const float4 p[3] = { __ldg(pos + ids[0]), __ldg(pos + ids[1]), __ldg(pos + ids[2]) };
-        float4 nv[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
+        float4 p[3], nv[3];
+        if constexpr (kRec24)
         {
-          const float* q = reinterpret_cast<const float*>(nrmBase + static_cast<size_t>(ids[j]) * nrmStride);
-          nv[j] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+          {
+            const float2* q = reinterpret_cast<const float2*>(nrmBase - 12 + static_cast<size_t>(ids[j]) * 24u);
+            const float2 a = __ldg(q), b = __ldg(q + 1), c2 = __ldg(q + 2);
+            p[j] = make_float4(a.x, a.y, b.x, 0.f);
+            nv[j] = make_float4(b.y, c2.x, c2.y, 0.f);
+          }
+        }
+        else
+        {
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            p[j] = __ldg(pos + ids[j]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+          {
+            const float* q = reinterpret_cast<const float*>(nrmBase + static_cast<size_t>(ids[j]) * nrmStride);
+            nv[j] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.f);
+          }
         }
         double s[3];
 #pragma unroll
@@ -2089,12 +2109,21 @@ void launchWaypoints(nb2_context* c, uint64_t w_cap, int emit_edges)
   unsigned gx = c->grid_planes ? c->grid_planes : 1024u, gy = (2u * c->grid_nmax + kWpChunk - 1u) / kWpChunk;
   gx = std::min(gx, 1u << 20);
   gy = std::max(1u, std::min(gy, 4096u));
-  k_waypoints<<<dim3(gx, gy), 256, 0, c->stream>>>(
-      c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm_base, c->nrm_stride, c->frame.as<FrameDev>(),
-      c->counters.as<unsigned>() + 4, c->counters.as<unsigned>() + 13, c->planeOff.as<unsigned>(),
-      c->planeMeta.as<unsigned>(), c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
-      c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(), c->outEdge.as<uint32_t>() + w_cap,
-      c->outSegLen.as<unsigned>(), emit_edges);
+  // the cloud as 24-byte {xyz, normal} records whose normals are the ones in use (not replaced by computed / set normals)
+  const bool rec24 = c->rec_step == 24 && c->rec_off_xyz == 0 && c->rec_off_nrm == 12 && c->nrm_stride == 24 &&
+                     c->nrm_base == c->blob.as<uint8_t>() + 12 && (reinterpret_cast<uintptr_t>(c->blob.ptr) & 7u) == 0;
+  auto launch = [&](auto kernel) {
+    kernel<<<dim3(gx, gy), 256, 0, c->stream>>>(
+        c->tri.as<uint32_t>(), c->pos.as<float4>(), c->nrm_base, c->nrm_stride, c->frame.as<FrameDev>(),
+        c->counters.as<unsigned>() + 4, c->counters.as<unsigned>() + 13, c->planeOff.as<unsigned>(),
+        c->planeMeta.as<unsigned>(), c->planePrefix.as<uint2>(), c->wpTag.as<unsigned>(), c->segLen.as<unsigned>(),
+        c->outPos.as<float>(), c->outNrm.as<float>(), c->outEdge.as<uint32_t>(), c->outEdge.as<uint32_t>() + w_cap,
+        c->outSegLen.as<unsigned>(), emit_edges);
+  };
+  if (rec24)
+    launch(k_waypoints<true>);
+  else
+    launch(k_waypoints<false>);
   NB2_CUDA(cudaGetLastError());
   ++c->launches;
 }
