@@ -176,4 +176,35 @@ NB2_DEV CutPoint interpolateCut(int index, int which, const uint32_t ids[3], con
   return c;
 }
 
+/** Both endpoints of the contour line of case `index` (1 .. 6), positions only — what k_emit_hits needs of every hit.
+ *  The same arithmetic as interpolateCut(index, 0 / 1, ...), arranged around the triangle's LONE vertex (the one on its
+ *  own side of the plane): both cut edges start there, so the three vertices are rotated once (lone vertex first) and
+ *  everything after is fixed positions instead of a select chain per operand.  In vtkTriangle's tables, after that
+ *  rotation, a case with one vertex inside reads {edge 0, edge 2} and a case with two inside {edge 2, edge 0}; an edge is
+ *  interpolated from its vertex outside (scalar < 0) to its vertex inside, t = (0 - s_out) / (s_in - s_out)
+ *  (-(a - b) and b - a are the same double, so the sign flip of cutParam needs no restating). */
+NB2_DEV void cutBothPositions(int index, const float4 p[3], const double s[3], float c0[3], float c1[3])
+{
+  const bool single = index == 1 || index == 2 || index == 4;  // one vertex inside: it is the lone one
+  const int hot = single ? index : (7 ^ index);                 // one-hot position of the lone vertex
+  const int l = hot >> 1;                                       // 1, 2, 4 -> 0, 1, 2
+  const int l1 = l == 2 ? 0 : l + 1, l2 = l == 0 ? 2 : l - 1;
+  const float4 q0 = pick3(p, l), q1 = pick3(p, l1), q2 = pick3(p, l2);
+  const double s0 = pick3(s, l), s1 = pick3(s, l1), s2 = pick3(s, l2);
+  // line end 0 / 1: single -> edges (q0,q1) / (q2,q0), from q1 / q2 towards q0;  double -> edges (q2,q0) / (q0,q1), from q0
+  const float4 a0 = single ? q1 : q0, b0 = single ? q0 : q2;
+  const float4 a1 = single ? q2 : q0, b1 = single ? q0 : q1;
+  const double lo0 = single ? s1 : s0, hi0 = single ? s0 : s2;
+  const double lo1 = single ? s2 : s0, hi1 = single ? s0 : s1;
+  const double d0 = dsub(hi0, lo0), d1 = dsub(hi1, lo1);
+  const double t0 = (d0 == 0.0) ? 0.0 : ddiv(dsub(0.0, lo0), d0);
+  const double t1 = (d1 == 0.0) ? 0.0 : ddiv(dsub(0.0, lo1), d1);
+  c0[0] = lerpPosition(a0.x, b0.x, t0);
+  c0[1] = lerpPosition(a0.y, b0.y, t0);
+  c0[2] = lerpPosition(a0.z, b0.z, t0);
+  c1[0] = lerpPosition(a1.x, b1.x, t1);
+  c1[1] = lerpPosition(a1.y, b1.y, t1);
+  c1[2] = lerpPosition(a1.z, b1.z, t1);
+}
+
 }  // namespace nb2

@@ -404,11 +404,10 @@ __global__ void __launch_bounds__(kEmitThreads, 4)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
           s[j] = planeScalar(L, org, p[j].x, p[j].y, p[j].z);
-        const int index = contourCase(s);
-        const CutPoint c0 = interpolateCut(index, 0, ids, p, s, nullptr);
-        const CutPoint c1 = interpolateCut(index, 1, ids, p, s, nullptr);
-        rec[2ull * slot] = make_float4(c0.x, c0.y, c0.z, __uint_as_float(2u * t));
-        rec[2ull * slot + 1] = make_float4(c1.x, c1.y, c1.z, __uint_as_float(2u * t + 1u));
+        float c0[3], c1[3];
+        cutBothPositions(contourCase(s), p, s, c0, c1);
+        rec[2ull * slot] = make_float4(c0[0], c0[1], c0[2], __uint_as_float(2u * t));
+        rec[2ull * slot + 1] = make_float4(c1[0], c1[1], c1[2], __uint_as_float(2u * t + 1u));
       }
     }
   }

@@ -287,6 +287,44 @@ void emu_export(int64_t* path_plane, uint32_t* path_segments, uint32_t* seg_len,
 }
 
 uint64_t emu_work_bytes(unsigned n) { return workBytes(n); }
+
+/** cutBothPositions (what k_emit_hits contours with) against interpolateCut (the statement of vtkTriangle::Contour the
+ *  waypoint pass and this replay use), bit for bit, on `n` random triangles per contour case incl. vertices exactly in the
+ *  plane; returns the number of mismatches */
+uint64_t emu_check_cut_both(unsigned seed, unsigned n)
+{
+  uint64_t bad = 0;
+  uint64_t x = 0x9E3779B97F4A7C15ull * (seed + 1);
+  auto rnd = [&]() {
+    x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+    return static_cast<double>(x >> 11) / 9007199254740992.0;  // [0, 1)
+  };
+  const uint32_t ids[3] = { 10, 20, 30 };
+  for (unsigned it = 0; it < n; ++it)
+    for (int index = 1; index <= 6; ++index)
+    {
+      float4 p[3];
+      double s[3];
+      for (int v = 0; v < 3; ++v)
+      {
+        p[v] = make_float4(static_cast<float>(rnd() * 20 - 10), static_cast<float>(rnd() * 20 - 10), static_cast<float>(rnd() * 20 - 10), 0.f);
+        const bool inside = (index >> v) & 1;
+        double mag = rnd() < 0.15 ? 0.0 : rnd() * (rnd() < 0.3 ? 1e-9 : 3.0);
+        if (!inside && mag == 0.0)
+          mag = 1e-300;  // outside means strictly negative
+        s[v] = inside ? mag : -mag;
+      }
+      if (contourCase(s) != index)
+        continue;
+      float c0[3], c1[3];
+      cutBothPositions(index, p, s, c0, c1);
+      const CutPoint r0 = interpolateCut(index, 0, ids, p, s, nullptr), r1 = interpolateCut(index, 1, ids, p, s, nullptr);
+      const float ref[6] = { r0.x, r0.y, r0.z, r1.x, r1.y, r1.z }, got[6] = { c0[0], c0[1], c0[2], c1[0], c1[1], c1[2] };
+      if (std::memcmp(ref, got, sizeof(ref)) != 0)
+        ++bad;
+    }
+  return bad;
+}
 unsigned emu_max_rounds() { return g.max_rounds; }
 uint64_t emu_stragglers() { return g.stragglers; }
 void emu_declined_misc(uint32_t* out) { std::memcpy(out, g.declined_misc.data(), 4 * g.declined_misc.size()); }

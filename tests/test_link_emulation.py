@@ -208,3 +208,12 @@ def test_work_area_fits_two_planes_per_sm(emu):
     """cfg3's planes (about 4000 cut lines) must fit two to an SM (227 KB of shared memory per SM, 1 KB reserved per CTA)"""
     assert emu.emu_work_bytes(4200) <= 113 * 1024
     assert emu.emu_work_bytes(1300) <= 37 * 1024    # cfg2's planes: six to an SM
+
+
+def test_contouring_of_both_line_ends_equals_the_one_at_a_time_statement(emu):
+    """k_emit_hits contours both ends of a cut line around the triangle's lone vertex (cutBothPositions); the waypoint pass
+    and the oracle-checked replay use interpolateCut, the line-by-line statement of vtkTriangle::Contour: same bits"""
+    emu.emu_check_cut_both.restype = C.c_uint64
+    emu.emu_check_cut_both.argtypes = [C.c_uint, C.c_uint]
+    for seed in range(4):
+        assert emu.emu_check_cut_both(seed, 50000) == 0
