@@ -151,7 +151,9 @@ def ncu_traffic(workload: str, stage: str):
     if kernel is None or not os.path.exists(path):
         return None
     with open(path) as f:
-        entry = json.load(f).get(kernel)
+        table = json.load(f)
+    # (template instances and kernel variants carry suffixes: k_count_hits<0>, k_link_planes_wide, k_waypoints<1>)
+    entry = table.get(kernel) or next((v for k, v in table.items() if k.startswith(kernel)), None)
     return entry["dram_bytes_per_launch"] if entry else None
 
 
