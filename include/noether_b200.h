@@ -75,8 +75,9 @@ typedef struct nb2_mesh_view
   uint64_t n_triangles;
 } nb2_mesh_view;
 /* flags: only positions and normals of this cloud will be used on the device (planning, normals, clustering — not the
- * face subdivisions, which copy whole records): a host cloud is compacted to {x y z [nx ny nz]} records on its way through
- * the pinned staging ring, so a 48-byte PointNormal record costs 24 bytes of PCIe and HBM traffic.
+ * face subdivisions, which copy whole records): a pageable host cloud is compacted to {x y z [nx ny nz]} records on its way
+ * through the pinned staging ring, so a 48-byte PointNormal record costs 24 bytes of PCIe and HBM traffic (a pinned cloud
+ * is copied as it is: the copy engine needs no host core for it).
  * nb2_mesh_record_layout reports the resident layout. */
 #define NB2_MESH_GEOMETRY_ONLY 1u
 
