@@ -192,3 +192,58 @@ def test_gpu_matches_the_oracle(orc, golden_dir):
     out = nb.NormalEstimationPCLMeshModifier(0.0, context=ctx).modify(blob)[0]
     assert np.isnan(out.normals()).all()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_random_clouds_against_the_oracle(orc):
+    """thirty random clouds — wavy sheets with noise, scattered points, coincident points, points in a line, isolated
+    points, view points on either side — with random radii: neighbour structure (NaN where fewer than three), angle within the
+    gap-scaled tolerance, curvature"""
+    import noether_b200 as nb
+    from noether_b200 import meshes
+    ctx = nb.Context(0)
+    for seed in range(30):
+        rng = np.random.default_rng(4100 + seed)
+        kind = int(rng.integers(4))
+        if kind == 0:
+            xyz, tri = meshes.wavy(int(rng.integers(20, 70)), int(rng.integers(20, 70)), amp=float(rng.uniform(0, 0.05)))
+            xyz = (xyz + rng.normal(0, 1e-4, xyz.shape)).astype(np.float32)
+            radius = float(rng.uniform(0.03, 0.09))
+        elif kind == 1:
+            xyz = rng.uniform(-1, 1, (int(rng.integers(300, 2500)), 3)).astype(np.float32)
+            radius = float(rng.uniform(0.15, 0.4))
+        elif kind == 2:   # duplicates and a line of points
+            base = rng.uniform(-1, 1, (600, 3)).astype(np.float32)
+            line = np.stack([np.linspace(-1, 1, 200), np.zeros(200), np.zeros(200)], 1).astype(np.float32) + 3.0
+            xyz = np.concatenate([base, base[:150], line])
+            radius = 0.3
+        else:             # a few isolated points far away
+            xyz = np.concatenate([rng.uniform(-1, 1, (800, 3)), rng.uniform(50, 60, (5, 3))]).astype(np.float32)
+            radius = 0.35
+        tri = np.array([[0, 1, 2]], np.uint32)
+        vp = tuple(float(v) for v in rng.uniform(-5, 5, 3))
+        ctx.upload(meshes.pack_blob(xyz, None, tri, "PointXYZ"), force=True)
+        ng, cg = ctx.normal_estimation_pcl(xyz.shape[0], radius, vp)
+        no, co, ko = orc.normal_estimation_pcl(xyz, radius, vp)
+        what = f"seed {seed} kind {kind}"
+        assert np.isnan(ng[ko < 3]).all() and np.isnan(no[ko < 3]).all(), what
+        ok, ref, gap = well_conditioned(xyz, radius)
+        assert not np.isnan(ng[ok]).any() and not np.isnan(no[ok]).any(), what
+        if ok.any():
+            a = np.minimum(angles(ng[ok], no[ok]), angles(-ng[ok], no[ok]))
+            # pcl::eigen33 solves the cubic with float trigonometry: where two eigenvalues are close (volumetric clouds) the
+            # reference itself is only good to about 1e-3 rad against the exact eigenvector, and two libms cannot agree
+            # better than that.  So: the gap-scaled tolerance, or a few times the oracle's own worst error on this cloud, whichever
+            # is larger.
+            own = np.minimum(angles(no[ok], ref[ok].astype(np.float32)), angles(-no[ok], ref[ok].astype(np.float32)))
+            allowed = np.maximum(tolerance(gap[ok]), 4.0 * own.max() + 1e-6)
+            assert (a <= allowed).all(), f"{what}: {a.max():.3e} rad"
+            if kind == 0:   # surfaces: the stated tolerance as it is
+                assert (a <= tolerance(gap[ok])).all(), f"{what}: {a.max():.3e} rad on a surface"
+            # the flip towards the view point agrees except where (vp - p) . n is within float noise of zero
+            w = np.asarray(vp, np.float64) - xyz[ok].astype(np.float64)
+            cosv = np.abs((w * no[ok]).sum(1)) / np.maximum(np.linalg.norm(w, axis=1), 1e-30)
+            clear = cosv > 1e-4
+            assert (np.sign((ng[ok][clear] * no[ok][clear]).sum(1)) > 0).all(), what
+            assert np.allclose(cg[ok], co[ok], rtol=2e-3, atol=2e-6), what
+    ctx.close()
