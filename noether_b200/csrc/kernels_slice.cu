@@ -1503,10 +1503,9 @@ __device__ __forceinline__ bool linkPlane2(const LinkParams& P, uint8_t* smem, l
   __syncthreads();
   clk.lap(1);
   // Claim rounds with plain stores; the first claim rode along with the hashing.  What the plain rounds leave unsettled
-  // finishes with compare-and-swap (phaseStragglers).  Measured on cfg3 (profiles/r02_summary.md): an ATOMS.CAS costs
-  // the SM tens of cycles per warp INSTRUCTION however few lanes are active, so compare-and-swap loops must stay out of
-  // code that every endpoint runs (a variant that probed with compare-and-swap inside an unrolled settle phase took 0.45
-  // - 0.8 ms); one plain round plus stragglers (0.226 ms) and many plain rounds (0.241 ms) are about level.
+  // finishes with compare-and-swap (phaseStragglers).  Measured on cfg3 (profiles/r02_summary.md): one plain round plus
+  // stragglers (0.226 ms) and many plain rounds (0.241 ms) are about level; a variant that probed with compare-and-swap
+  // inside an unrolled settle phase took 0.45 - 0.8 ms (the probe loop replicated per endpoint of the batch, few lanes each).
   bool left = true;
   for (unsigned round = 0; round < P.plainRounds && left; ++round)
   {
