@@ -12,8 +12,8 @@
 // the position and the interpolated normal.
 //
 // How (differences from the first-generation fast path; measurements in profiles/r02_summary.md):
-//   * NO SHARED-MEMORY ATOMICS.  On this part a warp-wide ATOMS costs tens of cycles per lane (the first generation spent
-//     most of its time in three of them per endpoint).  Cut points are merged through a hash whose slots are claimed with
+//   * NO SHARED-MEMORY ATOMICS on the common path (the first generation issues three per endpoint; whether they are what
+//     it waits for was not confirmed: profiles/r02_summary.md).  Cut points are merged through a hash whose slots are claimed with
 //     plain stores in rounds: every unsettled endpoint writes {fingerprint, endpoint} into its slot if the slot looks
 //     empty; after a barrier it reads the slot back — its own value: it holds the point; the same 32-bit hash: the holder
 //     is its twin; something else: next slot, next round.  Whichever store wins, everybody sees the same winner.
