@@ -117,3 +117,22 @@ def test_bench_reference_arm_runs_without_a_gpu():
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "triangles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the whole plan measured on every host core rides along (the fairer figure next to the single-threaded port)
+    opt = line["cpu_baseline_optimised"]
+    assert opt["kind"] == "port" and opt["cores"] >= 1 and opt["value"] > 0 and "whole plan measured" in opt["sample"]
+
+
+def test_bench_reference_arm_of_the_normals_workload():
+    """`bench.py --impl reference --workload cfg4` (NormalsFromMeshFaces + PCA frame through the oracle, on a tenth of the
+    mesh): the same contract keys, no device"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg4", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600, check=True)
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "triangles/s" and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "cfg4" in line["config"]["workload"]
