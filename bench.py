@@ -116,6 +116,20 @@ def build_workload(name: str):
     return xyz, tri, spacing, desc
 
 
+def workload_config(name: str, desc: str, world: int, V: int, F: int) -> dict:
+    """`config` of the bench line: the workload and how each arm measures it.  Both arms print the very same object, so that a
+    comparison of the two lines sees one configuration; what a run found out (planes, waypoints, wall times) is in `result`."""
+    return {
+        "workload": f"{name}: {desc}",
+        "parallelism": f"plane slabs x{world}" if world > 1 else "single GPU",
+        "l2": ("GPU arm: flushed between timed iterations (256 MB write outside the timed intervals); inputs are %d MB, resident as "
+               "24-byte {xyz, normal} cloud records (what this library's upload leaves in HBM) and uint32 x 3 triangles; reference arm: "
+               "host memory" % ((24 * V + 12 * F) // 2**20)),
+        "timing": ("GPU arm: CUDA events on the library stream (entry of nb2_plan_mesh .. behind the plan's last kernel), max over "
+                   "ranks; reference arm: wall clock of a bounded plane sample, extrapolated linearly to the full lattice"),
+    }
+
+
 def cpu_reference_sample(xyz, nrm, tri, spacing, n_planes: int):
     """The reference's algorithm (oracle, faithful mode, every vertex + every cell per plane, one thread) on a bounded
     sample: the plane-independent prologue plus `n_planes` evenly spaced lattice planes, extrapolated linearly in the
@@ -317,7 +331,7 @@ def main():
             "impl": "reference", "metric": "triangles sliced/sec", "value": value, "unit": "triangles/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_plan,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "timing": "wall clock; extrapolated to the full lattice"},
+            "config": workload_config(args.workload, desc, args.gpus, V, F),
             "cpu_baseline": {"value": value, "unit": "triangles/s", "cores": 1, "kind": "port",
                              "sample": (f"plane-independent prologue + {runs[0]['planes_sampled']} of {runs[0]['planes']} "
                                         "lattice planes per step (every vertex and every cell visited per plane, as "
@@ -597,14 +611,10 @@ def main():
         "metric": "triangles sliced/sec", "value": F / (ms_per_step / 1e3), "unit": "triangles/s",
         "n_gpus": info.world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "planes": P_planes, "tool_paths": int(n_paths),
-                   "segments": int(n_segments), "waypoints": int(n_waypoints),
-                   "parallelism": f"plane slabs x{info.world}" if info.world > 1 else "single GPU",
-                   "l2": "flushed between timed iterations (256 MB write outside the timed intervals); inputs are %d MB" % ((blob_dev.data.size + tri.size * 4) // 2**20),
-                   "resident_layout": "cloud as 24-byte {xyz, normal} records (what this library's upload leaves in HBM), triangles uint32 x 3",
-                   "timing": "CUDA events on the library stream (entry of nb2_plan_mesh .. behind the plan's last kernel), max over ranks; "
-                             "events recorded from this interpreter around the call %.3f ms/step, wall clock %.3f ms/step"
-                             % (bracket_ms / args.steps, wall_ms / args.steps)},
+        "config": workload_config(args.workload, desc, info.world, V, F),
+        "result": {"planes": P_planes, "tool_paths": int(n_paths), "segments": int(n_segments), "waypoints": int(n_waypoints),
+                   "events_recorded_from_the_interpreter_ms_per_step": bracket_ms / args.steps,
+                   "wall_clock_ms_per_step": wall_ms / args.steps},
         "clocks": clocks,
         "e2e": e2e,
         "e2e_compact": e2e_compact,
